@@ -1,0 +1,403 @@
+"""CUDA emitter: symbolic model description -> inlined FP64 ``__host__ __device__`` functions.
+
+This is the B200 counterpart of the reference's C++ code generator
+(reference python/sdist/amici/exporters/sundials/de_export.py:267-508 writes one
+``<fn>_<model>.cpp`` per model function with the signatures of
+exporters/sundials/cxx_functions.py:101-418).  The reference back end cannot be
+imported in this image (libsbml/toposort are missing), so the emitter starts from
+a small SymPy model description (``ModelSpec``) instead of a ``DEModel``; the set
+of functions it writes is the one the batched BDF engine consumes.
+
+Differences from the reference's generated code that are deliberate:
+
+* One header per model holding a traits struct with ``static`` inline functions;
+  no sparse-matrix objects at run time (the CSC pattern is burnt into straight
+  line code: ``jac`` writes the non-zeros, ``jac_mul_add``/``jac_to_A`` are
+  unrolled over the static pattern).
+* ``sxdot`` pieces are *column functions*: ``dxdotdp(ip, ...)`` returns the total
+  derivative column for one parameter.  Instead of the reference's
+  ``switch(ip)`` (dydp.cpp, sx0.cpp ...) they are select chains
+  ``(ip == 3) ? e3 : (ip == 7) ? e7 : 0`` so that the lanes of a warp, each
+  holding a different parameter column, do not diverge.
+* ``w`` expressions are inlined; only spline outputs stay opaque (``spl[i]``,
+  ``sspl[i]`` = d spl_i / d p_ip for the calling lane's parameter).
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Sequence
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+
+@dataclasses.dataclass
+class Spline:
+    """Cubic Hermite spline in time (reference src/splinefunctions.cpp, HermiteSpline).
+
+    Supported configuration = what the reference's shipped models use
+    (models/model_jakstat_adjoint_py/create_splines.cpp): non-equidistant nodes,
+    node derivatives by finite differences, zero-derivative boundary conditions,
+    constant extrapolation, optional logarithmic parametrisation.
+    """
+    name: str
+    nodes: Sequence[float]
+    values: Sequence[sp.Expr]
+    logarithmic: bool = True
+
+
+@dataclasses.dataclass
+class Observable:
+    name: str
+    formula: sp.Expr
+    sigma: sp.Expr = sp.Float(1.0)
+
+
+@dataclasses.dataclass
+class Event:
+    """AMICI event: fires when ``root`` crosses zero from below (rising)."""
+    root: sp.Expr                       # trigger function g(t, x, p, k)
+    bolus: dict | None = None           # {state symbol: new value expression} (assignment x <- expr)
+    z: Sequence[sp.Expr] = ()           # event observables recorded at this event
+    time_trigger: sp.Expr | None = None  # explicit trigger time if root == t - time_trigger (pure time event)
+    initial_value: bool = True
+
+
+@dataclasses.dataclass
+class ModelSpec:
+    name: str
+    states: Sequence[sp.Symbol]
+    params: Sequence[sp.Symbol]
+    fixed: Sequence[sp.Symbol]
+    xdot: Sequence[sp.Expr]
+    x0: Sequence[sp.Expr]
+    observables: Sequence[Observable]
+    p_nominal: Sequence[float]
+    k_nominal: Sequence[float]
+    splines: Sequence[Spline] = ()
+    events: Sequence[Event] = ()
+    heavisides: Sequence[sp.Symbol] = ()   # h symbols appearing in xdot (value 0/1 state)
+    doc: str = ""
+
+
+t_sym = sp.Symbol("t", real=True)
+
+
+class _Printer(C99CodePrinter):
+    """C printer: small integer powers -> products, everything double."""
+
+    def _print_Pow(self, expr):
+        b, e = expr.as_base_exp()
+        if e.is_Integer and 2 <= int(e) <= 4:
+            s = self._print(b)
+            if not (b.is_Symbol or b.is_Number):
+                s = f"({s})"
+            return "(" + "*".join([s] * int(e)) + ")"
+        if e.is_Integer and -4 <= int(e) <= -1:
+            s = self._print(b)
+            if not (b.is_Symbol or b.is_Number):
+                s = f"({s})"
+            return "(1.0/(" + "*".join([s] * (-int(e))) + "))"
+        return super()._print_Pow(expr)
+
+    def _print_Rational(self, expr):
+        return f"({float(expr.p)!r}/{float(expr.q)!r})"
+
+    def _print_Integer(self, expr):
+        return f"{float(int(expr))!r}"
+
+    def _print_Heaviside(self, expr):
+        return f"((({self._print(expr.args[0])}) > 0.0) ? 1.0 : 0.0)"
+
+
+_printer = _Printer()
+
+
+def _c(e) -> str:
+    return _printer.doprint(sp.sympify(e))
+
+
+class _FnWriter:
+    """Writes one function body: CSE over all outputs, then assignments."""
+
+    def __init__(self, subs: dict):
+        self.subs = subs  # symbol -> C lvalue text
+
+    def body(self, assigns: list[tuple[str, sp.Expr]], indent="        ") -> str:
+        if not assigns:
+            return ""
+        exprs = [sp.sympify(e) for _, e in assigns]
+        repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("c_"), optimizations="basic")
+        lines = []
+        for s, e in repl:
+            lines.append(f"{indent}const double {s} = {self._pr(e)};")
+        for (lhs, _), e in zip(assigns, red):
+            lines.append(f"{indent}{lhs} = {self._pr(e)};")
+        return "\n".join(lines) + "\n"
+
+    def _pr(self, e) -> str:
+        e = sp.sympify(e)
+        return _c(e.xreplace(self.subs))
+
+
+def _select_chain(ip_var: str, cases: list[tuple[int, str]]) -> str:
+    """(ip==a)? ea : (ip==b)? eb : 0.0"""
+    out = "0.0"
+    for ip, txt in reversed(cases):
+        out = f"({ip_var} == {ip}) ? ({txt}) : {out}"
+    return out
+
+
+def emit_model(spec: ModelSpec) -> str:
+    nx, npar, nk, ny = len(spec.states), len(spec.params), len(spec.fixed), len(spec.observables)
+    nspl, ne = len(spec.splines), len(spec.events)
+    spl_syms = [sp.Symbol(f"spl_{s.name}", real=True) for s in spec.splines]
+    sspl_syms = [sp.Symbol(f"sspl_{s.name}", real=True) for s in spec.splines]
+    spl_map = {sp.Symbol(s.name, real=True): spl_syms[i] for i, s in enumerate(spec.splines)}
+    spl_map.update({sp.Symbol(s.name): spl_syms[i] for i, s in enumerate(spec.splines)})
+    h_syms = list(spec.heavisides)
+
+    subs = {}
+    for i, s in enumerate(spec.states):
+        subs[s] = sp.Symbol(f"x[{i}]")
+    for i, s in enumerate(spec.params):
+        subs[s] = sp.Symbol(f"p[{i}]")
+    for i, s in enumerate(spec.fixed):
+        subs[s] = sp.Symbol(f"k[{i}]")
+    for i, s in enumerate(spl_syms):
+        subs[s] = sp.Symbol(f"spl[{i}]")
+    for i, s in enumerate(sspl_syms):
+        subs[s] = sp.Symbol(f"sspl[{i}]")
+    for i, s in enumerate(h_syms):
+        subs[s] = sp.Symbol(f"h[{i}]")
+    y_syms = [sp.Symbol(f"y_{o.name}", real=True) for o in spec.observables]
+    sig_syms = [sp.Symbol(f"sigma_{o.name}", positive=True) for o in spec.observables]
+    my_syms = [sp.Symbol(f"my_{o.name}", real=True) for o in spec.observables]
+    for i in range(ny):
+        subs[y_syms[i]] = sp.Symbol(f"y[{i}]")
+        subs[sig_syms[i]] = sp.Symbol(f"sigmay[{i}]")
+        subs[my_syms[i]] = sp.Symbol(f"my[{i}]")
+    sx_syms = [sp.Symbol(f"sx_{i}", real=True) for i in range(nx)]
+    for i in range(nx):
+        subs[sx_syms[i]] = sp.Symbol(f"sx[{i}]")
+    W = _FnWriter(subs)
+
+    xdot = [sp.sympify(e).xreplace(spl_map) for e in spec.xdot]
+    x0 = [sp.sympify(e) for e in spec.x0]
+    yexpr = [sp.sympify(o.formula).xreplace(spl_map) for o in spec.observables]
+    sigexpr = [sp.sympify(o.sigma) for o in spec.observables]
+
+    # ---- Jacobian (static CSC pattern, column major like the reference's dxdotdx) ----
+    Jfull = [[sp.diff(xdot[r], spec.states[c]) for c in range(nx)] for r in range(nx)]
+    colptr, rowval, jvals = [0], [], []
+    for c in range(nx):
+        for r in range(nx):
+            if Jfull[r][c] != 0:
+                rowval.append(r)
+                jvals.append(Jfull[r][c])
+        colptr.append(len(rowval))
+    nnz = len(rowval)
+
+    # ---- total parameter derivative columns ----
+    def total_dp(expr, ip):
+        e = sp.diff(expr, spec.params[ip])
+        for i, s in enumerate(spl_syms):
+            # d spl_i / d p_ip is supplied at run time (sspl[i]) for the lane's own parameter
+            if spec.splines[i] and any(sp.diff(v, spec.params[ip]) != 0 for v in spec.splines[i].values):
+                e = e + sp.diff(expr, s) * sspl_syms[i]
+        return sp.simplify(e) if e != 0 else e
+
+    out = []
+    A = out.append
+    guard = f"AMICI_B200_MODEL_{spec.name.upper()}_CUH"
+    A(f"// GENERATED by amici_b200/codegen/emitter.py from amici_b200/codegen/models.py::{spec.name} — do not edit.")
+    A(f"// Device functions of model '{spec.name}' for the batched BDF engine (see emitter.py for the")
+    A("// mapping onto the reference's generated <fn>_<model>.cpp files).")
+    A(f"#ifndef {guard}\n#define {guard}\n#include \"../model_common.cuh\"\nnamespace amici_b200 {{ namespace models {{\n")
+    A(f"struct {spec.name} {{")
+    A(f"    static constexpr int NX = {nx}, NP = {npar}, NK = {nk}, NY = {ny}, NSPL = {nspl}, NE = {ne}, NH = {len(h_syms)};")
+    A(f"    static constexpr int NNZ_J = {nnz};")
+    nz = sum(len(ev.z) for ev in spec.events)
+    A(f"    static constexpr int NZ = {nz};")
+    nn_max = max([len(s.nodes) for s in spec.splines], default=1)
+    A(f"    static constexpr int SPL_NN = {nn_max};  // nodes per spline")
+    A(f"    static constexpr bool SPL_LOG = {'true' if all(s.logarithmic for s in spec.splines) else 'false'};")
+    A(f"    static const char* name() {{ return \"{spec.name}\"; }}")
+    A("    static void nominal(double* p, double* k) {")
+    for i, v in enumerate(spec.p_nominal):
+        A(f"        p[{i}] = {float(v)!r};")
+    for i, v in enumerate(spec.k_nominal):
+        A(f"        k[{i}] = {float(v)!r};")
+    A("    }")
+
+    sig_common = "const double t, const double* x, const double* p, const double* k, const double* h, const double* spl"
+
+    # x0 / sx0
+    A("    AB_HD static void x0(const double* p, const double* k, double* x0) {")
+    A("        (void)p; (void)k;")
+    A(W.body([(f"x0[{i}]", x0[i]) for i in range(nx)]).rstrip("\n"))
+    A("    }")
+    A("    AB_HD static void sx0(const int ip, const double* p, const double* k, double* sx0) {")
+    A("        (void)p; (void)k; (void)ip;")
+    for i in range(nx):
+        cases = [(ip, W._pr(sp.diff(x0[i], spec.params[ip]))) for ip in range(npar) if sp.diff(x0[i], spec.params[ip]) != 0]
+        A(f"        sx0[{i}] = {_select_chain('ip', cases)};")
+    A("    }")
+
+    # xdot
+    A(f"    AB_HD static void xdot({sig_common}, double* xdot) {{")
+    A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl;")
+    A(W.body([(f"xdot[{i}]", xdot[i]) for i in range(nx)]).rstrip("\n"))
+    A("    }")
+    # jac
+    A(f"    // CSC pattern of J = d xdot / d x (cf. reference dxdotdx_explicit_{{colptrs,rowvals}})")
+    A(f"    // colptr = {colptr}\n    // rowval = {rowval}")
+    A(f"    AB_HD static void jac({sig_common}, double* J) {{")
+    A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl;")
+    A(W.body([(f"J[{i}]", jvals[i]) for i in range(nnz)]).rstrip("\n"))
+    A("    }")
+    A("    // out += J * s")
+    A("    AB_HD static void jac_mul_add(const double* J, const double* s, double* out) {")
+    for r in range(nx):
+        terms = []
+        for c in range(nx):
+            for idx in range(colptr[c], colptr[c + 1]):
+                if rowval[idx] == r:
+                    terms.append(f"J[{idx}] * s[{c}]")
+        if terms:
+            A(f"        out[{r}] += " + " + ".join(terms) + ";")
+    A("    }")
+    A("    // A (row-major NX*NX) = I - gamma * J")
+    A("    template <class Mat> AB_HD static void jac_to_A(const double* J, const double gamma, Mat& A) {")
+    for r in range(nx):
+        for c in range(nx):
+            idx = None
+            for q in range(colptr[c], colptr[c + 1]):
+                if rowval[q] == r:
+                    idx = q
+            diag = "1.0" if r == c else "0.0"
+            if idx is None:
+                A(f"        A({r}, {c}) = {diag};")
+            else:
+                A(f"        A({r}, {c}) = {diag} - gamma * J[{idx}];")
+    A("    }")
+    A("    // dense row-major copy of J (ReturnData::J layout, reference include/amici/rdata.h:707-728)")
+    A("    AB_HD static void jac_to_dense(const double* J, double* D) {")
+    for r in range(nx):
+        for c in range(nx):
+            idx = None
+            for q in range(colptr[c], colptr[c + 1]):
+                if rowval[q] == r:
+                    idx = q
+            A(f"        D[{r * nx + c}] = " + (f"J[{idx}];" if idx is not None else "0.0;"))
+    A("    }")
+
+    # dxdotdp column
+    A("    // total derivative column d xdot / d p_ip (explicit + through splines), select-chain form")
+    A(f"    AB_HD static void dxdotdp(const int ip, {sig_common}, const double* sspl, double* out) {{")
+    A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)sspl; (void)ip;")
+    vals, rows = [], []
+    for r in range(nx):
+        cases = []
+        for ip in range(npar):
+            e = total_dp(xdot[r], ip)
+            if e != 0:
+                vals.append((f"const double v_{r}_{ip}", e))
+                cases.append((ip, f"v_{r}_{ip}"))
+        rows.append(cases)
+    A(W.body(vals).rstrip("\n"))
+    for r in range(nx):
+        A(f"        out[{r}] = {_select_chain('ip', rows[r])};")
+    A("    }")
+
+    # observables
+    A(f"    AB_HD static void y({sig_common}, double* y) {{")
+    A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl;")
+    A(W.body([(f"y[{i}]", yexpr[i]) for i in range(ny)]).rstrip("\n"))
+    A("    }")
+    A("    // sy = dydx * sx + dydp(ip)   (reference Model::get_observable_sensitivity, src/model.cpp:1123-1156)")
+    A(f"    AB_HD static void sy(const int ip, {sig_common}, const double* sspl, const double* sx, double* sy) {{")
+    A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)sspl; (void)ip; (void)sx;")
+    vals, rows = [], []
+    for iy in range(ny):
+        lin = sum((sp.diff(yexpr[iy], spec.states[c]) * sx_syms[c] for c in range(nx)), sp.Integer(0))
+        vals.append((f"const double l_{iy}", lin))
+        cases = []
+        for ip in range(npar):
+            e = total_dp(yexpr[iy], ip)
+            if e != 0:
+                vals.append((f"const double v_{iy}_{ip}", e))
+                cases.append((ip, f"v_{iy}_{ip}"))
+        rows.append(cases)
+    A(W.body(vals).rstrip("\n"))
+    for iy in range(ny):
+        A(f"        sy[{iy}] = l_{iy} + ({_select_chain('ip', rows[iy])});")
+    A("    }")
+    ysub = {}
+    # sigma may depend on p, k and y (symbols y_<name>)
+    A("    AB_HD static void sigmay(const double* p, const double* k, const double* y, double* sigmay) {")
+    A("        (void)p; (void)k; (void)y;")
+    A(W.body([(f"sigmay[{i}]", sigexpr[i]) for i in range(ny)]).rstrip("\n"))
+    A("    }")
+    A("    // ssigmay = dsigmaydp(ip) + dsigmaydy * sy   (reference src/model.cpp:1165-1192)")
+    A("    AB_HD static void ssigmay(const int ip, const double* p, const double* k, const double* y, const double* sy, double* out) {")
+    A("        (void)p; (void)k; (void)y; (void)sy; (void)ip;")
+    sy_syms = [sp.Symbol(f"sy[{i}]") for i in range(ny)]
+    for iy in range(ny):
+        cases = [(ip, W._pr(sp.diff(sigexpr[iy], spec.params[ip]))) for ip in range(npar)
+                 if sp.diff(sigexpr[iy], spec.params[ip]) != 0]
+        lin = sum((sp.diff(sigexpr[iy], y_syms[j]) * sy_syms[j] for j in range(ny)), sp.Integer(0))
+        A(f"        out[{iy}] = ({_select_chain('ip', cases)}) + {W._pr(lin)};")
+    A("    }")
+    A("    // only the explicit part dsigmaydp(ip) (enters sllh through dJydsigma, reference src/model.cpp:2340-2377)")
+    A("    AB_HD static void dsigmaydp(const int ip, const double* p, const double* k, const double* y, double* out) {")
+    A("        (void)p; (void)k; (void)y; (void)ip;")
+    for iy in range(ny):
+        cases = [(ip, W._pr(sp.diff(sigexpr[iy], spec.params[ip]))) for ip in range(npar)
+                 if sp.diff(sigexpr[iy], spec.params[ip]) != 0]
+        A(f"        out[{iy}] = {_select_chain('ip', cases)};")
+    A("    }")
+
+    # splines: node positions, node values and their parameter derivative (select chain)
+    if nspl:
+        A("    // spline node data (reference create_splines_<model>.cpp / dspline_valuesdp_<model>.cpp)")
+        A("    AB_HD static double spline_node(const int ispl, const int i) {")
+        for i, s in enumerate(spec.splines):
+            arr = ", ".join(repr(float(v)) for v in s.nodes)
+            A(f"        {{ const double n{i}[{len(s.nodes)}] = {{{arr}}}; if (ispl == {i}) return n{i}[i]; }}")
+        A("        return 0.0;\n    }")
+        A("    AB_HD static void spline_values(const int ispl, const double* p, const double* k, double* v) {")
+        A("        (void)p; (void)k;")
+        for i, s in enumerate(spec.splines):
+            A(f"        if (ispl == {i}) {{")
+            A(W.body([(f"v[{j}]", e) for j, e in enumerate(s.values)], indent="            ").rstrip("\n"))
+            A("        }")
+        A("    }")
+        A("    AB_HD static void spline_dvaluesdp(const int ispl, const int ip, const double* p, const double* k, double* dv) {")
+        A("        (void)p; (void)k; (void)ip;")
+        for i, s in enumerate(spec.splines):
+            A(f"        if (ispl == {i}) {{")
+            for j, e in enumerate(s.values):
+                cases = [(ip, W._pr(sp.diff(e, spec.params[ip]))) for ip in range(npar) if sp.diff(e, spec.params[ip]) != 0]
+                A(f"            dv[{j}] = {_select_chain('ip', cases)};")
+            A("        }")
+        A("    }")
+    else:
+        A("    AB_HD static double spline_node(const int, const int) { return 0.0; }")
+        A("    AB_HD static void spline_values(const int, const double*, const double*, double*) {}")
+        A("    AB_HD static void spline_dvaluesdp(const int, const int, const double*, const double*, double*) {}")
+    A("};\n")
+    A("}}  // namespace amici_b200::models")
+    A(f"#endif  // {guard}")
+    return "\n".join(out) + "\n"
+
+
+def write_model(spec: ModelSpec, out_dir: str) -> str:
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, f"{spec.name}.cuh")
+    txt = emit_model(spec)
+    if not os.path.exists(path) or open(path).read() != txt:
+        with open(path, "w") as f:
+            f.write(txt)
+    return path

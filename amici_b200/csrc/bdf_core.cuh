@@ -1,0 +1,1220 @@
+// Batched variable-order, variable-step BDF with simultaneous forward sensitivities.
+//
+// Behavioural specification: SUNDIALS CVODES 7.1.1 as driven by AMICI's CVodeSolver
+// (reference ThirdParty/sundials/src/cvodes/cvodes.c; cvodes_nls_sim.c; cvodes_ls.c;
+// sunnonlinsol_newton.c; reference src/solver_cvodes.cpp, src/forwardproblem.cpp).  This is not
+// a translation of those sources: there are no N_Vector/SUNMatrix/SUNLinearSolver objects.
+// The stacked (state | sensitivity) system is stored column-wise, every lane of a lane-group
+// (group.cuh) owns C columns, the Nordsieck history of all columns sits in the group's
+// shared-memory slice, the per-column work vectors in registers, and all scalar step control
+// is computed redundantly per lane.  Function names below cite the CVODES routine whose
+// decisions they must reproduce (constants: reference cvodes_impl.h:57-131,202-204;
+// cvodes_ls_impl.h:40-41).
+//
+// The same source is compiled for the host with G = 1 by tests/cpu_emul (algorithm check
+// against the compiled reference without a GPU); the product is the CUDA instantiation.
+#ifndef AMICI_B200_BDF_CORE_CUH
+#define AMICI_B200_BDF_CORE_CUH
+#include "group.cuh"
+#include "model_common.cuh"
+#include "spline.cuh"
+
+namespace amici_b200 {
+
+// ---------------------------------------------------------------------------------------------
+// plain-data interface structs (also part of the C ABI, see include/amici_b200.h)
+// ---------------------------------------------------------------------------------------------
+struct SolverOptions {
+    double rtol, atol;          // Solver::set_relative/absolute_tolerance (reference solver.h:2057-2060)
+    double rtol_fsa, atol_fsa;  // already resolved (NaN -> rtol/atol, reference src/solver.cpp:874-891)
+    double t0;
+    double hmax_inv;            // 1/max_step_size, 0 = unbounded (reference solver.h:2115)
+    int sensi;                  // 0 none, 1 first-order forward
+    int ism;                    // 1 simultaneous (only mode implemented)
+    int maxsteps;               // budget for the whole simulation (reference src/solver.cpp:107-119)
+    int stldet;                 // BDF stability-limit detection (reference solver.h:2037, default on)
+    int max_nonlin_iters;       // 3
+    int max_conv_fails;         // 10
+    int max_err_test_fails;     // 7 (CVODES default MXNEF)
+    int reporting;              // RDataReporting: 0 full, 2 likelihood
+};
+
+struct BatchView {
+    // ---- inputs ----
+    int N, nt, nplist;
+    const double* ts;         // [nt]
+    const int* plist;         // [nplist]
+    const int* pscale;        // [NP]
+    const double* p;          // [N][NP] on the scale given by pscale
+    const double* k;          // [N][NK]
+    const double* my;         // [N][nt][NY] or null; NaN = missing (reference src/edata.cpp:178-181)
+    const double* sigmay_in;  // [N][nt][NY] or null; NaN = use model sigma
+    // ---- outputs (any may be null) ----
+    int* status;     // [N]
+    double* llh;     // [N]
+    double* chi2;    // [N]
+    double* sllh;    // [N][nplist]
+    double* x;       // [N][nt][NX]
+    double* sx;      // [N][nt][nplist][NX]
+    double* y;       // [N][nt][NY]
+    double* sy;      // [N][nt][nplist][NY]
+    double* sigmay;  // [N][nt][NY]
+    double* ssigmay; // [N][nt][nplist][NY]
+    double* res;     // [N][nt*NY]
+    double* sres;    // [N][nt*NY][nplist]
+    double* FIM;     // [N][nplist][nplist]
+    double* x0;      // [N][NX]
+    double* sx0;     // [N][nplist][NX]
+    double* xdot;    // [N][NX]
+    double* J;       // [N][NX][NX]
+    int* numsteps;   // [N][nt]
+    int* numrhsevals;
+    int* numerrtestfails;
+    int* numnonlinsolvconvfails;
+    int* order;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-trajectory shared storage
+// ---------------------------------------------------------------------------------------------
+constexpr int QMAX = 5;           // BDF_Q_MAX
+constexpr int LMAX = QMAX + 1;
+
+template <class M, int NCOLS>
+struct TrajShared {
+    double zn[LMAX][M::NX][NCOLS];   // Nordsieck history, column fastest
+    double lu[M::NX][M::NX];         // LU factors of I - gamma*J (row-major, unit lower)
+    double savedJ[M::NNZ_J > 0 ? M::NNZ_J : 1];
+    double ybuf[M::NX];              // broadcast buffer for the state column
+    double scratch[NCOLS];
+    double p[M::NP > 0 ? M::NP : 1];
+    double k[M::NK > 0 ? M::NK : 1];
+    double h[M::NH > 0 ? M::NH : 1];
+    double pcoef[NCOLS];             // chain-rule factor per column
+    double ssdat[6][4];              // cvBDFStab history
+    int piv[M::NX];
+    int ip_of_col[NCOLS];
+    SplineTable<M, NCOLS> spl;
+};
+
+// internal flags of cvStep (cvodes.c local defines)
+enum : int { FIRST_CALL = 101, PREV_CONV_FAIL = 102, PREV_ERR_FAIL = 103 };
+enum : int { NLS_CONV_RECVR = 902, NLS_RHS_RECVR = 903 };
+enum : int { CONVFAIL_NONE = 0, CONVFAIL_BAD_J = 1, CONVFAIL_OTHER = 2 };
+
+template <class M, int G, int C>
+struct Bdf {
+    static constexpr int NX = M::NX;
+    static constexpr int NCOLS = G * C;
+    using Shared = TrajShared<M, NCOLS>;
+
+    Shared& S;
+    const SolverOptions& o;
+    Group<G> g;
+    int ncols;  // active columns: 1 + nplist (1 without sensitivities)
+
+    // per-lane column registers
+    double acor[C][NX];
+    double ewt[C][NX];
+
+    // step control (group-uniform scalars; CVodeMem fields of the same name)
+    double tn, h, hscale, hprime, eta, etamax, etaq, etaqm1, etaqp1, hu;
+    double tau[LMAX + 1], l[LMAX], tq[6];
+    double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
+    double tstop, tretlast;
+    int q, qprime, qwait, L, qu;
+    int nst, nstlp, nstlj, nscon, nfe, netf, ncfn, nni, nsetups, nje;
+    int convfail;
+    bool jcur, tstopset;
+
+    AB_HD Bdf(Shared& s, const SolverOptions& opt, int ncols_) : S(s), o(opt), ncols(ncols_) {}
+
+    AB_HD int col(int c) const { return g.lane + G * c; }
+    AB_HD bool active(int c) const { return col(c) < ncols; }
+
+    // -----------------------------------------------------------------------------------------
+    // norms
+    // -----------------------------------------------------------------------------------------
+    // max over active columns of WRMS(v_col, ewt_col)  (N_VWrmsNorm_SensWrapper + cvSensUpdateNorm,
+    // reference sundials_nvector_senswrapper.c:426-440; errconS = TRUE in AMICI, src/solver.cpp:641-656)
+    AB_HD double wrms_max(const double (&v)[C][NX]) const {
+        double m = 0.0;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            double s = 0.0;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                const double pr = v[c][r] * ewt[c][r];
+                s += pr * pr;
+            }
+            const double n = sqrt(s / NX);
+            m = (n > m || n != n) ? n : m;
+        }
+        return g.max(m);
+    }
+    // same for a Nordsieck column j held in shared memory
+    AB_HD double wrms_max_zn(int j) const {
+        double m = 0.0;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            double s = 0.0;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                const double pr = S.zn[j][r][col(c)] * ewt[c][r];
+                s += pr * pr;
+            }
+            const double n = sqrt(s / NX);
+            m = (n > m || n != n) ? n : m;
+        }
+        return g.max(m);
+    }
+    // WRMS of the state column only (used by cvBDFStab)
+    AB_HD double wrms_state_zn(int j) const {
+        double n = 0.0;
+        if (g.lane == 0) {
+            double s = 0.0;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                const double pr = S.zn[j][r][0] * ewt[0][r];
+                s += pr * pr;
+            }
+            n = sqrt(s / NX);
+        }
+        return g.bcast(n, 0);
+    }
+
+    // cvEwtSetSS (cvodes.c:9118) / cvSensEwtSetSS (:9263)
+    AB_HD void set_ewt() {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            const bool st = (col(c) == 0);
+            const double rt = st ? o.rtol : o.rtol_fsa, at = st ? o.atol : o.atol_fsa;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) ewt[c][r] = 1.0 / (rt * fabs(S.zn[0][r][col(c)]) + at);
+        }
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // model right-hand sides
+    // -----------------------------------------------------------------------------------------
+    struct ModelEval {
+        double y[NX];                                   // state column (broadcast)
+        double spl[M::NSPL > 0 ? M::NSPL : 1];
+        double sspl[C][M::NSPL > 0 ? M::NSPL : 1];
+    };
+
+    AB_HD void eval_splines(double t, ModelEval& e) const {
+        AB_UNROLL
+        for (int is = 0; is < M::NSPL; ++is) {
+            const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
+            e.spl[is] = M::SPL_LOG ? exp(v) : v;
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                e.sspl[c][is] = 0.0;
+                if (!active(c) || col(c) == 0) continue;
+                const double s = spline_eval_scaled<M, NCOLS>(S.spl, is, col(c), t, false);
+                e.sspl[c][is] = M::SPL_LOG ? s * e.spl[is] : s;
+            }
+        }
+    }
+
+    // Broadcast the state column ycol0 (valid on the lane that owns column 0) to all lanes.
+    AB_HD void bcast_state(const double (&v)[C][NX], ModelEval& e) {
+        if (G == 1) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) e.y[r] = v[0][r];
+            return;
+        }
+        g.sync();
+        if (g.lane == 0) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) S.ybuf[r] = v[0][r];
+        }
+        g.sync();
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) e.y[r] = S.ybuf[r];
+    }
+
+    // f for column 0, J(y)*s_c + dfdp_c for sensitivity columns (Model_ODE::fxdot / fsxdot,
+    // reference src/model_ode.cpp:105-114, :426-450).  ycols = current values of all own columns.
+    // Returns false if any output is non-finite (AMICI's check_finite -> recoverable error).
+    AB_HD bool rhs(double t, const double (&ycols)[C][NX], double (&out)[C][NX], ModelEval& e) {
+        bcast_state(ycols, e);
+        eval_splines(t, e);
+        double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
+        bool need_j = false;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) need_j = need_j || (active(c) && col(c) > 0);
+        if (need_j) M::jac(t, e.y, S.p, S.k, S.h, e.spl, Jv);
+        bool ok = true;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            if (col(c) == 0) {
+                M::xdot(t, e.y, S.p, S.k, S.h, e.spl, out[c]);
+            } else {
+                M::dxdotdp(S.ip_of_col[col(c)], t, e.y, S.p, S.k, S.h, e.spl, e.sspl[c], out[c]);
+                M::jac_mul_add(Jv, ycols[c], out[c]);
+            }
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) ok = ok && isfinite(out[c][r]);
+        }
+        nfe++;
+        return !g.any(!ok);
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // linear algebra: dense LU with partial pivoting in shared memory (SUNLinSol_Dense semantics;
+    // the reference's default KLU differs only in pivot order / round-off)
+    // -----------------------------------------------------------------------------------------
+    struct LuRef {
+        Shared& S;
+        AB_HD double& operator()(int r, int c) { return S.lu[r][c]; }
+    };
+
+    // returns false on an exactly singular matrix
+    AB_HD bool lu_factor() {
+        g.sync();
+        int ok = 1;
+        if (g.lane == 0) {
+            for (int kk = 0; kk < NX; ++kk) {
+                int pr = kk;
+                double best = fabs(S.lu[kk][kk]);
+                for (int i = kk + 1; i < NX; ++i) {
+                    const double a = fabs(S.lu[i][kk]);
+                    if (a > best) { best = a; pr = i; }
+                }
+                S.piv[kk] = pr;
+                if (best == 0.0) { ok = 0; break; }
+                if (pr != kk)
+                    for (int j = 0; j < NX; ++j) {
+                        const double tmp = S.lu[kk][j];
+                        S.lu[kk][j] = S.lu[pr][j];
+                        S.lu[pr][j] = tmp;
+                    }
+                const double inv = 1.0 / S.lu[kk][kk];
+                for (int i = kk + 1; i < NX; ++i) {
+                    const double m = S.lu[i][kk] * inv;
+                    S.lu[i][kk] = m;
+                    if (m != 0.0)
+                        for (int j = kk + 1; j < NX; ++j) S.lu[i][j] -= m * S.lu[kk][j];
+                }
+            }
+        }
+        ok = g.bcast(ok, 0);
+        g.sync();
+        return ok != 0;
+    }
+
+    // b <- A^{-1} b for every own column
+    AB_HD void lu_solve(double (&b)[C][NX]) const {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            // row interchanges (register array: select-swap keeps indices static)
+            AB_UNROLL
+            for (int kk = 0; kk < NX; ++kk) {
+                const int pr = S.piv[kk];
+                double vp = b[c][kk];
+                AB_UNROLL
+                for (int i = kk + 1; i < NX; ++i)
+                    if (i == pr) {
+                        const double tmp = b[c][i];
+                        b[c][i] = vp;
+                        vp = tmp;
+                    }
+                b[c][kk] = vp;
+            }
+            AB_UNROLL
+            for (int i = 1; i < NX; ++i) {
+                double s = b[c][i];
+                AB_UNROLL
+                for (int j = 0; j < i; ++j) s -= S.lu[i][j] * b[c][j];
+                b[c][i] = s;
+            }
+            AB_UNROLL
+            for (int i = NX - 1; i >= 0; --i) {
+                double s = b[c][i];
+                AB_UNROLL
+                for (int j = i + 1; j < NX; ++j) s -= S.lu[i][j] * b[c][j];
+                b[c][i] = s / S.lu[i][i];
+            }
+        }
+    }
+
+    // cvLsSetup + cvLsLinSys + cvNlsLSetupSensSim (cvodes_ls.c:1611-1710, :1386-1470; cvodes_nls_sim.c:300-331)
+    AB_HD int lsetup(bool jbad_nls, const ModelEval& e) {
+        if (jbad_nls) convfail = CONVFAIL_BAD_J;
+        const double dgamma = fabs(gamma / gammap - 1.0);
+        const bool jbad = (nst == 0) || (nst >= nstlj + 51) || (convfail == CONVFAIL_BAD_J && dgamma < 0.2) ||
+                          (convfail == CONVFAIL_OTHER);
+        double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
+        g.sync();
+        if (jbad) {
+            jcur = true;
+            M::jac(tn, e.y, S.p, S.k, S.h, e.spl, Jv);
+            if (g.lane == 0) {
+                AB_UNROLL
+                for (int i = 0; i < M::NNZ_J; ++i) S.savedJ[i] = Jv[i];
+            }
+            nje++;
+            nstlj = nst;
+        } else {
+            jcur = false;
+            AB_UNROLL
+            for (int i = 0; i < M::NNZ_J; ++i) Jv[i] = S.savedJ[i];
+        }
+        bool fin = true;
+        AB_UNROLL
+        for (int i = 0; i < M::NNZ_J; ++i) fin = fin && isfinite(Jv[i]);
+        if (g.lane == 0) {
+            LuRef A{S};
+            M::jac_to_A(Jv, gamma, A);
+        }
+        const bool okf = lu_factor();
+        nsetups++;
+        gamrat = 1.0;
+        gammap = gamma;
+        crate = 1.0;
+        nstlp = nst;
+        if (!fin || !okf) return NLS_CONV_RECVR;  // recoverable setup failure
+        return AB_SUCCESS;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // Nordsieck array manipulation (per row in registers)
+    // -----------------------------------------------------------------------------------------
+    // cvPredict (cvodes.c:6507) / cvRestore (:7373): Pascal-triangle update, sign = +1 / -1
+    AB_HD void pascal(const double sign) {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                double z[LMAX];
+                AB_UNROLL
+                for (int j = 0; j < LMAX; ++j) z[j] = (j <= q) ? S.zn[j][r][col(c)] : 0.0;
+                AB_UNROLL
+                for (int kk = 1; kk <= QMAX; ++kk) {
+                    AB_UNROLL
+                    for (int j = QMAX; j >= 1; --j)
+                        if (j >= kk && j <= q && kk <= q) z[j - 1] += sign * z[j];
+                }
+                AB_UNROLL
+                for (int j = 0; j < QMAX; ++j)
+                    if (j < q) S.zn[j][r][col(c)] = z[j];
+            }
+        }
+    }
+
+    // cvRescale (cvodes.c:6425): zn[j] *= eta^j, h = hscale*eta
+    AB_HD void rescale() {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                double f = eta;
+                AB_UNROLL
+                for (int j = 1; j <= QMAX; ++j) {
+                    if (j <= q) S.zn[j][r][col(c)] *= f;
+                    f *= eta;
+                }
+            }
+        }
+        h = hscale * eta;
+        hscale = h;
+        nscon = 0;
+    }
+
+    // zn[j] += cf[j] * v for j in [j0, j1]
+    AB_HD void zn_axpy(const double* cf, int j0, int j1, const double (&v)[C][NX]) {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int j = 0; j < LMAX; ++j) {
+                if (j < j0 || j > j1) continue;
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) S.zn[j][r][col(c)] += cf[j] * v[c][r];
+            }
+        }
+    }
+
+    // cvIncreaseBDF (cvodes.c:6256)
+    AB_HD void increase_bdf() {
+        double ll[LMAX + 1];
+        for (int i = 0; i <= LMAX; ++i) ll[i] = 0.0;
+        double alpha0 = -1.0, alpha1 = 1.0, prod = 1.0, xiold = 1.0, hsum = hscale;
+        ll[2] = 1.0;
+        if (q > 1) {
+            for (int j = 1; j < q; ++j) {
+                hsum += tau[j + 1];
+                const double xi = hsum / hscale;
+                prod *= xi;
+                alpha0 -= 1.0 / (j + 1);
+                alpha1 += 1.0 / xi;
+                for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xiold + ll[i - 1];
+                xiold = xi;
+            }
+        }
+        const double A1 = (-alpha0 - alpha1) / prod;
+        // zn[L] = A1 * zn[indx_acor = qmax]
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                const double zL = A1 * S.zn[QMAX][r][col(c)];
+                AB_UNROLL
+                for (int j = 2; j <= QMAX; ++j) {
+                    if (j == L) S.zn[j][r][col(c)] = zL;
+                    else if (j <= q) S.zn[j][r][col(c)] += ll[j] * zL;
+                }
+            }
+        }
+    }
+
+    // cvDecreaseBDF (cvodes.c:6363)
+    AB_HD void decrease_bdf() {
+        double ll[LMAX + 1];
+        for (int i = 0; i <= LMAX; ++i) ll[i] = 0.0;
+        ll[2] = 1.0;
+        double hsum = 0.0;
+        for (int j = 1; j <= q - 2; ++j) {
+            hsum += tau[j];
+            const double xi = hsum / hscale;
+            for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xi + ll[i - 1];
+        }
+        if (q > 2) {
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                if (!active(c)) continue;
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) {
+                    double zq = 0.0;
+                    AB_UNROLL
+                    for (int j = 2; j <= QMAX; ++j)
+                        if (j == q) zq = S.zn[j][r][col(c)];
+                    AB_UNROLL
+                    for (int j = 2; j < QMAX; ++j)
+                        if (j < q) S.zn[j][r][col(c)] -= ll[j] * zq;
+                }
+            }
+        }
+    }
+
+    // cvAdjustOrder (cvodes.c:6134)
+    AB_HD void adjust_order(int deltaq) {
+        if (q == 2 && deltaq != 1) return;
+        if (deltaq == 1) increase_bdf();
+        else if (deltaq == -1) decrease_bdf();
+    }
+
+    // cvAdjustParams (cvodes.c:6112)
+    AB_HD void adjust_params() {
+        if (qprime != q) {
+            adjust_order(qprime - q);
+            q = qprime;
+            L = q + 1;
+            qwait = L;
+        }
+        rescale();
+    }
+
+    // cvSetBDF + cvSetTqBDF + cvSet (cvodes.c:6788-6892, :6617)
+    AB_HD void set_coeffs() {
+        double alpha0 = -1.0, alpha0_hat = -1.0, xi_inv = 1.0, xistar_inv = 1.0, hsum = h;
+        l[0] = l[1] = 1.0;
+        for (int i = 2; i <= q; ++i) l[i] = 0.0;
+        if (q > 1) {
+            for (int j = 2; j < q; ++j) {
+                hsum += tau[j - 1];
+                xi_inv = h / hsum;
+                alpha0 -= 1.0 / j;
+                for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
+            }
+            alpha0 -= 1.0 / q;
+            xistar_inv = -l[1] - alpha0;
+            hsum += tau[q - 1];
+            xi_inv = h / hsum;
+            alpha0_hat = -l[1] - xi_inv;
+            for (int i = q; i >= 1; --i) l[i] += l[i - 1] * xistar_inv;
+        }
+        const double A1 = 1.0 - alpha0_hat + alpha0;
+        const double A2 = 1.0 + q * A1;
+        tq[2] = fabs(A1 / (alpha0 * A2));
+        tq[5] = fabs(A2 * xistar_inv / (l[q] * xi_inv));
+        if (qwait == 1) {
+            if (q > 1) {
+                const double Cc = xistar_inv / l[q];
+                const double A3 = alpha0 + 1.0 / q;
+                const double A4 = alpha0_hat + xi_inv;
+                const double Cpinv = (1.0 - A4 + A3) / A3;
+                tq[1] = fabs(Cc * Cpinv);
+            } else {
+                tq[1] = 1.0;
+            }
+            hsum += tau[q];
+            xi_inv = h / hsum;
+            const double A5 = alpha0 - (1.0 / (q + 1));
+            const double A6 = alpha0_hat - xi_inv;
+            const double Cppinv = (1.0 - A6 + A5) / A2;
+            tq[3] = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+        }
+        tq[4] = 0.1 / tq[2];  // nlscoef = CORTES = 0.1
+        rl1 = 1.0 / l[1];
+        gamma = h * rl1;
+        if (nst == 0) gammap = gamma;
+        gamrat = (nst > 0) ? gamma / gammap : 1.0;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // nonlinear solve: cvNls (cvodes.c:6894) + SUNNonlinSolSolve_Newton (sunnonlinsol_newton.c:176-330)
+    // + cvNlsResidualSensSim / cvNlsLSolveSensSim / cvNlsConvTestSensSim (cvodes_nls_sim.c:333-515)
+    // -----------------------------------------------------------------------------------------
+    // residual: res = rl1*zn1 + ycor - gamma * F(tn, zn0 + ycor); returns false on non-finite rhs
+    AB_HD bool residual(double (&res)[C][NX], ModelEval& e) {
+        double ycur[C][NX];
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) ycur[c][r] = active(c) ? S.zn[0][r][col(c)] + acor[c][r] : 0.0;
+        }
+        const bool ok = rhs(tn, ycur, res, e);
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) res[c][r] = rl1 * S.zn[1][r][col(c)] + acor[c][r] - gamma * res[c][r];
+        }
+        return ok;
+    }
+
+    AB_HD int nls(int nflag) {
+        convfail = (nflag == FIRST_CALL || nflag == PREV_ERR_FAIL) ? CONVFAIL_NONE : CONVFAIL_OTHER;
+        bool callSetup = (nflag == PREV_CONV_FAIL) || (nflag == PREV_ERR_FAIL) || (nst == 0) ||
+                         (nst >= nstlp + 20) || (fabs(gamrat - 1.0) > 0.3);
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) acor[c][r] = 0.0;
+        }
+        bool jbad = false;
+        int ret;
+        ModelEval e;
+        double delta[C][NX];
+        for (;;) {
+            int m = 0;
+            ret = AB_SUCCESS;
+            if (!residual(delta, e)) ret = NLS_RHS_RECVR;
+            if (ret == AB_SUCCESS && callSetup) ret = lsetup(jbad, e);
+            if (ret == AB_SUCCESS) {
+                for (;;) {
+                    nni++;
+                    AB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r) delta[c][r] = -delta[c][r];
+                    }
+                    lu_solve(delta);
+                    if (gamrat != 1.0) {
+                        const double sc = 2.0 / (1.0 + gamrat);
+                        AB_UNROLL
+                        for (int c = 0; c < C; ++c) {
+                            AB_UNROLL
+                            for (int r = 0; r < NX; ++r) delta[c][r] *= sc;
+                        }
+                    }
+                    AB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        if (!active(c)) continue;
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r) acor[c][r] += delta[c][r];
+                    }
+                    const double Del = wrms_max(delta);
+                    if (m > 0) crate = ab_max(0.3 * crate, Del / delp);
+                    const double dcon = Del * ab_min(1.0, crate) / tq[4];
+                    if (dcon <= 1.0) {
+                        acnrm = (m == 0) ? Del : wrms_max(acor);
+                        jcur = false;
+                        return AB_SUCCESS;
+                    }
+                    if (!(Del == Del)) { ret = NLS_CONV_RECVR; break; }  // NaN correction: treat as divergence
+                    if (m >= 1 && Del > 2.0 * delp) { ret = NLS_CONV_RECVR; break; }
+                    delp = Del;
+                    m++;
+                    if (m >= o.max_nonlin_iters) { ret = NLS_CONV_RECVR; break; }
+                    if (!residual(delta, e)) { ret = NLS_RHS_RECVR; break; }
+                }
+            }
+            // recoverable failure with stale Jacobian data: retry once with a fresh J
+            if (ret > 0 && !jcur) {
+                callSetup = true;
+                jbad = true;
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) acor[c][r] = 0.0;
+                }
+                continue;
+            }
+            break;
+        }
+        return ret;
+    }
+
+    // cvHandleNFlag (cvodes.c:7309): returns 0 = do error test, 1 = predict again, <0 = failure
+    AB_HD int handle_nflag(int& nflag, double saved_t, int& ncf) {
+        if (nflag == AB_SUCCESS) return 0;
+        ncfn++;
+        pascal(-1.0);
+        tn = saved_t;
+        ncf++;
+        etamax = 1.0;
+        if (fabs(h) <= 0.0 /*hmin*/ * 1.000001 || ncf == o.max_conv_fails) {
+            return (nflag == NLS_RHS_RECVR) ? AB_REPTD_RHSFUNC_ERR : AB_CONV_FAILURE;
+        }
+        eta = 0.25;  // max(eta_cf, hmin/|h|), hmin = 0
+        nflag = PREV_CONV_FAIL;
+        rescale();
+        return 1;
+    }
+
+    // cvDoErrorTest (cvodes.c:7461): 0 = passed, 1 = try again, <0 failure
+    AB_HD int do_error_test(int& nflag, double saved_t, int& nef, double& dsm) {
+        dsm = acnrm * tq[2];
+        if (dsm <= 1.0) return 0;
+        nef++;
+        netf++;
+        nflag = PREV_ERR_FAIL;
+        pascal(-1.0);
+        tn = saved_t;
+        if (fabs(h) <= 0.0 || nef == o.max_err_test_fails) return AB_ERR_FAILURE;
+        etamax = 1.0;
+        if (nef <= 3) {  // MXNEF1
+            eta = 1.0 / (pow(6.0 * dsm, 1.0 / L) + 1e-6);
+            eta = ab_max(0.1, eta);
+            if (nef >= 2) eta = ab_min(eta, 0.2);
+            rescale();
+            return 1;
+        }
+        if (q > 1) {
+            eta = 0.1;
+            adjust_order(-1);
+            L = q;
+            q--;
+            qwait = L;
+            rescale();
+            return 1;
+        }
+        // order 1: restart from scratch with h*eta
+        eta = 0.1;
+        h *= eta;
+        hscale = h;
+        qwait = 10;  // LONG_WAIT
+        nscon = 0;
+        {
+            ModelEval e;
+            double y0[C][NX], f[C][NX];
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) y0[c][r] = active(c) ? S.zn[0][r][col(c)] : 0.0;
+            }
+            if (!rhs(tn, y0, f, e)) return AB_UNREC_RHSFUNC_ERR;
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                if (!active(c)) continue;
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] = h * f[c][r];
+            }
+        }
+        return 1;
+    }
+
+    // cvCompleteStep (cvodes.c:7634)
+    AB_HD void complete_step() {
+        nst++;
+        nscon++;
+        hu = h;
+        qu = q;
+        for (int i = q; i >= 2; --i) tau[i] = tau[i - 1];
+        if (q == 1 && nst > 1) tau[2] = tau[1];
+        tau[1] = h;
+        zn_axpy(l, 0, q, acor);
+        qwait--;
+        if (qwait == 1 && q != QMAX) {
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                if (!active(c)) continue;
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) S.zn[QMAX][r][col(c)] = acor[c][r];
+            }
+            saved_tq5 = tq[5];
+        }
+    }
+
+    // cvSetEta (cvodes.c:7798) with eta_min_fx = 0, eta_max_fx = 1.5, hmin = 0
+    AB_HD void set_eta() {
+        if (eta > 0.0 && eta < 1.5) {
+            eta = 1.0;
+            hprime = h;
+        } else {
+            if (eta >= 1.5) {
+                eta = ab_min(eta, etamax);
+                eta /= ab_max(1.0, fabs(h) * o.hmax_inv * eta);
+            } else {
+                eta = ab_max(eta, 0.1);
+            }
+            hprime = h * eta;
+            if (qprime < q) nscon = 0;
+        }
+    }
+
+    // cvPrepareNextStep (cvodes.c:7747) incl. cvComputeEtaqm1/qp1 and cvChooseEta
+    AB_HD void prepare_next_step(double dsm) {
+        if (etamax == 1.0) {
+            qwait = qwait > 2 ? qwait : 2;
+            qprime = q;
+            hprime = h;
+            eta = 1.0;
+            return;
+        }
+        etaq = 1.0 / (pow(6.0 * dsm, 1.0 / L) + 1e-6);
+        if (qwait != 0) {
+            eta = etaq;
+            qprime = q;
+            set_eta();
+            return;
+        }
+        qwait = 2;
+        etaqm1 = 0.0;
+        if (q > 1) {
+            const double ddn = wrms_max_zn(q) * tq[1];
+            etaqm1 = 1.0 / (pow(6.0 * ddn, 1.0 / q) + 1e-6);
+        }
+        etaqp1 = 0.0;
+        if (q != QMAX && saved_tq5 != 0.0) {
+            double ratio = h / tau[2], pw = 1.0;
+            for (int i = 0; i < L; ++i) pw *= ratio;  // SUNRpowerI(h/tau[2], L)
+            const double cquot = (tq[5] / saved_tq5) * pw;
+            double tmp[C][NX];
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r)
+                    tmp[c][r] = active(c) ? acor[c][r] - cquot * S.zn[QMAX][r][col(c)] : 0.0;
+            }
+            const double dup = wrms_max(tmp) * tq[3];
+            etaqp1 = 1.0 / (pow(10.0 * dup, 1.0 / (L + 1)) + 1e-6);
+        }
+        // cvChooseEta (cvodes.c:7935)
+        const double etam = ab_max(etaqm1, ab_max(etaq, etaqp1));
+        if (etam > 0.0 && etam < 1.5) {
+            eta = 1.0;
+            qprime = q;
+        } else if (etam == etaq) {
+            eta = etaq;
+            qprime = q;
+        } else if (etam == etaqm1) {
+            eta = etaqm1;
+            qprime = q - 1;
+        } else {
+            eta = etaqp1;
+            qprime = q + 1;
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                if (!active(c)) continue;
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) S.zn[QMAX][r][col(c)] = acor[c][r];
+            }
+        }
+        set_eta();
+    }
+
+    // cvSLdet (cvodes.c:8256); scalar code on the shared ssdat history
+    AB_HD_NOINLINE int sldet() const {
+        const double TINY_ = 1e-10;
+        double rat[5][4], rav[4], qkr[4], sigsq[4], smax[4], ssmax[4];
+        double drr[4], rrc[4], sqmx[4], qjk[4][4], vrat[5], qc[6][4], qco[6][4];
+        const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
+        double rr = 0.0, sqmin = 0.0;
+        int kflag = 0, kmin = 0;
+        for (int kk = 1; kk <= 3; kk++) {
+            double smink = S.ssdat[1][kk], smaxk = 0.0;
+            for (int i = 1; i <= 5; i++) {
+                smink = ab_min(smink, S.ssdat[i][kk]);
+                smaxk = ab_max(smaxk, S.ssdat[i][kk]);
+            }
+            if (smink < TINY_ * smaxk) return -1;
+            smax[kk] = smaxk;
+            ssmax[kk] = smaxk * smaxk;
+            double sumrat = 0.0, sumrsq = 0.0;
+            for (int i = 1; i <= 4; i++) {
+                rat[i][kk] = S.ssdat[i][kk] / S.ssdat[i + 1][kk];
+                sumrat += rat[i][kk];
+                sumrsq += rat[i][kk] * rat[i][kk];
+            }
+            rav[kk] = 0.25 * sumrat;
+            vrat[kk] = fabs(0.25 * sumrsq - rav[kk] * rav[kk]);
+            qc[5][kk] = S.ssdat[1][kk] * S.ssdat[3][kk] - S.ssdat[2][kk] * S.ssdat[2][kk];
+            qc[4][kk] = S.ssdat[2][kk] * S.ssdat[3][kk] - S.ssdat[1][kk] * S.ssdat[4][kk];
+            qc[3][kk] = 0.0;
+            qc[2][kk] = S.ssdat[2][kk] * S.ssdat[5][kk] - S.ssdat[3][kk] * S.ssdat[4][kk];
+            qc[1][kk] = S.ssdat[4][kk] * S.ssdat[4][kk] - S.ssdat[3][kk] * S.ssdat[5][kk];
+            for (int i = 1; i <= 5; i++) qco[i][kk] = qc[i][kk];
+        }
+        const double vmin = ab_min(vrat[1], ab_min(vrat[2], vrat[3]));
+        const double vmax = ab_max(vrat[1], ab_max(vrat[2], vrat[3]));
+        if (vmin < vrrtol * vrrtol) {
+            if (vmax > vrrt2 * vrrt2) return -2;
+            rr = (rav[1] + rav[2] + rav[3]) / 3.0;
+            double drrmax = 0.0;
+            for (int kk = 1; kk <= 3; kk++) drrmax = ab_max(drrmax, fabs(rav[kk] - rr));
+            if (drrmax > vrrt2) return -3;
+            kflag = 1;
+        } else {
+            if (fabs(qco[1][1]) < TINY_ * ssmax[1]) return -4;
+            double tem = qco[1][2] / qco[1][1];
+            for (int i = 2; i <= 5; i++) qco[i][2] -= tem * qco[i][1];
+            qco[1][2] = 0.0;
+            tem = qco[1][3] / qco[1][1];
+            for (int i = 2; i <= 5; i++) qco[i][3] -= tem * qco[i][1];
+            qco[1][3] = 0.0;
+            if (fabs(qco[2][2]) < TINY_ * ssmax[2]) return -4;
+            tem = qco[2][3] / qco[2][2];
+            for (int i = 3; i <= 5; i++) qco[i][3] -= tem * qco[i][2];
+            if (fabs(qco[4][3]) < TINY_ * ssmax[3]) return -4;
+            rr = -qco[5][3] / qco[4][3];
+            if (rr < TINY_ || rr > 100.0) return -5;
+            for (int kk = 1; kk <= 3; kk++)
+                qkr[kk] = qc[5][kk] + rr * (qc[4][kk] + rr * rr * (qc[2][kk] + rr * qc[1][kk]));
+            double sqmax = 0.0;
+            for (int kk = 1; kk <= 3; kk++) {
+                const double saqk = fabs(qkr[kk]) / ssmax[kk];
+                if (saqk > sqmax) sqmax = saqk;
+            }
+            if (sqmax < sqtol) {
+                kflag = 2;
+            } else {
+                for (int it = 1; it <= 3; it++) {
+                    for (int kk = 1; kk <= 3; kk++) {
+                        const double qp = qc[4][kk] + rr * rr * (3.0 * qc[2][kk] + rr * 4.0 * qc[1][kk]);
+                        drr[kk] = 0.0;
+                        if (fabs(qp) > TINY_ * ssmax[kk]) drr[kk] = -qkr[kk] / qp;
+                        rrc[kk] = rr + drr[kk];
+                    }
+                    for (int kk = 1; kk <= 3; kk++) {
+                        const double s = rrc[kk];
+                        double sqmaxk = 0.0;
+                        for (int j = 1; j <= 3; j++) {
+                            qjk[j][kk] = qc[5][j] + s * (qc[4][j] + s * s * (qc[2][j] + s * qc[1][j]));
+                            const double saqj = fabs(qjk[j][kk]) / ssmax[j];
+                            if (saqj > sqmaxk) sqmaxk = saqj;
+                        }
+                        sqmx[kk] = sqmaxk;
+                    }
+                    sqmin = sqmx[1] + 1.0;
+                    for (int kk = 1; kk <= 3; kk++)
+                        if (sqmx[kk] < sqmin) {
+                            kmin = kk;
+                            sqmin = sqmx[kk];
+                        }
+                    rr = rrc[kmin];
+                    if (sqmin < sqtol) {
+                        kflag = 3;
+                        break;
+                    }
+                    for (int j = 1; j <= 3; j++) qkr[j] = qjk[j][kmin];
+                }
+                if (sqmin > sqtol) return -6;
+            }
+        }
+        for (int kk = 1; kk <= 3; kk++) {
+            const double rsa = S.ssdat[1][kk], rsb = S.ssdat[2][kk] * rr, rsc = S.ssdat[3][kk] * rr * rr;
+            const double rsd = S.ssdat[4][kk] * rr * rr * rr;
+            const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
+            const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c, rd3a = rd2a - rd2b;
+            if (fabs(rd1b) < TINY_ * smax[kk]) return -7;
+            const double cest1 = -rd3a / rd1b;
+            if (cest1 < TINY_ || cest1 > 4.0) return -7;
+            const double corr1 = (rd2b / cest1) / (rr * rr);
+            sigsq[kk] = S.ssdat[3][kk] + corr1;
+        }
+        if (sigsq[2] < TINY_) return -8;
+        const double ratp = sigsq[3] / sigsq[2], ratm = sigsq[1] / sigsq[2];
+        const double qfac1 = 0.25 * (q * q - 1.0), qfac2 = 2.0 / (q - 1.0);
+        const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
+        const double tem = 1.0 - qfac2 * bb;
+        if (fabs(tem) < TINY_) return -8;
+        const double rrb = 1.0 / tem;
+        if (fabs(rrb - rr) > rrtol) return -9;
+        if (rr > rrcut) {
+            if (kflag == 1) kflag = 4;
+            if (kflag == 2) kflag = 5;
+            if (kflag == 3) kflag = 6;
+        }
+        return kflag;
+    }
+
+    // cvBDFStab (cvodes.c:8158)
+    AB_HD void bdf_stab() {
+        if (q >= 3) {
+            double factorial = 1.0;
+            for (int i = 1; i <= q - 1; i++) factorial *= i;
+            const double sq = factorial * q * (q + 1) * acnrm / ab_max(tq[5], 1e-10);
+            const double sqm1 = factorial * q * wrms_state_zn(q);
+            const double sqm2 = factorial * wrms_state_zn(q - 1);
+            g.sync();
+            if (g.lane == 0) {
+                for (int kk = 1; kk <= 3; kk++)
+                    for (int i = 5; i >= 2; i--) S.ssdat[i][kk] = S.ssdat[i - 1][kk];
+                S.ssdat[1][1] = sqm2 * sqm2;
+                S.ssdat[1][2] = sqm1 * sqm1;
+                S.ssdat[1][3] = sq * sq;
+            }
+            g.sync();
+        }
+        if (qprime >= q) {
+            if (q >= 3 && nscon >= q + 5) {
+                const int ldflag = sldet();
+                if (ldflag > 3) {
+                    qprime = q - 1;
+                    eta = etaqm1;
+                    eta = ab_min(eta, etamax);
+                    eta = eta / ab_max(1.0, fabs(h) * o.hmax_inv * eta);
+                    hprime = h * eta;
+                }
+            }
+        } else {
+            nscon = 0;
+        }
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // cvStep (cvodes.c:5800)
+    // -----------------------------------------------------------------------------------------
+    AB_HD int step() {
+        const double saved_t = tn;
+        int ncf = 0, nef = 0, nflag = FIRST_CALL;
+        double dsm = 0.0;
+        if (nst > 0 && hprime != h) adjust_params();
+        for (;;) {
+            // cvPredict
+            tn += h;
+            if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
+            pascal(1.0);
+            set_coeffs();
+            nflag = nls(nflag);
+            const int kflag = handle_nflag(nflag, saved_t, ncf);
+            if (kflag == 1) continue;
+            if (kflag < 0) return kflag;
+            const int eflag = do_error_test(nflag, saved_t, nef, dsm);
+            if (eflag == 1) continue;
+            if (eflag < 0) return eflag;
+            break;
+        }
+        complete_step();
+        prepare_next_step(dsm);
+        if (o.stldet) bdf_stab();
+        etamax = 10.0;  // eta_max_es == eta_max_gs == 10
+        return AB_SUCCESS;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // initial step size: cvHin / cvUpperBoundH0 / cvYddNorm (cvodes.c:5436-5798)
+    // -----------------------------------------------------------------------------------------
+    AB_HD int hin(double tout) {
+        const double tdiff = tout - tn;
+        if (tdiff == 0.0) return AB_TOO_CLOSE;
+        const double sign = tdiff > 0.0 ? 1.0 : -1.0;
+        const double tdist = fabs(tdiff);
+        const double tround = DBL_EPSILON * ab_max(fabs(tn), fabs(tout));
+        if (tdist < 2.0 * tround) return AB_TOO_CLOSE;
+        const double hlb = 100.0 * tround;
+        // cvUpperBoundH0
+        double hub_inv = 0.0;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                const double den = 0.1 * fabs(S.zn[0][r][col(c)]) + 1.0 / ewt[c][r];
+                const double v = fabs(S.zn[1][r][col(c)]) / den;
+                hub_inv = (v > hub_inv || v != v) ? v : hub_inv;
+            }
+        }
+        hub_inv = g.max(hub_inv);
+        double hub = 0.1 * tdist;
+        if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
+        double hg = sqrt(hlb * hub);
+        if (hub < hlb) {
+            h = sign * hg;
+            return AB_SUCCESS;
+        }
+        double hs = hg, hnew = hg;
+        for (int count1 = 1; count1 <= 4; count1++) {
+            bool hgOK = false;
+            double yddnrm = 0.0;
+            for (int count2 = 1; count2 <= 4; count2++) {
+                const double hgs = hg * sign;
+                // cvYddNorm
+                ModelEval e;
+                double yy[C][NX], f[C][NX];
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r)
+                        yy[c][r] = active(c) ? hgs * S.zn[1][r][col(c)] + S.zn[0][r][col(c)] : 0.0;
+                }
+                const bool ok = rhs(tn + hgs, yy, f, e);
+                if (ok) {
+                    AB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r)
+                            f[c][r] = active(c) ? (1.0 / hgs) * f[c][r] - (1.0 / hgs) * S.zn[1][r][col(c)] : 0.0;
+                    }
+                    yddnrm = wrms_max(f);
+                    hgOK = true;
+                    break;
+                }
+                hg *= 0.2;
+            }
+            if (!hgOK) {
+                if (count1 <= 2) return AB_REPTD_RHSFUNC_ERR;
+                hnew = hs;
+                break;
+            }
+            hs = hg;
+            hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
+            if (count1 == 4) break;
+            const double hrat = hnew / hg;
+            if (hrat > 0.5 && hrat < 2.0) break;
+            if (count1 > 1 && hrat > 2.0) {
+                hnew = hg;
+                break;
+            }
+            hg = hnew;
+        }
+        double h0 = 0.5 * hnew;
+        if (h0 < hlb) h0 = hlb;
+        if (h0 > hub) h0 = hub;
+        h = sign * h0;
+        return AB_SUCCESS;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // solver (re-)initialisation: Solver::setup -> CVodeInit/CVodeSensInit1 (reference src/solver.cpp:193-265);
+    // zn[0] must hold the initial state and sensitivities
+    // -----------------------------------------------------------------------------------------
+    AB_HD void init(double t0) {
+        tn = t0;
+        q = 1; L = 2; qwait = 2; qprime = 1; qu = 0;
+        etamax = 1e4;  // eta_max_fs
+        h = hscale = hprime = hu = 0.0;
+        eta = 1.0;
+        nst = nstlp = nstlj = nscon = nfe = netf = ncfn = nni = nsetups = nje = 0;
+        for (int i = 0; i <= LMAX; ++i) tau[i] = 0.0;
+        for (int i = 0; i < LMAX; ++i) l[i] = 0.0;
+        for (int i = 0; i < 6; ++i) tq[i] = 0.0;
+        rl1 = gamma = gammap = gamrat = 1.0;
+        crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5 = 0.0;
+        etaq = etaqm1 = etaqp1 = 0.0;
+        tstopset = false; tstop = 0.0; tretlast = t0;
+        convfail = CONVFAIL_NONE; jcur = false;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) { acor[c][r] = 0.0; ewt[c][r] = 0.0; }
+        }
+        g.sync();
+        if (g.lane == 0)
+            for (int i = 0; i < 6; ++i)
+                for (int kk = 0; kk < 4; ++kk) S.ssdat[i][kk] = 0.0;
+        g.sync();
+        set_ewt();  // cvInitialSetup
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // CVode(tout, CV_NORMAL) with tstop = tout, as AMICI's Solver::run drives it
+    // (reference src/solver.cpp:141-160; cvodes.c:2890-3650). Returns AB_TSTOP_RETURN or an error.
+    // -----------------------------------------------------------------------------------------
+    AB_HD int solve_to(double tout) {
+        // Solver::apply_max_num_steps (reference src/solver.cpp:107-119)
+        if (o.maxsteps <= nst) return AB_ERROR;
+        const int mxstep = o.maxsteps - nst;
+        tstop = tout;
+        tstopset = true;
+        if (nst == 0) {
+            // first call: zn[1] = h * f(t0, y0) (cvodes.c first-call block)
+            {
+                ModelEval e;
+                double y0[C][NX], f[C][NX];
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) y0[c][r] = active(c) ? S.zn[0][r][col(c)] : 0.0;
+                }
+                if (!rhs(tn, y0, f, e)) return AB_FIRST_RHSFUNC_ERR;
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] = f[c][r];
+                }
+            }
+            if ((tstop - tn) * (tout - tn) <= 0.0) return AB_ILL_INPUT;
+            const int hflag = hin(tout);
+            if (hflag != AB_SUCCESS) return hflag;
+            const double rh = fabs(h) * o.hmax_inv;
+            if (rh > 1.0) h /= rh;
+            if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+            hscale = h;
+            hprime = h;
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                if (!active(c)) continue;
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] *= h;
+            }
+        } else {
+            const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
+            if (fabs(tn - tstop) <= troundoff) {
+                tretlast = tstop;
+                tstopset = false;
+                return AB_TSTOP_RETURN;
+            } else if ((tn + hprime - tstop) * h > 0.0) {
+                hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+                eta = hprime / h;
+            }
+        }
+        int nstloc = 0;
+        for (;;) {
+            if (nst > 0) set_ewt();
+            if (nstloc >= mxstep) { tretlast = tn; return AB_TOO_MUCH_WORK; }
+            const double nrm = wrms_max_zn(0);
+            if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; return AB_TOO_MUCH_ACC; }
+            const int kflag = step();
+            if (kflag != AB_SUCCESS) { tretlast = tn; return kflag; }
+            nstloc++;
+            const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
+            if (fabs(tn - tstop) <= troundoff) {
+                tn = tstop;
+                tretlast = tstop;
+                tstopset = false;
+                return AB_TSTOP_RETURN;
+            } else if ((tn + hprime - tstop) * h > 0.0) {
+                hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+                eta = hprime / h;
+            }
+        }
+    }
+};
+
+}  // namespace amici_b200
+#endif

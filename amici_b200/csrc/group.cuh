@@ -1,0 +1,81 @@
+// Lane-group primitives.
+//
+// One trajectory is integrated by a group of G lanes of one warp (G = 1, 2, 4, 8, 16, 32);
+// lane g owns the columns g, g+G, ... of the stacked (state | sensitivities) system.
+// All scalar step-control logic is executed redundantly and identically by every lane
+// of a group, so the only communication is: broadcast of the state column, max-reduction
+// of the per-column WRMS norms, and visibility of the group's shared-memory slice.
+// Different groups inside one warp may diverge freely (independent thread scheduling);
+// every collective below names the group's own lane mask.
+//
+// With G == 1 all collectives are the identity, which is also how the same solver source is
+// compiled for the host in tests/cpu_emul (an algorithm check that runs without a GPU).
+#ifndef AMICI_B200_GROUP_CUH
+#define AMICI_B200_GROUP_CUH
+#include "model_common.cuh"
+
+namespace amici_b200 {
+
+template <int G>
+struct Group {
+    static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
+    int lane;        // lane index inside the group
+    unsigned mask;   // warp mask of the group's lanes
+
+    AB_HD Group() : lane(0), mask(1u) {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) {
+            const int wl = threadIdx.x & 31;
+            lane = wl & (G - 1);
+            mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(G - 1)));
+        }
+#endif
+    }
+
+    AB_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) __syncwarp(mask);
+#endif
+    }
+
+    AB_HD double max(double v) const {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) {
+            AB_UNROLL
+            for (int off = G / 2; off > 0; off >>= 1) {
+                const double o = __shfl_xor_sync(mask, v, off, G);
+                v = (o > v || o != o) ? o : v;   // NaN-propagating, so every lane ends with the same value
+            }
+        }
+#endif
+        return v;
+    }
+
+    AB_HD double bcast(double v, int src) const {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) v = __shfl_sync(mask, v, src, G);
+#else
+        (void)src;
+#endif
+        return v;
+    }
+
+    AB_HD int bcast(int v, int src) const {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) v = __shfl_sync(mask, v, src, G);
+#else
+        (void)src;
+#endif
+        return v;
+    }
+
+    AB_HD bool any(bool p) const {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) return (__ballot_sync(mask, p) & mask) != 0u;
+#endif
+        return p;
+    }
+};
+
+}  // namespace amici_b200
+#endif

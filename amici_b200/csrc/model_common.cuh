@@ -1,0 +1,53 @@
+// Common macros for code shared between the CUDA kernels and the host-compiled
+// lane-group emulation used by the CPU unit tests (tests/cpu_emul).
+#ifndef AMICI_B200_MODEL_COMMON_CUH
+#define AMICI_B200_MODEL_COMMON_CUH
+
+#include <cmath>
+#include <cfloat>
+
+#if defined(__CUDACC__)
+#define AB_HD __host__ __device__ __forceinline__
+#define AB_HD_NOINLINE __host__ __device__ __noinline__
+#define AB_UNROLL _Pragma("unroll")
+#else
+#define AB_HD inline
+#define AB_HD_NOINLINE
+#define AB_UNROLL
+#endif
+
+namespace amici_b200 {
+
+// status / return codes: numeric values of the reference (include/amici/defines.h:64-101),
+// which are SUNDIALS' CV_* codes (static_asserts in src/solver_cvodes.cpp:40-61).
+enum : int {
+    AB_SUCCESS = 0,
+    AB_TSTOP_RETURN = 1,
+    AB_ROOT_RETURN = 2,
+    AB_TOO_MUCH_WORK = -1,
+    AB_TOO_MUCH_ACC = -2,
+    AB_ERR_FAILURE = -3,
+    AB_CONV_FAILURE = -4,
+    AB_LSETUP_FAIL = -6,
+    AB_RHSFUNC_FAIL = -8,
+    AB_FIRST_RHSFUNC_ERR = -9,
+    AB_REPTD_RHSFUNC_ERR = -10,
+    AB_UNREC_RHSFUNC_ERR = -11,
+    AB_ILL_INPUT = -22,
+    AB_TOO_CLOSE = -27,
+    AB_ERROR = -99,
+    AB_NOT_RUN = -1001,
+};
+
+// parameter scaling (reference include/amici/defines.h ParameterScaling)
+enum : int { AB_PSCALE_NONE = 0, AB_PSCALE_LN = 1, AB_PSCALE_LOG10 = 2 };
+
+#if !defined(__CUDACC__)
+using std::isfinite;
+#endif
+
+AB_HD double ab_max(double a, double b) { return a > b ? a : b; }
+AB_HD double ab_min(double a, double b) { return a < b ? a : b; }
+
+}  // namespace amici_b200
+#endif

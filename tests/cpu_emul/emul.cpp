@@ -1,0 +1,35 @@
+// tests/cpu_emul/emul.cpp — TEST INFRASTRUCTURE, never loaded by the product.
+//
+// Compiles the solver source (amici_b200/csrc/*.cuh) for the host with a lane-group of one
+// lane that owns every column, so the step-control logic can be checked against the compiled
+// reference on machines without a GPU.  The product path is the CUDA build of the same source.
+#include "../../amici_b200/csrc/simulate.cuh"
+#include "../../amici_b200/csrc/models/jakstat_adjoint.cuh"
+#include "../../amici_b200/csrc/models/robertson_ode.cuh"
+#include "../../amici_b200/csrc/models/steadystate.cuh"
+
+#include <memory>
+#include <string>
+
+using namespace amici_b200;
+
+template <class M>
+static int run_model(const SolverOptions* o, const BatchView* b) {
+    constexpr int NC = M::NP + 1;
+    using Sim = Simulation<M, 1, NC>;
+    auto S = std::make_unique<typename Sim::Shared>();
+    if (o->sensi >= 1 && b->nplist + 1 > NC) return -1;
+    for (int n = 0; n < b->N; ++n) {
+        Sim sim(*S, *o, *b, n);
+        sim.run();
+    }
+    return 0;
+}
+
+extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchView* b) {
+    std::string m(model);
+    if (m == "jakstat_adjoint") return run_model<models::jakstat_adjoint>(o, b);
+    if (m == "steadystate") return run_model<models::steadystate>(o, b);
+    if (m == "robertson_ode") return run_model<models::robertson_ode>(o, b);
+    return -2;
+}
