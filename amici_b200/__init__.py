@@ -1,0 +1,501 @@
+"""amici_b200 — host-side mirror of ``amici.sim.sundials`` for the batched CUDA BDF engine.
+
+The classes and functions here keep the names and argument meaning of the reference's Python
+layer for the one path this package replaces:
+
+* ``run_simulations(model, solver, edata_list, failfast=True, num_threads=1)`` and
+  ``run_simulation`` (reference python/sdist/amici/sim/sundials/_swig_wrappers.py:46-133),
+* ``Model`` / ``Solver`` / ``ExpData`` setters and getters that parametrise that call (reference
+  include/amici/model.h, include/amici/solver.h:1869-2127, include/amici/edata.h),
+* ``ReturnDataView`` field names and shapes (reference python/sdist/amici/sim/sundials/_numpy.py:414-459).
+
+There is no CPU fallback: everything routes through the C ABI of ``lib/libamici_b200.so``
+(include/amici_b200.h) and raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+import os
+from typing import Sequence
+
+import numpy as np
+
+from . import _capi
+
+__all__ = [
+    "Model", "Solver", "ExpData", "ExpDataBatch", "ReturnDataView", "BatchResult", "run_simulation",
+    "run_simulations", "runAmiciSimulations", "runAmiciSimulation", "SensitivityOrder", "SensitivityMethod",
+    "InternalSensitivityMethod", "ParameterScaling", "RDataReporting", "LinearSolver", "get_model",
+    "available_models", "load_library", "AMICI_SUCCESS",
+]
+
+AMICI_SUCCESS = 0
+AMICI_NOT_RUN = -1001
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libamici_b200.so")
+_lib = None
+
+
+class SensitivityOrder(enum.IntEnum):
+    none = 0
+    first = 1
+    second = 2
+
+
+class SensitivityMethod(enum.IntEnum):
+    none = 0
+    forward = 1
+    adjoint = 2
+
+
+class InternalSensitivityMethod(enum.IntEnum):
+    simultaneous = 1
+    staggered = 2
+    staggered1 = 3
+
+
+class ParameterScaling(enum.IntEnum):
+    none = 0
+    ln = 1
+    log10 = 2
+
+
+class RDataReporting(enum.IntEnum):
+    full = 0
+    residuals = 1
+    likelihood = 2
+    observables_likelihood = 3
+
+
+class LinearSolver(enum.IntEnum):
+    dense = 1
+    KLU = 9
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA engine; fails loudly when it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} is missing: build the CUDA engine first (__graft_entry__.build()); "
+                           "amici_b200 has no CPU fallback")
+    lib = C.CDLL(_LIB_PATH)
+    lib.ab_model_count.restype = C.c_int
+    lib.ab_model_name.restype = C.c_char_p
+    lib.ab_model_name.argtypes = [C.c_int]
+    lib.ab_get_dims.argtypes = [C.c_char_p, C.c_void_p]
+    lib.ab_get_nominal.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
+    lib.ab_run_batch.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.ab_solve_device.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ab_reduce_objective.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ab_kernel_launch_count.restype = C.c_long
+    lib.ab_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class _Dims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nx", "np", "nk", "ny", "nz", "ne", "nspl", "group_lanes", "cols_per_lane")]
+
+
+def available_models() -> list[str]:
+    lib = load_library()
+    return [lib.ab_model_name(i).decode() for i in range(lib.ab_model_count())]
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"amici_b200: error {rc}: {load_library().ab_last_error().decode()}")
+
+
+class Model:
+    """Counterpart of ``amici.Model`` for a model compiled into the engine (settings container)."""
+
+    def __init__(self, name: str):
+        lib = load_library()
+        d = _Dims()
+        _check(lib.ab_get_dims(name.encode(), C.byref(d)))
+        self.name = name
+        self.nx_rdata = self.nx_solver = self.nx = d.nx
+        self._np, self._nk = d.np, d.nk
+        self.ny = self.nytrue = d.ny
+        self.nz, self.ne, self.nspl = d.nz, d.ne, d.nspl
+        self.group_lanes, self.cols_per_lane = d.group_lanes, d.cols_per_lane
+        p = np.zeros(max(d.np, 1))
+        k = np.zeros(max(d.nk, 1))
+        _check(lib.ab_get_nominal(name.encode(), p.ctypes.data, k.ctypes.data))
+        self._pscale = [ParameterScaling.none] * d.np
+        self._p = list(p[: d.np])   # on parameter scale
+        self._k = list(k[: d.nk])
+        self._ts: list[float] = []
+        self._plist = list(range(d.np))
+        self._t0 = 0.0
+
+    # -- dimensions
+    def np(self) -> int: return self._np
+    def nk(self) -> int: return self._nk
+    def nplist(self) -> int: return len(self._plist)
+    def nt(self) -> int: return len(self._ts)
+    def dims(self) -> dict: return dict(nx=self.nx, np=self._np, nk=self._nk, ny=self.ny)
+
+    # -- settings (reference include/amici/model.h)
+    def set_timepoints(self, ts: Sequence[float]):
+        ts = [float(t) for t in ts]
+        if any(b < a for a, b in zip(ts, ts[1:])):
+            raise RuntimeError("Encountered non-monotonic timepoints, please order timepoints such that they are monotonically increasing!")
+        self._ts = ts
+    def get_timepoints(self): return list(self._ts)
+    def set_t0(self, t0: float): self._t0 = float(t0)
+    def t0(self): return self._t0
+    def set_parameter_list(self, plist: Sequence[int]):
+        plist = [int(i) for i in plist]
+        if any(i < 0 or i >= self._np for i in plist):
+            raise RuntimeError("Indices in plist must be in [0..np]")
+        self._plist = plist
+    def get_parameter_list(self): return list(self._plist)
+    def set_parameter_scale(self, pscale):
+        if isinstance(pscale, (int, enum.IntEnum)):
+            pscale = [pscale] * self._np
+        if len(pscale) != self._np:
+            raise RuntimeError("Dimension mismatch. Size of parameter scaling does not match number of model parameters.")
+        # keep unscaled values fixed, as Model::set_parameter_scale does
+        un = self.get_unscaled_parameters()
+        self._pscale = [ParameterScaling(int(s)) for s in pscale]
+        self._p = [_scale(v, s) for v, s in zip(un, self._pscale)]
+    def get_parameter_scale(self): return list(self._pscale)
+    def set_free_parameters(self, p):
+        if len(p) != self._np:
+            raise RuntimeError("Dimension mismatch. Size of parameters does not match number of model parameters.")
+        self._p = [float(v) for v in p]
+    def get_free_parameters(self): return list(self._p)
+    def get_unscaled_parameters(self): return [_unscale(v, s) for v, s in zip(self._p, self._pscale)]
+    def set_fixed_parameters(self, k):
+        if len(k) != self._nk:
+            raise RuntimeError("Dimension mismatch. Size of fixedParameters does not match number of fixed model parameters.")
+        self._k = [float(v) for v in k]
+    def get_fixed_parameters(self): return list(self._k)
+    def create_solver(self) -> "Solver": return Solver()
+    def get_name(self): return self.name
+    def clone(self) -> "Model":
+        import copy
+        return copy.deepcopy(self)
+
+
+def _unscale(v, s):
+    return 10.0 ** v if s == ParameterScaling.log10 else math.exp(v) if s == ParameterScaling.ln else v
+
+
+def _scale(v, s):
+    return math.log10(v) if s == ParameterScaling.log10 else math.log(v) if s == ParameterScaling.ln else v
+
+
+def get_model(name: str) -> Model:
+    """Counterpart of the generated module's ``get_model()`` (reference models/*/wrapfunctions.cpp)."""
+    return Model(name)
+
+
+class Solver:
+    """Settings of the batched BDF solver; setters/defaults follow ``amici::Solver`` (reference include/amici/solver.h:1869-2127)."""
+
+    def __init__(self):
+        self._rtol, self._atol = 1e-8, 1e-16
+        self._rtol_fsa = self._atol_fsa = float("nan")
+        self._sensi = SensitivityOrder.none
+        self._sensi_meth = SensitivityMethod.forward
+        self._ism = InternalSensitivityMethod.simultaneous
+        self._maxsteps = 10000
+        self._stldet = True
+        self._max_nonlin_iters, self._max_conv_fails = 3, 10
+        self._max_step_size = 0.0
+        self._reporting = RDataReporting.full
+        self._linsol = LinearSolver.KLU
+
+    @staticmethod
+    def _nonneg(v, what):
+        if v < 0:
+            raise RuntimeError(f"{what} must be a non-negative number")
+        return float(v)
+
+    def set_relative_tolerance(self, v): self._rtol = self._nonneg(v, "rtol")
+    def get_relative_tolerance(self): return self._rtol
+    def set_absolute_tolerance(self, v): self._atol = self._nonneg(v, "atol")
+    def get_absolute_tolerance(self): return self._atol
+    def set_relative_tolerance_fsa(self, v): self._rtol_fsa = self._nonneg(v, "rtol")
+    def get_relative_tolerance_fsa(self): return self._rtol if math.isnan(self._rtol_fsa) else self._rtol_fsa
+    def set_absolute_tolerance_fsa(self, v): self._atol_fsa = self._nonneg(v, "atol")
+    def get_absolute_tolerance_fsa(self): return self._atol if math.isnan(self._atol_fsa) else self._atol_fsa
+    def set_sensitivity_order(self, v): self._sensi = SensitivityOrder(int(v))
+    def get_sensitivity_order(self): return self._sensi
+    def set_sensitivity_method(self, v):
+        v = SensitivityMethod(int(v))
+        if v == SensitivityMethod.adjoint:
+            raise RuntimeError("amici_b200: adjoint sensitivities are outside the batched forward path")
+        self._sensi_meth = v
+    def get_sensitivity_method(self): return self._sensi_meth
+    def set_internal_sensitivity_method(self, v):
+        v = InternalSensitivityMethod(int(v))
+        if v != InternalSensitivityMethod.simultaneous:
+            raise RuntimeError("amici_b200: only InternalSensitivityMethod.simultaneous is implemented")
+        self._ism = v
+    def get_internal_sensitivity_method(self): return self._ism
+    def set_max_steps(self, v):
+        if v <= 0:
+            raise RuntimeError("maxsteps must be a positive number")
+        self._maxsteps = int(v)
+    def get_max_steps(self): return self._maxsteps
+    def set_stability_limit_flag(self, v): self._stldet = bool(v)
+    def get_stability_limit_flag(self): return self._stldet
+    def set_max_nonlin_iters(self, v):
+        if v < 0:
+            raise RuntimeError("max_nonlin_iters must be non-negative")
+        self._max_nonlin_iters = int(v)
+    def get_max_nonlin_iters(self): return self._max_nonlin_iters
+    def set_max_conv_fails(self, v):
+        if v < 0:
+            raise RuntimeError("max_conv_fails must be non-negative")
+        self._max_conv_fails = int(v)
+    def get_max_conv_fails(self): return self._max_conv_fails
+    def set_max_step_size(self, v):
+        if v < 0:
+            raise RuntimeError("max_step_size must be non-negative.")
+        self._max_step_size = float(v)
+    def get_max_step_size(self): return self._max_step_size
+    def set_return_data_reporting_mode(self, v):
+        v = RDataReporting(int(v))
+        if v not in (RDataReporting.full, RDataReporting.likelihood):
+            raise RuntimeError("amici_b200: reporting modes implemented: full, likelihood")
+        self._reporting = v
+    def get_return_data_reporting_mode(self): return self._reporting
+    def set_linear_solver(self, v): self._linsol = LinearSolver(int(v))  # accepted; the engine always uses its batched LU
+    def get_linear_solver(self): return self._linsol
+    def clone(self):
+        import copy
+        return copy.deepcopy(self)
+
+    def _options(self, t0: float) -> _capi.SolverOptions:
+        fsa = self._sensi >= SensitivityOrder.first and self._sensi_meth == SensitivityMethod.forward
+        if self._sensi >= SensitivityOrder.second:
+            raise RuntimeError("amici_b200: second-order sensitivities are not implemented")
+        return _capi.default_options(
+            rtol=self._rtol, atol=self._atol, rtol_fsa=self.get_relative_tolerance_fsa(),
+            atol_fsa=self.get_absolute_tolerance_fsa(), t0=t0,
+            hmax_inv=(1.0 / self._max_step_size if self._max_step_size > 0 else 0.0), sensi=1 if fsa else 0,
+            ism=int(self._ism), maxsteps=self._maxsteps, stldet=int(self._stldet),
+            max_nonlin_iters=self._max_nonlin_iters, max_conv_fails=self._max_conv_fails, max_err_test_fails=7,
+            reporting=int(self._reporting))
+
+
+class ExpData:
+    """One experimental condition (``amici::ExpData``, reference include/amici/edata.h:20)."""
+
+    def __init__(self, model: Model):
+        self._ny = model.ny
+        self.ts_ = model.get_timepoints()
+        self.free_parameters: list[float] = []   # empty = use the model's
+        self.fixed_parameters: list[float] = []
+        self.pscale: list = []
+        self.plist: list[int] = []
+        n = len(self.ts_) * self._ny
+        self._my = np.full(n, np.nan)
+        self._sigmay = np.full(n, np.nan)
+
+    def nt(self): return len(self.ts_)
+    def set_timepoints(self, ts):
+        self.ts_ = [float(t) for t in ts]
+        n = len(self.ts_) * self._ny
+        self._my = np.full(n, np.nan)
+        self._sigmay = np.full(n, np.nan)
+    def get_timepoints(self): return list(self.ts_)
+    def set_measurements(self, my):
+        my = np.asarray(my, dtype=np.float64).ravel()
+        if my.size != self.nt() * self._ny:
+            raise RuntimeError(f"Input observedData did not match dimensions nt ({self.nt()}) x nytrue ({self._ny}), was {my.size}.")
+        self._my = my.copy()
+    def get_measurements(self): return self._my.copy()
+    def set_noise_scales(self, s):
+        s = np.asarray(s, dtype=np.float64).ravel()
+        if s.size == 1:
+            s = np.full(self.nt() * self._ny, float(s[0]))
+        if s.size != self.nt() * self._ny:
+            raise RuntimeError(f"Input observedDataStdDev did not match dimensions nt ({self.nt()}) x nytrue ({self._ny}), was {s.size}.")
+        if np.any(s[~np.isnan(s)] <= 0):
+            raise RuntimeError("Encountered sigma <= 0 in sigmay! value: %g" % float(s[~np.isnan(s)].min()))
+        self._sigmay = s.copy()
+    def get_noise_scales(self): return self._sigmay.copy()
+
+
+class ExpDataBatch:
+    """Struct-of-arrays form of ``list[ExpData]`` for conditions that share ts / plist / pscale.
+
+    This is what the C ABI consumes (``ab_batch``); ``run_simulations`` builds it from a list of
+    ``ExpData`` or accepts it directly, which avoids one Python object per condition for large batches.
+    """
+
+    def __init__(self, ts, p, k, my=None, sigmay=None, plist=None, pscale=None):
+        self.ts = np.ascontiguousarray(ts, dtype=np.float64)
+        self.p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
+        self.k = np.ascontiguousarray(np.atleast_2d(k), dtype=np.float64)
+        self.my = None if my is None else np.ascontiguousarray(my, dtype=np.float64)
+        self.sigmay = None if sigmay is None else np.ascontiguousarray(sigmay, dtype=np.float64)
+        self.plist = None if plist is None else np.ascontiguousarray(plist, dtype=np.int32)
+        self.pscale = None if pscale is None else np.ascontiguousarray(pscale, dtype=np.int32)
+
+    def __len__(self): return self.p.shape[0]
+
+    @staticmethod
+    def from_list(model: Model, edatas: Sequence[ExpData | None]) -> "ExpDataBatch":
+        N = len(edatas)
+        ts = None
+        plist = pscale = None
+        p = np.empty((N, model.np()))
+        k = np.empty((N, model.nk()))
+        for i, e in enumerate(edatas):
+            e_ts = model.get_timepoints() if e is None or not e.ts_ else e.ts_
+            e_plist = model.get_parameter_list() if e is None or not e.plist else list(e.plist)
+            e_pscale = [int(s) for s in (model.get_parameter_scale() if e is None or not e.pscale else e.pscale)]
+            if ts is None:
+                ts, plist, pscale = e_ts, e_plist, e_pscale
+            elif list(e_ts) != list(ts) or e_plist != plist or e_pscale != pscale:
+                raise RuntimeError("amici_b200: all conditions of one batch must share timepoints, plist and pscale")
+            p[i] = model.get_free_parameters() if e is None or not len(e.free_parameters) else e.free_parameters
+            k[i] = model.get_fixed_parameters() if e is None or not len(e.fixed_parameters) else e.fixed_parameters
+        nt = len(ts)
+        my = np.full((N, nt, model.ny), np.nan)
+        sg = np.full((N, nt, model.ny), np.nan)
+        for i, e in enumerate(edatas):
+            if e is not None:
+                my[i] = e._my.reshape(nt, model.ny)
+                sg[i] = e._sigmay.reshape(nt, model.ny)
+        return ExpDataBatch(ts, p, k, my, sg, plist, pscale)
+
+
+_RDATA_ALIASES = {"num_rhs_evals": "numrhsevals", "num_err_test_fails": "numerrtestfails",
+                  "num_non_lin_solv_conv_fails": "numnonlinsolvconvfails", "t": "ts"}
+
+
+class BatchResult:
+    """All ReturnData fields of a batch as arrays with the condition index first."""
+
+    def __init__(self, fields: dict, ts, nplist: int, kernel_ms: float | None = None):
+        self.fields = fields
+        self.ts = np.asarray(ts)
+        self.nplist = nplist
+        self.kernel_ms = kernel_ms
+
+    def __getitem__(self, key): return self.fields[_RDATA_ALIASES.get(key, key)]
+    def __contains__(self, key): return _RDATA_ALIASES.get(key, key) in self.fields
+    def __len__(self): return len(self.fields["status"])
+    def view(self, i: int) -> "ReturnDataView": return ReturnDataView(self, i)
+    def views(self) -> list["ReturnDataView"]: return [ReturnDataView(self, i) for i in range(len(self))]
+
+
+class ReturnDataView:
+    """Per-condition view with the reference's field names/shapes (reference _numpy.py:414-459)."""
+
+    def __init__(self, batch: BatchResult, i: int):
+        self._b, self._i = batch, i
+
+    def __getitem__(self, key):
+        key = _RDATA_ALIASES.get(key, key)
+        if key == "ts":
+            return self._b.ts
+        v = self._b.fields[key][self._i]
+        return v.item() if np.ndim(v) == 0 else v
+
+    def __getattr__(self, key):
+        if key.startswith("_"):
+            raise AttributeError(key)
+        try:
+            return self[key]
+        except KeyError as e:
+            raise AttributeError(key) from e
+
+    def keys(self): return ["ts"] + list(self._b.fields.keys())
+    def __contains__(self, key): return key == "ts" or key in self._b
+
+
+def _pinned_empty(shape, dtype):
+    """Host output buffer; page-locked through torch when available so D2H copies run at full PCIe rate."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = torch.float64 if dtype == np.float64 else torch.int32
+            t = torch.empty(tuple(int(s) for s in shape), dtype=tdt, pin_memory=True)
+            a = t.numpy()
+            return a, t
+    except Exception:  # pragma: no cover - pinned memory is an optimisation only
+        pass
+    return np.empty(shape, dtype=dtype), None
+
+
+def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequence[str] | None = None) -> BatchResult:
+    """Run one ``ab_run_batch`` call on host arrays (the drop-in for the reference's batch call)."""
+    lib = load_library()
+    N, nt = len(batch), len(batch.ts)
+    plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist
+    pscale = np.asarray([int(s) for s in model.get_parameter_scale()], dtype=np.int32) if batch.pscale is None else batch.pscale
+    opts = solver._options(model.t0())
+    q = len(plist) if opts.sensi else 0
+    d = model.dims()
+    b = _capi.BatchView(N=N, nt=nt, nplist=len(plist))
+    keep = [batch.ts, batch.p, batch.k, plist, pscale]
+    if batch.p.shape != (N, d["np"]) or batch.k.shape != (N, d["nk"]):
+        raise RuntimeError("amici_b200: parameter array shapes do not match the model")
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    b.ts, b.p, b.k = batch.ts.ctypes.data_as(dp), batch.p.ctypes.data_as(dp), batch.k.ctypes.data_as(dp)
+    b.plist, b.pscale = plist.ctypes.data_as(ip), pscale.ctypes.data_as(ip)
+    if batch.my is not None:
+        b.my = batch.my.ctypes.data_as(dp)
+    if batch.sigmay is not None:
+        b.sigmay_in = batch.sigmay.ctypes.data_as(dp)
+    likelihood_only = opts.reporting == int(RDataReporting.likelihood)
+    lk_fields = {"status", "llh", "chi2", "sllh", "numsteps", "numrhsevals", "numerrtestfails",
+                 "numnonlinsolvconvfails", "order"}
+    out = {}
+    for name, t, shp in _capi.OUT_FIELDS:
+        if fields is not None and name not in fields and name != "status":
+            continue
+        if likelihood_only and name not in lk_fields:
+            continue
+        shape = shp(d, N, nt, q)
+        if q == 0 and name in ("sllh", "sx", "sy", "ssigmay", "sres", "FIM", "sx0"):
+            out[name] = np.zeros(shape)
+            continue
+        a, t_keep = _pinned_empty(shape, np.float64 if t == "d" else np.int32)
+        keep.append(t_keep)
+        out[name] = a
+        setattr(b, name, a.ctypes.data_as(dp if t == "d" else ip))
+    kms = C.c_float(0.0)
+    _check(lib.ab_run_batch(model.name.encode(), C.byref(opts), C.byref(b), C.byref(kms)))
+    res = BatchResult(out, batch.ts, q, float(kms.value))
+    res._keep = keep
+    return res
+
+
+def run_simulations(model: Model, solver: Solver, edata_list, failfast: bool = True, num_threads: int = 1):
+    """Drop-in for ``amici.sim.sundials.run_simulations`` (reference _swig_wrappers.py:87-133).
+
+    ``edata_list`` is a list of ``ExpData`` (returns ``list[ReturnDataView]`` like the reference) or an
+    ``ExpDataBatch`` (returns a ``BatchResult``).  ``num_threads`` is accepted for signature
+    compatibility; the batch runs on the current CUDA device.  ``failfast``: the whole batch is
+    integrated concurrently, so — as in the reference with several threads (src/amici.cpp:246-260) —
+    which conditions are skipped after a failure is not deterministic there; here none are skipped.
+    """
+    del failfast, num_threads
+    if isinstance(edata_list, ExpDataBatch):
+        return run_batch(model, solver, edata_list)
+    if len(edata_list) == 0:
+        return []
+    return run_batch(model, solver, ExpDataBatch.from_list(model, edata_list)).views()
+
+
+def run_simulation(model: Model, solver: Solver, edata: ExpData | None = None) -> ReturnDataView:
+    """Drop-in for ``amici.sim.sundials.run_simulation`` (reference _swig_wrappers.py:46-84)."""
+    return run_batch(model, solver, ExpDataBatch.from_list(model, [edata])).view(0)
+
+
+# names used by older AMICI releases (BASELINE.json quotes them)
+runAmiciSimulations = run_simulations
+runAmiciSimulation = run_simulation

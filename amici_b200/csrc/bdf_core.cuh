@@ -15,64 +15,16 @@
 // against the compiled reference without a GPU); the product is the CUDA instantiation.
 #ifndef AMICI_B200_BDF_CORE_CUH
 #define AMICI_B200_BDF_CORE_CUH
+#include "../../include/amici_b200.h"
 #include "group.cuh"
 #include "model_common.cuh"
 #include "spline.cuh"
 
 namespace amici_b200 {
 
-// ---------------------------------------------------------------------------------------------
-// plain-data interface structs (also part of the C ABI, see include/amici_b200.h)
-// ---------------------------------------------------------------------------------------------
-struct SolverOptions {
-    double rtol, atol;          // Solver::set_relative/absolute_tolerance (reference solver.h:2057-2060)
-    double rtol_fsa, atol_fsa;  // already resolved (NaN -> rtol/atol, reference src/solver.cpp:874-891)
-    double t0;
-    double hmax_inv;            // 1/max_step_size, 0 = unbounded (reference solver.h:2115)
-    int sensi;                  // 0 none, 1 first-order forward
-    int ism;                    // 1 simultaneous (only mode implemented)
-    int maxsteps;               // budget for the whole simulation (reference src/solver.cpp:107-119)
-    int stldet;                 // BDF stability-limit detection (reference solver.h:2037, default on)
-    int max_nonlin_iters;       // 3
-    int max_conv_fails;         // 10
-    int max_err_test_fails;     // 7 (CVODES default MXNEF)
-    int reporting;              // RDataReporting: 0 full, 2 likelihood
-};
-
-struct BatchView {
-    // ---- inputs ----
-    int N, nt, nplist;
-    const double* ts;         // [nt]
-    const int* plist;         // [nplist]
-    const int* pscale;        // [NP]
-    const double* p;          // [N][NP] on the scale given by pscale
-    const double* k;          // [N][NK]
-    const double* my;         // [N][nt][NY] or null; NaN = missing (reference src/edata.cpp:178-181)
-    const double* sigmay_in;  // [N][nt][NY] or null; NaN = use model sigma
-    // ---- outputs (any may be null) ----
-    int* status;     // [N]
-    double* llh;     // [N]
-    double* chi2;    // [N]
-    double* sllh;    // [N][nplist]
-    double* x;       // [N][nt][NX]
-    double* sx;      // [N][nt][nplist][NX]
-    double* y;       // [N][nt][NY]
-    double* sy;      // [N][nt][nplist][NY]
-    double* sigmay;  // [N][nt][NY]
-    double* ssigmay; // [N][nt][nplist][NY]
-    double* res;     // [N][nt*NY]
-    double* sres;    // [N][nt*NY][nplist]
-    double* FIM;     // [N][nplist][nplist]
-    double* x0;      // [N][NX]
-    double* sx0;     // [N][nplist][NX]
-    double* xdot;    // [N][NX]
-    double* J;       // [N][NX][NX]
-    int* numsteps;   // [N][nt]
-    int* numrhsevals;
-    int* numerrtestfails;
-    int* numnonlinsolvconvfails;
-    int* order;
-};
+// plain-data interface structs: the C ABI's (include/amici_b200.h)
+using SolverOptions = ab_solver_options;
+using BatchView = ab_batch;
 
 // ---------------------------------------------------------------------------------------------
 // per-trajectory shared storage
@@ -105,7 +57,7 @@ enum : int { CONVFAIL_NONE = 0, CONVFAIL_BAD_J = 1, CONVFAIL_OTHER = 2 };
 template <class M, int G, int C>
 struct Bdf {
     static constexpr int NX = M::NX;
-    static constexpr int NCOLS = G * C;
+    static constexpr int NCOLS = (G * C < M::NP + 1) ? G * C : M::NP + 1;  // columns that can ever be active
     using Shared = TrajShared<M, NCOLS>;
 
     Shared& S;

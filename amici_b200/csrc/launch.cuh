@@ -1,0 +1,97 @@
+// launch.cuh — solve kernel, per-model launch configuration and registry entry (one translation unit per model).
+#ifndef AMICI_B200_LAUNCH_CUH
+#define AMICI_B200_LAUNCH_CUH
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+
+#include "registry.h"
+#include "simulate.cuh"
+
+namespace amici_b200 {
+
+template <class M, int G, int C, int THREADS>
+__global__ void __launch_bounds__(THREADS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head) {
+    using Sim = Simulation<M, G, C>;
+    using Shared = typename Sim::Shared;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared* slices = reinterpret_cast<Shared*>(smem_raw);
+    Shared& S = slices[threadIdx.x / G];
+    Group<G> g;
+    for (;;) {
+        int n = 0;
+        if (g.lane == 0) n = atomicAdd(queue_head, 1);
+        n = g.bcast(n, 0);
+        if (n >= b.N) break;
+        Sim sim(S, o, b, n);
+        sim.run();
+        g.sync();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-model launch configuration
+// ---------------------------------------------------------------------------------------------
+constexpr int pow2_at_least(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+
+template <class M>
+struct Config {
+    static constexpr int COLS = M::NP + 1;
+    static constexpr int G = pow2_at_least(COLS);
+    static constexpr int C = (COLS + G - 1) / G;
+    static constexpr int THREADS = 64;  // small blocks: shared-memory granularity decides occupancy
+};
+
+template <class M, int G, int C, int THREADS>
+int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
+    using Sim = Simulation<M, G, C>;
+    auto kern = bdf_solve_kernel<M, G, C, THREADS>;
+    constexpr int groups = THREADS / G;
+    const size_t smem = sizeof(typename Sim::Shared) * groups;
+    int dev = 0, sms = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    AB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    if (per_sm < 1) {
+        last_error() = "kernel does not fit on an SM";
+        return AB_E_CUDA;
+    }
+    long want = ((long)b.N + groups - 1) / groups;
+    long grid = (long)sms * per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    AB_CUDA(cudaMemsetAsync(queue_head, 0, sizeof(int), st));
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(o, b, queue_head);
+    g_launches++;
+    AB_CUDA(cudaGetLastError());
+    return AB_OK;
+}
+
+template <class M>
+int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
+    if (o.sensi >= 1 && b.nplist > 0) {
+        if (b.nplist + 1 > Config<M>::COLS) {
+            last_error() = "nplist exceeds the number of model parameters";
+            return AB_E_UNSUPPORTED;
+        }
+        return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS>(o, b, queue_head, st);
+    }
+    // no sensitivities: one thread per condition
+    return launch_variant<M, 1, 1, 32>(o, b, queue_head, st);
+}
+
+template <class M>
+ModelEntry make_entry() {
+    ModelEntry e;
+    e.name = M::name();
+    e.dims = ab_dims{M::NX, M::NP, M::NK, M::NY, M::NZ, M::NE, M::NSPL, Config<M>::G, Config<M>::C};
+    e.nominal = &M::nominal;
+    e.launch = &launch_model<M>;
+    return e;
+}
+
+}  // namespace amici_b200
+#endif

@@ -1,0 +1,39 @@
+// registry.h — what the per-model translation units (tu/<model>.cu) hand to the C ABI (engine.cu).
+#ifndef AMICI_B200_REGISTRY_H
+#define AMICI_B200_REGISTRY_H
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/amici_b200.h"
+
+namespace amici_b200 {
+
+extern std::atomic<long> g_launches;  // kernels launched by this library
+std::string& last_error();            // thread-local message behind ab_last_error()
+
+inline bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    last_error() = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+#define AB_CUDA(x)                                   \
+    do {                                             \
+        if (!cuda_ok((x), #x)) return AB_E_CUDA;     \
+    } while (0)
+
+struct ModelEntry {
+    const char* name;
+    ab_dims dims;
+    void (*nominal)(double*, double*);
+    int (*launch)(const ab_solver_options&, const ab_batch&, int*, cudaStream_t);
+};
+
+// defined in tu/<model>.cu
+ModelEntry entry_jakstat_adjoint();
+ModelEntry entry_steadystate();
+ModelEntry entry_robertson_ode();
+
+}  // namespace amici_b200
+#endif

@@ -25,8 +25,8 @@ AB_HD bool next_t_too_close(double cur_t, double t_next) {
 
 template <class M, int G, int C>
 struct Simulation {
-    static constexpr int NX = M::NX, NY = M::NY, NCOLS = G * C;
     using Solver = Bdf<M, G, C>;
+    static constexpr int NX = M::NX, NY = M::NY, NCOLS = Solver::NCOLS;
     using Shared = typename Solver::Shared;
 
     Shared& S;

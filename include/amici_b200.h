@@ -1,0 +1,137 @@
+/* amici_b200.h — C ABI of the B200 batched BDF engine.
+ *
+ * Drop-in boundary for ONE path of AMICI: the batch call
+ *     amici::run_simulations(Solver const&, std::vector<ExpData*> const&, Model const&, bool failfast, int num_threads)
+ * (reference include/amici/amici.h:36-39, src/amici.cpp:220-264; Python face
+ * amici.sim.sundials.run_simulations, reference python/sdist/amici/sim/sundials/_swig_wrappers.py:87-133).
+ * The reference has no FFI for this path (it is C++ behind SWIG); the entry points below are what a
+ * binding of that call needs: plain pointers and sizes, no C++/torch types, integer return codes,
+ * no exceptions across the boundary.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - all arrays row-major doubles/ints, borrowed from the caller, never retained after return;
+ *  - one `ab_batch` describes N conditions of one model that share ts / plist / pscale
+ *    (the per-condition fields of amici::ExpData, reference include/amici/edata.h:20,
+ *    include/amici/simulation_parameters.h, flattened to struct-of-arrays);
+ *  - outputs use the reference's ReturnData layouts per condition (reference
+ *    python/sdist/amici/sim/sundials/_numpy.py:414-459) with the condition index as the slowest
+ *    dimension; a NULL output pointer means "do not report";
+ *  - per-condition failures never make the call fail: they are reported in status[] with the
+ *    reference's codes (reference include/amici/defines.h:64-101) and NaN-filled outputs from the
+ *    failing timepoint on (reference src/rdata.cpp:684-735).
+ */
+#ifndef AMICI_B200_H
+#define AMICI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Solver settings: the subset of amici::Solver that parametrises this path
+ * (defaults and meaning: reference include/amici/solver.h:1869-2127). */
+typedef struct ab_solver_options {
+    double rtol, atol;         /* Solver::set_relative_tolerance / set_absolute_tolerance           */
+    double rtol_fsa, atol_fsa; /* resolved values (NaN already replaced by rtol/atol, solver.cpp:874) */
+    double t0;                 /* Model::set_t0                                                      */
+    double hmax_inv;           /* 1 / Solver::set_max_step_size, 0 = unbounded                       */
+    int sensi;                 /* SensitivityOrder: 0 none, 1 first (forward)                        */
+    int ism;                   /* InternalSensitivityMethod: 1 simultaneous                          */
+    int maxsteps;              /* Solver::set_max_steps (budget for the whole simulation)            */
+    int stldet;                /* Solver::set_stability_limit_flag                                   */
+    int max_nonlin_iters;      /* Solver::set_max_nonlin_iters (3)                                   */
+    int max_conv_fails;        /* Solver::set_max_conv_fails (10)                                    */
+    int max_err_test_fails;    /* CVODES default 7                                                   */
+    int reporting;             /* RDataReporting: 0 full, 2 likelihood                               */
+} ab_solver_options;
+
+/* One batch of N conditions (replaces std::vector<ExpData*> in, std::vector<ReturnData> out). */
+typedef struct ab_batch {
+    /* ---- inputs ---- */
+    int N, nt, nplist;
+    const double* ts;        /* [nt]            ExpData::ts_ / Model::set_timepoints              */
+    const int* plist;        /* [nplist]        SimulationParameters::plist                       */
+    const int* pscale;       /* [np]            SimulationParameters::pscale (0 none, 1 ln, 2 log10) */
+    const double* p;         /* [N][np]         SimulationParameters::free_parameters (scaled)    */
+    const double* k;         /* [N][nk]         SimulationParameters::fixed_parameters            */
+    const double* my;        /* [N][nt][ny]     ExpData measurements, NaN = missing; may be NULL  */
+    const double* sigmay_in; /* [N][nt][ny]     ExpData noise scales, NaN = model sigma; may be NULL */
+    /* ---- outputs (ReturnData fields; any may be NULL) ---- */
+    int* status;             /* [N]                                  */
+    double* llh;             /* [N]                                  */
+    double* chi2;            /* [N]                                  */
+    double* sllh;            /* [N][nplist]                          */
+    double* x;               /* [N][nt][nx]                          */
+    double* sx;              /* [N][nt][nplist][nx]                  */
+    double* y;               /* [N][nt][ny]                          */
+    double* sy;              /* [N][nt][nplist][ny]                  */
+    double* sigmay;          /* [N][nt][ny]                          */
+    double* ssigmay;         /* [N][nt][nplist][ny]                  */
+    double* res;             /* [N][nt*ny]                           */
+    double* sres;            /* [N][nt*ny][nplist]                   */
+    double* FIM;             /* [N][nplist][nplist]                  */
+    double* x0;              /* [N][nx]                              */
+    double* sx0;             /* [N][nplist][nx]                      */
+    double* xdot;            /* [N][nx]                              */
+    double* J;               /* [N][nx][nx]                          */
+    int* numsteps;           /* [N][nt]                              */
+    int* numrhsevals;        /* [N][nt]                              */
+    int* numerrtestfails;    /* [N][nt]                              */
+    int* numnonlinsolvconvfails; /* [N][nt]                          */
+    int* order;              /* [N][nt]                              */
+} ab_batch;
+
+/* Model dimensions (amici::ModelDimensions, reference include/amici/model_dimensions.h:14). */
+typedef struct ab_dims {
+    int nx, np, nk, ny, nz, ne, nspl;
+    int group_lanes;   /* lanes of one warp that integrate one condition (FSA kernel) */
+    int cols_per_lane; /* state/sensitivity columns per lane                          */
+} ab_dims;
+
+/* error codes of the ABI itself (not per-condition status) */
+#define AB_OK 0
+#define AB_E_UNKNOWN_MODEL -1
+#define AB_E_BAD_ARGUMENT -2
+#define AB_E_CUDA -3
+#define AB_E_UNSUPPORTED -4
+
+/* Registry of compiled models (replaces amici::generic_model::get_model(), reference
+ * models/model_*_py/wrapfunctions.cpp). */
+int ab_model_count(void);
+const char* ab_model_name(int index);
+int ab_get_dims(const char* model, ab_dims* out);
+/* nominal parameters (Model::get_unscaled_parameters / get_fixed_parameters) */
+int ab_get_nominal(const char* model, double* p, double* k);
+
+/* Solve a batch whose arrays are all HOST memory: copies inputs to the device, integrates every
+ * condition on the GPU of the calling thread's current device, copies the requested outputs back.
+ * This is the replacement for amici::run_simulations (reference src/amici.cpp:220-264).
+ * kernel_ms (may be NULL) receives the device time of the solve kernel alone. */
+int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch* host_batch, float* kernel_ms);
+
+/* Solve a batch whose arrays are all DEVICE memory (ts/plist/pscale included), asynchronously on
+ * `stream` (a cudaStream_t passed as void*). `work_counter` is one device int used as the
+ * trajectory queue head; it is reset by the call. res/sres/FIM are zero-filled by the call. */
+int ab_solve_device(const char* model, const ab_solver_options* opt, const ab_batch* device_batch,
+                    int* work_counter, void* stream);
+
+/* Device reduction of the objective over the batch: out[0] = sum llh, out[1+i] = sum sllh[:, i],
+ * out[1+nplist] = number of failed conditions (status != 0; their llh/sllh are skipped).
+ * All pointers device memory; asynchronous on `stream`.  The result is what a multi-GPU caller
+ * all-reduces (the reference sums in Python: petab/v1/_simulations.py:213-232). */
+int ab_reduce_objective(int N, int nplist, const int* status, const double* llh, const double* sllh,
+                        double* out, void* stream);
+
+/* Measured FP64 FMA throughput of the current device in TFLOP/s (dependent-FMA chains, all SMs busy);
+ * bench.py uses it as the FP64 roofline denominator. */
+int ab_measure_fp64_peak(double* tflops);
+
+/* Number of kernels launched by this library since load (for bench accounting). */
+long ab_kernel_launch_count(void);
+
+/* Last CUDA error string seen by the library on this thread ("" if none). */
+const char* ab_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMICI_B200_H */

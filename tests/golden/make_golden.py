@@ -1,0 +1,55 @@
+"""Generate golden vectors with the compiled reference (oracle/_ref, built from /root/reference).
+
+Run once in the build container:  python tests/golden/make_golden.py
+Each fixture holds the inputs of a small batch, the reference's ReturnData at the working tolerances
+(rtol 1e-8 / atol 1e-12, KLU and dense linear solver -> the reference's own noise floor) and a
+tight-tolerance "truth" run (rtol 1e-12 / atol 1e-16).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.refsim import RefModel  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIELDS = ["status", "llh", "chi2", "sllh", "x", "sx", "y", "sy", "sigmay", "ssigmay", "res", "sres", "FIM", "x0",
+          "sx0", "xdot", "J", "numsteps"]
+
+
+def make(model, ts, N, seed, sensi=1, pscale=None, tag=""):
+    m = RefModel(model)
+    d = m.dims
+    rng = np.random.default_rng(seed)
+    p = np.tile(m.p_nominal, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, d.np))
+    p[0] = m.p_nominal
+    k = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.8, 1.25, (N, d.nk))
+    k[0] = m.k_nominal
+    y0 = m.run(ts, p, k, sensi_order=0, fields=["y"])["y"]
+    my = y0 + 0.1 * rng.standard_normal(y0.shape)
+    my[1, 2, :] = np.nan          # missing measurements
+    my[2, :, 0] = np.nan
+    sig = np.full_like(my, 0.1)
+    sig[1] = np.nan               # model sigma for condition 1
+    sig[3, 4:, 1] = np.nan
+    pin = p.copy()
+    if pscale is not None:
+        pin = np.where(np.asarray(pscale) == 2, np.log10(p), np.where(np.asarray(pscale) == 1, np.log(p), p))
+    kw = dict(my=my, sigmay=sig, sensi_order=sensi, pscale=pscale, fields=FIELDS)
+    out = dict(ts=ts, p=pin, k=k, my=my, sigmay_in=sig, pscale=np.zeros(d.np, int) if pscale is None else np.asarray(pscale))
+    for name, extra in (("klu", dict(linsol=9)), ("dense", dict(linsol=1)),
+                        ("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=200000))):
+        r = m.run(ts, pin, k, **{**kw, **extra})
+        for f in FIELDS:
+            out[f"{name}_{f}"] = r[f]
+    path = os.path.join(HERE, f"{model}{tag}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    make("jakstat_adjoint", np.arange(0, 61, 5.0), N=6, seed=11)
+    make("jakstat_adjoint", np.arange(0, 61, 5.0), N=4, seed=12, pscale=[2] * 17, tag="_log10")
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=13)

@@ -1,0 +1,49 @@
+"""Parity protocol shared by the CPU (lane-group emulation) and GPU tests.
+
+The reference does not agree with itself to 10*rtol / 10*atol on sensitivities at rtol=1e-8, atol=1e-12
+(KLU vs dense linear solver, simultaneous vs staggered), because step sequences are
+chaotic w.r.t. round-off.  Every fixture therefore stores three reference runs: `klu` (the default
+path), `dense` (same tolerances, other linear solver) and `truth` (rtol 1e-12 / atol 1e-16).
+
+A candidate passes for a field iff
+  (a) discrete outputs (status) are identical,
+  (b) its error against `truth` is at most FACTOR x the reference's own error against `truth`
+      (max of klu, dense), measured in the scaled norm |a-b| / (atol_f + rtol_f*|truth|), and
+  (c) it deviates from `klu` by at most FACTOR x the klu-vs-dense deviation in the same norm, or by less
+      than 1 in that norm (i.e. inside 10*rtol / 10*atol outright).
+"""
+import numpy as np
+
+RTOL, ATOL = 1e-8, 1e-12          # solver tolerances of the fixtures
+FACTOR = 4.0
+FLOAT_FIELDS = ["x", "y", "llh", "chi2", "sigmay", "res", "x0", "xdot", "J", "sx", "sy", "sllh", "ssigmay", "sres", "FIM", "sx0"]
+
+
+def scaled_err(a, b, truth, rtol=10 * RTOL, atol=10 * ATOL):
+    a, b, truth = np.asarray(a, float), np.asarray(b, float), np.asarray(truth, float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert (nan_a == nan_b).all(), "NaN pattern differs"
+    err = np.abs(a - b) / (atol + rtol * np.abs(truth))
+    return float(np.nanmax(err)) if err.size and not nan_a.all() else 0.0
+
+
+def check_against_golden(cand: dict, gold, fields=None, factor=FACTOR, verbose=True):
+    """cand: field -> array; gold: loaded npz. Returns report dict; raises AssertionError on failure."""
+    report = {}
+    np.testing.assert_array_equal(cand["status"], gold["klu_status"], err_msg="status codes differ")
+    for f in fields or FLOAT_FIELDS:
+        if f not in cand or f"klu_{f}" not in gold:
+            continue
+        klu, dense, truth = gold[f"klu_{f}"], gold[f"dense_{f}"], gold[f"truth_{f}"]
+        scale_ref = truth
+        floor_truth = max(scaled_err(klu, truth, scale_ref), scaled_err(dense, truth, scale_ref))
+        floor_pair = scaled_err(dense, klu, scale_ref)
+        e_truth = scaled_err(cand[f], truth, scale_ref)
+        e_klu = scaled_err(cand[f], klu, scale_ref)
+        report[f] = dict(err_vs_truth=e_truth, ref_err_vs_truth=floor_truth, dev_vs_klu=e_klu, ref_dev=floor_pair)
+        if verbose:
+            print(f"{f:8s} cand-truth {e_truth:10.3e} (ref {floor_truth:10.3e})   cand-klu {e_klu:10.3e} (dense-klu {floor_pair:10.3e})")
+        assert e_truth <= max(1.0, factor * floor_truth), (f, report[f])
+        assert e_klu <= max(1.0, factor * floor_pair), (f, report[f])
+    return report

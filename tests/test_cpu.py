@@ -1,0 +1,149 @@
+"""CPU-side tests (no GPU): oracle vs golden vectors, host logic, C-ABI symbols, lane-group emulation."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from amici_b200 import _capi
+from tests import parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+MODEL_DIMS = {"jakstat_adjoint": dict(nx=9, np=17, nk=2, ny=3), "steadystate": dict(nx=3, np=5, nk=4, ny=3)}
+
+
+def _emul(built):
+    return C.CDLL(os.path.join(ROOT, "tests", "cpu_emul", "libemul.so"))
+
+
+def run_emul(lib, model, g, sensi=1, **opt):
+    dims = MODEL_DIMS[model]
+    b, out, keep = _capi.make_batch(dims, g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"])
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=sensi, **opt)
+    assert lib.emul_run(model.encode(), C.byref(o), C.byref(b)) == 0
+    return out
+
+
+@pytest.mark.parametrize("fixture,model", [("jakstat_adjoint", "jakstat_adjoint"), ("jakstat_adjoint_log10", "jakstat_adjoint"),
+                                           ("steadystate", "steadystate")])
+def test_emulation_matches_golden(built, fixture, model):
+    """The solver source (host build, one-lane groups) reproduces the reference inside its own noise floor."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    out = run_emul(_emul(built), model, g)
+    parity.check_against_golden(out, g)
+    # step counts are not expected to be equal (chaotic), but must be of the same size
+    assert abs(out["numsteps"][:, -1] / g["klu_numsteps"][:, -1] - 1).max() < 0.15
+
+
+def test_oracle_reproduces_golden():
+    """The compiled reference (oracle/_ref) still reproduces the committed vectors bit for bit."""
+    from oracle import refsim
+    if not refsim.available("jakstat_adjoint"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))
+    r = refsim.RefModel("jakstat_adjoint").run(g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], linsol=9)
+    for f in ("x", "sx", "llh", "sllh", "FIM"):
+        np.testing.assert_array_equal(r[f], g[f"klu_{f}"])
+
+
+def test_maxsteps_status(built):
+    """Exhausting the step budget inside a call gives CV_TOO_MUCH_WORK (-1) and NaN outputs from that timepoint on."""
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))
+    out = run_emul(_emul(built), "jakstat_adjoint", g, maxsteps=300)
+    assert (out["status"] == -1).all()
+    assert np.isnan(out["llh"]).all() and np.isnan(out["sllh"]).all() and np.isnan(out["FIM"]).all()
+    assert not np.isnan(out["x"][:, 0]).any() and np.isnan(out["x"][:, -1]).all()
+    from oracle import refsim
+    if refsim.available("jakstat_adjoint"):
+        r = refsim.RefModel("jakstat_adjoint").run(g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], maxsteps=300)
+        np.testing.assert_array_equal(out["status"], r["status"])
+        np.testing.assert_array_equal(np.isnan(out["x"]), np.isnan(r["x"]))
+        np.testing.assert_array_equal(np.isnan(out["sx"]), np.isnan(r["sx"]))
+        np.testing.assert_array_equal(np.isnan(out["res"]), np.isnan(r["res"]))
+
+
+def test_no_sensitivities(built):
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    out = run_emul(_emul(built), "steadystate", g, sensi=0)
+    assert (out["status"] == 0).all()
+    np.testing.assert_allclose(out["x"], g["truth_x"], rtol=1e-6, atol=1e-10)
+    assert (out["sllh"] == 0).all()
+
+
+def test_empty_batch_and_no_measurements(built):
+    lib = _emul(built)
+    dims = MODEL_DIMS["steadystate"]
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    b, out, keep = _capi.make_batch(dims, g["ts"], g["p"][:0].reshape(0, 5), g["k"][:0].reshape(0, 4))
+    o = _capi.default_options(rtol=1e-8, atol=1e-12, sensi=1)
+    assert lib.emul_run(b"steadystate", C.byref(o), C.byref(b)) == 0
+    b, out, keep = _capi.make_batch(dims, g["ts"], g["p"], g["k"])  # no measurements: llh = 0, res = 0
+    assert lib.emul_run(b"steadystate", C.byref(o), C.byref(b)) == 0
+    assert (out["llh"] == 0).all() and (out["res"] == 0).all() and (out["FIM"] == 0).all()
+    np.testing.assert_allclose(out["x"], g["truth_x"], rtol=1e-6, atol=1e-10)
+
+
+def test_cabi_exports_every_declared_symbol(built):
+    """Every function declared in include/amici_b200.h is exported by the CUDA library (no compute call here)."""
+    hdr = open(os.path.join(ROOT, "include", "amici_b200.h")).read()
+    names = re.findall(r"^\s*(?:int|long|const char\*)\s+(ab_\w+)\s*\(", hdr, flags=re.M)
+    assert len(names) >= 8
+    lib = C.CDLL(os.path.join(ROOT, "amici_b200", "lib", "libamici_b200.so"))
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.ab_model_count.restype = C.c_int
+    assert lib.ab_model_count() >= 3
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors have the size the C compiler gives the header's structs."""
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "amici_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(ab_solver_options), sizeof(ab_batch), sizeof(ab_dims));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "s.c"), "-o", os.path.join(td, "s")])
+        a, b, d = map(int, subprocess.check_output([os.path.join(td, "s")]).split())
+    import amici_b200
+    assert a == C.sizeof(_capi.SolverOptions) and b == C.sizeof(_capi.BatchView) and d == C.sizeof(amici_b200._Dims)
+
+
+def test_host_api_settings_and_errors(built):
+    """Setters mirror the reference's error behaviour (AmiException -> RuntimeError, src/solver.cpp:764-1087)."""
+    import amici_b200 as ab
+    m = ab.get_model("jakstat_adjoint")
+    assert (m.nx, m.np(), m.nk(), m.ny) == (9, 17, 2, 3)
+    s = m.create_solver()
+    with pytest.raises(RuntimeError):
+        s.set_relative_tolerance(-1)
+    with pytest.raises(RuntimeError):
+        s.set_max_steps(0)
+    with pytest.raises(RuntimeError):
+        m.set_parameter_list([99])
+    with pytest.raises(RuntimeError):
+        m.set_timepoints([1, 0])
+    p0 = m.get_unscaled_parameters()
+    m.set_parameter_scale(ab.ParameterScaling.log10)
+    np.testing.assert_allclose(m.get_unscaled_parameters(), p0)
+    np.testing.assert_allclose(m.get_free_parameters(), np.log10(p0))
+    m.set_timepoints([0, 1, 2])
+    e = ab.ExpData(m)
+    with pytest.raises(RuntimeError):
+        e.set_measurements([1.0])
+    with pytest.raises(RuntimeError):
+        e.set_noise_scales(np.zeros(9))
+    e.set_measurements(np.ones(9))
+    batch = ab.ExpDataBatch.from_list(m, [e, None])
+    assert batch.p.shape == (2, 17) and np.isnan(batch.my[1]).all() and (batch.pscale == 2).all()
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    assert s._options(0.0).sensi == 1 and s._options(0.0).atol_fsa == s.get_absolute_tolerance()
+
+
+def test_emitter_is_reproducible(tmp_path):
+    """The committed generated headers are what the emitter produces from the model definitions."""
+    from amici_b200.codegen import models
+    for p in models.generate_all(str(tmp_path)):
+        committed = os.path.join(ROOT, "amici_b200", "csrc", "models", os.path.basename(p))
+        assert open(p).read() == open(committed).read(), os.path.basename(p)

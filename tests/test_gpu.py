@@ -1,0 +1,164 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the golden vectors and the compiled reference."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _run(model_name, g, sensi=True, ts=None, **solver_kw):
+    import amici_b200 as ab
+    m = ab.get_model(model_name)
+    m.set_timepoints(g["ts"] if ts is None else ts)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    if sensi:
+        s.set_sensitivity_order(ab.SensitivityOrder.first)
+    for k_, v in solver_kw.items():
+        getattr(s, "set_" + k_)(v)
+    batch = ab.ExpDataBatch(m.get_timepoints(), g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"])
+    return ab.run_simulations(m, s, batch)
+
+
+@pytest.mark.parametrize("fixture,model", [("jakstat_adjoint", "jakstat_adjoint"), ("jakstat_adjoint_log10", "jakstat_adjoint"),
+                                           ("steadystate", "steadystate")])
+def test_cuda_matches_golden(fixture, model):
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    res = _run(model, g)
+    parity.check_against_golden(res.fields, g)
+
+
+def test_cuda_matches_cpu_emulation_bitwise_counters(built):
+    """Same source, host vs device: results agree to round-off and step counts are close."""
+    import ctypes as C
+    from amici_b200 import _capi
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))
+    res = _run("jakstat_adjoint", g)
+    lib = C.CDLL(os.path.join(ROOT, "tests", "cpu_emul", "libemul.so"))
+    b, out, keep = _capi.make_batch(dict(nx=9, np=17, nk=2, ny=3), g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"])
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
+    assert lib.emul_run(b"jakstat_adjoint", C.byref(o), C.byref(b)) == 0
+    np.testing.assert_allclose(res["x"], out["x"], rtol=1e-6, atol=1e-10)
+    assert abs(res["numsteps"][:, -1] / out["numsteps"][:, -1] - 1).max() < 0.1
+
+
+def test_cuda_vs_reference_random_batch():
+    """A larger seeded batch against the compiled reference run on the host cores (when oracle/_ref is present)."""
+    from oracle import refsim
+    if not refsim.available("jakstat_adjoint"):
+        pytest.skip("oracle/_ref not available")
+    import amici_b200 as ab
+    ref = refsim.RefModel("jakstat_adjoint")
+    N = 256
+    rng = np.random.default_rng(5)
+    p = np.tile(ref.p_nominal, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, 17))
+    k = np.tile(ref.k_nominal, (N, 1)) * rng.uniform(0.8, 1.25, (N, 2))
+    ts = np.arange(0, 61, 5.0)
+    my = rng.normal(0.5, 0.3, (N, 13, 3))
+    sig = np.full_like(my, 0.1)
+    nthr = min(ref.max_threads(), 32)
+    r_klu = ref.run(ts, p, k, my=my, sigmay=sig, num_threads=nthr, linsol=9)
+    r_dense = ref.run(ts, p, k, my=my, sigmay=sig, num_threads=nthr, linsol=1)
+    r_truth = ref.run(ts, p, k, my=my, sigmay=sig, num_threads=nthr, rtol=1e-12, atol=1e-16, maxsteps=200000)
+    gold = {}
+    for name, r in (("klu", r_klu), ("dense", r_dense), ("truth", r_truth)):
+        for f, v in r.items():
+            gold[f"{name}_{f}"] = v
+    g = dict(ts=ts, p=p, k=k, my=my, sigmay_in=sig, pscale=np.zeros(17, int))
+    res = _run("jakstat_adjoint", g)
+    parity.check_against_golden(res.fields, gold)
+
+
+def test_status_codes_and_nan_pattern():
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))
+    res = _run("jakstat_adjoint", g, max_steps=300)
+    assert (res["status"] == -1).all()
+    assert np.isnan(res["llh"]).all() and np.isnan(res["x"][:, -1]).all() and not np.isnan(res["x"][:, 0]).any()
+
+
+def test_no_sensitivities_thread_per_condition_kernel():
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    res = _run("steadystate", g, sensi=False)
+    assert (res["status"] == 0).all()
+    np.testing.assert_allclose(res["x"], g["truth_x"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(res["llh"], g["truth_llh"], rtol=1e-6)
+
+
+def test_list_of_expdata_entry_point():
+    """run_simulations(model, solver, [ExpData, ...]) returns per-condition views like the reference."""
+    import amici_b200 as ab
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    m = ab.get_model("steadystate")
+    m.set_timepoints(g["ts"])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    edatas = []
+    for i in range(3):
+        e = ab.ExpData(m)
+        e.free_parameters = list(g["p"][i])
+        e.fixed_parameters = list(g["k"][i])
+        e.set_measurements(g["my"][i])
+        e.set_noise_scales(np.where(np.isnan(g["sigmay_in"][i]), np.nan, g["sigmay_in"][i]))
+        edatas.append(e)
+    rdatas = ab.run_simulations(m, s, edatas, failfast=False, num_threads=2)
+    assert len(rdatas) == 3
+    for i, r in enumerate(rdatas):
+        assert r.status == 0 and r["sx"].shape == (11, 5, 3) and r.x.shape == (11, 3)
+        np.testing.assert_allclose(r.x, g["truth_x"][i], rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose(r.llh, g["truth_llh"][i], rtol=1e-6)
+    single = ab.run_simulation(m, s, edatas[0])
+    np.testing.assert_allclose(single.x, rdatas[0].x, rtol=1e-12)
+
+
+def test_objective_reduction_kernel():
+    import ctypes as C
+    import torch
+    import amici_b200 as ab
+    lib = ab.load_library()
+    N, q = 1000, 17
+    rng = np.random.default_rng(0)
+    llh, sllh = rng.normal(size=N), rng.normal(size=(N, q))
+    status = np.zeros(N, np.int32)
+    status[::7] = -4
+    d_llh, d_sllh, d_st = torch.tensor(llh).cuda(), torch.tensor(sllh).cuda(), torch.tensor(status).cuda()
+    out = torch.zeros(q + 2, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.ab_reduce_objective(N, q, d_st.data_ptr(), d_llh.data_ptr(), d_sllh.data_ptr(), out.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    ok = status == 0
+    np.testing.assert_allclose(o[0], llh[ok].sum(), rtol=1e-12)
+    np.testing.assert_allclose(o[1:-1], sllh[ok].sum(0), rtol=1e-11)
+    assert o[-1] == (~ok).sum()
+
+
+def test_linearity_property_full_size_batch():
+    """Size-independent property at a BASELINE-sized batch: the batch result does not depend on the position
+    of a condition in the batch nor on its neighbours (work-queue scheduling), and duplicated conditions agree bitwise."""
+    import amici_b200 as ab
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))
+    m = ab.get_model("jakstat_adjoint")
+    m.set_timepoints(g["ts"])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    s.set_return_data_reporting_mode(ab.RDataReporting.likelihood)
+    N = 8192
+    idx = np.random.default_rng(1).integers(0, len(g["p"]), N)
+    batch = ab.ExpDataBatch(g["ts"], g["p"][idx], g["k"][idx], my=g["my"][idx], sigmay=g["sigmay_in"][idx])
+    res = ab.run_simulations(m, s, batch)
+    assert (res["status"] == 0).all()
+    for j in range(len(g["p"])):
+        sel = idx == j
+        assert (res["llh"][sel] == res["llh"][sel][0]).all()
+        assert (res["sllh"][sel] == res["sllh"][sel][0]).all()
+        np.testing.assert_allclose(res["llh"][sel][0], g["truth_llh"][j], rtol=1e-6)
