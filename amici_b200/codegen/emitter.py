@@ -293,6 +293,100 @@ def emit_model(spec: ModelSpec) -> str:
             A(f"        D[{r * nx + c}] = " + (f"J[{idx}];" if idx is not None else "0.0;"))
     A("    }")
 
+    # ---- sparse LU of A = I - gamma*J with a static, fill-reducing diagonal pivot order ----
+    # (replaces SUNLinSol KLU/dense for small systems: straight-line factor and solve code; the run time
+    #  checks KLU's diagonal-preference test |a_kk| >= 1e-3 * max|a_ik| and falls back to dense partial
+    #  pivoting when it fails, reference ThirdParty/sundials/src/sunlinsol/klu/sunlinsol_klu.c:240-342)
+    pat = [[(r == c) or (Jfull[r][c] != 0) for c in range(nx)] for r in range(nx)]
+    jidx = {}
+    for c in range(nx):
+        for q_ in range(colptr[c], colptr[c + 1]):
+            jidx[(rowval[q_], c)] = q_
+    work = [row[:] for row in pat]
+    remaining = list(range(nx))
+    order = []
+    while remaining:
+        best, bestcost = None, None
+        for kk in remaining:
+            rc = sum(1 for i in remaining if work[i][kk]) - 1
+            cc_ = sum(1 for j in remaining if work[kk][j]) - 1
+            cost = rc * cc_
+            if bestcost is None or cost < bestcost:
+                best, bestcost = kk, cost
+        kk = best
+        remaining.remove(kk)
+        order.append(kk)
+        for i in remaining:
+            if work[i][kk]:
+                for j in remaining:
+                    if work[kk][j]:
+                        work[i][j] = True
+    # symbolic elimination in that order, emitting code
+    fact, solve_f, solve_b = [], [], []
+    cur = [row[:] for row in pat]
+    done = set()
+    lu_slots = {}
+
+    def slot(name):
+        if name not in lu_slots:
+            lu_slots[name] = len(lu_slots)
+        return lu_slots[name]
+
+    for r in range(nx):
+        for c in range(nx):
+            if pat[r][c]:
+                diag = "1.0" if r == c else "0.0"
+                if (r, c) in jidx:
+                    fact.append(f"double a_{r}_{c} = {diag} - gamma * J[{jidx[(r, c)]}];")
+                else:
+                    fact.append(f"double a_{r}_{c} = {diag};")
+    declared = {(r, c) for r in range(nx) for c in range(nx) if pat[r][c]}
+    fact.append("bool ok = true;")
+    for kk in order:
+        rows_k = [i for i in range(nx) if i not in done and i != kk and cur[i][kk]]
+        cols_k = [j for j in range(nx) if j not in done and j != kk and cur[kk][j]]
+        if rows_k:
+            mx = " , ".join(f"fabs(a_{i}_{kk})" for i in rows_k)
+            expr = f"fabs(a_{rows_k[0]}_{kk})"
+            for i in rows_k[1:]:
+                expr = f"ab_max({expr}, fabs(a_{i}_{kk}))"
+            fact.append(f"ok = ok && (fabs(a_{kk}_{kk}) >= 1e-3 * ({expr}));")
+        else:
+            fact.append(f"ok = ok && (a_{kk}_{kk} != 0.0);")
+        fact.append(f"const double inv_{kk} = 1.0 / a_{kk}_{kk};")
+        fact.append(f"LU[{slot(f'inv_{kk}')}] = inv_{kk};")
+        for i in rows_k:
+            fact.append(f"const double l_{i}_{kk} = a_{i}_{kk} * inv_{kk};")
+            fact.append(f"LU[{slot(f'l_{i}_{kk}')}] = l_{i}_{kk};")
+            solve_f.append(f"b[{i}] -= LU[{slot(f'l_{i}_{kk}')}] * b[{kk}];")
+            for j in cols_k:
+                if (i, j) in declared:
+                    fact.append(f"a_{i}_{j} -= l_{i}_{kk} * a_{kk}_{j};")
+                else:
+                    fact.append(f"double a_{i}_{j} = -l_{i}_{kk} * a_{kk}_{j};")
+                    declared.add((i, j))
+                cur[i][j] = True
+        for j in cols_k:
+            fact.append(f"LU[{slot(f'u_{kk}_{j}')}] = a_{kk}_{j};")
+        terms = "".join(f" - LU[{slot(f'u_{kk}_{j}')}] * b[{j}]" for j in cols_k)
+        solve_b.append(f"b[{kk}] = (b[{kk}]{terms}) * LU[{slot(f'inv_{kk}')}];")
+        done.add(kk)
+    nlu = len(lu_slots)
+    A(f"    static constexpr int NLU = {nlu};  // stored entries of the sparse LU (pivot order {order})")
+    A("    // LU <- factors of I - gamma*J (no row exchanges); returns false if a pivot fails the diagonal-preference test")
+    A("    AB_HD static bool lu_factor(const double* J, const double gamma, double* LU) {")
+    for ln in fact:
+        A("        " + ln)
+    A("        return ok;")
+    A("    }")
+    A("    // b <- (I - gamma*J)^{-1} b")
+    A("    AB_HD static void lu_solve(const double* LU, double* b) {")
+    for ln in solve_f:
+        A("        " + ln)
+    for ln in reversed(solve_b):
+        A("        " + ln)
+    A("    }")
+
     # dxdotdp column
     A("    // total derivative column d xdot / d p_ip (explicit + through splines), select-chain form")
     A(f"    AB_HD static void dxdotdp(const int ip, {sig_common}, const double* sspl, double* out) {{")

@@ -11,6 +11,13 @@
 // decisions they must reproduce (constants: reference cvodes_impl.h:57-131,202-204;
 // cvodes_ls_impl.h:40-41).
 //
+// Code layout is driven by the instruction cache (profiles/r01_v0_ncu_summary.md): everything on
+// the per-step path is inlined exactly once (one call site for the model right-hand side, the
+// Pascal-triangle update, the rescale, the triangular solves), everything rare (first step,
+// initial step size, order-1 restart, stability-limit detection) is an out-of-line AB_COLD
+// function that only touches the shared-memory slice, so the solver object itself never has its
+// address taken and stays in registers.
+//
 // The same source is compiled for the host with G = 1 by tests/cpu_emul (algorithm check
 // against the compiled reference without a GPU); the product is the CUDA instantiation.
 #ifndef AMICI_B200_BDF_CORE_CUH
@@ -35,7 +42,8 @@ constexpr int LMAX = QMAX + 1;
 template <class M, int NCOLS>
 struct TrajShared {
     double zn[LMAX][M::NX][NCOLS];   // Nordsieck history, column fastest
-    double lu[M::NX][M::NX];         // LU factors of I - gamma*J (row-major, unit lower)
+    double lus[M::NLU];              // sparse LU of I - gamma*J (static pivot order, emitted per model)
+    double lu[M::NX][M::NX];         // dense LU with partial pivoting: fallback when a static pivot is rejected
     double savedJ[M::NNZ_J > 0 ? M::NNZ_J : 1];
     double ybuf[M::NX];              // broadcast buffer for the state column
     double scratch[NCOLS];
@@ -43,10 +51,17 @@ struct TrajShared {
     double k[M::NK > 0 ? M::NK : 1];
     double h[M::NH > 0 ? M::NH : 1];
     double pcoef[NCOLS];             // chain-rule factor per column
-    double ssdat[6][4];              // cvBDFStab history
+    double ssdat[5][4];              // cvBDFStab history: ring buffer of (sqm2^2, sqm1^2, sq^2), newest at ss_head
     int piv[M::NX];
     int ip_of_col[NCOLS];
     SplineTable<M, NCOLS> spl;
+};
+
+template <class M, int G, int C>
+struct Layout {
+    static constexpr int NX = M::NX;
+    static constexpr int NCOLS = (G * C < M::NP + 1) ? G * C : M::NP + 1;  // columns that can ever be active
+    using Shared = TrajShared<M, NCOLS>;
 };
 
 // internal flags of cvStep (cvodes.c local defines)
@@ -54,11 +69,447 @@ enum : int { FIRST_CALL = 101, PREV_CONV_FAIL = 102, PREV_ERR_FAIL = 103 };
 enum : int { NLS_CONV_RECVR = 902, NLS_RHS_RECVR = 903 };
 enum : int { CONVFAIL_NONE = 0, CONVFAIL_BAD_J = 1, CONVFAIL_OTHER = 2 };
 
+template <int N>
+AB_HD double pick(const double (&a)[N], int i) {
+    double v = a[0];
+    AB_UNROLL
+    for (int j = 1; j < N; ++j) v = (i == j) ? a[j] : v;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// model right-hand side of the stacked system (shared by the hot inlined path and the cold helpers)
+// ---------------------------------------------------------------------------------------------
+template <class M, int C>
+struct ModelEval {
+    double y[M::NX];                                   // state column (broadcast)
+    double spl[M::NSPL > 0 ? M::NSPL : 1];
+    double sspl[C][M::NSPL > 0 ? M::NSPL : 1];
+};
+
+template <class M, int G, int C>
+AB_HD void eval_splines(const typename Layout<M, G, C>::Shared& S, const Group<G>& g, int ncols, double t,
+                        ModelEval<M, C>& e) {
+    constexpr int NCOLS = Layout<M, G, C>::NCOLS;
+    AB_UNROLL
+    for (int is = 0; is < M::NSPL; ++is) {
+        const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
+        e.spl[is] = M::SPL_LOG ? exp(v) : v;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            const int cc = g.lane + G * c;
+            e.sspl[c][is] = 0.0;
+            if (cc >= ncols || cc == 0) continue;
+            const double s = spline_eval_scaled<M, NCOLS>(S.spl, is, cc, t, false);
+            e.sspl[c][is] = M::SPL_LOG ? s * e.spl[is] : s;
+        }
+    }
+}
+
+// Broadcast the state column (valid on the lane that owns column 0) to all lanes of the group.
+template <class M, int G, int C>
+AB_HD void bcast_state(typename Layout<M, G, C>::Shared& S, const Group<G>& g, const double (&v)[C][M::NX],
+                       ModelEval<M, C>& e) {
+    if (G == 1) {
+        AB_UNROLL
+        for (int r = 0; r < M::NX; ++r) e.y[r] = v[0][r];
+        return;
+    }
+    g.sync();
+    if (g.lane == 0) {
+        AB_UNROLL
+        for (int r = 0; r < M::NX; ++r) S.ybuf[r] = v[0][r];
+    }
+    g.sync();
+    AB_UNROLL
+    for (int r = 0; r < M::NX; ++r) e.y[r] = S.ybuf[r];
+}
+
+// f for column 0, J(y)*s_c + dfdp_c for sensitivity columns (Model_ODE::fxdot / fsxdot,
+// reference src/model_ode.cpp:105-114, :426-450).  ycols = current values of all own columns.
+// Returns false if any output is non-finite (AMICI's check_finite -> recoverable error).
+template <class M, int G, int C>
+AB_HD bool model_rhs(typename Layout<M, G, C>::Shared& S, const Group<G>& g, int ncols, double t,
+                     const double (&ycols)[C][M::NX], double (&out)[C][M::NX], ModelEval<M, C>& e) {
+    bcast_state<M, G, C>(S, g, ycols, e);
+    eval_splines<M, G, C>(S, g, ncols, t, e);
+    double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
+    AB_UNROLL
+    for (int i = 0; i < (M::NNZ_J > 0 ? M::NNZ_J : 1); ++i) Jv[i] = 0.0;
+    bool need_j = false;
+    AB_UNROLL
+    for (int c = 0; c < C; ++c) need_j = need_j || (g.lane + G * c < ncols && g.lane + G * c > 0);
+    if (need_j) M::jac(t, e.y, S.p, S.k, S.h, e.spl, Jv);
+    bool ok = true;
+    AB_UNROLL
+    for (int c = 0; c < C; ++c) {
+        const int cc = g.lane + G * c;
+        if (cc >= ncols) continue;
+        if (cc == 0) {
+            M::xdot(t, e.y, S.p, S.k, S.h, e.spl, out[c]);
+        } else {
+            M::dxdotdp(S.ip_of_col[cc], t, e.y, S.p, S.k, S.h, e.spl, e.sspl[c], out[c]);
+            M::jac_mul_add(Jv, ycols[c], out[c]);
+        }
+        AB_UNROLL
+        for (int r = 0; r < M::NX; ++r) ok = ok && isfinite(out[c][r]);
+    }
+    return !g.any(!ok);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cold helpers (out of line; touch only the shared-memory slice)
+// ---------------------------------------------------------------------------------------------
+// zn[dst] <- scale * F(t, zn[0] + a * zn[1]); returns false on a non-finite right-hand side
+template <class M, int G, int C>
+AB_COLD bool cold_rhs_store(typename Layout<M, G, C>::Shared& S, int ncols, double t, double a, double scale, int dst) {
+    constexpr int NX = M::NX;
+    Group<G> g;
+    ModelEval<M, C> e;
+    double yy[C][NX], f[C][NX];
+    AB_UNROLL
+    for (int c = 0; c < C; ++c) {
+        const int cc = g.lane + G * c;
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) yy[c][r] = (cc < ncols) ? S.zn[0][r][cc] + (a != 0.0 ? a * S.zn[1][r][cc] : 0.0) : 0.0;
+    }
+    const bool ok = model_rhs<M, G, C>(S, g, ncols, t, yy, f, e);
+    g.sync();
+    AB_UNROLL
+    for (int c = 0; c < C; ++c) {
+        const int cc = g.lane + G * c;
+        if (cc >= ncols) continue;
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) S.zn[dst][r][cc] = scale * f[c][r];
+    }
+    g.sync();
+    return ok;
+}
+
+// cvHin / cvUpperBoundH0 / cvYddNorm (cvodes.c:5436-5798): initial step size. zn[0], zn[1] = y0, f(t0, y0);
+// zn[2] is used as scratch (the order is 1 here). Returns AB_SUCCESS / AB_TOO_CLOSE / AB_REPTD_RHSFUNC_ERR.
+template <class M, int G, int C>
+AB_COLD int cold_hin(typename Layout<M, G, C>::Shared& S, const SolverOptions& o, int ncols, double tn, double tout,
+                     double* h_out, int* nfe) {
+    constexpr int NX = M::NX;
+    Group<G> g;
+    const double tdiff = tout - tn;
+    if (tdiff == 0.0) return AB_TOO_CLOSE;
+    const double sign = tdiff > 0.0 ? 1.0 : -1.0;
+    const double tdist = fabs(tdiff);
+    const double tround = DBL_EPSILON * ab_max(fabs(tn), fabs(tout));
+    if (tdist < 2.0 * tround) return AB_TOO_CLOSE;
+    const double hlb = 100.0 * tround;
+    double hub_inv = 0.0;
+    AB_UNROLL
+    for (int c = 0; c < C; ++c) {
+        const int cc = g.lane + G * c;
+        if (cc >= ncols) continue;
+        const double rt = cc == 0 ? o.rtol : o.rtol_fsa, at = cc == 0 ? o.atol : o.atol_fsa;
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) {
+            const double ew = 1.0 / (rt * fabs(S.zn[0][r][cc]) + at);
+            const double den = 0.1 * fabs(S.zn[0][r][cc]) + 1.0 / ew;
+            const double v = fabs(S.zn[1][r][cc]) / den;
+            hub_inv = (v > hub_inv || v != v) ? v : hub_inv;
+        }
+    }
+    hub_inv = g.max(hub_inv);
+    double hub = 0.1 * tdist;
+    if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
+    double hg = sqrt(hlb * hub);
+    if (hub < hlb) {
+        *h_out = sign * hg;
+        return AB_SUCCESS;
+    }
+    double hs = hg, hnew = hg;
+    for (int count1 = 1; count1 <= 4; count1++) {
+        bool hgOK = false;
+        double yddnrm = 0.0;
+        for (int count2 = 1; count2 <= 4; count2++) {
+            const double hgs = hg * sign;
+            const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn + hgs, hgs, 1.0, 2);
+            (*nfe)++;
+            if (ok) {
+                double m = 0.0;
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    const int cc = g.lane + G * c;
+                    if (cc >= ncols) continue;
+                    const double rt = cc == 0 ? o.rtol : o.rtol_fsa, at = cc == 0 ? o.atol : o.atol_fsa;
+                    double s = 0.0;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) {
+                        const double ew = 1.0 / (rt * fabs(S.zn[0][r][cc]) + at);
+                        const double ydd = (1.0 / hgs) * S.zn[2][r][cc] - (1.0 / hgs) * S.zn[1][r][cc];
+                        const double pr = ydd * ew;
+                        s += pr * pr;
+                    }
+                    const double n = sqrt(s * (1.0 / NX));
+                    m = (n > m || n != n) ? n : m;
+                }
+                yddnrm = g.max(m);
+                hgOK = true;
+                break;
+            }
+            hg *= 0.2;
+        }
+        if (!hgOK) {
+            if (count1 <= 2) return AB_REPTD_RHSFUNC_ERR;
+            hnew = hs;
+            break;
+        }
+        hs = hg;
+        hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
+        if (count1 == 4) break;
+        const double hrat = hnew / hg;
+        if (hrat > 0.5 && hrat < 2.0) break;
+        if (count1 > 1 && hrat > 2.0) {
+            hnew = hg;
+            break;
+        }
+        hg = hnew;
+    }
+    double h0 = 0.5 * hnew;
+    if (h0 < hlb) h0 = hlb;
+    if (h0 > hub) h0 = hub;
+    *h_out = sign * h0;
+    return AB_SUCCESS;
+}
+
+// cvSLdet (cvodes.c:8256): stability-limit detection on the 5-deep history of scaled derivative norms.
+// s[i][k]: i = 1 (current) .. 5 (oldest), k = 1..3 (orders q-1, q, q+1).  All loops are unrolled with static
+// indices so that the work arrays live in registers; divisions whose divisor has been range-checked use fast_div.
+AB_HD int bdf_sldet(const double (&s)[6][4], const int q) {
+    const double TINY_ = 1e-10;
+    double rav[4], qkr[4], sigsq[4], smax[4], ssmax[4], vrat[4], qc[6][4], qco[6][4];
+    const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
+    double rr = 0.0;
+    int kflag = 0;
+    bool bad = false;
+    AB_UNROLL
+    for (int kk = 1; kk <= 3; kk++) {
+        double smink = s[1][kk], smaxk = 0.0;
+        AB_UNROLL
+        for (int i = 1; i <= 5; i++) {
+            smink = ab_min(smink, s[i][kk]);
+            smaxk = ab_max(smaxk, s[i][kk]);
+        }
+        bad = bad || (smink < TINY_ * smaxk);
+        smax[kk] = smaxk;
+        ssmax[kk] = smaxk * smaxk;
+    }
+    if (bad) return -1;
+    AB_UNROLL
+    for (int kk = 1; kk <= 3; kk++) {
+        double sumrat = 0.0, sumrsq = 0.0;
+        AB_UNROLL
+        for (int i = 1; i <= 4; i++) {
+            const double rat = fast_div(s[i][kk], s[i + 1][kk]);
+            sumrat += rat;
+            sumrsq += rat * rat;
+        }
+        rav[kk] = 0.25 * sumrat;
+        vrat[kk] = fabs(0.25 * sumrsq - rav[kk] * rav[kk]);
+        qc[5][kk] = s[1][kk] * s[3][kk] - s[2][kk] * s[2][kk];
+        qc[4][kk] = s[2][kk] * s[3][kk] - s[1][kk] * s[4][kk];
+        qc[3][kk] = 0.0;
+        qc[2][kk] = s[2][kk] * s[5][kk] - s[3][kk] * s[4][kk];
+        qc[1][kk] = s[4][kk] * s[4][kk] - s[3][kk] * s[5][kk];
+        AB_UNROLL
+        for (int i = 1; i <= 5; i++) qco[i][kk] = qc[i][kk];
+    }
+    const double vmin = ab_min(vrat[1], ab_min(vrat[2], vrat[3]));
+    const double vmax = ab_max(vrat[1], ab_max(vrat[2], vrat[3]));
+    if (vmin < vrrtol * vrrtol) {
+        if (vmax > vrrt2 * vrrt2) return -2;
+        rr = (rav[1] + rav[2] + rav[3]) / 3.0;
+        double drrmax = 0.0;
+        AB_UNROLL
+        for (int kk = 1; kk <= 3; kk++) drrmax = ab_max(drrmax, fabs(rav[kk] - rr));
+        if (drrmax > vrrt2) return -3;
+        kflag = 1;
+    } else {
+        if (fabs(qco[1][1]) < TINY_ * ssmax[1]) return -4;
+        double tem = fast_div(qco[1][2], qco[1][1]);
+        AB_UNROLL
+        for (int i = 2; i <= 5; i++) qco[i][2] -= tem * qco[i][1];
+        tem = fast_div(qco[1][3], qco[1][1]);
+        AB_UNROLL
+        for (int i = 2; i <= 5; i++) qco[i][3] -= tem * qco[i][1];
+        if (fabs(qco[2][2]) < TINY_ * ssmax[2]) return -4;
+        tem = fast_div(qco[2][3], qco[2][2]);
+        AB_UNROLL
+        for (int i = 3; i <= 5; i++) qco[i][3] -= tem * qco[i][2];
+        if (fabs(qco[4][3]) < TINY_ * ssmax[3]) return -4;
+        rr = -fast_div(qco[5][3], qco[4][3]);
+        if (rr < TINY_ || rr > 100.0) return -5;
+        AB_UNROLL
+        for (int kk = 1; kk <= 3; kk++)
+            qkr[kk] = qc[5][kk] + rr * (qc[4][kk] + rr * rr * (qc[2][kk] + rr * qc[1][kk]));
+        double sqmax = 0.0;
+        AB_UNROLL
+        for (int kk = 1; kk <= 3; kk++) {
+            const double saqk = fast_div(fabs(qkr[kk]), ssmax[kk]);
+            if (saqk > sqmax) sqmax = saqk;
+        }
+        if (sqmax < sqtol) {
+            kflag = 2;
+        } else {
+            // Newton corrections to improve rr (rolled: this branch is rare)
+            double sqmin = 0.0;
+            AB_NOUNROLL
+            for (int it = 1; it <= 3; it++) {
+                double rrc[4], sqmx[4], qjk[4][4];
+                AB_UNROLL
+                for (int kk = 1; kk <= 3; kk++) {
+                    const double qp = qc[4][kk] + rr * rr * (3.0 * qc[2][kk] + rr * 4.0 * qc[1][kk]);
+                    double drr = 0.0;
+                    if (fabs(qp) > TINY_ * ssmax[kk]) drr = -qkr[kk] / qp;
+                    rrc[kk] = rr + drr;
+                }
+                AB_UNROLL
+                for (int kk = 1; kk <= 3; kk++) {
+                    const double sv = rrc[kk];
+                    double sqmaxk = 0.0;
+                    AB_UNROLL
+                    for (int j = 1; j <= 3; j++) {
+                        qjk[j][kk] = qc[5][j] + sv * (qc[4][j] + sv * sv * (qc[2][j] + sv * qc[1][j]));
+                        const double saqj = fast_div(fabs(qjk[j][kk]), ssmax[j]);
+                        if (saqj > sqmaxk) sqmaxk = saqj;
+                    }
+                    sqmx[kk] = sqmaxk;
+                }
+                sqmin = sqmx[1] + 1.0;
+                int kmin = 1;
+                AB_UNROLL
+                for (int kk = 1; kk <= 3; kk++)
+                    if (sqmx[kk] < sqmin) {
+                        kmin = kk;
+                        sqmin = sqmx[kk];
+                    }
+                rr = (kmin == 1) ? rrc[1] : (kmin == 2) ? rrc[2] : rrc[3];
+                if (sqmin < sqtol) {
+                    kflag = 3;
+                    break;
+                }
+                AB_UNROLL
+                for (int j = 1; j <= 3; j++) qkr[j] = (kmin == 1) ? qjk[j][1] : (kmin == 2) ? qjk[j][2] : qjk[j][3];
+            }
+            if (sqmin > sqtol) return -6;
+        }
+    }
+    bool bad7 = false;
+    AB_UNROLL
+    for (int kk = 1; kk <= 3; kk++) {
+        const double rsa = s[1][kk], rsb = s[2][kk] * rr, rsc = s[3][kk] * rr * rr;
+        const double rsd = s[4][kk] * rr * rr * rr;
+        const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
+        const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c, rd3a = rd2a - rd2b;
+        // CVODES returns -7 at the first k that fails; later k are not evaluated there, and their values are unused here
+        const bool small = fabs(rd1b) < TINY_ * smax[kk];
+        const double cest1 = small ? 1.0 : -rd3a / rd1b;
+        bad7 = bad7 || small || (cest1 < TINY_ || cest1 > 4.0);
+        const double corr1 = fast_div(fast_div(rd2b, cest1), rr * rr);
+        sigsq[kk] = s[3][kk] + corr1;
+    }
+    if (bad7) return -7;
+    if (sigsq[2] < TINY_) return -8;
+    const double ratp = fast_div(sigsq[3], sigsq[2]), ratm = fast_div(sigsq[1], sigsq[2]);
+    const double qfac1 = 0.25 * (q * q - 1.0), qfac2 = 2.0 / (q - 1.0);
+    const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
+    const double tem = 1.0 - qfac2 * bb;
+    if (fabs(tem) < TINY_) return -8;
+    const double rrb = 1.0 / tem;
+    if (fabs(rrb - rr) > rrtol) return -9;
+    if (rr > rrcut) {
+        if (kflag == 1) kflag = 4;
+        if (kflag == 2) kflag = 5;
+        if (kflag == 3) kflag = 6;
+    }
+    return kflag;
+}
+
+// x^(1/n): one out-of-line copy for the four step-size formulas (eta = 1/((bias*err)^(1/n) + addon))
+AB_COLD inline double nth_root(double x, int n) { return pow(x, 1.0 / n); }
+
+// Dense LU with partial pivoting of I - gamma*J (J = S.savedJ) in shared memory: the fallback when the emitted
+// static-pivot sparse LU rejects a pivot (SUNLinSol_Dense semantics). Returns false on an exactly singular matrix.
+template <class M, int G, int C>
+struct DenseRef {
+    typename Layout<M, G, C>::Shared& S;
+    AB_HD double& operator()(int r, int c) { return S.lu[r][c]; }
+};
+
+template <class M, int G, int C>
+AB_COLD bool cold_dense_factor(typename Layout<M, G, C>::Shared& S, double gamma) {
+    constexpr int NX = M::NX;
+    Group<G> g;
+    g.sync();
+    int ok = 1;
+    if (g.lane == 0) {
+        DenseRef<M, G, C> A{S};
+        M::jac_to_A(S.savedJ, gamma, A);
+        for (int kk = 0; kk < NX; ++kk) {
+            int pr = kk;
+            double best = fabs(S.lu[kk][kk]);
+            for (int i = kk + 1; i < NX; ++i) {
+                const double a = fabs(S.lu[i][kk]);
+                if (a > best) { best = a; pr = i; }
+            }
+            S.piv[kk] = pr;
+            if (best == 0.0) { ok = 0; break; }
+            if (pr != kk)
+                for (int j = 0; j < NX; ++j) {
+                    const double tmp = S.lu[kk][j];
+                    S.lu[kk][j] = S.lu[pr][j];
+                    S.lu[pr][j] = tmp;
+                }
+            const double inv = 1.0 / S.lu[kk][kk];
+            for (int i = kk + 1; i < NX; ++i) {
+                const double m = S.lu[i][kk] * inv;
+                S.lu[i][kk] = m;
+                if (m != 0.0)
+                    for (int j = kk + 1; j < NX; ++j) S.lu[i][j] -= m * S.lu[kk][j];
+            }
+        }
+    }
+    ok = g.bcast(ok, 0);
+    g.sync();
+    return ok != 0;
+}
+
+// b <- A^{-1} b with the dense factors, one column (b lives in the caller's local memory)
+template <class M, int G, int C>
+AB_COLD void cold_dense_solve(const typename Layout<M, G, C>::Shared& S, double* b) {
+    constexpr int NX = M::NX;
+    for (int kk = 0; kk < NX; ++kk) {
+        const int pr = S.piv[kk];
+        const double tmp = b[kk];
+        b[kk] = b[pr];
+        b[pr] = tmp;
+    }
+    for (int i = 1; i < NX; ++i) {
+        double s = b[i];
+        for (int j = 0; j < i; ++j) s -= S.lu[i][j] * b[j];
+        b[i] = s;
+    }
+    for (int i = NX - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int j = i + 1; j < NX; ++j) s -= S.lu[i][j] * b[j];
+        b[i] = s / S.lu[i][i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the solver
+// ---------------------------------------------------------------------------------------------
 template <class M, int G, int C>
 struct Bdf {
     static constexpr int NX = M::NX;
-    static constexpr int NCOLS = (G * C < M::NP + 1) ? G * C : M::NP + 1;  // columns that can ever be active
-    using Shared = TrajShared<M, NCOLS>;
+    static constexpr int NCOLS = Layout<M, G, C>::NCOLS;
+    using Shared = typename Layout<M, G, C>::Shared;
+    using Eval = ModelEval<M, C>;
 
     Shared& S;
     const SolverOptions& o;
@@ -69,15 +520,16 @@ struct Bdf {
     double acor[C][NX];
     double ewt[C][NX];
 
-    // step control (group-uniform scalars; CVodeMem fields of the same name)
+    // step control (group-uniform scalars; CVodeMem fields of the same name). Arrays are only ever
+    // indexed with compile-time constants (unrolled, predicated loops) so that they stay in registers.
     double tn, h, hscale, hprime, eta, etamax, etaq, etaqm1, etaqp1, hu;
     double tau[LMAX + 1], l[LMAX], tq[6];
     double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
     double tstop, tretlast;
     int q, qprime, qwait, L, qu;
     int nst, nstlp, nstlj, nscon, nfe, netf, ncfn, nni, nsetups, nje;
-    int convfail;
-    bool jcur, tstopset;
+    int convfail, ss_head;
+    bool jcur, tstopset, dense_lu;
 
     AB_HD Bdf(Shared& s, const SolverOptions& opt, int ncols_) : S(s), o(opt), ncols(ncols_) {}
 
@@ -100,7 +552,7 @@ struct Bdf {
                 const double pr = v[c][r] * ewt[c][r];
                 s += pr * pr;
             }
-            const double n = sqrt(s / NX);
+            const double n = sqrt(s * (1.0 / NX));
             m = (n > m || n != n) ? n : m;
         }
         return g.max(m);
@@ -117,24 +569,10 @@ struct Bdf {
                 const double pr = S.zn[j][r][col(c)] * ewt[c][r];
                 s += pr * pr;
             }
-            const double n = sqrt(s / NX);
+            const double n = sqrt(s * (1.0 / NX));
             m = (n > m || n != n) ? n : m;
         }
         return g.max(m);
-    }
-    // WRMS of the state column only (used by cvBDFStab)
-    AB_HD double wrms_state_zn(int j) const {
-        double n = 0.0;
-        if (g.lane == 0) {
-            double s = 0.0;
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) {
-                const double pr = S.zn[j][r][0] * ewt[0][r];
-                s += pr * pr;
-            }
-            n = sqrt(s / NX);
-        }
-        return g.bcast(n, 0);
     }
 
     // cvEwtSetSS (cvodes.c:9118) / cvSensEwtSetSS (:9263)
@@ -145,162 +583,37 @@ struct Bdf {
             const bool st = (col(c) == 0);
             const double rt = st ? o.rtol : o.rtol_fsa, at = st ? o.atol : o.atol_fsa;
             AB_UNROLL
-            for (int r = 0; r < NX; ++r) ewt[c][r] = 1.0 / (rt * fabs(S.zn[0][r][col(c)]) + at);
+            for (int r = 0; r < NX; ++r) ewt[c][r] = fast_div(1.0, rt * fabs(S.zn[0][r][col(c)]) + at);
         }
     }
 
     // -----------------------------------------------------------------------------------------
-    // model right-hand sides
+    // linear algebra: emitted sparse LU (M::lu_factor / M::lu_solve) with a dense pivoted fallback
     // -----------------------------------------------------------------------------------------
-    struct ModelEval {
-        double y[NX];                                   // state column (broadcast)
-        double spl[M::NSPL > 0 ? M::NSPL : 1];
-        double sspl[C][M::NSPL > 0 ? M::NSPL : 1];
-    };
-
-    AB_HD void eval_splines(double t, ModelEval& e) const {
-        AB_UNROLL
-        for (int is = 0; is < M::NSPL; ++is) {
-            const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
-            e.spl[is] = M::SPL_LOG ? exp(v) : v;
-            AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                e.sspl[c][is] = 0.0;
-                if (!active(c) || col(c) == 0) continue;
-                const double s = spline_eval_scaled<M, NCOLS>(S.spl, is, col(c), t, false);
-                e.sspl[c][is] = M::SPL_LOG ? s * e.spl[is] : s;
-            }
-        }
-    }
-
-    // Broadcast the state column ycol0 (valid on the lane that owns column 0) to all lanes.
-    AB_HD void bcast_state(const double (&v)[C][NX], ModelEval& e) {
-        if (G == 1) {
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) e.y[r] = v[0][r];
-            return;
-        }
-        g.sync();
-        if (g.lane == 0) {
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) S.ybuf[r] = v[0][r];
-        }
-        g.sync();
-        AB_UNROLL
-        for (int r = 0; r < NX; ++r) e.y[r] = S.ybuf[r];
-    }
-
-    // f for column 0, J(y)*s_c + dfdp_c for sensitivity columns (Model_ODE::fxdot / fsxdot,
-    // reference src/model_ode.cpp:105-114, :426-450).  ycols = current values of all own columns.
-    // Returns false if any output is non-finite (AMICI's check_finite -> recoverable error).
-    AB_HD bool rhs(double t, const double (&ycols)[C][NX], double (&out)[C][NX], ModelEval& e) {
-        bcast_state(ycols, e);
-        eval_splines(t, e);
-        double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
-        bool need_j = false;
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) need_j = need_j || (active(c) && col(c) > 0);
-        if (need_j) M::jac(t, e.y, S.p, S.k, S.h, e.spl, Jv);
-        bool ok = true;
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            if (col(c) == 0) {
-                M::xdot(t, e.y, S.p, S.k, S.h, e.spl, out[c]);
-            } else {
-                M::dxdotdp(S.ip_of_col[col(c)], t, e.y, S.p, S.k, S.h, e.spl, e.sspl[c], out[c]);
-                M::jac_mul_add(Jv, ycols[c], out[c]);
-            }
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) ok = ok && isfinite(out[c][r]);
-        }
-        nfe++;
-        return !g.any(!ok);
-    }
-
-    // -----------------------------------------------------------------------------------------
-    // linear algebra: dense LU with partial pivoting in shared memory (SUNLinSol_Dense semantics;
-    // the reference's default KLU differs only in pivot order / round-off)
-    // -----------------------------------------------------------------------------------------
-    struct LuRef {
-        Shared& S;
-        AB_HD double& operator()(int r, int c) { return S.lu[r][c]; }
-    };
-
-    // returns false on an exactly singular matrix
-    AB_HD bool lu_factor() {
-        g.sync();
-        int ok = 1;
-        if (g.lane == 0) {
-            for (int kk = 0; kk < NX; ++kk) {
-                int pr = kk;
-                double best = fabs(S.lu[kk][kk]);
-                for (int i = kk + 1; i < NX; ++i) {
-                    const double a = fabs(S.lu[i][kk]);
-                    if (a > best) { best = a; pr = i; }
-                }
-                S.piv[kk] = pr;
-                if (best == 0.0) { ok = 0; break; }
-                if (pr != kk)
-                    for (int j = 0; j < NX; ++j) {
-                        const double tmp = S.lu[kk][j];
-                        S.lu[kk][j] = S.lu[pr][j];
-                        S.lu[pr][j] = tmp;
-                    }
-                const double inv = 1.0 / S.lu[kk][kk];
-                for (int i = kk + 1; i < NX; ++i) {
-                    const double m = S.lu[i][kk] * inv;
-                    S.lu[i][kk] = m;
-                    if (m != 0.0)
-                        for (int j = kk + 1; j < NX; ++j) S.lu[i][j] -= m * S.lu[kk][j];
-                }
-            }
-        }
-        ok = g.bcast(ok, 0);
-        g.sync();
-        return ok != 0;
-    }
-
     // b <- A^{-1} b for every own column
     AB_HD void lu_solve(double (&b)[C][NX]) const {
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            // row interchanges (register array: select-swap keeps indices static)
+        if (!dense_lu) {
             AB_UNROLL
-            for (int kk = 0; kk < NX; ++kk) {
-                const int pr = S.piv[kk];
-                double vp = b[c][kk];
-                AB_UNROLL
-                for (int i = kk + 1; i < NX; ++i)
-                    if (i == pr) {
-                        const double tmp = b[c][i];
-                        b[c][i] = vp;
-                        vp = tmp;
-                    }
-                b[c][kk] = vp;
-            }
+            for (int c = 0; c < C; ++c)
+                if (active(c)) M::lu_solve(S.lus, b[c]);
+        } else {
             AB_UNROLL
-            for (int i = 1; i < NX; ++i) {
-                double s = b[c][i];
+            for (int c = 0; c < C; ++c) {
+                if (!active(c)) continue;
+                double tmp[NX];
                 AB_UNROLL
-                for (int j = 0; j < i; ++j) s -= S.lu[i][j] * b[c][j];
-                b[c][i] = s;
-            }
-            AB_UNROLL
-            for (int i = NX - 1; i >= 0; --i) {
-                double s = b[c][i];
+                for (int r = 0; r < NX; ++r) tmp[r] = b[c][r];
+                cold_dense_solve<M, G, C>(S, tmp);
                 AB_UNROLL
-                for (int j = i + 1; j < NX; ++j) s -= S.lu[i][j] * b[c][j];
-                b[c][i] = s / S.lu[i][i];
+                for (int r = 0; r < NX; ++r) b[c][r] = tmp[r];
             }
         }
     }
 
     // cvLsSetup + cvLsLinSys + cvNlsLSetupSensSim (cvodes_ls.c:1611-1710, :1386-1470; cvodes_nls_sim.c:300-331)
-    AB_HD int lsetup(bool jbad_nls, const ModelEval& e) {
+    AB_HD int lsetup(bool jbad_nls, const Eval& e) {
         if (jbad_nls) convfail = CONVFAIL_BAD_J;
-        const double dgamma = fabs(gamma / gammap - 1.0);
+        const double dgamma = fabs(fast_div(gamma, gammap) - 1.0);
         const bool jbad = (nst == 0) || (nst >= nstlj + 51) || (convfail == CONVFAIL_BAD_J && dgamma < 0.2) ||
                           (convfail == CONVFAIL_OTHER);
         double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
@@ -322,11 +635,19 @@ struct Bdf {
         bool fin = true;
         AB_UNROLL
         for (int i = 0; i < M::NNZ_J; ++i) fin = fin && isfinite(Jv[i]);
+        double LUr[M::NLU];
+        bool okf = M::lu_factor(Jv, gamma, LUr);   // every lane redundantly: no communication
+        dense_lu = false;
+        g.sync();
         if (g.lane == 0) {
-            LuRef A{S};
-            M::jac_to_A(Jv, gamma, A);
+            AB_UNROLL
+            for (int i = 0; i < M::NLU; ++i) S.lus[i] = LUr[i];
         }
-        const bool okf = lu_factor();
+        g.sync();
+        if (fin && !okf) {   // a static pivot failed the diagonal-preference test: dense partial pivoting
+            dense_lu = true;   // S.savedJ holds the Jacobian in either branch above
+            okf = cold_dense_factor<M, G, C>(S, gamma);
+        }
         nsetups++;
         gamrat = 1.0;
         gammap = gamma;
@@ -339,26 +660,36 @@ struct Bdf {
     // -----------------------------------------------------------------------------------------
     // Nordsieck array manipulation (per row in registers)
     // -----------------------------------------------------------------------------------------
-    // cvPredict (cvodes.c:6507) / cvRestore (:7373): Pascal-triangle update, sign = +1 / -1
-    AB_HD void pascal(const double sign) {
+    // cvPredict (cvodes.c:6507) / cvRestore (:7373): Pascal-triangle update, sign = +1 / -1.
+    // Rolled over the rows (operands are in shared memory) and specialised on the order, so the code stays small.
+    template <int Q>
+    AB_HD void pascal_q(const double sign) {
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             if (!active(c)) continue;
-            AB_UNROLL
+            const int cc = col(c);
+            AB_NOUNROLL
             for (int r = 0; r < NX; ++r) {
-                double z[LMAX];
+                double z[Q + 1];
                 AB_UNROLL
-                for (int j = 0; j < LMAX; ++j) z[j] = (j <= q) ? S.zn[j][r][col(c)] : 0.0;
+                for (int j = 0; j <= Q; ++j) z[j] = S.zn[j][r][cc];
                 AB_UNROLL
-                for (int kk = 1; kk <= QMAX; ++kk) {
+                for (int kk = 1; kk <= Q; ++kk) {
                     AB_UNROLL
-                    for (int j = QMAX; j >= 1; --j)
-                        if (j >= kk && j <= q && kk <= q) z[j - 1] += sign * z[j];
+                    for (int j = Q; j >= kk; --j) z[j - 1] += sign * z[j];
                 }
                 AB_UNROLL
-                for (int j = 0; j < QMAX; ++j)
-                    if (j < q) S.zn[j][r][col(c)] = z[j];
+                for (int j = 0; j < Q; ++j) S.zn[j][r][cc] = z[j];
             }
+        }
+    }
+    AB_HD void pascal(const double sign) {
+        switch (q) {
+            case 1: pascal_q<1>(sign); break;
+            case 2: pascal_q<2>(sign); break;
+            case 3: pascal_q<3>(sign); break;
+            case 4: pascal_q<4>(sign); break;
+            default: pascal_q<5>(sign); break;
         }
     }
 
@@ -367,7 +698,7 @@ struct Bdf {
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             if (!active(c)) continue;
-            AB_UNROLL
+            AB_NOUNROLL
             for (int r = 0; r < NX; ++r) {
                 double f = eta;
                 AB_UNROLL
@@ -382,170 +713,133 @@ struct Bdf {
         nscon = 0;
     }
 
-    // zn[j] += cf[j] * v for j in [j0, j1]
-    AB_HD void zn_axpy(const double* cf, int j0, int j1, const double (&v)[C][NX]) {
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            AB_UNROLL
-            for (int j = 0; j < LMAX; ++j) {
-                if (j < j0 || j > j1) continue;
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r) S.zn[j][r][col(c)] += cf[j] * v[c][r];
-            }
-        }
-    }
-
-    // cvIncreaseBDF (cvodes.c:6256)
-    AB_HD void increase_bdf() {
+    // cvIncreaseBDF (cvodes.c:6256) for deltaq = +1, cvDecreaseBDF (:6363) for deltaq = -1 (cvAdjustOrder :6134)
+    AB_HD void adjust_order(int deltaq) {
+        if (q == 2 && deltaq != 1) return;
         double ll[LMAX + 1];
-        for (int i = 0; i <= LMAX; ++i) ll[i] = 0.0;
-        double alpha0 = -1.0, alpha1 = 1.0, prod = 1.0, xiold = 1.0, hsum = hscale;
-        ll[2] = 1.0;
-        if (q > 1) {
-            for (int j = 1; j < q; ++j) {
-                hsum += tau[j + 1];
-                const double xi = hsum / hscale;
-                prod *= xi;
-                alpha0 -= 1.0 / (j + 1);
-                alpha1 += 1.0 / xi;
-                for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xiold + ll[i - 1];
-                xiold = xi;
-            }
-        }
-        const double A1 = (-alpha0 - alpha1) / prod;
-        // zn[L] = A1 * zn[indx_acor = qmax]
         AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
+        for (int i = 0; i <= LMAX; ++i) ll[i] = 0.0;
+        ll[2] = 1.0;
+        if (deltaq == 1) {
+            double alpha0 = -1.0, alpha1 = 1.0, prod = 1.0, xiold = 1.0, hsum = hscale;
             AB_UNROLL
-            for (int r = 0; r < NX; ++r) {
-                const double zL = A1 * S.zn[QMAX][r][col(c)];
-                AB_UNROLL
-                for (int j = 2; j <= QMAX; ++j) {
-                    if (j == L) S.zn[j][r][col(c)] = zL;
-                    else if (j <= q) S.zn[j][r][col(c)] += ll[j] * zL;
+            for (int j = 1; j < QMAX; ++j) {
+                if (j < q) {
+                    hsum += tau[j + 1];
+                    const double xi = hsum / hscale;
+                    prod *= xi;
+                    alpha0 -= 1.0 / (j + 1);
+                    alpha1 += 1.0 / xi;
+                    AB_UNROLL
+                    for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xiold + ll[i - 1];
+                    xiold = xi;
                 }
             }
-        }
-    }
-
-    // cvDecreaseBDF (cvodes.c:6363)
-    AB_HD void decrease_bdf() {
-        double ll[LMAX + 1];
-        for (int i = 0; i <= LMAX; ++i) ll[i] = 0.0;
-        ll[2] = 1.0;
-        double hsum = 0.0;
-        for (int j = 1; j <= q - 2; ++j) {
-            hsum += tau[j];
-            const double xi = hsum / hscale;
-            for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xi + ll[i - 1];
-        }
-        if (q > 2) {
+            const double A1 = (-alpha0 - alpha1) / prod;
+            // zn[L] = A1 * zn[qmax] (saved correction), zn[2..q] += ll[j] * zn[L]
             AB_UNROLL
             for (int c = 0; c < C; ++c) {
                 if (!active(c)) continue;
                 AB_UNROLL
                 for (int r = 0; r < NX; ++r) {
-                    double zq = 0.0;
+                    const double zL = A1 * S.zn[QMAX][r][col(c)];
                     AB_UNROLL
-                    for (int j = 2; j <= QMAX; ++j)
-                        if (j == q) zq = S.zn[j][r][col(c)];
+                    for (int j = 2; j <= QMAX; ++j) {
+                        if (j == L) S.zn[j][r][col(c)] = zL;
+                        else if (j <= q) S.zn[j][r][col(c)] += ll[j] * zL;
+                    }
+                }
+            }
+        } else if (deltaq == -1) {
+            double hsum = 0.0;
+            AB_UNROLL
+            for (int j = 1; j <= QMAX - 2; ++j) {
+                if (j <= q - 2) {
+                    hsum += tau[j];
+                    const double xi = hsum / hscale;
                     AB_UNROLL
-                    for (int j = 2; j < QMAX; ++j)
-                        if (j < q) S.zn[j][r][col(c)] -= ll[j] * zq;
+                    for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xi + ll[i - 1];
+                }
+            }
+            if (q > 2) {
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) {
+                        double zq = 0.0;
+                        AB_UNROLL
+                        for (int j = 2; j <= QMAX; ++j)
+                            if (j == q) zq = S.zn[j][r][col(c)];
+                        AB_UNROLL
+                        for (int j = 2; j < QMAX; ++j)
+                            if (j < q) S.zn[j][r][col(c)] -= ll[j] * zq;
+                    }
                 }
             }
         }
-    }
-
-    // cvAdjustOrder (cvodes.c:6134)
-    AB_HD void adjust_order(int deltaq) {
-        if (q == 2 && deltaq != 1) return;
-        if (deltaq == 1) increase_bdf();
-        else if (deltaq == -1) decrease_bdf();
-    }
-
-    // cvAdjustParams (cvodes.c:6112)
-    AB_HD void adjust_params() {
-        if (qprime != q) {
-            adjust_order(qprime - q);
-            q = qprime;
-            L = q + 1;
-            qwait = L;
-        }
-        rescale();
     }
 
     // cvSetBDF + cvSetTqBDF + cvSet (cvodes.c:6788-6892, :6617)
     AB_HD void set_coeffs() {
         double alpha0 = -1.0, alpha0_hat = -1.0, xi_inv = 1.0, xistar_inv = 1.0, hsum = h;
         l[0] = l[1] = 1.0;
-        for (int i = 2; i <= q; ++i) l[i] = 0.0;
+        AB_UNROLL
+        for (int i = 2; i < LMAX; ++i) l[i] = 0.0;
         if (q > 1) {
-            for (int j = 2; j < q; ++j) {
-                hsum += tau[j - 1];
-                xi_inv = h / hsum;
-                alpha0 -= 1.0 / j;
-                for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
+            AB_UNROLL
+            for (int j = 2; j < QMAX; ++j) {
+                if (j < q) {
+                    hsum += tau[j - 1];
+                    xi_inv = fast_div(h, hsum);
+                    alpha0 -= 1.0 / j;
+                    AB_UNROLL
+                    for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
+                }
             }
-            alpha0 -= 1.0 / q;
+            alpha0 -= (q == 2) ? 0.5 : (q == 3) ? (1.0 / 3.0) : (q == 4) ? 0.25 : 0.2;
             xistar_inv = -l[1] - alpha0;
-            hsum += tau[q - 1];
-            xi_inv = h / hsum;
+            hsum += pick(tau, q - 1);
+            xi_inv = fast_div(h, hsum);
             alpha0_hat = -l[1] - xi_inv;
-            for (int i = q; i >= 1; --i) l[i] += l[i - 1] * xistar_inv;
+            AB_UNROLL
+            for (int i = QMAX; i >= 1; --i)
+                if (i <= q) l[i] += l[i - 1] * xistar_inv;
         }
+        const double lq = pick(l, q);
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
-        tq[2] = fabs(A1 / (alpha0 * A2));
-        tq[5] = fabs(A2 * xistar_inv / (l[q] * xi_inv));
+        tq[2] = fabs(fast_div(A1, alpha0 * A2));
+        tq[5] = fabs(fast_div(A2 * xistar_inv, lq * xi_inv));
         if (qwait == 1) {
             if (q > 1) {
-                const double Cc = xistar_inv / l[q];
+                const double Cc = fast_div(xistar_inv, lq);
                 const double A3 = alpha0 + 1.0 / q;
                 const double A4 = alpha0_hat + xi_inv;
-                const double Cpinv = (1.0 - A4 + A3) / A3;
+                const double Cpinv = fast_div(1.0 - A4 + A3, A3);
                 tq[1] = fabs(Cc * Cpinv);
             } else {
                 tq[1] = 1.0;
             }
-            hsum += tau[q];
-            xi_inv = h / hsum;
+            hsum += pick(tau, q);
+            xi_inv = fast_div(h, hsum);
             const double A5 = alpha0 - (1.0 / (q + 1));
             const double A6 = alpha0_hat - xi_inv;
-            const double Cppinv = (1.0 - A6 + A5) / A2;
-            tq[3] = fabs(Cppinv / (xi_inv * (q + 2) * A5));
+            const double Cppinv = fast_div(1.0 - A6 + A5, A2);
+            tq[3] = fabs(fast_div(Cppinv, xi_inv * (q + 2) * A5));
         }
-        tq[4] = 0.1 / tq[2];  // nlscoef = CORTES = 0.1
-        rl1 = 1.0 / l[1];
+        tq[4] = fast_div(0.1, tq[2]);  // nlscoef = CORTES = 0.1
+        rl1 = fast_div(1.0, l[1]);
         gamma = h * rl1;
         if (nst == 0) gammap = gamma;
-        gamrat = (nst > 0) ? gamma / gammap : 1.0;
+        gamrat = (nst > 0) ? fast_div(gamma, gammap) : 1.0;
     }
 
     // -----------------------------------------------------------------------------------------
     // nonlinear solve: cvNls (cvodes.c:6894) + SUNNonlinSolSolve_Newton (sunnonlinsol_newton.c:176-330)
-    // + cvNlsResidualSensSim / cvNlsLSolveSensSim / cvNlsConvTestSensSim (cvodes_nls_sim.c:333-515)
+    // + cvNlsResidualSensSim / cvNlsLSolveSensSim / cvNlsConvTestSensSim (cvodes_nls_sim.c:333-515).
+    // One residual site, one solve site.
     // -----------------------------------------------------------------------------------------
-    // residual: res = rl1*zn1 + ycor - gamma * F(tn, zn0 + ycor); returns false on non-finite rhs
-    AB_HD bool residual(double (&res)[C][NX], ModelEval& e) {
-        double ycur[C][NX];
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) ycur[c][r] = active(c) ? S.zn[0][r][col(c)] + acor[c][r] : 0.0;
-        }
-        const bool ok = rhs(tn, ycur, res, e);
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) res[c][r] = rl1 * S.zn[1][r][col(c)] + acor[c][r] - gamma * res[c][r];
-        }
-        return ok;
-    }
-
     AB_HD int nls(int nflag) {
         convfail = (nflag == FIRST_CALL || nflag == PREV_ERR_FAIL) ? CONVFAIL_NONE : CONVFAIL_OTHER;
         bool callSetup = (nflag == PREV_CONV_FAIL) || (nflag == PREV_ERR_FAIL) || (nst == 0) ||
@@ -556,52 +850,60 @@ struct Bdf {
             for (int r = 0; r < NX; ++r) acor[c][r] = 0.0;
         }
         bool jbad = false;
-        int ret;
-        ModelEval e;
+        int ret = AB_SUCCESS;
+        Eval e;
         double delta[C][NX];
-        for (;;) {
+        for (;;) {          // attempts (at most two: stale Jacobian data, then fresh)
             int m = 0;
-            ret = AB_SUCCESS;
-            if (!residual(delta, e)) ret = NLS_RHS_RECVR;
-            if (ret == AB_SUCCESS && callSetup) ret = lsetup(jbad, e);
-            if (ret == AB_SUCCESS) {
-                for (;;) {
-                    nni++;
+            for (;;) {      // Newton iterations
+                // residual: rl1*zn1 + ycor - gamma * F(tn, zn0 + ycor)
+                {
+                    double ycur[C][NX];
                     AB_UNROLL
                     for (int c = 0; c < C; ++c) {
                         AB_UNROLL
-                        for (int r = 0; r < NX; ++r) delta[c][r] = -delta[c][r];
+                        for (int r = 0; r < NX; ++r) ycur[c][r] = active(c) ? S.zn[0][r][col(c)] + acor[c][r] : 0.0;
                     }
-                    lu_solve(delta);
-                    if (gamrat != 1.0) {
-                        const double sc = 2.0 / (1.0 + gamrat);
-                        AB_UNROLL
-                        for (int c = 0; c < C; ++c) {
-                            AB_UNROLL
-                            for (int r = 0; r < NX; ++r) delta[c][r] *= sc;
-                        }
-                    }
-                    AB_UNROLL
-                    for (int c = 0; c < C; ++c) {
-                        if (!active(c)) continue;
-                        AB_UNROLL
-                        for (int r = 0; r < NX; ++r) acor[c][r] += delta[c][r];
-                    }
-                    const double Del = wrms_max(delta);
-                    if (m > 0) crate = ab_max(0.3 * crate, Del / delp);
-                    const double dcon = Del * ab_min(1.0, crate) / tq[4];
-                    if (dcon <= 1.0) {
-                        acnrm = (m == 0) ? Del : wrms_max(acor);
-                        jcur = false;
-                        return AB_SUCCESS;
-                    }
-                    if (!(Del == Del)) { ret = NLS_CONV_RECVR; break; }  // NaN correction: treat as divergence
-                    if (m >= 1 && Del > 2.0 * delp) { ret = NLS_CONV_RECVR; break; }
-                    delp = Del;
-                    m++;
-                    if (m >= o.max_nonlin_iters) { ret = NLS_CONV_RECVR; break; }
-                    if (!residual(delta, e)) { ret = NLS_RHS_RECVR; break; }
+                    const bool ok = model_rhs<M, G, C>(S, g, ncols, tn, ycur, delta, e);
+                    nfe++;
+                    if (!ok) { ret = NLS_RHS_RECVR; break; }
                 }
+                if (m == 0 && callSetup) {
+                    ret = lsetup(jbad, e);
+                    if (ret != AB_SUCCESS) break;
+                }
+                nni++;
+                // delta <- -A^{-1} residual
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r)
+                        delta[c][r] = -(rl1 * S.zn[1][r][col(c)] + acor[c][r] - gamma * delta[c][r]);
+                }
+                lu_solve(delta);
+                const double sc = (gamrat != 1.0) ? fast_div(2.0, 1.0 + gamrat) : 1.0;   // cvLsSolve scaling
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) {
+                        if (gamrat != 1.0) delta[c][r] *= sc;
+                        acor[c][r] += delta[c][r];
+                    }
+                }
+                const double Del = wrms_max(delta);
+                if (m > 0) crate = ab_max(0.3 * crate, fast_div(Del, delp));
+                const double dcon = fast_div(Del * ab_min(1.0, crate), tq[4]);
+                if (dcon <= 1.0) {
+                    acnrm = (m == 0) ? Del : wrms_max(acor);
+                    jcur = false;
+                    return AB_SUCCESS;
+                }
+                if (!(Del == Del) || (m >= 1 && Del > 2.0 * delp)) { ret = NLS_CONV_RECVR; break; }
+                delp = Del;
+                m++;
+                if (m >= o.max_nonlin_iters) { ret = NLS_CONV_RECVR; break; }
             }
             // recoverable failure with stale Jacobian data: retry once with a fresh J
             if (ret > 0 && !jcur) {
@@ -619,95 +921,31 @@ struct Bdf {
         return ret;
     }
 
-    // cvHandleNFlag (cvodes.c:7309): returns 0 = do error test, 1 = predict again, <0 = failure
-    AB_HD int handle_nflag(int& nflag, double saved_t, int& ncf) {
-        if (nflag == AB_SUCCESS) return 0;
-        ncfn++;
-        pascal(-1.0);
-        tn = saved_t;
-        ncf++;
-        etamax = 1.0;
-        if (fabs(h) <= 0.0 /*hmin*/ * 1.000001 || ncf == o.max_conv_fails) {
-            return (nflag == NLS_RHS_RECVR) ? AB_REPTD_RHSFUNC_ERR : AB_CONV_FAILURE;
-        }
-        eta = 0.25;  // max(eta_cf, hmin/|h|), hmin = 0
-        nflag = PREV_CONV_FAIL;
-        rescale();
-        return 1;
-    }
-
-    // cvDoErrorTest (cvodes.c:7461): 0 = passed, 1 = try again, <0 failure
-    AB_HD int do_error_test(int& nflag, double saved_t, int& nef, double& dsm) {
-        dsm = acnrm * tq[2];
-        if (dsm <= 1.0) return 0;
-        nef++;
-        netf++;
-        nflag = PREV_ERR_FAIL;
-        pascal(-1.0);
-        tn = saved_t;
-        if (fabs(h) <= 0.0 || nef == o.max_err_test_fails) return AB_ERR_FAILURE;
-        etamax = 1.0;
-        if (nef <= 3) {  // MXNEF1
-            eta = 1.0 / (pow(6.0 * dsm, 1.0 / L) + 1e-6);
-            eta = ab_max(0.1, eta);
-            if (nef >= 2) eta = ab_min(eta, 0.2);
-            rescale();
-            return 1;
-        }
-        if (q > 1) {
-            eta = 0.1;
-            adjust_order(-1);
-            L = q;
-            q--;
-            qwait = L;
-            rescale();
-            return 1;
-        }
-        // order 1: restart from scratch with h*eta
-        eta = 0.1;
-        h *= eta;
-        hscale = h;
-        qwait = 10;  // LONG_WAIT
-        nscon = 0;
-        {
-            ModelEval e;
-            double y0[C][NX], f[C][NX];
-            AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r) y0[c][r] = active(c) ? S.zn[0][r][col(c)] : 0.0;
-            }
-            if (!rhs(tn, y0, f, e)) return AB_UNREC_RHSFUNC_ERR;
-            AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                if (!active(c)) continue;
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] = h * f[c][r];
-            }
-        }
-        return 1;
-    }
-
     // cvCompleteStep (cvodes.c:7634)
     AB_HD void complete_step() {
         nst++;
         nscon++;
         hu = h;
         qu = q;
-        for (int i = q; i >= 2; --i) tau[i] = tau[i - 1];
+        AB_UNROLL
+        for (int i = QMAX; i >= 2; --i)
+            if (i <= q) tau[i] = tau[i - 1];
         if (q == 1 && nst > 1) tau[2] = tau[1];
         tau[1] = h;
-        zn_axpy(l, 0, q, acor);
         qwait--;
-        if (qwait == 1 && q != QMAX) {
+        const bool save = (qwait == 1 && q != QMAX);
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
             AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                if (!active(c)) continue;
+            for (int r = 0; r < NX; ++r) {
                 AB_UNROLL
-                for (int r = 0; r < NX; ++r) S.zn[QMAX][r][col(c)] = acor[c][r];
+                for (int j = 0; j < LMAX; ++j)
+                    if (j <= q) S.zn[j][r][col(c)] += l[j] * acor[c][r];
+                if (save) S.zn[QMAX][r][col(c)] = acor[c][r];
             }
-            saved_tq5 = tq[5];
         }
+        if (save) saved_tq5 = tq[5];
     }
 
     // cvSetEta (cvodes.c:7798) with eta_min_fx = 0, eta_max_fx = 1.5, hmin = 0
@@ -736,204 +974,93 @@ struct Bdf {
             eta = 1.0;
             return;
         }
-        etaq = 1.0 / (pow(6.0 * dsm, 1.0 / L) + 1e-6);
+        etaq = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
         if (qwait != 0) {
             eta = etaq;
             qprime = q;
-            set_eta();
-            return;
-        }
-        qwait = 2;
-        etaqm1 = 0.0;
-        if (q > 1) {
-            const double ddn = wrms_max_zn(q) * tq[1];
-            etaqm1 = 1.0 / (pow(6.0 * ddn, 1.0 / q) + 1e-6);
-        }
-        etaqp1 = 0.0;
-        if (q != QMAX && saved_tq5 != 0.0) {
-            double ratio = h / tau[2], pw = 1.0;
-            for (int i = 0; i < L; ++i) pw *= ratio;  // SUNRpowerI(h/tau[2], L)
-            const double cquot = (tq[5] / saved_tq5) * pw;
-            double tmp[C][NX];
-            AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r)
-                    tmp[c][r] = active(c) ? acor[c][r] - cquot * S.zn[QMAX][r][col(c)] : 0.0;
-            }
-            const double dup = wrms_max(tmp) * tq[3];
-            etaqp1 = 1.0 / (pow(10.0 * dup, 1.0 / (L + 1)) + 1e-6);
-        }
-        // cvChooseEta (cvodes.c:7935)
-        const double etam = ab_max(etaqm1, ab_max(etaq, etaqp1));
-        if (etam > 0.0 && etam < 1.5) {
-            eta = 1.0;
-            qprime = q;
-        } else if (etam == etaq) {
-            eta = etaq;
-            qprime = q;
-        } else if (etam == etaqm1) {
-            eta = etaqm1;
-            qprime = q - 1;
         } else {
-            eta = etaqp1;
-            qprime = q + 1;
-            AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                if (!active(c)) continue;
+            qwait = 2;
+            etaqm1 = 0.0;
+            if (q > 1) {
+                const double ddn = wrms_max_zn(q) * tq[1];
+                etaqm1 = 1.0 / (nth_root(6.0 * ddn, q) + 1e-6);
+            }
+            etaqp1 = 0.0;
+            if (q != QMAX && saved_tq5 != 0.0) {
+                double ratio = h / tau[2], pw = 1.0;
+                for (int i = 0; i < L; ++i) pw *= ratio;  // SUNRpowerI(h/tau[2], L)
+                const double cquot = (tq[5] / saved_tq5) * pw;
+                double tmp[C][NX];
                 AB_UNROLL
-                for (int r = 0; r < NX; ++r) S.zn[QMAX][r][col(c)] = acor[c][r];
+                for (int c = 0; c < C; ++c) {
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r)
+                        tmp[c][r] = active(c) ? acor[c][r] - cquot * S.zn[QMAX][r][col(c)] : 0.0;
+                }
+                const double dup = wrms_max(tmp) * tq[3];
+                etaqp1 = 1.0 / (nth_root(10.0 * dup, L + 1) + 1e-6);
+            }
+            // cvChooseEta (cvodes.c:7935)
+            const double etam = ab_max(etaqm1, ab_max(etaq, etaqp1));
+            if (etam > 0.0 && etam < 1.5) {
+                eta = 1.0;
+                qprime = q;
+            } else if (etam == etaq) {
+                eta = etaq;
+                qprime = q;
+            } else if (etam == etaqm1) {
+                eta = etaqm1;
+                qprime = q - 1;
+            } else {
+                eta = etaqp1;
+                qprime = q + 1;
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) S.zn[QMAX][r][col(c)] = acor[c][r];
+                }
             }
         }
         set_eta();
     }
 
-    // cvSLdet (cvodes.c:8256); scalar code on the shared ssdat history
-    AB_HD_NOINLINE int sldet() const {
-        const double TINY_ = 1e-10;
-        double rat[5][4], rav[4], qkr[4], sigsq[4], smax[4], ssmax[4];
-        double drr[4], rrc[4], sqmx[4], qjk[4][4], vrat[5], qc[6][4], qco[6][4];
-        const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
-        double rr = 0.0, sqmin = 0.0;
-        int kflag = 0, kmin = 0;
-        for (int kk = 1; kk <= 3; kk++) {
-            double smink = S.ssdat[1][kk], smaxk = 0.0;
-            for (int i = 1; i <= 5; i++) {
-                smink = ab_min(smink, S.ssdat[i][kk]);
-                smaxk = ab_max(smaxk, S.ssdat[i][kk]);
-            }
-            if (smink < TINY_ * smaxk) return -1;
-            smax[kk] = smaxk;
-            ssmax[kk] = smaxk * smaxk;
-            double sumrat = 0.0, sumrsq = 0.0;
-            for (int i = 1; i <= 4; i++) {
-                rat[i][kk] = S.ssdat[i][kk] / S.ssdat[i + 1][kk];
-                sumrat += rat[i][kk];
-                sumrsq += rat[i][kk] * rat[i][kk];
-            }
-            rav[kk] = 0.25 * sumrat;
-            vrat[kk] = fabs(0.25 * sumrsq - rav[kk] * rav[kk]);
-            qc[5][kk] = S.ssdat[1][kk] * S.ssdat[3][kk] - S.ssdat[2][kk] * S.ssdat[2][kk];
-            qc[4][kk] = S.ssdat[2][kk] * S.ssdat[3][kk] - S.ssdat[1][kk] * S.ssdat[4][kk];
-            qc[3][kk] = 0.0;
-            qc[2][kk] = S.ssdat[2][kk] * S.ssdat[5][kk] - S.ssdat[3][kk] * S.ssdat[4][kk];
-            qc[1][kk] = S.ssdat[4][kk] * S.ssdat[4][kk] - S.ssdat[3][kk] * S.ssdat[5][kk];
-            for (int i = 1; i <= 5; i++) qco[i][kk] = qc[i][kk];
-        }
-        const double vmin = ab_min(vrat[1], ab_min(vrat[2], vrat[3]));
-        const double vmax = ab_max(vrat[1], ab_max(vrat[2], vrat[3]));
-        if (vmin < vrrtol * vrrtol) {
-            if (vmax > vrrt2 * vrrt2) return -2;
-            rr = (rav[1] + rav[2] + rav[3]) / 3.0;
-            double drrmax = 0.0;
-            for (int kk = 1; kk <= 3; kk++) drrmax = ab_max(drrmax, fabs(rav[kk] - rr));
-            if (drrmax > vrrt2) return -3;
-            kflag = 1;
-        } else {
-            if (fabs(qco[1][1]) < TINY_ * ssmax[1]) return -4;
-            double tem = qco[1][2] / qco[1][1];
-            for (int i = 2; i <= 5; i++) qco[i][2] -= tem * qco[i][1];
-            qco[1][2] = 0.0;
-            tem = qco[1][3] / qco[1][1];
-            for (int i = 2; i <= 5; i++) qco[i][3] -= tem * qco[i][1];
-            qco[1][3] = 0.0;
-            if (fabs(qco[2][2]) < TINY_ * ssmax[2]) return -4;
-            tem = qco[2][3] / qco[2][2];
-            for (int i = 3; i <= 5; i++) qco[i][3] -= tem * qco[i][2];
-            if (fabs(qco[4][3]) < TINY_ * ssmax[3]) return -4;
-            rr = -qco[5][3] / qco[4][3];
-            if (rr < TINY_ || rr > 100.0) return -5;
-            for (int kk = 1; kk <= 3; kk++)
-                qkr[kk] = qc[5][kk] + rr * (qc[4][kk] + rr * rr * (qc[2][kk] + rr * qc[1][kk]));
-            double sqmax = 0.0;
-            for (int kk = 1; kk <= 3; kk++) {
-                const double saqk = fabs(qkr[kk]) / ssmax[kk];
-                if (saqk > sqmax) sqmax = saqk;
-            }
-            if (sqmax < sqtol) {
-                kflag = 2;
-            } else {
-                for (int it = 1; it <= 3; it++) {
-                    for (int kk = 1; kk <= 3; kk++) {
-                        const double qp = qc[4][kk] + rr * rr * (3.0 * qc[2][kk] + rr * 4.0 * qc[1][kk]);
-                        drr[kk] = 0.0;
-                        if (fabs(qp) > TINY_ * ssmax[kk]) drr[kk] = -qkr[kk] / qp;
-                        rrc[kk] = rr + drr[kk];
-                    }
-                    for (int kk = 1; kk <= 3; kk++) {
-                        const double s = rrc[kk];
-                        double sqmaxk = 0.0;
-                        for (int j = 1; j <= 3; j++) {
-                            qjk[j][kk] = qc[5][j] + s * (qc[4][j] + s * s * (qc[2][j] + s * qc[1][j]));
-                            const double saqj = fabs(qjk[j][kk]) / ssmax[j];
-                            if (saqj > sqmaxk) sqmaxk = saqj;
-                        }
-                        sqmx[kk] = sqmaxk;
-                    }
-                    sqmin = sqmx[1] + 1.0;
-                    for (int kk = 1; kk <= 3; kk++)
-                        if (sqmx[kk] < sqmin) {
-                            kmin = kk;
-                            sqmin = sqmx[kk];
-                        }
-                    rr = rrc[kmin];
-                    if (sqmin < sqtol) {
-                        kflag = 3;
-                        break;
-                    }
-                    for (int j = 1; j <= 3; j++) qkr[j] = qjk[j][kmin];
-                }
-                if (sqmin > sqtol) return -6;
-            }
-        }
-        for (int kk = 1; kk <= 3; kk++) {
-            const double rsa = S.ssdat[1][kk], rsb = S.ssdat[2][kk] * rr, rsc = S.ssdat[3][kk] * rr * rr;
-            const double rsd = S.ssdat[4][kk] * rr * rr * rr;
-            const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
-            const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c, rd3a = rd2a - rd2b;
-            if (fabs(rd1b) < TINY_ * smax[kk]) return -7;
-            const double cest1 = -rd3a / rd1b;
-            if (cest1 < TINY_ || cest1 > 4.0) return -7;
-            const double corr1 = (rd2b / cest1) / (rr * rr);
-            sigsq[kk] = S.ssdat[3][kk] + corr1;
-        }
-        if (sigsq[2] < TINY_) return -8;
-        const double ratp = sigsq[3] / sigsq[2], ratm = sigsq[1] / sigsq[2];
-        const double qfac1 = 0.25 * (q * q - 1.0), qfac2 = 2.0 / (q - 1.0);
-        const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
-        const double tem = 1.0 - qfac2 * bb;
-        if (fabs(tem) < TINY_) return -8;
-        const double rrb = 1.0 / tem;
-        if (fabs(rrb - rr) > rrtol) return -9;
-        if (rr > rrcut) {
-            if (kflag == 1) kflag = 4;
-            if (kflag == 2) kflag = 5;
-            if (kflag == 3) kflag = 6;
-        }
-        return kflag;
-    }
-
-    // cvBDFStab (cvodes.c:8158)
+    // cvBDFStab (cvodes.c:8158); the 5-deep history is a ring buffer in shared memory (no shifting)
     AB_HD void bdf_stab() {
         if (q >= 3) {
-            double factorial = 1.0;
-            for (int i = 1; i <= q - 1; i++) factorial *= i;
-            const double sq = factorial * q * (q + 1) * acnrm / ab_max(tq[5], 1e-10);
-            const double sqm1 = factorial * q * wrms_state_zn(q);
-            const double sqm2 = factorial * wrms_state_zn(q - 1);
+            const double factorial = (q == 3) ? 2.0 : (q == 4) ? 6.0 : 24.0;   // (q-1)!
+            const double sq = factorial * q * (q + 1) * fast_div(acnrm, ab_max(tq[5], 1e-10));
+            // WRMS of the state column only (lane 0 owns it)
+            double s1 = 0.0, s2 = 0.0;
+            if (g.lane == 0) {
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) {
+                    const double a = S.zn[q][r][0] * ewt[0][r], b = S.zn[q - 1][r][0] * ewt[0][r];
+                    s1 += a * a;
+                    s2 += b * b;
+                }
+            }
+            const double f2 = factorial * factorial * (1.0 / NX);
+            ss_head = (ss_head == 0) ? 4 : ss_head - 1;
             g.sync();
             if (g.lane == 0) {
-                for (int kk = 1; kk <= 3; kk++)
-                    for (int i = 5; i >= 2; i--) S.ssdat[i][kk] = S.ssdat[i - 1][kk];
-                S.ssdat[1][1] = sqm2 * sqm2;
-                S.ssdat[1][2] = sqm1 * sqm1;
-                S.ssdat[1][3] = sq * sq;
+                S.ssdat[ss_head][1] = f2 * s2;            // sqm2^2
+                S.ssdat[ss_head][2] = f2 * q * q * s1;    // sqm1^2
+                S.ssdat[ss_head][3] = sq * sq;
             }
             g.sync();
         }
         if (qprime >= q) {
             if (q >= 3 && nscon >= q + 5) {
-                const int ldflag = sldet();
+                double s[6][4];
+                AB_UNROLL
+                for (int i = 1; i <= 5; ++i) {
+                    int idx = ss_head + i - 1;
+                    idx = idx >= 5 ? idx - 5 : idx;
+                    AB_UNROLL
+                    for (int kk = 1; kk <= 3; ++kk) s[i][kk] = S.ssdat[idx][kk];
+                }
+                const int ldflag = bdf_sldet(s, q);
                 if (ldflag > 3) {
                     qprime = q - 1;
                     eta = etaqm1;
@@ -948,115 +1075,90 @@ struct Bdf {
     }
 
     // -----------------------------------------------------------------------------------------
-    // cvStep (cvodes.c:5800)
+    // cvStep (cvodes.c:5800) with cvHandleNFlag (:7309) and cvDoErrorTest (:7461) folded in: every
+    // retry path sets flags that are executed at the single history-manipulation site at the loop top.
     // -----------------------------------------------------------------------------------------
     AB_HD int step() {
         const double saved_t = tn;
         int ncf = 0, nef = 0, nflag = FIRST_CALL;
         double dsm = 0.0;
-        if (nst > 0 && hprime != h) adjust_params();
+        bool restore = false, resc = false, reload = false;
+        int dq = 0;
+        if (nst > 0 && hprime != h) {  // cvAdjustParams
+            dq = qprime - q;
+            resc = true;
+        }
         for (;;) {
-            // cvPredict
-            tn += h;
-            if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
-            pascal(1.0);
+            for (int pass = restore ? 0 : 1; pass < 2; ++pass) {
+                if (pass == 1) {
+                    if (dq != 0) {
+                        adjust_order(dq);
+                        q += dq;
+                        L = q + 1;
+                        qwait = L;
+                        dq = 0;
+                    }
+                    if (resc) rescale();
+                    if (reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
+                        const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, h, 1);
+                        nfe++;
+                        if (!ok) return AB_UNREC_RHSFUNC_ERR;
+                    }
+                    tn += h;  // cvPredict
+                    if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
+                }
+                pascal(pass == 0 ? -1.0 : 1.0);
+                if (pass == 0) tn = saved_t;
+            }
+            restore = resc = reload = false;
             set_coeffs();
             nflag = nls(nflag);
-            const int kflag = handle_nflag(nflag, saved_t, ncf);
-            if (kflag == 1) continue;
-            if (kflag < 0) return kflag;
-            const int eflag = do_error_test(nflag, saved_t, nef, dsm);
-            if (eflag == 1) continue;
-            if (eflag < 0) return eflag;
-            break;
+            if (nflag != AB_SUCCESS) {  // cvHandleNFlag
+                ncfn++;
+                ncf++;
+                etamax = 1.0;
+                if (ncf == o.max_conv_fails) {
+                    tn = saved_t;
+                    return (nflag == NLS_RHS_RECVR) ? AB_REPTD_RHSFUNC_ERR : AB_CONV_FAILURE;
+                }
+                eta = 0.25;  // max(eta_cf, hmin/|h|), hmin = 0
+                nflag = PREV_CONV_FAIL;
+                restore = resc = true;
+                continue;
+            }
+            dsm = acnrm * tq[2];  // cvDoErrorTest
+            if (dsm <= 1.0) break;
+            nef++;
+            netf++;
+            nflag = PREV_ERR_FAIL;
+            restore = true;
+            if (nef == o.max_err_test_fails) {
+                tn = saved_t;
+                return AB_ERR_FAILURE;
+            }
+            etamax = 1.0;
+            if (nef <= 3) {  // MXNEF1
+                eta = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
+                eta = ab_max(0.1, eta);
+                if (nef >= 2) eta = ab_min(eta, 0.2);
+                resc = true;
+            } else if (q > 1) {  // force an order reduction
+                eta = 0.1;
+                dq = -1;
+                resc = true;
+            } else {  // already at order 1: restart from scratch with h*eta
+                eta = 0.1;
+                h *= eta;
+                hscale = h;
+                qwait = 10;  // LONG_WAIT
+                nscon = 0;
+                reload = true;
+            }
         }
         complete_step();
         prepare_next_step(dsm);
         if (o.stldet) bdf_stab();
         etamax = 10.0;  // eta_max_es == eta_max_gs == 10
-        return AB_SUCCESS;
-    }
-
-    // -----------------------------------------------------------------------------------------
-    // initial step size: cvHin / cvUpperBoundH0 / cvYddNorm (cvodes.c:5436-5798)
-    // -----------------------------------------------------------------------------------------
-    AB_HD int hin(double tout) {
-        const double tdiff = tout - tn;
-        if (tdiff == 0.0) return AB_TOO_CLOSE;
-        const double sign = tdiff > 0.0 ? 1.0 : -1.0;
-        const double tdist = fabs(tdiff);
-        const double tround = DBL_EPSILON * ab_max(fabs(tn), fabs(tout));
-        if (tdist < 2.0 * tround) return AB_TOO_CLOSE;
-        const double hlb = 100.0 * tround;
-        // cvUpperBoundH0
-        double hub_inv = 0.0;
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) {
-                const double den = 0.1 * fabs(S.zn[0][r][col(c)]) + 1.0 / ewt[c][r];
-                const double v = fabs(S.zn[1][r][col(c)]) / den;
-                hub_inv = (v > hub_inv || v != v) ? v : hub_inv;
-            }
-        }
-        hub_inv = g.max(hub_inv);
-        double hub = 0.1 * tdist;
-        if (hub * hub_inv > 1.0) hub = 1.0 / hub_inv;
-        double hg = sqrt(hlb * hub);
-        if (hub < hlb) {
-            h = sign * hg;
-            return AB_SUCCESS;
-        }
-        double hs = hg, hnew = hg;
-        for (int count1 = 1; count1 <= 4; count1++) {
-            bool hgOK = false;
-            double yddnrm = 0.0;
-            for (int count2 = 1; count2 <= 4; count2++) {
-                const double hgs = hg * sign;
-                // cvYddNorm
-                ModelEval e;
-                double yy[C][NX], f[C][NX];
-                AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    AB_UNROLL
-                    for (int r = 0; r < NX; ++r)
-                        yy[c][r] = active(c) ? hgs * S.zn[1][r][col(c)] + S.zn[0][r][col(c)] : 0.0;
-                }
-                const bool ok = rhs(tn + hgs, yy, f, e);
-                if (ok) {
-                    AB_UNROLL
-                    for (int c = 0; c < C; ++c) {
-                        AB_UNROLL
-                        for (int r = 0; r < NX; ++r)
-                            f[c][r] = active(c) ? (1.0 / hgs) * f[c][r] - (1.0 / hgs) * S.zn[1][r][col(c)] : 0.0;
-                    }
-                    yddnrm = wrms_max(f);
-                    hgOK = true;
-                    break;
-                }
-                hg *= 0.2;
-            }
-            if (!hgOK) {
-                if (count1 <= 2) return AB_REPTD_RHSFUNC_ERR;
-                hnew = hs;
-                break;
-            }
-            hs = hg;
-            hnew = (yddnrm * hub * hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(hg * hub);
-            if (count1 == 4) break;
-            const double hrat = hnew / hg;
-            if (hrat > 0.5 && hrat < 2.0) break;
-            if (count1 > 1 && hrat > 2.0) {
-                hnew = hg;
-                break;
-            }
-            hg = hnew;
-        }
-        double h0 = 0.5 * hnew;
-        if (h0 < hlb) h0 = hlb;
-        if (h0 > hub) h0 = hub;
-        h = sign * h0;
         return AB_SUCCESS;
     }
 
@@ -1071,22 +1173,26 @@ struct Bdf {
         h = hscale = hprime = hu = 0.0;
         eta = 1.0;
         nst = nstlp = nstlj = nscon = nfe = netf = ncfn = nni = nsetups = nje = 0;
+        AB_UNROLL
         for (int i = 0; i <= LMAX; ++i) tau[i] = 0.0;
+        AB_UNROLL
         for (int i = 0; i < LMAX; ++i) l[i] = 0.0;
+        AB_UNROLL
         for (int i = 0; i < 6; ++i) tq[i] = 0.0;
         rl1 = gamma = gammap = gamrat = 1.0;
         crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5 = 0.0;
         etaq = etaqm1 = etaqp1 = 0.0;
         tstopset = false; tstop = 0.0; tretlast = t0;
-        convfail = CONVFAIL_NONE; jcur = false;
+        convfail = CONVFAIL_NONE; jcur = false; dense_lu = false;
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             AB_UNROLL
             for (int r = 0; r < NX; ++r) { acor[c][r] = 0.0; ewt[c][r] = 0.0; }
         }
         g.sync();
+        ss_head = 0;
         if (g.lane == 0)
-            for (int i = 0; i < 6; ++i)
+            for (int i = 0; i < 5; ++i)
                 for (int kk = 0; kk < 4; ++kk) S.ssdat[i][kk] = 0.0;
         g.sync();
         set_ewt();  // cvInitialSetup
@@ -1103,26 +1209,17 @@ struct Bdf {
         tstop = tout;
         tstopset = true;
         if (nst == 0) {
-            // first call: zn[1] = h * f(t0, y0) (cvodes.c first-call block)
-            {
-                ModelEval e;
-                double y0[C][NX], f[C][NX];
-                AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    AB_UNROLL
-                    for (int r = 0; r < NX; ++r) y0[c][r] = active(c) ? S.zn[0][r][col(c)] : 0.0;
-                }
-                if (!rhs(tn, y0, f, e)) return AB_FIRST_RHSFUNC_ERR;
-                AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    if (!active(c)) continue;
-                    AB_UNROLL
-                    for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] = f[c][r];
-                }
-            }
+            // first call: zn[1] = f(t0, y0) (cvodes.c first-call block), initial step, zn[1] *= h
+            const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, 1.0, 1);
+            nfe++;
+            if (!ok) return AB_FIRST_RHSFUNC_ERR;
             if ((tstop - tn) * (tout - tn) <= 0.0) return AB_ILL_INPUT;
-            const int hflag = hin(tout);
+            double h0 = 0.0;
+            int nfe_hin = 0;
+            const int hflag = cold_hin<M, G, C>(S, o, ncols, tn, tout, &h0, &nfe_hin);
+            nfe += nfe_hin;
             if (hflag != AB_SUCCESS) return hflag;
+            h = h0;
             const double rh = fabs(h) * o.hmax_inv;
             if (rh > 1.0) h /= rh;
             if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);

@@ -8,12 +8,14 @@
 
 #if defined(__CUDACC__)
 #define AB_HD __host__ __device__ __forceinline__
-#define AB_HD_NOINLINE __host__ __device__ __noinline__
+#define AB_COLD __host__ __device__ __noinline__
 #define AB_UNROLL _Pragma("unroll")
+#define AB_NOUNROLL _Pragma("unroll 1")
 #else
 #define AB_HD inline
-#define AB_HD_NOINLINE
+#define AB_COLD __attribute__((noinline))
 #define AB_UNROLL
+#define AB_NOUNROLL
 #endif
 
 namespace amici_b200 {
@@ -45,6 +47,21 @@ enum : int { AB_PSCALE_NONE = 0, AB_PSCALE_LN = 1, AB_PSCALE_LOG10 = 2 };
 #if !defined(__CUDACC__)
 using std::isfinite;
 #endif
+
+// a / b for finite, normal, non-zero b: reciprocal seed + two Newton steps + one residual correction
+// (8 instructions instead of the ~25 of the IEEE division sequence; result within 1-2 ulp). Host builds divide.
+AB_HD double fast_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(r, fma(-b, r, 1.0), r);
+    r = fma(r, fma(-b, r, 1.0), r);
+    const double q = a * r;
+    return fma(r, fma(-b, q, a), q);
+#else
+    return a / b;
+#endif
+}
 
 AB_HD double ab_max(double a, double b) { return a > b ? a : b; }
 AB_HD double ab_min(double a, double b) { return a < b ? a : b; }

@@ -96,15 +96,15 @@ struct Simulation {
         auto& g = bdf.g;
         const int nt = b.nt;
         const double t = b.ts[it];
-        typename Solver::ModelEval e;
+        typename Solver::Eval e;
         double xc[C][NX];
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             AB_UNROLL
             for (int r = 0; r < NX; ++r) xc[c][r] = bdf.active(c) ? S.zn[0][r][bdf.col(c)] : 0.0;
         }
-        bdf.bcast_state(xc, e);
-        bdf.eval_splines(t, e);
+        bcast_state<M, G, C>(S, g, xc, e);
+        eval_splines<M, G, C>(S, g, bdf.ncols, t, e);
         double y[NY], sig[NY], my[NY];
         bool my_set[NY], sig_set[NY];
         M::y(t, e.y, S.p, S.k, S.h, e.spl, y);
@@ -294,15 +294,15 @@ struct Simulation {
         if (status != AB_SUCCESS) invalidate(it);
         // xdot and J at the final state (ReturnData::store_jacobian_and_derivative, reference rdata.h:707-728)
         if (full() && (b.xdot || b.J)) {
-            typename Solver::ModelEval e;
+            typename Solver::Eval e;
             double xc[C][NX];
             AB_UNROLL
             for (int c = 0; c < C; ++c) {
                 AB_UNROLL
                 for (int r = 0; r < NX; ++r) xc[c][r] = bdf.active(c) ? S.zn[0][r][bdf.col(c)] : 0.0;
             }
-            bdf.bcast_state(xc, e);
-            bdf.eval_splines(t, e);
+            bcast_state<M, G, C>(S, g, xc, e);
+            eval_splines<M, G, C>(S, g, bdf.ncols, t, e);
             if (g.lane == 0) {
                 double f[NX], Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
                 M::xdot(t, e.y, S.p, S.k, S.h, e.spl, f);
