@@ -33,7 +33,7 @@ __all__ = [
 
 AMICI_SUCCESS = 0
 AMICI_NOT_RUN = -1001
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libamici_b200.so")
+_LIB_PATH = os.environ.get("AMICI_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libamici_b200.so")
 _lib = None
 
 

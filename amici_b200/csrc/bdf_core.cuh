@@ -365,7 +365,7 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const int q) {
                 for (int kk = 1; kk <= 3; kk++) {
                     const double qp = qc[4][kk] + rr * rr * (3.0 * qc[2][kk] + rr * 4.0 * qc[1][kk]);
                     double drr = 0.0;
-                    if (fabs(qp) > TINY_ * ssmax[kk]) drr = -qkr[kk] / qp;
+                    if (fabs(qp) > TINY_ * ssmax[kk]) drr = -fast_div(qkr[kk], qp);
                     rrc[kk] = rr + drr;
                 }
                 AB_UNROLL
@@ -430,8 +430,16 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const int q) {
     return kflag;
 }
 
-// x^(1/n): one out-of-line copy for the four step-size formulas (eta = 1/((bias*err)^(1/n) + addon))
-AB_COLD inline double nth_root(double x, int n) { return pow(x, 1.0 / n); }
+// x^(1/n) for the four step-size formulas (eta = 1/((bias*err)^(1/n) + addon))
+AB_HD double nth_root(double x, int n) {
+#if defined(__CUDA_ARCH__)
+    // Step-size ratios are heuristics that CVODES itself clips and thresholds (eta < 1.5 keeps h, eta <= etamax):
+    // single-precision exp2/log2 (relative error ~1e-6 in eta) instead of the ~150-instruction double pow.
+    return (double)exp2f(__log2f((float)x) * (1.0f / (float)n));
+#else
+    return pow(x, 1.0 / n);
+#endif
+}
 
 // Dense LU with partial pivoting of I - gamma*J (J = S.savedJ) in shared memory: the fallback when the emitted
 // static-pivot sparse LU rejects a pivot (SUNLinSol_Dense semantics). Returns false on an exactly singular matrix.

@@ -9,10 +9,14 @@
 #include "registry.h"
 #include "simulate.cuh"
 
+#ifndef AB_MINBLOCKS
+#define AB_MINBLOCKS 4
+#endif
+
 namespace amici_b200 {
 
-template <class M, int G, int C, int THREADS>
-__global__ void __launch_bounds__(THREADS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head) {
+template <class M, int G, int C, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head) {
     using Sim = Simulation<M, G, C>;
     using Shared = typename Sim::Shared;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -41,12 +45,13 @@ struct Config {
     static constexpr int G = pow2_at_least(COLS);
     static constexpr int C = (COLS + G - 1) / G;
     static constexpr int THREADS = 64;  // small blocks: shared-memory granularity decides occupancy
+    static constexpr int MINBLOCKS = AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
 };
 
-template <class M, int G, int C, int THREADS>
+template <class M, int G, int C, int THREADS, int MINBLOCKS>
 int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
     using Sim = Simulation<M, G, C>;
-    auto kern = bdf_solve_kernel<M, G, C, THREADS>;
+    auto kern = bdf_solve_kernel<M, G, C, THREADS, MINBLOCKS>;
     constexpr int groups = THREADS / G;
     const size_t smem = sizeof(typename Sim::Shared) * groups;
     int dev = 0, sms = 0;
@@ -77,10 +82,10 @@ int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head,
             last_error() = "nplist exceeds the number of model parameters";
             return AB_E_UNSUPPORTED;
         }
-        return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS>(o, b, queue_head, st);
+        return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS, Config<M>::MINBLOCKS>(o, b, queue_head, st);
     }
     // no sensitivities: one thread per condition
-    return launch_variant<M, 1, 1, 32>(o, b, queue_head, st);
+    return launch_variant<M, 1, 1, 32, 1>(o, b, queue_head, st);
 }
 
 template <class M>
