@@ -387,6 +387,12 @@ class BatchResult:
     def __getitem__(self, key): return self.fields[_RDATA_ALIASES.get(key, key)]
     def __contains__(self, key): return _RDATA_ALIASES.get(key, key) in self.fields
     def __len__(self): return len(self.fields["status"])
+
+    def release(self):
+        """Return the page-locked output buffers to the pool; the arrays of this result must not be used afterwards."""
+        keep, self._keep = getattr(self, "_keep", []), []
+        self.fields = {}
+        _recycle(keep)
     def view(self, i: int) -> "ReturnDataView": return ReturnDataView(self, i)
     def views(self) -> list["ReturnDataView"]: return [ReturnDataView(self, i) for i in range(len(self))]
 
@@ -416,18 +422,33 @@ class ReturnDataView:
     def __contains__(self, key): return key == "ts" or key in self._b
 
 
+_PINNED_POOL: dict = {}   # (shape, dtype) -> [torch tensors]: page-locked output buffers are recycled explicitly
+
+
 def _pinned_empty(shape, dtype):
-    """Host output buffer; page-locked through torch when available so D2H copies run at full PCIe rate."""
+    """Host output buffer; page-locked through torch when available so D2H copies run at full PCIe rate and
+    overlap the solve. Buffers return to a pool when their BatchResult is garbage-collected (pinning 2.5 GB
+    costs seconds, so it must not happen per call)."""
     try:
         import torch
         if torch.cuda.is_available():
-            tdt = torch.float64 if dtype == np.float64 else torch.int32
-            t = torch.empty(tuple(int(s) for s in shape), dtype=tdt, pin_memory=True)
-            a = t.numpy()
-            return a, t
+            key = (tuple(int(s) for s in shape), np.dtype(dtype).str)
+            pool = _PINNED_POOL.get(key)
+            if pool:
+                t = pool.pop()
+            else:
+                tdt = torch.float64 if dtype == np.float64 else torch.int32
+                t = torch.empty(key[0], dtype=tdt, pin_memory=True)
+            return t.numpy(), (key, t)
     except Exception:  # pragma: no cover - pinned memory is an optimisation only
         pass
     return np.empty(shape, dtype=dtype), None
+
+
+def _recycle(keep):
+    for item in keep:
+        if isinstance(item, tuple) and len(item) == 2 and isinstance(item[0], tuple):
+            _PINNED_POOL.setdefault(item[0], []).append(item[1])
 
 
 def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequence[str] | None = None) -> BatchResult:

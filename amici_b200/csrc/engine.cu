@@ -10,7 +10,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -192,91 +194,125 @@ struct DevBuf {
 };
 }  // namespace
 
+// Field table of ab_batch: per-condition element counts, so that host and device views of a chunk can be built generically.
+namespace {
+struct FieldDesc {
+    size_t offset;      // offsetof(ab_batch, field)
+    size_t elem;        // sizeof element
+    size_t per_cond;    // elements per condition
+    bool input;
+};
+}  // namespace
+
 int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch* hb, float* kernel_ms) {
     const ModelEntry* e = find_model(model);
     if (!e) return AB_E_UNKNOWN_MODEL;
     int rc = check_args(opt, hb);
     if (rc != AB_OK) return rc;
+    if (kernel_ms) *kernel_ms = 0.f;
     if (hb->N == 0) return AB_OK;
     const ab_dims& d = e->dims;
     const size_t N = hb->N, nt = hb->nt, q = (opt->sensi >= 1) ? hb->nplist : 0;
-    const size_t nx = d.nx, ny = d.ny;
-    ab_batch db = *hb;
-    constexpr int MAXB = 40;
-    DevBuf bufs[MAXB];
-    int nb = 0;
-    cudaStream_t st;
-    AB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    struct Out { void* host; void* dev; size_t bytes; } outs[MAXB];
-    int nout = 0;
+    const size_t nx = d.nx, ny = d.ny, D = sizeof(double), I = sizeof(int);
+#define AB_F(f, el, cnt, in) FieldDesc{offsetof(ab_batch, f), el, (size_t)(cnt), in}
+    const FieldDesc fields[] = {
+        AB_F(p, D, d.np, true), AB_F(k, D, d.nk, true), AB_F(my, D, nt * ny, true), AB_F(sigmay_in, D, nt * ny, true),
+        AB_F(status, I, 1, false), AB_F(llh, D, 1, false), AB_F(chi2, D, 1, false), AB_F(sllh, D, q, false),
+        AB_F(x, D, nt * nx, false), AB_F(sx, D, nt * q * nx, false), AB_F(y, D, nt * ny, false),
+        AB_F(sy, D, nt * q * ny, false), AB_F(sigmay, D, nt * ny, false), AB_F(ssigmay, D, nt * q * ny, false),
+        AB_F(res, D, nt * ny, false), AB_F(sres, D, nt * ny * q, false), AB_F(FIM, D, q * q, false),
+        AB_F(x0, D, nx, false), AB_F(sx0, D, q * nx, false), AB_F(xdot, D, nx, false), AB_F(J, D, nx * nx, false),
+        AB_F(numsteps, I, nt, false), AB_F(numrhsevals, I, nt, false), AB_F(numerrtestfails, I, nt, false),
+        AB_F(numnonlinsolvconvfails, I, nt, false), AB_F(order, I, nt, false)};
+#undef AB_F
+    constexpr int NF = (int)(sizeof(fields) / sizeof(fields[0]));
+    auto host_ptr = [&](const FieldDesc& f) -> char* { return *(char* const*)((const char*)hb + f.offset); };
+
+    // Chunked double-buffered pipeline: H2D(c+1) / solve(c+1) overlap D2H(c); the persistent kernels of consecutive
+    // chunks run on two streams, so the draining tail of one chunk is filled by the blocks of the next.
+    size_t chunk = 8192;
+    if (const char* env = getenv("AMICI_B200_CHUNK")) chunk = (size_t)atol(env) > 0 ? (size_t)atol(env) : chunk;
+    if (chunk > N) chunk = N;
+    const int nbuf = (chunk < N) ? 2 : 1;
+    DevBuf shared_in[3];
+    DevBuf bufs[2][NF];
+    DevBuf counters[2];
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
     bool fail = false;
-    auto in = [&](const void* h, size_t bytes) -> void* {
-        if (!h || bytes == 0 || fail) return nullptr;
-        if (!cuda_ok(cudaMalloc(&bufs[nb].d, bytes), "cudaMalloc")) { fail = true; return nullptr; }
-        if (!cuda_ok(cudaMemcpyAsync(bufs[nb].d, h, bytes, cudaMemcpyHostToDevice, st), "H2D")) fail = true;
-        return bufs[nb++].d;
-    };
-    auto out = [&](void* h, size_t bytes) -> void* {
-        if (!h || bytes == 0 || fail) return nullptr;
-        if (!cuda_ok(cudaMalloc(&bufs[nb].d, bytes), "cudaMalloc")) { fail = true; return nullptr; }
-        outs[nout++] = Out{h, bufs[nb].d, bytes};
-        return bufs[nb++].d;
-    };
-    const size_t D = sizeof(double), I = sizeof(int);
-    db.ts = (const double*)in(hb->ts, D * nt);
-    db.plist = (const int*)in(hb->plist, I * hb->nplist);
-    db.pscale = (const int*)in(hb->pscale, I * d.np);
-    db.p = (const double*)in(hb->p, D * N * d.np);
-    db.k = (const double*)in(hb->k, D * N * d.nk);
-    db.my = (const double*)in(hb->my, D * N * nt * ny);
-    db.sigmay_in = (const double*)in(hb->sigmay_in, D * N * nt * ny);
-    db.status = (int*)out(hb->status, I * N);
-    db.llh = (double*)out(hb->llh, D * N);
-    db.chi2 = (double*)out(hb->chi2, D * N);
-    db.sllh = (double*)out(hb->sllh, D * N * q);
-    db.x = (double*)out(hb->x, D * N * nt * nx);
-    db.sx = (double*)out(hb->sx, D * N * nt * q * nx);
-    db.y = (double*)out(hb->y, D * N * nt * ny);
-    db.sy = (double*)out(hb->sy, D * N * nt * q * ny);
-    db.sigmay = (double*)out(hb->sigmay, D * N * nt * ny);
-    db.ssigmay = (double*)out(hb->ssigmay, D * N * nt * q * ny);
-    db.res = (double*)out(hb->res, D * N * nt * ny);
-    db.sres = (double*)out(hb->sres, D * N * nt * ny * q);
-    db.FIM = (double*)out(hb->FIM, D * N * q * q);
-    db.x0 = (double*)out(hb->x0, D * N * nx);
-    db.sx0 = (double*)out(hb->sx0, D * N * q * nx);
-    db.xdot = (double*)out(hb->xdot, D * N * nx);
-    db.J = (double*)out(hb->J, D * N * nx * nx);
-    db.numsteps = (int*)out(hb->numsteps, I * N * nt);
-    db.numrhsevals = (int*)out(hb->numrhsevals, I * N * nt);
-    db.numerrtestfails = (int*)out(hb->numerrtestfails, I * N * nt);
-    db.numnonlinsolvconvfails = (int*)out(hb->numnonlinsolvconvfails, I * N * nt);
-    db.order = (int*)out(hb->order, I * N * nt);
-    DevBuf counter;
-    if (!fail && !cuda_ok(cudaMalloc(&counter.d, sizeof(int)), "cudaMalloc")) fail = true;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (!fail) {
-        // outputs the kernel may leave untouched must not be garbage
-        for (int i = 0; i < nout && !fail; ++i)
-            if (!cuda_ok(cudaMemsetAsync(outs[i].dev, 0, outs[i].bytes, st), "memset")) fail = true;
-    }
-    if (!fail) {
-        cudaEventCreate(&e0);
-        cudaEventCreate(&e1);
-        cudaEventRecord(e0, st);
-        rc = ab_solve_device(model, opt, &db, (int*)counter.d, st);
-        cudaEventRecord(e1, st);
-        if (rc == AB_OK) {
-            for (int i = 0; i < nout && !fail; ++i)
-                if (!cuda_ok(cudaMemcpyAsync(outs[i].host, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, st), "D2H"))
-                    fail = true;
+    auto ok = [&](cudaError_t err, const char* what) { if (!cuda_ok(err, what)) fail = true; return !fail; };
+    for (int i = 0; i < nbuf && !fail; ++i) {
+        ok(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking), "cudaStreamCreate");
+        ok(cudaEventCreate(&ev0[i]), "cudaEventCreate");
+        ok(cudaEventCreate(&ev1[i]), "cudaEventCreate");
+        ok(cudaMalloc(&counters[i].d, sizeof(int)), "cudaMalloc");
+        for (int f = 0; f < NF && !fail; ++f) {
+            const size_t bytes = fields[f].elem * fields[f].per_cond * chunk;
+            if (host_ptr(fields[f]) && bytes) ok(cudaMalloc(&bufs[i][f].d, bytes), "cudaMalloc");
         }
-        if (!cuda_ok(cudaStreamSynchronize(st), "cudaStreamSynchronize")) fail = true;
-        if (kernel_ms && !fail) cudaEventElapsedTime(kernel_ms, e0, e1);
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
     }
-    cudaStreamDestroy(st);
+    ab_batch base = *hb;
+    if (!fail) {
+        ok(cudaMalloc(&shared_in[0].d, D * (nt ? nt : 1)), "cudaMalloc");
+        ok(cudaMalloc(&shared_in[1].d, I * (hb->nplist ? hb->nplist : 1)), "cudaMalloc");
+        ok(cudaMalloc(&shared_in[2].d, I * (d.np ? d.np : 1)), "cudaMalloc");
+    }
+    if (!fail) {
+        if (nt) ok(cudaMemcpy(shared_in[0].d, hb->ts, D * nt, cudaMemcpyHostToDevice), "H2D ts");
+        if (hb->plist && hb->nplist) ok(cudaMemcpy(shared_in[1].d, hb->plist, I * hb->nplist, cudaMemcpyHostToDevice), "H2D plist");
+        if (hb->pscale && d.np) ok(cudaMemcpy(shared_in[2].d, hb->pscale, I * d.np, cudaMemcpyHostToDevice), "H2D pscale");
+        base.ts = (const double*)shared_in[0].d;
+        base.plist = hb->plist ? (const int*)shared_in[1].d : nullptr;
+        base.pscale = hb->pscale ? (const int*)shared_in[2].d : nullptr;
+    }
+    float kms_total = 0.f;
+    int pending[2] = {0, 0};
+    size_t c = 0;
+    for (size_t lo = 0; lo < N && !fail; lo += chunk, ++c) {
+        const int bi = (int)(c % nbuf);
+        const size_t cnt = (lo + chunk <= N) ? chunk : N - lo;
+        if (pending[bi]) {   // buffer reuse is ordered by the stream; only the timing events need a host wait
+            ok(cudaEventSynchronize(ev1[bi]), "cudaEventSynchronize");
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev0[bi], ev1[bi]);
+            kms_total += ms;
+        }
+        ab_batch db = base;
+        db.N = (int)cnt;
+        for (int f = 0; f < NF && !fail; ++f) {
+            char* h = host_ptr(fields[f]);
+            *(void**)((char*)&db + fields[f].offset) = h ? bufs[bi][f].d : nullptr;
+            if (!h) continue;
+            const size_t stride = fields[f].elem * fields[f].per_cond;
+            if (stride == 0) { *(void**)((char*)&db + fields[f].offset) = nullptr; continue; }
+            if (fields[f].input) ok(cudaMemcpyAsync(bufs[bi][f].d, h + lo * stride, stride * cnt, cudaMemcpyHostToDevice, st[bi]), "H2D");
+            else ok(cudaMemsetAsync(bufs[bi][f].d, 0, stride * cnt, st[bi]), "memset");
+        }
+        if (fail) break;
+        cudaEventRecord(ev0[bi], st[bi]);
+        rc = ab_solve_device(model, opt, &db, (int*)counters[bi].d, st[bi]);
+        cudaEventRecord(ev1[bi], st[bi]);
+        pending[bi] = 1;
+        if (rc != AB_OK) break;
+        for (int f = 0; f < NF && !fail; ++f) {
+            char* h = host_ptr(fields[f]);
+            const size_t stride = fields[f].elem * fields[f].per_cond;
+            if (!h || fields[f].input || stride == 0) continue;
+            ok(cudaMemcpyAsync(h + lo * stride, bufs[bi][f].d, stride * cnt, cudaMemcpyDeviceToHost, st[bi]), "D2H");
+        }
+    }
+    for (int i = 0; i < nbuf; ++i) {
+        if (st[i] && !cuda_ok(cudaStreamSynchronize(st[i]), "cudaStreamSynchronize")) fail = true;
+        if (pending[i] && !fail) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev0[i], ev1[i]);
+            kms_total += ms;
+        }
+        if (ev0[i]) cudaEventDestroy(ev0[i]);
+        if (ev1[i]) cudaEventDestroy(ev1[i]);
+        if (st[i]) cudaStreamDestroy(st[i]);
+    }
+    if (kernel_ms) *kernel_ms = kms_total;   // sum of per-chunk solve durations (chunks on the two streams overlap)
     if (fail) return AB_E_CUDA;
     return rc;
 }

@@ -280,7 +280,10 @@ def main():
                 e2e_t.append(t1 - t0)
             h2d = int(batch.ts.nbytes + batch.p.nbytes + batch.k.nbytes + batch.my.nbytes + batch.sigmay.nbytes + 4 * (17 + 17))
             d2h = int(sum(v.nbytes for v in res.fields.values()))
+            res.release()   # hand the pinned output buffers back for the next step
             del res
+        if os.environ.get("BENCH_DEBUG"):
+            print("e2e times", e2e_t, file=sys.stderr)
         e2e_s = float(np.mean(e2e_t))
         if world > 1:
             t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
