@@ -27,7 +27,8 @@ from . import _capi
 __all__ = [
     "Model", "Solver", "ExpData", "ExpDataBatch", "ReturnDataView", "BatchResult", "run_simulation",
     "run_simulations", "runAmiciSimulations", "runAmiciSimulation", "SensitivityOrder", "SensitivityMethod",
-    "InternalSensitivityMethod", "ParameterScaling", "RDataReporting", "LinearSolver", "get_model",
+    "InternalSensitivityMethod", "ParameterScaling", "RDataReporting", "LinearSolver", "SteadyStateComputationMode",
+    "SteadyStateSensitivityMode", "SteadyStateStatus", "NewtonDampingFactorMode", "get_model",
     "available_models", "load_library", "AMICI_SUCCESS",
 ]
 
@@ -71,6 +72,33 @@ class RDataReporting(enum.IntEnum):
 class LinearSolver(enum.IntEnum):
     dense = 1
     KLU = 9
+
+
+class SteadyStateComputationMode(enum.IntEnum):
+    newtonOnly = 0
+    integrationOnly = 1
+    integrateIfNewtonFails = 2
+
+
+class SteadyStateSensitivityMode(enum.IntEnum):
+    newtonOnly = 0
+    integrationOnly = 1
+    integrateIfNewtonFails = 2
+
+
+class SteadyStateStatus(enum.IntEnum):
+    failed_too_long_simulation = -5
+    failed_damping = -4
+    failed_factorization = -3
+    failed_convergence = -2
+    failed = -1
+    not_run = 0
+    success = 1
+
+
+class NewtonDampingFactorMode(enum.IntEnum):
+    off = 0
+    on = 1
 
 
 def load_library() -> C.CDLL:
@@ -132,6 +160,9 @@ class Model:
         self._ts: list[float] = []
         self._plist = list(range(d.np))
         self._t0 = 0.0
+        self._ss_mode = SteadyStateComputationMode.integrateIfNewtonFails
+        self._ss_sensi_mode = SteadyStateSensitivityMode.integrateIfNewtonFails
+        self._nmaxevent = 10
 
     # -- dimensions
     def np(self) -> int: return self._np
@@ -176,6 +207,16 @@ class Model:
             raise RuntimeError("Dimension mismatch. Size of fixedParameters does not match number of fixed model parameters.")
         self._k = [float(v) for v in k]
     def get_fixed_parameters(self): return list(self._k)
+    # steady-state / event settings of amici::Model (reference include/amici/model.h)
+    def set_steady_state_computation_mode(self, mode): self._ss_mode = SteadyStateComputationMode(int(mode))
+    def get_steady_state_computation_mode(self): return self._ss_mode
+    def set_steady_state_sensitivity_mode(self, mode): self._ss_sensi_mode = SteadyStateSensitivityMode(int(mode))
+    def get_steady_state_sensitivity_mode(self): return self._ss_sensi_mode
+    def set_n_max_event(self, n):
+        if int(n) < 0:
+            raise RuntimeError("nmaxevent must be non-negative")
+        self._nmaxevent = int(n)
+    def n_max_event(self): return self._nmaxevent
     def create_solver(self) -> "Solver": return Solver()
     def get_name(self): return self.name
     def clone(self) -> "Model":
@@ -211,6 +252,15 @@ class Solver:
         self._max_step_size = 0.0
         self._reporting = RDataReporting.full
         self._linsol = LinearSolver.KLU
+        # steady-state solver (reference include/amici/solver.h:2040-2100)
+        self._newton_maxsteps = 0
+        self._newton_damping_mode = NewtonDampingFactorMode.on
+        self._newton_damping_lb = 1e-8
+        self._newton_step_ss_check = False
+        self._sensi_ss_check = True
+        self._ss_tol_factor = self._ss_tol_sensi_factor = 100.0
+        self._rtol_ss = self._atol_ss = self._rtol_ss_sensi = self._atol_ss_sensi = float("nan")
+        self._sensi_meth_preeq = SensitivityMethod.forward
 
     @staticmethod
     def _nonneg(v, what):
@@ -268,13 +318,51 @@ class Solver:
             raise RuntimeError("amici_b200: reporting modes implemented: full, likelihood")
         self._reporting = v
     def get_return_data_reporting_mode(self): return self._reporting
+    def set_newton_max_steps(self, v):
+        if v < 0:
+            raise RuntimeError("newton_maxsteps must be a non-negative number")
+        self._newton_maxsteps = int(v)
+    def get_newton_max_steps(self): return self._newton_maxsteps
+    def set_newton_damping_factor_mode(self, v): self._newton_damping_mode = NewtonDampingFactorMode(int(v))
+    def get_newton_damping_factor_mode(self): return self._newton_damping_mode
+    def set_newton_damping_factor_lower_bound(self, v): self._newton_damping_lb = float(v)
+    def get_newton_damping_factor_lower_bound(self): return self._newton_damping_lb
+    def set_newton_step_steady_state_check(self, flag):
+        if flag:
+            raise RuntimeError("amici_b200: the Newton-step steady-state convergence check is not implemented")
+        self._newton_step_ss_check = False
+    def get_newton_step_steady_state_check(self): return self._newton_step_ss_check
+    def set_sensi_steady_state_check(self, flag): self._sensi_ss_check = bool(flag)
+    def get_sensi_steady_state_check(self): return self._sensi_ss_check
+    def set_steady_state_tolerance_factor(self, v): self._ss_tol_factor = self._nonneg(v, "ss_tol_factor")
+    def get_steady_state_tolerance_factor(self): return self._ss_tol_factor
+    def set_steady_state_sensi_tolerance_factor(self, v): self._ss_tol_sensi_factor = self._nonneg(v, "ss_tol_sensi_factor")
+    def get_steady_state_sensi_tolerance_factor(self): return self._ss_tol_sensi_factor
+    def set_relative_tolerance_steady_state(self, v): self._rtol_ss = self._nonneg(v, "rtol")
+    def get_relative_tolerance_steady_state(self):
+        return self._rtol * self._ss_tol_factor if math.isnan(self._rtol_ss) else self._rtol_ss
+    def set_absolute_tolerance_steady_state(self, v): self._atol_ss = self._nonneg(v, "atol")
+    def get_absolute_tolerance_steady_state(self):
+        return self._atol * self._ss_tol_factor if math.isnan(self._atol_ss) else self._atol_ss
+    def set_relative_tolerance_steady_state_sensi(self, v): self._rtol_ss_sensi = self._nonneg(v, "rtol")
+    def get_relative_tolerance_steady_state_sensi(self):
+        return self._rtol * self._ss_tol_sensi_factor if math.isnan(self._rtol_ss_sensi) else self._rtol_ss_sensi
+    def set_absolute_tolerance_steady_state_sensi(self, v): self._atol_ss_sensi = self._nonneg(v, "atol")
+    def get_absolute_tolerance_steady_state_sensi(self):
+        return self._atol * self._ss_tol_sensi_factor if math.isnan(self._atol_ss_sensi) else self._atol_ss_sensi
+    def set_sensitivity_method_pre_equilibration(self, v):
+        v = SensitivityMethod(int(v))
+        if v == SensitivityMethod.adjoint:
+            raise RuntimeError("amici_b200: adjoint pre-equilibration is outside the batched forward path")
+        self._sensi_meth_preeq = v
+    def get_sensitivity_method_pre_equilibration(self): return self._sensi_meth_preeq
     def set_linear_solver(self, v): self._linsol = LinearSolver(int(v))  # accepted; the engine always uses its batched LU
     def get_linear_solver(self): return self._linsol
     def clone(self):
         import copy
         return copy.deepcopy(self)
 
-    def _options(self, t0: float) -> _capi.SolverOptions:
+    def _options(self, t0: float, model: "Model | None" = None) -> _capi.SolverOptions:
         fsa = self._sensi >= SensitivityOrder.first and self._sensi_meth == SensitivityMethod.forward
         if self._sensi >= SensitivityOrder.second:
             raise RuntimeError("amici_b200: second-order sensitivities are not implemented")
@@ -284,7 +372,15 @@ class Solver:
             hmax_inv=(1.0 / self._max_step_size if self._max_step_size > 0 else 0.0), sensi=1 if fsa else 0,
             ism=int(self._ism), maxsteps=self._maxsteps, stldet=int(self._stldet),
             max_nonlin_iters=self._max_nonlin_iters, max_conv_fails=self._max_conv_fails, max_err_test_fails=7,
-            reporting=int(self._reporting))
+            reporting=int(self._reporting),
+            rtol_ss=self.get_relative_tolerance_steady_state(), atol_ss=self.get_absolute_tolerance_steady_state(),
+            rtol_ss_sensi=self.get_relative_tolerance_steady_state_sensi(),
+            atol_ss_sensi=self.get_absolute_tolerance_steady_state_sensi(),
+            newton_damping_lower_bound=self._newton_damping_lb, newton_maxsteps=self._newton_maxsteps,
+            newton_damping_mode=int(self._newton_damping_mode), sensi_ss_check=int(self._sensi_ss_check),
+            ss_mode=int(model._ss_mode) if model is not None else 2,
+            ss_sensi_mode=int(model._ss_sensi_mode) if model is not None else 2,
+            nmaxevent=model._nmaxevent if model is not None else 10)
 
 
 class ExpData:
@@ -295,6 +391,7 @@ class ExpData:
         self.ts_ = model.get_timepoints()
         self.free_parameters: list[float] = []   # empty = use the model's
         self.fixed_parameters: list[float] = []
+        self.fixed_parameters_pre_equilibration: list[float] = []   # non-empty = pre-equilibrate (edata.h)
         self.pscale: list = []
         self.plist: list[int] = []
         n = len(self.ts_) * self._ny
@@ -333,7 +430,7 @@ class ExpDataBatch:
     ``ExpData`` or accepts it directly, which avoids one Python object per condition for large batches.
     """
 
-    def __init__(self, ts, p, k, my=None, sigmay=None, plist=None, pscale=None):
+    def __init__(self, ts, p, k, my=None, sigmay=None, plist=None, pscale=None, k_preeq=None, mz=None, sigmaz=None):
         self.ts = np.ascontiguousarray(ts, dtype=np.float64)
         self.p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
         self.k = np.ascontiguousarray(np.atleast_2d(k), dtype=np.float64)
@@ -341,6 +438,9 @@ class ExpDataBatch:
         self.sigmay = None if sigmay is None else np.ascontiguousarray(sigmay, dtype=np.float64)
         self.plist = None if plist is None else np.ascontiguousarray(plist, dtype=np.int32)
         self.pscale = None if pscale is None else np.ascontiguousarray(pscale, dtype=np.int32)
+        self.k_preeq = None if k_preeq is None else np.ascontiguousarray(np.atleast_2d(k_preeq), dtype=np.float64)
+        self.mz = None if mz is None else np.ascontiguousarray(mz, dtype=np.float64)
+        self.sigmaz = None if sigmaz is None else np.ascontiguousarray(sigmaz, dtype=np.float64)
 
     def __len__(self): return self.p.shape[0]
 
@@ -368,7 +468,15 @@ class ExpDataBatch:
             if e is not None:
                 my[i] = e._my.reshape(nt, model.ny)
                 sg[i] = e._sigmay.reshape(nt, model.ny)
-        return ExpDataBatch(ts, p, k, my, sg, plist, pscale)
+        has_preeq = [e is not None and len(e.fixed_parameters_pre_equilibration) > 0 for e in edatas]
+        k_preeq = None
+        if any(has_preeq):
+            if not all(has_preeq):
+                raise RuntimeError("amici_b200: either all or none of the conditions of one batch pre-equilibrate")
+            k_preeq = np.array([e.fixed_parameters_pre_equilibration for e in edatas], dtype=np.float64)
+            if k_preeq.shape != (N, model.nk()):
+                raise RuntimeError("Dimension mismatch. Size of fixed_parameters_pre_equilibration does not match nk.")
+        return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq)
 
 
 _RDATA_ALIASES = {"num_rhs_evals": "numrhsevals", "num_err_test_fails": "numerrtestfails",
@@ -457,9 +565,9 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
     N, nt = len(batch), len(batch.ts)
     plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist
     pscale = np.asarray([int(s) for s in model.get_parameter_scale()], dtype=np.int32) if batch.pscale is None else batch.pscale
-    opts = solver._options(model.t0())
+    opts = solver._options(model.t0(), model)
     q = len(plist) if opts.sensi else 0
-    d = model.dims()
+    d = dict(model.dims(), nz=model.nz, nmaxevent=opts.nmaxevent)
     b = _capi.BatchView(N=N, nt=nt, nplist=len(plist))
     keep = [batch.ts, batch.p, batch.k, plist, pscale]
     if batch.p.shape != (N, d["np"]) or batch.k.shape != (N, d["nk"]):
@@ -471,6 +579,15 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
         b.my = batch.my.ctypes.data_as(dp)
     if batch.sigmay is not None:
         b.sigmay_in = batch.sigmay.ctypes.data_as(dp)
+    if batch.k_preeq is not None:
+        if batch.k_preeq.shape != (N, d["nk"]):
+            raise RuntimeError("amici_b200: k_preeq shape does not match the model")
+        b.k_preeq = batch.k_preeq.ctypes.data_as(dp)
+    for name, arr in (("mz", batch.mz), ("sigmaz_in", batch.sigmaz)):
+        if arr is not None:
+            if arr.shape != (N, opts.nmaxevent, model.nz):
+                raise RuntimeError(f"amici_b200: {name} must have shape [N][nmaxevent][nz]")
+            setattr(b, name, arr.ctypes.data_as(dp))
     likelihood_only = opts.reporting == int(RDataReporting.likelihood)
     lk_fields = {"status", "llh", "chi2", "sllh", "numsteps", "numrhsevals", "numerrtestfails",
                  "numnonlinsolvconvfails", "order"}
@@ -480,8 +597,15 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
             continue
         if likelihood_only and name not in lk_fields:
             continue
+        if name in _capi.EVENT_FIELDS and model.nz == 0:
+            continue
+        if name in _capi.PREEQ_FIELDS and batch.k_preeq is None:
+            # ReturnData defaults without pre-equilibration (reference src/rdata.cpp:170-171, :192-196)
+            shape = shp(d, N, nt, q)
+            out[name] = (np.zeros(shape, dtype=np.int32) if t == "i" else np.full(shape, np.nan))
+            continue
         shape = shp(d, N, nt, q)
-        if q == 0 and name in ("sllh", "sx", "sy", "ssigmay", "sres", "FIM", "sx0"):
+        if q == 0 and name in ("sllh", "sx", "sy", "ssigmay", "sres", "FIM", "sx0", "sx_ss", "sz", "srz"):
             out[name] = np.zeros(shape)
             continue
         a, t_keep = _pinned_empty(shape, np.float64 if t == "d" else np.int32)

@@ -13,10 +13,13 @@ class SolverOptions(C.Structure):
     """``ab_solver_options`` (include/amici_b200.h)."""
     _fields_ = [(n, C.c_double) for n in ("rtol", "atol", "rtol_fsa", "atol_fsa", "t0", "hmax_inv")] + [
         (n, C.c_int) for n in ("sensi", "ism", "maxsteps", "stldet", "max_nonlin_iters", "max_conv_fails",
-                               "max_err_test_fails", "reporting")]
+                               "max_err_test_fails", "reporting")] + [
+        (n, C.c_double) for n in ("rtol_ss", "atol_ss", "rtol_ss_sensi", "atol_ss_sensi", "newton_damping_lower_bound")] + [
+        (n, C.c_int) for n in ("newton_maxsteps", "newton_damping_mode", "sensi_ss_check", "ss_mode", "ss_sensi_mode",
+                               "nmaxevent")]
 
 
-# (name, dtype, shape(dims, N, nt, nplist)) for every output buffer of ab_batch
+# (name, dtype, shape(dims, N, nt, nplist)) for every output buffer of ab_batch; dims["ne_"] = nmaxevent of the call
 OUT_FIELDS = [
     ("status", "i", lambda d, N, nt, q: (N,)),
     ("llh", "d", lambda d, N, nt, q: (N,)),
@@ -40,31 +43,51 @@ OUT_FIELDS = [
     ("numerrtestfails", "i", lambda d, N, nt, q: (N, nt)),
     ("numnonlinsolvconvfails", "i", lambda d, N, nt, q: (N, nt)),
     ("order", "i", lambda d, N, nt, q: (N, nt)),
+    ("x_ss", "d", lambda d, N, nt, q: (N, d["nx"])),
+    ("sx_ss", "d", lambda d, N, nt, q: (N, q, d["nx"])),
+    ("preeq_status", "i", lambda d, N, nt, q: (N, 3)),
+    ("preeq_numsteps", "i", lambda d, N, nt, q: (N, 3)),
+    ("preeq_wrms", "d", lambda d, N, nt, q: (N,)),
+    ("preeq_t", "d", lambda d, N, nt, q: (N,)),
+    ("z", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), d.get("nz", 0))),
+    ("sz", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), q, d.get("nz", 0))),
+    ("rz", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), d.get("nz", 0))),
+    ("srz", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), q, d.get("nz", 0))),
+    ("sigmaz", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), d.get("nz", 0))),
 ]
+PREEQ_FIELDS = ("x_ss", "sx_ss", "preeq_status", "preeq_numsteps", "preeq_wrms", "preeq_t")
+EVENT_FIELDS = ("z", "sz", "rz", "srz", "sigmaz")
 
 
 class BatchView(C.Structure):
     """``ab_batch`` (include/amici_b200.h): borrowed host (or device) pointers, row-major."""
     _fields_ = [("N", C.c_int), ("nt", C.c_int), ("nplist", C.c_int),
                 ("ts", _dp), ("plist", _ip), ("pscale", _ip), ("p", _dp), ("k", _dp),
-                ("my", _dp), ("sigmay_in", _dp)] + [
+                ("my", _dp), ("sigmay_in", _dp), ("k_preeq", _dp), ("mz", _dp), ("sigmaz_in", _dp)] + [
         (n, _dp if t == "d" else _ip) for n, t, _ in OUT_FIELDS]
 
 
 def default_options(**kw) -> SolverOptions:
     o = SolverOptions(rtol=1e-8, atol=1e-16, rtol_fsa=float("nan"), atol_fsa=float("nan"), t0=0.0, hmax_inv=0.0,
                       sensi=0, ism=1, maxsteps=10000, stldet=1, max_nonlin_iters=3, max_conv_fails=10,
-                      max_err_test_fails=7, reporting=0)
+                      max_err_test_fails=7, reporting=0, rtol_ss=float("nan"), atol_ss=float("nan"),
+                      rtol_ss_sensi=float("nan"), atol_ss_sensi=float("nan"), newton_damping_lower_bound=1e-8,
+                      newton_maxsteps=0, newton_damping_mode=1, sensi_ss_check=1, ss_mode=2, ss_sensi_mode=2, nmaxevent=10)
     for k_, v in kw.items():
         setattr(o, k_, v)
     if o.rtol_fsa != o.rtol_fsa:
         o.rtol_fsa = o.rtol
     if o.atol_fsa != o.atol_fsa:
         o.atol_fsa = o.atol
+    # steady-state tolerances default to 100x the integration tolerances (reference src/solver.cpp:981-1037)
+    for name, base in (("rtol_ss", o.rtol), ("atol_ss", o.atol), ("rtol_ss_sensi", o.rtol), ("atol_ss_sensi", o.atol)):
+        if getattr(o, name) != getattr(o, name):
+            setattr(o, name, 100.0 * base)
     return o
 
 
-def make_batch(dims: dict, ts, p, k, plist=None, pscale=None, my=None, sigmay=None, fields=None):
+def make_batch(dims: dict, ts, p, k, plist=None, pscale=None, my=None, sigmay=None, fields=None, k_preeq=None,
+               mz=None, sigmaz=None, nmaxevent=10):
     """Build an ab_batch over freshly allocated numpy outputs. Returns (batch, outputs dict, keepalive)."""
     ts = np.ascontiguousarray(ts, dtype=np.float64)
     p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
@@ -82,9 +105,23 @@ def make_batch(dims: dict, ts, p, k, plist=None, pscale=None, my=None, sigmay=No
             a = np.ascontiguousarray(arr, dtype=np.float64).reshape(N, nt, dims["ny"])
             keep.append(a)
             setattr(b, name, a.ctypes.data_as(_dp))
+    dims = dict(dims, nmaxevent=nmaxevent)
+    if k_preeq is not None:
+        a = np.ascontiguousarray(k_preeq, dtype=np.float64).reshape(N, dims["nk"])
+        keep.append(a)
+        b.k_preeq = a.ctypes.data_as(_dp)
+    for name, arr in (("mz", mz), ("sigmaz_in", sigmaz)):
+        if arr is not None:
+            a = np.ascontiguousarray(arr, dtype=np.float64).reshape(N, nmaxevent, dims.get("nz", 0))
+            keep.append(a)
+            setattr(b, name, a.ctypes.data_as(_dp))
     out = {}
     for name, t, shp in OUT_FIELDS:
         if fields is not None and name not in fields and name != "status":
+            continue
+        if name in PREEQ_FIELDS and k_preeq is None and (fields is None or name not in fields):
+            continue
+        if name in EVENT_FIELDS and dims.get("nz", 0) == 0:
             continue
         a = np.zeros(shp(dims, N, nt, q), dtype=np.float64 if t == "d" else np.int32)
         out[name] = a

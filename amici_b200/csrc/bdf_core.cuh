@@ -46,6 +46,7 @@ struct TrajShared {
     double lu[M::NX][M::NX];         // dense LU with partial pivoting: fallback when a static pivot is rejected
     double savedJ[M::NNZ_J > 0 ? M::NNZ_J : 1];
     double ybuf[M::NX];              // broadcast buffer for the state column
+    double xfin[M::NX];              // state at the last successful solver return (ReturnData::xdot/J are evaluated there)
     double scratch[NCOLS];
     double p[M::NP > 0 ? M::NP : 1];
     double k[M::NK > 0 ? M::NK : 1];
@@ -449,38 +450,45 @@ struct DenseRef {
     AB_HD double& operator()(int r, int c) { return S.lu[r][c]; }
 };
 
+// In-place LU with partial pivoting of the matrix in S.lu (executed by one lane); false if exactly singular.
+template <class M, int G, int C>
+AB_HD bool dense_lu_inplace(typename Layout<M, G, C>::Shared& S) {
+    constexpr int NX = M::NX;
+    for (int kk = 0; kk < NX; ++kk) {
+        int pr = kk;
+        double best = fabs(S.lu[kk][kk]);
+        for (int i = kk + 1; i < NX; ++i) {
+            const double a = fabs(S.lu[i][kk]);
+            if (a > best) { best = a; pr = i; }
+        }
+        S.piv[kk] = pr;
+        if (!(best > 0.0)) return false;
+        if (pr != kk)
+            for (int j = 0; j < NX; ++j) {
+                const double tmp = S.lu[kk][j];
+                S.lu[kk][j] = S.lu[pr][j];
+                S.lu[pr][j] = tmp;
+            }
+        const double inv = 1.0 / S.lu[kk][kk];
+        for (int i = kk + 1; i < NX; ++i) {
+            const double m = S.lu[i][kk] * inv;
+            S.lu[i][kk] = m;
+            if (m != 0.0)
+                for (int j = kk + 1; j < NX; ++j) S.lu[i][j] -= m * S.lu[kk][j];
+        }
+    }
+    return true;
+}
+
 template <class M, int G, int C>
 AB_COLD bool cold_dense_factor(typename Layout<M, G, C>::Shared& S, double gamma) {
-    constexpr int NX = M::NX;
     Group<G> g;
     g.sync();
     int ok = 1;
     if (g.lane == 0) {
         DenseRef<M, G, C> A{S};
         M::jac_to_A(S.savedJ, gamma, A);
-        for (int kk = 0; kk < NX; ++kk) {
-            int pr = kk;
-            double best = fabs(S.lu[kk][kk]);
-            for (int i = kk + 1; i < NX; ++i) {
-                const double a = fabs(S.lu[i][kk]);
-                if (a > best) { best = a; pr = i; }
-            }
-            S.piv[kk] = pr;
-            if (best == 0.0) { ok = 0; break; }
-            if (pr != kk)
-                for (int j = 0; j < NX; ++j) {
-                    const double tmp = S.lu[kk][j];
-                    S.lu[kk][j] = S.lu[pr][j];
-                    S.lu[pr][j] = tmp;
-                }
-            const double inv = 1.0 / S.lu[kk][kk];
-            for (int i = kk + 1; i < NX; ++i) {
-                const double m = S.lu[i][kk] * inv;
-                S.lu[i][kk] = m;
-                if (m != 0.0)
-                    for (int j = kk + 1; j < NX; ++j) S.lu[i][j] -= m * S.lu[kk][j];
-            }
-        }
+        ok = dense_lu_inplace<M, G, C>(S) ? 1 : 0;
     }
     ok = g.bcast(ok, 0);
     g.sync();
@@ -1208,20 +1216,24 @@ struct Bdf {
 
     // -----------------------------------------------------------------------------------------
     // CVode(tout, CV_NORMAL) with tstop = tout, as AMICI's Solver::run drives it
-    // (reference src/solver.cpp:141-160; cvodes.c:2890-3650). Returns AB_TSTOP_RETURN or an error.
+    // (reference src/solver.cpp:141-160; cvodes.c:2890-3650): returns AB_TSTOP_RETURN or an error.
+    // one_step = true is CVode(tout, CV_ONE_STEP) without a stop time, as Solver::step drives it during
+    // steady-state simulation (reference src/solver.cpp:162-178, src/forwardproblem.cpp:197-206): tout only
+    // gives the direction and the scale of the initial step; returns AB_SUCCESS after one internal step.
+    // Both modes share this function so that the (inlined) step has a single call site.
     // -----------------------------------------------------------------------------------------
-    AB_HD int solve_to(double tout) {
+    AB_HD int solve_to(double tout, bool one_step = false) {
         // Solver::apply_max_num_steps (reference src/solver.cpp:107-119)
         if (o.maxsteps <= nst) return AB_ERROR;
         const int mxstep = o.maxsteps - nst;
         tstop = tout;
-        tstopset = true;
+        tstopset = !one_step;
         if (nst == 0) {
             // first call: zn[1] = f(t0, y0) (cvodes.c first-call block), initial step, zn[1] *= h
             const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, 1.0, 1);
             nfe++;
             if (!ok) return AB_FIRST_RHSFUNC_ERR;
-            if ((tstop - tn) * (tout - tn) <= 0.0) return AB_ILL_INPUT;
+            if (tstopset && (tstop - tn) * (tout - tn) <= 0.0) return AB_ILL_INPUT;
             double h0 = 0.0;
             int nfe_hin = 0;
             const int hflag = cold_hin<M, G, C>(S, o, ncols, tn, tout, &h0, &nfe_hin);
@@ -1230,7 +1242,7 @@ struct Bdf {
             h = h0;
             const double rh = fabs(h) * o.hmax_inv;
             if (rh > 1.0) h /= rh;
-            if ((tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+            if (tstopset && (tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
             hscale = h;
             hprime = h;
             AB_UNROLL
@@ -1239,7 +1251,7 @@ struct Bdf {
                 AB_UNROLL
                 for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] *= h;
             }
-        } else {
+        } else if (tstopset) {
             const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
             if (fabs(tn - tstop) <= troundoff) {
                 tretlast = tstop;
@@ -1259,6 +1271,7 @@ struct Bdf {
             const int kflag = step();
             if (kflag != AB_SUCCESS) { tretlast = tn; return kflag; }
             nstloc++;
+            if (one_step) { tretlast = tn; return AB_SUCCESS; }
             const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
             if (fabs(tn - tstop) <= troundoff) {
                 tn = tstop;

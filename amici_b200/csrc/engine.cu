@@ -87,6 +87,19 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
     if (o->sensi >= 1 && b->nplist > 0 && !b->plist) { g_err = "plist is NULL"; return AB_E_BAD_ARGUMENT; }
     if (o->sensi >= 1 && o->ism != 1) { g_err = "only simultaneous forward sensitivities are implemented"; return AB_E_UNSUPPORTED; }
     if (!(o->rtol >= 0) || !(o->atol >= 0)) { g_err = "negative tolerance"; return AB_E_BAD_ARGUMENT; }
+    if (b->k_preeq && (!(o->rtol_ss >= 0) || !(o->atol_ss >= 0) || !(o->rtol_ss_sensi >= 0) || !(o->atol_ss_sensi >= 0))) {
+        g_err = "steady-state tolerances must be resolved (non-negative) when k_preeq is given";
+        return AB_E_BAD_ARGUMENT;
+    }
+    if (b->k_preeq && (o->ss_mode < 0 || o->ss_mode > 2 || o->ss_sensi_mode < 0 || o->ss_sensi_mode > 2)) {
+        g_err = "invalid steady-state mode";
+        return AB_E_BAD_ARGUMENT;
+    }
+    if (b->k_preeq && o->sensi >= 1 && o->ss_mode == 0 && o->ss_sensi_mode == 1) {
+        // SteadyStateProblem constructor (reference src/forwardproblem.cpp:792-806)
+        g_err = "steady-state computation mode 'newtonOnly' and sensitivity mode 'integrationOnly' are not compatible";
+        return AB_E_BAD_ARGUMENT;
+    }
     return AB_OK;
 }
 
@@ -213,17 +226,23 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
     if (hb->N == 0) return AB_OK;
     const ab_dims& d = e->dims;
     const size_t N = hb->N, nt = hb->nt, q = (opt->sensi >= 1) ? hb->nplist : 0;
-    const size_t nx = d.nx, ny = d.ny, D = sizeof(double), I = sizeof(int);
+    const size_t nx = d.nx, ny = d.ny, nz = d.nz, D = sizeof(double), I = sizeof(int);
+    const size_t nme = opt->nmaxevent > 0 ? opt->nmaxevent : 0;
 #define AB_F(f, el, cnt, in) FieldDesc{offsetof(ab_batch, f), el, (size_t)(cnt), in}
     const FieldDesc fields[] = {
         AB_F(p, D, d.np, true), AB_F(k, D, d.nk, true), AB_F(my, D, nt * ny, true), AB_F(sigmay_in, D, nt * ny, true),
+        AB_F(k_preeq, D, d.nk, true), AB_F(mz, D, nme * nz, true), AB_F(sigmaz_in, D, nme * nz, true),
         AB_F(status, I, 1, false), AB_F(llh, D, 1, false), AB_F(chi2, D, 1, false), AB_F(sllh, D, q, false),
         AB_F(x, D, nt * nx, false), AB_F(sx, D, nt * q * nx, false), AB_F(y, D, nt * ny, false),
         AB_F(sy, D, nt * q * ny, false), AB_F(sigmay, D, nt * ny, false), AB_F(ssigmay, D, nt * q * ny, false),
         AB_F(res, D, nt * ny, false), AB_F(sres, D, nt * ny * q, false), AB_F(FIM, D, q * q, false),
         AB_F(x0, D, nx, false), AB_F(sx0, D, q * nx, false), AB_F(xdot, D, nx, false), AB_F(J, D, nx * nx, false),
         AB_F(numsteps, I, nt, false), AB_F(numrhsevals, I, nt, false), AB_F(numerrtestfails, I, nt, false),
-        AB_F(numnonlinsolvconvfails, I, nt, false), AB_F(order, I, nt, false)};
+        AB_F(numnonlinsolvconvfails, I, nt, false), AB_F(order, I, nt, false),
+        AB_F(x_ss, D, nx, false), AB_F(sx_ss, D, q * nx, false), AB_F(preeq_status, I, 3, false),
+        AB_F(preeq_numsteps, I, 3, false), AB_F(preeq_wrms, D, 1, false), AB_F(preeq_t, D, 1, false),
+        AB_F(z, D, nme * nz, false), AB_F(sz, D, nme * q * nz, false), AB_F(rz, D, nme * nz, false),
+        AB_F(srz, D, nme * q * nz, false), AB_F(sigmaz, D, nme * nz, false)};
 #undef AB_F
     constexpr int NF = (int)(sizeof(fields) / sizeof(fields[0]));
     auto host_ptr = [&](const FieldDesc& f) -> char* { return *(char* const*)((const char*)hb + f.offset); };

@@ -15,9 +15,9 @@
 
 namespace amici_b200 {
 
-template <class M, int G, int C, int THREADS, int MINBLOCKS>
+template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head) {
-    using Sim = Simulation<M, G, C>;
+    using Sim = Simulation<M, G, C, PREEQ>;
     using Shared = typename Sim::Shared;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared* slices = reinterpret_cast<Shared*>(smem_raw);
@@ -48,10 +48,10 @@ struct Config {
     static constexpr int MINBLOCKS = AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
 };
 
-template <class M, int G, int C, int THREADS, int MINBLOCKS>
+template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
 int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
-    using Sim = Simulation<M, G, C>;
-    auto kern = bdf_solve_kernel<M, G, C, THREADS, MINBLOCKS>;
+    using Sim = Simulation<M, G, C, PREEQ>;
+    auto kern = bdf_solve_kernel<M, G, C, THREADS, MINBLOCKS, PREEQ>;
     constexpr int groups = THREADS / G;
     const size_t smem = sizeof(typename Sim::Shared) * groups;
     int dev = 0, sms = 0;
@@ -75,17 +75,28 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
     return AB_OK;
 }
 
-template <class M>
-int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
+// PREEQ = true variants (conditions with ExpData::fixed_parameters_pre_equilibration) are instantiated in their own
+// translation unit (tu/<model>_preeq.cu) to keep the build parallel.
+template <class M, bool PREEQ>
+int launch_model_impl(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
     if (o.sensi >= 1 && b.nplist > 0) {
         if (b.nplist + 1 > Config<M>::COLS) {
             last_error() = "nplist exceeds the number of model parameters";
             return AB_E_UNSUPPORTED;
         }
-        return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS, Config<M>::MINBLOCKS>(o, b, queue_head, st);
+        return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS, Config<M>::MINBLOCKS, PREEQ>(o, b, queue_head, st);
     }
     // no sensitivities: one thread per condition
-    return launch_variant<M, 1, 1, 32, 1>(o, b, queue_head, st);
+    return launch_variant<M, 1, 1, 32, 1, PREEQ>(o, b, queue_head, st);
+}
+
+template <class M>
+int launch_model_preeq(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st);
+
+template <class M>
+int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
+    if (b.k_preeq) return launch_model_preeq<M>(o, b, queue_head, st);
+    return launch_model_impl<M, false>(o, b, queue_head, st);
 }
 
 template <class M>

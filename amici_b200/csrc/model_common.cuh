@@ -37,7 +37,11 @@ enum : int {
     AB_UNREC_RHSFUNC_ERR = -11,
     AB_ILL_INPUT = -22,
     AB_TOO_CLOSE = -27,
+    AB_NO_STEADY_STATE = -81,
+    AB_DAMPING_FACTOR_ERROR = -86,
     AB_ERROR = -99,
+    AB_SINGULAR_JACOBIAN = -9987,
+    AB_T_OVERFLOW = -1002,
     AB_NOT_RUN = -1001,
 };
 

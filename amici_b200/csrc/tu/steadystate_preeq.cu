@@ -1,0 +1,9 @@
+// GENERATED: instantiates the solve kernel with the pre-equilibration phase for model 'steadystate'.
+#include "../launch.cuh"
+#include "../models/steadystate.cuh"
+namespace amici_b200 {
+template <>
+int launch_model_preeq<models::steadystate>(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
+    return launch_model_impl<models::steadystate, true>(o, b, queue_head, st);
+}
+}  // namespace amici_b200

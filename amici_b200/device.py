@@ -18,7 +18,7 @@ class DeviceBatch:
         self.lib = load_library()
         self.model, self.solver = model, solver
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        self.opts = solver._options(model.t0())
+        self.opts = solver._options(model.t0(), model)
         d = model.dims()
         N, nt = len(batch), len(batch.ts)
         plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist

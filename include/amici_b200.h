@@ -42,6 +42,17 @@ typedef struct ab_solver_options {
     int max_conv_fails;        /* Solver::set_max_conv_fails (10)                                    */
     int max_err_test_fails;    /* CVODES default 7                                                   */
     int reporting;             /* RDataReporting: 0 full, 2 likelihood                               */
+    /* steady-state (pre-equilibration) settings: amici::Solver / amici::Model, reference
+     * include/amici/solver.h:2040-2100, include/amici/defines.h:204-232 */
+    double rtol_ss, atol_ss;             /* resolved get_{relative,absolute}_tolerance_steady_state (solver.cpp:981-998)        */
+    double rtol_ss_sensi, atol_ss_sensi; /* resolved ..._steady_state_sensi (solver.cpp:1020-1037)                             */
+    double newton_damping_lower_bound;   /* Solver::set_newton_damping_factor_lower_bound (1e-8)                               */
+    int newton_maxsteps;       /* Solver::set_newton_max_steps (0 = Newton's method off)                                  */
+    int newton_damping_mode;   /* NewtonDampingFactorMode: 0 off, 1 on                                                    */
+    int sensi_ss_check;        /* Solver::set_sensi_steady_state_check (1)                                                */
+    int ss_mode;               /* SteadyStateComputationMode: 0 newtonOnly, 1 integrationOnly, 2 integrateIfNewtonFails   */
+    int ss_sensi_mode;         /* SteadyStateSensitivityMode: same values                                                 */
+    int nmaxevent;             /* Model::set_n_max_event (10): event-observable slots per event                           */
 } ab_solver_options;
 
 /* One batch of N conditions (replaces std::vector<ExpData*> in, std::vector<ReturnData> out). */
@@ -55,6 +66,9 @@ typedef struct ab_batch {
     const double* k;         /* [N][nk]         SimulationParameters::fixed_parameters            */
     const double* my;        /* [N][nt][ny]     ExpData measurements, NaN = missing; may be NULL  */
     const double* sigmay_in; /* [N][nt][ny]     ExpData noise scales, NaN = model sigma; may be NULL */
+    const double* k_preeq;   /* [N][nk]         ExpData::fixed_parameters_pre_equilibration; NULL = no pre-equilibration */
+    const double* mz;        /* [N][nmaxevent][nz]  ExpData event measurements, NaN = missing; may be NULL */
+    const double* sigmaz_in; /* [N][nmaxevent][nz]  ExpData event noise scales, NaN = model sigma; may be NULL */
     /* ---- outputs (ReturnData fields; any may be NULL) ---- */
     int* status;             /* [N]                                  */
     double* llh;             /* [N]                                  */
@@ -78,6 +92,19 @@ typedef struct ab_batch {
     int* numerrtestfails;    /* [N][nt]                              */
     int* numnonlinsolvconvfails; /* [N][nt]                          */
     int* order;              /* [N][nt]                              */
+    /* pre-equilibration (ReturnData::x_ss, sx_ss, preeq_*; reference src/rdata.cpp:261-286) */
+    double* x_ss;            /* [N][nx]                              */
+    double* sx_ss;           /* [N][nplist][nx]                      */
+    int* preeq_status;       /* [N][3]  SteadyStateStatus of (Newton, simulation, Newton) */
+    int* preeq_numsteps;     /* [N][3]                               */
+    double* preeq_wrms;      /* [N]                                  */
+    double* preeq_t;         /* [N]                                  */
+    /* event observables (ReturnData::z, sz, rz, srz, sigmaz; reference src/rdata.cpp:434-512) */
+    double* z;               /* [N][nmaxevent][nz]                   */
+    double* sz;              /* [N][nmaxevent][nplist][nz]           */
+    double* rz;              /* [N][nmaxevent][nz]                   */
+    double* srz;             /* [N][nmaxevent][nplist][nz]           */
+    double* sigmaz;          /* [N][nmaxevent][nz]                   */
 } ab_batch;
 
 /* Model dimensions (amici::ModelDimensions, reference include/amici/model_dimensions.h:14). */

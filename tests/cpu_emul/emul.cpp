@@ -16,7 +16,7 @@ using namespace amici_b200;
 template <class M>
 static int run_model(const SolverOptions* o, const BatchView* b) {
     constexpr int NC = M::NP + 1;
-    using Sim = Simulation<M, 1, NC>;
+    using Sim = Simulation<M, 1, NC, true>;
     auto S = std::make_unique<typename Sim::Shared>();
     if (o->sensi >= 1 && b->nplist + 1 > NC) return -1;
     for (int n = 0; n < b->N; ++n) {

@@ -17,9 +17,10 @@ from oracle.refsim import RefModel  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIELDS = ["status", "llh", "chi2", "sllh", "x", "sx", "y", "sy", "sigmay", "ssigmay", "res", "sres", "FIM", "x0",
           "sx0", "xdot", "J", "numsteps"]
+PREEQ_FIELDS = ["x_ss", "sx_ss", "preeq_status", "preeq_numsteps", "preeq_wrms", "preeq_t"]
 
 
-def make(model, ts, N, seed, sensi=1, pscale=None, tag=""):
+def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, **run_kw):
     m = RefModel(model)
     d = m.dims
     rng = np.random.default_rng(seed)
@@ -27,7 +28,9 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag=""):
     p[0] = m.p_nominal
     k = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.8, 1.25, (N, d.nk))
     k[0] = m.k_nominal
-    y0 = m.run(ts, p, k, sensi_order=0, fields=["y"])["y"]
+    k_preeq = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.5, 2.0, (N, d.nk)) if preeq else None
+    fields = FIELDS + (PREEQ_FIELDS if preeq else [])
+    y0 = m.run(ts, p, k, sensi_order=0, fields=["y"], k_preeq=k_preeq, **run_kw)["y"]
     my = y0 + 0.1 * rng.standard_normal(y0.shape)
     my[1, 2, :] = np.nan          # missing measurements
     my[2, :, 0] = np.nan
@@ -37,13 +40,17 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag=""):
     pin = p.copy()
     if pscale is not None:
         pin = np.where(np.asarray(pscale) == 2, np.log10(p), np.where(np.asarray(pscale) == 1, np.log(p), p))
-    kw = dict(my=my, sigmay=sig, sensi_order=sensi, pscale=pscale, fields=FIELDS)
+    kw = dict(my=my, sigmay=sig, sensi_order=sensi, pscale=pscale, fields=fields, k_preeq=k_preeq, **run_kw)
     out = dict(ts=ts, p=pin, k=k, my=my, sigmay_in=sig, pscale=np.zeros(d.np, int) if pscale is None else np.asarray(pscale))
     for name, extra in (("klu", dict(linsol=9)), ("dense", dict(linsol=1)),
                         ("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=200000))):
         r = m.run(ts, pin, k, **{**kw, **extra})
-        for f in FIELDS:
+        for f in fields:
             out[f"{name}_{f}"] = r[f]
+    if preeq:
+        out["k_preeq"] = k_preeq
+        for k_, v in run_kw.items():
+            out["opt_" + k_] = np.asarray(v)
     path = os.path.join(HERE, f"{model}{tag}.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
@@ -53,3 +60,11 @@ if __name__ == "__main__":
     make("jakstat_adjoint", np.arange(0, 61, 5.0), N=6, seed=11)
     make("jakstat_adjoint", np.arange(0, 61, 5.0), N=4, seed=12, pscale=[2] * 17, tag="_log10")
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=13)
+    # BASELINE config 3: pre-equilibration, Newton first / simulation if it fails, steady-state sensitivities from the
+    # Newton linear solve; and the reference's default modes with Newton off (simulation carrying the sensitivities)
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=14, tag="_preeq_newton", preeq=True, newton_maxsteps=50,
+         ss_mode=2, ss_sensi_mode=0)
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=15, tag="_preeq_sim", preeq=True, newton_maxsteps=0,
+         ss_mode=2, ss_sensi_mode=2)
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=16, tag="_preeq_newton2", preeq=True, newton_maxsteps=2,
+         ss_mode=2, ss_sensi_mode=0)

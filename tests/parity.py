@@ -17,7 +17,10 @@ import numpy as np
 
 RTOL, ATOL = 1e-8, 1e-12          # solver tolerances of the fixtures
 FACTOR = 4.0
-FLOAT_FIELDS = ["x", "y", "llh", "chi2", "sigmay", "res", "x0", "xdot", "J", "sx", "sy", "sllh", "ssigmay", "sres", "FIM", "sx0"]
+FLOAT_FIELDS = ["x", "y", "llh", "chi2", "sigmay", "res", "x0", "xdot", "J", "sx", "sy", "sllh", "ssigmay", "sres", "FIM", "sx0",
+                "x_ss", "sx_ss", "z", "sz", "rz", "srz", "sigmaz"]
+# discrete outputs that must be identical to the reference's
+EXACT_FIELDS = ["status", "preeq_status"]
 
 
 def scaled_err(a, b, truth, rtol=10 * RTOL, atol=10 * ATOL):
@@ -32,7 +35,9 @@ def scaled_err(a, b, truth, rtol=10 * RTOL, atol=10 * ATOL):
 def check_against_golden(cand: dict, gold, fields=None, factor=FACTOR, verbose=True):
     """cand: field -> array; gold: loaded npz. Returns report dict; raises AssertionError on failure."""
     report = {}
-    np.testing.assert_array_equal(cand["status"], gold["klu_status"], err_msg="status codes differ")
+    for f in EXACT_FIELDS:
+        if f in cand and f"klu_{f}" in gold:
+            np.testing.assert_array_equal(cand[f], gold[f"klu_{f}"], err_msg=f"{f} differs")
     for f in fields or FLOAT_FIELDS:
         if f not in cand or f"klu_{f}" not in gold:
             continue

@@ -20,7 +20,9 @@ def _emul(built):
 
 def run_emul(lib, model, g, sensi=1, **opt):
     dims = MODEL_DIMS[model]
-    b, out, keep = _capi.make_batch(dims, g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"])
+    b, out, keep = _capi.make_batch(dims, g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
+                                    k_preeq=g["k_preeq"] if "k_preeq" in g else None)
+    opt = {**{k_[4:]: int(g[k_]) for k_ in g.keys() if k_.startswith("opt_")}, **opt}
     o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=sensi, **opt)
     assert lib.emul_run(model.encode(), C.byref(o), C.byref(b)) == 0
     return out
@@ -35,6 +37,45 @@ def test_emulation_matches_golden(built, fixture, model):
     parity.check_against_golden(out, g)
     # step counts are not expected to be equal (chaotic), but must be of the same size
     assert abs(out["numsteps"][:, -1] / g["klu_numsteps"][:, -1] - 1).max() < 0.15
+
+
+@pytest.mark.parametrize("fixture", ["steadystate_preeq_newton", "steadystate_preeq_sim", "steadystate_preeq_newton2"])
+def test_emulation_preequilibration_matches_golden(built, fixture):
+    """Pre-equilibration (Newton / simulation / both) reproduces the reference: same SteadyStateStatus triple, same
+    number of Newton steps, x_ss / sx_ss and everything downstream inside the parity protocol."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    out = run_emul(_emul(built), "steadystate", g)
+    parity.check_against_golden(out, g)
+    np.testing.assert_array_equal(out["preeq_numsteps"][:, 0], g["klu_preeq_numsteps"][:, 0])
+    np.testing.assert_array_equal(out["preeq_numsteps"][:, 2], g["klu_preeq_numsteps"][:, 2])
+    sim = g["klu_preeq_numsteps"][:, 1]
+    assert (np.abs(out["preeq_numsteps"][:, 1] - sim) <= 0.15 * sim + 2).all()
+    np.testing.assert_array_equal(np.isnan(out["preeq_t"]), np.isnan(g["klu_preeq_t"]))
+
+
+def test_preequilibration_failure_modes(built):
+    """Failed pre-equilibration: status AMICI_ERROR, SteadyStateStatus codes, x0 NaN, per-timepoint outputs left at 0
+    and x_ss holding the last state -- checked against the compiled reference when it is available."""
+    from oracle import refsim
+    g = dict(np.load(os.path.join(GOLD, "steadystate_preeq_newton.npz")))
+    cases = [dict(newton_maxsteps=2, ss_mode=0, ss_sensi_mode=0), dict(newton_maxsteps=0, ss_mode=2, ss_sensi_mode=2, maxsteps=30)]
+    for case in cases:
+        for k_, v in case.items():
+            g["opt_" + k_] = np.asarray(v)
+        out = run_emul(_emul(built), "steadystate", g)
+        assert (out["status"] == -99).all()
+        assert np.isnan(out["x0"]).all() and np.isnan(out["sx0"]).all()
+        assert (out["x"] == 0).all() and (out["llh"] == 0).all() and (out["sllh"] == 0).all()
+        assert np.isfinite(out["x_ss"]).all()
+        if refsim.available("steadystate"):
+            r = refsim.RefModel("steadystate").run(g["ts"], g["p"], g["k"], k_preeq=g["k_preeq"], my=g["my"], sigmay=g["sigmay_in"],
+                                                   **{k_: v for k_, v in case.items()})
+            for f in ("status", "preeq_status"):
+                np.testing.assert_array_equal(out[f], r[f], err_msg=f)
+            np.testing.assert_array_equal(out["preeq_numsteps"][:, [0, 2]], r["preeq_numsteps"][:, [0, 2]])
+            for f in ("x", "sx", "y", "llh", "sllh", "x0", "sx0"):
+                np.testing.assert_array_equal(np.isnan(out[f]), np.isnan(r[f]), err_msg=f)
+            np.testing.assert_allclose(out["preeq_wrms"], r["preeq_wrms"], rtol=1e-5)
 
 
 def test_oracle_reproduces_golden():

@@ -22,7 +22,12 @@ def _run(model_name, g, sensi=True, ts=None, **solver_kw):
         s.set_sensitivity_order(ab.SensitivityOrder.first)
     for k_, v in solver_kw.items():
         getattr(s, "set_" + k_)(v)
-    batch = ab.ExpDataBatch(m.get_timepoints(), g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"])
+    if "opt_newton_maxsteps" in g:
+        s.set_newton_max_steps(int(g["opt_newton_maxsteps"]))
+        m.set_steady_state_computation_mode(int(g["opt_ss_mode"]))
+        m.set_steady_state_sensitivity_mode(int(g["opt_ss_sensi_mode"]))
+    batch = ab.ExpDataBatch(m.get_timepoints(), g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
+                            k_preeq=g["k_preeq"] if "k_preeq" in g else None)
     return ab.run_simulations(m, s, batch)
 
 
@@ -32,6 +37,26 @@ def test_cuda_matches_golden(fixture, model):
     g = np.load(os.path.join(GOLD, fixture + ".npz"))
     res = _run(model, g)
     parity.check_against_golden(res.fields, g)
+
+
+@pytest.mark.parametrize("fixture", ["steadystate_preeq_newton", "steadystate_preeq_sim", "steadystate_preeq_newton2"])
+def test_cuda_preequilibration_matches_golden(fixture):
+    """BASELINE config 3: batched Newton steady state + sensitivities, simulation fallback, through the C ABI."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    res = _run("steadystate", g)
+    parity.check_against_golden(res.fields, g)
+    np.testing.assert_array_equal(res["preeq_numsteps"][:, [0, 2]], g["klu_preeq_numsteps"][:, [0, 2]])
+    sim = g["klu_preeq_numsteps"][:, 1]
+    assert (np.abs(res["preeq_numsteps"][:, 1] - sim) <= 0.15 * sim + 2).all()
+
+
+def test_cuda_preequilibration_failure():
+    g = dict(np.load(os.path.join(GOLD, "steadystate_preeq_newton.npz")))
+    g["opt_newton_maxsteps"], g["opt_ss_mode"] = np.asarray(2), np.asarray(0)
+    res = _run("steadystate", g)
+    assert (res["status"] == -99).all() and (res["preeq_status"][:, 0] == -2).all()
+    assert np.isnan(res["x0"]).all() and (res["x"] == 0).all() and (res["llh"] == 0).all()
+    assert np.isfinite(res["x_ss"]).all()
 
 
 def test_cuda_matches_cpu_emulation_bitwise_counters(built):
