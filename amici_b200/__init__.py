@@ -388,6 +388,9 @@ class ExpData:
 
     def __init__(self, model: Model):
         self._ny = model.ny
+        self._nz, self._nmaxevent = model.nz, model.n_max_event()
+        self._mz = np.full(self._nmaxevent * self._nz, np.nan)
+        self._sigmaz = np.full(self._nmaxevent * self._nz, np.nan)
         self.ts_ = model.get_timepoints()
         self.free_parameters: list[float] = []   # empty = use the model's
         self.fixed_parameters: list[float] = []
@@ -421,6 +424,22 @@ class ExpData:
             raise RuntimeError("Encountered sigma <= 0 in sigmay! value: %g" % float(s[~np.isnan(s)].min()))
         self._sigmay = s.copy()
     def get_noise_scales(self): return self._sigmay.copy()
+    def set_event_measurements(self, mz):
+        mz = np.asarray(mz, dtype=np.float64).ravel()
+        if mz.size != self._nmaxevent * self._nz:
+            raise RuntimeError(f"Input observedEvents did not match dimensions nmaxevent ({self._nmaxevent}) x nztrue ({self._nz}), was {mz.size}.")
+        self._mz = mz.copy()
+    def get_event_measurements(self): return self._mz.copy()
+    def set_event_noise_scales(self, s):
+        s = np.asarray(s, dtype=np.float64).ravel()
+        if s.size == 1:
+            s = np.full(self._nmaxevent * self._nz, float(s[0]))
+        if s.size != self._nmaxevent * self._nz:
+            raise RuntimeError(f"Input observedEventsStdDev did not match dimensions nmaxevent ({self._nmaxevent}) x nztrue ({self._nz}), was {s.size}.")
+        if np.any(s[~np.isnan(s)] <= 0):
+            raise RuntimeError("Encountered sigma <= 0 in sigmaz! value: %g" % float(s[~np.isnan(s)].min()))
+        self._sigmaz = s.copy()
+    def get_event_noise_scales(self): return self._sigmaz.copy()
 
 
 class ExpDataBatch:
@@ -476,7 +495,18 @@ class ExpDataBatch:
             k_preeq = np.array([e.fixed_parameters_pre_equilibration for e in edatas], dtype=np.float64)
             if k_preeq.shape != (N, model.nk()):
                 raise RuntimeError("Dimension mismatch. Size of fixed_parameters_pre_equilibration does not match nk.")
-        return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq)
+        mz = sz = None
+        if model.nz > 0 and any(e is not None and not np.isnan(e._mz).all() for e in edatas):
+            nme = model.n_max_event()
+            mz = np.full((N, nme, model.nz), np.nan)
+            sz = np.full((N, nme, model.nz), np.nan)
+            for i, e in enumerate(edatas):
+                if e is not None:
+                    if e._nmaxevent != nme:
+                        raise RuntimeError("amici_b200: ExpData was created with a different n_max_event than the model has now")
+                    mz[i] = e._mz.reshape(nme, model.nz)
+                    sz[i] = e._sigmaz.reshape(nme, model.nz)
+        return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq, mz=mz, sigmaz=sz)
 
 
 _RDATA_ALIASES = {"num_rhs_evals": "numrhsevals", "num_err_test_fails": "numerrtestfails",

@@ -56,12 +56,27 @@ class Observable:
 
 @dataclasses.dataclass
 class Event:
-    """AMICI event: fires when ``root`` crosses zero from below (rising)."""
-    root: sp.Expr                       # trigger function g(t, x, p, k)
-    bolus: dict | None = None           # {state symbol: new value expression} (assignment x <- expr)
-    z: Sequence[sp.Expr] = ()           # event observables recorded at this event
-    time_trigger: sp.Expr | None = None  # explicit trigger time if root == t - time_trigger (pure time event)
+    """AMICI event (reference include/amici/event.h): fires when ``root`` crosses zero from below.
+
+    ``root`` is the trigger function g(t, x, p, k).  Events whose root depends on the state are
+    tracked by the integrator's root finder and must come first (``ne_solver`` of the reference);
+    events whose root depends only on time and parameters (the Heaviside/piecewise switches the
+    reference importer creates in +/- pairs, cf. models/model_events_py/root.cpp) are handled as
+    explicit stop times.  ``assignments`` maps state symbols to their new value (evaluated on the
+    pre-event state).
+    """
+    root: sp.Expr
+    assignments: dict | None = None
     initial_value: bool = True
+
+
+@dataclasses.dataclass
+class EventObservable:
+    """Event-resolved observable z recorded when event ``event`` fires (MeasurementChannel with event_id)."""
+    name: str
+    event: int
+    formula: sp.Expr
+    sigma: sp.Expr = sp.Float(1.0)
 
 
 @dataclasses.dataclass
@@ -77,7 +92,8 @@ class ModelSpec:
     k_nominal: Sequence[float]
     splines: Sequence[Spline] = ()
     events: Sequence[Event] = ()
-    heavisides: Sequence[sp.Symbol] = ()   # h symbols appearing in xdot (value 0/1 state)
+    event_observables: Sequence[EventObservable] = ()
+    heavisides: dict | None = None         # {symbol used in xdot/y: event index}: value of h[event index]
     doc: str = ""
 
 
@@ -156,7 +172,7 @@ def emit_model(spec: ModelSpec) -> str:
     sspl_syms = [sp.Symbol(f"sspl_{s.name}", real=True) for s in spec.splines]
     spl_map = {sp.Symbol(s.name, real=True): spl_syms[i] for i, s in enumerate(spec.splines)}
     spl_map.update({sp.Symbol(s.name): spl_syms[i] for i, s in enumerate(spec.splines)})
-    h_syms = list(spec.heavisides)
+    h_map = dict(spec.heavisides or {})
 
     subs = {}
     for i, s in enumerate(spec.states):
@@ -169,8 +185,8 @@ def emit_model(spec: ModelSpec) -> str:
         subs[s] = sp.Symbol(f"spl[{i}]")
     for i, s in enumerate(sspl_syms):
         subs[s] = sp.Symbol(f"sspl[{i}]")
-    for i, s in enumerate(h_syms):
-        subs[s] = sp.Symbol(f"h[{i}]")
+    for s, ie in h_map.items():
+        subs[s] = sp.Symbol(f"h[{ie}]")
     y_syms = [sp.Symbol(f"y_{o.name}", real=True) for o in spec.observables]
     sig_syms = [sp.Symbol(f"sigma_{o.name}", positive=True) for o in spec.observables]
     my_syms = [sp.Symbol(f"my_{o.name}", real=True) for o in spec.observables]
@@ -216,9 +232,9 @@ def emit_model(spec: ModelSpec) -> str:
     A("// mapping onto the reference's generated <fn>_<model>.cpp files).")
     A(f"#ifndef {guard}\n#define {guard}\n#include \"../model_common.cuh\"\nnamespace amici_b200 {{ namespace models {{\n")
     A(f"struct {spec.name} {{")
-    A(f"    static constexpr int NX = {nx}, NP = {npar}, NK = {nk}, NY = {ny}, NSPL = {nspl}, NE = {ne}, NH = {len(h_syms)};")
+    A(f"    static constexpr int NX = {nx}, NP = {npar}, NK = {nk}, NY = {ny}, NSPL = {nspl}, NE = {ne}, NH = {ne};")
     A(f"    static constexpr int NNZ_J = {nnz};")
-    nz = sum(len(ev.z) for ev in spec.events)
+    nz = len(spec.event_observables)
     A(f"    static constexpr int NZ = {nz};")
     nn_max = max([len(s.nodes) for s in spec.splines], default=1)
     A(f"    static constexpr int SPL_NN = {nn_max};  // nodes per spline")
@@ -452,6 +468,192 @@ def emit_model(spec: ModelSpec) -> str:
                  if sp.diff(sigexpr[iy], spec.params[ip]) != 0]
         A(f"        out[{iy}] = {_select_chain('ip', cases)};")
     A("    }")
+
+    # ---- events (reference generated root/stau/deltax/deltasx/z/rz/dzdx/drzdx/explicit_roots files; the symbolic
+    # ---- construction follows python/sdist/amici/_symbolic/de_model.py:1560-1760) ----
+    roots = [sp.sympify(ev.root).xreplace(spl_map) for ev in spec.events]
+    state_dep = [any(r.has(xs) for xs in spec.states) for r in roots]
+    ne_solver = sum(1 for d_ in state_dep if d_)
+    if any(state_dep[ne_solver:]):
+        raise ValueError("events with state-dependent roots must come first")
+    A(f"    static constexpr int NE_SOLVER = {ne_solver};  // events tracked by the integrator's root finder")
+    if ne:
+        x_old_syms = [sp.Symbol(f"xold_{i}", real=True) for i in range(nx)]
+        xdot_syms = [sp.Symbol(f"xdotnew_{i}", real=True) for i in range(nx)]
+        xdot_old_syms = [sp.Symbol(f"xdotold_{i}", real=True) for i in range(nx)]
+        stau_sym = sp.Symbol("stau_ip", real=True)
+        for i in range(nx):
+            subs[x_old_syms[i]] = sp.Symbol(f"x_old[{i}]")
+            subs[xdot_syms[i]] = sp.Symbol(f"xdot[{i}]")
+            subs[xdot_old_syms[i]] = sp.Symbol(f"xdot_old[{i}]")
+        subs[stau_sym] = sp.Symbol("stau")
+        sig_ev = "const double t, const double* x, const double* p, const double* k, const double* h, const double* spl"
+        z2event = [zo.event for zo in spec.event_observables]
+        zexpr = [sp.sympify(zo.formula).xreplace(spl_map) for zo in spec.event_observables]
+        sigz = [sp.sympify(zo.sigma) for zo in spec.event_observables]
+        drootdt_total = [sp.diff(r, t_sym) + sum((sp.diff(r, spec.states[c]) * xdot[c] for c in range(nx)), sp.Integer(0))
+                         for r in roots]
+        drootdt_total = [sp.simplify(e) for e in drootdt_total]
+
+        A("    AB_HD static bool event_initial_value(const int ie) {")
+        A("        return " + " : ".join([f"(ie == {ie}) ? {'true' if ev.initial_value else 'false'}"
+                                            for ie, ev in enumerate(spec.events)] + ["true"]) + ";")
+        A("    }")
+        A("    AB_HD static int z2event(const int iz) {")
+        A("        return " + " : ".join([f"(iz == {iz}) ? {ie}" for iz, ie in enumerate(z2event)] + ["-1"]) + ";")
+        A("    }")
+        A(f"    AB_HD static void root({sig_ev}, double* root) {{")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl;")
+        A(W.body([(f"root[{ie}]", roots[ie]) for ie in range(ne)]).rstrip("\n"))
+        A("    }")
+        # explicit trigger time of the time-triggered events
+        A("    // trigger time of a time-triggered event (reference explicit_roots_<model>.cpp)")
+        A("    AB_HD static double explicit_time(const int ie, const double* p, const double* k) {")
+        A("        (void)p; (void)k;")
+        for ie in range(ne_solver, ne):
+            sol = sp.solve(roots[ie], t_sym)
+            if len(sol) != 1:
+                raise ValueError(f"event {ie}: expected exactly one trigger time, got {sol}")
+            A(f"        if (ie == {ie}) return {W._pr(sol[0])};")
+        A("        return INFINITY;\n    }")
+        # stau: sroot / drootdt_total (minus the parameter derivative of the event time)
+        A("    // stau = (drootdx*sx + drootdp_ip) / drootdt_total for event ie, parameter ip (reference stau_<model>.cpp)")
+        A(f"    AB_HD static double stau(const int ie, const int ip, {sig_ev}, const double* sx) {{")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)sx; (void)ip;")
+        stau_zero = []
+        for ie in range(ne):
+            if drootdt_total[ie] == 0:
+                stau_zero.append(True)
+                continue
+            lin = sum((sp.diff(roots[ie], spec.states[c]) * sx_syms[c] for c in range(nx)), sp.Integer(0))
+            cases = [(ip, sp.diff(roots[ie], spec.params[ip])) for ip in range(npar) if sp.diff(roots[ie], spec.params[ip]) != 0]
+            stau_zero.append(lin == 0 and not cases)
+            if stau_zero[-1]:
+                continue
+            A(f"        if (ie == {ie}) {{")
+            vals = [("const double lin", lin), ("const double den", drootdt_total[ie])]
+            vals += [(f"const double v_{ip}", e) for ip, e in cases]
+            A(W.body(vals, indent="            ").rstrip("\n"))
+            A(f"            return (lin + ({_select_chain('ip', [(ip, f'v_{ip}') for ip, _ in cases])})) / den;")
+            A("        }")
+        A("        return 0.0;\n    }")
+        # deltax
+        deltax = []
+        for ie, ev in enumerate(spec.events):
+            if not ev.assignments:
+                deltax.append(None)
+                continue
+            to_old = dict(zip(spec.states, x_old_syms))
+            deltax.append([(sp.sympify(ev.assignments[xs]).xreplace(to_old) - xs) if xs in ev.assignments else sp.Integer(0)
+                           for xs in spec.states])
+        A("    // state update x += deltax (reference deltax_<model>.cpp); x_old = state the assignment is evaluated on")
+        A("    AB_HD static void deltax(const int ie, const double t, const double* x, const double* p, const double* k, const double* h, const double* x_old, double* out) {")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)x_old; (void)ie;")
+        for r in range(nx):
+            A(f"        out[{r}] = 0.0;")
+        for ie in range(ne):
+            if deltax[ie] is None:
+                continue
+            A(f"        if (ie == {ie}) {{")
+            A(W.body([(f"out[{r}]", deltax[ie][r]) for r in range(nx)], indent="            ").rstrip("\n"))
+            A("        }")
+        A("    }")
+        A("    AB_HD static bool event_updates_state(const int ie) {")
+        A("        return " + " || ".join([f"ie == {ie}" for ie in range(ne) if deltax[ie] is not None] + ["false"]) + ";")
+        A("    }")
+        # deltasx
+        A("    // sensitivity update sx_ip += deltasx (reference deltasx_<model>.cpp; de_model.py:1700-1750)")
+        A(f"    AB_HD static void deltasx(const int ie, const int ip, {sig_ev}, const double* xdot, const double* xdot_old, const double* sx, const double stau, const double* x_old, double* out) {{")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)xdot; (void)xdot_old; (void)sx; (void)stau; (void)x_old; (void)ip;")
+        for r in range(nx):
+            A(f"        out[{r}] = 0.0;")
+        for ie in range(ne):
+            base = [sp.Integer(0)] * nx
+            if not stau_zero[ie]:
+                base = [(xdot_syms[r] - xdot_old_syms[r]) * stau_sym for r in range(nx)]
+            percase = {}
+            if deltax[ie] is not None:
+                dx_ = deltax[ie]
+                ddx = [[sp.diff(dx_[r], spec.states[c]) + sp.diff(dx_[r], x_old_syms[c]) for c in range(nx)] for r in range(nx)]
+                tmp_dxdp = [sx_syms[c] - (xdot_old_syms[c] * stau_sym if not stau_zero[ie] else 0) for c in range(nx)]
+                for r in range(nx):
+                    add = sum((ddx[r][c] * tmp_dxdp[c] for c in range(nx)), sp.Integer(0))
+                    if not stau_zero[ie]:
+                        add += sp.diff(dx_[r], t_sym) * (-stau_sym)
+                    base[r] = base[r] + add
+                    for ip in range(npar):
+                        e = sp.diff(dx_[r], spec.params[ip])
+                        if e != 0:
+                            percase.setdefault(r, []).append((ip, W._pr(e)))
+            if all(b_ == 0 for b_ in base) and not percase:
+                continue
+            A(f"        if (ie == {ie}) {{")
+            A(W.body([(f"const double b_{r}", base[r]) for r in range(nx)], indent="            ").rstrip("\n"))
+            for r in range(nx):
+                A(f"            out[{r}] = b_{r} + ({_select_chain('ip', percase.get(r, []))});")
+            A("        }")
+        A("    }")
+        # z, sz, rz, srz, sigmaz
+        dtaudx = [[(sp.diff(roots[ie], spec.states[c]) / drootdt_total[ie]) if drootdt_total[ie] != 0 else sp.Integer(0)
+                   for c in range(nx)] for ie in range(ne)]
+        A("    // event observables of event ie (only the entries iz with z2event(iz) == ie are written; reference z_/rz_<model>.cpp)")
+        A(f"    AB_HD static void z(const int ie, {sig_ev}, double* z) {{")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)ie; (void)z;")
+        for iz in range(nz):
+            A(f"        if (ie == {z2event[iz]}) z[{iz}] = {W._pr(zexpr[iz])};")
+        A("    }")
+        A(f"    AB_HD static void rz(const int ie, {sig_ev}, double* rz) {{")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)ie; (void)rz;")
+        for iz in range(nz):
+            A(f"        if (ie == {z2event[iz]}) rz[{iz}] = {W._pr(roots[z2event[iz]])};")
+        A("    }")
+        A("    // sz = dzdx*sx + dzdp with dzdx including -dz/dt * dtau/dx (reference src/model.cpp:1267-1296; de_model.py:1622-1641)")
+        A(f"    AB_HD static void sz(const int ie, const int ip, {sig_ev}, const double* sx, double* sz) {{")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)ie; (void)ip; (void)sx; (void)sz;")
+        for iz in range(nz):
+            ie = z2event[iz]
+            lin = sum(((sp.diff(zexpr[iz], spec.states[c]) - sp.diff(zexpr[iz], t_sym) * dtaudx[ie][c]) * sx_syms[c]
+                       for c in range(nx)), sp.Integer(0))
+            cases = [(ip, W._pr(sp.diff(zexpr[iz], spec.params[ip]))) for ip in range(npar) if sp.diff(zexpr[iz], spec.params[ip]) != 0]
+            A(f"        if (ie == {ie}) sz[{iz}] = ({W._pr(sp.simplify(lin))}) + ({_select_chain('ip', cases)});")
+        A("    }")
+        A("    // srz = drootdx*sx + drootdp (reference src/model.cpp:1317-1350)")
+        A(f"    AB_HD static void srz(const int ie, const int ip, {sig_ev}, const double* sx, double* srz) {{")
+        A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)ie; (void)ip; (void)sx; (void)srz;")
+        for iz in range(nz):
+            ie = z2event[iz]
+            lin = sum((sp.diff(roots[ie], spec.states[c]) * sx_syms[c] for c in range(nx)), sp.Integer(0))
+            cases = [(ip, W._pr(sp.diff(roots[ie], spec.params[ip]))) for ip in range(npar) if sp.diff(roots[ie], spec.params[ip]) != 0]
+            A(f"        if (ie == {ie}) srz[{iz}] = ({W._pr(lin)}) + ({_select_chain('ip', cases)});")
+        A("    }")
+        A("    AB_HD static void sigmaz(const double* p, const double* k, double* sigmaz) {")
+        A("        (void)p; (void)k; (void)sigmaz;")
+        if nz:
+            A(W.body([(f"sigmaz[{iz}]", sigz[iz]) for iz in range(nz)]).rstrip("\n"))
+        A("    }")
+        A("    AB_HD static void dsigmazdp(const int ip, const double* p, const double* k, double* out) {")
+        A("        (void)p; (void)k; (void)ip; (void)out;")
+        for iz in range(nz):
+            cases = [(ip, W._pr(sp.diff(sigz[iz], spec.params[ip]))) for ip in range(npar) if sp.diff(sigz[iz], spec.params[ip]) != 0]
+            A(f"        out[{iz}] = {_select_chain('ip', cases)};")
+        A("    }")
+
+    if not ne:
+        A("    // no events: stubs so that the event code paths compile away")
+        A("    AB_HD static bool event_initial_value(const int) { return true; }")
+        A("    AB_HD static int z2event(const int) { return -1; }")
+        A("    AB_HD static void root(const double, const double*, const double*, const double*, const double*, const double*, double*) {}")
+        A("    AB_HD static double explicit_time(const int, const double*, const double*) { return INFINITY; }")
+        A("    AB_HD static double stau(const int, const int, const double, const double*, const double*, const double*, const double*, const double*, const double*) { return 0.0; }")
+        A("    AB_HD static void deltax(const int, const double, const double*, const double*, const double*, const double*, const double*, double*) {}")
+        A("    AB_HD static bool event_updates_state(const int) { return false; }")
+        A("    AB_HD static void deltasx(const int, const int, const double, const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double, const double*, double*) {}")
+        A("    AB_HD static void z(const int, const double, const double*, const double*, const double*, const double*, const double*, double*) {}")
+        A("    AB_HD static void rz(const int, const double, const double*, const double*, const double*, const double*, const double*, double*) {}")
+        A("    AB_HD static void sz(const int, const int, const double, const double*, const double*, const double*, const double*, const double*, const double*, double*) {}")
+        A("    AB_HD static void srz(const int, const int, const double, const double*, const double*, const double*, const double*, const double*, const double*, double*) {}")
+        A("    AB_HD static void sigmaz(const double*, const double*, double*) {}")
+        A("    AB_HD static void dsigmazdp(const int, const double*, const double*, double*) {}")
 
     # splines: node positions, node values and their parameter derivative (select chain)
     if nspl:

@@ -12,7 +12,7 @@ import os
 
 import sympy as sp
 
-from .emitter import ModelSpec, Observable, Spline, write_model
+from .emitter import Event, EventObservable, ModelSpec, Observable, Spline, t_sym, write_model
 
 
 def _syms(names):
@@ -82,7 +82,39 @@ def robertson_ode() -> ModelSpec:
                      x0=[k1, 0, 1 - k1], observables=obs, p_nominal=[0.04, 1e4, 3e7], k_nominal=[0.9])
 
 
-ALL = {"jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode}
+def events() -> ModelSpec:
+    """The reference's events test model (reference python/sdist/amici/testing/models.py:261-323; generated code
+    models/model_events_py/): two state-triggered events with event observables z = t, and two piecewise time
+    switches that the reference importer turns into +/- root pairs (root.cpp: p4-t, t-p4, 4-t, t-4) whose
+    Heaviside states h[2], h[4] enter xdot."""
+    x1, x2, x3 = states = _syms("x1 x2 x3")
+    p1, p2, p3, p4 = params = _syms("p1 p2 p3 p4")
+    k1, k2, k3, k4 = fixed = _syms("k1 k2 k3 k4")
+    h2, h4 = _syms("Heaviside_2 Heaviside_4")
+    t = t_sym
+    xdot = [-p1 * x1 * (1 - h2), p2 * x1 * sp.exp(-t / 10) - p3 * x2, -h4 - x3 + 1]
+    evs = [Event(x2 - x3), Event(x1 - x3), Event(p4 - t), Event(t - p4), Event(4 - t), Event(t - 4)]
+    zs = [EventObservable("z1", 0, t), EventObservable("z2", 1, t)]
+    return ModelSpec(name="events", states=states, params=params, fixed=fixed, xdot=xdot, x0=[k1, k2, k3],
+                     observables=[Observable("y1", p4 * (x1 + x2 + x3))], p_nominal=[0.5, 2, 0.5, 0.5],
+                     k_nominal=[4, 8, 10, 4], events=evs, event_observables=zs, heavisides={h2: 2, h4: 4})
+
+
+def neuron() -> ModelSpec:
+    """The reference's neuron test model (reference python/sdist/amici/testing/models.py:192-258; generated code
+    models/model_neuron_py/): Izhikevich neuron, spike event v > 30 with reset v <- -c, u <- u + d and z = t."""
+    v, u = states = _syms("v u")
+    a, b, c, d = params = _syms("a b c d")
+    v0, I0 = fixed = _syms("v0 I0")
+    xdot = [sp.Rational(1, 25) * v ** 2 + 5 * v + 140 - u + I0, a * (b * v - u)]
+    evs = [Event(v - 30, assignments={v: -c, u: d + u})]
+    return ModelSpec(name="neuron", states=states, params=params, fixed=fixed, xdot=xdot, x0=[v0, b * v0],
+                     observables=[Observable("y1", v)], p_nominal=[0.02, 0.3, 65, 0.9], k_nominal=[-60, 10],
+                     events=evs, event_observables=[EventObservable("z1", 0, t_sym)])
+
+
+ALL = {"jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode,
+       "events": events, "neuron": neuron}
 
 
 def generate_all(out_dir: str | None = None) -> list[str]:

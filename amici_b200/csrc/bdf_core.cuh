@@ -547,6 +547,16 @@ struct Bdf {
     int convfail, ss_head;
     bool jcur, tstopset, dense_lu;
 
+    // root finding (CVodeRootInit, cvodes.c:2674; cvRcheck1/2/3, cvRootfind :8576-9100) for the NES solver-tracked
+    // event triggers; all group-uniform, arrays only indexed with compile-time constants
+    static constexpr int NES = M::NE_SOLVER > 0 ? M::NE_SOLVER : 1;
+    double glo[NES], ghi[NES], grout[NES];
+    bool gactive[NES];
+    int iroots[NES];
+    double tlo, thi, trout, ttol;
+    int irfnd, nge;
+    bool reinit_pending;   // AMICI's CVodeSolver::reinit happened: the next call starts with reInit_post_process
+
     AB_HD Bdf(Shared& s, const SolverOptions& opt, int ncols_) : S(s), o(opt), ncols(ncols_) {}
 
     AB_HD int col(int c) const { return g.lane + G * c; }
@@ -1091,6 +1101,253 @@ struct Bdf {
     }
 
     // -----------------------------------------------------------------------------------------
+    // root finding on the state column (every lane evaluates g redundantly from column 0 in shared memory)
+    // -----------------------------------------------------------------------------------------
+    AB_HD void root_init() {
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) { glo[i] = ghi[i] = grout[i] = 0.0; gactive[i] = true; iroots[i] = 0; }
+        tlo = thi = trout = ttol = 0.0;
+        irfnd = 0;
+        nge = 0;
+    }
+    // CVodeGetDky(t, 0) for the state column: y(t) = sum_j zn[j] * s^j, s = (t - tn) / h
+    AB_HD void state_at(double t, double (&y)[NX]) const {
+        const double s = (t - tn) / h;
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) {
+            double v = 0.0;
+            AB_UNROLL
+            for (int j = QMAX; j >= 0; --j)
+                if (j <= q) v = v * s + S.zn[j][r][0];
+            y[r] = v;
+        }
+    }
+    // zn[0] + a * zn[1] for the state column
+    AB_HD void state_lin(double a, double (&y)[NX]) const {
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) y[r] = S.zn[0][r][0] + (a != 0.0 ? a * S.zn[1][r][0] : 0.0);
+    }
+    AB_HD void eval_g(double t, const double (&y)[NX], double (&gv)[NES]) {
+        double spl[M::NSPL > 0 ? M::NSPL : 1], rv[M::NE > 0 ? M::NE : 1];
+        AB_UNROLL
+        for (int is = 0; is < M::NSPL; ++is) {
+            const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
+            spl[is] = M::SPL_LOG ? exp(v) : v;
+        }
+        M::root(t, y, S.p, S.k, S.h, spl, rv);
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) gv[i] = rv[i];
+        nge++;
+    }
+    // Solution at the root: overwrite zn[0] of every column by y(trout) and move tn there.  AMICI re-initialises the
+    // solver after every root return (reference src/forwardproblem.cpp:389-514), so the history is not needed again.
+    AB_HD void collapse_to(double t) {
+        const double s = (t - tn) / h;
+        g.sync();
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_NOUNROLL
+            for (int r = 0; r < NX; ++r) {
+                double v = 0.0;
+                AB_UNROLL
+                for (int j = QMAX; j >= 0; --j)
+                    if (j <= q) v = v * s + S.zn[j][r][col(c)];
+                S.zn[0][r][col(c)] = v;
+            }
+        }
+        g.sync();
+        tn = t;
+    }
+    // cvRcheck1 (cvodes.c:8576)
+    AB_HD void rcheck1() {
+        double y[NX];
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) iroots[i] = 0;
+        tlo = tn;
+        ttol = (fabs(tn) + fabs(h)) * DBL_EPSILON * 100.0;
+        g.sync();
+        state_lin(0.0, y);
+        eval_g(tlo, y, glo);
+        nge = 1;
+        bool zroot = false;
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i)
+            if (fabs(glo[i]) == 0.0) { zroot = true; gactive[i] = false; }
+        if (!zroot) return;
+        const double hratio = ab_max(ttol / fabs(h), 0.1);
+        const double tplus = tlo + hratio * h;
+        state_lin(hratio, y);
+        eval_g(tplus, y, ghi);
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i)
+            if (!gactive[i] && fabs(ghi[i]) != 0.0) { gactive[i] = true; glo[i] = ghi[i]; }
+    }
+    // cvRcheck2 (cvodes.c:8648): 0, 1 = RTFOUND, 3 = CLOSERT
+    AB_HD int rcheck2() {
+        if (irfnd == 0) return 0;
+        double y[NX];
+        g.sync();
+        state_at(tlo, y);
+        eval_g(tlo, y, glo);
+        bool zroot = false;
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) iroots[i] = 0;
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i)
+            if (gactive[i] && fabs(glo[i]) == 0.0) { zroot = true; iroots[i] = 1; }
+        if (!zroot) return 0;
+        ttol = (fabs(tn) + fabs(h)) * DBL_EPSILON * 100.0;
+        const double smallh = (h > 0.0) ? ttol : -ttol;
+        const double tplus = tlo + smallh;
+        if ((tplus - tn) * h >= 0.0) {
+            const double hratio = smallh / h;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) y[r] += hratio * S.zn[1][r][0];
+        } else {
+            state_at(tplus, y);
+        }
+        eval_g(tplus, y, ghi);
+        zroot = false;
+        bool closert = false;
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) {
+            if (!gactive[i]) continue;
+            if (fabs(ghi[i]) == 0.0) {
+                if (iroots[i] == 1) closert = true;
+                zroot = true;
+                iroots[i] = 1;
+            } else if (iroots[i] == 1) {
+                glo[i] = ghi[i];
+            }
+        }
+        if (closert) return 3;
+        return zroot ? 1 : 0;
+    }
+    // sign-change scan shared by cvRootfind's entry and loop (cvodes.c:8871-8900, :8990-9020)
+    AB_HD void scan_signs(const double (&gv)[NES], bool& zroot, bool& sgnchg, int& imax) const {
+        double maxfrac = 0.0;
+        zroot = false;
+        sgnchg = false;
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) {
+            if (!gactive[i]) continue;
+            if (fabs(gv[i]) == 0.0) {
+                zroot = true;   // rootdir = 0: both directions
+            } else if ((glo[i] < 0.0 && gv[i] > 0.0) || (glo[i] > 0.0 && gv[i] < 0.0)) {
+                const double gfrac = fabs(gv[i] / (gv[i] - glo[i]));
+                if (gfrac > maxfrac) { sgnchg = true; maxfrac = gfrac; imax = i; }
+            }
+        }
+    }
+    // cvRootfind (cvodes.c:8859): Illinois iteration on (tlo, thi]; returns true if a root was found
+    AB_HD bool rootfind() {
+        int imax = 0;
+        bool zroot, sgnchg;
+        scan_signs(ghi, zroot, sgnchg, imax);
+        if (!sgnchg) {
+            trout = thi;
+            AB_UNROLL
+            for (int i = 0; i < NES; ++i) grout[i] = ghi[i];
+            if (!zroot) return false;
+            AB_UNROLL
+            for (int i = 0; i < NES; ++i) {
+                iroots[i] = 0;
+                if (gactive[i] && fabs(ghi[i]) == 0.0) iroots[i] = glo[i] > 0.0 ? -1 : 1;
+            }
+            return true;
+        }
+        double alph = 1.0;
+        int side = 0, sideprev = -1;
+        for (;;) {
+            if (fabs(thi - tlo) <= ttol) break;
+            if (sideprev == side) alph = (side == 2) ? alph * 2.0 : alph * 0.5;
+            else alph = 1.0;
+            const double ghim = pick(ghi, imax), glom = pick(glo, imax);
+            double tmid = thi - (thi - tlo) * ghim / (ghim - alph * glom);
+            if (fabs(tmid - tlo) < 0.5 * ttol) {
+                const double fracint = fabs(thi - tlo) / ttol;
+                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+                tmid = tlo + fracsub * (thi - tlo);
+            }
+            if (fabs(thi - tmid) < 0.5 * ttol) {
+                const double fracint = fabs(thi - tlo) / ttol;
+                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+                tmid = thi - fracsub * (thi - tlo);
+            }
+            double y[NX];
+            state_at(tmid, y);
+            eval_g(tmid, y, grout);
+            sideprev = side;
+            scan_signs(grout, zroot, sgnchg, imax);
+            if (sgnchg) {
+                thi = tmid;
+                AB_UNROLL
+                for (int i = 0; i < NES; ++i) ghi[i] = grout[i];
+                side = 1;
+                if (fabs(thi - tlo) <= ttol) break;
+                continue;
+            }
+            if (zroot) {
+                thi = tmid;
+                AB_UNROLL
+                for (int i = 0; i < NES; ++i) ghi[i] = grout[i];
+                break;
+            }
+            tlo = tmid;
+            AB_UNROLL
+            for (int i = 0; i < NES; ++i) glo[i] = grout[i];
+            side = 2;
+            if (fabs(thi - tlo) <= ttol) break;
+        }
+        trout = thi;
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) {
+            grout[i] = ghi[i];
+            iroots[i] = 0;
+            if (!gactive[i]) continue;
+            if (fabs(ghi[i]) == 0.0) iroots[i] = glo[i] > 0.0 ? -1 : 1;
+            if ((glo[i] < 0.0 && ghi[i] > 0.0) || (glo[i] > 0.0 && ghi[i] < 0.0)) iroots[i] = glo[i] > 0.0 ? -1 : 1;
+        }
+        return true;
+    }
+    // cvRcheck3 (cvodes.c:8725): look for a root in (tlo, min(tn, tout)]; true = found (trout, iroots set)
+    AB_HD bool rcheck3(double toutc, bool one_step) {
+        double y[NX];
+        g.sync();
+        if (one_step || (toutc - tn) * h >= 0.0) {
+            thi = tn;
+            state_lin(0.0, y);
+        } else {
+            thi = toutc;
+            state_at(thi, y);
+        }
+        eval_g(thi, y, ghi);
+        ttol = (fabs(tn) + fabs(h)) * DBL_EPSILON * 100.0;
+        const bool found = rootfind();
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i)
+            if (!gactive[i] && grout[i] != 0.0) gactive[i] = true;
+        tlo = trout;
+        AB_UNROLL
+        for (int i = 0; i < NES; ++i) glo[i] = grout[i];
+        return found;
+    }
+
+    // CVodeSolver::reinit + sens_reinit (reference src/solver_cvodes.cpp:471-503, :586-616): the caller has written the
+    // post-event state and sensitivities to zn[0]; restart at order 1 keeping counters, step-size history and linear
+    // solver data; the next solve_to call begins with reInit_post_process (:517-565).
+    AB_HD void amici_reinit(double t0) {
+        tn = t0;
+        q = 1;
+        L = 2;
+        qwait = 2;
+        qu = 0;
+        hu = 0.0;
+        reinit_pending = true;
+    }
+
+    // -----------------------------------------------------------------------------------------
     // cvStep (cvodes.c:5800) with cvHandleNFlag (:7309) and cvDoErrorTest (:7461) folded in: every
     // retry path sets flags that are executed at the single history-manipulation site at the loop top.
     // -----------------------------------------------------------------------------------------
@@ -1200,6 +1457,8 @@ struct Bdf {
         etaq = etaqm1 = etaqp1 = 0.0;
         tstopset = false; tstop = 0.0; tretlast = t0;
         convfail = CONVFAIL_NONE; jcur = false; dense_lu = false;
+        reinit_pending = false;
+        root_init();
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             AB_UNROLL
@@ -1223,11 +1482,22 @@ struct Bdf {
     // Both modes share this function so that the (inlined) step has a single call site.
     // -----------------------------------------------------------------------------------------
     AB_HD int solve_to(double tout, bool one_step = false) {
+        constexpr bool ROOTS = M::NE_SOLVER > 0;
         // Solver::apply_max_num_steps (reference src/solver.cpp:107-119)
         if (o.maxsteps <= nst) return AB_ERROR;
         const int mxstep = o.maxsteps - nst;
         tstop = tout;
         tstopset = !one_step;
+        // reInit_post_process (reference src/solver_cvodes.cpp:517-565): after an event the first step is taken as a
+        // "first call" (nst = 0) in one-step mode with tstop = tout, then the step counter is restored
+        bool post = ROOTS || M::NE > 0 ? reinit_pending : false;
+        int nst_saved = 0;
+        if (post) {
+            reinit_pending = false;
+            nst_saved = nst;
+            nst = 0;
+            set_ewt();   // cvInitialSetup
+        }
         if (nst == 0) {
             // first call: zn[1] = f(t0, y0) (cvodes.c first-call block), initial step, zn[1] *= h
             const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, 1.0, 1);
@@ -1251,15 +1521,34 @@ struct Bdf {
                 AB_UNROLL
                 for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] *= h;
             }
-        } else if (tstopset) {
+            if (ROOTS) rcheck1();
+        } else {
             const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
-            if (fabs(tn - tstop) <= troundoff) {
-                tretlast = tstop;
-                tstopset = false;
-                return AB_TSTOP_RETURN;
-            } else if ((tn + hprime - tstop) * h > 0.0) {
-                hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                eta = hprime / h;
+            if (ROOTS) {   // cvodes.c "check for a root in the last step taken" on entry
+                const int irfndp = irfnd;
+                const int rc = rcheck2();
+                if (rc == 3) return AB_ILL_INPUT;
+                if (rc == 1) { tretlast = tlo; collapse_to(tlo); return AB_ROOT_RETURN; }
+                if (fabs(tn - tretlast) > troundoff) {
+                    if (rcheck3(tout, one_step)) {
+                        irfnd = 1;
+                        tretlast = tlo;
+                        collapse_to(tlo);
+                        return AB_ROOT_RETURN;
+                    }
+                    irfnd = 0;
+                    if (irfndp == 1 && one_step) { tretlast = tn; return AB_SUCCESS; }
+                }
+            }
+            if (tstopset) {
+                if (fabs(tn - tstop) <= troundoff) {
+                    tretlast = tstop;
+                    tstopset = false;
+                    return AB_TSTOP_RETURN;
+                } else if ((tn + hprime - tstop) * h > 0.0) {
+                    hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+                    eta = hprime / h;
+                }
             }
         }
         int nstloc = 0;
@@ -1271,10 +1560,39 @@ struct Bdf {
             const int kflag = step();
             if (kflag != AB_SUCCESS) { tretlast = tn; return kflag; }
             nstloc++;
+            double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
+            const bool at_tstop = tstopset && fabs(tn - tstop) <= troundoff;
+            if (at_tstop) tn = tstop;
+            if (ROOTS) {
+                if (rcheck3(tout, one_step || post)) {
+                    irfnd = 1;
+                    tretlast = tlo;
+                    // a root right after re-initialisation is an error in the reference (src/solver_cvodes.cpp:531-540)
+                    if (post) { nst = nst_saved + 1; return AB_ERROR; }
+                    collapse_to(tlo);
+                    return AB_ROOT_RETURN;
+                }
+            }
+            if ((ROOTS || M::NE > 0) && post) {
+                // end of reInit_post_process: anything but CV_SUCCESS throws there; then the regular call starts
+                nst = nst_saved + 1;
+                post = false;
+                nstloc = 0;
+                tretlast = tn;
+                if (at_tstop) return AB_ERROR;
+                if ((tn + hprime - tstop) * h > 0.0) {
+                    hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+                    eta = hprime / h;
+                }
+                if (ROOTS) {
+                    const int rc = rcheck2();
+                    if (rc == 3) return AB_ILL_INPUT;
+                    if (rc == 1) { tretlast = tlo; collapse_to(tlo); return AB_ROOT_RETURN; }
+                }
+                continue;
+            }
             if (one_step) { tretlast = tn; return AB_SUCCESS; }
-            const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
-            if (fabs(tn - tstop) <= troundoff) {
-                tn = tstop;
+            if (at_tstop) {
                 tretlast = tstop;
                 tstopset = false;
                 return AB_TSTOP_RETURN;

@@ -65,6 +65,8 @@ static const ModelEntry* registry(int* count) {
         entry_jakstat_adjoint(),
         entry_steadystate(),
         entry_robertson_ode(),
+        entry_events(),
+        entry_neuron(),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
@@ -87,6 +89,7 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
     if (o->sensi >= 1 && b->nplist > 0 && !b->plist) { g_err = "plist is NULL"; return AB_E_BAD_ARGUMENT; }
     if (o->sensi >= 1 && o->ism != 1) { g_err = "only simultaneous forward sensitivities are implemented"; return AB_E_UNSUPPORTED; }
     if (!(o->rtol >= 0) || !(o->atol >= 0)) { g_err = "negative tolerance"; return AB_E_BAD_ARGUMENT; }
+    if (o->nmaxevent < 0) { g_err = "nmaxevent must be non-negative"; return AB_E_BAD_ARGUMENT; }
     if (b->k_preeq && (!(o->rtol_ss >= 0) || !(o->atol_ss >= 0) || !(o->rtol_ss_sensi >= 0) || !(o->atol_ss_sensi >= 0))) {
         g_err = "steady-state tolerances must be resolved (non-negative) when k_preeq is given";
         return AB_E_BAD_ARGUMENT;
@@ -152,6 +155,15 @@ int ab_solve_device(const char* model, const ab_solver_options* opt, const ab_ba
     if (b->res) AB_CUDA(cudaMemsetAsync(b->res, 0, sizeof(double) * N * nt * ny, st));
     if (b->sres && npl) AB_CUDA(cudaMemsetAsync(b->sres, 0, sizeof(double) * N * nt * ny * npl, st));
     if (b->FIM && npl) AB_CUDA(cudaMemsetAsync(b->FIM, 0, sizeof(double) * N * npl * npl, st));
+    // event-observable slots that are never reached stay 0 as in the reference (src/rdata.cpp:160-165, :203-205)
+    const size_t nzs = (size_t)e->dims.nz * (opt->nmaxevent > 0 ? opt->nmaxevent : 0) * N;
+    if (nzs) {
+        if (b->z) AB_CUDA(cudaMemsetAsync(b->z, 0, sizeof(double) * nzs, st));
+        if (b->rz) AB_CUDA(cudaMemsetAsync(b->rz, 0, sizeof(double) * nzs, st));
+        if (b->sigmaz) AB_CUDA(cudaMemsetAsync(b->sigmaz, 0, sizeof(double) * nzs, st));
+        if (b->sz && npl) AB_CUDA(cudaMemsetAsync(b->sz, 0, sizeof(double) * nzs * npl, st));
+        if (b->srz && npl) AB_CUDA(cudaMemsetAsync(b->srz, 0, sizeof(double) * nzs * npl, st));
+    }
     return e->launch(*opt, *b, work_counter, st);
 }
 

@@ -34,6 +34,8 @@ struct ModelEntry {
 ModelEntry entry_jakstat_adjoint();
 ModelEntry entry_steadystate();
 ModelEntry entry_robertson_ode();
+ModelEntry entry_events();
+ModelEntry entry_neuron();
 
 }  // namespace amici_b200
 #endif

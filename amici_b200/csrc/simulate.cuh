@@ -40,6 +40,13 @@ struct Simulation {
     int nplist;
     double llh, chi2;
     double sllh[C];
+    // event bookkeeping (FwdSimWorkspace, reference include/amici/forwardproblem.h:109-175): group-uniform registers
+    static constexpr int NEV = M::NE > 0 ? M::NE : 1, NZV = M::NZ > 0 ? M::NZ : 1;
+    int roots_found[NEV], nroots[NEV];
+    double rootvals[NEV], rval_tmp[NEV];
+    double ev_x_old[NX], ev_xdot_old[NX];
+    double stau[C];
+    double tlastroot, t_trig_done;
 
     AB_HD Simulation(Shared& s, const SolverOptions& opt, const BatchView& bv, int n_)
         : S(s), o(opt), b(bv), bdf(s, opt, (opt.sensi >= 1 ? 1 + bv.nplist : 1)), n(n_),
@@ -296,6 +303,291 @@ struct Simulation {
         }
     }
 
+    // ---------------------------------------------------------------------------------------------
+    // events (EventHandlingSimulator, reference src/forwardproblem.cpp:389-735; Model event functions,
+    // reference src/model.cpp:407-472, :1464-1534, :1588-1592; event outputs src/rdata.cpp:434-512)
+    // ---------------------------------------------------------------------------------------------
+    AB_HD void state_col(double (&x)[NX]) const {
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) x[r] = S.zn[0][r][0];
+    }
+    AB_HD void eval_roots(double t, const double (&x)[NX], double (&rv)[NEV]) const {
+        double spl[M::NSPL > 0 ? M::NSPL : 1];
+        spline_values_at<M, G, C>(S, t, spl);
+        M::root(t, x, S.p, S.k, S.h, spl, rv);
+    }
+    AB_HD void eval_xdot(double t, const double (&x)[NX], double (&f)[NX]) const {
+        double spl[M::NSPL > 0 ? M::NSPL : 1];
+        spline_values_at<M, G, C>(S, t, spl);
+        M::xdot(t, x, S.p, S.k, S.h, spl, f);
+    }
+    // h += roots_found (Model::update_heaviside)
+    AB_HD void update_heaviside() {
+        auto& g = bdf.g;
+        g.sync();
+        if (g.lane == 0) {
+            AB_UNROLL
+            for (int ie = 0; ie < M::NE; ++ie) S.h[ie] += roots_found[ie];
+        }
+        g.sync();
+    }
+    // Model::initialize_events / reinit_events (reference src/model.cpp:407-442)
+    AB_HD void initialize_events(double t) {
+        auto& g = bdf.g;
+        double x[NX], rv[NEV];
+        g.sync();
+        state_col(x);
+        eval_roots(t, x, rv);
+        AB_UNROLL
+        for (int ie = 0; ie < M::NE; ++ie) {
+            roots_found[ie] = (!(rv[ie] < 0.0) && !M::event_initial_value(ie)) ? 1 : 0;
+            nroots[ie] = 0;
+            rootvals[ie] = rval_tmp[ie] = 0.0;
+        }
+        g.sync();
+        if (g.lane == 0) {
+            AB_UNROLL
+            for (int ie = 0; ie < M::NE; ++ie) S.h[ie] = (rv[ie] < 0.0) ? 0.0 : 1.0;
+        }
+        g.sync();
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) stau[c] = 0.0;
+        tlastroot = t;
+        t_trig_done = t;
+    }
+    // next explicit trigger time in (t_trig_done, t_end] (Model::get_trigger_timepoints, filtered as in
+    // reference src/forwardproblem.cpp:70-79)
+    AB_HD double next_trigger(double t_end) const {
+        double best = INFINITY;
+        AB_UNROLL
+        for (int ie = M::NE_SOLVER; ie < M::NE; ++ie) {
+            const double te = M::explicit_time(ie, S.p, S.k);
+            if (te > t_trig_done && te <= t_end && te < best) best = te;
+        }
+        return best;
+    }
+
+    // ReturnData::get_event_output + get_event_sensis_fsa for the events flagged in roots_found, from the current
+    // (pre-event) state; EventHandlingSimulator::store_event's counter logic (reference src/forwardproblem.cpp:524-574)
+    AB_HD void store_event(double t) {
+        auto& g = bdf.g;
+        const int nt = b.nt, nme = o.nmaxevent;
+        const bool is_last = nt > 0 && t == b.ts[nt - 1];
+        double x[NX];
+        g.sync();
+        state_col(x);
+        for (;;) {
+        if (is_last) {
+            eval_roots(t, x, rootvals);
+            AB_UNROLL
+            for (int ie = 0; ie < M::NE; ++ie) roots_found[ie] = nroots[ie] < nme ? 1 : 0;
+        }
+        double spl[M::NSPL > 0 ? M::NSPL : 1];
+        spline_values_at<M, G, C>(S, t, spl);
+        AB_UNROLL
+        for (int ie = 0; ie < M::NE; ++ie) {
+            if (nroots[ie] >= nme) continue;
+            if (roots_found[ie] != 1) continue;
+            const int slot = nroots[ie];
+            const size_t zrow = ((size_t)n * nme + slot) * M::NZ;
+            double zv[NZV], rzv[NZV], sig[NZV], mz[NZV];
+            bool mz_set[NZV], sig_set[NZV];
+            AB_UNROLL
+            for (int iz = 0; iz < M::NZ; ++iz) zv[iz] = rzv[iz] = 0.0;
+            M::z(ie, t, x, S.p, S.k, S.h, spl, zv);
+            M::rz(ie, t, x, S.p, S.k, S.h, spl, rzv);
+            M::sigmaz(S.p, S.k, sig);
+            AB_UNROLL
+            for (int iz = 0; iz < M::NZ; ++iz) {
+                mz[iz] = b.mz ? b.mz[zrow + iz] : ab_nan();
+                mz_set[iz] = (mz[iz] == mz[iz]) && M::z2event(iz) == ie;
+                const double se = b.sigmaz_in ? b.sigmaz_in[zrow + iz] : ab_nan();
+                sig_set[iz] = (se == se);
+                if (sig_set[iz]) sig[iz] = se;
+            }
+            AB_UNROLL
+            for (int c = 0; c < C; ++c) {
+                if (!bdf.active(c)) continue;
+                const int cc = bdf.col(c);
+                if (cc == 0) {
+                    AB_UNROLL
+                    for (int iz = 0; iz < M::NZ; ++iz) {
+                        if (M::z2event(iz) != ie) continue;
+                        if (full()) {
+                            if (b.z) b.z[zrow + iz] = zv[iz];
+                            if (b.rz && is_last) b.rz[zrow + iz] = rzv[iz];
+                            if (b.sigmaz) b.sigmaz[zrow + iz] = sig[iz];
+                        }
+                        if (mz_set[iz]) {
+                            const double pi_ = 3.14159265358979323846;
+                            const double s2 = sig[iz] * sig[iz], r_ = zv[iz] - mz[iz];
+                            llh -= 0.5 * log(2.0 * pi_ * s2) + 0.5 * r_ * r_ / s2;                      // Jz
+                            if (is_last) llh -= 0.5 * log(2.0 * pi_ * s2) + 0.5 * rzv[iz] * rzv[iz] / s2;  // Jrz
+                        }
+                    }
+                } else {
+                    const int ip = S.ip_of_col[cc], il = cc - 1;
+                    const double pc = S.pcoef[cc];
+                    double sxc[NX], szv[NZV], srzv[NZV], dsig[NZV];
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) sxc[r] = S.zn[0][r][cc];
+                    AB_UNROLL
+                    for (int iz = 0; iz < M::NZ; ++iz) szv[iz] = srzv[iz] = 0.0;
+                    if (!is_last) M::sz(ie, ip, t, x, S.p, S.k, S.h, spl, sxc, szv);
+                    else M::srz(ie, ip, t, x, S.p, S.k, S.h, spl, sxc, srzv);
+                    M::dsigmazdp(ip, S.p, S.k, dsig);
+                    const size_t srow = (((size_t)n * nme + slot) * nplist + il) * M::NZ;
+                    AB_UNROLL
+                    for (int iz = 0; iz < M::NZ; ++iz) {
+                        if (M::z2event(iz) != ie) continue;
+                        if (full()) {
+                            if (b.sz) b.sz[srow + iz] = chain(szv[iz], pc);
+                            if (b.srz && is_last) b.srz[srow + iz] = chain(srzv[iz], pc);
+                        }
+                        if (mz_set[iz]) {
+                            // Model::add_event_objective_sensitivity (reference src/model.cpp:1411-1450, :2643-2760)
+                            const double s2 = sig[iz] * sig[iz], r_ = zv[iz] - mz[iz];
+                            const double dsp = sig_set[iz] ? 0.0 : dsig[iz];
+                            const double dJzds = 1.0 / sig[iz] - r_ * r_ / (s2 * sig[iz]);
+                            if (!is_last) {
+                                sllh[c] -= r_ / s2 * szv[iz] + dJzds * dsp;
+                            } else {
+                                const double dJrzds = 1.0 / sig[iz] - rzv[iz] * rzv[iz] / (s2 * sig[iz]);
+                                sllh[c] -= rzv[iz] / s2 * srzv[iz] + (dJrzds + dJzds) * dsp;
+                            }
+                        }
+                    }
+                }
+            }
+            nroots[ie]++;
+        }
+        // at the last timepoint fill_events repeats until every slot is used (reference include/amici/forwardproblem.h:352-360)
+        bool more = false;
+        AB_UNROLL
+        for (int ie = 0; ie < M::NE; ++ie) more = more || nroots[ie] < nme;
+        if (!(is_last && more)) break;
+        }
+    }
+
+    // store_pre_event_info + store_pre_event_state (reference src/forwardproblem.cpp:408-426, :576-613)
+    AB_HD void store_pre_event(double t, bool seflag, bool initial_event) {
+        auto& g = bdf.g;
+        double x[NX];
+        g.sync();
+        state_col(x);
+        eval_roots(t, x, rootvals);
+        AB_UNROLL
+        for (int ie = 0; ie < M::NE; ++ie) rval_tmp[ie] = rootvals[ie];
+        if (M::NZ > 0) store_event(t);
+        if (nplist > 0 || o.sensi >= 1) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) ev_x_old[r] = x[r];
+            eval_xdot(t, x, ev_xdot_old);
+        }
+        if (nplist > 0) {
+            if (!seflag && !initial_event) {
+                double spl[M::NSPL > 0 ? M::NSPL : 1];
+                spline_values_at<M, G, C>(S, t, spl);
+                AB_UNROLL
+                for (int ie = 0; ie < M::NE; ++ie) {
+                    if (roots_found[ie] != 1) continue;
+                    AB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        const int cc = bdf.col(c);
+                        stau[c] = 0.0;
+                        if (!bdf.active(c) || cc == 0) continue;
+                        double sxc[NX];
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r) sxc[r] = S.zn[0][r][cc];
+                        stau[c] = M::stau(ie, S.ip_of_col[cc], t, x, S.p, S.k, S.h, spl, sxc);
+                    }
+                }
+            }
+            if (initial_event) {
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) stau[c] = 0.0;
+            }
+        }
+    }
+
+    // EventHandlingSimulator::handle_events (reference src/forwardproblem.cpp:389-514). The solver state zn[0] holds
+    // x, sx at the event time t. Returns AB_SUCCESS or AB_ERROR ("stuck in an event").
+    AB_HD int handle_events(double t, bool initial_event) {
+        auto& g = bdf.g;
+        if (!initial_event && t == tlastroot) return AB_ERROR;
+        tlastroot = t;
+        store_pre_event(t, false, initial_event);
+        if (!initial_event) update_heaviside();
+        // pending events, first in first out (EventQueue with undefined priorities, reference include/amici/event.h:136-215)
+        unsigned long long queue = 0ull;
+        int qn = 0;
+        AB_UNROLL
+        for (int ie = 0; ie < M::NE; ++ie)
+            if (roots_found[ie] == 1 && qn < 16) queue |= (unsigned long long)ie << (4 * qn++);
+        while (qn > 0) {
+            const int ie = (int)(queue & 15ull);
+            queue >>= 4;
+            qn--;
+            double x[NX], dx[NX], f[NX];
+            g.sync();
+            state_col(x);
+            // Model::add_state_event_update (reference src/model.cpp:1481-1503)
+            M::deltax(ie, t, x, S.p, S.k, S.h, x, dx);
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) x[r] += dx[r];
+            g.sync();
+            if (g.lane == 0) {
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) S.zn[0][r][0] = x[r];
+            }
+            g.sync();
+            if (nplist > 0) {
+                // Model::add_state_sensitivity_event_update (reference src/model.cpp:1505-1534)
+                eval_xdot(t, x, f);
+                double spl[M::NSPL > 0 ? M::NSPL : 1];
+                spline_values_at<M, G, C>(S, t, spl);
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    const int cc = bdf.col(c);
+                    if (!bdf.active(c) || cc == 0) continue;
+                    double sxc[NX], dsx[NX];
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) sxc[r] = S.zn[0][r][cc];
+                    M::deltasx(ie, S.ip_of_col[cc], t, x, S.p, S.k, S.h, spl, f, ev_xdot_old, sxc, stau[c], ev_x_old, dsx);
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) S.zn[0][r][cc] = sxc[r] + dsx[r];
+                }
+            }
+            // detect_secondary_events (reference src/forwardproblem.cpp:615-665)
+            eval_roots(t, x, rootvals);
+            int secondevent = 0;
+            AB_UNROLL
+            for (int ie2 = 0; ie2 < M::NE; ++ie2) {
+                if (roots_found[ie2] == 0) {
+                    const bool h_a = !(rval_tmp[ie2] < 0.0), h_b = !(rootvals[ie2] < 0.0);   // heaviside_differs
+                    if (h_a != h_b) {
+                        if (rval_tmp[ie2] < rootvals[ie2]) {
+                            roots_found[ie2] = 1;
+                            if (qn < 16) queue |= (unsigned long long)ie2 << (4 * qn++);
+                        } else {
+                            roots_found[ie2] = -1;
+                        }
+                        secondevent++;
+                    }
+                } else {
+                    roots_found[ie2] = 0;
+                }
+            }
+            if (secondevent > 0) {
+                store_pre_event(t, true, initial_event);
+                update_heaviside();
+            }
+        }
+        // Solver::reinit + sens_reinit
+        bdf.amici_reinit(t);
+        return AB_SUCCESS;
+    }
+
     // SteadyStateProblem::run for pre-equilibration (reference src/forwardproblem.cpp:812-870, :1107-1206), part 1:
     // Newton's method (stage 0 or 2). Returns true if the steady state was found.
     AB_HD bool preeq_newton(int stage, int (&pe_status)[3], int (&pe_steps)[3], double& pe_wrms) {
@@ -348,8 +640,22 @@ struct Simulation {
             }
         }
         if (phase == 0) {
+            if (M::NE > 0) {
+                // Model::initialize_events, then EventHandlingSimulator::handle_initial_events (src/forwardproblem.cpp:516-522)
+                initialize_events(o.t0);
+                bool any = false;
+                AB_UNROLL
+                for (int ie = 0; ie < M::NE; ++ie) any = any || roots_found[ie] == 1;
+                if (any) handle_events(o.t0, true);
+            }
             write_initial_state();
             bdf.init(o.t0);
+            if (M::NE > 0) {   // root information at t0 (src/forwardproblem.cpp:66-67)
+                double x[NX];
+                g.sync();
+                state_col(x);
+                eval_roots(o.t0, x, rootvals);
+            }
         }
         // ---- condition driver: the one call site of the integrator serves both phases ----
         for (;;) {
@@ -412,6 +718,7 @@ struct Simulation {
                     phase = 0;
                 }
             }
+            double next_t_event = INFINITY;
             if (!PREEQ || phase == 0) {
                 if (it >= nt) break;
                 tout = b.ts[it];
@@ -419,6 +726,10 @@ struct Simulation {
                     datapoint(it);
                     ++it;
                     continue;
+                }
+                if (M::NE > M::NE_SOLVER) {   // next stop: output time or time-triggered event (src/forwardproblem.cpp:100-106)
+                    next_t_event = next_trigger(b.ts[nt - 1]);
+                    tout = ab_min(tout, next_t_event);
                 }
             }
             const int flag = bdf.solve_to(tout, one_step);
@@ -438,6 +749,33 @@ struct Simulation {
                     AB_UNROLL
                     for (int r = 0; r < NX; ++r) S.xfin[r] = S.zn[0][r][0];
                 }
+                if (M::NE > 0 && (flag == AB_ROOT_RETURN || t == next_t_event)) {
+                    // solver-tracked or time-triggered event (src/forwardproblem.cpp:116-134)
+                    AB_UNROLL
+                    for (int ie = 0; ie < M::NE_SOLVER; ++ie) roots_found[ie] = bdf.iroots[ie];
+                    if (t == next_t_event) {
+                        AB_UNROLL
+                        for (int ie = M::NE_SOLVER; ie < M::NE; ++ie)
+                            if (M::explicit_time(ie, S.p, S.k) == t) roots_found[ie] = rootvals[ie] > 0.0 ? -1 : 1;   // copysign(1, -rootvals)
+                        t_trig_done = t;
+                    }
+                    const int rc = handle_events(t, false);
+                    if (rc != AB_SUCCESS) {
+                        status = rc;
+                        break;
+                    }
+                }
+            }
+        }
+        // fill unused event-observable slots at the final timepoint (src/forwardproblem.cpp:144-148)
+        if (M::NZ > 0 && nt > 0 && status == AB_SUCCESS && !(PREEQ && preeq_failed)) {
+            bool more = false;
+            AB_UNROLL
+            for (int ie = 0; ie < M::NE; ++ie) more = more || nroots[ie] < o.nmaxevent;
+            if (more) {
+                AB_UNROLL
+                for (int ie = 0; ie < M::NE; ++ie) roots_found[ie] = 0;
+                store_event(t);
             }
         }
         if (PREEQ && preeq_failed) {

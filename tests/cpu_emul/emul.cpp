@@ -7,6 +7,8 @@
 #include "../../amici_b200/csrc/models/jakstat_adjoint.cuh"
 #include "../../amici_b200/csrc/models/robertson_ode.cuh"
 #include "../../amici_b200/csrc/models/steadystate.cuh"
+#include "../../amici_b200/csrc/models/events.cuh"
+#include "../../amici_b200/csrc/models/neuron.cuh"
 
 #include <memory>
 #include <string>
@@ -31,5 +33,7 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "jakstat_adjoint") return run_model<models::jakstat_adjoint>(o, b);
     if (m == "steadystate") return run_model<models::steadystate>(o, b);
     if (m == "robertson_ode") return run_model<models::robertson_ode>(o, b);
+    if (m == "events") return run_model<models::events>(o, b);
+    if (m == "neuron") return run_model<models::neuron>(o, b);
     return -2;
 }

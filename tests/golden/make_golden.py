@@ -18,9 +18,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FIELDS = ["status", "llh", "chi2", "sllh", "x", "sx", "y", "sy", "sigmay", "ssigmay", "res", "sres", "FIM", "x0",
           "sx0", "xdot", "J", "numsteps"]
 PREEQ_FIELDS = ["x_ss", "sx_ss", "preeq_status", "preeq_numsteps", "preeq_wrms", "preeq_t"]
+EVENT_FIELDS = ["z", "sz", "rz", "srz", "sigmaz"]
 
 
-def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, **run_kw):
+def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=None, **run_kw):
     m = RefModel(model)
     d = m.dims
     rng = np.random.default_rng(seed)
@@ -29,14 +30,17 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, **run_kw
     k = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.8, 1.25, (N, d.nk))
     k[0] = m.k_nominal
     k_preeq = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.5, 2.0, (N, d.nk)) if preeq else None
-    fields = FIELDS + (PREEQ_FIELDS if preeq else [])
+    fields = FIELDS + (PREEQ_FIELDS if preeq else []) + (EVENT_FIELDS if d.nz > 0 else [])
+    if kscale is not None:
+        k = np.tile(m.k_nominal, (N, 1)) * rng.uniform(kscale[0], kscale[1], (N, d.nk))
+        k[0] = m.k_nominal
     y0 = m.run(ts, p, k, sensi_order=0, fields=["y"], k_preeq=k_preeq, **run_kw)["y"]
     my = y0 + 0.1 * rng.standard_normal(y0.shape)
     my[1, 2, :] = np.nan          # missing measurements
     my[2, :, 0] = np.nan
     sig = np.full_like(my, 0.1)
     sig[1] = np.nan               # model sigma for condition 1
-    sig[3, 4:, 1] = np.nan
+    sig[3, 4:, min(1, d.ny - 1)] = np.nan
     pin = p.copy()
     if pscale is not None:
         pin = np.where(np.asarray(pscale) == 2, np.log10(p), np.where(np.asarray(pscale) == 1, np.log(p), p))
@@ -49,8 +53,8 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, **run_kw
             out[f"{name}_{f}"] = r[f]
     if preeq:
         out["k_preeq"] = k_preeq
-        for k_, v in run_kw.items():
-            out["opt_" + k_] = np.asarray(v)
+    for k_, v in run_kw.items():
+        out["opt_" + k_] = np.asarray(v)
     path = os.path.join(HERE, f"{model}{tag}.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
@@ -66,5 +70,8 @@ if __name__ == "__main__":
          ss_mode=2, ss_sensi_mode=0)
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=15, tag="_preeq_sim", preeq=True, newton_maxsteps=0,
          ss_mode=2, ss_sensi_mode=2)
+    # BASELINE config 4: Heaviside switches, root finding, event observables (z, sz, rz, srz), state resets
+    make("events", np.linspace(0, 10, 21), N=6, seed=17, kscale=(1.0, 1.0), nmaxevent=2)
+    make("neuron", np.linspace(0, 100, 21), N=6, seed=18, kscale=(1.0, 1.0), nmaxevent=10)
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=16, tag="_preeq_newton2", preeq=True, newton_maxsteps=2,
          ss_mode=2, ss_sensi_mode=0)

@@ -11,7 +11,8 @@ from tests import parity
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-MODEL_DIMS = {"jakstat_adjoint": dict(nx=9, np=17, nk=2, ny=3), "steadystate": dict(nx=3, np=5, nk=4, ny=3)}
+MODEL_DIMS = {"jakstat_adjoint": dict(nx=9, np=17, nk=2, ny=3), "steadystate": dict(nx=3, np=5, nk=4, ny=3),
+              "events": dict(nx=3, np=4, nk=4, ny=1, nz=2), "neuron": dict(nx=2, np=4, nk=2, ny=1, nz=1)}
 
 
 def _emul(built):
@@ -20,9 +21,10 @@ def _emul(built):
 
 def run_emul(lib, model, g, sensi=1, **opt):
     dims = MODEL_DIMS[model]
-    b, out, keep = _capi.make_batch(dims, g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
-                                    k_preeq=g["k_preeq"] if "k_preeq" in g else None)
     opt = {**{k_[4:]: int(g[k_]) for k_ in g.keys() if k_.startswith("opt_")}, **opt}
+    b, out, keep = _capi.make_batch(dims, g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
+                                    k_preeq=g["k_preeq"] if "k_preeq" in g else None, nmaxevent=opt.get("nmaxevent", 10),
+                                    mz=g["mz"] if "mz" in g else None)
     o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=sensi, **opt)
     assert lib.emul_run(model.encode(), C.byref(o), C.byref(b)) == 0
     return out
@@ -51,6 +53,52 @@ def test_emulation_preequilibration_matches_golden(built, fixture):
     sim = g["klu_preeq_numsteps"][:, 1]
     assert (np.abs(out["preeq_numsteps"][:, 1] - sim) <= 0.15 * sim + 2).all()
     np.testing.assert_array_equal(np.isnan(out["preeq_t"]), np.isnan(g["klu_preeq_t"]))
+
+
+@pytest.mark.parametrize("model", ["events", "neuron"])
+def test_emulation_events_match_golden(built, model):
+    """Heaviside switches, root finding and state resets (BASELINE config 4): event observables z/sz/rz/srz, the number
+    of recorded events per root and everything downstream agree with the compiled reference."""
+    g = np.load(os.path.join(GOLD, model + ".npz"))
+    out = run_emul(_emul(built), model, g)
+    parity.check_against_golden(out, g)
+    # identical event counts: slots filled at the final timepoint carry a non-zero regularisation rz, real events do not
+    np.testing.assert_array_equal(out["rz"] != 0, g["klu_rz"] != 0)
+    np.testing.assert_array_equal(out["z"] < g["ts"][-1], g["klu_z"] < g["ts"][-1])
+    np.testing.assert_allclose(out["z"], g["klu_z"], rtol=1e-6, atol=1e-9)
+    assert abs(out["numsteps"][:, -1] / g["klu_numsteps"][:, -1] - 1).max() < 0.05
+
+
+def test_events_without_sensitivities_and_known_event_times(built):
+    """Closed-form check in the spirit of the reference's python/tests/test_events.py: in the events model x3 relaxes
+    from k3 = 10 to 0 as 10*exp(-t) until t = 4, and x1 is constant until t = p4, so event 2 (x1 > x3) fires at
+    t = log(k3/k1)."""
+    g = dict(np.load(os.path.join(GOLD, "events.npz")))
+    g["p"] = g["p"].copy()
+    g["p"][:, 3] = 2.0   # p4 > log(10/4): x1 still constant when it crosses x3
+    out = run_emul(_emul(built), "events", g, sensi=0)
+    assert (out["status"] == 0).all()
+    np.testing.assert_allclose(out["z"][:, 0, 1], np.log(10.0 / 4.0), rtol=2e-6)
+    np.testing.assert_allclose(out["x"][:, 4, 2], 10.0 * np.exp(-g["ts"][4]), rtol=1e-6)
+
+
+def test_event_measurements_enter_the_objective(built):
+    """mz / sigma_z: llh and sllh contributions of the event observables against the compiled reference."""
+    from oracle import refsim
+    if not refsim.available("neuron"):
+        pytest.skip("oracle/_ref not built")
+    g = dict(np.load(os.path.join(GOLD, "neuron.npz")))
+    N = g["p"].shape[0]
+    rng = np.random.default_rng(3)
+    mz = g["klu_z"] + 0.05 * rng.standard_normal(g["klu_z"].shape)
+    mz[:, 7:, :] = np.nan
+    g["mz"] = mz
+    g["my"] = np.full_like(g["my"], np.nan)
+    out = run_emul(_emul(built), "neuron", g)
+    r = refsim.RefModel("neuron").run(g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], mz=mz, nmaxevent=10)
+    np.testing.assert_array_equal(out["status"], r["status"])
+    np.testing.assert_allclose(out["llh"], r["llh"], rtol=1e-5)
+    np.testing.assert_allclose(out["sllh"], r["sllh"], rtol=2e-3, atol=1e-3)
 
 
 def test_preequilibration_failure_modes(built):

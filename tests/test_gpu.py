@@ -26,8 +26,10 @@ def _run(model_name, g, sensi=True, ts=None, **solver_kw):
         s.set_newton_max_steps(int(g["opt_newton_maxsteps"]))
         m.set_steady_state_computation_mode(int(g["opt_ss_mode"]))
         m.set_steady_state_sensitivity_mode(int(g["opt_ss_sensi_mode"]))
+    if "opt_nmaxevent" in g:
+        m.set_n_max_event(int(g["opt_nmaxevent"]))
     batch = ab.ExpDataBatch(m.get_timepoints(), g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
-                            k_preeq=g["k_preeq"] if "k_preeq" in g else None)
+                            k_preeq=g["k_preeq"] if "k_preeq" in g else None, mz=g["mz"] if "mz" in g else None)
     return ab.run_simulations(m, s, batch)
 
 
@@ -48,6 +50,89 @@ def test_cuda_preequilibration_matches_golden(fixture):
     np.testing.assert_array_equal(res["preeq_numsteps"][:, [0, 2]], g["klu_preeq_numsteps"][:, [0, 2]])
     sim = g["klu_preeq_numsteps"][:, 1]
     assert (np.abs(res["preeq_numsteps"][:, 1] - sim) <= 0.15 * sim + 2).all()
+
+
+@pytest.mark.parametrize("model", ["events", "neuron"])
+def test_cuda_events_match_golden(model):
+    """BASELINE config 4: Heaviside events and root finding with divergent per-condition step control, through the C ABI."""
+    g = np.load(os.path.join(GOLD, model + ".npz"))
+    res = _run(model, g)
+    parity.check_against_golden(res.fields, g)
+    np.testing.assert_array_equal(res["rz"] != 0, g["klu_rz"] != 0)
+    np.testing.assert_array_equal(res["z"] < g["ts"][-1], g["klu_z"] < g["ts"][-1])
+    np.testing.assert_allclose(res["z"], g["klu_z"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("model,N", [("events", 4096), ("neuron", 2048)])
+def test_cuda_events_large_batch_vs_reference(model, N):
+    """A seeded batch of parameter samples (p x 10^N(0, 0.1^2)): status codes and event counts per root
+    identical to the compiled reference on a random subset, event times to 1e-6; every condition of the batch succeeds."""
+    import amici_b200 as ab
+    from oracle import refsim
+    m = ab.get_model(model)
+    ts = np.linspace(0, 10, 21) if model == "events" else np.linspace(0, 100, 21)
+    nme = 2 if model == "events" else 10
+    m.set_timepoints(ts)
+    m.set_n_max_event(nme)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    rng = np.random.default_rng(4)
+    p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.normal(0, 0.1, (N, m.np()))
+    k = np.tile(m.get_fixed_parameters(), (N, 1))
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
+    assert (res["status"] == 0).all()
+    assert np.isfinite(res["sx"]).all() and np.isfinite(res["sz"]).all()
+    if not refsim.available(model):
+        return
+    idx = rng.choice(N, 64, replace=False)
+    ref = refsim.RefModel(model)
+    r = ref.run(ts, p[idx], k[idx], nmaxevent=nme, num_threads=min(ref.max_threads(), 16))
+    np.testing.assert_array_equal(res["status"][idx], r["status"])
+    np.testing.assert_array_equal(res["z"][idx] < ts[-1], r["z"] < ts[-1])
+    np.testing.assert_allclose(res["z"][idx], r["z"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(res["x"][idx], r["x"], rtol=1e-5, atol=1e-8)
+
+
+def test_cuda_preequilibration_large_batch_vs_reference():
+    """BASELINE config 3 inputs (k_preeq = k x U(0.5, 2), k x U(0.5, 2), p x 10^N(0, 0.1^2); Newton first, simulation if it
+    fails, sensitivities from the Newton solve): SteadyStateStatus triples and Newton step counts identical to the compiled
+    reference on a random subset, x_ss / sx_ss / llh / sllh within tolerance."""
+    import amici_b200 as ab
+    from oracle import refsim
+    N = 8192
+    m = ab.get_model("steadystate")
+    ts = np.linspace(0, 10, 11)
+    m.set_timepoints(ts)
+    m.set_steady_state_computation_mode(ab.SteadyStateComputationMode.integrateIfNewtonFails)
+    m.set_steady_state_sensitivity_mode(ab.SteadyStateSensitivityMode.newtonOnly)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    s.set_newton_max_steps(50)
+    rng = np.random.default_rng(3)
+    p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.normal(0, 0.1, (N, 5))
+    k = np.tile(m.get_fixed_parameters(), (N, 1)) * rng.uniform(0.5, 2, (N, 4))
+    kp = np.tile(m.get_fixed_parameters(), (N, 1)) * rng.uniform(0.5, 2, (N, 4))
+    my = rng.normal(0.5, 0.3, (N, 11, 3))
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k, my=my, sigmay=np.full_like(my, 0.1), k_preeq=kp))
+    assert (res["status"] == 0).all()
+    assert (res["preeq_status"][:, 0] == 1).mean() > 0.9   # Newton finds almost all steady states
+    if not refsim.available("steadystate"):
+        return
+    idx = rng.choice(N, 128, replace=False)
+    ref = refsim.RefModel("steadystate")
+    r = ref.run(ts, p[idx], k[idx], k_preeq=kp[idx], my=my[idx], sigmay=np.full_like(my[idx], 0.1), newton_maxsteps=50,
+                ss_mode=2, ss_sensi_mode=0, num_threads=min(ref.max_threads(), 16))
+    np.testing.assert_array_equal(res["status"][idx], r["status"])
+    np.testing.assert_array_equal(res["preeq_status"][idx], r["preeq_status"])
+    np.testing.assert_array_equal(res["preeq_numsteps"][idx][:, [0, 2]], r["preeq_numsteps"][:, [0, 2]])
+    np.testing.assert_allclose(res["x_ss"][idx], r["x_ss"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(res["sx_ss"][idx], r["sx_ss"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(res["llh"][idx], r["llh"], rtol=1e-6)
+    np.testing.assert_allclose(res["sllh"][idx], r["sllh"], rtol=1e-4, atol=1e-5)
 
 
 def test_cuda_preequilibration_failure():
