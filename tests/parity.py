@@ -53,3 +53,14 @@ def check_against_golden(cand: dict, gold, fields=None, factor=FACTOR, verbose=T
         assert e_truth <= max(1.0, factor * floor_truth), (f, report[f])
         assert e_klu <= max(1.0, factor * max(floor_pair, floor_truth)), (f, report[f])
     return report
+
+
+def robertson_view(g, sensi):
+    """tests/golden/robertson.npz holds a plain forward run (`*_nosens_*`) and a forward-sensitivity run; select one."""
+    v = {}
+    for name in ("klu", "dense", "truth"):
+        for f in ("status", "x", "y"):
+            v[f"{name}_{f}"] = g[f"{name}_{f}"] if sensi else g[f"{name}_nosens_{f}"]
+        if sensi:
+            v[f"{name}_sx"], v[f"{name}_sy"] = g[f"{name}_sx"], g[f"{name}_sy"]
+    return v

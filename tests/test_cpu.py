@@ -11,7 +11,7 @@ from tests import parity
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-MODEL_DIMS = {"jakstat_adjoint": dict(nx=9, np=17, nk=2, ny=3), "steadystate": dict(nx=3, np=5, nk=4, ny=3),
+MODEL_DIMS = {"robertson_ode": dict(nx=3, np=3, nk=1, ny=3), "jakstat_adjoint": dict(nx=9, np=17, nk=2, ny=3), "steadystate": dict(nx=3, np=5, nk=4, ny=3),
               "events": dict(nx=3, np=4, nk=4, ny=1, nz=2), "neuron": dict(nx=2, np=4, nk=2, ny=1, nz=1)}
 
 
@@ -39,6 +39,18 @@ def test_emulation_matches_golden(built, fixture, model):
     parity.check_against_golden(out, g)
     # step counts are not expected to be equal (chaotic), but must be of the same size
     assert abs(out["numsteps"][:, -1] / g["klu_numsteps"][:, -1] - 1).max() < 0.15
+
+
+@pytest.mark.parametrize("sensi", [0, 1])
+def test_emulation_robertson_matches_reference_dae(built, sensi):
+    """BASELINE config 1: Robertson in ODE form through the CVODES-equivalent BDF against the shipped DAE model run by the
+    reference through IDAS (klu / dense / tight-tolerance truth), on the reference's own time grid 0, 4e-6 .. 4e6."""
+    g = np.load(os.path.join(GOLD, "robertson.npz"))
+    b, out, keep = _capi.make_batch(MODEL_DIMS["robertson_ode"], g["ts"], g["p"], g["k"])
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=sensi)
+    assert _emul(built).emul_run(b"robertson_ode", C.byref(o), C.byref(b)) == 0
+    parity.check_against_golden(out, parity.robertson_view(g, sensi), fields=["x", "y"] + (["sx", "sy"] if sensi else []))
+    np.testing.assert_allclose(out["x"].sum(-1), 1.0, rtol=0, atol=1e-9)   # mass conservation (the DAE's algebraic equation)
 
 
 @pytest.mark.parametrize("fixture", ["steadystate_preeq_newton", "steadystate_preeq_sim", "steadystate_preeq_newton2"])

@@ -41,6 +41,50 @@ def test_cuda_matches_golden(fixture, model):
     parity.check_against_golden(res.fields, g)
 
 
+@pytest.mark.parametrize("sensi", [False, True])
+def test_cuda_robertson_matches_reference_dae(sensi):
+    """BASELINE config 1 (small): Robertson, ODE form, against the reference's shipped DAE model run through IDAS."""
+    g = np.load(os.path.join(GOLD, "robertson.npz"))
+    gg = dict(ts=g["ts"], p=g["p"], k=g["k"], my=None, sigmay_in=None, pscale=g["pscale"])
+    res = _run("robertson_ode", gg, sensi=sensi)
+    parity.check_against_golden(res.fields, parity.robertson_view(g, sensi), fields=["x", "y"] + (["sx", "sy"] if sensi else []))
+
+
+def test_cuda_robertson_4096_log_uniform_draws():
+    """BASELINE config 1 at full size: 4096 log-uniform parameter draws (p = nominal x 10^U(-1,1), seed 1), forward
+    simulation, rtol 1e-8 / atol 1e-12, on the grid 0, 4e-6 .. 4e6.  Size-independent properties: every draw succeeds, mass
+    is conserved (x1 + x2 + x3 = 1, the algebraic equation of the reference's DAE form), x1 decays monotonically;
+    a random subset is compared with the reference's IDAS run on the host cores."""
+    import amici_b200 as ab
+    from oracle import refsim
+    m = ab.get_model("robertson_ode")
+    ts = np.concatenate([[0.0], 4 * np.logspace(-6, 6, 50)])
+    m.set_timepoints(ts)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    N = 4096
+    rng = np.random.default_rng(1)
+    p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.uniform(-1, 1, (N, 3))
+    k = np.full((N, 1), 0.9)
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
+    assert (res["status"] == 0).all()
+    np.testing.assert_allclose(res["x"].sum(-1), 1.0, rtol=0, atol=1e-9)
+    assert (np.diff(res["x"][:, :, 0], axis=1) <= 1e-12).all()
+    np.testing.assert_allclose(res["y"][:, :, 1], 1e4 * res["x"][:, :, 1], rtol=1e-15)
+    if not refsim.available("robertson"):
+        return
+    idx = rng.choice(N, 64, replace=False)
+    ref = refsim.RefModel("robertson")
+    nthr = min(ref.max_threads(), 16)
+    r = ref.run(ts, p[idx], k[idx], sensi_order=0, num_threads=nthr, fields=["status", "x"])
+    t = ref.run(ts, p[idx], k[idx], sensi_order=0, num_threads=nthr, fields=["status", "x"], rtol=1e-12, atol=1e-16, maxsteps=500000)
+    np.testing.assert_array_equal(res["status"][idx], r["status"])
+    ref_err = parity.scaled_err(r["x"], t["x"], t["x"])
+    our_err = parity.scaled_err(res["x"][idx], t["x"], t["x"])
+    assert our_err <= max(1.0, parity.FACTOR * ref_err), (our_err, ref_err)
+
+
 @pytest.mark.parametrize("fixture", ["steadystate_preeq_newton", "steadystate_preeq_sim", "steadystate_preeq_newton2"])
 def test_cuda_preequilibration_matches_golden(fixture):
     """BASELINE config 3: batched Newton steady state + sensitivities, simulation fallback, through the C ABI."""
@@ -66,7 +110,7 @@ def test_cuda_events_match_golden(model):
 @pytest.mark.parametrize("model,N", [("events", 4096), ("neuron", 2048)])
 def test_cuda_events_large_batch_vs_reference(model, N):
     """A seeded batch of parameter samples (p x 10^N(0, 0.1^2)): status codes and event counts per root
-    identical to the compiled reference on a random subset, event times to 1e-6; every condition of the batch succeeds."""
+    identical to the compiled reference on a random subset plus every failing condition, event times to 1e-6."""
     import amici_b200 as ab
     from oracle import refsim
     m = ab.get_model(model)
@@ -82,17 +126,25 @@ def test_cuda_events_large_batch_vs_reference(model, N):
     p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.normal(0, 0.1, (N, m.np()))
     k = np.tile(m.get_fixed_parameters(), (N, 1))
     res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
-    assert (res["status"] == 0).all()
-    assert np.isfinite(res["sx"]).all() and np.isfinite(res["sz"]).all()
+    ok = res["status"] == 0
+    # neuron: ~5 % of these draws spike so often that the default maxsteps (10000) runs out -- in the reference too
+    assert ok.mean() > 0.9
+    assert np.isfinite(res["sx"][ok]).all() and np.isfinite(res["sz"][ok]).all()
     if not refsim.available(model):
         return
-    idx = rng.choice(N, 64, replace=False)
+    idx = np.union1d(rng.choice(N, 64, replace=False), np.nonzero(~ok)[0][:64])
     ref = refsim.RefModel(model)
     r = ref.run(ts, p[idx], k[idx], nmaxevent=nme, num_threads=min(ref.max_threads(), 16))
-    np.testing.assert_array_equal(res["status"][idx], r["status"])
-    np.testing.assert_array_equal(res["z"][idx] < ts[-1], r["z"] < ts[-1])
-    np.testing.assert_allclose(res["z"][idx], r["z"], rtol=1e-6, atol=1e-8)
-    np.testing.assert_allclose(res["x"][idx], r["x"], rtol=1e-5, atol=1e-8)
+    # same conditions fail; a failing one runs out of steps either inside CVode (-1) or on AMICI's own check (-99),
+    # which of the two depends on where the 10000th step lands (the step counts agree to ~1e-3, not exactly)
+    np.testing.assert_array_equal(res["status"][idx] == 0, r["status"] == 0)
+    both = np.stack([res["status"][idx], r["status"]])
+    assert np.isin(both, (0, -1, -99)).all()
+    good = r["status"] == 0
+    np.testing.assert_array_equal(res["status"][idx][good], r["status"][good])
+    np.testing.assert_array_equal(res["z"][idx][good] < ts[-1], r["z"][good] < ts[-1])
+    np.testing.assert_allclose(res["z"][idx][good], r["z"][good], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(res["x"][idx][good], r["x"][good], rtol=1e-5, atol=1e-8)
 
 
 def test_cuda_preequilibration_large_batch_vs_reference():
