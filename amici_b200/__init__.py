@@ -106,10 +106,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        raise RuntimeError(f"{_LIB_PATH} is missing: build the CUDA engine first (__graft_entry__.build()); "
+    path = os.environ.get("AMICI_B200_LIB", _LIB_PATH)   # override: experimental builds (tools/build_variant.py)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build the CUDA engine first (__graft_entry__.build()); "
                            "amici_b200 has no CPU fallback")
-    lib = C.CDLL(_LIB_PATH)
+    lib = C.CDLL(path)
     lib.ab_model_count.restype = C.c_int
     lib.ab_model_name.restype = C.c_char_p
     lib.ab_model_name.argtypes = [C.c_int]

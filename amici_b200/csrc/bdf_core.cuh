@@ -557,7 +557,60 @@ struct Bdf {
     int irfnd, nge;
     bool reinit_pending;   // AMICI's CVodeSolver::reinit happened: the next call starts with reInit_post_process
 
+    // Step alignment of the warps of one block (G == 32 only): see step_sync_* below.
+    volatile int* sync_pos = nullptr;
+    int sync_n = 0, sync_w = 0, sync_gen = 0;
+
     AB_HD Bdf(Shared& s, const SolverOptions& opt, int ncols_) : S(s), o(opt), ncols(ncols_) {}
+
+    // -----------------------------------------------------------------------------------------
+    // Step alignment.  The per-step code is larger than the SM's instruction cache; warps that run it at unrelated
+    // phases evict each other's lines (profiles/r01_v1_ncu_summary.md: stall_no_instruction is the top stall).  The
+    // warps of a block that are inside the step loop therefore start every step together: a generation barrier in
+    // shared memory with dynamic membership (a warp leaves while it writes outputs or loads the next condition, and
+    // re-joins at the generation of the slowest member).  sync_pos[v] = generation warp v has arrived at, INT_MAX =
+    // not a member.  The member with the smallest generation never waits, so the scheme cannot deadlock.
+    // -----------------------------------------------------------------------------------------
+    AB_HD void step_sync_join() {
+#if defined(__CUDA_ARCH__)
+        if (G == 32 && sync_pos) {
+            int m = 0x7fffffff;
+            for (int v = 0; v < sync_n; ++v) {
+                const int pv = sync_pos[v];
+                if (v != sync_w && pv < m) m = pv;
+            }
+            if (m != 0x7fffffff) sync_gen = m;
+            if (g.lane == 0) sync_pos[sync_w] = sync_gen;
+            __syncwarp();
+        }
+#endif
+    }
+    AB_HD void step_sync_leave() {
+#if defined(__CUDA_ARCH__)
+        if (G == 32 && sync_pos) {
+            if (g.lane == 0) sync_pos[sync_w] = 0x7fffffff;
+            __syncwarp();
+        }
+#endif
+    }
+    AB_HD void step_sync_arrive() {
+#if defined(__CUDA_ARCH__)
+        if (G == 32 && sync_pos) {
+            ++sync_gen;
+            if (g.lane == 0) sync_pos[sync_w] = sync_gen;
+            __syncwarp();
+            for (;;) {
+                int m = 0x7fffffff;
+                for (int v = 0; v < sync_n; ++v) {
+                    const int pv = sync_pos[v];
+                    if (pv < m) m = pv;
+                }
+                if (m >= sync_gen) break;
+                __nanosleep(40);
+            }
+        }
+#endif
+    }
 
     AB_HD int col(int c) const { return g.lane + G * c; }
     AB_HD bool active(int c) const { return col(c) < ncols; }
@@ -1552,13 +1605,15 @@ struct Bdf {
             }
         }
         int nstloc = 0;
+        step_sync_join();
         for (;;) {
+            step_sync_arrive();
             if (nst > 0) set_ewt();
-            if (nstloc >= mxstep) { tretlast = tn; return AB_TOO_MUCH_WORK; }
+            if (nstloc >= mxstep) { tretlast = tn; { step_sync_leave(); return AB_TOO_MUCH_WORK; } }
             const double nrm = wrms_max_zn(0);
-            if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; return AB_TOO_MUCH_ACC; }
+            if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; { step_sync_leave(); return AB_TOO_MUCH_ACC; } }
             const int kflag = step();
-            if (kflag != AB_SUCCESS) { tretlast = tn; return kflag; }
+            if (kflag != AB_SUCCESS) { tretlast = tn; { step_sync_leave(); return kflag; } }
             nstloc++;
             double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
             const bool at_tstop = tstopset && fabs(tn - tstop) <= troundoff;
@@ -1568,9 +1623,9 @@ struct Bdf {
                     irfnd = 1;
                     tretlast = tlo;
                     // a root right after re-initialisation is an error in the reference (src/solver_cvodes.cpp:531-540)
-                    if (post) { nst = nst_saved + 1; return AB_ERROR; }
+                    if (post) { nst = nst_saved + 1; { step_sync_leave(); return AB_ERROR; } }
                     collapse_to(tlo);
-                    return AB_ROOT_RETURN;
+                    { step_sync_leave(); return AB_ROOT_RETURN; }
                 }
             }
             if ((ROOTS || M::NE > 0) && post) {
@@ -1579,23 +1634,23 @@ struct Bdf {
                 post = false;
                 nstloc = 0;
                 tretlast = tn;
-                if (at_tstop) return AB_ERROR;
+                if (at_tstop) { step_sync_leave(); return AB_ERROR; }
                 if ((tn + hprime - tstop) * h > 0.0) {
                     hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
                     eta = hprime / h;
                 }
                 if (ROOTS) {
                     const int rc = rcheck2();
-                    if (rc == 3) return AB_ILL_INPUT;
-                    if (rc == 1) { tretlast = tlo; collapse_to(tlo); return AB_ROOT_RETURN; }
+                    if (rc == 3) { step_sync_leave(); return AB_ILL_INPUT; }
+                    if (rc == 1) { tretlast = tlo; collapse_to(tlo); { step_sync_leave(); return AB_ROOT_RETURN; } }
                 }
                 continue;
             }
-            if (one_step) { tretlast = tn; return AB_SUCCESS; }
+            if (one_step) { tretlast = tn; { step_sync_leave(); return AB_SUCCESS; } }
             if (at_tstop) {
                 tretlast = tstop;
                 tstopset = false;
-                return AB_TSTOP_RETURN;
+                { step_sync_leave(); return AB_TSTOP_RETURN; }
             } else if ((tn + hprime - tstop) * h > 0.0) {
                 hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
                 eta = hprime / h;

@@ -12,23 +12,43 @@
 #ifndef AB_MINBLOCKS
 #define AB_MINBLOCKS 4
 #endif
+#ifndef AB_STEP_SYNC
+#define AB_STEP_SYNC 1
+#endif
+#ifndef AB_THREADS_G32
+#define AB_THREADS_G32 256
+#endif
 
 namespace amici_b200 {
+
+constexpr int SYNC_BYTES = 128;
 
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head) {
     using Sim = Simulation<M, G, C, PREEQ>;
     using Shared = typename Sim::Shared;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Shared* slices = reinterpret_cast<Shared*>(smem_raw);
+    // [0, SYNC_BYTES): step-alignment generations of the block's warps (Bdf::step_sync_*), then one slice per group
+    int* sync_pos = reinterpret_cast<int*>(smem_raw);
+    Shared* slices = reinterpret_cast<Shared*>(smem_raw + SYNC_BYTES);
     Shared& S = slices[threadIdx.x / G];
     Group<G> g;
+    constexpr bool STEP_SYNC = AB_STEP_SYNC && G == 32 && THREADS > 32;
+    if (STEP_SYNC) {
+        if (threadIdx.x < THREADS / 32) sync_pos[threadIdx.x] = 0x7fffffff;
+        __syncthreads();
+    }
     for (;;) {
         int n = 0;
         if (g.lane == 0) n = atomicAdd(queue_head, 1);
         n = g.bcast(n, 0);
         if (n >= b.N) break;
         Sim sim(S, o, b, n);
+        if (STEP_SYNC) {
+            sim.bdf.sync_pos = sync_pos;
+            sim.bdf.sync_n = THREADS / 32;
+            sim.bdf.sync_w = threadIdx.x / 32;
+        }
         sim.run();
         g.sync();
     }
@@ -44,8 +64,10 @@ struct Config {
     static constexpr int COLS = M::NP + 1;
     static constexpr int G = pow2_at_least(COLS);
     static constexpr int C = (COLS + G - 1) / G;
-    static constexpr int THREADS = 64;  // small blocks: shared-memory granularity decides occupancy
-    static constexpr int MINBLOCKS = AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
+    // One warp per condition (G == 32): all resident warps of an SM in ONE block, so that they can align their steps
+    // (Bdf::step_sync_*).  Otherwise small blocks: shared-memory granularity decides occupancy.
+    static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : 64;
+    static constexpr int MINBLOCKS = (G == 32) ? (AB_MINBLOCKS * 64) / AB_THREADS_G32 : AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
 };
 
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
@@ -53,7 +75,7 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
     using Sim = Simulation<M, G, C, PREEQ>;
     auto kern = bdf_solve_kernel<M, G, C, THREADS, MINBLOCKS, PREEQ>;
     constexpr int groups = THREADS / G;
-    const size_t smem = sizeof(typename Sim::Shared) * groups;
+    const size_t smem = SYNC_BYTES + sizeof(typename Sim::Shared) * groups;
     int dev = 0, sms = 0;
     AB_CUDA(cudaGetDevice(&dev));
     AB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
