@@ -135,15 +135,63 @@ def _c(e) -> str:
 
 
 class _FnWriter:
-    """Writes one function body: CSE over all outputs, then assignments."""
+    """Writes one function body: CSE over all outputs, then assignments.
 
-    def __init__(self, subs: dict):
+    ``hoist=True`` (used for the functions of the integrator's inner loop: xdot, jac, dxdotdp) moves every maximal
+    sub-expression that depends on parameters only out of the function: it becomes a *derived constant*, evaluated
+    once per condition by the generated ``derived()`` and stored behind the fixed parameters (``k[NK + i]``).
+    The reference's generated code re-evaluates such terms (e.g. the compartment-volume quotients of JAK-STAT,
+    an FP64 division each) in every right-hand-side call.
+    """
+
+    def __init__(self, subs: dict, const_syms=(), nk: int = 0):
         self.subs = subs  # symbol -> C lvalue text
+        self.const_syms = set(const_syms)   # parameters + fixed parameters
+        self.nk = nk
+        self.derived: list[sp.Expr] = []    # derived constant i lives in k[nk + i]
 
-    def body(self, assigns: list[tuple[str, sp.Expr]], indent="        ") -> str:
+    def _derived_symbol(self, e):
+        for i, d in enumerate(self.derived):
+            if d == e:
+                return sp.Symbol(f"k[{self.nk + i}]")
+        self.derived.append(e)
+        return sp.Symbol(f"k[{self.nk + len(self.derived) - 1}]")
+
+    def _is_const(self, e):
+        return bool(e.free_symbols) and e.free_symbols <= self.const_syms
+
+    def _worth(self, e):
+        # a bare symbol or its negation costs nothing at the point of use
+        if e.is_Atom:
+            return False
+        if e.is_Mul and len(e.args) == 2 and e.args[0] == -1 and e.args[1].is_Atom:
+            return False
+        return True
+
+    def _hoist(self, e):
+        e = sp.sympify(e)
+        if e.is_Atom:
+            return e
+        if self._is_const(e):
+            return self._derived_symbol(e) if self._worth(e) else e
+        if e.is_Mul or e.is_Add:
+            cargs = [a for a in e.args if self._is_const(a)]
+            nums = [a for a in e.args if a.is_Number]
+            rest = [self._hoist(a) for a in e.args if not self._is_const(a) and not a.is_Number]
+            if cargs:
+                c = e.func(*(cargs + (nums if e.is_Mul else [])))
+                head = self._derived_symbol(c) if self._worth(c) else c
+                tail = [] if e.is_Mul else nums
+                return e.func(head, *tail, *rest)
+            return e.func(*nums, *rest)
+        return e.func(*[self._hoist(a) for a in e.args])
+
+    def body(self, assigns: list[tuple[str, sp.Expr]], indent="        ", hoist: bool = False) -> str:
         if not assigns:
             return ""
         exprs = [sp.sympify(e) for _, e in assigns]
+        if hoist:
+            exprs = [self._hoist(sp.expand_mul(e) if False else e) for e in exprs]
         repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("c_"), optimizations="basic")
         lines = []
         for s, e in repl:
@@ -161,7 +209,15 @@ def _select_chain(ip_var: str, cases: list[tuple[int, str]]) -> str:
     """(ip==a)? ea : (ip==b)? eb : 0.0"""
     out = "0.0"
     for ip, txt in reversed(cases):
-        out = f"({ip_var} == {ip}) ? ({txt}) : {out}"
+        if isinstance(ip, (list, tuple)):   # several parameters share one value
+            ips = sorted(ip)
+            if len(ips) > 2 and ips == list(range(ips[0], ips[-1] + 1)):
+                cond = f"({ip_var} >= {ips[0]} && {ip_var} <= {ips[-1]})"
+            else:
+                cond = "(" + " || ".join(f"{ip_var} == {i}" for i in ips) + ")"
+        else:
+            cond = f"({ip_var} == {ip})"
+        out = f"{cond} ? ({txt}) : {out}"
     return out
 
 
@@ -197,7 +253,7 @@ def emit_model(spec: ModelSpec) -> str:
     sx_syms = [sp.Symbol(f"sx_{i}", real=True) for i in range(nx)]
     for i in range(nx):
         subs[sx_syms[i]] = sp.Symbol(f"sx[{i}]")
-    W = _FnWriter(subs)
+    W = _FnWriter(subs, const_syms=list(spec.params) + list(spec.fixed), nk=nk)
 
     xdot = [sp.sympify(e).xreplace(spl_map) for e in spec.xdot]
     x0 = [sp.sympify(e) for e in spec.x0]
@@ -264,14 +320,14 @@ def emit_model(spec: ModelSpec) -> str:
     # xdot
     A(f"    AB_HD static void xdot({sig_common}, double* xdot) {{")
     A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl;")
-    A(W.body([(f"xdot[{i}]", xdot[i]) for i in range(nx)]).rstrip("\n"))
+    A(W.body([(f"xdot[{i}]", xdot[i]) for i in range(nx)], hoist=True).rstrip("\n"))
     A("    }")
     # jac
     A(f"    // CSC pattern of J = d xdot / d x (cf. reference dxdotdx_explicit_{{colptrs,rowvals}})")
     A(f"    // colptr = {colptr}\n    // rowval = {rowval}")
     A(f"    AB_HD static void jac({sig_common}, double* J) {{")
     A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl;")
-    A(W.body([(f"J[{i}]", jvals[i]) for i in range(nnz)]).rstrip("\n"))
+    A(W.body([(f"J[{i}]", jvals[i]) for i in range(nnz)], hoist=True).rstrip("\n"))
     A("    }")
     A("    // out += J * s")
     A("    AB_HD static void jac_mul_add(const double* J, const double* s, double* out) {")
@@ -409,14 +465,23 @@ def emit_model(spec: ModelSpec) -> str:
     A("        (void)t; (void)x; (void)p; (void)k; (void)h; (void)spl; (void)sspl; (void)ip;")
     vals, rows = [], []
     for r in range(nx):
-        cases = []
+        groups: list[tuple[sp.Expr, list[int]]] = []   # parameters with identical derivative share one select
         for ip in range(npar):
             e = total_dp(xdot[r], ip)
-            if e != 0:
-                vals.append((f"const double v_{r}_{ip}", e))
-                cases.append((ip, f"v_{r}_{ip}"))
+            if e == 0:
+                continue
+            for ge, gi in groups:
+                if ge == e:
+                    gi.append(ip)
+                    break
+            else:
+                groups.append((e, [ip]))
+        cases = []
+        for e, ips in groups:
+            vals.append((f"const double v_{r}_{ips[0]}", e))
+            cases.append((ips if len(ips) > 1 else ips[0], f"v_{r}_{ips[0]}"))
         rows.append(cases)
-    A(W.body(vals).rstrip("\n"))
+    A(W.body(vals, hoist=True).rstrip("\n"))
     for r in range(nx):
         A(f"        out[{r}] = {_select_chain('ip', rows[r])};")
     A("    }")
@@ -683,6 +748,14 @@ def emit_model(spec: ModelSpec) -> str:
         A("    AB_HD static double spline_node(const int, const int) { return 0.0; }")
         A("    AB_HD static void spline_values(const int, const double*, const double*, double*) {}")
         A("    AB_HD static void spline_dvaluesdp(const int, const int, const double*, const double*, double*) {}")
+    # derived constants hoisted out of xdot / jac / dxdotdp (see _FnWriter): k[NK .. NK_EXT)
+    A(f"    static constexpr int NK_EXT = {nk + len(W.derived)};  // fixed parameters + derived constants")
+    A("    // k[NK + i] <- parameter-only sub-expressions of the right-hand side, evaluated once per condition")
+    A("    AB_HD static void derived(const double* p, double* k) {")
+    A("        (void)p; (void)k;")
+    for i, e in enumerate(W.derived):
+        A(f"        k[{nk + i}] = {W._pr(e)};")
+    A("    }")
     A("};\n")
     A("}}  // namespace amici_b200::models")
     A(f"#endif  // {guard}")

@@ -49,10 +49,11 @@ struct TrajShared {
     double xfin[M::NX];              // state at the last successful solver return (ReturnData::xdot/J are evaluated there)
     double scratch[NCOLS];
     double p[M::NP > 0 ? M::NP : 1];
-    double k[M::NK > 0 ? M::NK : 1];
+    double k[M::NK_EXT > 0 ? M::NK_EXT : 1];   // fixed parameters, then the model's derived constants (M::derived)
     double h[M::NH > 0 ? M::NH : 1];
     double pcoef[NCOLS];             // chain-rule factor per column
-    double ssdat[5][4];              // cvBDFStab history: ring buffer of (sqm2^2, sqm1^2, sq^2), newest at ss_head
+    double ssdat[5][8];              // cvBDFStab history: ring buffer of (sqm2^2, sqm1^2, sq^2) in [1..3] and their ratios to
+                                     // the next older entry in [5..7] (the rat[][] of cvSLdet, computed once), newest at ss_head
     int piv[M::NX];
     int ip_of_col[NCOLS];
     SplineTable<M, NCOLS> spl;
@@ -281,7 +282,7 @@ AB_COLD int cold_hin(typename Layout<M, G, C>::Shared& S, const SolverOptions& o
 // cvSLdet (cvodes.c:8256): stability-limit detection on the 5-deep history of scaled derivative norms.
 // s[i][k]: i = 1 (current) .. 5 (oldest), k = 1..3 (orders q-1, q, q+1).  All loops are unrolled with static
 // indices so that the work arrays live in registers; divisions whose divisor has been range-checked use fast_div.
-AB_HD int bdf_sldet(const double (&s)[6][4], const int q) {
+AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const int q) {
     const double TINY_ = 1e-10;
     double rav[4], qkr[4], sigsq[4], smax[4], ssmax[4], vrat[4], qc[6][4], qco[6][4];
     const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
@@ -306,7 +307,7 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const int q) {
         double sumrat = 0.0, sumrsq = 0.0;
         AB_UNROLL
         for (int i = 1; i <= 4; i++) {
-            const double rat = fast_div(s[i][kk], s[i + 1][kk]);
+            const double rat = ratc[i][kk];   // s[i][kk] / s[i + 1][kk], cached by bdf_stab
             sumrat += rat;
             sumrsq += rat * rat;
         }
@@ -1123,23 +1124,32 @@ struct Bdf {
             ss_head = (ss_head == 0) ? 4 : ss_head - 1;
             g.sync();
             if (g.lane == 0) {
-                S.ssdat[ss_head][1] = f2 * s2;            // sqm2^2
-                S.ssdat[ss_head][2] = f2 * q * q * s1;    // sqm1^2
-                S.ssdat[ss_head][3] = sq * sq;
+                const int older = (ss_head == 4) ? 0 : ss_head + 1;
+                const double v1 = f2 * s2, v2 = f2 * q * q * s1, v3 = sq * sq;
+                S.ssdat[ss_head][1] = v1;            // sqm2^2
+                S.ssdat[ss_head][2] = v2;            // sqm1^2
+                S.ssdat[ss_head][3] = v3;
+                // ratios to the previous entry: cvSLdet recomputes these 12 quotients on every call, 9 of them unchanged
+                S.ssdat[ss_head][5] = fast_div(v1, S.ssdat[older][1]);
+                S.ssdat[ss_head][6] = fast_div(v2, S.ssdat[older][2]);
+                S.ssdat[ss_head][7] = fast_div(v3, S.ssdat[older][3]);
             }
             g.sync();
         }
         if (qprime >= q) {
             if (q >= 3 && nscon >= q + 5) {
-                double s[6][4];
+                double s[6][4], ratc[5][4];
                 AB_UNROLL
                 for (int i = 1; i <= 5; ++i) {
                     int idx = ss_head + i - 1;
                     idx = idx >= 5 ? idx - 5 : idx;
                     AB_UNROLL
-                    for (int kk = 1; kk <= 3; ++kk) s[i][kk] = S.ssdat[idx][kk];
+                    for (int kk = 1; kk <= 3; ++kk) {
+                        s[i][kk] = S.ssdat[idx][kk];
+                        if (i <= 4) ratc[i][kk] = S.ssdat[idx][4 + kk];
+                    }
                 }
-                const int ldflag = bdf_sldet(s, q);
+                const int ldflag = bdf_sldet(s, ratc, q);
                 if (ldflag > 3) {
                     qprime = q - 1;
                     eta = etaqm1;
@@ -1521,7 +1531,7 @@ struct Bdf {
         ss_head = 0;
         if (g.lane == 0)
             for (int i = 0; i < 5; ++i)
-                for (int kk = 0; kk < 4; ++kk) S.ssdat[i][kk] = 0.0;
+                for (int kk = 0; kk < 8; ++kk) S.ssdat[i][kk] = 0.0;
         g.sync();
         set_ewt();  // cvInitialSetup
     }
@@ -1610,8 +1620,12 @@ struct Bdf {
             step_sync_arrive();
             if (nst > 0) set_ewt();
             if (nstloc >= mxstep) { tretlast = tn; { step_sync_leave(); return AB_TOO_MUCH_WORK; } }
-            const double nrm = wrms_max_zn(0);
-            if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; { step_sync_leave(); return AB_TOO_MUCH_ACC; } }
+            // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the
+            // norm is below 1/rtol and the test can only fire when rtol is of the order of the unit round-off.
+            if (!(o.rtol > 8.0 * DBL_EPSILON && o.rtol_fsa > 8.0 * DBL_EPSILON)) {
+                const double nrm = wrms_max_zn(0);
+                if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; { step_sync_leave(); return AB_TOO_MUCH_ACC; } }
+            }
             const int kflag = step();
             if (kflag != AB_SUCCESS) { tretlast = tn; { step_sync_leave(); return kflag; } }
             nstloc++;

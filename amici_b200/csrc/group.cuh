@@ -38,14 +38,16 @@ struct Group {
 #endif
     }
 
+    // Maximum of a NON-NEGATIVE value (a norm) over the group.  Non-negative doubles order like their bit patterns, and
+    // a NaN pattern is larger than every finite one and +inf, so two 32-bit integer warp reductions (REDUX) give a
+    // NaN-propagating maximum that is identical on every lane — instead of a five-stage 64-bit shuffle tree.
     AB_HD double max(double v) const {
 #if defined(__CUDA_ARCH__)
         if (G > 1) {
-            AB_UNROLL
-            for (int off = G / 2; off > 0; off >>= 1) {
-                const double o = __shfl_xor_sync(mask, v, off, G);
-                v = (o > v || o != o) ? o : v;   // NaN-propagating, so every lane ends with the same value
-            }
+            const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
+            const unsigned mhi = __reduce_max_sync(mask, hi);
+            const unsigned mlo = __reduce_max_sync(mask, hi == mhi ? lo : 0u);
+            v = __hiloint2double((int)mhi, (int)mlo);
         }
 #endif
         return v;

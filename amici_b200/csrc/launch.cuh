@@ -67,7 +67,7 @@ struct Config {
     // One warp per condition (G == 32): all resident warps of an SM in ONE block, so that they can align their steps
     // (Bdf::step_sync_*).  Otherwise small blocks: shared-memory granularity decides occupancy.
     static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : 64;
-    static constexpr int MINBLOCKS = (G == 32) ? (AB_MINBLOCKS * 64) / AB_THREADS_G32 : AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
+    static constexpr int MINBLOCKS = (G == 32) ? 1 : AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
 };
 
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>

@@ -67,6 +67,7 @@ struct Simulation {
             }
             // ConditionContext with FixedParameterContext::preequilibration (reference src/edata.cpp:438-556)
             for (int i = 0; i < M::NK; ++i) S.k[i] = (preeq ? b.k_preeq : b.k)[(size_t)n * M::NK + i];
+            M::derived(S.p, S.k);
             for (int i = 0; i < M::NH; ++i) S.h[i] = 0.0;
             for (int cc = 0; cc < NCOLS; ++cc) {
                 int ip = -1;
@@ -709,8 +710,10 @@ struct Simulation {
                     write_steady_state();
                     // back to the simulation condition (ConditionContext restore) and on to the main simulation
                     g.sync();
-                    if (g.lane == 0)
+                    if (g.lane == 0) {
                         for (int i = 0; i < M::NK; ++i) S.k[i] = b.k[(size_t)n * M::NK + i];
+                        M::derived(S.p, S.k);
+                    }
                     g.sync();
                     write_initial_state();
                     bdf.init(o.t0);
