@@ -27,6 +27,18 @@
 #include "model_common.cuh"
 #include "spline.cuh"
 
+// step alignment (Bdf::step_sync_*): a warp may run ahead of the slowest member by AB_SYNC_SLACK sync points;
+// AB_SYNC_HALF adds a second sync point in the middle of the step
+#ifndef AB_SYNC_SLACK
+#define AB_SYNC_SLACK 0
+#endif
+#ifndef AB_SYNC_HALF
+#define AB_SYNC_HALF 0
+#endif
+#ifndef AB_SYNC_SLEEP
+#define AB_SYNC_SLEEP 40
+#endif
+
 namespace amici_b200 {
 
 // plain-data interface structs: the C ABI's (include/amici_b200.h)
@@ -42,6 +54,7 @@ constexpr int LMAX = QMAX + 1;
 template <class M, int NCOLS>
 struct TrajShared {
     double zn[LMAX][M::NX][NCOLS];   // Nordsieck history, column fastest
+    double acorbuf[M::NX][NCOLS];    // accepted correction of the last step while its cvCompleteStep is deferred (Bdf::pending)
     double lus[M::NLU];              // sparse LU of I - gamma*J (static pivot order, emitted per model)
     double lu[M::NX][M::NX];         // dense LU with partial pivoting: fallback when a static pivot is rejected
     double savedJ[M::NNZ_J > 0 ? M::NNZ_J : 1];
@@ -547,6 +560,7 @@ struct Bdf {
     int nst, nstlp, nstlj, nscon, nfe, netf, ncfn, nni, nsetups, nje;
     int convfail, ss_head;
     bool jcur, tstopset, dense_lu;
+    bool pending;   // the accepted correction (acor, S.acorbuf) has not been added to the history yet: see history_pass
 
     // root finding (CVodeRootInit, cvodes.c:2674; cvRcheck1/2/3, cvRootfind :8576-9100) for the NES solver-tracked
     // event triggers; all group-uniform, arrays only indexed with compile-time constants
@@ -594,10 +608,14 @@ struct Bdf {
         }
 #endif
     }
-    AB_HD void step_sync_arrive() {
+    // phase = index of the sync point inside the step (0 = step start) of AB_SYNC_HALF + 1 points: generations are
+    // congruent to the phase, so that a warp that joins late pairs its step start with the step start of the others
+    AB_HD void step_sync_arrive(const int phase = 0) {
 #if defined(__CUDA_ARCH__)
         if (G == 32 && sync_pos) {
+            constexpr int NPH = AB_SYNC_HALF + 1;
             ++sync_gen;
+            if (NPH > 1) sync_gen += (phase - sync_gen % NPH + NPH) % NPH;
             if (g.lane == 0) sync_pos[sync_w] = sync_gen;
             __syncwarp();
             for (;;) {
@@ -606,8 +624,8 @@ struct Bdf {
                     const int pv = sync_pos[v];
                     if (pv < m) m = pv;
                 }
-                if (m >= sync_gen) break;
-                __nanosleep(40);
+                if (m >= sync_gen - AB_SYNC_SLACK) break;
+                if (AB_SYNC_SLEEP > 0) __nanosleep(AB_SYNC_SLEEP);
             }
         }
 #endif
@@ -637,8 +655,8 @@ struct Bdf {
         }
         return g.max(m);
     }
-    // same for a Nordsieck column j held in shared memory
-    AB_HD double wrms_max_zn(int j) const {
+    // same for a Nordsieck column j held in shared memory (+ lj * acor while the completion of the step is pending)
+    AB_HD double wrms_max_zn(int j, const double lj = 0.0) const {
         double m = 0.0;
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
@@ -646,7 +664,7 @@ struct Bdf {
             double s = 0.0;
             AB_UNROLL
             for (int r = 0; r < NX; ++r) {
-                const double pr = S.zn[j][r][col(c)] * ewt[c][r];
+                const double pr = (pending ? S.zn[j][r][col(c)] + lj * acor[c][r] : S.zn[j][r][col(c)]) * ewt[c][r];
                 s += pr * pr;
             }
             const double n = sqrt(s * (1.0 / NX));
@@ -663,7 +681,10 @@ struct Bdf {
             const bool st = (col(c) == 0);
             const double rt = st ? o.rtol : o.rtol_fsa, at = st ? o.atol : o.atol_fsa;
             AB_UNROLL
-            for (int r = 0; r < NX; ++r) ewt[c][r] = fast_div(1.0, rt * fabs(S.zn[0][r][col(c)]) + at);
+            for (int r = 0; r < NX; ++r) {
+                const double y = pending ? S.zn[0][r][col(c)] + acor[c][r] : S.zn[0][r][col(c)];   // l[0] = 1
+                ewt[c][r] = fast_div(1.0, rt * fabs(y) + at);
+            }
         }
     }
 
@@ -740,57 +761,66 @@ struct Bdf {
     // -----------------------------------------------------------------------------------------
     // Nordsieck array manipulation (per row in registers)
     // -----------------------------------------------------------------------------------------
-    // cvPredict (cvodes.c:6507) / cvRestore (:7373): Pascal-triangle update, sign = +1 / -1.
-    // Rolled over the rows (operands are in shared memory) and specialised on the order, so the code stays small.
+    // The three elementwise operations on the Nordsieck history — cvCompleteStep's zn[j] += l[j]*acor (cvodes.c:7634),
+    // cvRescale's zn[j] *= eta^j (:6425) and cvPredict / cvRestore's Pascal-triangle update (:6507, :7373) — in ONE pass
+    // over shared memory.  CVODES runs them as separate vector sweeps at the end of one step and the beginning of the
+    // next; here the completion is deferred (pending) until the next step starts, so that a history entry is loaded and
+    // stored once per step instead of three times.  The pass is flat: zn[j] is NX*NCOLS contiguous doubles and an
+    // elementwise update does not care which lane owns a column, so all G lanes share the elements (JAK-STAT: 162
+    // elements in 6 rounds of a warp instead of 9 rows on 18 lanes).  pred = +1 predict, -1 restore, 0 neither.
     template <int Q>
-    AB_HD void pascal_q(const double sign) {
+    AB_HD void history_pass_q(const bool cmpl, const bool resc, const int pred) {
+        constexpr int NEL = NX * NCOLS;
+        double* z0 = &S.zn[0][0][0];
+        const double* ab = &S.acorbuf[0][0];
+        double f[Q + 1];
+        f[0] = 1.0;
         AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            const int cc = col(c);
-            AB_NOUNROLL
-            for (int r = 0; r < NX; ++r) {
-                double z[Q + 1];
+        for (int jj = 1; jj <= Q; ++jj) f[jj] = f[jj - 1] * eta;
+        const double sg = pred < 0 ? -1.0 : 1.0;
+        g.sync();
+        AB_NOUNROLL
+        for (int e = g.lane; e < NEL; e += G) {
+            double z[Q + 1];
+            AB_UNROLL
+            for (int jj = 0; jj <= Q; ++jj) z[jj] = z0[jj * NEL + e];
+            if (cmpl) {
+                const double a = ab[e];
                 AB_UNROLL
-                for (int j = 0; j <= Q; ++j) z[j] = S.zn[j][r][cc];
+                for (int jj = 0; jj <= Q; ++jj) z[jj] += l[jj] * a;
+            }
+            if (resc) {
+                AB_UNROLL
+                for (int jj = 1; jj <= Q; ++jj) z[jj] *= f[jj];
+            }
+            if (pred != 0) {
                 AB_UNROLL
                 for (int kk = 1; kk <= Q; ++kk) {
                     AB_UNROLL
-                    for (int j = Q; j >= kk; --j) z[j - 1] += sign * z[j];
+                    for (int jj = Q; jj >= kk; --jj) z[jj - 1] += sg * z[jj];
                 }
-                AB_UNROLL
-                for (int j = 0; j < Q; ++j) S.zn[j][r][cc] = z[j];
             }
+            AB_UNROLL
+            for (int jj = 0; jj <= Q; ++jj) z0[jj * NEL + e] = z[jj];
         }
+        g.sync();
     }
-    AB_HD void pascal(const double sign) {
+    AB_HD void history_pass(const bool cmpl, const bool resc, const int pred) {
         switch (q) {
-            case 1: pascal_q<1>(sign); break;
-            case 2: pascal_q<2>(sign); break;
-            case 3: pascal_q<3>(sign); break;
-            case 4: pascal_q<4>(sign); break;
-            default: pascal_q<5>(sign); break;
+            case 1: history_pass_q<1>(cmpl, resc, pred); break;
+            case 2: history_pass_q<2>(cmpl, resc, pred); break;
+            case 3: history_pass_q<3>(cmpl, resc, pred); break;
+            case 4: history_pass_q<4>(cmpl, resc, pred); break;
+            default: history_pass_q<5>(cmpl, resc, pred); break;
         }
     }
-
-    // cvRescale (cvodes.c:6425): zn[j] *= eta^j, h = hscale*eta
-    AB_HD void rescale() {
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            AB_NOUNROLL
-            for (int r = 0; r < NX; ++r) {
-                double f = eta;
-                AB_UNROLL
-                for (int j = 1; j <= QMAX; ++j) {
-                    if (j <= q) S.zn[j][r][col(c)] *= f;
-                    f *= eta;
-                }
-            }
+    // add a pending correction to the history (anything that reads zn other than through the pending-aware
+    // accessors — outputs, root finding, order changes — needs this first)
+    AB_HD void flush_pending() {
+        if (pending) {
+            history_pass(true, false, 0);
+            pending = false;
         }
-        h = hscale * eta;
-        hscale = h;
-        nscon = 0;
     }
 
     // cvIncreaseBDF (cvodes.c:6256) for deltaq = +1, cvDecreaseBDF (:6363) for deltaq = -1 (cvAdjustOrder :6134)
@@ -1001,7 +1031,8 @@ struct Bdf {
         return ret;
     }
 
-    // cvCompleteStep (cvodes.c:7634)
+    // cvCompleteStep (cvodes.c:7634): counters and step-size history now; the update of the Nordsieck array is deferred
+    // to the next history_pass (pending), the correction is kept in registers and in S.acorbuf (flat layout)
     AB_HD void complete_step() {
         nst++;
         nscon++;
@@ -1019,13 +1050,12 @@ struct Bdf {
             if (!active(c)) continue;
             AB_UNROLL
             for (int r = 0; r < NX; ++r) {
-                AB_UNROLL
-                for (int j = 0; j < LMAX; ++j)
-                    if (j <= q) S.zn[j][r][col(c)] += l[j] * acor[c][r];
+                S.acorbuf[r][col(c)] = acor[c][r];
                 if (save) S.zn[QMAX][r][col(c)] = acor[c][r];
             }
         }
         if (save) saved_tq5 = tq[5];
+        pending = true;
     }
 
     // cvSetEta (cvodes.c:7798) with eta_min_fx = 0, eta_max_fx = 1.5, hmin = 0
@@ -1062,7 +1092,7 @@ struct Bdf {
             qwait = 2;
             etaqm1 = 0.0;
             if (q > 1) {
-                const double ddn = wrms_max_zn(q) * tq[1];
+                const double ddn = wrms_max_zn(q, pick(l, q)) * tq[1];
                 etaqm1 = 1.0 / (nth_root(6.0 * ddn, q) + 1e-6);
             }
             etaqp1 = 0.0;
@@ -1113,9 +1143,11 @@ struct Bdf {
             // WRMS of the state column only (lane 0 owns it)
             double s1 = 0.0, s2 = 0.0;
             if (g.lane == 0) {
+                const double lq = pending ? pick(l, q) : 0.0, lqm1 = pending ? pick(l, q - 1) : 0.0;   // deferred completion
                 AB_UNROLL
                 for (int r = 0; r < NX; ++r) {
-                    const double a = S.zn[q][r][0] * ewt[0][r], b = S.zn[q - 1][r][0] * ewt[0][r];
+                    const double a = (S.zn[q][r][0] + lq * acor[0][r]) * ewt[0][r];
+                    const double b = (S.zn[q - 1][r][0] + lqm1 * acor[0][r]) * ewt[0][r];
                     s1 += a * a;
                     s2 += b * b;
                 }
@@ -1425,29 +1457,36 @@ struct Bdf {
             resc = true;
         }
         for (;;) {
-            for (int pass = restore ? 0 : 1; pass < 2; ++pass) {
-                if (pass == 1) {
-                    if (dq != 0) {
-                        adjust_order(dq);
-                        q += dq;
-                        L = q + 1;
-                        qwait = L;
-                        dq = 0;
-                    }
-                    if (resc) rescale();
-                    if (reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
-                        const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, h, 1);
-                        nfe++;
-                        if (!ok) return AB_UNREC_RHSFUNC_ERR;
-                    }
-                    tn += h;  // cvPredict
-                    if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
-                }
-                pascal(pass == 0 ? -1.0 : 1.0);
-                if (pass == 0) tn = saved_t;
+            // the one history-manipulation site: [restore] -> [complete] -> [order change] -> [rescale] -> predict
+            if (restore) {
+                history_pass(false, false, -1);
+                tn = saved_t;
             }
+            if (dq != 0) {
+                flush_pending();   // cvAdjustOrder works on the completed history (rare)
+                adjust_order(dq);
+                q += dq;
+                L = q + 1;
+                qwait = L;
+                dq = 0;
+            }
+            if (resc) {   // scalar part of cvRescale; the history is scaled in the pass below
+                h = hscale * eta;
+                hscale = h;
+                nscon = 0;
+            }
+            if (reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
+                const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, h, 1);
+                nfe++;
+                if (!ok) return AB_UNREC_RHSFUNC_ERR;
+            }
+            tn += h;  // cvPredict
+            if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
+            history_pass(pending, resc, 1);
+            pending = false;
             restore = resc = reload = false;
             set_coeffs();
+            if (AB_SYNC_HALF >= 2 && nflag == FIRST_CALL) step_sync_arrive(1);
             nflag = nls(nflag);
             if (nflag != AB_SUCCESS) {  // cvHandleNFlag
                 ncfn++;
@@ -1491,8 +1530,10 @@ struct Bdf {
                 reload = true;
             }
         }
+        if (AB_SYNC_HALF >= 1) step_sync_arrive(AB_SYNC_HALF >= 2 ? 2 : 1);
         complete_step();
         prepare_next_step(dsm);
+        if (AB_SYNC_HALF >= 3) step_sync_arrive(3);
         if (o.stldet) bdf_stab();
         etamax = 10.0;  // eta_max_es == eta_max_gs == 10
         return AB_SUCCESS;
@@ -1521,6 +1562,7 @@ struct Bdf {
         tstopset = false; tstop = 0.0; tretlast = t0;
         convfail = CONVFAIL_NONE; jcur = false; dense_lu = false;
         reinit_pending = false;
+        pending = false;
         root_init();
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
@@ -1614,32 +1656,36 @@ struct Bdf {
                 }
             }
         }
-        int nstloc = 0;
+        // Step loop.  Every exit goes through the epilogue below: a pending completion is written to the history (the
+        // caller reads zn[0]) and the warp leaves the step-alignment group.
+        int nstloc = 0, rc = AB_SUCCESS;
         step_sync_join();
         for (;;) {
             step_sync_arrive();
             if (nst > 0) set_ewt();
-            if (nstloc >= mxstep) { tretlast = tn; { step_sync_leave(); return AB_TOO_MUCH_WORK; } }
+            if (nstloc >= mxstep) { tretlast = tn; rc = AB_TOO_MUCH_WORK; break; }
             // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the
             // norm is below 1/rtol and the test can only fire when rtol is of the order of the unit round-off.
             if (!(o.rtol > 8.0 * DBL_EPSILON && o.rtol_fsa > 8.0 * DBL_EPSILON)) {
-                const double nrm = wrms_max_zn(0);
-                if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; { step_sync_leave(); return AB_TOO_MUCH_ACC; } }
+                const double nrm = wrms_max_zn(0, 1.0);
+                if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; rc = AB_TOO_MUCH_ACC; break; }
             }
             const int kflag = step();
-            if (kflag != AB_SUCCESS) { tretlast = tn; { step_sync_leave(); return kflag; } }
+            if (kflag != AB_SUCCESS) { tretlast = tn; rc = kflag; break; }
             nstloc++;
             double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
             const bool at_tstop = tstopset && fabs(tn - tstop) <= troundoff;
             if (at_tstop) tn = tstop;
             if (ROOTS) {
+                flush_pending();   // the root finder interpolates on the completed history
                 if (rcheck3(tout, one_step || post)) {
                     irfnd = 1;
                     tretlast = tlo;
                     // a root right after re-initialisation is an error in the reference (src/solver_cvodes.cpp:531-540)
-                    if (post) { nst = nst_saved + 1; { step_sync_leave(); return AB_ERROR; } }
+                    if (post) { nst = nst_saved + 1; rc = AB_ERROR; break; }
                     collapse_to(tlo);
-                    { step_sync_leave(); return AB_ROOT_RETURN; }
+                    rc = AB_ROOT_RETURN;
+                    break;
                 }
             }
             if ((ROOTS || M::NE > 0) && post) {
@@ -1648,28 +1694,32 @@ struct Bdf {
                 post = false;
                 nstloc = 0;
                 tretlast = tn;
-                if (at_tstop) { step_sync_leave(); return AB_ERROR; }
+                if (at_tstop) { rc = AB_ERROR; break; }
                 if ((tn + hprime - tstop) * h > 0.0) {
                     hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
                     eta = hprime / h;
                 }
                 if (ROOTS) {
-                    const int rc = rcheck2();
-                    if (rc == 3) { step_sync_leave(); return AB_ILL_INPUT; }
-                    if (rc == 1) { tretlast = tlo; collapse_to(tlo); { step_sync_leave(); return AB_ROOT_RETURN; } }
+                    const int rc2 = rcheck2();
+                    if (rc2 == 3) { rc = AB_ILL_INPUT; break; }
+                    if (rc2 == 1) { tretlast = tlo; collapse_to(tlo); rc = AB_ROOT_RETURN; break; }
                 }
                 continue;
             }
-            if (one_step) { tretlast = tn; { step_sync_leave(); return AB_SUCCESS; } }
+            if (one_step) { tretlast = tn; rc = AB_SUCCESS; break; }
             if (at_tstop) {
                 tretlast = tstop;
                 tstopset = false;
-                { step_sync_leave(); return AB_TSTOP_RETURN; }
+                rc = AB_TSTOP_RETURN;
+                break;
             } else if ((tn + hprime - tstop) * h > 0.0) {
                 hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
                 eta = hprime / h;
             }
         }
+        flush_pending();
+        step_sync_leave();
+        return rc;
     }
 };
 
