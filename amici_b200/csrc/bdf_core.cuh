@@ -108,14 +108,15 @@ AB_HD void eval_splines(const typename Layout<M, G, C>::Shared& S, const Group<G
     constexpr int NCOLS = Layout<M, G, C>::NCOLS;
     AB_UNROLL
     for (int is = 0; is < M::NSPL; ++is) {
-        const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
+        const SplineLoc loc = spline_locate<M>(is, t);
+        const double v = spline_eval_at<M, NCOLS>(S.spl, is, 0, loc, true);
         e.spl[is] = M::SPL_LOG ? exp(v) : v;
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             const int cc = g.lane + G * c;
             e.sspl[c][is] = 0.0;
             if (cc >= ncols || cc == 0) continue;
-            const double s = spline_eval_scaled<M, NCOLS>(S.spl, is, cc, t, false);
+            const double s = spline_eval_at<M, NCOLS>(S.spl, is, cc, loc, false);
             e.sspl[c][is] = M::SPL_LOG ? s * e.spl[is] : s;
         }
     }
@@ -295,6 +296,12 @@ AB_COLD int cold_hin(typename Layout<M, G, C>::Shared& S, const SolverOptions& o
 // cvSLdet (cvodes.c:8256): stability-limit detection on the 5-deep history of scaled derivative norms.
 // s[i][k]: i = 1 (current) .. 5 (oldest), k = 1..3 (orders q-1, q, q+1).  All loops are unrolled with static
 // indices so that the work arrays live in registers; divisions whose divisor has been range-checked use fast_div.
+#if defined(AB_SLDET_STATS) && !defined(__CUDA_ARCH__)
+#define AB_SLDET_TRACE(tag, rr) sldet_trace(tag, rr)
+void sldet_trace(int tag, double rr);
+#else
+#define AB_SLDET_TRACE(tag, rr)
+#endif
 AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const int q) {
     const double TINY_ = 1e-10;
     double rav[4], qkr[4], sigsq[4], smax[4], ssmax[4], vrat[4], qc[6][4], qco[6][4];
@@ -344,6 +351,7 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
         for (int kk = 1; kk <= 3; kk++) drrmax = ab_max(drrmax, fabs(rav[kk] - rr));
         if (drrmax > vrrt2) return -3;
         kflag = 1;
+        AB_SLDET_TRACE(1, rr);
     } else {
         if (fabs(qco[1][1]) < TINY_ * ssmax[1]) return -4;
         double tem = fast_div(qco[1][2], qco[1][1]);
@@ -368,6 +376,7 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
             const double saqk = fast_div(fabs(qkr[kk]), ssmax[kk]);
             if (saqk > sqmax) sqmax = saqk;
         }
+        AB_SLDET_TRACE(20, rr);
         if (sqmax < sqtol) {
             kflag = 2;
         } else {
@@ -414,6 +423,9 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
             if (sqmin > sqtol) return -6;
         }
     }
+    // Only a result > 3 makes cvBDFStab act, and that needs rr > rrcut (the promotion of kflag at the end): with
+    // rr <= rrcut every remaining path returns a value <= 3, so the rest can be skipped.
+    if (!(rr > rrcut)) return kflag;
     bool bad7 = false;
     AB_UNROLL
     for (int kk = 1; kk <= 3; kk++) {
@@ -768,36 +780,35 @@ struct Bdf {
     // stored once per step instead of three times.  The pass is flat: zn[j] is NX*NCOLS contiguous doubles and an
     // elementwise update does not care which lane owns a column, so all G lanes share the elements (JAK-STAT: 162
     // elements in 6 rounds of a warp instead of 9 rows on 18 lanes).  pred = +1 predict, -1 restore, 0 neither.
-    template <int Q>
-    AB_HD void history_pass_q(const bool cmpl, const bool resc, const int pred) {
+    template <int Q, int PRED>
+    AB_HD void history_pass_q(const bool cmpl, const bool resc) {
         constexpr int NEL = NX * NCOLS;
         double* z0 = &S.zn[0][0][0];
         const double* ab = &S.acorbuf[0][0];
-        double f[Q + 1];
+        double f[Q + 1], lc[Q + 1];
         f[0] = 1.0;
         AB_UNROLL
         for (int jj = 1; jj <= Q; ++jj) f[jj] = f[jj - 1] * eta;
-        const double sg = pred < 0 ? -1.0 : 1.0;
+        AB_UNROLL
+        for (int jj = 0; jj <= Q; ++jj) lc[jj] = cmpl ? l[jj] : 0.0;   // no pending correction: add 0 * acorbuf
         g.sync();
         AB_NOUNROLL
         for (int e = g.lane; e < NEL; e += G) {
             double z[Q + 1];
             AB_UNROLL
             for (int jj = 0; jj <= Q; ++jj) z[jj] = z0[jj * NEL + e];
-            if (cmpl) {
-                const double a = ab[e];
-                AB_UNROLL
-                for (int jj = 0; jj <= Q; ++jj) z[jj] += l[jj] * a;
-            }
+            const double a = cmpl ? ab[e] : 0.0;
+            AB_UNROLL
+            for (int jj = 0; jj <= Q; ++jj) z[jj] += lc[jj] * a;
             if (resc) {
                 AB_UNROLL
                 for (int jj = 1; jj <= Q; ++jj) z[jj] *= f[jj];
             }
-            if (pred != 0) {
+            if (PRED != 0) {
                 AB_UNROLL
                 for (int kk = 1; kk <= Q; ++kk) {
                     AB_UNROLL
-                    for (int jj = Q; jj >= kk; --jj) z[jj - 1] += sg * z[jj];
+                    for (int jj = Q; jj >= kk; --jj) z[jj - 1] = PRED > 0 ? z[jj - 1] + z[jj] : z[jj - 1] - z[jj];
                 }
             }
             AB_UNROLL
@@ -805,20 +816,21 @@ struct Bdf {
         }
         g.sync();
     }
-    AB_HD void history_pass(const bool cmpl, const bool resc, const int pred) {
+    template <int PRED>
+    AB_HD void history_pass(const bool cmpl, const bool resc) {
         switch (q) {
-            case 1: history_pass_q<1>(cmpl, resc, pred); break;
-            case 2: history_pass_q<2>(cmpl, resc, pred); break;
-            case 3: history_pass_q<3>(cmpl, resc, pred); break;
-            case 4: history_pass_q<4>(cmpl, resc, pred); break;
-            default: history_pass_q<5>(cmpl, resc, pred); break;
+            case 1: history_pass_q<1, PRED>(cmpl, resc); break;
+            case 2: history_pass_q<2, PRED>(cmpl, resc); break;
+            case 3: history_pass_q<3, PRED>(cmpl, resc); break;
+            case 4: history_pass_q<4, PRED>(cmpl, resc); break;
+            default: history_pass_q<5, PRED>(cmpl, resc); break;
         }
     }
     // add a pending correction to the history (anything that reads zn other than through the pending-aware
     // accessors — outputs, root finding, order changes — needs this first)
     AB_HD void flush_pending() {
         if (pending) {
-            history_pass(true, false, 0);
+            history_pass<0>(true, false);
             pending = false;
         }
     }
@@ -1457,9 +1469,12 @@ struct Bdf {
             resc = true;
         }
         for (;;) {
+            // Step alignment is per ATTEMPT: a warp that repeats a step after a failed error or convergence test joins
+            // the others at their next step instead of making them wait a whole attempt.
+            step_sync_arrive();
             // the one history-manipulation site: [restore] -> [complete] -> [order change] -> [rescale] -> predict
             if (restore) {
-                history_pass(false, false, -1);
+                history_pass<-1>(false, false);
                 tn = saved_t;
             }
             if (dq != 0) {
@@ -1482,7 +1497,7 @@ struct Bdf {
             }
             tn += h;  // cvPredict
             if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
-            history_pass(pending, resc, 1);
+            history_pass<1>(pending, resc);
             pending = false;
             restore = resc = reload = false;
             set_coeffs();
@@ -1661,7 +1676,6 @@ struct Bdf {
         int nstloc = 0, rc = AB_SUCCESS;
         step_sync_join();
         for (;;) {
-            step_sync_arrive();
             if (nst > 0) set_ewt();
             if (nstloc >= mxstep) { tretlast = tn; rc = AB_TOO_MUCH_WORK; break; }
             // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the

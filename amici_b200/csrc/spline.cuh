@@ -80,30 +80,58 @@ AB_HD void spline_build_column(SplineTable<M, NCOLS>& T, const int ispl, const i
     for (int i = 0; i < NN; ++i) T.nodeval[ispl][i][col] = P[i];
 }
 
-// Scaled polynomial value of column `col` at time t. `exact_nodes`: return the stored node value at
-// a node (the reference does this for values only, not for sensitivities).
-template <class M, int NCOLS>
-AB_HD double spline_eval_scaled(const SplineTable<M, NCOLS>& T, const int ispl, const int col, const double t,
-                                const bool exact_nodes) {
-    constexpr int NN = SplineTable<M, NCOLS>::NN;
-    if (t > M::spline_node(ispl, NN - 1)) return T.nodeval[ispl][NN - 1][col];
-    if (t < M::spline_node(ispl, 0)) return T.nodeval[ispl][0][col];
+// Position of t relative to the nodes of spline ispl: computed once per evaluation time and shared by the value
+// column and the lane's sensitivity column (the reference locates the interval separately in get_value_scaled and
+// get_sensitivity_scaled, src/splinefunctions.cpp:846-1049).
+struct SplineLoc {
+    int region;    // -1: before the first node, +1: after the last node (constant extrapolation), 0: inside
+    int i_node;    // interval index
+    double s;      // (t - t_i) / (t_{i+1} - t_i)
+    bool at_node;  // t equals the right node of the interval exactly
+};
+
+template <class M>
+AB_HD SplineLoc spline_locate(const int ispl, const double t) {
+    constexpr int NN = M::SPL_NN > 1 ? M::SPL_NN : 2;
+    SplineLoc L;
+    L.region = (t > M::spline_node(ispl, NN - 1)) ? 1 : (t < M::spline_node(ispl, 0)) ? -1 : 0;
     int i_node = 0;
     AB_UNROLL
     for (int i = 1; i < NN - 1; ++i)
         if (M::spline_node(ispl, i) < t) i_node = i;
     double t0 = M::spline_node(ispl, 0), t1 = M::spline_node(ispl, 1);
+    double inv = 1.0 / (M::spline_node(ispl, 1) - M::spline_node(ispl, 0));   // node distances are compile-time constants
     AB_UNROLL
     for (int i = 1; i < NN - 1; ++i)
         if (i_node == i) {
             t0 = M::spline_node(ispl, i);
             t1 = M::spline_node(ispl, i + 1);
+            inv = 1.0 / (M::spline_node(ispl, i + 1) - M::spline_node(ispl, i));
         }
-    if (exact_nodes && t == t1) return T.nodeval[ispl][i_node + 1][col];
-    const double s = (t - t0) / (t1 - t0);
-    const double d = T.coef[ispl][i_node][0][col], c = T.coef[ispl][i_node][1][col];
-    const double b = T.coef[ispl][i_node][2][col], a = T.coef[ispl][i_node][3][col];
-    return d + s * (c + s * (b + s * a));
+    L.i_node = i_node;
+    L.at_node = (t == t1);
+    L.s = (t - t0) * inv;
+    return L;
+}
+
+// Scaled polynomial value of column `col` at the located time. `exact_nodes`: return the stored node value at
+// a node (the reference does this for values only, not for sensitivities).
+template <class M, int NCOLS>
+AB_HD double spline_eval_at(const SplineTable<M, NCOLS>& T, const int ispl, const int col, const SplineLoc& L,
+                            const bool exact_nodes) {
+    constexpr int NN = SplineTable<M, NCOLS>::NN;
+    if (L.region > 0) return T.nodeval[ispl][NN - 1][col];
+    if (L.region < 0) return T.nodeval[ispl][0][col];
+    if (exact_nodes && L.at_node) return T.nodeval[ispl][L.i_node + 1][col];
+    const double d = T.coef[ispl][L.i_node][0][col], c = T.coef[ispl][L.i_node][1][col];
+    const double b = T.coef[ispl][L.i_node][2][col], a = T.coef[ispl][L.i_node][3][col];
+    return d + L.s * (c + L.s * (b + L.s * a));
+}
+
+template <class M, int NCOLS>
+AB_HD double spline_eval_scaled(const SplineTable<M, NCOLS>& T, const int ispl, const int col, const double t,
+                                const bool exact_nodes) {
+    return spline_eval_at<M, NCOLS>(T, ispl, col, spline_locate<M>(ispl, t), exact_nodes);
 }
 
 }  // namespace amici_b200
