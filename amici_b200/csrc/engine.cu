@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 
 #include "model_common.cuh"
 #include "registry.h"
@@ -164,7 +166,7 @@ int ab_solve_device(const char* model, const ab_solver_options* opt, const ab_ba
         if (b->sz && npl) AB_CUDA(cudaMemsetAsync(b->sz, 0, sizeof(double) * nzs * npl, st));
         if (b->srz && npl) AB_CUDA(cudaMemsetAsync(b->srz, 0, sizeof(double) * nzs * npl, st));
     }
-    return e->launch(*opt, *b, work_counter, st);
+    return e->launch(*opt, *b, work_counter, Progress{}, st);
 }
 
 int ab_reduce_objective(int N, int nplist, const int* status, const double* llh, const double* sllh, double* out, void* stream) {
@@ -213,22 +215,81 @@ const char* ab_last_error(void) { return last_error().c_str(); }
 
 // ---- host-buffer entry point ------------------------------------------------------------------
 namespace {
-struct DevBuf {
-    void* d = nullptr;
-    ~DevBuf() { if (d) cudaFree(d); }
-};
-}  // namespace
-
-// Field table of ab_batch: per-condition element counts, so that host and device views of a chunk can be built generically.
-namespace {
+// Field table of ab_batch: per-condition element counts, so that host and device views can be built generically.
 struct FieldDesc {
     size_t offset;      // offsetof(ab_batch, field)
     size_t elem;        // sizeof element
     size_t per_cond;    // elements per condition
     bool input;
 };
+
+// Device workspace of ab_run_batch, kept between calls: allocating and freeing ~70 buffers (2.6 GB for the JAK-STAT
+// bench batch) per call costs more than the copies.  Released by ab_release_workspace() or at process exit.
+constexpr int WS_SLOTS = 64;
+constexpr int WS_MAX_CHUNKS = 4096;
+struct Workspace {
+    std::mutex mu;
+    void* dev[WS_SLOTS] = {};
+    size_t cap[WS_SLOTS] = {};
+    int* host_flags = nullptr;      // mapped pinned memory, WS_MAX_CHUNKS ints
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int device = -1;
+
+    bool reserve(int slot, size_t bytes) {
+        if (bytes <= cap[slot]) return true;
+        if (dev[slot]) cudaFree(dev[slot]);
+        dev[slot] = nullptr;
+        cap[slot] = 0;
+        if (!cuda_ok(cudaMalloc(&dev[slot], bytes), "cudaMalloc")) return false;
+        cap[slot] = bytes;
+        return true;
+    }
+    void release() {
+        for (int i = 0; i < WS_SLOTS; ++i) {
+            if (dev[i]) cudaFree(dev[i]);
+            dev[i] = nullptr;
+            cap[i] = 0;
+        }
+        if (host_flags) cudaFreeHost(host_flags);
+        host_flags = nullptr;
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+        ev0 = ev1 = nullptr;
+        compute = copy = nullptr;
+        device = -1;
+    }
+    bool init() {
+        int d = 0;
+        if (!cuda_ok(cudaGetDevice(&d), "cudaGetDevice")) return false;
+        if (device == d) return true;
+        release();   // the caller switched devices: start over on the new one
+        if (!cuda_ok(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+        if (!cuda_ok(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+        if (!cuda_ok(cudaEventCreate(&ev0), "cudaEventCreate") || !cuda_ok(cudaEventCreate(&ev1), "cudaEventCreate")) return false;
+        if (!cuda_ok(cudaHostAlloc((void**)&host_flags, sizeof(int) * WS_MAX_CHUNKS, cudaHostAllocMapped), "cudaHostAlloc")) return false;
+        device = d;
+        return true;
+    }
+};
+Workspace& workspace() {
+    static Workspace w;
+    return w;
+}
 }  // namespace
 
+void ab_release_workspace(void) {
+    Workspace& w = workspace();
+    std::lock_guard<std::mutex> lock(w.mu);
+    w.release();
+}
+
+// One launch per super-batch (all inputs resident first), outputs streamed back while the kernel runs: the kernel raises
+// a flag in mapped host memory whenever a sub-batch of `chunk` consecutive conditions is complete (Progress in
+// registry.h), and this thread then queues that sub-batch's D2H copies on a second stream.  Compared with one launch
+// per sub-batch there is no drain of the persistent grid between sub-batches, and the copies still overlap the solve.
 int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch* hb, float* kernel_ms) {
     const ModelEntry* e = find_model(model);
     if (!e) return AB_E_UNKNOWN_MODEL;
@@ -257,93 +318,106 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
         AB_F(srz, D, nme * q * nz, false), AB_F(sigmaz, D, nme * nz, false)};
 #undef AB_F
     constexpr int NF = (int)(sizeof(fields) / sizeof(fields[0]));
+    static_assert(NF + 8 <= WS_SLOTS, "workspace slots");
+    enum { S_TS = NF, S_PLIST, S_PSCALE, S_QUEUE, S_DONE };
     auto host_ptr = [&](const FieldDesc& f) -> char* { return *(char* const*)((const char*)hb + f.offset); };
 
-    // Chunked double-buffered pipeline: H2D(c+1) / solve(c+1) overlap D2H(c); the persistent kernels of consecutive
-    // chunks run on two streams, so the draining tail of one chunk is filled by the blocks of the next.
+    // sizes: sub-batch (granularity of the streamed copies) and super-batch (one launch; bounds the device footprint)
     size_t chunk = 8192;
     if (const char* env = getenv("AMICI_B200_CHUNK")) chunk = (size_t)atol(env) > 0 ? (size_t)atol(env) : chunk;
-    if (chunk > N) chunk = N;
-    const int nbuf = (chunk < N) ? 2 : 1;
-    DevBuf shared_in[3];
-    DevBuf bufs[2][NF];
-    DevBuf counters[2];
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
+    size_t bytes_per_cond = 0;
+    for (int f = 0; f < NF; ++f)
+        if (host_ptr(fields[f])) bytes_per_cond += fields[f].elem * fields[f].per_cond;
+    size_t budget = (size_t)16 << 30;   // device bytes per launch
+    if (const char* env = getenv("AMICI_B200_LAUNCH_BYTES")) budget = (size_t)atoll(env) > 0 ? (size_t)atoll(env) : budget;
+    size_t super = bytes_per_cond ? budget / bytes_per_cond : N;
+    if (super > chunk * (size_t)WS_MAX_CHUNKS) super = chunk * (size_t)WS_MAX_CHUNKS;
+    super = super / chunk * chunk;
+    if (super < chunk) super = chunk;
+    if (super > N) super = N;
+
+    Workspace& w = workspace();
+    std::lock_guard<std::mutex> lock(w.mu);
+    if (!w.init()) return AB_E_CUDA;
+    if (!w.reserve(S_TS, D * (nt ? nt : 1)) || !w.reserve(S_PLIST, I * (hb->nplist ? hb->nplist : 1)) ||
+        !w.reserve(S_PSCALE, I * (d.np ? d.np : 1)) || !w.reserve(S_QUEUE, I) || !w.reserve(S_DONE, I * WS_MAX_CHUNKS))
+        return AB_E_CUDA;
+    for (int f = 0; f < NF; ++f) {
+        const size_t bytes = fields[f].elem * fields[f].per_cond * super;
+        if (host_ptr(fields[f]) && bytes && !w.reserve(f, bytes)) return AB_E_CUDA;
+    }
     bool fail = false;
     auto ok = [&](cudaError_t err, const char* what) { if (!cuda_ok(err, what)) fail = true; return !fail; };
-    for (int i = 0; i < nbuf && !fail; ++i) {
-        ok(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking), "cudaStreamCreate");
-        ok(cudaEventCreate(&ev0[i]), "cudaEventCreate");
-        ok(cudaEventCreate(&ev1[i]), "cudaEventCreate");
-        ok(cudaMalloc(&counters[i].d, sizeof(int)), "cudaMalloc");
-        for (int f = 0; f < NF && !fail; ++f) {
-            const size_t bytes = fields[f].elem * fields[f].per_cond * chunk;
-            if (host_ptr(fields[f]) && bytes) ok(cudaMalloc(&bufs[i][f].d, bytes), "cudaMalloc");
-        }
-    }
     ab_batch base = *hb;
-    if (!fail) {
-        ok(cudaMalloc(&shared_in[0].d, D * (nt ? nt : 1)), "cudaMalloc");
-        ok(cudaMalloc(&shared_in[1].d, I * (hb->nplist ? hb->nplist : 1)), "cudaMalloc");
-        ok(cudaMalloc(&shared_in[2].d, I * (d.np ? d.np : 1)), "cudaMalloc");
-    }
-    if (!fail) {
-        if (nt) ok(cudaMemcpy(shared_in[0].d, hb->ts, D * nt, cudaMemcpyHostToDevice), "H2D ts");
-        if (hb->plist && hb->nplist) ok(cudaMemcpy(shared_in[1].d, hb->plist, I * hb->nplist, cudaMemcpyHostToDevice), "H2D plist");
-        if (hb->pscale && d.np) ok(cudaMemcpy(shared_in[2].d, hb->pscale, I * d.np, cudaMemcpyHostToDevice), "H2D pscale");
-        base.ts = (const double*)shared_in[0].d;
-        base.plist = hb->plist ? (const int*)shared_in[1].d : nullptr;
-        base.pscale = hb->pscale ? (const int*)shared_in[2].d : nullptr;
-    }
+    if (nt) ok(cudaMemcpyAsync(w.dev[S_TS], hb->ts, D * nt, cudaMemcpyHostToDevice, w.compute), "H2D ts");
+    if (hb->plist && hb->nplist) ok(cudaMemcpyAsync(w.dev[S_PLIST], hb->plist, I * hb->nplist, cudaMemcpyHostToDevice, w.compute), "H2D plist");
+    if (hb->pscale && d.np) ok(cudaMemcpyAsync(w.dev[S_PSCALE], hb->pscale, I * d.np, cudaMemcpyHostToDevice, w.compute), "H2D pscale");
+    base.ts = (const double*)w.dev[S_TS];
+    base.plist = hb->plist ? (const int*)w.dev[S_PLIST] : nullptr;
+    base.pscale = hb->pscale ? (const int*)w.dev[S_PSCALE] : nullptr;
+    int* dev_flags = nullptr;
+    ok(cudaHostGetDevicePointer((void**)&dev_flags, w.host_flags, 0), "cudaHostGetDevicePointer");
+
     float kms_total = 0.f;
-    int pending[2] = {0, 0};
-    size_t c = 0;
-    for (size_t lo = 0; lo < N && !fail; lo += chunk, ++c) {
-        const int bi = (int)(c % nbuf);
-        const size_t cnt = (lo + chunk <= N) ? chunk : N - lo;
-        if (pending[bi]) {   // buffer reuse is ordered by the stream; only the timing events need a host wait
-            ok(cudaEventSynchronize(ev1[bi]), "cudaEventSynchronize");
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev0[bi], ev1[bi]);
-            kms_total += ms;
-        }
+    for (size_t lo = 0; lo < N && !fail && rc == AB_OK; lo += super) {
+        const size_t cnt = (lo + super <= N) ? super : N - lo;
+        const int nchunks = (int)((cnt + chunk - 1) / chunk);
+        // the previous super-batch's copies read the same device buffers
+        ok(cudaStreamSynchronize(w.copy), "cudaStreamSynchronize");
         ab_batch db = base;
         db.N = (int)cnt;
         for (int f = 0; f < NF && !fail; ++f) {
             char* h = host_ptr(fields[f]);
-            *(void**)((char*)&db + fields[f].offset) = h ? bufs[bi][f].d : nullptr;
-            if (!h) continue;
             const size_t stride = fields[f].elem * fields[f].per_cond;
-            if (stride == 0) { *(void**)((char*)&db + fields[f].offset) = nullptr; continue; }
-            if (fields[f].input) ok(cudaMemcpyAsync(bufs[bi][f].d, h + lo * stride, stride * cnt, cudaMemcpyHostToDevice, st[bi]), "H2D");
-            else ok(cudaMemsetAsync(bufs[bi][f].d, 0, stride * cnt, st[bi]), "memset");
+            *(void**)((char*)&db + fields[f].offset) = (h && stride) ? w.dev[f] : nullptr;
+            if (!h || !stride) continue;
+            if (fields[f].input) ok(cudaMemcpyAsync(w.dev[f], h + lo * stride, stride * cnt, cudaMemcpyHostToDevice, w.compute), "H2D");
+            else ok(cudaMemsetAsync(w.dev[f], 0, stride * cnt, w.compute), "memset");
         }
+        ok(cudaMemsetAsync(w.dev[S_DONE], 0, I * nchunks, w.compute), "memset");
+        for (int c = 0; c < nchunks; ++c) w.host_flags[c] = 0;
         if (fail) break;
-        cudaEventRecord(ev0[bi], st[bi]);
-        rc = ab_solve_device(model, opt, &db, (int*)counters[bi].d, st[bi]);
-        cudaEventRecord(ev1[bi], st[bi]);
-        pending[bi] = 1;
+        Progress pg;
+        pg.done = (int*)w.dev[S_DONE];
+        pg.host_flags = dev_flags;
+        pg.chunk = (int)chunk;
+        cudaEventRecord(w.ev0, w.compute);
+        rc = e->launch(*opt, db, (int*)w.dev[S_QUEUE], pg, w.compute);
+        cudaEventRecord(w.ev1, w.compute);
         if (rc != AB_OK) break;
-        for (int f = 0; f < NF && !fail; ++f) {
-            char* h = host_ptr(fields[f]);
-            const size_t stride = fields[f].elem * fields[f].per_cond;
-            if (!h || fields[f].input || stride == 0) continue;
-            ok(cudaMemcpyAsync(h + lo * stride, bufs[bi][f].d, stride * cnt, cudaMemcpyDeviceToHost, st[bi]), "D2H");
+        volatile int* flags = w.host_flags;
+        for (int c = 0; c < nchunks && !fail; ++c) {
+            unsigned spins = 0;
+            bool finished = false;
+            while (!flags[c]) {
+                if ((++spins & 0x3ffu) == 0) {
+                    // the kernel ended (or died) without raising the flag: stop waiting; a clean end has set every flag
+                    if (cudaEventQuery(w.ev1) != cudaErrorNotReady) { finished = true; break; }
+                }
+                std::this_thread::yield();
+            }
+            if (finished && !flags[c]) {
+                if (!cuda_ok(cudaStreamSynchronize(w.compute), "solve kernel")) fail = true;
+                if (!flags[c] && !fail) { g_err = "solve kernel ended without completing a sub-batch"; fail = true; }
+                if (fail) break;
+            }
+            const size_t clo = (size_t)c * chunk, ccnt = (clo + chunk <= cnt) ? chunk : cnt - clo;
+            for (int f = 0; f < NF && !fail; ++f) {
+                char* h = host_ptr(fields[f]);
+                const size_t stride = fields[f].elem * fields[f].per_cond;
+                if (!h || fields[f].input || stride == 0) continue;
+                ok(cudaMemcpyAsync(h + (lo + clo) * stride, (char*)w.dev[f] + clo * stride, stride * ccnt, cudaMemcpyDeviceToHost, w.copy), "D2H");
+            }
         }
-    }
-    for (int i = 0; i < nbuf; ++i) {
-        if (st[i] && !cuda_ok(cudaStreamSynchronize(st[i]), "cudaStreamSynchronize")) fail = true;
-        if (pending[i] && !fail) {
+        if (!cuda_ok(cudaStreamSynchronize(w.compute), "cudaStreamSynchronize")) fail = true;
+        if (!fail) {
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev0[i], ev1[i]);
+            cudaEventElapsedTime(&ms, w.ev0, w.ev1);
             kms_total += ms;
         }
-        if (ev0[i]) cudaEventDestroy(ev0[i]);
-        if (ev1[i]) cudaEventDestroy(ev1[i]);
-        if (st[i]) cudaStreamDestroy(st[i]);
     }
-    if (kernel_ms) *kernel_ms = kms_total;   // sum of per-chunk solve durations (chunks on the two streams overlap)
+    if (!cuda_ok(cudaStreamSynchronize(w.copy), "cudaStreamSynchronize")) fail = true;
+    if (kernel_ms) *kernel_ms = kms_total;
     if (fail) return AB_E_CUDA;
     return rc;
 }

@@ -24,7 +24,7 @@ namespace amici_b200 {
 constexpr int SYNC_BYTES = 128;
 
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
-__global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head) {
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head, const Progress pg) {
     using Sim = Simulation<M, G, C, PREEQ>;
     using Shared = typename Sim::Shared;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -51,6 +51,21 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
         }
         sim.run();
         g.sync();
+        if (pg.done) {
+            // Completion tracking for the streaming host path (ab_run_batch): conditions are handed out in index order, so
+            // the sub-batches [c*chunk, (c+1)*chunk) complete roughly in order; the group that finishes the last condition
+            // of a sub-batch raises its flag in mapped host memory and the host starts that sub-batch's D2H copies.
+            __threadfence();   // every lane: its ReturnData stores are visible device-wide before the count below
+            g.sync();
+            if (g.lane == 0) {
+                const int c = n / pg.chunk;
+                const int size = (b.N - c * pg.chunk < pg.chunk) ? b.N - c * pg.chunk : pg.chunk;
+                if (atomicAdd(pg.done + c, 1) == size - 1) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile int*>(pg.host_flags + c) = 1;
+                }
+            }
+        }
     }
 }
 
@@ -71,7 +86,7 @@ struct Config {
 };
 
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
-int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
+int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
     using Sim = Simulation<M, G, C, PREEQ>;
     auto kern = bdf_solve_kernel<M, G, C, THREADS, MINBLOCKS, PREEQ>;
     constexpr int groups = THREADS / G;
@@ -91,7 +106,7 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     AB_CUDA(cudaMemsetAsync(queue_head, 0, sizeof(int), st));
-    kern<<<(unsigned)grid, THREADS, smem, st>>>(o, b, queue_head);
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(o, b, queue_head, pg);
     g_launches++;
     AB_CUDA(cudaGetLastError());
     return AB_OK;
@@ -100,25 +115,25 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
 // PREEQ = true variants (conditions with ExpData::fixed_parameters_pre_equilibration) are instantiated in their own
 // translation unit (tu/<model>_preeq.cu) to keep the build parallel.
 template <class M, bool PREEQ>
-int launch_model_impl(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
+int launch_model_impl(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
     if (o.sensi >= 1 && b.nplist > 0) {
         if (b.nplist + 1 > Config<M>::COLS) {
             last_error() = "nplist exceeds the number of model parameters";
             return AB_E_UNSUPPORTED;
         }
-        return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS, Config<M>::MINBLOCKS, PREEQ>(o, b, queue_head, st);
+        return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS, Config<M>::MINBLOCKS, PREEQ>(o, b, queue_head, pg, st);
     }
     // no sensitivities: one thread per condition
-    return launch_variant<M, 1, 1, 32, 1, PREEQ>(o, b, queue_head, st);
+    return launch_variant<M, 1, 1, 32, 1, PREEQ>(o, b, queue_head, pg, st);
 }
 
 template <class M>
-int launch_model_preeq(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st);
+int launch_model_preeq(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st);
 
 template <class M>
-int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, cudaStream_t st) {
-    if (b.k_preeq) return launch_model_preeq<M>(o, b, queue_head, st);
-    return launch_model_impl<M, false>(o, b, queue_head, st);
+int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
+    if (b.k_preeq) return launch_model_preeq<M>(o, b, queue_head, pg, st);
+    return launch_model_impl<M, false>(o, b, queue_head, pg, st);
 }
 
 template <class M>

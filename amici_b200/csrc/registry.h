@@ -23,11 +23,19 @@ inline bool cuda_ok(cudaError_t e, const char* what) {
         if (!cuda_ok((x), #x)) return AB_E_CUDA;     \
     } while (0)
 
+// Optional completion tracking of a launch (see bdf_solve_kernel): done[c] counts the finished conditions of sub-batch c
+// (device memory, zeroed by the caller), host_flags[c] is raised in mapped pinned host memory when sub-batch c is complete.
+struct Progress {
+    int* done = nullptr;
+    int* host_flags = nullptr;   // device-side address of the mapped host array
+    int chunk = 0;
+};
+
 struct ModelEntry {
     const char* name;
     ab_dims dims;
     void (*nominal)(double*, double*);
-    int (*launch)(const ab_solver_options&, const ab_batch&, int*, cudaStream_t);
+    int (*launch)(const ab_solver_options&, const ab_batch&, int*, const Progress&, cudaStream_t);
 };
 
 // defined in tu/<model>.cu

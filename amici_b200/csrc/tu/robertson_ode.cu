@@ -3,5 +3,5 @@
 #include "../models/robertson_ode.cuh"
 namespace amici_b200 {
 template <>
-int launch_model_preeq<models::robertson_ode>(const ab_solver_options&, const ab_batch&, int*, cudaStream_t);
+int launch_model_preeq<models::robertson_ode>(const ab_solver_options&, const ab_batch&, int*, const Progress&, cudaStream_t);
 ModelEntry entry_robertson_ode() { return make_entry<models::robertson_ode>(); } }

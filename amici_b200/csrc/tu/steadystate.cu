@@ -3,5 +3,5 @@
 #include "../models/steadystate.cuh"
 namespace amici_b200 {
 template <>
-int launch_model_preeq<models::steadystate>(const ab_solver_options&, const ab_batch&, int*, cudaStream_t);
+int launch_model_preeq<models::steadystate>(const ab_solver_options&, const ab_batch&, int*, const Progress&, cudaStream_t);
 ModelEntry entry_steadystate() { return make_entry<models::steadystate>(); } }
