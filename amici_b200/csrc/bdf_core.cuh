@@ -546,23 +546,25 @@ AB_COLD void cold_dense_solve(const typename Layout<M, G, C>::Shared& S, double*
 // ---------------------------------------------------------------------------------------------
 // the solver
 // ---------------------------------------------------------------------------------------------
-template <class M, int G, int C>
-struct Bdf {
-    static constexpr int NX = M::NX;
-    static constexpr int NCOLS = Layout<M, G, C>::NCOLS;
-    using Shared = typename Layout<M, G, C>::Shared;
-    using Eval = ModelEval<M, C>;
-
-    Shared& S;
+// ---------------------------------------------------------------------------------------------
+// CVODES step control, shared by the lane-group solver (Bdf below: a condition per group of lanes, vectors in registers)
+// and the block solver (bdf_block.cuh: a condition per thread block, vectors in global memory).  CRTP: D supplies the
+// vector primitives
+//   nx() gsync() leader()                       size / barrier of the cooperating threads / one elected thread
+//   set_ewt() wrms_max_zn(j, lj) wrms_max_up(cquot) stab_sums(lq, lqm1, s1, s2)
+//   history_pass<PRED>(cmpl, resc) order_up(A1, ll) order_down(ll)
+//   store_correction(save) store_correction_high() scale_zn1(f) init_vectors()
+//   nls(nflag) rhs_to_zn1(scale) initial_step(tout, &h0, &nfe)
+//   step_sync_join() step_sync_arrive() step_sync_leave()
+//   and, if D::ROOTS: rcheck1() rcheck2() rcheck3(tout, one_step) collapse_to(t), members tlo, irfnd
+// and everything here is scalar logic that every thread executes identically.
+// ---------------------------------------------------------------------------------------------
+template <class D, class SharedT>
+struct BdfControl {
+    SharedT& S;
     const SolverOptions& o;
-    Group<G> g;
-    int ncols;  // active columns: 1 + nplist (1 without sensitivities)
 
-    // per-lane column registers
-    double acor[C][NX];
-    double ewt[C][NX];
-
-    // step control (group-uniform scalars; CVodeMem fields of the same name). Arrays are only ever
+    // step control (uniform scalars; CVodeMem fields of the same name). Arrays are only ever
     // indexed with compile-time constants (unrolled, predicated loops) so that they stay in registers.
     double tn, h, hscale, hprime, eta, etamax, etaq, etaqm1, etaqp1, hu;
     double tau[LMAX + 1], l[LMAX], tq[6];
@@ -571,8 +573,567 @@ struct Bdf {
     int q, qprime, qwait, L, qu;
     int nst, nstlp, nstlj, nscon, nfe, netf, ncfn, nni, nsetups, nje;
     int convfail, ss_head;
-    bool jcur, tstopset, dense_lu;
-    bool pending;   // the accepted correction (acor, S.acorbuf) has not been added to the history yet: see history_pass
+    bool jcur, tstopset;
+    bool pending;          // the accepted correction has not been added to the history yet: see history_pass
+    bool reinit_pending;   // AMICI's CVodeSolver::reinit happened: the next call starts with reInit_post_process
+
+    AB_HD BdfControl(SharedT& s, const SolverOptions& opt) : S(s), o(opt) {}
+    AB_HD D& self() { return static_cast<D&>(*this); }
+    AB_HD const D& self() const { return static_cast<const D&>(*this); }
+
+    // add a pending correction to the history (anything that reads zn other than through the pending-aware
+    // accessors — outputs, root finding, order changes — needs this first)
+    AB_HD void flush_pending() {
+        if (pending) {
+            self().template history_pass<0>(true, false);
+            pending = false;
+        }
+    }
+
+    // cvIncreaseBDF (cvodes.c:6256) for deltaq = +1, cvDecreaseBDF (:6363) for deltaq = -1 (cvAdjustOrder :6134)
+    AB_HD void adjust_order(int deltaq) {
+        if (q == 2 && deltaq != 1) return;
+        double ll[LMAX + 1];
+        AB_UNROLL
+        for (int i = 0; i <= LMAX; ++i) ll[i] = 0.0;
+        ll[2] = 1.0;
+        if (deltaq == 1) {
+            double alpha0 = -1.0, alpha1 = 1.0, prod = 1.0, xiold = 1.0, hsum = hscale;
+            AB_UNROLL
+            for (int j = 1; j < QMAX; ++j) {
+                if (j < q) {
+                    hsum += tau[j + 1];
+                    const double xi = hsum / hscale;
+                    prod *= xi;
+                    alpha0 -= 1.0 / (j + 1);
+                    alpha1 += 1.0 / xi;
+                    AB_UNROLL
+                    for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xiold + ll[i - 1];
+                    xiold = xi;
+                }
+            }
+            const double A1 = (-alpha0 - alpha1) / prod;
+            self().order_up(A1, ll);   // zn[L] = A1 * zn[qmax] (saved correction), zn[2..q] += ll[j] * zn[L]
+        } else if (deltaq == -1) {
+            double hsum = 0.0;
+            AB_UNROLL
+            for (int j = 1; j <= QMAX - 2; ++j) {
+                if (j <= q - 2) {
+                    hsum += tau[j];
+                    const double xi = hsum / hscale;
+                    AB_UNROLL
+                    for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xi + ll[i - 1];
+                }
+            }
+            if (q > 2) self().order_down(ll);   // zn[2..q-1] -= ll[j] * zn[q]
+        }
+    }
+
+    // cvSetBDF + cvSetTqBDF + cvSet (cvodes.c:6788-6892, :6617)
+    AB_HD void set_coeffs() {
+        double alpha0 = -1.0, alpha0_hat = -1.0, xi_inv = 1.0, xistar_inv = 1.0, hsum = h;
+        l[0] = l[1] = 1.0;
+        AB_UNROLL
+        for (int i = 2; i < LMAX; ++i) l[i] = 0.0;
+        if (q > 1) {
+            AB_UNROLL
+            for (int j = 2; j < QMAX; ++j) {
+                if (j < q) {
+                    hsum += tau[j - 1];
+                    xi_inv = fast_div(h, hsum);
+                    alpha0 -= 1.0 / j;
+                    AB_UNROLL
+                    for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
+                }
+            }
+            alpha0 -= (q == 2) ? 0.5 : (q == 3) ? (1.0 / 3.0) : (q == 4) ? 0.25 : 0.2;
+            xistar_inv = -l[1] - alpha0;
+            hsum += pick(tau, q - 1);
+            xi_inv = fast_div(h, hsum);
+            alpha0_hat = -l[1] - xi_inv;
+            AB_UNROLL
+            for (int i = QMAX; i >= 1; --i)
+                if (i <= q) l[i] += l[i - 1] * xistar_inv;
+        }
+        const double lq = pick(l, q);
+        const double A1 = 1.0 - alpha0_hat + alpha0;
+        const double A2 = 1.0 + q * A1;
+        tq[2] = fabs(fast_div(A1, alpha0 * A2));
+        tq[5] = fabs(fast_div(A2 * xistar_inv, lq * xi_inv));
+        if (qwait == 1) {
+            if (q > 1) {
+                const double Cc = fast_div(xistar_inv, lq);
+                const double A3 = alpha0 + 1.0 / q;
+                const double A4 = alpha0_hat + xi_inv;
+                const double Cpinv = fast_div(1.0 - A4 + A3, A3);
+                tq[1] = fabs(Cc * Cpinv);
+            } else {
+                tq[1] = 1.0;
+            }
+            hsum += pick(tau, q);
+            xi_inv = fast_div(h, hsum);
+            const double A5 = alpha0 - (1.0 / (q + 1));
+            const double A6 = alpha0_hat - xi_inv;
+            const double Cppinv = fast_div(1.0 - A6 + A5, A2);
+            tq[3] = fabs(fast_div(Cppinv, xi_inv * (q + 2) * A5));
+        }
+        tq[4] = fast_div(0.1, tq[2]);  // nlscoef = CORTES = 0.1
+        rl1 = fast_div(1.0, l[1]);
+        gamma = h * rl1;
+        if (nst == 0) gammap = gamma;
+        gamrat = (nst > 0) ? fast_div(gamma, gammap) : 1.0;
+    }
+
+    // cvCompleteStep (cvodes.c:7634): counters and step-size history now; the update of the Nordsieck array is deferred
+    // to the next history_pass (pending), the correction is kept in registers and in S.acorbuf (flat layout)
+    AB_HD void complete_step() {
+        nst++;
+        nscon++;
+        hu = h;
+        qu = q;
+        AB_UNROLL
+        for (int i = QMAX; i >= 2; --i)
+            if (i <= q) tau[i] = tau[i - 1];
+        if (q == 1 && nst > 1) tau[2] = tau[1];
+        tau[1] = h;
+        qwait--;
+        const bool save = (qwait == 1 && q != QMAX);
+        self().store_correction(save);   // acorbuf = acor, and zn[qmax] = acor if save
+        if (save) saved_tq5 = tq[5];
+        pending = true;
+    }
+
+    // cvSetEta (cvodes.c:7798) with eta_min_fx = 0, eta_max_fx = 1.5, hmin = 0
+    AB_HD void set_eta() {
+        if (eta > 0.0 && eta < 1.5) {
+            eta = 1.0;
+            hprime = h;
+        } else {
+            if (eta >= 1.5) {
+                eta = ab_min(eta, etamax);
+                eta /= ab_max(1.0, fabs(h) * o.hmax_inv * eta);
+            } else {
+                eta = ab_max(eta, 0.1);
+            }
+            hprime = h * eta;
+            if (qprime < q) nscon = 0;
+        }
+    }
+
+    // cvPrepareNextStep (cvodes.c:7747) incl. cvComputeEtaqm1/qp1 and cvChooseEta
+    AB_HD void prepare_next_step(double dsm) {
+        if (etamax == 1.0) {
+            qwait = qwait > 2 ? qwait : 2;
+            qprime = q;
+            hprime = h;
+            eta = 1.0;
+            return;
+        }
+        etaq = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
+        if (qwait != 0) {
+            eta = etaq;
+            qprime = q;
+        } else {
+            qwait = 2;
+            etaqm1 = 0.0;
+            if (q > 1) {
+                const double ddn = self().wrms_max_zn(q, pick(l, q)) * tq[1];
+                etaqm1 = 1.0 / (nth_root(6.0 * ddn, q) + 1e-6);
+            }
+            etaqp1 = 0.0;
+            if (q != QMAX && saved_tq5 != 0.0) {
+                double ratio = h / tau[2], pw = 1.0;
+                for (int i = 0; i < L; ++i) pw *= ratio;  // SUNRpowerI(h/tau[2], L)
+                const double cquot = (tq[5] / saved_tq5) * pw;
+                const double dup = self().wrms_max_up(cquot) * tq[3];   // norm of acor - cquot * zn[qmax]
+                etaqp1 = 1.0 / (nth_root(10.0 * dup, L + 1) + 1e-6);
+            }
+            // cvChooseEta (cvodes.c:7935)
+            const double etam = ab_max(etaqm1, ab_max(etaq, etaqp1));
+            if (etam > 0.0 && etam < 1.5) {
+                eta = 1.0;
+                qprime = q;
+            } else if (etam == etaq) {
+                eta = etaq;
+                qprime = q;
+            } else if (etam == etaqm1) {
+                eta = etaqm1;
+                qprime = q - 1;
+            } else {
+                eta = etaqp1;
+                qprime = q + 1;
+                self().store_correction_high();   // zn[qmax] = acor
+            }
+        }
+        set_eta();
+    }
+
+    // cvBDFStab (cvodes.c:8158); the 5-deep history is a ring buffer in shared memory (no shifting)
+    AB_HD void bdf_stab() {
+        if (q >= 3) {
+            const double factorial = (q == 3) ? 2.0 : (q == 4) ? 6.0 : 24.0;   // (q-1)!
+            const double sq = factorial * q * (q + 1) * fast_div(acnrm, ab_max(tq[5], 1e-10));
+            // WRMS of the state column only (lane 0 owns it)
+            double s1 = 0.0, s2 = 0.0;   // valid on the leader
+            {
+                const double lq = pending ? pick(l, q) : 0.0, lqm1 = pending ? pick(l, q - 1) : 0.0;   // deferred completion
+                self().stab_sums(lq, lqm1, s1, s2);
+            }
+            const double f2 = factorial * factorial * (1.0 / self().nx());
+            ss_head = (ss_head == 0) ? 4 : ss_head - 1;
+            self().gsync();
+            if (self().leader()) {
+                const int older = (ss_head == 4) ? 0 : ss_head + 1;
+                const double v1 = f2 * s2, v2 = f2 * q * q * s1, v3 = sq * sq;
+                S.ssdat[ss_head][1] = v1;            // sqm2^2
+                S.ssdat[ss_head][2] = v2;            // sqm1^2
+                S.ssdat[ss_head][3] = v3;
+                // ratios to the previous entry: cvSLdet recomputes these 12 quotients on every call, 9 of them unchanged
+                S.ssdat[ss_head][5] = fast_div(v1, S.ssdat[older][1]);
+                S.ssdat[ss_head][6] = fast_div(v2, S.ssdat[older][2]);
+                S.ssdat[ss_head][7] = fast_div(v3, S.ssdat[older][3]);
+            }
+            self().gsync();
+        }
+        if (qprime >= q) {
+            if (q >= 3 && nscon >= q + 5) {
+                double s[6][4], ratc[5][4];
+                AB_UNROLL
+                for (int i = 1; i <= 5; ++i) {
+                    int idx = ss_head + i - 1;
+                    idx = idx >= 5 ? idx - 5 : idx;
+                    AB_UNROLL
+                    for (int kk = 1; kk <= 3; ++kk) {
+                        s[i][kk] = S.ssdat[idx][kk];
+                        if (i <= 4) ratc[i][kk] = S.ssdat[idx][4 + kk];
+                    }
+                }
+                const int ldflag = bdf_sldet(s, ratc, q);
+                if (ldflag > 3) {
+                    qprime = q - 1;
+                    eta = etaqm1;
+                    eta = ab_min(eta, etamax);
+                    eta = eta / ab_max(1.0, fabs(h) * o.hmax_inv * eta);
+                    hprime = h * eta;
+                }
+            }
+        } else {
+            nscon = 0;
+        }
+    }
+
+    // CVodeSolver::reinit + sens_reinit (reference src/solver_cvodes.cpp:471-503, :586-616): the caller has written the
+    // post-event state and sensitivities to zn[0]; restart at order 1 keeping counters, step-size history and linear
+    // solver data; the next solve_to call begins with reInit_post_process (:517-565).
+    AB_HD void amici_reinit(double t0) {
+        tn = t0;
+        q = 1;
+        L = 2;
+        qwait = 2;
+        qu = 0;
+        hu = 0.0;
+        reinit_pending = true;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // cvStep (cvodes.c:5800) with cvHandleNFlag (:7309) and cvDoErrorTest (:7461) folded in: every
+    // retry path sets flags that are executed at the single history-manipulation site at the loop top.
+    // -----------------------------------------------------------------------------------------
+    AB_HD int step() {
+        const double saved_t = tn;
+        int ncf = 0, nef = 0, nflag = FIRST_CALL;
+        double dsm = 0.0;
+        bool restore = false, resc = false, reload = false;
+        int dq = 0;
+        if (nst > 0 && hprime != h) {  // cvAdjustParams
+            dq = qprime - q;
+            resc = true;
+        }
+        for (;;) {
+            // Step alignment is per ATTEMPT: a warp that repeats a step after a failed error or convergence test joins
+            // the others at their next step instead of making them wait a whole attempt.
+            self().step_sync_arrive();
+            // the one history-manipulation site: [restore] -> [complete] -> [order change] -> [rescale] -> predict
+            if (restore) {
+                self().template history_pass<-1>(false, false);
+                tn = saved_t;
+            }
+            if (dq != 0) {
+                flush_pending();   // cvAdjustOrder works on the completed history (rare)
+                adjust_order(dq);
+                q += dq;
+                L = q + 1;
+                qwait = L;
+                dq = 0;
+            }
+            if (resc) {   // scalar part of cvRescale; the history is scaled in the pass below
+                h = hscale * eta;
+                hscale = h;
+                nscon = 0;
+            }
+            if (reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
+                const bool ok = self().rhs_to_zn1(h);
+                nfe++;
+                if (!ok) return AB_UNREC_RHSFUNC_ERR;
+            }
+            tn += h;  // cvPredict
+            if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
+            self().template history_pass<1>(pending, resc);
+            pending = false;
+            restore = resc = reload = false;
+            set_coeffs();
+            if (AB_SYNC_HALF >= 2 && nflag == FIRST_CALL) self().step_sync_arrive(1);
+            nflag = self().nls(nflag);
+            if (nflag != AB_SUCCESS) {  // cvHandleNFlag
+                ncfn++;
+                ncf++;
+                etamax = 1.0;
+                if (ncf == o.max_conv_fails) {
+                    tn = saved_t;
+                    return (nflag == NLS_RHS_RECVR) ? AB_REPTD_RHSFUNC_ERR : AB_CONV_FAILURE;
+                }
+                eta = 0.25;  // max(eta_cf, hmin/|h|), hmin = 0
+                nflag = PREV_CONV_FAIL;
+                restore = resc = true;
+                continue;
+            }
+            dsm = acnrm * tq[2];  // cvDoErrorTest
+            if (dsm <= 1.0) break;
+            nef++;
+            netf++;
+            nflag = PREV_ERR_FAIL;
+            restore = true;
+            if (nef == o.max_err_test_fails) {
+                tn = saved_t;
+                return AB_ERR_FAILURE;
+            }
+            etamax = 1.0;
+            if (nef <= 3) {  // MXNEF1
+                eta = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
+                eta = ab_max(0.1, eta);
+                if (nef >= 2) eta = ab_min(eta, 0.2);
+                resc = true;
+            } else if (q > 1) {  // force an order reduction
+                eta = 0.1;
+                dq = -1;
+                resc = true;
+            } else {  // already at order 1: restart from scratch with h*eta
+                eta = 0.1;
+                h *= eta;
+                hscale = h;
+                qwait = 10;  // LONG_WAIT
+                nscon = 0;
+                reload = true;
+            }
+        }
+        if (AB_SYNC_HALF >= 1) self().step_sync_arrive(AB_SYNC_HALF >= 2 ? 2 : 1);
+        complete_step();
+        prepare_next_step(dsm);
+        if (AB_SYNC_HALF >= 3) self().step_sync_arrive(3);
+        if (o.stldet) bdf_stab();
+        etamax = 10.0;  // eta_max_es == eta_max_gs == 10
+        return AB_SUCCESS;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // solver (re-)initialisation: Solver::setup -> CVodeInit/CVodeSensInit1 (reference src/solver.cpp:193-265);
+    // zn[0] must hold the initial state and sensitivities
+    // -----------------------------------------------------------------------------------------
+    AB_HD void init(double t0) {
+        tn = t0;
+        q = 1; L = 2; qwait = 2; qprime = 1; qu = 0;
+        etamax = 1e4;  // eta_max_fs
+        h = hscale = hprime = hu = 0.0;
+        eta = 1.0;
+        nst = nstlp = nstlj = nscon = nfe = netf = ncfn = nni = nsetups = nje = 0;
+        AB_UNROLL
+        for (int i = 0; i <= LMAX; ++i) tau[i] = 0.0;
+        AB_UNROLL
+        for (int i = 0; i < LMAX; ++i) l[i] = 0.0;
+        AB_UNROLL
+        for (int i = 0; i < 6; ++i) tq[i] = 0.0;
+        rl1 = gamma = gammap = gamrat = 1.0;
+        crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5 = 0.0;
+        etaq = etaqm1 = etaqp1 = 0.0;
+        tstopset = false; tstop = 0.0; tretlast = t0;
+        convfail = CONVFAIL_NONE; jcur = false;         reinit_pending = false;
+        pending = false;
+        self().init_vectors();   // acor = ewt = 0, root-finding state
+        self().gsync();
+        ss_head = 0;
+        if (self().leader())
+            for (int i = 0; i < 5; ++i)
+                for (int kk = 0; kk < 8; ++kk) S.ssdat[i][kk] = 0.0;
+        self().gsync();
+        self().set_ewt();  // cvInitialSetup
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // CVode(tout, CV_NORMAL) with tstop = tout, as AMICI's Solver::run drives it
+    // (reference src/solver.cpp:141-160; cvodes.c:2890-3650): returns AB_TSTOP_RETURN or an error.
+    // one_step = true is CVode(tout, CV_ONE_STEP) without a stop time, as Solver::step drives it during
+    // steady-state simulation (reference src/solver.cpp:162-178, src/forwardproblem.cpp:197-206): tout only
+    // gives the direction and the scale of the initial step; returns AB_SUCCESS after one internal step.
+    // Both modes share this function so that the (inlined) step has a single call site.
+    // -----------------------------------------------------------------------------------------
+    AB_HD int solve_to(double tout, bool one_step = false) {
+        constexpr bool ROOTS = D::ROOTS;
+        // Solver::apply_max_num_steps (reference src/solver.cpp:107-119)
+        if (o.maxsteps <= nst) return AB_ERROR;
+        const int mxstep = o.maxsteps - nst;
+        tstop = tout;
+        tstopset = !one_step;
+        // reInit_post_process (reference src/solver_cvodes.cpp:517-565): after an event the first step is taken as a
+        // "first call" (nst = 0) in one-step mode with tstop = tout, then the step counter is restored
+        bool post = D::EVENTS ? reinit_pending : false;
+        int nst_saved = 0;
+        if (post) {
+            reinit_pending = false;
+            nst_saved = nst;
+            nst = 0;
+            self().set_ewt();   // cvInitialSetup
+        }
+        if (nst == 0) {
+            // first call: zn[1] = f(t0, y0) (cvodes.c first-call block), initial step, zn[1] *= h
+            const bool ok = self().rhs_to_zn1(1.0);
+            nfe++;
+            if (!ok) return AB_FIRST_RHSFUNC_ERR;
+            if (tstopset && (tstop - tn) * (tout - tn) <= 0.0) return AB_ILL_INPUT;
+            double h0 = 0.0;
+            int nfe_hin = 0;
+            const int hflag = self().initial_step(tout, &h0, &nfe_hin);
+            nfe += nfe_hin;
+            if (hflag != AB_SUCCESS) return hflag;
+            h = h0;
+            const double rh = fabs(h) * o.hmax_inv;
+            if (rh > 1.0) h /= rh;
+            if (tstopset && (tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+            hscale = h;
+            hprime = h;
+            self().scale_zn1(h);
+            if constexpr (ROOTS) self().rcheck1();
+        } else {
+            const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
+            if constexpr (ROOTS) {   // cvodes.c "check for a root in the last step taken" on entry
+                const int irfndp = self().irfnd;
+                const int rc = self().rcheck2();
+                if (rc == 3) return AB_ILL_INPUT;
+                if (rc == 1) { tretlast = self().tlo; self().collapse_to(self().tlo); return AB_ROOT_RETURN; }
+                if (fabs(tn - tretlast) > troundoff) {
+                    if (self().rcheck3(tout, one_step)) {
+                        self().irfnd = 1;
+                        tretlast = self().tlo;
+                        self().collapse_to(self().tlo);
+                        return AB_ROOT_RETURN;
+                    }
+                    self().irfnd = 0;
+                    if (irfndp == 1 && one_step) { tretlast = tn; return AB_SUCCESS; }
+                }
+            }
+            if (tstopset) {
+                if (fabs(tn - tstop) <= troundoff) {
+                    tretlast = tstop;
+                    tstopset = false;
+                    return AB_TSTOP_RETURN;
+                } else if ((tn + hprime - tstop) * h > 0.0) {
+                    hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+                    eta = hprime / h;
+                }
+            }
+        }
+        // Step loop.  Every exit goes through the epilogue below: a pending completion is written to the history (the
+        // caller reads zn[0]) and the warp leaves the step-alignment group.
+        int nstloc = 0, rc = AB_SUCCESS;
+        self().step_sync_join();
+        for (;;) {
+            if (nst > 0) self().set_ewt();
+            if (nstloc >= mxstep) { tretlast = tn; rc = AB_TOO_MUCH_WORK; break; }
+            // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the
+            // norm is below 1/rtol and the test can only fire when rtol is of the order of the unit round-off.
+            if (!(o.rtol > 8.0 * DBL_EPSILON && o.rtol_fsa > 8.0 * DBL_EPSILON)) {
+                const double nrm = self().wrms_max_zn(0, 1.0);
+                if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; rc = AB_TOO_MUCH_ACC; break; }
+            }
+            const int kflag = step();
+            if (kflag != AB_SUCCESS) { tretlast = tn; rc = kflag; break; }
+            nstloc++;
+            double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
+            const bool at_tstop = tstopset && fabs(tn - tstop) <= troundoff;
+            if (at_tstop) tn = tstop;
+            if constexpr (ROOTS) {
+                flush_pending();   // the root finder interpolates on the completed history
+                if (self().rcheck3(tout, one_step || post)) {
+                    self().irfnd = 1;
+                    tretlast = self().tlo;
+                    // a root right after re-initialisation is an error in the reference (src/solver_cvodes.cpp:531-540)
+                    if (post) { nst = nst_saved + 1; rc = AB_ERROR; break; }
+                    self().collapse_to(self().tlo);
+                    rc = AB_ROOT_RETURN;
+                    break;
+                }
+            }
+            if (D::EVENTS && post) {
+                // end of reInit_post_process: anything but CV_SUCCESS throws there; then the regular call starts
+                nst = nst_saved + 1;
+                post = false;
+                nstloc = 0;
+                tretlast = tn;
+                if (at_tstop) { rc = AB_ERROR; break; }
+                if ((tn + hprime - tstop) * h > 0.0) {
+                    hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+                    eta = hprime / h;
+                }
+                if constexpr (ROOTS) {
+                    const int rc2 = self().rcheck2();
+                    if (rc2 == 3) { rc = AB_ILL_INPUT; break; }
+                    if (rc2 == 1) { tretlast = self().tlo; self().collapse_to(self().tlo); rc = AB_ROOT_RETURN; break; }
+                }
+                continue;
+            }
+            if (one_step) { tretlast = tn; rc = AB_SUCCESS; break; }
+            if (at_tstop) {
+                tretlast = tstop;
+                tstopset = false;
+                rc = AB_TSTOP_RETURN;
+                break;
+            } else if ((tn + hprime - tstop) * h > 0.0) {
+                hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+                eta = hprime / h;
+            }
+        }
+        flush_pending();
+        self().step_sync_leave();
+        return rc;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// the lane-group solver: one condition per group of G lanes, C columns per lane, work vectors in registers
+// ---------------------------------------------------------------------------------------------
+template <class M, int G, int C>
+struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
+    static constexpr int NX = M::NX;
+    static constexpr int NCOLS = Layout<M, G, C>::NCOLS;
+    static constexpr bool ROOTS = M::NE_SOLVER > 0;   // the integrator tracks event triggers
+    static constexpr bool EVENTS = M::NE > 0;         // AMICI re-initialises the solver after events
+    using Shared = typename Layout<M, G, C>::Shared;
+    using Eval = ModelEval<M, C>;
+    using Base = BdfControl<Bdf<M, G, C>, Shared>;
+    // names of the dependent base used by the vector code below
+    using Base::S; using Base::o;
+    using Base::tn; using Base::h; using Base::hscale; using Base::hprime; using Base::eta; using Base::etamax;
+    using Base::tau; using Base::l; using Base::tq; using Base::rl1; using Base::gamma; using Base::gammap;
+    using Base::gamrat; using Base::crate; using Base::delp; using Base::acnrm; using Base::q; using Base::L;
+    using Base::nst; using Base::nstlp; using Base::nstlj; using Base::nfe; using Base::nni; using Base::nsetups;
+    using Base::nje; using Base::convfail; using Base::jcur; using Base::pending; using Base::tstop;
+    using Base::tstopset; using Base::tretlast;
+
+    Group<G> g;
+    int ncols;  // active columns: 1 + nplist (1 without sensitivities)
+
+    // per-lane column registers
+    double acor[C][NX];
+    double ewt[C][NX];
 
     // root finding (CVodeRootInit, cvodes.c:2674; cvRcheck1/2/3, cvRootfind :8576-9100) for the NES solver-tracked
     // event triggers; all group-uniform, arrays only indexed with compile-time constants
@@ -582,13 +1143,115 @@ struct Bdf {
     int iroots[NES];
     double tlo, thi, trout, ttol;
     int irfnd, nge;
-    bool reinit_pending;   // AMICI's CVodeSolver::reinit happened: the next call starts with reInit_post_process
 
     // Step alignment of the warps of one block (G == 32 only): see step_sync_* below.
     volatile int* sync_pos = nullptr;
     int sync_n = 0, sync_w = 0, sync_gen = 0;
 
-    AB_HD Bdf(Shared& s, const SolverOptions& opt, int ncols_) : S(s), o(opt), ncols(ncols_) {}
+    bool dense_lu;
+
+    AB_HD Bdf(Shared& s, const SolverOptions& opt, int ncols_) : Base(s, opt), ncols(ncols_) {}
+
+    // -----------------------------------------------------------------------------------------
+    // primitives BdfControl calls (see the list at its top)
+    // -----------------------------------------------------------------------------------------
+    AB_HD int nx() const { return NX; }
+    AB_HD void gsync() const { g.sync(); }
+    AB_HD bool leader() const { return g.lane == 0; }
+    AB_HD bool rhs_to_zn1(double scale) { return cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, scale, 1); }
+    AB_HD int initial_step(double tout, double* h0, int* nfe_hin) { return cold_hin<M, G, C>(S, o, ncols, tn, tout, h0, nfe_hin); }
+    AB_HD void scale_zn1(double f) {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] *= f;
+        }
+    }
+    AB_HD void init_vectors() {
+        dense_lu = false;
+        root_init();
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) { acor[c][r] = 0.0; ewt[c][r] = 0.0; }
+        }
+    }
+    // cvIncreaseBDF's vector part: zn[L] = A1 * zn[qmax], zn[2..q] += ll[j] * zn[L]
+    AB_HD void order_up(const double A1, const double (&ll)[LMAX + 1]) {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                const double zL = A1 * S.zn[QMAX][r][col(c)];
+                AB_UNROLL
+                for (int j = 2; j <= QMAX; ++j) {
+                    if (j == L) S.zn[j][r][col(c)] = zL;
+                    else if (j <= q) S.zn[j][r][col(c)] += ll[j] * zL;
+                }
+            }
+        }
+    }
+    // cvDecreaseBDF's vector part: zn[2..q-1] -= ll[j] * zn[q]
+    AB_HD void order_down(const double (&ll)[LMAX + 1]) {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                double zq = 0.0;
+                AB_UNROLL
+                for (int j = 2; j <= QMAX; ++j)
+                    if (j == q) zq = S.zn[j][r][col(c)];
+                AB_UNROLL
+                for (int j = 2; j < QMAX; ++j)
+                    if (j < q) S.zn[j][r][col(c)] -= ll[j] * zq;
+            }
+        }
+    }
+    // cvCompleteStep's vector part while the history update is deferred
+    AB_HD void store_correction(const bool save) {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                S.acorbuf[r][col(c)] = acor[c][r];
+                if (save) S.zn[QMAX][r][col(c)] = acor[c][r];
+            }
+        }
+    }
+    AB_HD void store_correction_high() {
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) S.zn[QMAX][r][col(c)] = acor[c][r];
+        }
+    }
+    // max-WRMS of acor - cquot * zn[qmax] (cvComputeEtaqp1, cvodes.c:7900)
+    AB_HD double wrms_max_up(const double cquot) const {
+        double tmp[C][NX];
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) tmp[c][r] = active(c) ? acor[c][r] - cquot * S.zn[QMAX][r][col(c)] : 0.0;
+        }
+        return wrms_max(tmp);
+    }
+    // cvBDFStab: squared weighted sums of the (completed) state column of zn[q] and zn[q-1]; valid on the leader
+    AB_HD void stab_sums(const double lq, const double lqm1, double& s1, double& s2) const {
+        if (g.lane == 0) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) {
+                const double a = (S.zn[q][r][0] + lq * acor[0][r]) * ewt[0][r];
+                const double b = (S.zn[q - 1][r][0] + lqm1 * acor[0][r]) * ewt[0][r];
+                s1 += a * a;
+                s2 += b * b;
+            }
+        }
+    }
 
     // -----------------------------------------------------------------------------------------
     // Step alignment.  The per-step code is larger than the SM's instruction cache; warps that run it at unrelated
@@ -826,137 +1489,6 @@ struct Bdf {
             default: history_pass_q<5, PRED>(cmpl, resc); break;
         }
     }
-    // add a pending correction to the history (anything that reads zn other than through the pending-aware
-    // accessors — outputs, root finding, order changes — needs this first)
-    AB_HD void flush_pending() {
-        if (pending) {
-            history_pass<0>(true, false);
-            pending = false;
-        }
-    }
-
-    // cvIncreaseBDF (cvodes.c:6256) for deltaq = +1, cvDecreaseBDF (:6363) for deltaq = -1 (cvAdjustOrder :6134)
-    AB_HD void adjust_order(int deltaq) {
-        if (q == 2 && deltaq != 1) return;
-        double ll[LMAX + 1];
-        AB_UNROLL
-        for (int i = 0; i <= LMAX; ++i) ll[i] = 0.0;
-        ll[2] = 1.0;
-        if (deltaq == 1) {
-            double alpha0 = -1.0, alpha1 = 1.0, prod = 1.0, xiold = 1.0, hsum = hscale;
-            AB_UNROLL
-            for (int j = 1; j < QMAX; ++j) {
-                if (j < q) {
-                    hsum += tau[j + 1];
-                    const double xi = hsum / hscale;
-                    prod *= xi;
-                    alpha0 -= 1.0 / (j + 1);
-                    alpha1 += 1.0 / xi;
-                    AB_UNROLL
-                    for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xiold + ll[i - 1];
-                    xiold = xi;
-                }
-            }
-            const double A1 = (-alpha0 - alpha1) / prod;
-            // zn[L] = A1 * zn[qmax] (saved correction), zn[2..q] += ll[j] * zn[L]
-            AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                if (!active(c)) continue;
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r) {
-                    const double zL = A1 * S.zn[QMAX][r][col(c)];
-                    AB_UNROLL
-                    for (int j = 2; j <= QMAX; ++j) {
-                        if (j == L) S.zn[j][r][col(c)] = zL;
-                        else if (j <= q) S.zn[j][r][col(c)] += ll[j] * zL;
-                    }
-                }
-            }
-        } else if (deltaq == -1) {
-            double hsum = 0.0;
-            AB_UNROLL
-            for (int j = 1; j <= QMAX - 2; ++j) {
-                if (j <= q - 2) {
-                    hsum += tau[j];
-                    const double xi = hsum / hscale;
-                    AB_UNROLL
-                    for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xi + ll[i - 1];
-                }
-            }
-            if (q > 2) {
-                AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    if (!active(c)) continue;
-                    AB_UNROLL
-                    for (int r = 0; r < NX; ++r) {
-                        double zq = 0.0;
-                        AB_UNROLL
-                        for (int j = 2; j <= QMAX; ++j)
-                            if (j == q) zq = S.zn[j][r][col(c)];
-                        AB_UNROLL
-                        for (int j = 2; j < QMAX; ++j)
-                            if (j < q) S.zn[j][r][col(c)] -= ll[j] * zq;
-                    }
-                }
-            }
-        }
-    }
-
-    // cvSetBDF + cvSetTqBDF + cvSet (cvodes.c:6788-6892, :6617)
-    AB_HD void set_coeffs() {
-        double alpha0 = -1.0, alpha0_hat = -1.0, xi_inv = 1.0, xistar_inv = 1.0, hsum = h;
-        l[0] = l[1] = 1.0;
-        AB_UNROLL
-        for (int i = 2; i < LMAX; ++i) l[i] = 0.0;
-        if (q > 1) {
-            AB_UNROLL
-            for (int j = 2; j < QMAX; ++j) {
-                if (j < q) {
-                    hsum += tau[j - 1];
-                    xi_inv = fast_div(h, hsum);
-                    alpha0 -= 1.0 / j;
-                    AB_UNROLL
-                    for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
-                }
-            }
-            alpha0 -= (q == 2) ? 0.5 : (q == 3) ? (1.0 / 3.0) : (q == 4) ? 0.25 : 0.2;
-            xistar_inv = -l[1] - alpha0;
-            hsum += pick(tau, q - 1);
-            xi_inv = fast_div(h, hsum);
-            alpha0_hat = -l[1] - xi_inv;
-            AB_UNROLL
-            for (int i = QMAX; i >= 1; --i)
-                if (i <= q) l[i] += l[i - 1] * xistar_inv;
-        }
-        const double lq = pick(l, q);
-        const double A1 = 1.0 - alpha0_hat + alpha0;
-        const double A2 = 1.0 + q * A1;
-        tq[2] = fabs(fast_div(A1, alpha0 * A2));
-        tq[5] = fabs(fast_div(A2 * xistar_inv, lq * xi_inv));
-        if (qwait == 1) {
-            if (q > 1) {
-                const double Cc = fast_div(xistar_inv, lq);
-                const double A3 = alpha0 + 1.0 / q;
-                const double A4 = alpha0_hat + xi_inv;
-                const double Cpinv = fast_div(1.0 - A4 + A3, A3);
-                tq[1] = fabs(Cc * Cpinv);
-            } else {
-                tq[1] = 1.0;
-            }
-            hsum += pick(tau, q);
-            xi_inv = fast_div(h, hsum);
-            const double A5 = alpha0 - (1.0 / (q + 1));
-            const double A6 = alpha0_hat - xi_inv;
-            const double Cppinv = fast_div(1.0 - A6 + A5, A2);
-            tq[3] = fabs(fast_div(Cppinv, xi_inv * (q + 2) * A5));
-        }
-        tq[4] = fast_div(0.1, tq[2]);  // nlscoef = CORTES = 0.1
-        rl1 = fast_div(1.0, l[1]);
-        gamma = h * rl1;
-        if (nst == 0) gammap = gamma;
-        gamrat = (nst > 0) ? fast_div(gamma, gammap) : 1.0;
-    }
-
     // -----------------------------------------------------------------------------------------
     // nonlinear solve: cvNls (cvodes.c:6894) + SUNNonlinSolSolve_Newton (sunnonlinsol_newton.c:176-330)
     // + cvNlsResidualSensSim / cvNlsLSolveSensSim / cvNlsConvTestSensSim (cvodes_nls_sim.c:333-515).
@@ -1041,170 +1573,6 @@ struct Bdf {
             break;
         }
         return ret;
-    }
-
-    // cvCompleteStep (cvodes.c:7634): counters and step-size history now; the update of the Nordsieck array is deferred
-    // to the next history_pass (pending), the correction is kept in registers and in S.acorbuf (flat layout)
-    AB_HD void complete_step() {
-        nst++;
-        nscon++;
-        hu = h;
-        qu = q;
-        AB_UNROLL
-        for (int i = QMAX; i >= 2; --i)
-            if (i <= q) tau[i] = tau[i - 1];
-        if (q == 1 && nst > 1) tau[2] = tau[1];
-        tau[1] = h;
-        qwait--;
-        const bool save = (qwait == 1 && q != QMAX);
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!active(c)) continue;
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) {
-                S.acorbuf[r][col(c)] = acor[c][r];
-                if (save) S.zn[QMAX][r][col(c)] = acor[c][r];
-            }
-        }
-        if (save) saved_tq5 = tq[5];
-        pending = true;
-    }
-
-    // cvSetEta (cvodes.c:7798) with eta_min_fx = 0, eta_max_fx = 1.5, hmin = 0
-    AB_HD void set_eta() {
-        if (eta > 0.0 && eta < 1.5) {
-            eta = 1.0;
-            hprime = h;
-        } else {
-            if (eta >= 1.5) {
-                eta = ab_min(eta, etamax);
-                eta /= ab_max(1.0, fabs(h) * o.hmax_inv * eta);
-            } else {
-                eta = ab_max(eta, 0.1);
-            }
-            hprime = h * eta;
-            if (qprime < q) nscon = 0;
-        }
-    }
-
-    // cvPrepareNextStep (cvodes.c:7747) incl. cvComputeEtaqm1/qp1 and cvChooseEta
-    AB_HD void prepare_next_step(double dsm) {
-        if (etamax == 1.0) {
-            qwait = qwait > 2 ? qwait : 2;
-            qprime = q;
-            hprime = h;
-            eta = 1.0;
-            return;
-        }
-        etaq = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
-        if (qwait != 0) {
-            eta = etaq;
-            qprime = q;
-        } else {
-            qwait = 2;
-            etaqm1 = 0.0;
-            if (q > 1) {
-                const double ddn = wrms_max_zn(q, pick(l, q)) * tq[1];
-                etaqm1 = 1.0 / (nth_root(6.0 * ddn, q) + 1e-6);
-            }
-            etaqp1 = 0.0;
-            if (q != QMAX && saved_tq5 != 0.0) {
-                double ratio = h / tau[2], pw = 1.0;
-                for (int i = 0; i < L; ++i) pw *= ratio;  // SUNRpowerI(h/tau[2], L)
-                const double cquot = (tq[5] / saved_tq5) * pw;
-                double tmp[C][NX];
-                AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    AB_UNROLL
-                    for (int r = 0; r < NX; ++r)
-                        tmp[c][r] = active(c) ? acor[c][r] - cquot * S.zn[QMAX][r][col(c)] : 0.0;
-                }
-                const double dup = wrms_max(tmp) * tq[3];
-                etaqp1 = 1.0 / (nth_root(10.0 * dup, L + 1) + 1e-6);
-            }
-            // cvChooseEta (cvodes.c:7935)
-            const double etam = ab_max(etaqm1, ab_max(etaq, etaqp1));
-            if (etam > 0.0 && etam < 1.5) {
-                eta = 1.0;
-                qprime = q;
-            } else if (etam == etaq) {
-                eta = etaq;
-                qprime = q;
-            } else if (etam == etaqm1) {
-                eta = etaqm1;
-                qprime = q - 1;
-            } else {
-                eta = etaqp1;
-                qprime = q + 1;
-                AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    if (!active(c)) continue;
-                    AB_UNROLL
-                    for (int r = 0; r < NX; ++r) S.zn[QMAX][r][col(c)] = acor[c][r];
-                }
-            }
-        }
-        set_eta();
-    }
-
-    // cvBDFStab (cvodes.c:8158); the 5-deep history is a ring buffer in shared memory (no shifting)
-    AB_HD void bdf_stab() {
-        if (q >= 3) {
-            const double factorial = (q == 3) ? 2.0 : (q == 4) ? 6.0 : 24.0;   // (q-1)!
-            const double sq = factorial * q * (q + 1) * fast_div(acnrm, ab_max(tq[5], 1e-10));
-            // WRMS of the state column only (lane 0 owns it)
-            double s1 = 0.0, s2 = 0.0;
-            if (g.lane == 0) {
-                const double lq = pending ? pick(l, q) : 0.0, lqm1 = pending ? pick(l, q - 1) : 0.0;   // deferred completion
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r) {
-                    const double a = (S.zn[q][r][0] + lq * acor[0][r]) * ewt[0][r];
-                    const double b = (S.zn[q - 1][r][0] + lqm1 * acor[0][r]) * ewt[0][r];
-                    s1 += a * a;
-                    s2 += b * b;
-                }
-            }
-            const double f2 = factorial * factorial * (1.0 / NX);
-            ss_head = (ss_head == 0) ? 4 : ss_head - 1;
-            g.sync();
-            if (g.lane == 0) {
-                const int older = (ss_head == 4) ? 0 : ss_head + 1;
-                const double v1 = f2 * s2, v2 = f2 * q * q * s1, v3 = sq * sq;
-                S.ssdat[ss_head][1] = v1;            // sqm2^2
-                S.ssdat[ss_head][2] = v2;            // sqm1^2
-                S.ssdat[ss_head][3] = v3;
-                // ratios to the previous entry: cvSLdet recomputes these 12 quotients on every call, 9 of them unchanged
-                S.ssdat[ss_head][5] = fast_div(v1, S.ssdat[older][1]);
-                S.ssdat[ss_head][6] = fast_div(v2, S.ssdat[older][2]);
-                S.ssdat[ss_head][7] = fast_div(v3, S.ssdat[older][3]);
-            }
-            g.sync();
-        }
-        if (qprime >= q) {
-            if (q >= 3 && nscon >= q + 5) {
-                double s[6][4], ratc[5][4];
-                AB_UNROLL
-                for (int i = 1; i <= 5; ++i) {
-                    int idx = ss_head + i - 1;
-                    idx = idx >= 5 ? idx - 5 : idx;
-                    AB_UNROLL
-                    for (int kk = 1; kk <= 3; ++kk) {
-                        s[i][kk] = S.ssdat[idx][kk];
-                        if (i <= 4) ratc[i][kk] = S.ssdat[idx][4 + kk];
-                    }
-                }
-                const int ldflag = bdf_sldet(s, ratc, q);
-                if (ldflag > 3) {
-                    qprime = q - 1;
-                    eta = etaqm1;
-                    eta = ab_min(eta, etamax);
-                    eta = eta / ab_max(1.0, fabs(h) * o.hmax_inv * eta);
-                    hprime = h * eta;
-                }
-            }
-        } else {
-            nscon = 0;
-        }
     }
 
     // -----------------------------------------------------------------------------------------
@@ -1441,300 +1809,6 @@ struct Bdf {
         return found;
     }
 
-    // CVodeSolver::reinit + sens_reinit (reference src/solver_cvodes.cpp:471-503, :586-616): the caller has written the
-    // post-event state and sensitivities to zn[0]; restart at order 1 keeping counters, step-size history and linear
-    // solver data; the next solve_to call begins with reInit_post_process (:517-565).
-    AB_HD void amici_reinit(double t0) {
-        tn = t0;
-        q = 1;
-        L = 2;
-        qwait = 2;
-        qu = 0;
-        hu = 0.0;
-        reinit_pending = true;
-    }
-
-    // -----------------------------------------------------------------------------------------
-    // cvStep (cvodes.c:5800) with cvHandleNFlag (:7309) and cvDoErrorTest (:7461) folded in: every
-    // retry path sets flags that are executed at the single history-manipulation site at the loop top.
-    // -----------------------------------------------------------------------------------------
-    AB_HD int step() {
-        const double saved_t = tn;
-        int ncf = 0, nef = 0, nflag = FIRST_CALL;
-        double dsm = 0.0;
-        bool restore = false, resc = false, reload = false;
-        int dq = 0;
-        if (nst > 0 && hprime != h) {  // cvAdjustParams
-            dq = qprime - q;
-            resc = true;
-        }
-        for (;;) {
-            // Step alignment is per ATTEMPT: a warp that repeats a step after a failed error or convergence test joins
-            // the others at their next step instead of making them wait a whole attempt.
-            step_sync_arrive();
-            // the one history-manipulation site: [restore] -> [complete] -> [order change] -> [rescale] -> predict
-            if (restore) {
-                history_pass<-1>(false, false);
-                tn = saved_t;
-            }
-            if (dq != 0) {
-                flush_pending();   // cvAdjustOrder works on the completed history (rare)
-                adjust_order(dq);
-                q += dq;
-                L = q + 1;
-                qwait = L;
-                dq = 0;
-            }
-            if (resc) {   // scalar part of cvRescale; the history is scaled in the pass below
-                h = hscale * eta;
-                hscale = h;
-                nscon = 0;
-            }
-            if (reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
-                const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, h, 1);
-                nfe++;
-                if (!ok) return AB_UNREC_RHSFUNC_ERR;
-            }
-            tn += h;  // cvPredict
-            if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
-            history_pass<1>(pending, resc);
-            pending = false;
-            restore = resc = reload = false;
-            set_coeffs();
-            if (AB_SYNC_HALF >= 2 && nflag == FIRST_CALL) step_sync_arrive(1);
-            nflag = nls(nflag);
-            if (nflag != AB_SUCCESS) {  // cvHandleNFlag
-                ncfn++;
-                ncf++;
-                etamax = 1.0;
-                if (ncf == o.max_conv_fails) {
-                    tn = saved_t;
-                    return (nflag == NLS_RHS_RECVR) ? AB_REPTD_RHSFUNC_ERR : AB_CONV_FAILURE;
-                }
-                eta = 0.25;  // max(eta_cf, hmin/|h|), hmin = 0
-                nflag = PREV_CONV_FAIL;
-                restore = resc = true;
-                continue;
-            }
-            dsm = acnrm * tq[2];  // cvDoErrorTest
-            if (dsm <= 1.0) break;
-            nef++;
-            netf++;
-            nflag = PREV_ERR_FAIL;
-            restore = true;
-            if (nef == o.max_err_test_fails) {
-                tn = saved_t;
-                return AB_ERR_FAILURE;
-            }
-            etamax = 1.0;
-            if (nef <= 3) {  // MXNEF1
-                eta = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
-                eta = ab_max(0.1, eta);
-                if (nef >= 2) eta = ab_min(eta, 0.2);
-                resc = true;
-            } else if (q > 1) {  // force an order reduction
-                eta = 0.1;
-                dq = -1;
-                resc = true;
-            } else {  // already at order 1: restart from scratch with h*eta
-                eta = 0.1;
-                h *= eta;
-                hscale = h;
-                qwait = 10;  // LONG_WAIT
-                nscon = 0;
-                reload = true;
-            }
-        }
-        if (AB_SYNC_HALF >= 1) step_sync_arrive(AB_SYNC_HALF >= 2 ? 2 : 1);
-        complete_step();
-        prepare_next_step(dsm);
-        if (AB_SYNC_HALF >= 3) step_sync_arrive(3);
-        if (o.stldet) bdf_stab();
-        etamax = 10.0;  // eta_max_es == eta_max_gs == 10
-        return AB_SUCCESS;
-    }
-
-    // -----------------------------------------------------------------------------------------
-    // solver (re-)initialisation: Solver::setup -> CVodeInit/CVodeSensInit1 (reference src/solver.cpp:193-265);
-    // zn[0] must hold the initial state and sensitivities
-    // -----------------------------------------------------------------------------------------
-    AB_HD void init(double t0) {
-        tn = t0;
-        q = 1; L = 2; qwait = 2; qprime = 1; qu = 0;
-        etamax = 1e4;  // eta_max_fs
-        h = hscale = hprime = hu = 0.0;
-        eta = 1.0;
-        nst = nstlp = nstlj = nscon = nfe = netf = ncfn = nni = nsetups = nje = 0;
-        AB_UNROLL
-        for (int i = 0; i <= LMAX; ++i) tau[i] = 0.0;
-        AB_UNROLL
-        for (int i = 0; i < LMAX; ++i) l[i] = 0.0;
-        AB_UNROLL
-        for (int i = 0; i < 6; ++i) tq[i] = 0.0;
-        rl1 = gamma = gammap = gamrat = 1.0;
-        crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5 = 0.0;
-        etaq = etaqm1 = etaqp1 = 0.0;
-        tstopset = false; tstop = 0.0; tretlast = t0;
-        convfail = CONVFAIL_NONE; jcur = false; dense_lu = false;
-        reinit_pending = false;
-        pending = false;
-        root_init();
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) { acor[c][r] = 0.0; ewt[c][r] = 0.0; }
-        }
-        g.sync();
-        ss_head = 0;
-        if (g.lane == 0)
-            for (int i = 0; i < 5; ++i)
-                for (int kk = 0; kk < 8; ++kk) S.ssdat[i][kk] = 0.0;
-        g.sync();
-        set_ewt();  // cvInitialSetup
-    }
-
-    // -----------------------------------------------------------------------------------------
-    // CVode(tout, CV_NORMAL) with tstop = tout, as AMICI's Solver::run drives it
-    // (reference src/solver.cpp:141-160; cvodes.c:2890-3650): returns AB_TSTOP_RETURN or an error.
-    // one_step = true is CVode(tout, CV_ONE_STEP) without a stop time, as Solver::step drives it during
-    // steady-state simulation (reference src/solver.cpp:162-178, src/forwardproblem.cpp:197-206): tout only
-    // gives the direction and the scale of the initial step; returns AB_SUCCESS after one internal step.
-    // Both modes share this function so that the (inlined) step has a single call site.
-    // -----------------------------------------------------------------------------------------
-    AB_HD int solve_to(double tout, bool one_step = false) {
-        constexpr bool ROOTS = M::NE_SOLVER > 0;
-        // Solver::apply_max_num_steps (reference src/solver.cpp:107-119)
-        if (o.maxsteps <= nst) return AB_ERROR;
-        const int mxstep = o.maxsteps - nst;
-        tstop = tout;
-        tstopset = !one_step;
-        // reInit_post_process (reference src/solver_cvodes.cpp:517-565): after an event the first step is taken as a
-        // "first call" (nst = 0) in one-step mode with tstop = tout, then the step counter is restored
-        bool post = ROOTS || M::NE > 0 ? reinit_pending : false;
-        int nst_saved = 0;
-        if (post) {
-            reinit_pending = false;
-            nst_saved = nst;
-            nst = 0;
-            set_ewt();   // cvInitialSetup
-        }
-        if (nst == 0) {
-            // first call: zn[1] = f(t0, y0) (cvodes.c first-call block), initial step, zn[1] *= h
-            const bool ok = cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, 1.0, 1);
-            nfe++;
-            if (!ok) return AB_FIRST_RHSFUNC_ERR;
-            if (tstopset && (tstop - tn) * (tout - tn) <= 0.0) return AB_ILL_INPUT;
-            double h0 = 0.0;
-            int nfe_hin = 0;
-            const int hflag = cold_hin<M, G, C>(S, o, ncols, tn, tout, &h0, &nfe_hin);
-            nfe += nfe_hin;
-            if (hflag != AB_SUCCESS) return hflag;
-            h = h0;
-            const double rh = fabs(h) * o.hmax_inv;
-            if (rh > 1.0) h /= rh;
-            if (tstopset && (tn + h - tstop) * h > 0.0) h = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-            hscale = h;
-            hprime = h;
-            AB_UNROLL
-            for (int c = 0; c < C; ++c) {
-                if (!active(c)) continue;
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r) S.zn[1][r][col(c)] *= h;
-            }
-            if (ROOTS) rcheck1();
-        } else {
-            const double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
-            if (ROOTS) {   // cvodes.c "check for a root in the last step taken" on entry
-                const int irfndp = irfnd;
-                const int rc = rcheck2();
-                if (rc == 3) return AB_ILL_INPUT;
-                if (rc == 1) { tretlast = tlo; collapse_to(tlo); return AB_ROOT_RETURN; }
-                if (fabs(tn - tretlast) > troundoff) {
-                    if (rcheck3(tout, one_step)) {
-                        irfnd = 1;
-                        tretlast = tlo;
-                        collapse_to(tlo);
-                        return AB_ROOT_RETURN;
-                    }
-                    irfnd = 0;
-                    if (irfndp == 1 && one_step) { tretlast = tn; return AB_SUCCESS; }
-                }
-            }
-            if (tstopset) {
-                if (fabs(tn - tstop) <= troundoff) {
-                    tretlast = tstop;
-                    tstopset = false;
-                    return AB_TSTOP_RETURN;
-                } else if ((tn + hprime - tstop) * h > 0.0) {
-                    hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                    eta = hprime / h;
-                }
-            }
-        }
-        // Step loop.  Every exit goes through the epilogue below: a pending completion is written to the history (the
-        // caller reads zn[0]) and the warp leaves the step-alignment group.
-        int nstloc = 0, rc = AB_SUCCESS;
-        step_sync_join();
-        for (;;) {
-            if (nst > 0) set_ewt();
-            if (nstloc >= mxstep) { tretlast = tn; rc = AB_TOO_MUCH_WORK; break; }
-            // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the
-            // norm is below 1/rtol and the test can only fire when rtol is of the order of the unit round-off.
-            if (!(o.rtol > 8.0 * DBL_EPSILON && o.rtol_fsa > 8.0 * DBL_EPSILON)) {
-                const double nrm = wrms_max_zn(0, 1.0);
-                if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; rc = AB_TOO_MUCH_ACC; break; }
-            }
-            const int kflag = step();
-            if (kflag != AB_SUCCESS) { tretlast = tn; rc = kflag; break; }
-            nstloc++;
-            double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
-            const bool at_tstop = tstopset && fabs(tn - tstop) <= troundoff;
-            if (at_tstop) tn = tstop;
-            if (ROOTS) {
-                flush_pending();   // the root finder interpolates on the completed history
-                if (rcheck3(tout, one_step || post)) {
-                    irfnd = 1;
-                    tretlast = tlo;
-                    // a root right after re-initialisation is an error in the reference (src/solver_cvodes.cpp:531-540)
-                    if (post) { nst = nst_saved + 1; rc = AB_ERROR; break; }
-                    collapse_to(tlo);
-                    rc = AB_ROOT_RETURN;
-                    break;
-                }
-            }
-            if ((ROOTS || M::NE > 0) && post) {
-                // end of reInit_post_process: anything but CV_SUCCESS throws there; then the regular call starts
-                nst = nst_saved + 1;
-                post = false;
-                nstloc = 0;
-                tretlast = tn;
-                if (at_tstop) { rc = AB_ERROR; break; }
-                if ((tn + hprime - tstop) * h > 0.0) {
-                    hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                    eta = hprime / h;
-                }
-                if (ROOTS) {
-                    const int rc2 = rcheck2();
-                    if (rc2 == 3) { rc = AB_ILL_INPUT; break; }
-                    if (rc2 == 1) { tretlast = tlo; collapse_to(tlo); rc = AB_ROOT_RETURN; break; }
-                }
-                continue;
-            }
-            if (one_step) { tretlast = tn; rc = AB_SUCCESS; break; }
-            if (at_tstop) {
-                tretlast = tstop;
-                tstopset = false;
-                rc = AB_TSTOP_RETURN;
-                break;
-            } else if ((tn + hprime - tstop) * h > 0.0) {
-                hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                eta = hprime / h;
-            }
-        }
-        flush_pending();
-        step_sync_leave();
-        return rc;
-    }
 };
 
 }  // namespace amici_b200
