@@ -69,6 +69,8 @@ static const ModelEntry* registry(int* count) {
         entry_robertson_ode(),
         entry_events(),
         entry_neuron(),
+        entry_massaction(),
+        entry_massaction_small(),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
@@ -137,7 +139,7 @@ int ab_get_dims(const char* model, ab_dims* out) {
 int ab_get_nominal(const char* model, double* p, double* k) {
     const ModelEntry* e = find_model(model);
     if (!e) return AB_E_UNKNOWN_MODEL;
-    double pt[64], kt[64];
+    double pt[512], kt[64];
     e->nominal(pt, kt);
     if (p) std::memcpy(p, pt, sizeof(double) * e->dims.np);
     if (k) std::memcpy(k, kt, sizeof(double) * e->dims.nk);

@@ -44,6 +44,8 @@ ModelEntry entry_steadystate();
 ModelEntry entry_robertson_ode();
 ModelEntry entry_events();
 ModelEntry entry_neuron();
+ModelEntry entry_massaction();
+ModelEntry entry_massaction_small();
 
 }  // namespace amici_b200
 #endif
