@@ -85,9 +85,38 @@ def make_robertson(N=8, seed=1):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def make_massaction_big(N=3, seed=20):
+    """BASELINE config 5 (100 species / 300 rate constants, FSA over all 300): the full ReturnData of one condition is
+    2.6 MB, so the fixture keeps the objective, the states and a slice of the state sensitivities."""
+    m = RefModel("massaction")
+    ts = np.linspace(0, 10, 11)
+    rng = np.random.default_rng(seed)
+    p = np.tile(m.p_nominal, (N, 1)) * 10 ** rng.uniform(-1, 1, (N, m.dims.np))
+    p[0] = m.p_nominal
+    k = np.ones((N, 1))
+    y0 = m.run(ts, p, k, sensi_order=0, fields=["y"])["y"]
+    my = y0 + 0.1 * rng.standard_normal(y0.shape)
+    sig = np.full_like(my, 0.1)
+    out = dict(ts=ts, p=p, k=k, my=my, sigmay_in=sig, pscale=np.zeros(m.dims.np, int))
+    for name, extra in (("klu", dict(linsol=9)), ("dense", dict(linsol=1)),
+                        ("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=200000))):
+        r = m.run(ts, p, k, my=my, sigmay=sig, sensi_order=1,
+                  fields=["status", "llh", "chi2", "sllh", "x", "y", "res", "xdot", "sx", "numsteps"], **extra)
+        for f in ("status", "llh", "chi2", "sllh", "x", "y", "res", "xdot", "numsteps"):
+            out[f"{name}_{f}"] = r[f]
+        out[f"{name}_sxpick"] = r["sx"][:, -1, ::10, :]   # last timepoint, every 10th parameter
+    path = os.path.join(HERE, "massaction.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["robertson"]:
         make_robertson()
+        sys.exit(0)
+    if sys.argv[1:] == ["massaction"]:
+        make("massaction_small", np.linspace(0, 10, 11), N=6, seed=19, kscale=(1.0, 1.0))
+        make_massaction_big()
         sys.exit(0)
     make_robertson()
     make("jakstat_adjoint", np.arange(0, 61, 5.0), N=6, seed=11)
@@ -102,5 +131,8 @@ if __name__ == "__main__":
     # BASELINE config 4: Heaviside switches, root finding, event observables (z, sz, rz, srz), state resets
     make("events", np.linspace(0, 10, 21), N=6, seed=17, kscale=(1.0, 1.0), nmaxevent=2)
     make("neuron", np.linspace(0, 100, 21), N=6, seed=18, kscale=(1.0, 1.0), nmaxevent=10)
+    # BASELINE config 5: synthetic mass-action networks (block solver), small variant with the full ReturnData
+    make("massaction_small", np.linspace(0, 10, 11), N=6, seed=19, kscale=(1.0, 1.0))
+    make_massaction_big()
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=16, tag="_preeq_newton2", preeq=True, newton_maxsteps=2,
          ss_mode=2, ss_sensi_mode=0)

@@ -149,6 +149,32 @@ def test_oracle_reproduces_golden():
         np.testing.assert_array_equal(r[f], g[f"klu_{f}"])
 
 
+def test_oracle_massaction_model_is_the_network():
+    """The reference-format model the oracle generator writes (oracle/gen_massaction_ref.py) integrates the network of
+    codegen/massaction.py: the compiled reference reproduces the committed vectors bit for bit, and its states agree with
+    an independent integrator (scipy LSODA) on the numpy restatement of xdot."""
+    from oracle import refsim
+    if not refsim.available("massaction_small"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from scipy.integrate import solve_ivp
+    from amici_b200.codegen.massaction import network, xdot
+    g = np.load(os.path.join(GOLD, "massaction_small.npz"))
+    r = refsim.RefModel("massaction_small").run(g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], linsol=9)
+    for f in ("x", "sx", "llh", "sllh"):
+        np.testing.assert_array_equal(r[f], g[f"klu_{f}"])
+    net = network("massaction_small")
+    sol = solve_ivp(lambda t, x: xdot(net, x, g["p"][1]), (0, 10), net["x0"], method="LSODA", rtol=1e-11, atol=1e-14, t_eval=g["ts"])
+    np.testing.assert_allclose(g["truth_x"][1], sol.y.T, rtol=1e-7, atol=1e-10)
+
+
+def test_massaction_generated_headers_are_current():
+    """csrc/models/massaction*.cuh are what codegen/massaction.py emits (the tables the oracle model is written from)."""
+    from amici_b200.codegen import massaction
+    for name in massaction.SPECS:
+        path = os.path.join(ROOT, "amici_b200", "csrc", "models", name + ".cuh")
+        assert open(path).read() == massaction.emit_cuda(massaction.network(name))
+
+
 def test_maxsteps_status(built):
     """Exhausting the step budget inside a call gives CV_TOO_MUCH_WORK (-1) and NaN outputs from that timepoint on."""
     g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))

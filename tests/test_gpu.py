@@ -34,7 +34,7 @@ def _run(model_name, g, sensi=True, ts=None, **solver_kw):
 
 
 @pytest.mark.parametrize("fixture,model", [("jakstat_adjoint", "jakstat_adjoint"), ("jakstat_adjoint_log10", "jakstat_adjoint"),
-                                           ("steadystate", "steadystate")])
+                                           ("steadystate", "steadystate"), ("massaction_small", "massaction_small")])
 def test_cuda_matches_golden(fixture, model):
     g = np.load(os.path.join(GOLD, fixture + ".npz"))
     res = _run(model, g)
@@ -324,3 +324,71 @@ def test_linearity_property_full_size_batch():
         assert (res["llh"][sel] == res["llh"][sel][0]).all()
         assert (res["sllh"][sel] == res["sllh"][sel][0]).all()
         np.testing.assert_allclose(res["llh"][sel][0], g["truth_llh"][j], rtol=1e-6)
+
+
+# ---- BASELINE config 5: synthetic mass-action networks on the block solver (one condition per thread block) ----------
+def test_block_solver_massaction_100x300_matches_golden():
+    """100 species / 300 rate constants, forward sensitivities for all 300 parameters: objective, states and a slice of the
+    state sensitivities against the committed reference vectors (same protocol as the small models)."""
+    import amici_b200 as ab
+    g = np.load(os.path.join(GOLD, "massaction.npz"))
+    m = ab.get_model("massaction")
+    m.set_timepoints(g["ts"])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    batch = ab.ExpDataBatch(g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"])
+    res = ab.run_batch(m, s, batch, fields=["status", "llh", "chi2", "sllh", "x", "y", "res", "xdot", "sx", "numsteps"])
+    cand = dict(res.fields)
+    cand["sxpick"] = res["sx"][:, -1, ::10, :]
+    parity.check_against_golden(cand, g, fields=["x", "y", "llh", "chi2", "sllh", "res", "xdot", "sxpick"])
+    # step counts are statistically equivalent to the reference's (chaotic w.r.t. round-off, SURVEY.md finding 5)
+    nst, ref = res["numsteps"][:, -1], g["klu_numsteps"][:, -1]
+    assert np.all(np.abs(nst - ref) <= 0.1 * ref), (nst, ref)
+
+
+def test_block_solver_plist_subset_and_log10_scale_vs_reference():
+    """A parameter subset in log10 scale exercises plist, the unscaling and the chain rule of the block solver."""
+    import amici_b200 as ab
+    from oracle.refsim import RefModel, available
+    if not available("massaction_small"):
+        pytest.skip("oracle/_ref/libref_massaction_small.so not built")
+    g = np.load(os.path.join(GOLD, "massaction_small.npz"))
+    N, npar = g["p"].shape
+    plist = [1, 5, 6, 17, 23]
+    pscale = np.full(npar, 2, dtype=np.int32)
+    p = np.log10(g["p"])
+    m = ab.get_model("massaction_small")
+    m.set_timepoints(g["ts"])
+    m.set_parameter_list(plist)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    batch = ab.ExpDataBatch(g["ts"], p, g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=pscale)
+    res = ab.run_simulations(m, s, batch)
+    ref = RefModel("massaction_small")
+    r = {}
+    for name, kw in (("klu", dict(linsol=9)), ("dense", dict(linsol=1)), ("truth", dict(rtol=1e-12, atol=1e-16, maxsteps=200000))):
+        rr = ref.run(g["ts"], p, g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=pscale, plist=plist, sensi_order=1, **kw)
+        for f, v in rr.items():
+            r[f"{name}_{f}"] = v
+    assert res["sx"].shape == (N, len(g["ts"]), len(plist), 10)
+    parity.check_against_golden(res.fields, r, fields=["x", "y", "llh", "sllh", "sx", "sy", "sres", "FIM"])
+
+
+def test_block_solver_status_and_nan_pattern_on_step_budget():
+    """maxsteps exhaustion: CV_TOO_MUCH_WORK and NaN from the failing timepoint on, like the lane-group solver."""
+    import amici_b200 as ab
+    g = np.load(os.path.join(GOLD, "massaction_small.npz"))
+    res = _run("massaction_small", g, max_steps=200)
+    assert (res["status"] == -1).all()
+    assert np.isnan(res["llh"]).all() and np.isnan(res["sllh"]).all()
+    assert not np.isnan(res["x"][:, 0]).any() and np.isnan(res["x"][:, -1]).all()
+    from oracle.refsim import RefModel, available
+    if available("massaction_small"):
+        r = RefModel("massaction_small").run(g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], maxsteps=200)
+        np.testing.assert_array_equal(res["status"], r["status"])
+        np.testing.assert_array_equal(np.isnan(res["x"]), np.isnan(r["x"]))
+        np.testing.assert_array_equal(np.isnan(res["sx"]), np.isnan(r["sx"]))
