@@ -130,6 +130,10 @@ def emit_cuda(net: dict) -> str:
         for i, c in pj:
             ptsp.append(i); ptcoef.append(int(c))
         ptptr.append(len(ptsp))
+    rc = []
+    for i in range(nx):
+        assert rowptr[i + 1] > rowptr[i], "every species must take part in a reaction"
+        rc += [(i << 16) | k for k in col[rowptr[i]:rowptr[i + 1]]]
     guard = f"AMICI_B200_MODEL_{name.upper()}_CUH"
     tables = [   # (C type, name, values, comment)
         ("int", "r1", [int(v) for v in net["r1"]], "first reactant of reaction j"),
@@ -139,7 +143,8 @@ def emit_cuda(net: dict) -> str:
         ("int", "pt_ptr", ptptr, "reaction -> (species, stoichiometric coefficient): d xdot / d p_j = coef * v_j / p_j"),
         ("int", "pt_sp", ptsp, ""), ("signed char", "pt_coef", ptcoef, ""),
         ("int", "j_rowptr", rowptr, "J = d xdot / d x in CSR; entry e = sum over its terms of coef * p[rxn] * (partner >= 0 ? x[partner] : 1)"),
-        ("int", "j_col", col, ""), ("int", "jt_ptr", tptr, ""), ("int", "jt_rxn", trxn, ""),
+        ("int", "j_col", col, ""), ("int", "j_rc", rc, "row << 16 | column of entry e (flat sweep over the entries)"),
+        ("int", "jt_ptr", tptr, ""), ("int", "jt_rxn", trxn, ""),
         ("int", "jt_partner", tpart, ""), ("signed char", "jt_coef", [int(c) for c in tcoef], ""),
         ("int", "obs", [int(v) for v in net["obs"]], "observable iy = x[obs[iy]]"),
         ("double", "x0", [repr(float(v)) for v in net["x0"]], "initial state (constants)"),

@@ -13,13 +13,16 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 tag, flags = sys.argv[1], sys.argv[2:]
+tu = "jakstat_adjoint"
+if flags and flags[0].startswith("--tu="):
+    tu, flags = flags[0][5:], flags[1:]
 ge.build_cuda()
 objdir = os.path.join(ROOT, "build", "obj_" + tag)
 os.makedirs(objdir, exist_ok=True)
-src = os.path.join(ge.CSRC, "tu", "jakstat_adjoint.cu")
-obj = os.path.join(objdir, "jakstat_adjoint.o")
+src = os.path.join(ge.CSRC, "tu", tu + ".cu")
+obj = os.path.join(objdir, tu + ".o")
 ge._run(["nvcc"] + ge.NVCC_FLAGS + flags + ["-c", src, "-o", obj])
-objs = [os.path.join(ge.OBJDIR, f) for f in sorted(os.listdir(ge.OBJDIR)) if f.endswith(".o") and f != "jakstat_adjoint.o"] + [obj]
+objs = [os.path.join(ge.OBJDIR, f) for f in sorted(os.listdir(ge.OBJDIR)) if f.endswith(".o") and f != tu + ".o"] + [obj]
 lib = os.path.join(ge.LIBDIR, "libamici_b200_%s.so" % tag)
 ge._run(["nvcc", "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
 print(lib)
