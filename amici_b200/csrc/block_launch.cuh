@@ -8,10 +8,14 @@
 #include "bdf_block.cuh"
 #include "registry.h"
 
+#ifndef AB_BLOCK_MINB
+#define AB_BLOCK_MINB 2
+#endif
+
 namespace amici_b200 {
 
 template <class M, int NCP>
-__global__ void __launch_bounds__(NCP, 2) block_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head,
+__global__ void __launch_bounds__(NCP, AB_BLOCK_MINB) block_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head,
                                                              const Progress pg, double* workspace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockShared<M>& S = *reinterpret_cast<BlockShared<M>*>(smem_raw);
