@@ -425,7 +425,7 @@ def emit_model(spec: ModelSpec) -> str:
             fact.append(f"ok = ok && (fabs(a_{kk}_{kk}) >= 1e-3 * ({expr}));")
         else:
             fact.append(f"ok = ok && (a_{kk}_{kk} != 0.0);")
-        fact.append(f"const double inv_{kk} = 1.0 / a_{kk}_{kk};")
+        fact.append(f"const double inv_{kk} = fast_rcp(a_{kk}_{kk});")
         fact.append(f"LU[{slot(f'inv_{kk}')}] = inv_{kk};")
         for i in rows_k:
             fact.append(f"const double l_{i}_{kk} = a_{i}_{kk} * inv_{kk};")

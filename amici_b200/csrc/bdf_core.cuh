@@ -38,6 +38,12 @@
 #ifndef AB_SYNC_SLEEP
 #define AB_SYNC_SLEEP 40
 #endif
+#ifndef AB_SYNC_EVERY
+#define AB_SYNC_EVERY 1
+#endif
+#ifndef AB_SYNC_JOINWAIT
+#define AB_SYNC_JOINWAIT 1
+#endif
 
 namespace amici_b200 {
 
@@ -1146,7 +1152,7 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
 
     // Step alignment of the warps of one block (G == 32 only): see step_sync_* below.
     volatile int* sync_pos = nullptr;
-    int sync_n = 0, sync_w = 0, sync_gen = 0;
+    int sync_n = 0, sync_w = 0, sync_gen = 0, sync_skip = 1;
 
     bool dense_lu;
 
@@ -1270,6 +1276,7 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
                 if (v != sync_w && pv < m) m = pv;
             }
             if (m != 0x7fffffff) sync_gen = m;
+            sync_skip = AB_SYNC_JOINWAIT ? 1 : AB_SYNC_EVERY;
             if (g.lane == 0) sync_pos[sync_w] = sync_gen;
             __syncwarp();
         }
@@ -1289,6 +1296,10 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
 #if defined(__CUDA_ARCH__)
         if (G == 32 && sync_pos) {
             constexpr int NPH = AB_SYNC_HALF + 1;
+            if (AB_SYNC_EVERY > 1 && phase == 0) {   // align only every AB_SYNC_EVERY-th attempt: the drift in between stays small
+                if (--sync_skip > 0) return;
+                sync_skip = AB_SYNC_EVERY;
+            }
             ++sync_gen;
             if (NPH > 1) sync_gen += (phase - sync_gen % NPH + NPH) % NPH;
             if (g.lane == 0) sync_pos[sync_w] = sync_gen;

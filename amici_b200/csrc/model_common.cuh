@@ -66,6 +66,18 @@ AB_HD double fast_div(double a, double b) {
 #endif
 }
 
+// 1 / b for finite, normal, non-zero b (pivots of the emitted sparse LU): reciprocal seed + two Newton steps, within 1-2 ulp
+AB_HD double fast_rcp(double b) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(r, fma(-b, r, 1.0), r);
+    return fma(r, fma(-b, r, 1.0), r);
+#else
+    return 1.0 / b;
+#endif
+}
+
 AB_HD double ab_max(double a, double b) { return a > b ? a : b; }
 AB_HD double ab_min(double a, double b) { return a < b ? a : b; }
 
