@@ -150,11 +150,12 @@ AB_HD void bcast_state(typename Layout<M, G, C>::Shared& S, const Group<G>& g, c
 // f for column 0, J(y)*s_c + dfdp_c for sensitivity columns (Model_ODE::fxdot / fsxdot,
 // reference src/model_ode.cpp:105-114, :426-450).  ycols = current values of all own columns.
 // Returns false if any output is non-finite (AMICI's check_finite -> recoverable error).
+// same_t: e.spl / e.sspl already hold the splines at this t (later Newton iterations of one step evaluate at the same tn).
 template <class M, int G, int C>
 AB_HD bool model_rhs(typename Layout<M, G, C>::Shared& S, const Group<G>& g, int ncols, double t,
-                     const double (&ycols)[C][M::NX], double (&out)[C][M::NX], ModelEval<M, C>& e) {
+                     const double (&ycols)[C][M::NX], double (&out)[C][M::NX], ModelEval<M, C>& e, const bool same_t = false) {
     bcast_state<M, G, C>(S, g, ycols, e);
-    eval_splines<M, G, C>(S, g, ncols, t, e);
+    if (M::NSPL > 0 && !same_t) eval_splines<M, G, C>(S, g, ncols, t, e);
     double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
     AB_UNROLL
     for (int i = 0; i < (M::NNZ_J > 0 ? M::NNZ_J : 1); ++i) Jv[i] = 0.0;
@@ -735,7 +736,7 @@ struct BdfControl {
             eta = 1.0;
             return;
         }
-        etaq = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
+        etaq = fast_div(1.0, nth_root(6.0 * dsm, L) + 1e-6);
         if (qwait != 0) {
             eta = etaq;
             qprime = q;
@@ -744,15 +745,15 @@ struct BdfControl {
             etaqm1 = 0.0;
             if (q > 1) {
                 const double ddn = self().wrms_max_zn(q, pick(l, q)) * tq[1];
-                etaqm1 = 1.0 / (nth_root(6.0 * ddn, q) + 1e-6);
+                etaqm1 = fast_div(1.0, nth_root(6.0 * ddn, q) + 1e-6);
             }
             etaqp1 = 0.0;
             if (q != QMAX && saved_tq5 != 0.0) {
-                double ratio = h / tau[2], pw = 1.0;
+                double ratio = fast_div(h, tau[2]), pw = 1.0;
                 for (int i = 0; i < L; ++i) pw *= ratio;  // SUNRpowerI(h/tau[2], L)
-                const double cquot = (tq[5] / saved_tq5) * pw;
+                const double cquot = fast_div(tq[5], saved_tq5) * pw;
                 const double dup = self().wrms_max_up(cquot) * tq[3];   // norm of acor - cquot * zn[qmax]
-                etaqp1 = 1.0 / (nth_root(10.0 * dup, L + 1) + 1e-6);
+                etaqp1 = fast_div(1.0, nth_root(10.0 * dup, L + 1) + 1e-6);
             }
             // cvChooseEta (cvodes.c:7935)
             const double etam = ab_max(etaqm1, ab_max(etaq, etaqp1));
@@ -1529,7 +1530,7 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
                         AB_UNROLL
                         for (int r = 0; r < NX; ++r) ycur[c][r] = active(c) ? S.zn[0][r][col(c)] + acor[c][r] : 0.0;
                     }
-                    const bool ok = model_rhs<M, G, C>(S, g, ncols, tn, ycur, delta, e);
+                    const bool ok = model_rhs<M, G, C>(S, g, ncols, tn, ycur, delta, e, m > 0);
                     nfe++;
                     if (!ok) { ret = NLS_RHS_RECVR; break; }
                 }
