@@ -442,19 +442,19 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
         const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c, rd3a = rd2a - rd2b;
         // CVODES returns -7 at the first k that fails; later k are not evaluated there, and their values are unused here
         const bool small = fabs(rd1b) < TINY_ * smax[kk];
-        const double cest1 = small ? 1.0 : -rd3a / rd1b;
+        const double cest1 = small ? 1.0 : -fast_div(rd3a, rd1b);   // |rd1b| >= TINY * smax here
         bad7 = bad7 || small || (cest1 < TINY_ || cest1 > 4.0);
-        const double corr1 = fast_div(fast_div(rd2b, cest1), rr * rr);
+        const double corr1 = fast_div(rd2b, cest1 * (rr * rr));   // (rd2b / cest1) / rr^2 with one quotient; the value is only used if cest1 is in [TINY, 4]
         sigsq[kk] = s[3][kk] + corr1;
     }
     if (bad7) return -7;
     if (sigsq[2] < TINY_) return -8;
     const double ratp = fast_div(sigsq[3], sigsq[2]), ratm = fast_div(sigsq[1], sigsq[2]);
-    const double qfac1 = 0.25 * (q * q - 1.0), qfac2 = 2.0 / (q - 1.0);
+    const double qfac1 = 0.25 * (q * q - 1.0), qfac2 = (q == 3) ? 1.0 : (q == 4) ? (2.0 / 3.0) : 0.5;   // 2 / (q - 1), q in 3..5
     const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
     const double tem = 1.0 - qfac2 * bb;
     if (fabs(tem) < TINY_) return -8;
-    const double rrb = 1.0 / tem;
+    const double rrb = fast_div(1.0, tem);   // |tem| >= TINY
     if (fabs(rrb - rr) > rrtol) return -9;
     if (rr > rrcut) {
         if (kflag == 1) kflag = 4;
