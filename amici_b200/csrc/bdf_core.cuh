@@ -377,14 +377,12 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
         AB_UNROLL
         for (int kk = 1; kk <= 3; kk++)
             qkr[kk] = qc[5][kk] + rr * (qc[4][kk] + rr * rr * (qc[2][kk] + rr * qc[1][kk]));
-        double sqmax = 0.0;
+        // max_k |qkr_k| / ssmax_k < sqtol without the three quotients (only the comparison is needed)
+        bool sq_small = true;
         AB_UNROLL
-        for (int kk = 1; kk <= 3; kk++) {
-            const double saqk = fast_div(fabs(qkr[kk]), ssmax[kk]);
-            if (saqk > sqmax) sqmax = saqk;
-        }
+        for (int kk = 1; kk <= 3; kk++) sq_small = sq_small && (fabs(qkr[kk]) < sqtol * ssmax[kk]);
         AB_SLDET_TRACE(20, rr);
-        if (sqmax < sqtol) {
+        if (sq_small) {
             kflag = 2;
         } else {
             // Newton corrections to improve rr (rolled: this branch is rare)
