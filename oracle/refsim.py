@@ -105,7 +105,12 @@ class RefModel:
         self.p_nominal, self.k_nominal = p, k[: d.nk]
 
     def max_threads(self) -> int:
-        return int(self.lib.ref_max_threads())
+        """Host cores this process may use. Not omp_get_max_threads(): launchers such as torchrun export OMP_NUM_THREADS=1
+        for their workers, which would time the reference on one core; run_simulations takes its thread count explicitly."""
+        try:
+            return max(1, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            return max(1, os.cpu_count() or int(self.lib.ref_max_threads()))
 
     def run(self, ts, p, k, *, plist=None, pscale=None, k_preeq=None, my=None, sigmay=None,
             mz=None, sigmaz=None, rtol=1e-8, atol=1e-12, rtol_fsa=np.nan, atol_fsa=np.nan,
