@@ -27,24 +27,6 @@
 #include "model_common.cuh"
 #include "spline.cuh"
 
-// step alignment (Bdf::step_sync_*): a warp may run ahead of the slowest member by AB_SYNC_SLACK sync points;
-// AB_SYNC_HALF adds a second sync point in the middle of the step
-#ifndef AB_SYNC_SLACK
-#define AB_SYNC_SLACK 0
-#endif
-#ifndef AB_SYNC_HALF
-#define AB_SYNC_HALF 0
-#endif
-#ifndef AB_SYNC_SLEEP
-#define AB_SYNC_SLEEP 40
-#endif
-#ifndef AB_SYNC_EVERY
-#define AB_SYNC_EVERY 1
-#endif
-#ifndef AB_SYNC_JOINWAIT
-#define AB_SYNC_JOINWAIT 1
-#endif
-
 namespace amici_b200 {
 
 // plain-data interface structs: the C ABI's (include/amici_b200.h)
@@ -887,7 +869,6 @@ struct BdfControl {
             pending = false;
             restore = resc = reload = false;
             set_coeffs();
-            if (AB_SYNC_HALF >= 2 && nflag == FIRST_CALL) self().step_sync_arrive(1);
             nflag = self().nls(nflag);
             if (nflag != AB_SUCCESS) {  // cvHandleNFlag
                 ncfn++;
@@ -931,10 +912,8 @@ struct BdfControl {
                 reload = true;
             }
         }
-        if (AB_SYNC_HALF >= 1) self().step_sync_arrive(AB_SYNC_HALF >= 2 ? 2 : 1);
         complete_step();
         prepare_next_step(dsm);
-        if (AB_SYNC_HALF >= 3) self().step_sync_arrive(3);
         if (o.stldet) bdf_stab();
         etamax = 10.0;  // eta_max_es == eta_max_gs == 10
         return AB_SUCCESS;
@@ -1151,7 +1130,7 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
 
     // Step alignment of the warps of one block (G == 32 only): see step_sync_* below.
     volatile int* sync_pos = nullptr;
-    int sync_n = 0, sync_w = 0, sync_gen = 0, sync_skip = 1;
+    int sync_n = 0, sync_w = 0, sync_gen = 0;
 
     bool dense_lu;
 
@@ -1275,7 +1254,6 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
                 if (v != sync_w && pv < m) m = pv;
             }
             if (m != 0x7fffffff) sync_gen = m;
-            sync_skip = AB_SYNC_JOINWAIT ? 1 : AB_SYNC_EVERY;
             if (g.lane == 0) sync_pos[sync_w] = sync_gen;
             __syncwarp();
         }
@@ -1289,18 +1267,10 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
         }
 #endif
     }
-    // phase = index of the sync point inside the step (0 = step start) of AB_SYNC_HALF + 1 points: generations are
-    // congruent to the phase, so that a warp that joins late pairs its step start with the step start of the others
-    AB_HD void step_sync_arrive(const int phase = 0) {
+    AB_HD void step_sync_arrive() {
 #if defined(__CUDA_ARCH__)
         if (G == 32 && sync_pos) {
-            constexpr int NPH = AB_SYNC_HALF + 1;
-            if (AB_SYNC_EVERY > 1 && phase == 0) {   // align only every AB_SYNC_EVERY-th attempt: the drift in between stays small
-                if (--sync_skip > 0) return;
-                sync_skip = AB_SYNC_EVERY;
-            }
             ++sync_gen;
-            if (NPH > 1) sync_gen += (phase - sync_gen % NPH + NPH) % NPH;
             if (g.lane == 0) sync_pos[sync_w] = sync_gen;
             __syncwarp();
             for (;;) {
@@ -1309,8 +1279,8 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
                     const int pv = sync_pos[v];
                     if (pv < m) m = pv;
                 }
-                if (m >= sync_gen - AB_SYNC_SLACK) break;
-                if (AB_SYNC_SLEEP > 0) __nanosleep(AB_SYNC_SLEEP);
+                if (m >= sync_gen) break;
+                __nanosleep(40);
             }
         }
 #endif
