@@ -664,7 +664,29 @@ def run_simulations(model: Model, solver: Solver, edata_list, failfast: bool = T
         return run_batch(model, solver, edata_list)
     if len(edata_list) == 0:
         return []
-    return run_batch(model, solver, ExpDataBatch.from_list(model, edata_list)).views()
+    # The reference lets every ExpData carry its own timepoints, parameter list, scales and pre-equilibration condition
+    # (ConditionContext, reference src/edata.cpp:438-556).  Conditions that agree on those are integrated as one batch;
+    # the results go back in the caller's order.
+    out: list = [None] * len(edata_list)
+    for idx, batch in group_edatas(model, edata_list):
+        views = run_batch(model, solver, batch).views()
+        for i, v in zip(idx, views):
+            out[i] = v
+    return out
+
+
+def group_edatas(model: Model, edatas: Sequence[ExpData | None]) -> list[tuple[list[int], ExpDataBatch]]:
+    """Partition a list of ExpData into batches of conditions that share (timepoints, plist, pscale, pre-equilibration
+    yes/no) — what one ``ab_run_batch`` call requires. Returns ``[(indices into edatas, ExpDataBatch), ...]`` in order of
+    first appearance."""
+    groups: dict = {}
+    for i, e in enumerate(edatas):
+        ts = tuple(model.get_timepoints() if e is None or not e.ts_ else e.ts_)
+        plist = tuple(model.get_parameter_list() if e is None or not e.plist else e.plist)
+        pscale = tuple(int(s) for s in (model.get_parameter_scale() if e is None or not e.pscale else e.pscale))
+        preeq = e is not None and len(e.fixed_parameters_pre_equilibration) > 0
+        groups.setdefault((ts, plist, pscale, preeq), []).append(i)
+    return [(idx, ExpDataBatch.from_list(model, [edatas[i] for i in idx])) for idx in groups.values()]
 
 
 def run_simulation(model: Model, solver: Solver, edata: ExpData | None = None) -> ReturnDataView:

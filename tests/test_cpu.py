@@ -175,6 +175,37 @@ def test_massaction_generated_headers_are_current():
         assert open(path).read() == massaction.emit_cuda(massaction.network(name))
 
 
+def test_group_edatas_partitions_by_condition_context(monkeypatch):
+    """Host logic of the list entry point: conditions are batched by (timepoints, plist, pscale, pre-equilibration), in
+    order of first appearance, without needing the CUDA library."""
+    import amici_b200 as ab
+
+    class _M(ab.Model):
+        def __init__(self):   # a model shell with steadystate's dimensions (no registry / library access)
+            self.name, self.nx, self._np, self._nk, self.ny, self.nytrue, self.nz = "shell", 3, 5, 4, 3, 3, 0
+            self._p, self._k = [1.0] * 5, [1.0] * 4
+            self._pscale = [ab.ParameterScaling.none] * 5
+            self._plist = list(range(5))
+            self._ts = [0.0, 1.0]
+            self._nmaxevent = 10
+    m = _M()
+    es = []
+    for ts, plist, pre in (([0, 1], None, None), ([0, 2], None, None), ([0, 1], None, None), ([0, 1], [1, 2], None),
+                           ([0, 1], None, [1, 1, 1, 1]), ([0, 2], None, None)):
+        e = ab.ExpData(m)
+        e.set_timepoints(ts)
+        if plist:
+            e.plist = plist
+        if pre:
+            e.fixed_parameters_pre_equilibration = pre
+        es.append(e)
+    groups = ab.group_edatas(m, es)
+    assert [idx for idx, _ in groups] == [[0, 2], [1, 5], [3], [4]]
+    assert [len(b) for _, b in groups] == [2, 2, 1, 1]
+    assert list(groups[2][1].plist) == [1, 2] and groups[3][1].k_preeq.shape == (1, 4) and groups[0][1].k_preeq is None
+    assert list(groups[1][1].ts) == [0.0, 2.0]
+
+
 def test_maxsteps_status(built):
     """Exhausting the step budget inside a call gives CV_TOO_MUCH_WORK (-1) and NaN outputs from that timepoint on."""
     g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))

@@ -280,6 +280,54 @@ def test_list_of_expdata_entry_point():
     np.testing.assert_allclose(single.x, rdatas[0].x, rtol=1e-12)
 
 
+def test_ragged_expdata_list_matches_reference():
+    """Like the reference, every ExpData of the list may have its own timepoints, parameter list and pre-equilibration
+    condition (ConditionContext): the engine groups compatible conditions into batches and returns results in list order."""
+    import amici_b200 as ab
+    from oracle.refsim import RefModel, available
+    if not available("steadystate"):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    m = ab.get_model("steadystate")
+    m.set_timepoints(g["ts"])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    s.set_newton_max_steps(50)
+    grids = [np.linspace(0, 10, 11), np.array([0.0, 0.5, 2.0, 7.5]), np.linspace(0, 10, 11), np.array([1.0, 3.0])]
+    plists = [None, [0, 2, 4], None, [1]]
+    preeq = [None, None, [0.2, 0.5, 0.9, 1.5], None]
+    edatas, rng = [], np.random.default_rng(0)
+    for i in range(4):
+        e = ab.ExpData(m)
+        e.set_timepoints(grids[i])
+        e.free_parameters = list(g["p"][i])
+        e.fixed_parameters = list(g["k"][i])
+        if plists[i] is not None:
+            e.plist = plists[i]
+        if preeq[i] is not None:
+            e.fixed_parameters_pre_equilibration = preeq[i]
+        e.set_measurements(rng.uniform(0.2, 1.0, (len(grids[i]), 3)))
+        e.set_noise_scales(np.full((len(grids[i]), 3), 0.1))
+        edatas.append(e)
+    assert len(ab.group_edatas(m, edatas)) == 4
+    rdatas = ab.run_simulations(m, s, edatas + [edatas[0]])
+    assert len(rdatas) == 5
+    ref = RefModel("steadystate")
+    for i, (e, r) in enumerate(zip(edatas, rdatas)):
+        pl = plists[i] if plists[i] is not None else list(range(5))
+        rr = ref.run(grids[i], g["p"][i:i + 1], g["k"][i:i + 1], my=e.get_measurements().reshape(1, -1, 3),
+                     sigmay=e.get_noise_scales().reshape(1, -1, 3), plist=pl, sensi_order=1, newton_maxsteps=50,
+                     k_preeq=None if preeq[i] is None else np.array([preeq[i]]))
+        assert r.status == rr["status"][0] == 0
+        assert r["sx"].shape == (len(grids[i]), len(pl), 3)
+        np.testing.assert_allclose(r.x, rr["x"][0], rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose(r.llh, rr["llh"][0], rtol=1e-6)
+        np.testing.assert_allclose(r.sllh, rr["sllh"][0], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(rdatas[4].x, rdatas[0].x, rtol=0, atol=0)
+
+
 def test_objective_reduction_kernel():
     import ctypes as C
     import torch
