@@ -364,13 +364,18 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
         AB_UNROLL
         for (int kk = 1; kk <= 3; kk++) sq_small = sq_small && (fabs(qkr[kk]) < sqtol * ssmax[kk]);
         AB_SLDET_TRACE(20, rr);
+        AB_SLDET_TRACE(sq_small ? 21 : 22, rr);
         if (sq_small) {
             kflag = 2;
         } else {
-            // Newton corrections to improve rr (rolled: this branch is rare)
-            double sqmin = 0.0;
+            // Newton corrections to improve rr.  This is the common branch (JAK-STAT: 59 % of the calls that get here), so
+            // the nine quotients |qjk| / ssmax_j per sweep are products with three reciprocals formed once.
+            double sqmin = 0.0, inv_ssmax[4];
+            AB_UNROLL
+            for (int j = 1; j <= 3; j++) inv_ssmax[j] = fast_div(1.0, ssmax[j]);
             AB_NOUNROLL
             for (int it = 1; it <= 3; it++) {
+                AB_SLDET_TRACE(23, rr);
                 double rrc[4], sqmx[4], qjk[4][4];
                 AB_UNROLL
                 for (int kk = 1; kk <= 3; kk++) {
@@ -386,7 +391,7 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
                     AB_UNROLL
                     for (int j = 1; j <= 3; j++) {
                         qjk[j][kk] = qc[5][j] + sv * (qc[4][j] + sv * sv * (qc[2][j] + sv * qc[1][j]));
-                        const double saqj = fast_div(fabs(qjk[j][kk]), ssmax[j]);
+                        const double saqj = fabs(qjk[j][kk]) * inv_ssmax[j];
                         if (saqj > sqmaxk) sqmaxk = saqj;
                     }
                     sqmx[kk] = sqmaxk;
@@ -413,6 +418,7 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
     // Only a result > 3 makes cvBDFStab act, and that needs rr > rrcut (the promotion of kflag at the end): with
     // rr <= rrcut every remaining path returns a value <= 3, so the rest can be skipped.
     if (!(rr > rrcut)) return kflag;
+    AB_SLDET_TRACE(30, rr);
     bool bad7 = false;
     AB_UNROLL
     for (int kk = 1; kk <= 3; kk++) {

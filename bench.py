@@ -166,6 +166,8 @@ def main():
     solver.set_relative_tolerance(RTOL)
     solver.set_absolute_tolerance(ATOL)
     solver.set_sensitivity_order(ab.SensitivityOrder.first)
+    if os.environ.get("BENCH_NO_STLDET"):   # experiment only: upper bound of what cvBDFStab costs (not the reference's default)
+        solver.set_stability_limit_flag(False)
     n = args.n_conditions
     p, k, noise = synthetic_inputs(n, 2 + 1000 * rank, np.array(model.get_free_parameters()), np.array(model.get_fixed_parameters()))
     # noise-free observables of every condition (one un-timed solve without sensitivities), then add noise
