@@ -398,6 +398,8 @@ class ExpData:
         self.fixed_parameters_pre_equilibration: list[float] = []   # non-empty = pre-equilibrate (edata.h)
         self.pscale: list = []
         self.plist: list[int] = []
+        self.x0: list[float] = []    # initial state override (edata.h); empty = the model's x0(p, k)
+        self.sx0: list[float] = []   # [nplist][nx] initial sensitivities on the parameter scale; empty = the model's
         n = len(self.ts_) * self._ny
         self._my = np.full(n, np.nan)
         self._sigmay = np.full(n, np.nan)
@@ -450,7 +452,8 @@ class ExpDataBatch:
     ``ExpData`` or accepts it directly, which avoids one Python object per condition for large batches.
     """
 
-    def __init__(self, ts, p, k, my=None, sigmay=None, plist=None, pscale=None, k_preeq=None, mz=None, sigmaz=None):
+    def __init__(self, ts, p, k, my=None, sigmay=None, plist=None, pscale=None, k_preeq=None, mz=None, sigmaz=None,
+                 x0=None, sx0=None):
         self.ts = np.ascontiguousarray(ts, dtype=np.float64)
         self.p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
         self.k = np.ascontiguousarray(np.atleast_2d(k), dtype=np.float64)
@@ -461,6 +464,9 @@ class ExpDataBatch:
         self.k_preeq = None if k_preeq is None else np.ascontiguousarray(np.atleast_2d(k_preeq), dtype=np.float64)
         self.mz = None if mz is None else np.ascontiguousarray(mz, dtype=np.float64)
         self.sigmaz = None if sigmaz is None else np.ascontiguousarray(sigmaz, dtype=np.float64)
+        # ExpData::x0 / sx0: initial state (and its sensitivities, on the parameter scale) instead of the model's
+        self.x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        self.sx0 = None if sx0 is None else np.ascontiguousarray(sx0, dtype=np.float64)
 
     def __len__(self): return self.p.shape[0]
 
@@ -507,7 +513,22 @@ class ExpDataBatch:
                         raise RuntimeError("amici_b200: ExpData was created with a different n_max_event than the model has now")
                     mz[i] = e._mz.reshape(nme, model.nz)
                     sz[i] = e._sigmaz.reshape(nme, model.nz)
-        return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq, mz=mz, sigmaz=sz)
+        x0 = sx0 = None
+        has_x0 = [e is not None and len(e.x0) > 0 for e in edatas]
+        has_sx0 = [e is not None and len(e.sx0) > 0 for e in edatas]
+        if any(has_x0) != all(has_x0) or any(has_sx0) != all(has_sx0):
+            raise RuntimeError("amici_b200: either all or none of the conditions of one batch give x0 / sx0")
+        if any(has_x0):
+            x0 = np.array([e.x0 for e in edatas], dtype=np.float64)
+            if x0.shape != (N, model.nx):
+                raise RuntimeError("Dimension mismatch. Size of x0 does not match number of model states.")
+        if any(has_sx0):
+            sx0 = np.array([np.asarray(e.sx0, dtype=np.float64).reshape(-1) for e in edatas])
+            if sx0.shape != (N, len(plist) * model.nx):
+                raise RuntimeError("Dimension mismatch. Size of sx0 does not match number of model states * number of "
+                                   "parameter selected for sensitivities.")
+            sx0 = sx0.reshape(N, len(plist), model.nx)
+        return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq, mz=mz, sigmaz=sz, x0=x0, sx0=sx0)
 
 
 _RDATA_ALIASES = {"num_rhs_evals": "numrhsevals", "num_err_test_fails": "numerrtestfails",
@@ -610,6 +631,15 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
         b.my = batch.my.ctypes.data_as(dp)
     if batch.sigmay is not None:
         b.sigmay_in = batch.sigmay.ctypes.data_as(dp)
+    if batch.x0 is not None:
+        if batch.x0.shape != (N, d["nx"]):
+            raise RuntimeError("Dimension mismatch. Size of x0 does not match number of model states.")
+        b.x0_in = batch.x0.ctypes.data_as(dp)
+    if batch.sx0 is not None and opts.sensi:
+        if batch.sx0.shape != (N, len(plist), d["nx"]):
+            raise RuntimeError("Dimension mismatch. Size of sx0 does not match number of model states * number of "
+                               "parameter selected for sensitivities.")
+        b.sx0_in = batch.sx0.ctypes.data_as(dp)
     if batch.k_preeq is not None:
         if batch.k_preeq.shape != (N, d["nk"]):
             raise RuntimeError("amici_b200: k_preeq shape does not match the model")
@@ -685,7 +715,8 @@ def group_edatas(model: Model, edatas: Sequence[ExpData | None]) -> list[tuple[l
         plist = tuple(model.get_parameter_list() if e is None or not e.plist else e.plist)
         pscale = tuple(int(s) for s in (model.get_parameter_scale() if e is None or not e.pscale else e.pscale))
         preeq = e is not None and len(e.fixed_parameters_pre_equilibration) > 0
-        groups.setdefault((ts, plist, pscale, preeq), []).append(i)
+        init = (e is not None and len(e.x0) > 0, e is not None and len(e.sx0) > 0)
+        groups.setdefault((ts, plist, pscale, preeq, init), []).append(i)
     return [(idx, ExpDataBatch.from_list(model, [edatas[i] for i in idx])) for idx in groups.values()]
 
 

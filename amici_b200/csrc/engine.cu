@@ -307,6 +307,7 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
     const FieldDesc fields[] = {
         AB_F(p, D, d.np, true), AB_F(k, D, d.nk, true), AB_F(my, D, nt * ny, true), AB_F(sigmay_in, D, nt * ny, true),
         AB_F(k_preeq, D, d.nk, true), AB_F(mz, D, nme * nz, true), AB_F(sigmaz_in, D, nme * nz, true),
+        AB_F(x0_in, D, nx, true), AB_F(sx0_in, D, q * nx, true),
         AB_F(status, I, 1, false), AB_F(llh, D, 1, false), AB_F(chi2, D, 1, false), AB_F(sllh, D, q, false),
         AB_F(x, D, nt * nx, false), AB_F(sx, D, nt * q * nx, false), AB_F(y, D, nt * ny, false),
         AB_F(sy, D, nt * q * ny, false), AB_F(sigmay, D, nt * ny, false), AB_F(ssigmay, D, nt * q * ny, false),

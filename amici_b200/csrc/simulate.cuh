@@ -88,8 +88,7 @@ struct Simulation {
             if (!bdf.active(c)) continue;
             const int cc = bdf.col(c);
             double v[NX];
-            if (cc == 0) M::x0(S.p, S.k, v);
-            else M::sx0(S.ip_of_col[cc], S.p, S.k, v);
+            initial_column(cc, v);
             AB_UNROLL
             for (int r = 0; r < NX; ++r) S.zn[0][r][cc] = v[r];
             AB_UNROLL
@@ -97,6 +96,22 @@ struct Simulation {
                 spline_build_column<M, NCOLS>(S.spl, is, cc, cc == 0 ? -1 : S.ip_of_col[cc], S.p, S.k);
         }
         g.sync();
+    }
+
+    // Model::fx0 / fsx0 with the ExpData overrides (reference src/model.cpp:1907-1966; ConditionContext src/edata.cpp:472-490):
+    // a given sx0 is on the parameter scale of pscale and is un-scaled with the chain-rule factor (src/model.cpp:986-1024)
+    AB_HD void initial_column(const int cc, double (&v)[NX]) const {
+        if (cc == 0) {
+            M::x0(S.p, S.k, v);
+            if (b.x0_in)
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) v[r] = b.x0_in[(size_t)n * NX + r];
+        } else {
+            M::sx0(S.ip_of_col[cc], S.p, S.k, v);
+            if (b.sx0_in)
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) v[r] = b.sx0_in[((size_t)n * nplist + (cc - 1)) * NX + r] / S.pcoef[cc];
+        }
     }
 
     AB_HD double chain(double v, double pc) const { return v != 0.0 ? v * pc : v; }
@@ -631,7 +646,7 @@ struct Simulation {
                 // are integrated along unless they come from the Newton solve afterwards (:872-920, :1023-1033)
                 if (newton_on && g.lane == 0) {
                     double v[NX];
-                    M::x0(S.p, S.k, v);
+                    initial_column(0, v);
                     for (int r = 0; r < NX; ++r) S.zn[0][r][0] = v[r];
                 }
                 g.sync();

@@ -19,7 +19,7 @@ class DeviceBatch:
         self.model, self.solver = model, solver
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.opts = solver._options(model.t0(), model)
-        d = model.dims()
+        d = dict(model.dims(), nz=model.nz, nmaxevent=self.opts.nmaxevent)
         N, nt = len(batch), len(batch.ts)
         plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist
         pscale = (np.asarray([int(s) for s in model.get_parameter_scale()], dtype=np.int32)
@@ -33,6 +33,13 @@ class DeviceBatch:
             self.host_inputs["my"] = batch.my
         if batch.sigmay is not None:
             self.host_inputs["sigmay_in"] = batch.sigmay
+        for name, arr in (("k_preeq", batch.k_preeq), ("mz", batch.mz), ("sigmaz_in", batch.sigmaz)):
+            if arr is not None:
+                self.host_inputs[name] = arr
+        if getattr(batch, "x0", None) is not None:
+            self.host_inputs["x0_in"] = batch.x0
+        if getattr(batch, "sx0", None) is not None and self.opts.sensi:
+            self.host_inputs["sx0_in"] = batch.sx0
         self.inputs = {k_: torch.as_tensor(v).to(dev) for k_, v in self.host_inputs.items()}
         likelihood_only = self.opts.reporting == int(RDataReporting.likelihood)
         lk = {"status", "llh", "chi2", "sllh", "numsteps", "numrhsevals", "numerrtestfails", "numnonlinsolvconvfails", "order"}
@@ -41,6 +48,8 @@ class DeviceBatch:
             if fields is not None and name not in fields and name != "status":
                 continue
             if likelihood_only and name not in lk:
+                continue
+            if name in _capi.PREEQ_FIELDS and batch.k_preeq is None:
                 continue
             shape = shp(d, N, nt, q)
             if int(np.prod(shape)) == 0:

@@ -69,6 +69,8 @@ typedef struct ab_batch {
     const double* k_preeq;   /* [N][nk]         ExpData::fixed_parameters_pre_equilibration; NULL = no pre-equilibration */
     const double* mz;        /* [N][nmaxevent][nz]  ExpData event measurements, NaN = missing; may be NULL */
     const double* sigmaz_in; /* [N][nmaxevent][nz]  ExpData event noise scales, NaN = model sigma; may be NULL */
+    const double* x0_in;     /* [N][nx]         ExpData::x0, initial state instead of the model's x0(p, k); NULL = model's (reference src/edata.cpp:472-480) */
+    const double* sx0_in;    /* [N][nplist][nx] ExpData::sx0 on the parameter scale given by pscale; NULL = model's (src/edata.cpp:482-490, src/model.cpp:986-1024) */
     /* ---- outputs (ReturnData fields; any may be NULL) ---- */
     int* status;             /* [N]                                  */
     double* llh;             /* [N]                                  */

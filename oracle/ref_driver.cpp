@@ -103,6 +103,9 @@ extern "C" int ref_run(ref_options const* o, ref_batch* b) {
                                                              b->k_preeq + (size_t)(i + 1) * nk);
             e->pscale = pscale;
             e->plist = plist;
+            if (b->x0_in) e->x0.assign(b->x0_in + (size_t)i * nx, b->x0_in + (size_t)(i + 1) * nx);
+            if (b->sx0_in && npl > 0)
+                e->sx0.assign(b->sx0_in + (size_t)i * npl * nx, b->sx0_in + (size_t)(i + 1) * npl * nx);
             if (b->my) {
                 size_t n = (size_t)nt * nyt;
                 e->set_measurements(std::vector<realtype>(b->my + i * n, b->my + (i + 1) * n));

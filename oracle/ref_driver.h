@@ -55,6 +55,8 @@ typedef struct {
     const double* sigmay_in; /* [N][nt][nytrue] or NULL (NaN = model)  */
     const double* mz;        /* [N][nmaxevent][nztrue] or NULL         */
     const double* sigmaz_in; /* [N][nmaxevent][nztrue] or NULL         */
+    const double* x0_in;     /* [N][nx] ExpData::x0 or NULL            */
+    const double* sx0_in;    /* [N][nplist][nx] ExpData::sx0 or NULL   */
     /* ---- outputs (any may be NULL) ---- */
     int* status;             /* [N]                         */
     double* llh;             /* [N]                         */

@@ -175,6 +175,34 @@ def test_massaction_generated_headers_are_current():
         assert open(path).read() == massaction.emit_cuda(massaction.network(name))
 
 
+def test_emulation_initial_state_overrides_match_reference(built):
+    """ExpData::x0 / sx0 (reference src/edata.cpp:472-490): the given initial state replaces the model's, the given
+    sensitivities are on the parameter scale (log10 here) and are un-scaled with the chain-rule factor."""
+    from oracle import refsim
+    if not refsim.available("steadystate"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    N = 4
+    rng = np.random.default_rng(7)
+    x0 = rng.uniform(0.05, 1.0, (N, 3))
+    sx0 = rng.normal(0, 0.3, (N, 5, 3))
+    pscale = np.full(5, 2, dtype=np.int32)
+    p = np.log10(g["p"][:N])
+    dims = MODEL_DIMS["steadystate"]
+    b, out, keep = _capi.make_batch(dims, g["ts"], p, g["k"][:N], pscale=pscale, my=g["my"][:N], sigmay=g["sigmay_in"][:N], x0=x0, sx0=sx0)
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
+    assert _emul(built).emul_run(b"steadystate", C.byref(o), C.byref(b)) == 0
+    r = refsim.RefModel("steadystate").run(g["ts"], p, g["k"][:N], pscale=pscale, my=g["my"][:N], sigmay=g["sigmay_in"][:N],
+                                           x0=x0, sx0=sx0, rtol=1e-12, atol=1e-16, maxsteps=200000)
+    np.testing.assert_array_equal(out["status"], 0)
+    np.testing.assert_allclose(out["x0"], x0, rtol=0, atol=0)
+    np.testing.assert_allclose(out["sx0"], r["sx0"], rtol=1e-13)
+    np.testing.assert_allclose(out["sx0"], sx0, rtol=1e-13)
+    np.testing.assert_allclose(out["x"], r["x"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(out["sx"], r["sx"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(out["sllh"], r["sllh"], rtol=1e-4, atol=1e-6)
+
+
 def test_group_edatas_partitions_by_condition_context(monkeypatch):
     """Host logic of the list entry point: conditions are batched by (timepoints, plist, pscale, pre-equilibration), in
     order of first appearance, without needing the CUDA library."""

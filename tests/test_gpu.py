@@ -328,6 +328,51 @@ def test_ragged_expdata_list_matches_reference():
     np.testing.assert_allclose(rdatas[4].x, rdatas[0].x, rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("model", ["steadystate", "massaction_small"])
+def test_initial_state_overrides_match_reference(model):
+    """ExpData::x0 / sx0 through the C ABI (x0_in / sx0_in), lane-group and block solver, log10 parameter scale."""
+    import amici_b200 as ab
+    from oracle.refsim import RefModel, available
+    if not available(model):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, model + ".npz"))
+    N, npar = g["p"].shape
+    nx = g["klu_x"].shape[-1]
+    rng = np.random.default_rng(8)
+    x0 = rng.uniform(0.2, 1.2, (N, nx))
+    sx0 = rng.normal(0, 0.2, (N, npar, nx))
+    pscale = np.full(npar, 2, dtype=np.int32)
+    p = np.log10(g["p"])
+    m = ab.get_model(model)
+    m.set_timepoints(g["ts"])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    my = np.nan_to_num(g["my"], nan=0.4)
+    batch = ab.ExpDataBatch(g["ts"], p, g["k"], my=my, sigmay=np.full_like(my, 0.1), pscale=pscale, x0=x0, sx0=sx0)
+    res = ab.run_simulations(m, s, batch)
+    r = RefModel(model).run(g["ts"], p, g["k"], pscale=pscale, my=my, sigmay=np.full_like(my, 0.1), x0=x0, sx0=sx0,
+                            rtol=1e-12, atol=1e-16, maxsteps=200000)
+    assert (res["status"] == 0).all() and (r["status"] == 0).all()
+    np.testing.assert_array_equal(res["x0"], x0)
+    np.testing.assert_allclose(res["sx0"], sx0, rtol=1e-13)
+    np.testing.assert_allclose(res["x"], r["x"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(res["sx"], r["sx"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(res["llh"], r["llh"], rtol=1e-6)
+    np.testing.assert_allclose(res["sllh"], r["sllh"], rtol=1e-4, atol=1e-6)
+    # the list entry point carries the overrides too
+    e = ab.ExpData(m)
+    e.set_timepoints(g["ts"])
+    e.free_parameters, e.fixed_parameters, e.pscale = list(p[0]), list(g["k"][0]), list(pscale)
+    e.x0, e.sx0 = list(x0[0]), list(sx0[0].reshape(-1))
+    e.set_measurements(my[0])
+    e.set_noise_scales(np.full_like(my[0], 0.1))
+    one = ab.run_simulations(m, s, [e])[0]
+    np.testing.assert_allclose(one.x, res["x"][0], rtol=1e-12)
+    np.testing.assert_allclose(one.sllh, res["sllh"][0], rtol=1e-10)
+
+
 def test_objective_reduction_kernel():
     import ctypes as C
     import torch
