@@ -618,6 +618,10 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
     plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist
     pscale = np.asarray([int(s) for s in model.get_parameter_scale()], dtype=np.int32) if batch.pscale is None else batch.pscale
     opts = solver._options(model.t0(), model)
+    if not np.all(np.isfinite(batch.ts)):
+        # t = inf output points need the reference's post-equilibration (SteadyStateProblem after the last finite timepoint,
+        # reference src/forwardproblem.cpp:376-387), which is not part of this engine yet: fail loudly instead of integrating forever
+        raise RuntimeError("amici_b200: non-finite timepoints (post-equilibration) are not supported")
     q = len(plist) if opts.sensi else 0
     d = dict(model.dims(), nz=model.nz, nmaxevent=opts.nmaxevent)
     b = _capi.BatchView(N=N, nt=nt, nplist=len(plist))

@@ -90,6 +90,7 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
     if (b->N < 0 || b->nt < 0 || b->nplist < 0) { g_err = "negative size"; return AB_E_BAD_ARGUMENT; }
     if (!b->ts && b->nt > 0) { g_err = "ts is NULL"; return AB_E_BAD_ARGUMENT; }
     if (!b->p || !b->status) { g_err = "p/status is NULL"; return AB_E_BAD_ARGUMENT; }
+    if (!std::isfinite(o->t0)) { g_err = "t0 must be finite"; return AB_E_BAD_ARGUMENT; }
     if (o->sensi >= 1 && b->nplist > 0 && !b->plist) { g_err = "plist is NULL"; return AB_E_BAD_ARGUMENT; }
     if (o->sensi >= 1 && o->ism != 1) { g_err = "only simultaneous forward sensitivities are implemented"; return AB_E_UNSUPPORTED; }
     if (!(o->rtol >= 0) || !(o->atol >= 0)) { g_err = "negative tolerance"; return AB_E_BAD_ARGUMENT; }
@@ -299,6 +300,11 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
     if (rc != AB_OK) return rc;
     if (kernel_ms) *kernel_ms = 0.f;
     if (hb->N == 0) return AB_OK;
+    for (int it = 0; it < hb->nt; ++it)
+        if (!std::isfinite(hb->ts[it])) {   // t = inf needs post-equilibration (reference src/forwardproblem.cpp:376-387)
+            g_err = "non-finite timepoints (post-equilibration) are not supported";
+            return AB_E_UNSUPPORTED;
+        }
     const ab_dims& d = e->dims;
     const size_t N = hb->N, nt = hb->nt, q = (opt->sensi >= 1) ? hb->nplist : 0;
     const size_t nx = d.nx, ny = d.ny, nz = d.nz, D = sizeof(double), I = sizeof(int);

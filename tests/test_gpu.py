@@ -373,6 +373,15 @@ def test_initial_state_overrides_match_reference(model):
     np.testing.assert_allclose(one.sllh, res["sllh"][0], rtol=1e-10)
 
 
+def test_non_finite_timepoints_are_rejected():
+    """t = inf outputs (post-equilibration) are not implemented: the call fails loudly instead of integrating forever."""
+    import amici_b200 as ab
+    m = ab.get_model("steadystate")
+    m.set_timepoints([0.0, 1.0, np.inf])
+    with pytest.raises(RuntimeError, match="post-equilibration"):
+        ab.run_simulation(m, m.create_solver())
+
+
 def test_objective_reduction_kernel():
     import ctypes as C
     import torch
