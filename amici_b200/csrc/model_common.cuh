@@ -52,15 +52,18 @@ enum : int { AB_PSCALE_NONE = 0, AB_PSCALE_LN = 1, AB_PSCALE_LOG10 = 2 };
 using std::isfinite;
 #endif
 
-// a / b for finite, normal, non-zero b: reciprocal seed + one Newton step + one residual correction
-// (6 instructions instead of the ~25 of the IEEE division sequence; result within 1-2 ulp). Host builds divide.
+// a / b for finite, normal, non-zero b: reciprocal seed + one Newton step, then the product — 4 instructions, relative
+// error ~2^-40 (1e-12).  Every use is in step-control arithmetic (error weights, BDF coefficients, step-size and order
+// heuristics, stability-limit detection), where a relative perturbation of 1e-12 is four orders below the integration
+// tolerance; the IEEE sequence is ~25 instructions plus a slow-path call, and with ~45 divisions per step the code size
+// matters as much as the count (the step loop competes for the SM's instruction cache, DESIGN.md §2.6: dropping the
+// residual-correction step, 2 more instructions per site, was worth +3.7 %).  Host builds divide.
 AB_HD double fast_div(double a, double b) {
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(r, fma(-b, r, 1.0), r);   // seed is good to ~2^-20 (rcp.approx.ftz.f64 reads the upper 32 bits): 2^-40 here
-    const double q = a * r;            // the residual correction below squares the remaining error: ~2^-80
-    return fma(r, fma(-b, q, a), q);
+    return a * r;
 #else
     return a / b;
 #endif
