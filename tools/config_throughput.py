@@ -58,6 +58,9 @@ if __name__ == "__main__":
     ts = np.concatenate([[0.0], 4 * np.logspace(-6, 6, 50)])
     run("configs[0] Robertson, 4096 log-uniform draws, forward simulation", "robertson_ode", ts,
         np.tile(p0, (4096, 1)) * 10 ** rng.uniform(-1, 1, (4096, 3)), np.full((4096, 1), 0.9), sensi=False)
+    nbig = 262144   # the 4096-draw batch of configs[0] occupies 128 warps of the chip's ~9,500: same workload, 64x the draws
+    run("configs[0] workload at 262,144 draws (one thread per condition fills the chip)", "robertson_ode", ts,
+        np.tile(p0, (nbig, 1)) * 10 ** rng.uniform(-1, 1, (nbig, 3)), np.full((nbig, 1), 0.9), sensi=False)
     p0, k0 = nominal("steadystate")
     rng = np.random.default_rng(3)
     p = np.tile(p0, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, 5))
