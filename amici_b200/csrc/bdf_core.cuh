@@ -450,6 +450,123 @@ AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const i
     return kflag;
 }
 
+// cvSLdet with the three orders k = 1..3 in three LANES of the group instead of three unrolled copies in every lane.
+// The stability test is a long chain of dependent scalar FP64 operations that every lane would execute identically; it
+// sits on the pace-setting path of the aligned warps (a quarter of the JAK-STAT step time with the serial form).  Lane l
+// owns order k = l % 4 + 1 (lanes with l % 4 == 3 duplicate k = 1), lanes 0..2 are the shuffle sources; the arithmetic per
+// order is the serial function's, the cross-order steps (elimination, candidate scan, final ratios) exchange the few values
+// they need by shuffles.  Same return values as bdf_sldet.
+template <int G>
+AB_HD int bdf_sldet_lanes(const Group<G>& g, const double (&ssdat)[5][8], const int ss_head, const int q) {
+    const double TINY_ = 1e-10;
+    const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
+    const int k = ((g.lane & 3) == 3) ? 1 : (g.lane & 3) + 1;
+    double s[6], rat[5];
+    AB_UNROLL
+    for (int i = 1; i <= 5; ++i) {
+        int idx = ss_head + i - 1;
+        idx = idx >= 5 ? idx - 5 : idx;
+        s[i] = ssdat[idx][k];
+        if (i <= 4) rat[i] = ssdat[idx][4 + k];
+    }
+    double smink = s[1], smaxk = 0.0;
+    AB_UNROLL
+    for (int i = 1; i <= 5; i++) {
+        smink = ab_min(smink, s[i]);
+        smaxk = ab_max(smaxk, s[i]);
+    }
+    if (g.any(smink < TINY_ * smaxk)) return -1;
+    const double smax = smaxk, ssmax = smaxk * smaxk;
+    double sumrat = 0.0, sumrsq = 0.0;
+    AB_UNROLL
+    for (int i = 1; i <= 4; i++) {
+        sumrat += rat[i];
+        sumrsq += rat[i] * rat[i];
+    }
+    const double rav = 0.25 * sumrat;
+    const double vrat = fabs(0.25 * sumrsq - rav * rav);
+    const double qc5 = s[1] * s[3] - s[2] * s[2];
+    const double qc4 = s[2] * s[3] - s[1] * s[4];
+    const double qc2 = s[2] * s[5] - s[3] * s[4];
+    const double qc1 = s[4] * s[4] - s[3] * s[5];
+    const double vmin = g.min(vrat), vmax = g.max(vrat);
+    double rr = 0.0;
+    int kflag = 0;
+    if (vmin < vrrtol * vrrtol) {
+        if (vmax > vrrt2 * vrrt2) return -2;
+        rr = (g.bcast(rav, 0) + g.bcast(rav, 1) + g.bcast(rav, 2)) / 3.0;
+        if (g.max(fabs(rav - rr)) > vrrt2) return -3;
+        kflag = 1;
+    } else {
+        // eliminate with column 1, then column 2; rr from column 3 (rows 1, 2, 4, 5; row 3 is zero)
+        const double a1 = g.bcast(qc1, 0), a2 = g.bcast(qc2, 0), a4 = g.bcast(qc4, 0), a5 = g.bcast(qc5, 0);
+        if (fabs(a1) < TINY_ * g.bcast(ssmax, 0)) return -4;
+        const double tem1 = fast_div(qc1, a1);
+        const double e2 = qc2 - tem1 * a2, e4 = qc4 - tem1 * a4, e5 = qc5 - tem1 * a5;
+        const double b2 = g.bcast(e2, 1), b4 = g.bcast(e4, 1), b5 = g.bcast(e5, 1);
+        if (fabs(b2) < TINY_ * g.bcast(ssmax, 1)) return -4;
+        const double tem2 = fast_div(e2, b2);
+        const double f4 = e4 - tem2 * b4, f5 = e5 - tem2 * b5;
+        const double c4 = g.bcast(f4, 2), c5 = g.bcast(f5, 2);
+        if (fabs(c4) < TINY_ * g.bcast(ssmax, 2)) return -4;
+        rr = -fast_div(c5, c4);
+        if (rr < TINY_ || rr > 100.0) return -5;
+        double qkr = qc5 + rr * (qc4 + rr * rr * (qc2 + rr * qc1));
+        if (!g.any(!(fabs(qkr) < sqtol * ssmax))) {
+            kflag = 2;
+        } else {
+            const double inv_ssmax = fast_div(1.0, ssmax);
+            double sqmin = 0.0;
+            AB_NOUNROLL
+            for (int it = 1; it <= 3; it++) {
+                const double qp = qc4 + rr * rr * (3.0 * qc2 + rr * 4.0 * qc1);
+                double drr = 0.0;
+                if (fabs(qp) > TINY_ * ssmax) drr = -fast_div(qkr, qp);
+                const double rrc = rr + drr;
+                const double sv1 = g.bcast(rrc, 0), sv2 = g.bcast(rrc, 1), sv3 = g.bcast(rrc, 2);
+                const double p1 = qc5 + sv1 * (qc4 + sv1 * sv1 * (qc2 + sv1 * qc1));
+                const double p2 = qc5 + sv2 * (qc4 + sv2 * sv2 * (qc2 + sv2 * qc1));
+                const double p3 = qc5 + sv3 * (qc4 + sv3 * sv3 * (qc2 + sv3 * qc1));
+                const double m1 = g.max(fabs(p1) * inv_ssmax), m2 = g.max(fabs(p2) * inv_ssmax), m3 = g.max(fabs(p3) * inv_ssmax);
+                sqmin = m1 + 1.0;
+                int kmin = 1;
+                if (m1 < sqmin) { kmin = 1; sqmin = m1; }
+                if (m2 < sqmin) { kmin = 2; sqmin = m2; }
+                if (m3 < sqmin) { kmin = 3; sqmin = m3; }
+                rr = (kmin == 1) ? sv1 : (kmin == 2) ? sv2 : sv3;
+                if (sqmin < sqtol) {
+                    kflag = 3;
+                    break;
+                }
+                qkr = (kmin == 1) ? p1 : (kmin == 2) ? p2 : p3;
+            }
+            if (sqmin > sqtol) return -6;
+        }
+    }
+    if (!(rr > rrcut)) return kflag;   // only a result > 3 acts, and that needs rr > rrcut
+    const double rsa = s[1], rsb = s[2] * rr, rsc = s[3] * rr * rr;
+    const double rsd = s[4] * rr * rr * rr;
+    const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
+    const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c, rd3a = rd2a - rd2b;
+    const bool small = fabs(rd1b) < TINY_ * smax;
+    const double cest1 = small ? 1.0 : -fast_div(rd3a, rd1b);
+    if (g.any(small || cest1 < TINY_ || cest1 > 4.0)) return -7;
+    const double sigsq = s[3] + fast_div(rd2b, cest1 * (rr * rr));
+    const double sg1 = g.bcast(sigsq, 0), sg2 = g.bcast(sigsq, 1), sg3 = g.bcast(sigsq, 2);
+    if (sg2 < TINY_) return -8;
+    const double ratp = fast_div(sg3, sg2), ratm = fast_div(sg1, sg2);
+    const double qfac1 = 0.25 * (q * q - 1.0), qfac2 = (q == 3) ? 1.0 : (q == 4) ? (2.0 / 3.0) : 0.5;
+    const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
+    const double tem = 1.0 - qfac2 * bb;
+    if (fabs(tem) < TINY_) return -8;
+    const double rrb = fast_div(1.0, tem);
+    if (fabs(rrb - rr) > rrtol) return -9;
+    if (kflag == 1) kflag = 4;
+    if (kflag == 2) kflag = 5;
+    if (kflag == 3) kflag = 6;
+    return kflag;
+}
+
 // x^(1/n) for the four step-size formulas (eta = 1/((bias*err)^(1/n) + addon))
 AB_HD double nth_root(double x, int n) {
 #if defined(__CUDA_ARCH__)
@@ -544,6 +661,7 @@ AB_COLD void cold_dense_solve(const typename Layout<M, G, C>::Shared& S, double*
 // and the block solver (bdf_block.cuh: a condition per thread block, vectors in global memory).  CRTP: D supplies the
 // vector primitives
 //   nx() gsync() leader()                       size / barrier of the cooperating threads / one elected thread
+//   sldet()                                     cvSLdet on S.ssdat (sldet_serial() or a cooperative version)
 //   set_ewt() wrms_max_zn(j, lj) wrms_max_up(cquot) stab_sums(lq, lqm1, s1, s2)
 //   history_pass<PRED>(cmpl, resc) order_up(A1, ll) order_down(ll)
 //   store_correction(save) store_correction_high() scale_zn1(f) init_vectors()
@@ -696,6 +814,22 @@ struct BdfControl {
         pending = true;
     }
 
+    // cvSLdet on the ring buffer, every thread computing all three orders (the solvers may override this)
+    AB_HD int sldet_serial() const {
+        double s[6][4], ratc[5][4];
+        AB_UNROLL
+        for (int i = 1; i <= 5; ++i) {
+            int idx = ss_head + i - 1;
+            idx = idx >= 5 ? idx - 5 : idx;
+            AB_UNROLL
+            for (int kk = 1; kk <= 3; ++kk) {
+                s[i][kk] = S.ssdat[idx][kk];
+                if (i <= 4) ratc[i][kk] = S.ssdat[idx][4 + kk];
+            }
+        }
+        return bdf_sldet(s, ratc, q);
+    }
+
     // cvSetEta (cvodes.c:7798) with eta_min_fx = 0, eta_max_fx = 1.5, hmin = 0
     AB_HD void set_eta() {
         if (eta > 0.0 && eta < 1.5) {
@@ -790,18 +924,7 @@ struct BdfControl {
         }
         if (qprime >= q) {
             if (q >= 3 && nscon >= q + 5) {
-                double s[6][4], ratc[5][4];
-                AB_UNROLL
-                for (int i = 1; i <= 5; ++i) {
-                    int idx = ss_head + i - 1;
-                    idx = idx >= 5 ? idx - 5 : idx;
-                    AB_UNROLL
-                    for (int kk = 1; kk <= 3; ++kk) {
-                        s[i][kk] = S.ssdat[idx][kk];
-                        if (i <= 4) ratc[i][kk] = S.ssdat[idx][4 + kk];
-                    }
-                }
-                const int ldflag = bdf_sldet(s, ratc, q);
+                const int ldflag = self().sldet();
                 if (ldflag > 3) {
                     qprime = q - 1;
                     eta = etaqm1;
@@ -1146,6 +1269,12 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
     // primitives BdfControl calls (see the list at its top)
     // -----------------------------------------------------------------------------------------
     AB_HD int nx() const { return NX; }
+    AB_HD int sldet() const {
+#if defined(__CUDA_ARCH__)
+        if (G >= 4) return bdf_sldet_lanes<G>(g, S.ssdat, Base::ss_head, q);
+#endif
+        return Base::sldet_serial();
+    }
     AB_HD void gsync() const { g.sync(); }
     AB_HD bool leader() const { return g.lane == 0; }
     AB_HD bool rhs_to_zn1(double scale) { return cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, scale, 1); }

@@ -53,6 +53,19 @@ struct Group {
         return v;
     }
 
+    // Minimum of a non-negative value over the group (same bit-pattern argument as max)
+    AB_HD double min(double v) const {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) {
+            const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
+            const unsigned mhi = __reduce_min_sync(mask, hi);
+            const unsigned mlo = __reduce_min_sync(mask, hi == mhi ? lo : 0xffffffffu);
+            v = __hiloint2double((int)mhi, (int)mlo);
+        }
+#endif
+        return v;
+    }
+
     AB_HD double bcast(double v, int src) const {
 #if defined(__CUDA_ARCH__)
         if (G > 1) v = __shfl_sync(mask, v, src, G);
