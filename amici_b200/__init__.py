@@ -618,10 +618,12 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
     plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist
     pscale = np.asarray([int(s) for s in model.get_parameter_scale()], dtype=np.int32) if batch.pscale is None else batch.pscale
     opts = solver._options(model.t0(), model)
-    if not np.all(np.isfinite(batch.ts)):
-        # t = inf output points need the reference's post-equilibration (SteadyStateProblem after the last finite timepoint,
-        # reference src/forwardproblem.cpp:376-387), which is not part of this engine yet: fail loudly instead of integrating forever
-        raise RuntimeError("amici_b200: non-finite timepoints (post-equilibration) are not supported")
+    # t = inf output points: post-equilibration after the last finite timepoint (reference src/forwardproblem.cpp:376-387)
+    finite = np.isfinite(batch.ts)
+    has_posteq = bool(len(batch.ts)) and not finite.all()
+    if has_posteq and (np.isnan(batch.ts).any() or (batch.ts == -np.inf).any() or finite[int(np.argmin(finite)):].any()):
+        raise RuntimeError("amici_b200: timepoints must be finite, followed by t = inf entries only")
+    opts.posteq = int(has_posteq)
     q = len(plist) if opts.sensi else 0
     d = dict(model.dims(), nz=model.nz, nmaxevent=opts.nmaxevent)
     b = _capi.BatchView(N=N, nt=nt, nplist=len(plist))
@@ -663,6 +665,11 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
         if likelihood_only and name not in lk_fields:
             continue
         if name in _capi.EVENT_FIELDS and model.nz == 0:
+            continue
+        if name in _capi.POSTEQ_FIELDS and not has_posteq:
+            # ReturnData defaults without post-equilibration (reference src/rdata.cpp:172-173)
+            shape = shp(d, N, nt, q)
+            out[name] = (np.zeros(shape, dtype=np.int32) if t == "i" else np.full(shape, np.nan))
             continue
         if name in _capi.PREEQ_FIELDS and batch.k_preeq is None:
             # ReturnData defaults without pre-equilibration (reference src/rdata.cpp:170-171, :192-196)

@@ -16,7 +16,7 @@ class SolverOptions(C.Structure):
                                "max_err_test_fails", "reporting")] + [
         (n, C.c_double) for n in ("rtol_ss", "atol_ss", "rtol_ss_sensi", "atol_ss_sensi", "newton_damping_lower_bound")] + [
         (n, C.c_int) for n in ("newton_maxsteps", "newton_damping_mode", "sensi_ss_check", "ss_mode", "ss_sensi_mode",
-                               "nmaxevent")]
+                               "nmaxevent", "posteq")]
 
 
 # (name, dtype, shape(dims, N, nt, nplist)) for every output buffer of ab_batch; dims["ne_"] = nmaxevent of the call
@@ -49,6 +49,10 @@ OUT_FIELDS = [
     ("preeq_numsteps", "i", lambda d, N, nt, q: (N, 3)),
     ("preeq_wrms", "d", lambda d, N, nt, q: (N,)),
     ("preeq_t", "d", lambda d, N, nt, q: (N,)),
+    ("posteq_status", "i", lambda d, N, nt, q: (N, 3)),
+    ("posteq_numsteps", "i", lambda d, N, nt, q: (N, 3)),
+    ("posteq_wrms", "d", lambda d, N, nt, q: (N,)),
+    ("posteq_t", "d", lambda d, N, nt, q: (N,)),
     ("z", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), d.get("nz", 0))),
     ("sz", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), q, d.get("nz", 0))),
     ("rz", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), d.get("nz", 0))),
@@ -56,6 +60,7 @@ OUT_FIELDS = [
     ("sigmaz", "d", lambda d, N, nt, q: (N, d.get("nmaxevent", 10), d.get("nz", 0))),
 ]
 PREEQ_FIELDS = ("x_ss", "sx_ss", "preeq_status", "preeq_numsteps", "preeq_wrms", "preeq_t")
+POSTEQ_FIELDS = ("posteq_status", "posteq_numsteps", "posteq_wrms", "posteq_t")
 EVENT_FIELDS = ("z", "sz", "rz", "srz", "sigmaz")
 
 
@@ -73,7 +78,8 @@ def default_options(**kw) -> SolverOptions:
                       sensi=0, ism=1, maxsteps=10000, stldet=1, max_nonlin_iters=3, max_conv_fails=10,
                       max_err_test_fails=7, reporting=0, rtol_ss=float("nan"), atol_ss=float("nan"),
                       rtol_ss_sensi=float("nan"), atol_ss_sensi=float("nan"), newton_damping_lower_bound=1e-8,
-                      newton_maxsteps=0, newton_damping_mode=1, sensi_ss_check=1, ss_mode=2, ss_sensi_mode=2, nmaxevent=10)
+                      newton_maxsteps=0, newton_damping_mode=1, sensi_ss_check=1, ss_mode=2, ss_sensi_mode=2, nmaxevent=10,
+                      posteq=0)
     for k_, v in kw.items():
         setattr(o, k_, v)
     if o.rtol_fsa != o.rtol_fsa:
@@ -128,6 +134,8 @@ def make_batch(dims: dict, ts, p, k, plist=None, pscale=None, my=None, sigmay=No
         if name in PREEQ_FIELDS and k_preeq is None and (fields is None or name not in fields):
             continue
         if name in EVENT_FIELDS and dims.get("nz", 0) == 0:
+            continue
+        if name in POSTEQ_FIELDS and np.all(np.isfinite(ts)) and (fields is None or name not in fields):
             continue
         a = np.zeros(shp(dims, N, nt, q), dtype=np.float64 if t == "d" else np.int32)
         out[name] = a

@@ -95,15 +95,15 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
     if (o->sensi >= 1 && o->ism != 1) { g_err = "only simultaneous forward sensitivities are implemented"; return AB_E_UNSUPPORTED; }
     if (!(o->rtol >= 0) || !(o->atol >= 0)) { g_err = "negative tolerance"; return AB_E_BAD_ARGUMENT; }
     if (o->nmaxevent < 0) { g_err = "nmaxevent must be non-negative"; return AB_E_BAD_ARGUMENT; }
-    if (b->k_preeq && (!(o->rtol_ss >= 0) || !(o->atol_ss >= 0) || !(o->rtol_ss_sensi >= 0) || !(o->atol_ss_sensi >= 0))) {
+    if ((b->k_preeq || o->posteq) && (!(o->rtol_ss >= 0) || !(o->atol_ss >= 0) || !(o->rtol_ss_sensi >= 0) || !(o->atol_ss_sensi >= 0))) {
         g_err = "steady-state tolerances must be resolved (non-negative) when k_preeq is given";
         return AB_E_BAD_ARGUMENT;
     }
-    if (b->k_preeq && (o->ss_mode < 0 || o->ss_mode > 2 || o->ss_sensi_mode < 0 || o->ss_sensi_mode > 2)) {
+    if ((b->k_preeq || o->posteq) && (o->ss_mode < 0 || o->ss_mode > 2 || o->ss_sensi_mode < 0 || o->ss_sensi_mode > 2)) {
         g_err = "invalid steady-state mode";
         return AB_E_BAD_ARGUMENT;
     }
-    if (b->k_preeq && o->sensi >= 1 && o->ss_mode == 0 && o->ss_sensi_mode == 1) {
+    if ((b->k_preeq || o->posteq) && o->sensi >= 1 && o->ss_mode == 0 && o->ss_sensi_mode == 1) {
         // SteadyStateProblem constructor (reference src/forwardproblem.cpp:792-806)
         g_err = "steady-state computation mode 'newtonOnly' and sensitivity mode 'integrationOnly' are not compatible";
         return AB_E_BAD_ARGUMENT;
@@ -300,11 +300,18 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
     if (rc != AB_OK) return rc;
     if (kernel_ms) *kernel_ms = 0.f;
     if (hb->N == 0) return AB_OK;
-    for (int it = 0; it < hb->nt; ++it)
-        if (!std::isfinite(hb->ts[it])) {   // t = inf needs post-equilibration (reference src/forwardproblem.cpp:376-387)
-            g_err = "non-finite timepoints (post-equilibration) are not supported";
-            return AB_E_UNSUPPORTED;
+    // t = inf output points (post-equilibration, reference src/forwardproblem.cpp:376-387) must be the last ones
+    ab_solver_options opt_local = *opt;
+    opt_local.posteq = 0;
+    for (int it = 0; it < hb->nt; ++it) {
+        const double t = hb->ts[it];
+        if (t != t || t == -INFINITY || (opt_local.posteq && std::isfinite(t))) {
+            g_err = "timepoints must be finite, followed by t = inf entries only";
+            return AB_E_BAD_ARGUMENT;
         }
+        if (t == INFINITY) opt_local.posteq = 1;
+    }
+    opt = &opt_local;
     const ab_dims& d = e->dims;
     const size_t N = hb->N, nt = hb->nt, q = (opt->sensi >= 1) ? hb->nplist : 0;
     const size_t nx = d.nx, ny = d.ny, nz = d.nz, D = sizeof(double), I = sizeof(int);
@@ -323,6 +330,7 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
         AB_F(numnonlinsolvconvfails, I, nt, false), AB_F(order, I, nt, false),
         AB_F(x_ss, D, nx, false), AB_F(sx_ss, D, q * nx, false), AB_F(preeq_status, I, 3, false),
         AB_F(preeq_numsteps, I, 3, false), AB_F(preeq_wrms, D, 1, false), AB_F(preeq_t, D, 1, false),
+        AB_F(posteq_status, I, 3, false), AB_F(posteq_numsteps, I, 3, false), AB_F(posteq_wrms, D, 1, false), AB_F(posteq_t, D, 1, false),
         AB_F(z, D, nme * nz, false), AB_F(sz, D, nme * q * nz, false), AB_F(rz, D, nme * nz, false),
         AB_F(srz, D, nme * q * nz, false), AB_F(sigmaz, D, nme * nz, false)};
 #undef AB_F

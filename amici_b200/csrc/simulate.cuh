@@ -119,7 +119,7 @@ struct Simulation {
     // ReturnData::get_data_output + get_data_sensis_fsa for timepoint `it` from the solver state
     // (reference src/rdata.cpp:368-432; observables/likelihood: src/model.cpp:1112-1259, :2140-2413;
     //  residuals/FIM: src/rdata.cpp:985-1205).  Gaussian noise model (generated Jy.cpp/dJydy.cpp/dJydsigma.cpp).
-    AB_HD void datapoint(int it) {
+    AB_HD void datapoint(int it, const bool posteq_point = false) {
         auto& g = bdf.g;
         const int nt = b.nt;
         const double t = b.ts[it];
@@ -236,11 +236,12 @@ struct Simulation {
         }
         if (g.lane == 0) {
             const size_t idx = (size_t)n * nt + it;
-            if (b.numsteps) b.numsteps[idx] = bdf.nst;
-            if (b.numrhsevals) b.numrhsevals[idx] = bdf.nfe;
-            if (b.numerrtestfails) b.numerrtestfails[idx] = bdf.netf;
-            if (b.numnonlinsolvconvfails) b.numnonlinsolvconvfails[idx] = bdf.ncfn;
-            if (b.order) b.order[idx] = bdf.qu;
+            // the per-timepoint solver diagnostics are not written for t = inf points (they stay 0, src/rdata.cpp:288-300)
+            if (b.numsteps) b.numsteps[idx] = posteq_point ? 0 : bdf.nst;
+            if (b.numrhsevals) b.numrhsevals[idx] = posteq_point ? 0 : bdf.nfe;
+            if (b.numerrtestfails) b.numerrtestfails[idx] = posteq_point ? 0 : bdf.netf;
+            if (b.numnonlinsolvconvfails) b.numnonlinsolvconvfails[idx] = posteq_point ? 0 : bdf.ncfn;
+            if (b.order) b.order[idx] = posteq_point ? 0 : bdf.qu;
         }
     }
 
@@ -634,6 +635,11 @@ struct Simulation {
         // phase: 0 = main simulation, 1 = steady-state simulation, 2 = steady state found (finish), 3 = simulation failed
         int phase = 0;
         bool newton_on = false, sim_on = false, preeq_failed = false;
+        // post-equilibration (t = inf output points, reference src/forwardproblem.cpp:376-387): the same steady-state machinery,
+        // started from the solver state at the last finite timepoint.  pre_* keep the pre-equilibration results meanwhile.
+        bool posteq = false, posteq_failed = false;
+        int pre_status[3] = {SS_NOT_RUN, SS_NOT_RUN, SS_NOT_RUN}, pre_steps[3] = {0, 0, 0};
+        double pre_wrms = ab_nan(), pre_t = ab_nan();
         if (PREEQ && has_preeq) {
             const bool sens = ncols_main > 1;
             newton_on = !(o.ss_mode == SS_INTEGRATION_ONLY || o.newton_maxsteps == 0 ||
@@ -704,7 +710,8 @@ struct Simulation {
                         phase = 2;
                     } else {
                         status = AB_ERROR;   // handle_steady_state_failure -> AmiException (src/amici.cpp:155-170)
-                        preeq_failed = true;
+                        if (posteq) posteq_failed = true;
+                        else preeq_failed = true;
                         break;
                     }
                 }
@@ -717,11 +724,13 @@ struct Simulation {
                         const double tss = pe_status[1] == SS_SUCCESS ? t : INFINITY;
                         if (!cold_newton_sensis<M, G, C>(S, ncols_main, tss)) {
                             status = AB_ERROR;
-                            preeq_failed = true;
+                            if (posteq) posteq_failed = true;
+                            else preeq_failed = true;
                             break;
                         }
                     }
                     bdf.ncols = ncols_main;
+                    if (posteq) break;   // the t = inf outputs are written after the loop
                     write_steady_state();
                     // back to the simulation condition (ConditionContext restore) and on to the main simulation
                     g.sync();
@@ -734,12 +743,56 @@ struct Simulation {
                     bdf.init(o.t0);
                     t = o.t0;
                     phase = 0;
+                    AB_UNROLL
+                    for (int i = 0; i < 3; ++i) {   // keep the pre-equilibration record; pe_* are re-used by a post-equilibration
+                        pre_status[i] = pe_status[i];
+                        pre_steps[i] = pe_steps[i];
+                        pe_status[i] = SS_NOT_RUN;
+                        pe_steps[i] = 0;
+                    }
+                    pre_wrms = pe_wrms;
+                    pre_t = pe_t;
+                    pe_wrms = pe_t = ab_nan();
                 }
             }
             double next_t_event = INFINITY;
             if (!PREEQ || phase == 0) {
                 if (it >= nt) break;
                 tout = b.ts[it];
+                if (PREEQ && tout == INFINITY) {
+                    // SteadyStateProblem(is_preeq = false)::run from the current solver state (src/forwardproblem.cpp:812-870)
+                    posteq = true;
+                    const bool sens = ncols_main > 1;
+                    newton_on = !(o.ss_mode == SS_INTEGRATION_ONLY || o.newton_maxsteps == 0 ||
+                                  (sens && o.ss_sensi_mode == SS_INTEGRATION_ONLY));
+                    sim_on = o.ss_mode != SS_NEWTON_ONLY;
+                    g.sync();
+                    AB_UNROLL
+                    for (int c = 0; c < C; ++c) {   // Newton's method works on zn[0] in place: keep the solver's state (acorbuf is free here)
+                        if (!bdf.active(c)) continue;
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r) S.acorbuf[r][bdf.col(c)] = S.zn[0][r][bdf.col(c)];
+                    }
+                    g.sync();
+                    phase = 3;
+                    if (newton_on && preeq_newton(0, pe_status, pe_steps, pe_wrms)) phase = 2;
+                    else if (sim_on) {
+                        g.sync();
+                        AB_UNROLL
+                        for (int c = 0; c < C; ++c) {
+                            if (!bdf.active(c)) continue;
+                            AB_UNROLL
+                            for (int r = 0; r < NX; ++r) S.zn[0][r][bdf.col(c)] = S.acorbuf[r][bdf.col(c)];
+                        }
+                        g.sync();
+                        // "Postequilibration -> Solver was already created, use that one" (src/forwardproblem.cpp:877-878): the
+                        // integrator continues with its history; only steady-state sensitivity mode newtonOnly switches its
+                        // forward sensitivities off (switch_forward_sensis_off, :1022-1026)
+                        bdf.ncols = (sens && o.ss_sensi_mode != SS_NEWTON_ONLY) ? ncols_main : 1;
+                        phase = 1;
+                    }
+                    continue;
+                }
                 if (!(tout > o.t0) || !(t < tout) || next_t_too_close(t, tout)) {
                     datapoint(it);
                     ++it;
@@ -796,6 +849,32 @@ struct Simulation {
                 store_event(t);
             }
         }
+        if (PREEQ && posteq) {
+            // ReturnData::process_post_equilibration (reference src/rdata.cpp:288-312): the t = inf outputs come from the final
+            // state of the steady-state problem, also when it failed (status is AMICI_ERROR then, nothing is invalidated)
+            bdf.ncols = ncols_main;
+            g.sync();
+            if (g.lane == 0) {
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) S.xfin[r] = S.zn[0][r][0];
+            }
+            g.sync();
+            for (; it < nt; ++it) datapoint(it, true);
+            if (pe_status[1] != SS_SUCCESS || posteq_failed) t = INFINITY;
+            if (g.lane == 0) {
+                for (int i = 0; i < 3; ++i) {
+                    if (b.posteq_status) b.posteq_status[(size_t)n * 3 + i] = pe_status[i];
+                    if (b.posteq_numsteps) b.posteq_numsteps[(size_t)n * 3 + i] = pe_steps[i];
+                }
+                if (b.posteq_wrms) b.posteq_wrms[n] = pe_wrms;
+                if (b.posteq_t) b.posteq_t[n] = pe_t;
+            }
+        }
+        if (PREEQ && o.posteq && !posteq && g.lane == 0) {
+            // the post-equilibration never started (failure before the t = inf points): ReturnData defaults (src/rdata.cpp:172-175)
+            if (b.posteq_wrms) b.posteq_wrms[n] = ab_nan();
+            if (b.posteq_t) b.posteq_t[n] = ab_nan();
+        }
         if (PREEQ && preeq_failed) {
             // the steady-state problem's last state is reported as x_ss / sx_ss and used for xdot / J; the forward
             // problem never started: x0 / sx0 stay NaN (reference src/rdata.cpp:233-252, :261-273, :320-323)
@@ -807,14 +886,15 @@ struct Simulation {
             write_steady_state(false);
         }
         if (PREEQ && has_preeq && g.lane == 0) {
+            const bool done = !preeq_failed;   // a finished pre-equilibration moved its record to pre_*
             for (int i = 0; i < 3; ++i) {
-                if (b.preeq_status) b.preeq_status[(size_t)n * 3 + i] = pe_status[i];
-                if (b.preeq_numsteps) b.preeq_numsteps[(size_t)n * 3 + i] = pe_steps[i];
+                if (b.preeq_status) b.preeq_status[(size_t)n * 3 + i] = done ? pre_status[i] : pe_status[i];
+                if (b.preeq_numsteps) b.preeq_numsteps[(size_t)n * 3 + i] = done ? pre_steps[i] : pe_steps[i];
             }
-            if (b.preeq_wrms) b.preeq_wrms[n] = pe_wrms;
-            if (b.preeq_t) b.preeq_t[n] = pe_t;
+            if (b.preeq_wrms) b.preeq_wrms[n] = done ? pre_wrms : pe_wrms;
+            if (b.preeq_t) b.preeq_t[n] = done ? pre_t : pe_t;
         }
-        if (status != AB_SUCCESS) invalidate(it, (PREEQ && preeq_failed) ? 0.0 : ab_nan());
+        if (status != AB_SUCCESS && !(PREEQ && posteq_failed)) invalidate(it, (PREEQ && preeq_failed) ? 0.0 : ab_nan());
         // xdot and J at the final state = the last solution the solver returned (ReturnData::store_jacobian_and_derivative,
         // reference rdata.h:707-728; FinalStateStorer, src/forwardproblem.cpp:245-256)
         if (full() && (b.xdot || b.J)) {

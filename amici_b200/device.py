@@ -19,6 +19,7 @@ class DeviceBatch:
         self.model, self.solver = model, solver
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.opts = solver._options(model.t0(), model)
+        self.opts.posteq = int(len(batch.ts) > 0 and not np.all(np.isfinite(batch.ts)))
         d = dict(model.dims(), nz=model.nz, nmaxevent=self.opts.nmaxevent)
         N, nt = len(batch), len(batch.ts)
         plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist
@@ -50,6 +51,8 @@ class DeviceBatch:
             if likelihood_only and name not in lk:
                 continue
             if name in _capi.PREEQ_FIELDS and batch.k_preeq is None:
+                continue
+            if name in _capi.POSTEQ_FIELDS and np.all(np.isfinite(batch.ts)):
                 continue
             shape = shp(d, N, nt, q)
             if int(np.prod(shape)) == 0:

@@ -53,6 +53,8 @@ typedef struct ab_solver_options {
     int ss_mode;               /* SteadyStateComputationMode: 0 newtonOnly, 1 integrationOnly, 2 integrateIfNewtonFails   */
     int ss_sensi_mode;         /* SteadyStateSensitivityMode: same values                                                 */
     int nmaxevent;             /* Model::set_n_max_event (10): event-observable slots per event                           */
+    int posteq;                /* 1 if ts ends with t = inf output points: post-equilibration after the last finite timepoint
+                                  (reference src/forwardproblem.cpp:376-387); ab_run_batch sets it itself from the host ts  */
 } ab_solver_options;
 
 /* One batch of N conditions (replaces std::vector<ExpData*> in, std::vector<ReturnData> out). */
@@ -101,6 +103,11 @@ typedef struct ab_batch {
     int* preeq_numsteps;     /* [N][3]                               */
     double* preeq_wrms;      /* [N]                                  */
     double* preeq_t;         /* [N]                                  */
+    /* post-equilibration (ReturnData::posteq_*; reference src/rdata.cpp:288-312) */
+    int* posteq_status;      /* [N][3]                               */
+    int* posteq_numsteps;    /* [N][3]                               */
+    double* posteq_wrms;     /* [N]                                  */
+    double* posteq_t;        /* [N]                                  */
     /* event observables (ReturnData::z, sz, rz, srz, sigmaz; reference src/rdata.cpp:434-512) */
     double* z;               /* [N][nmaxevent][nz]                   */
     double* sz;              /* [N][nmaxevent][nplist][nz]           */

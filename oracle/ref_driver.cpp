@@ -150,6 +150,8 @@ extern "C" int ref_run(ref_options const* o, ref_batch* b) {
             if (b->chi2) b->chi2[i] = r.chi2;
             if (b->preeq_wrms) b->preeq_wrms[i] = r.preeq_wrms;
             if (b->preeq_t) b->preeq_t[i] = r.preeq_t;
+            if (b->posteq_wrms) b->posteq_wrms[i] = r.posteq_wrms;
+            if (b->posteq_t) b->posteq_t[i] = r.posteq_t;
             put(b->sllh, npl, i, r.sllh);
             put(b->x, (size_t)nt * nx, i, r.x);
             put(b->sx, (size_t)nt * npl * nx, i, r.sx);
@@ -180,6 +182,10 @@ extern "C" int ref_run(ref_options const* o, ref_batch* b) {
             if (b->preeq_status)
                 for (size_t j = 0; j < 3 && j < r.preeq_status.size(); ++j)
                     b->preeq_status[i * 3 + j] = static_cast<int>(r.preeq_status[j]);
+            put(b->posteq_numsteps, 3, i, r.posteq_numsteps);
+            if (b->posteq_status)
+                for (size_t j = 0; j < 3 && j < r.posteq_status.size(); ++j)
+                    b->posteq_status[i * 3 + j] = static_cast<int>(r.posteq_status[j]);
         }
         return 0;
     } catch (std::exception const& e) {

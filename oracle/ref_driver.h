@@ -86,6 +86,10 @@ typedef struct {
     int* preeq_numsteps;     /* [N][3]                      */
     double* preeq_wrms;      /* [N]                         */
     double* preeq_t;         /* [N]                         */
+    int* posteq_status;      /* [N][3]                      */
+    int* posteq_numsteps;    /* [N][3]                      */
+    double* posteq_wrms;     /* [N]                         */
+    double* posteq_t;        /* [N]                         */
     int* numsteps;           /* [N][nt]                     */
     int* numrhsevals;        /* [N][nt]                     */
     int* numerrtestfails;    /* [N][nt]                     */

@@ -64,6 +64,10 @@ _OUT_FIELDS = [  # name, ctype, shape-lambda(d, N, nt, npl, nmaxevent)
     ("preeq_numsteps", "i", lambda d, N, nt, q, e: (N, 3)),
     ("preeq_wrms", "d", lambda d, N, nt, q, e: (N,)),
     ("preeq_t", "d", lambda d, N, nt, q, e: (N,)),
+    ("posteq_status", "i", lambda d, N, nt, q, e: (N, 3)),
+    ("posteq_numsteps", "i", lambda d, N, nt, q, e: (N, 3)),
+    ("posteq_wrms", "d", lambda d, N, nt, q, e: (N,)),
+    ("posteq_t", "d", lambda d, N, nt, q, e: (N,)),
     ("numsteps", "i", lambda d, N, nt, q, e: (N, nt)),
     ("numrhsevals", "i", lambda d, N, nt, q, e: (N, nt)),
     ("numerrtestfails", "i", lambda d, N, nt, q, e: (N, nt)),

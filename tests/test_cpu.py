@@ -203,6 +203,46 @@ def test_emulation_initial_state_overrides_match_reference(built):
     np.testing.assert_allclose(out["sllh"], r["sllh"], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("kw", [dict(newton_maxsteps=50, ss_mode=2, ss_sensi_mode=0),     # Newton finds it, sensitivities by the linear solve
+                                dict(newton_maxsteps=0, ss_mode=2, ss_sensi_mode=2),      # simulation carrying the sensitivities
+                                dict(newton_maxsteps=2, ss_mode=2, ss_sensi_mode=0),      # Newton fails, simulation, Newton sensitivities
+                                dict(newton_maxsteps=2, ss_mode=0, ss_sensi_mode=0)])     # Newton only and too few steps: failure
+def test_emulation_postequilibration_matches_reference(built, kw):
+    """t = inf output points (post-equilibration, reference src/forwardproblem.cpp:376-387, src/rdata.cpp:288-312): status
+    triple, step counts, NaN pattern and values against the compiled reference, including a failing steady-state search."""
+    from oracle import refsim
+    if not refsim.available("steadystate"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    N = 4
+    ts = np.concatenate([np.linspace(0, 10, 6), [np.inf, np.inf]])
+    rng = np.random.default_rng(9)
+    my = rng.uniform(0.1, 1.0, (N, len(ts), 3))
+    sig = np.full_like(my, 0.1)
+    dims = MODEL_DIMS["steadystate"]
+    b, out, keep = _capi.make_batch(dims, ts, g["p"][:N], g["k"][:N], my=my, sigmay=sig)
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1, posteq=1, **kw)
+    assert _emul(built).emul_run(b"steadystate", C.byref(o), C.byref(b)) == 0
+    r = refsim.RefModel("steadystate").run(ts, g["p"][:N], g["k"][:N], my=my, sigmay=sig, sensi_order=1, **kw)
+    np.testing.assert_array_equal(out["status"], r["status"])
+    np.testing.assert_array_equal(out["posteq_status"], r["posteq_status"])
+    np.testing.assert_array_equal(out["posteq_numsteps"][:, [0, 2]], r["posteq_numsteps"][:, [0, 2]])
+    sim = r["posteq_numsteps"][:, 1]
+    assert np.all(np.abs(out["posteq_numsteps"][:, 1] - sim) <= np.maximum(3, 0.1 * sim))   # step sequences are chaotic w.r.t. round-off
+    np.testing.assert_array_equal(out["numsteps"][:, -2:], r["numsteps"][:, -2:])
+    for f in ("x", "sx", "y", "llh", "sllh", "posteq_t", "posteq_wrms"):
+        np.testing.assert_array_equal(np.isnan(out[f]), np.isnan(r[f]), err_msg=f)
+    ok = r["status"] == 0
+    np.testing.assert_allclose(out["x"][ok], r["x"][ok], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(out["llh"][ok], r["llh"][ok], rtol=1e-5)
+    np.testing.assert_allclose(out["sx"][ok], r["sx"][ok], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out["sllh"][ok], r["sllh"][ok], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(out["posteq_t"][ok], r["posteq_t"][ok], rtol=0.2)
+    if not ok.all():   # a failed search still reports the outputs of its final state (status AMICI_ERROR, nothing invalidated)
+        np.testing.assert_allclose(out["x"][~ok][:, :6], r["x"][~ok][:, :6], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(out["x"][~ok][:, 6:], r["x"][~ok][:, 6:], rtol=1e-3, atol=1e-6)
+
+
 def test_group_edatas_partitions_by_condition_context(monkeypatch):
     """Host logic of the list entry point: conditions are batched by (timepoints, plist, pscale, pre-equilibration), in
     order of first appearance, without needing the CUDA library."""

@@ -373,13 +373,58 @@ def test_initial_state_overrides_match_reference(model):
     np.testing.assert_allclose(one.sllh, res["sllh"][0], rtol=1e-10)
 
 
-def test_non_finite_timepoints_are_rejected():
-    """t = inf outputs (post-equilibration) are not implemented: the call fails loudly instead of integrating forever."""
+@pytest.mark.parametrize("kw", [dict(newton_maxsteps=50, ss_mode=2, ss_sensi_mode=0), dict(newton_maxsteps=0, ss_mode=2, ss_sensi_mode=2),
+                                dict(newton_maxsteps=2, ss_mode=2, ss_sensi_mode=0), dict(newton_maxsteps=2, ss_mode=0, ss_sensi_mode=0)])
+@pytest.mark.parametrize("preeq", [False, True])
+def test_postequilibration_matches_reference(kw, preeq):
+    """t = inf output points: post-equilibration after the last finite timepoint (reference src/forwardproblem.cpp:376-387,
+    src/rdata.cpp:288-312), alone and combined with pre-equilibration, including a failing steady-state search."""
+    import amici_b200 as ab
+    from oracle.refsim import RefModel, available
+    if not available("steadystate"):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, "steadystate_preeq_newton.npz"))
+    N = 6
+    ts = np.concatenate([np.linspace(0, 10, 6), [np.inf, np.inf]])
+    rng = np.random.default_rng(9)
+    my = rng.uniform(0.1, 1.0, (N, len(ts), 3))
+    sig = np.full_like(my, 0.1)
+    m = ab.get_model("steadystate")
+    m.set_timepoints(ts)
+    m.set_steady_state_computation_mode(kw["ss_mode"])
+    m.set_steady_state_sensitivity_mode(kw["ss_sensi_mode"])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    s.set_newton_max_steps(kw["newton_maxsteps"])
+    kp = g["k_preeq"][:N] if preeq else None
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, g["p"][:N], g["k"][:N], my=my, sigmay=sig, k_preeq=kp))
+    r = RefModel("steadystate").run(ts, g["p"][:N], g["k"][:N], my=my, sigmay=sig, sensi_order=1, k_preeq=kp, **kw)
+    np.testing.assert_array_equal(res["status"], r["status"])
+    np.testing.assert_array_equal(res["posteq_status"], r["posteq_status"])
+    np.testing.assert_array_equal(res["posteq_numsteps"][:, [0, 2]], r["posteq_numsteps"][:, [0, 2]])
+    sim = r["posteq_numsteps"][:, 1]
+    assert np.all(np.abs(res["posteq_numsteps"][:, 1] - sim) <= np.maximum(3, 0.1 * sim))
+    if preeq:
+        np.testing.assert_array_equal(res["preeq_status"], r["preeq_status"])
+    for f in ("x", "sx", "y", "llh", "sllh", "posteq_t", "posteq_wrms"):
+        np.testing.assert_array_equal(np.isnan(res[f]), np.isnan(r[f]), err_msg=f)
+    ok = (r["status"] == 0) & (r["posteq_status"][:, 0] != -99)
+    np.testing.assert_allclose(res["x"][ok], r["x"][ok], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(res["llh"][ok], r["llh"][ok], rtol=1e-5)
+    np.testing.assert_allclose(res["sx"][ok], r["sx"][ok], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(res["sllh"][ok], r["sllh"][ok], rtol=1e-3, atol=1e-5)
+
+
+def test_malformed_timepoints_are_rejected():
+    """t = inf entries must come last (they are the post-equilibration outputs); NaN or -inf are rejected."""
     import amici_b200 as ab
     m = ab.get_model("steadystate")
-    m.set_timepoints([0.0, 1.0, np.inf])
-    with pytest.raises(RuntimeError, match="post-equilibration"):
-        ab.run_simulation(m, m.create_solver())
+    for ts in ([0.0, np.inf, 1.0], [0.0, np.nan], [-np.inf, 0.0]):
+        with pytest.raises(RuntimeError, match="timepoints"):
+            m.set_timepoints(ts)   # non-monotonic grids are refused here, as in the reference
+            ab.run_simulation(m, m.create_solver())
 
 
 def test_objective_reduction_kernel():
