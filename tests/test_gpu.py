@@ -417,6 +417,29 @@ def test_postequilibration_matches_reference(kw, preeq):
     np.testing.assert_allclose(res["sllh"][ok], r["sllh"][ok], rtol=1e-3, atol=1e-5)
 
 
+def test_postequilibration_jakstat_spline_model_is_the_long_time_limit():
+    """Post-equilibration on the one-warp-per-condition kernel with a time-dependent input (the spline is extrapolated
+    constantly for t -> inf).  The compiled reference aborts on this model with t = inf (a contract violation inside its
+    post-equilibration), so the check is the defining property: the t = inf outputs equal the finite-time solution far out."""
+    import amici_b200 as ab
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))
+    N = 4
+    m = ab.get_model("jakstat_adjoint")
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    out = {}
+    for tag, ts in (("inf", [0.0, 20.0, 60.0, np.inf]), ("far", [0.0, 20.0, 60.0, 1e5])):
+        m.set_timepoints(ts)
+        out[tag] = ab.run_simulations(m, s, ab.ExpDataBatch(m.get_timepoints(), g["p"][:N], g["k"][:N]))
+        assert (out[tag]["status"] == 0).all()
+    assert (out["inf"]["posteq_status"][:, 1] == 1).all() or (out["inf"]["posteq_status"][:, 0] == 1).all()
+    np.testing.assert_allclose(out["inf"]["x"][:, :3], out["far"]["x"][:, :3], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(out["inf"]["x"][:, 3], out["far"]["x"][:, 3], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out["inf"]["sx"][:, 3], out["far"]["sx"][:, 3], rtol=1e-2, atol=1e-4)
+
+
 def test_malformed_timepoints_are_rejected():
     """t = inf entries must come last (they are the post-equilibration outputs); NaN or -inf are rejected."""
     import amici_b200 as ab
