@@ -219,6 +219,30 @@ class Model:
         self._nmaxevent = int(n)
     def n_max_event(self): return self._nmaxevent
     def create_solver(self) -> "Solver": return Solver()
+
+    def simulate(self, *, solver: "Solver | None" = None, edata=None, failfast: bool = True, num_threads: int = 1,
+                 sensi_method=None, sensi_order=None):
+        """``Model.simulate`` of the reference (python/sdist/amici/sim/sundials/_swig_wrappers.py:296-331): one ExpData (or
+        none) -> one ReturnDataView, a sequence (or an ``ExpDataBatch``) -> the batch call; ``sensi_method`` /
+        ``sensi_order`` (enum or its name) are applied to the solver for this call only."""
+        solver = solver if solver is not None else self.create_solver()
+        old_method = old_order = None
+        if sensi_method is not None:
+            old_method = solver.get_sensitivity_method()
+            solver.set_sensitivity_method(SensitivityMethod[sensi_method] if isinstance(sensi_method, str) else sensi_method)
+        if sensi_order is not None:
+            old_order = solver.get_sensitivity_order()
+            solver.set_sensitivity_order(SensitivityOrder[sensi_order] if isinstance(sensi_order, str) else sensi_order)
+        try:
+            if isinstance(edata, (list, tuple, ExpDataBatch)):
+                return run_simulations(self, solver, edata, failfast=failfast, num_threads=num_threads)
+            return run_simulation(self, solver, edata)
+        finally:
+            if old_method is not None:
+                solver.set_sensitivity_method(old_method)
+            if old_order is not None:
+                solver.set_sensitivity_order(old_order)
+
     def get_name(self): return self.name
     def clone(self) -> "Model":
         import copy

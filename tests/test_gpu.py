@@ -450,6 +450,22 @@ def test_malformed_timepoints_are_rejected():
             ab.run_simulation(m, m.create_solver())
 
 
+def test_model_simulate_entry_point():
+    """Model.simulate (reference _swig_wrappers.py:296-331): temporary sensitivity settings, single and list forms."""
+    import amici_b200 as ab
+    m = ab.get_model("steadystate")
+    m.set_timepoints(np.linspace(0, 10, 5))
+    s = m.create_solver()
+    r0 = m.simulate(solver=s)
+    assert r0.status == 0 and r0.sx is None or np.size(r0.sx) == 0
+    r1 = m.simulate(solver=s, sensi_order="first", sensi_method="forward")
+    assert r1["sx"].shape == (5, 5, 3) and s.get_sensitivity_order() == ab.SensitivityOrder.none
+    np.testing.assert_allclose(r1.x, r0.x, rtol=1e-6, atol=1e-12)
+    rs = m.simulate(solver=s, edata=[ab.ExpData(m), ab.ExpData(m)], sensi_order=ab.SensitivityOrder.first)
+    assert len(rs) == 2
+    np.testing.assert_allclose(rs[1]["sx"], r1["sx"], rtol=1e-12)
+
+
 def test_objective_reduction_kernel():
     import ctypes as C
     import torch
