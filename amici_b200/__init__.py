@@ -428,6 +428,31 @@ class ExpData:
         self._my = np.full(n, np.nan)
         self._sigmay = np.full(n, np.nan)
 
+    @classmethod
+    def from_return_data(cls, model: Model, rdata, sigma_y, sigma_z=(), seed: int = -1) -> "ExpData":
+        """Synthetic data: measurements = simulated observables + N(0, sigma^2) (``ExpData(rdata, sigma_y, sigma_z, seed)``,
+        reference src/edata.cpp:83-131).  ``sigma_y`` has ny or nt*ny entries, ``sigma_z`` nz or nmaxevent*nz; a negative
+        seed draws a fresh one.  The noise comes from numpy's generator, not std::mt19937: same distribution, other stream."""
+        e = cls(model)
+        e.set_timepoints(list(np.asarray(rdata["ts"], dtype=float)))
+        nt, ny, nz, nme = len(e.ts_), e._ny, e._nz, e._nmaxevent
+        sy, sz = np.asarray(sigma_y, dtype=float).ravel(), np.asarray(sigma_z, dtype=float).ravel()
+        if sy.size not in (ny, ny * nt):
+            raise RuntimeError(f"Dimension of sigma_y must be {ny} or {ny * nt}, was {sy.size}")
+        if sz.size not in (nz, nz * nme):
+            raise RuntimeError(f"Dimension of sigma_z must be {nz} or {nz * nme}, was {sz.size}")
+        if (sy.size and not (sy > 0).all()) or (sz.size and not (sz > 0).all()):
+            raise RuntimeError("Encountered sigma <= 0")
+        rng = np.random.default_rng(None if seed < 0 else seed)
+        sig_y = np.broadcast_to(sy.reshape(-1, ny), (nt, ny))
+        e.set_measurements(np.asarray(rdata["y"], dtype=float).reshape(nt, ny) + sig_y * rng.standard_normal((nt, ny)))
+        e.set_noise_scales(sig_y)
+        if nz:
+            sig_z = np.broadcast_to(sz.reshape(-1, nz), (nme, nz))
+            e.set_event_measurements(np.asarray(rdata["z"], dtype=float).reshape(nme, nz) + sig_z * rng.standard_normal((nme, nz)))
+            e.set_event_noise_scales(sig_z)
+        return e
+
     def nt(self): return len(self.ts_)
     def set_timepoints(self, ts):
         self.ts_ = [float(t) for t in ts]

@@ -466,6 +466,23 @@ def test_model_simulate_entry_point():
     np.testing.assert_allclose(rs[1]["sx"], r1["sx"], rtol=1e-12)
 
 
+def test_expdata_from_return_data_roundtrip():
+    """ExpData(rdata, sigma_y, sigma_z, seed) of the reference (src/edata.cpp:83-131): synthetic measurements around the
+    simulated observables; re-simulating against them gives chi2 ~ number of data points and a finite gradient."""
+    import amici_b200 as ab
+    m = ab.get_model("steadystate")
+    m.set_timepoints(np.linspace(0, 10, 41))
+    s = m.create_solver()
+    r = m.simulate(solver=s)
+    e = ab.ExpData.from_return_data(m, r, [0.05, 0.05, 0.05], seed=3)
+    assert e.get_measurements().shape[0] == 41 * 3 and (e.get_noise_scales() == 0.05).all()
+    np.testing.assert_allclose(ab.ExpData.from_return_data(m, r, [0.05] * 3, seed=3).get_measurements(), e.get_measurements())
+    r2 = m.simulate(solver=s, edata=e, sensi_order="first")
+    assert r2.status == 0 and 0.5 * 123 < r2.chi2 < 1.6 * 123 and np.isfinite(r2.sllh).all()
+    with pytest.raises(RuntimeError, match="sigma_y"):
+        ab.ExpData.from_return_data(m, r, [0.1, 0.1])
+
+
 def test_objective_reduction_kernel():
     import ctypes as C
     import torch
