@@ -53,6 +53,7 @@ struct TrajShared {
     double k[M::NK_EXT > 0 ? M::NK_EXT : 1];   // fixed parameters, then the model's derived constants (M::derived)
     double h[M::NH > 0 ? M::NH : 1];
     double pcoef[NCOLS];             // chain-rule factor per column
+    double ctl[16];                  // mirrors of tau[0..6] (ctl[0..6]) and l[0..5] (ctl[8..13]) for indexing by the run-time order
     double ssdat[5][8];              // cvBDFStab history: ring buffer of (sqm2^2, sqm1^2, sq^2) in [1..3] and their ratios to
                                      // the next older entry in [5..7] (the rat[][] of cvSLdet, computed once), newest at ss_head
     int piv[M::NX];
@@ -759,14 +760,15 @@ struct BdfControl {
             }
             alpha0 -= (q == 2) ? 0.5 : (q == 3) ? (1.0 / 3.0) : (q == 4) ? 0.25 : 0.2;
             xistar_inv = -l[1] - alpha0;
-            hsum += pick(tau, q - 1);
+            hsum += tau_at(q - 1);
             xi_inv = fast_div(h, hsum);
             alpha0_hat = -l[1] - xi_inv;
             AB_UNROLL
             for (int i = QMAX; i >= 1; --i)
                 if (i <= q) l[i] += l[i - 1] * xistar_inv;
         }
-        const double lq = pick(l, q);
+        mirror_l();
+        const double lq = l_at(q);
         const double A1 = 1.0 - alpha0_hat + alpha0;
         const double A2 = 1.0 + q * A1;
         tq[2] = fabs(fast_div(A1, alpha0 * A2));
@@ -781,7 +783,7 @@ struct BdfControl {
             } else {
                 tq[1] = 1.0;
             }
-            hsum += pick(tau, q);
+            hsum += tau_at(q);
             xi_inv = fast_div(h, hsum);
             const double A5 = alpha0 - (1.0 / (q + 1));
             const double A6 = alpha0_hat - xi_inv;
@@ -807,12 +809,27 @@ struct BdfControl {
             if (i <= q) tau[i] = tau[i - 1];
         if (q == 1 && nst > 1) tau[2] = tau[1];
         tau[1] = h;
+        mirror_tau();
         qwait--;
         const bool save = (qwait == 1 && q != QMAX);
         self().store_correction(save);   // acorbuf = acor, and zn[qmax] = acor if save
         if (save) saved_tq5 = tq[5];
         pending = true;
     }
+
+    // tau[] and l[] live in registers and are indexed with compile-time constants; where the index is the run-time order
+    // (tau[q], l[q]), a select chain over the array costs ~16 instructions per use.  Every thread writes the same values
+    // to S.ctl and reads back its own writes, so no synchronisation is needed.
+    AB_HD void mirror_tau() {
+        AB_UNROLL
+        for (int i = 1; i <= LMAX; ++i) S.ctl[i] = tau[i];
+    }
+    AB_HD void mirror_l() {
+        AB_UNROLL
+        for (int i = 0; i < LMAX; ++i) S.ctl[8 + i] = l[i];
+    }
+    AB_HD double tau_at(const int i) const { return S.ctl[i]; }
+    AB_HD double l_at(const int i) const { return S.ctl[8 + i]; }
 
     // cvSLdet on the ring buffer, every thread computing all three orders (the solvers may override this)
     AB_HD int sldet_serial() const {
@@ -864,7 +881,7 @@ struct BdfControl {
             qwait = 2;
             etaqm1 = 0.0;
             if (q > 1) {
-                const double ddn = self().wrms_max_zn(q, pick(l, q)) * tq[1];
+                const double ddn = self().wrms_max_zn(q, l_at(q)) * tq[1];
                 etaqm1 = fast_div(1.0, nth_root(6.0 * ddn, q) + 1e-6);
             }
             etaqp1 = 0.0;
@@ -903,7 +920,7 @@ struct BdfControl {
             // WRMS of the state column only (lane 0 owns it)
             double s1 = 0.0, s2 = 0.0;   // valid on the leader
             {
-                const double lq = pending ? pick(l, q) : 0.0, lqm1 = pending ? pick(l, q - 1) : 0.0;   // deferred completion
+                const double lq = pending ? l_at(q) : 0.0, lqm1 = pending ? l_at(q - 1) : 0.0;   // deferred completion
                 self().stab_sums(lq, lqm1, s1, s2);
             }
             const double f2 = factorial * factorial * (1.0 / self().nx());
@@ -1065,6 +1082,8 @@ struct BdfControl {
         for (int i = 0; i < LMAX; ++i) l[i] = 0.0;
         AB_UNROLL
         for (int i = 0; i < 6; ++i) tq[i] = 0.0;
+        mirror_tau();
+        mirror_l();
         rl1 = gamma = gammap = gamrat = 1.0;
         crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5 = 0.0;
         etaq = etaqm1 = etaqp1 = 0.0;
