@@ -715,16 +715,16 @@ struct BdfControl {
             for (int j = 1; j < QMAX; ++j) {
                 if (j < q) {
                     hsum += tau[j + 1];
-                    const double xi = hsum / hscale;
+                    const double xi = fast_div(hsum, hscale);
                     prod *= xi;
                     alpha0 -= 1.0 / (j + 1);
-                    alpha1 += 1.0 / xi;
+                    alpha1 += fast_div(1.0, xi);
                     AB_UNROLL
                     for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xiold + ll[i - 1];
                     xiold = xi;
                 }
             }
-            const double A1 = (-alpha0 - alpha1) / prod;
+            const double A1 = fast_div(-alpha0 - alpha1, prod);
             self().order_up(A1, ll);   // zn[L] = A1 * zn[qmax] (saved correction), zn[2..q] += ll[j] * zn[L]
         } else if (deltaq == -1) {
             double hsum = 0.0;
@@ -732,7 +732,7 @@ struct BdfControl {
             for (int j = 1; j <= QMAX - 2; ++j) {
                 if (j <= q - 2) {
                     hsum += tau[j];
-                    const double xi = hsum / hscale;
+                    const double xi = fast_div(hsum, hscale);
                     AB_UNROLL
                     for (int i = j + 2; i >= 2; --i) ll[i] = ll[i] * xi + ll[i - 1];
                 }
@@ -887,6 +887,7 @@ struct BdfControl {
             etaqp1 = 0.0;
             if (q != QMAX && saved_tq5 != 0.0) {
                 double ratio = fast_div(h, tau[2]), pw = 1.0;
+                AB_NOUNROLL
                 for (int i = 0; i < L; ++i) pw *= ratio;  // SUNRpowerI(h/tau[2], L)
                 const double cquot = fast_div(tq[5], saved_tq5) * pw;
                 const double dup = self().wrms_max_up(cquot) * tq[3];   // norm of acor - cquot * zn[qmax]
@@ -1169,7 +1170,7 @@ struct BdfControl {
                     return AB_TSTOP_RETURN;
                 } else if ((tn + hprime - tstop) * h > 0.0) {
                     hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                    eta = hprime / h;
+                    eta = fast_div(hprime, h);
                 }
             }
         }
@@ -1213,7 +1214,7 @@ struct BdfControl {
                 if (at_tstop) { rc = AB_ERROR; break; }
                 if ((tn + hprime - tstop) * h > 0.0) {
                     hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                    eta = hprime / h;
+                    eta = fast_div(hprime, h);
                 }
                 if constexpr (ROOTS) {
                     const int rc2 = self().rcheck2();
@@ -1230,7 +1231,7 @@ struct BdfControl {
                 break;
             } else if ((tn + hprime - tstop) * h > 0.0) {
                 hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                eta = hprime / h;
+                eta = fast_div(hprime, h);
             }
         }
         flush_pending();
@@ -1316,11 +1317,12 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
         }
     }
     // cvIncreaseBDF's vector part: zn[L] = A1 * zn[qmax], zn[2..q] += ll[j] * zn[L]
+    // (rolled over the rows: order changes are rare, and this code sits inside the step loop's address range)
     AB_HD void order_up(const double A1, const double (&ll)[LMAX + 1]) {
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             if (!active(c)) continue;
-            AB_UNROLL
+            AB_NOUNROLL
             for (int r = 0; r < NX; ++r) {
                 const double zL = A1 * S.zn[QMAX][r][col(c)];
                 AB_UNROLL
@@ -1336,7 +1338,7 @@ struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             if (!active(c)) continue;
-            AB_UNROLL
+            AB_NOUNROLL
             for (int r = 0; r < NX; ++r) {
                 double zq = 0.0;
                 AB_UNROLL
