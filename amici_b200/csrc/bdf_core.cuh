@@ -1234,8 +1234,8 @@ struct BdfControl {
                 eta = fast_div(hprime, h);
             }
         }
+        self().step_sync_leave();   // first: the other warps of the group must not wait for the flush below
         flush_pending();
-        self().step_sync_leave();
         return rc;
     }
 };
