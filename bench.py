@@ -26,7 +26,7 @@ METRIC = "ODE solves/sec w/ forward sens (JAK-STAT)"
 UNIT = "solves/s"
 TS = np.arange(0, 61, 5.0)
 RTOL, ATOL = 1e-8, 1e-12
-NCU_DRAM_BYTES_PER_CONDITION = (19.643392e6 + 145.870336e6) / 4736
+NCU_DRAM_BYTES_PER_CONDITION = (19.332096e6 + 139.997952e6) / 4736   # profiles/r01_v6_ncu_summary.md
 
 
 def synthetic_inputs(n: int, seed: int, p_nom, k_nom):
@@ -257,11 +257,10 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         ach = (in_b + out_b) / (kernel_ms * 1e-3) / 1e9
-        # DRAM bytes of this kernel from the ncu --set full capture under profiles/ (r01_v3_ncu_summary.md: 19.6 MB read +
-        # 145.9 MB written by a 4736-condition launch = 34.9 KB per condition), scaled to this launch's condition count
+        # DRAM bytes of this kernel from the ncu --set full capture under profiles/ (r01_v6_ncu_summary.md; 4736-condition launch), scaled to this launch's condition count
         traffic = NCU_DRAM_BYTES_PER_CONDITION * n
         line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                            "traffic": traffic, "traffic_source": "profiles/r01_v3_ncu_summary.md (dram__bytes_read+write per condition of a 4736-condition capture) x conditions per launch",
+                            "traffic": traffic, "traffic_source": "profiles/r01_v6_ncu_summary.md (dram__bytes_read+write per condition of a 4736-condition capture) x conditions per launch",
                             "kernel": "bdf_solve_kernel<jakstat_adjoint,32,1,256,1>", "kernel_ms": kernel_ms,
                             "algorithmic_bytes_per_launch": in_b + out_b, "peak_source": peak_src,
                             "note": "the solve is FP64-latency bound, not HBM bound (state lives in shared memory/registers); see roofline_fp64"}
