@@ -420,6 +420,8 @@ class ExpData:
         self.free_parameters: list[float] = []   # empty = use the model's
         self.fixed_parameters: list[float] = []
         self.fixed_parameters_pre_equilibration: list[float] = []   # non-empty = pre-equilibrate (edata.h)
+        self.fixed_parameters_presimulation: list[float] = []       # k during the presimulation; empty = the simulation's
+        self.t_presim: float = 0.0                                   # > 0: integrate [t0 - t_presim, t0] first (edata.h)
         self.pscale: list = []
         self.plist: list[int] = []
         self.x0: list[float] = []    # initial state override (edata.h); empty = the model's x0(p, k)
@@ -502,7 +504,7 @@ class ExpDataBatch:
     """
 
     def __init__(self, ts, p, k, my=None, sigmay=None, plist=None, pscale=None, k_preeq=None, mz=None, sigmaz=None,
-                 x0=None, sx0=None):
+                 x0=None, sx0=None, k_presim=None, t_presim=None):
         self.ts = np.ascontiguousarray(ts, dtype=np.float64)
         self.p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
         self.k = np.ascontiguousarray(np.atleast_2d(k), dtype=np.float64)
@@ -516,6 +518,11 @@ class ExpDataBatch:
         # ExpData::x0 / sx0: initial state (and its sensitivities, on the parameter scale) instead of the model's
         self.x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
         self.sx0 = None if sx0 is None else np.ascontiguousarray(sx0, dtype=np.float64)
+        # ExpData::t_presim / fixed_parameters_presimulation: per condition, 0 = no presimulation
+        self.t_presim = None if t_presim is None else np.ascontiguousarray(np.broadcast_to(np.asarray(t_presim, dtype=np.float64), (self.p.shape[0],)))
+        self.k_presim = None if k_presim is None else np.ascontiguousarray(np.atleast_2d(k_presim), dtype=np.float64)
+        if self.k_presim is not None and self.t_presim is None:
+            raise RuntimeError("amici_b200: k_presim without t_presim")
 
     def __len__(self): return self.p.shape[0]
 
@@ -577,7 +584,17 @@ class ExpDataBatch:
                 raise RuntimeError("Dimension mismatch. Size of sx0 does not match number of model states * number of "
                                    "parameter selected for sensitivities.")
             sx0 = sx0.reshape(N, len(plist), model.nx)
-        return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq, mz=mz, sigmaz=sz, x0=x0, sx0=sx0)
+        t_presim = k_presim = None
+        if any(e is not None and e.t_presim > 0 for e in edatas):
+            t_presim = np.array([0.0 if e is None else float(e.t_presim) for e in edatas])
+            k_presim = k.copy()   # ConditionContext(presimulation) without dedicated parameters keeps the simulation's
+            for i, e in enumerate(edatas):
+                if e is not None and len(e.fixed_parameters_presimulation):
+                    if len(e.fixed_parameters_presimulation) != model.nk():
+                        raise RuntimeError("Number of fixed parameters in model does not match ExpData (presimulation).")
+                    k_presim[i] = e.fixed_parameters_presimulation
+        return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq, mz=mz, sigmaz=sz, x0=x0, sx0=sx0,
+                            k_presim=k_presim, t_presim=t_presim)
 
 
 _RDATA_ALIASES = {"num_rhs_evals": "numrhsevals", "num_err_test_fails": "numerrtestfails",
@@ -699,6 +716,12 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
         if batch.k_preeq.shape != (N, d["nk"]):
             raise RuntimeError("amici_b200: k_preeq shape does not match the model")
         b.k_preeq = batch.k_preeq.ctypes.data_as(dp)
+    if batch.t_presim is not None and (batch.t_presim > 0).any():
+        b.t_presim = batch.t_presim.ctypes.data_as(dp)
+        if batch.k_presim is not None:
+            if batch.k_presim.shape != (N, d["nk"]):
+                raise RuntimeError("Number of fixed parameters in model does not match ExpData (presimulation).")
+            b.k_presim = batch.k_presim.ctypes.data_as(dp)
     for name, arr in (("mz", batch.mz), ("sigmaz_in", batch.sigmaz)):
         if arr is not None:
             if arr.shape != (N, opts.nmaxevent, model.nz):

@@ -69,7 +69,7 @@ class BatchView(C.Structure):
     _fields_ = [("N", C.c_int), ("nt", C.c_int), ("nplist", C.c_int),
                 ("ts", _dp), ("plist", _ip), ("pscale", _ip), ("p", _dp), ("k", _dp),
                 ("my", _dp), ("sigmay_in", _dp), ("k_preeq", _dp), ("mz", _dp), ("sigmaz_in", _dp),
-                ("x0_in", _dp), ("sx0_in", _dp)] + [
+                ("x0_in", _dp), ("sx0_in", _dp), ("k_presim", _dp), ("t_presim", _dp)] + [
         (n, _dp if t == "d" else _ip) for n, t, _ in OUT_FIELDS]
 
 
@@ -94,7 +94,7 @@ def default_options(**kw) -> SolverOptions:
 
 
 def make_batch(dims: dict, ts, p, k, plist=None, pscale=None, my=None, sigmay=None, fields=None, k_preeq=None,
-               mz=None, sigmaz=None, nmaxevent=10, x0=None, sx0=None):
+               mz=None, sigmaz=None, nmaxevent=10, x0=None, sx0=None, k_presim=None, t_presim=None):
     """Build an ab_batch over freshly allocated numpy outputs. Returns (batch, outputs dict, keepalive)."""
     ts = np.ascontiguousarray(ts, dtype=np.float64)
     p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
@@ -122,7 +122,8 @@ def make_batch(dims: dict, ts, p, k, plist=None, pscale=None, my=None, sigmay=No
             a = np.ascontiguousarray(arr, dtype=np.float64).reshape(N, nmaxevent, dims.get("nz", 0))
             keep.append(a)
             setattr(b, name, a.ctypes.data_as(_dp))
-    for name, arr, shape in (("x0_in", x0, (N, dims["nx"])), ("sx0_in", sx0, (N, q, dims["nx"]))):
+    for name, arr, shape in (("x0_in", x0, (N, dims["nx"])), ("sx0_in", sx0, (N, q, dims["nx"])),
+                             ("k_presim", k_presim, (N, dims["nk"])), ("t_presim", t_presim, (N,))):
         if arr is not None:
             a = np.ascontiguousarray(arr, dtype=np.float64).reshape(shape)
             keep.append(a)

@@ -1243,15 +1243,17 @@ struct BdfControl {
 // ---------------------------------------------------------------------------------------------
 // the lane-group solver: one condition per group of G lanes, C columns per lane, work vectors in registers
 // ---------------------------------------------------------------------------------------------
-template <class M, int G, int C>
-struct Bdf : BdfControl<Bdf<M, G, C>, typename Layout<M, G, C>::Shared> {
+// REINIT: compile CVodeSolver::reinit + reInit_post_process also for a model without events (the condition driver
+// re-initialises the solver after a presimulation)
+template <class M, int G, int C, bool REINIT = false>
+struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> {
     static constexpr int NX = M::NX;
     static constexpr int NCOLS = Layout<M, G, C>::NCOLS;
     static constexpr bool ROOTS = M::NE_SOLVER > 0;   // the integrator tracks event triggers
-    static constexpr bool EVENTS = M::NE > 0;         // AMICI re-initialises the solver after events
+    static constexpr bool EVENTS = M::NE > 0 || REINIT;   // AMICI re-initialises the solver after events
     using Shared = typename Layout<M, G, C>::Shared;
     using Eval = ModelEval<M, C>;
-    using Base = BdfControl<Bdf<M, G, C>, Shared>;
+    using Base = BdfControl<Bdf<M, G, C, REINIT>, Shared>;
     // names of the dependent base used by the vector code below
     using Base::S; using Base::o;
     using Base::tn; using Base::h; using Base::hscale; using Base::hprime; using Base::eta; using Base::etamax;

@@ -93,8 +93,8 @@ int launch_block_variant(const ab_solver_options& o, const ab_batch& b, int* que
 
 template <class M>
 int launch_block_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
-    if (b.k_preeq || o.posteq) {
-        last_error() = "pre-/post-equilibration is not implemented for block-solver models";
+    if (b.k_preeq || o.posteq || b.t_presim) {
+        last_error() = "pre-/post-equilibration and presimulation are not implemented for block-solver models";
         return AB_E_UNSUPPORTED;
     }
     const int npl = (o.sensi >= 1) ? b.nplist : 0;

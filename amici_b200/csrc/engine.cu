@@ -95,6 +95,7 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
     if (o->sensi >= 1 && o->ism != 1) { g_err = "only simultaneous forward sensitivities are implemented"; return AB_E_UNSUPPORTED; }
     if (!(o->rtol >= 0) || !(o->atol >= 0)) { g_err = "negative tolerance"; return AB_E_BAD_ARGUMENT; }
     if (o->nmaxevent < 0) { g_err = "nmaxevent must be non-negative"; return AB_E_BAD_ARGUMENT; }
+    if (b->k_presim && !b->t_presim) { g_err = "k_presim without t_presim"; return AB_E_BAD_ARGUMENT; }
     if ((b->k_preeq || o->posteq) && (!(o->rtol_ss >= 0) || !(o->atol_ss >= 0) || !(o->rtol_ss_sensi >= 0) || !(o->atol_ss_sensi >= 0))) {
         g_err = "steady-state tolerances must be resolved (non-negative) when k_preeq is given";
         return AB_E_BAD_ARGUMENT;
@@ -320,7 +321,7 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
     const FieldDesc fields[] = {
         AB_F(p, D, d.np, true), AB_F(k, D, d.nk, true), AB_F(my, D, nt * ny, true), AB_F(sigmay_in, D, nt * ny, true),
         AB_F(k_preeq, D, d.nk, true), AB_F(mz, D, nme * nz, true), AB_F(sigmaz_in, D, nme * nz, true),
-        AB_F(x0_in, D, nx, true), AB_F(sx0_in, D, q * nx, true),
+        AB_F(x0_in, D, nx, true), AB_F(sx0_in, D, q * nx, true), AB_F(k_presim, D, d.nk, true), AB_F(t_presim, D, 1, true),
         AB_F(status, I, 1, false), AB_F(llh, D, 1, false), AB_F(chi2, D, 1, false), AB_F(sllh, D, q, false),
         AB_F(x, D, nt * nx, false), AB_F(sx, D, nt * q * nx, false), AB_F(y, D, nt * ny, false),
         AB_F(sy, D, nt * q * ny, false), AB_F(sigmay, D, nt * ny, false), AB_F(ssigmay, D, nt * q * ny, false),

@@ -132,7 +132,7 @@ int launch_model_preeq(const ab_solver_options& o, const ab_batch& b, int* queue
 
 template <class M>
 int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
-    if (b.k_preeq || o.posteq) return launch_model_preeq<M>(o, b, queue_head, pg, st);   // the variant with the steady-state code
+    if (b.k_preeq || o.posteq || b.t_presim) return launch_model_preeq<M>(o, b, queue_head, pg, st);   // the variant with the steady-state code
     return launch_model_impl<M, false>(o, b, queue_head, pg, st);
 }
 

@@ -28,7 +28,7 @@ AB_HD bool next_t_too_close(double cur_t, double t_next) {
 // flag, not a run-time branch, so that the kernel used without pre-equilibration keeps its register budget.
 template <class M, int G, int C, bool PREEQ = false>
 struct Simulation {
-    using Solver = Bdf<M, G, C>;
+    using Solver = Bdf<M, G, C, PREEQ>;
     static constexpr int NX = M::NX, NY = M::NY, NCOLS = Solver::NCOLS;
     using Shared = typename Solver::Shared;
 
@@ -56,7 +56,7 @@ struct Simulation {
 
     // ConditionContext + Model::initialize (reference src/edata.cpp:438-556, src/model.cpp:251-278):
     // unscale parameters (reference include/amici/misc.h:164-195), x0, sx0, spline tables.
-    AB_HD void load_condition(const bool preeq) {
+    AB_HD void load_condition(const double* ksrc) {
         auto& g = bdf.g;
         g.sync();
         if (g.lane == 0) {
@@ -65,8 +65,8 @@ struct Simulation {
                 const int sc = b.pscale ? b.pscale[i] : AB_PSCALE_NONE;
                 S.p[i] = sc == AB_PSCALE_LOG10 ? pow(10.0, v) : sc == AB_PSCALE_LN ? exp(v) : v;
             }
-            // ConditionContext with FixedParameterContext::preequilibration (reference src/edata.cpp:438-556)
-            for (int i = 0; i < M::NK; ++i) S.k[i] = (preeq ? b.k_preeq : b.k)[(size_t)n * M::NK + i];
+            // ConditionContext with FixedParameterContext::simulation / preequilibration / presimulation (reference src/edata.cpp:438-556)
+            for (int i = 0; i < M::NK; ++i) S.k[i] = ksrc[(size_t)n * M::NK + i];
             M::derived(S.p, S.k);
             for (int i = 0; i < M::NH; ++i) S.h[i] = 0.0;
             for (int cc = 0; cc < NCOLS; ++cc) {
@@ -624,7 +624,11 @@ struct Simulation {
         AB_UNROLL
         for (int c = 0; c < C; ++c) sllh[c] = 0.0;
         const bool has_preeq = PREEQ && b.k_preeq != nullptr;
-        load_condition(has_preeq);
+        // presimulation (reference src/forwardproblem.cpp:284-321): integrate [t0 - t_presim, t0] with the presimulation
+        // fixed parameters (the simulation's if none are given, src/edata.cpp:531-548), nothing is recorded
+        const bool has_presim = PREEQ && b.t_presim != nullptr && b.t_presim[n] > 0.0;
+        const double* const k_presim = (PREEQ && b.k_presim) ? b.k_presim : b.k;
+        load_condition(has_preeq ? b.k_preeq : has_presim ? k_presim : b.k);
         double t = o.t0;
         int status = AB_SUCCESS;
         int it = 0;
@@ -632,7 +636,8 @@ struct Simulation {
         const int ncols_main = bdf.ncols;
         int pe_status[3] = {SS_NOT_RUN, SS_NOT_RUN, SS_NOT_RUN}, pe_steps[3] = {0, 0, 0};
         double pe_wrms = ab_nan(), pe_t = ab_nan();
-        // phase: 0 = main simulation, 1 = steady-state simulation, 2 = steady state found (finish), 3 = simulation failed
+        // phase: 0 = main simulation, 1 = steady-state simulation, 2 = steady state found (finish), 3 = simulation failed,
+        //        4 = presimulation
         int phase = 0;
         bool newton_on = false, sim_on = false, preeq_failed = false;
         // post-equilibration (t = inf output points, reference src/forwardproblem.cpp:376-387): the same steady-state machinery,
@@ -661,7 +666,12 @@ struct Simulation {
                 phase = 1;
             }
         }
-        if (phase == 0) {
+        if (PREEQ && phase == 0 && has_presim) {
+            // Model::initialize at t0 - t_presim under the presimulation context, Solver::setup (src/forwardproblem.cpp:299-316)
+            t = o.t0 - b.t_presim[n];
+            bdf.init(t);
+            phase = 4;
+        } else if (phase == 0) {
             if (M::NE > 0) {
                 // Model::initialize_events, then EventHandlingSimulator::handle_initial_events (src/forwardproblem.cpp:516-522)
                 initialize_events(o.t0);
@@ -684,6 +694,23 @@ struct Simulation {
             double tout = 0.0;
             bool one_step = false;
             if (PREEQ && phase != 0) {
+                if (phase == 4) {
+                    if (t < o.t0 && !next_t_too_close(t, o.t0)) tout = o.t0;
+                    else {
+                        // handle_main_simulation after a presimulation (src/forwardproblem.cpp:323-372): back to the simulation
+                        // condition, x0 / sx0 = the presimulated state, Solver::reinit + sens_reinit at t0
+                        g.sync();
+                        if (g.lane == 0) {
+                            for (int i = 0; i < M::NK; ++i) S.k[i] = b.k[(size_t)n * M::NK + i];
+                            M::derived(S.p, S.k);
+                        }
+                        g.sync();
+                        write_initial_state();
+                        bdf.amici_reinit(o.t0);   // the solver is not set up again: counters and step-size history carry on
+                        t = o.t0;
+                        phase = 0;
+                    }
+                }
                 if (phase == 1) {
                     // EventHandlingSimulator::run_steady_state (reference src/forwardproblem.cpp:153-243)
                     const bool check_sens = bdf.ncols > 1 && o.sensi_ss_check != 0;
@@ -735,14 +762,19 @@ struct Simulation {
                     // back to the simulation condition (ConditionContext restore) and on to the main simulation
                     g.sync();
                     if (g.lane == 0) {
-                        for (int i = 0; i < M::NK; ++i) S.k[i] = b.k[(size_t)n * M::NK + i];
+                        for (int i = 0; i < M::NK; ++i) S.k[i] = (has_presim ? k_presim : b.k)[(size_t)n * M::NK + i];
                         M::derived(S.p, S.k);
                     }
                     g.sync();
-                    write_initial_state();
-                    bdf.init(o.t0);
-                    t = o.t0;
-                    phase = 0;
+                    if (has_presim) {   // the presimulation starts from the steady state (src/forwardproblem.cpp:301-316)
+                        t = o.t0 - b.t_presim[n];
+                        phase = 4;
+                    } else {
+                        write_initial_state();
+                        t = o.t0;
+                        phase = 0;
+                    }
+                    bdf.init(t);
                     AB_UNROLL
                     for (int i = 0; i < 3; ++i) {   // keep the pre-equilibration record; pe_* are re-used by a post-equilibration
                         pre_status[i] = pe_status[i];
@@ -753,6 +785,7 @@ struct Simulation {
                     pre_wrms = pe_wrms;
                     pre_t = pe_t;
                     pe_wrms = pe_t = ab_nan();
+                    if (phase == 4) continue;   // next: the presimulation
                 }
             }
             double next_t_event = INFINITY;

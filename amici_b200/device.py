@@ -41,6 +41,10 @@ class DeviceBatch:
             self.host_inputs["x0_in"] = batch.x0
         if getattr(batch, "sx0", None) is not None and self.opts.sensi:
             self.host_inputs["sx0_in"] = batch.sx0
+        if getattr(batch, "t_presim", None) is not None and (batch.t_presim > 0).any():
+            self.host_inputs["t_presim"] = batch.t_presim
+            if batch.k_presim is not None:
+                self.host_inputs["k_presim"] = batch.k_presim
         self.inputs = {k_: torch.as_tensor(v).to(dev) for k_, v in self.host_inputs.items()}
         likelihood_only = self.opts.reporting == int(RDataReporting.likelihood)
         lk = {"status", "llh", "chi2", "sllh", "numsteps", "numrhsevals", "numerrtestfails", "numnonlinsolvconvfails", "order"}

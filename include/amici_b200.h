@@ -73,6 +73,8 @@ typedef struct ab_batch {
     const double* sigmaz_in; /* [N][nmaxevent][nz]  ExpData event noise scales, NaN = model sigma; may be NULL */
     const double* x0_in;     /* [N][nx]         ExpData::x0, initial state instead of the model's x0(p, k); NULL = model's (reference src/edata.cpp:472-480) */
     const double* sx0_in;    /* [N][nplist][nx] ExpData::sx0 on the parameter scale given by pscale; NULL = model's (src/edata.cpp:482-490, src/model.cpp:986-1024) */
+    const double* k_presim;  /* [N][nk]         ExpData::fixed_parameters_presimulation; NULL = the simulation's k (reference src/edata.cpp:531-548) */
+    const double* t_presim;  /* [N]             ExpData::t_presim: integrate from t0 - t_presim to t0 before the main simulation where > 0; NULL = none (src/forwardproblem.cpp:284-321) */
     /* ---- outputs (ReturnData fields; any may be NULL) ---- */
     int* status;             /* [N]                                  */
     double* llh;             /* [N]                                  */

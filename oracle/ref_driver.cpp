@@ -101,6 +101,9 @@ extern "C" int ref_run(ref_options const* o, ref_batch* b) {
             if (b->k_preeq)
                 e->fixed_parameters_pre_equilibration.assign(b->k_preeq + (size_t)i * nk,
                                                              b->k_preeq + (size_t)(i + 1) * nk);
+            if (b->k_presim)
+                e->fixed_parameters_presimulation.assign(b->k_presim + (size_t)i * nk, b->k_presim + (size_t)(i + 1) * nk);
+            if (b->t_presim) e->t_presim = b->t_presim[i];
             e->pscale = pscale;
             e->plist = plist;
             if (b->x0_in) e->x0.assign(b->x0_in + (size_t)i * nx, b->x0_in + (size_t)(i + 1) * nx);

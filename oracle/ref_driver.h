@@ -57,6 +57,8 @@ typedef struct {
     const double* sigmaz_in; /* [N][nmaxevent][nztrue] or NULL         */
     const double* x0_in;     /* [N][nx] ExpData::x0 or NULL            */
     const double* sx0_in;    /* [N][nplist][nx] ExpData::sx0 or NULL   */
+    const double* k_presim;  /* [N][nk] ExpData::fixed_parameters_presimulation or NULL */
+    const double* t_presim;  /* [N]     ExpData::t_presim or NULL (no presimulation)    */
     /* ---- outputs (any may be NULL) ---- */
     int* status;             /* [N]                         */
     double* llh;             /* [N]                         */

@@ -81,7 +81,7 @@ class RefBatch(C.Structure):
     _fields_ = [("N", C.c_int), ("nt", C.c_int), ("nplist", C.c_int),
                 ("ts", _dp), ("plist", _ip), ("pscale", _ip), ("p", _dp), ("k", _dp),
                 ("k_preeq", _dp), ("my", _dp), ("sigmay_in", _dp), ("mz", _dp),
-                ("sigmaz_in", _dp), ("x0_in", _dp), ("sx0_in", _dp)] + [
+                ("sigmaz_in", _dp), ("x0_in", _dp), ("sx0_in", _dp), ("k_presim", _dp), ("t_presim", _dp)] + [
         (n, _dp if t == "d" else _ip) for n, t, _ in _OUT_FIELDS]
 
 
@@ -117,6 +117,7 @@ class RefModel:
             return max(1, os.cpu_count() or int(self.lib.ref_max_threads()))
 
     def run(self, ts, p, k, *, plist=None, pscale=None, k_preeq=None, my=None, sigmay=None, x0=None, sx0=None,
+            k_presim=None, t_presim=None,
             mz=None, sigmaz=None, rtol=1e-8, atol=1e-12, rtol_fsa=np.nan, atol_fsa=np.nan,
             sensi_order=1, sensi_meth=1, ism=1, linsol=9, maxsteps=10000, newton_maxsteps=0,
             ss_mode=-1, ss_sensi_mode=-1, nmaxevent=-1, stldet=-1, reporting=0, num_threads=1,
@@ -144,7 +145,8 @@ class RefModel:
         for name, arr, shape in (("k_preeq", k_preeq, (N, d.nk)), ("my", my, (N, nt, d.nytrue)),
                                  ("sigmay_in", sigmay, (N, nt, d.nytrue)),
                                  ("mz", mz, (N, ne, d.nztrue)), ("sigmaz_in", sigmaz, (N, ne, d.nztrue)),
-                                 ("x0_in", x0, (N, d.nx)), ("sx0_in", sx0, (N, q, d.nx))):
+                                 ("x0_in", x0, (N, d.nx)), ("sx0_in", sx0, (N, q, d.nx)),
+                                 ("k_presim", k_presim, (N, d.nk)), ("t_presim", t_presim, (N,))):
             if arr is not None:
                 a = np.ascontiguousarray(arr, dtype=np.float64).reshape(shape)
                 keep.append(a)

@@ -21,7 +21,7 @@ PREEQ_FIELDS = ["x_ss", "sx_ss", "preeq_status", "preeq_numsteps", "preeq_wrms",
 EVENT_FIELDS = ["z", "sz", "rz", "srz", "sigmaz"]
 
 
-def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=None, **run_kw):
+def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=None, presim=False, **run_kw):
     m = RefModel(model)
     d = m.dims
     rng = np.random.default_rng(seed)
@@ -30,6 +30,11 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=N
     k = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.8, 1.25, (N, d.nk))
     k[0] = m.k_nominal
     k_preeq = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.5, 2.0, (N, d.nk)) if preeq else None
+    presim_kw = {}
+    if presim:   # ExpData::t_presim / fixed_parameters_presimulation; condition 2 has none
+        presim_kw = dict(k_presim=np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.5, 2.0, (N, d.nk)),
+                         t_presim=np.array([2.0, 0.5, 0.0, 10.0, 1e-3, 3.0])[:N])
+        run_kw = {**run_kw, **presim_kw}
     fields = FIELDS + (PREEQ_FIELDS if preeq else []) + (EVENT_FIELDS if d.nz > 0 else [])
     if kscale is not None:
         k = np.tile(m.k_nominal, (N, 1)) * rng.uniform(kscale[0], kscale[1], (N, d.nk))
@@ -54,7 +59,7 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=N
     if preeq:
         out["k_preeq"] = k_preeq
     for k_, v in run_kw.items():
-        out["opt_" + k_] = np.asarray(v)
+        out[k_ if k_ in presim_kw else "opt_" + k_] = np.asarray(v)
     path = os.path.join(HERE, f"{model}{tag}.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
@@ -110,7 +115,17 @@ def make_massaction_big(N=3, seed=20):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def make_presim():
+    # presimulation (reference src/forwardproblem.cpp:284-321), alone and after a pre-equilibration
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=21, tag="_presim", presim=True)
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=22, tag="_preeq_presim", preeq=True, presim=True, newton_maxsteps=50,
+         ss_mode=2, ss_sensi_mode=0)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["presim"]:
+        make_presim()
+        sys.exit(0)
     if sys.argv[1:] == ["robertson"]:
         make_robertson()
         sys.exit(0)
@@ -136,3 +151,4 @@ if __name__ == "__main__":
     make_massaction_big()
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=16, tag="_preeq_newton2", preeq=True, newton_maxsteps=2,
          ss_mode=2, ss_sensi_mode=0)
+    make_presim()

@@ -24,7 +24,9 @@ def run_emul(lib, model, g, sensi=1, **opt):
     opt = {**{k_[4:]: int(g[k_]) for k_ in g.keys() if k_.startswith("opt_")}, **opt}
     b, out, keep = _capi.make_batch(dims, g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
                                     k_preeq=g["k_preeq"] if "k_preeq" in g else None, nmaxevent=opt.get("nmaxevent", 10),
-                                    mz=g["mz"] if "mz" in g else None)
+                                    mz=g["mz"] if "mz" in g else None,
+                                    k_presim=g["k_presim"] if "k_presim" in g else None,
+                                    t_presim=g["t_presim"] if "t_presim" in g else None)
     o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=sensi, **opt)
     assert lib.emul_run(model.encode(), C.byref(o), C.byref(b)) == 0
     return out
@@ -65,6 +67,22 @@ def test_emulation_preequilibration_matches_golden(built, fixture):
     sim = g["klu_preeq_numsteps"][:, 1]
     assert (np.abs(out["preeq_numsteps"][:, 1] - sim) <= 0.15 * sim + 2).all()
     np.testing.assert_array_equal(np.isnan(out["preeq_t"]), np.isnan(g["klu_preeq_t"]))
+
+
+@pytest.mark.parametrize("fixture", ["steadystate_presim", "steadystate_preeq_presim"])
+def test_emulation_presimulation_matches_golden(built, fixture):
+    """Presimulation (ExpData::t_presim, fixed_parameters_presimulation; reference src/forwardproblem.cpp:284-321), alone and
+    after a pre-equilibration: x0 / sx0 are the presimulated state, the step counter runs on through AMICI's solver
+    re-initialisation at t0 (so the counts include the presimulation), a condition with t_presim = 0 has none."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    out = run_emul(_emul(built), "steadystate", g)
+    parity.check_against_golden(out, g)
+    ref = g["klu_numsteps"][:, -1]
+    assert (np.abs(out["numsteps"][:, -1] - ref) <= 0.1 * ref + 2).all()
+    plain = run_emul(_emul(built), "steadystate", {k_: g[k_] for k_ in g.keys() if k_ not in ("k_presim", "t_presim")})
+    i = int(np.flatnonzero(g["t_presim"] == 0)[0])
+    np.testing.assert_array_equal(out["x"][i], plain["x"][i])
+    assert not np.allclose(out["x0"][0], plain["x0"][0])
 
 
 @pytest.mark.parametrize("model", ["events", "neuron"])

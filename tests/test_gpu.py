@@ -29,7 +29,9 @@ def _run(model_name, g, sensi=True, ts=None, **solver_kw):
     if "opt_nmaxevent" in g:
         m.set_n_max_event(int(g["opt_nmaxevent"]))
     batch = ab.ExpDataBatch(m.get_timepoints(), g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
-                            k_preeq=g["k_preeq"] if "k_preeq" in g else None, mz=g["mz"] if "mz" in g else None)
+                            k_preeq=g["k_preeq"] if "k_preeq" in g else None, mz=g["mz"] if "mz" in g else None,
+                            k_presim=g["k_presim"] if "k_presim" in g else None,
+                            t_presim=g["t_presim"] if "t_presim" in g else None)
     return ab.run_simulations(m, s, batch)
 
 
@@ -94,6 +96,54 @@ def test_cuda_preequilibration_matches_golden(fixture):
     np.testing.assert_array_equal(res["preeq_numsteps"][:, [0, 2]], g["klu_preeq_numsteps"][:, [0, 2]])
     sim = g["klu_preeq_numsteps"][:, 1]
     assert (np.abs(res["preeq_numsteps"][:, 1] - sim) <= 0.15 * sim + 2).all()
+
+
+@pytest.mark.parametrize("fixture", ["steadystate_presim", "steadystate_preeq_presim"])
+def test_cuda_presimulation_matches_golden(fixture):
+    """Presimulation (reference src/forwardproblem.cpp:284-321) alone and after a pre-equilibration, through the C ABI; also as
+    a list of ExpData objects (t_presim / fixed_parameters_presimulation), which must give the same result bit for bit."""
+    import amici_b200 as ab
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    res = _run("steadystate", g)
+    parity.check_against_golden(res.fields, g)
+    ref = g["klu_numsteps"][:, -1]
+    assert (np.abs(res["numsteps"][:, -1] - ref) <= 0.1 * ref + 2).all()
+    m = ab.get_model("steadystate")
+    m.set_timepoints(g["ts"])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    if "opt_newton_maxsteps" in g:
+        s.set_newton_max_steps(int(g["opt_newton_maxsteps"]))
+        m.set_steady_state_computation_mode(int(g["opt_ss_mode"]))
+        m.set_steady_state_sensitivity_mode(int(g["opt_ss_sensi_mode"]))
+    edatas = []
+    for i in range(len(g["p"])):
+        e = ab.ExpData(m)
+        e.free_parameters, e.fixed_parameters = list(g["p"][i]), list(g["k"][i])
+        e.set_measurements(g["my"][i])
+        e.set_noise_scales(g["sigmay_in"][i])
+        e.t_presim = float(g["t_presim"][i])
+        if e.t_presim > 0:
+            e.fixed_parameters_presimulation = list(g["k_presim"][i])
+        if "k_preeq" in g:
+            e.fixed_parameters_pre_equilibration = list(g["k_preeq"][i])
+        edatas.append(e)
+    rl = ab.run_simulations(m, s, edatas)
+    for i, r in enumerate(rl):
+        if g["t_presim"][i] > 0:   # without presimulation the list path uses k, the batch path k_presim: both unused
+            np.testing.assert_array_equal(r["x"], res["x"][i])
+            np.testing.assert_array_equal(r["sllh"], res["sllh"][i])
+
+
+def test_presimulation_is_refused_for_event_models():
+    import amici_b200 as ab
+    m = ab.get_model("events")
+    m.set_timepoints(np.linspace(0, 10, 5))
+    s = m.create_solver()
+    with pytest.raises(RuntimeError, match="presimulation"):
+        ab.run_simulations(m, s, ab.ExpDataBatch(m.get_timepoints(), [m.get_free_parameters()], [m.get_fixed_parameters()], t_presim=[1.0]))
 
 
 @pytest.mark.parametrize("model", ["events", "neuron"])
