@@ -164,6 +164,8 @@ class Model:
         self._ss_mode = SteadyStateComputationMode.integrateIfNewtonFails
         self._ss_sensi_mode = SteadyStateSensitivityMode.integrateIfNewtonFails
         self._nmaxevent = 10
+        self._reinit_all = False          # Model::set_reinitialize_fixed_parameter_initial_states
+        self._reinit_idxs: list[int] = []  # Model::set_reinitialization_state_idxs
 
     # -- dimensions
     def np(self) -> int: return self._np
@@ -210,6 +212,19 @@ class Model:
     def get_fixed_parameters(self): return list(self._k)
     # steady-state / event settings of amici::Model (reference include/amici/model.h)
     def set_steady_state_computation_mode(self, mode): self._ss_mode = SteadyStateComputationMode(int(mode))
+    # re-initialisation of fixed-parameter-dependent initial states (reference src/model.cpp:1074-1097, :3110-3121)
+    def set_reinitialize_fixed_parameter_initial_states(self, flag):
+        self._reinit_all = bool(flag)
+        if not flag:
+            self._reinit_idxs = []
+    def get_reinitialize_fixed_parameter_initial_states(self): return self._reinit_all or bool(self._reinit_idxs)
+    def set_reinitialization_state_idxs(self, idxs):
+        idxs = [int(i) for i in idxs]
+        for i in idxs:
+            if i < 0 or i >= self.nx:
+                raise RuntimeError(f"Invalid state index given: {i}")
+        self._reinit_idxs = idxs
+    def get_reinitialization_state_idxs(self): return list(self._reinit_idxs)
     def get_steady_state_computation_mode(self): return self._ss_mode
     def set_steady_state_sensitivity_mode(self, mode): self._ss_sensi_mode = SteadyStateSensitivityMode(int(mode))
     def get_steady_state_sensitivity_mode(self): return self._ss_sensi_mode
@@ -422,6 +437,11 @@ class ExpData:
         self.fixed_parameters_pre_equilibration: list[float] = []   # non-empty = pre-equilibrate (edata.h)
         self.fixed_parameters_presimulation: list[float] = []       # k during the presimulation; empty = the simulation's
         self.t_presim: float = 0.0                                   # > 0: integrate [t0 - t_presim, t0] first (edata.h)
+        # ExpData(Model const&) (reference src/edata.cpp:60-72)
+        m_idxs = list(getattr(model, "_reinit_idxs", []))
+        self.reinitialize_fixed_parameter_initial_states: bool = bool(getattr(model, "_reinit_all", False)) and not m_idxs
+        self.reinitialization_state_idxs_sim: list[int] = m_idxs
+        self.reinitialization_state_idxs_presim: list[int] = []
         self.pscale: list = []
         self.plist: list[int] = []
         self.x0: list[float] = []    # initial state override (edata.h); empty = the model's x0(p, k)
@@ -496,6 +516,29 @@ class ExpData:
     def get_event_noise_scales(self): return self._sigmaz.copy()
 
 
+def _reinit_key(e) -> tuple:
+    """(simulation, presimulation) re-initialisation selection of one ExpData: "all" or a tuple of state indices
+    (ConditionContext, reference src/edata.cpp:492-548)."""
+    if e.reinitialize_fixed_parameter_initial_states:
+        return ("all", "all")
+    return (tuple(int(i) for i in e.reinitialization_state_idxs_sim), tuple(int(i) for i in e.reinitialization_state_idxs_presim))
+
+
+def _reinit_mask(sel, model, presim: bool = False) -> int:
+    if sel is None:   # the model's settings: its index list applies to the simulation context only
+        sel = True if (model._reinit_all and not model._reinit_idxs) else ([] if presim else model._reinit_idxs)
+    if sel is True:
+        return (1 << 64) - 1
+    mask = 0
+    for i in sel:
+        if int(i) < 0 or int(i) >= model.nx:
+            raise RuntimeError(f"Invalid state index given: {int(i)}")
+        if int(i) >= 64:
+            raise RuntimeError("amici_b200: state re-initialisation is limited to models with nx <= 64")
+        mask |= 1 << int(i)
+    return mask
+
+
 class ExpDataBatch:
     """Struct-of-arrays form of ``list[ExpData]`` for conditions that share ts / plist / pscale.
 
@@ -504,7 +547,8 @@ class ExpDataBatch:
     """
 
     def __init__(self, ts, p, k, my=None, sigmay=None, plist=None, pscale=None, k_preeq=None, mz=None, sigmaz=None,
-                 x0=None, sx0=None, k_presim=None, t_presim=None):
+                 x0=None, sx0=None, k_presim=None, t_presim=None,
+                 reinit_states_sim=None, reinit_states_presim=None):
         self.ts = np.ascontiguousarray(ts, dtype=np.float64)
         self.p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
         self.k = np.ascontiguousarray(np.atleast_2d(k), dtype=np.float64)
@@ -518,6 +562,8 @@ class ExpDataBatch:
         # ExpData::x0 / sx0: initial state (and its sensitivities, on the parameter scale) instead of the model's
         self.x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
         self.sx0 = None if sx0 is None else np.ascontiguousarray(sx0, dtype=np.float64)
+        # state re-initialisation after pre-equilibration / presimulation: index lists, True = all states, None = the model's
+        self.reinit_states_sim, self.reinit_states_presim = reinit_states_sim, reinit_states_presim
         # ExpData::t_presim / fixed_parameters_presimulation: per condition, 0 = no presimulation
         self.t_presim = None if t_presim is None else np.ascontiguousarray(np.broadcast_to(np.asarray(t_presim, dtype=np.float64), (self.p.shape[0],)))
         self.k_presim = None if k_presim is None else np.ascontiguousarray(np.atleast_2d(k_presim), dtype=np.float64)
@@ -593,8 +639,14 @@ class ExpDataBatch:
                     if len(e.fixed_parameters_presimulation) != model.nk():
                         raise RuntimeError("Number of fixed parameters in model does not match ExpData (presimulation).")
                     k_presim[i] = e.fixed_parameters_presimulation
+        reinit = {_reinit_key(e) for e in edatas if e is not None}
+        if len(reinit) > 1:
+            raise RuntimeError("amici_b200: all conditions of one batch must share the state re-initialisation settings")
+        r_sim, r_presim = reinit.pop() if reinit else (None, None)
         return ExpDataBatch(ts, p, k, my, sg, plist, pscale, k_preeq=k_preeq, mz=mz, sigmaz=sz, x0=x0, sx0=sx0,
-                            k_presim=k_presim, t_presim=t_presim)
+                            k_presim=k_presim, t_presim=t_presim,
+                            reinit_states_sim=True if r_sim == "all" else None if r_sim is None else list(r_sim),
+                            reinit_states_presim=True if r_presim == "all" else None if r_presim is None else list(r_presim))
 
 
 _RDATA_ALIASES = {"num_rhs_evals": "numrhsevals", "num_err_test_fails": "numerrtestfails",
@@ -690,6 +742,8 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
     if has_posteq and (np.isnan(batch.ts).any() or (batch.ts == -np.inf).any() or finite[int(np.argmin(finite)):].any()):
         raise RuntimeError("amici_b200: timepoints must be finite, followed by t = inf entries only")
     opts.posteq = int(has_posteq)
+    opts.reinit_states_sim = _reinit_mask(batch.reinit_states_sim, model)
+    opts.reinit_states_presim = _reinit_mask(batch.reinit_states_presim, model, presim=True)
     q = len(plist) if opts.sensi else 0
     d = dict(model.dims(), nz=model.nz, nmaxevent=opts.nmaxevent)
     b = _capi.BatchView(N=N, nt=nt, nplist=len(plist))
@@ -799,7 +853,8 @@ def group_edatas(model: Model, edatas: Sequence[ExpData | None]) -> list[tuple[l
         pscale = tuple(int(s) for s in (model.get_parameter_scale() if e is None or not e.pscale else e.pscale))
         preeq = e is not None and len(e.fixed_parameters_pre_equilibration) > 0
         init = (e is not None and len(e.x0) > 0, e is not None and len(e.sx0) > 0)
-        groups.setdefault((ts, plist, pscale, preeq, init), []).append(i)
+        reinit = None if e is None else _reinit_key(e)
+        groups.setdefault((ts, plist, pscale, preeq, init, reinit), []).append(i)
     return [(idx, ExpDataBatch.from_list(model, [edatas[i] for i in idx])) for idx in groups.values()]
 
 

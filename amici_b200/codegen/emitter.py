@@ -306,6 +306,13 @@ def emit_model(spec: ModelSpec) -> str:
     sig_common = "const double t, const double* x, const double* p, const double* k, const double* h, const double* spl"
 
     # x0 / sx0
+    # states whose initial value depends on fixed parameters (the index list of the reference's generated x0_fixedParameters.cpp);
+    # the reference disables re-initialisation at import when such a state also depends on parameters
+    kset, pset = set(spec.fixed), set(spec.params)
+    fixed_mask = sum(1 << i for i in range(nx) if sp.sympify(x0[i]).free_symbols & kset)
+    allowed = not any(sp.sympify(x0[i]).free_symbols & kset and sp.sympify(x0[i]).free_symbols & pset for i in range(nx))
+    A(f"    static constexpr unsigned long long X0_FIXED_MASK = {fixed_mask:#x}ull;")
+    A(f"    static constexpr bool X0_FIXED_REINIT_ALLOWED = {'true' if allowed else 'false'};")
     A("    AB_HD static void x0(const double* p, const double* k, double* x0) {")
     A("        (void)p; (void)k;")
     A(W.body([(f"x0[{i}]", x0[i]) for i in range(nx)]).rstrip("\n"))

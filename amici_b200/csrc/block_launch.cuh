@@ -93,7 +93,7 @@ int launch_block_variant(const ab_solver_options& o, const ab_batch& b, int* que
 
 template <class M>
 int launch_block_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
-    if (b.k_preeq || o.posteq || b.t_presim) {
+    if (b.k_preeq || o.posteq || b.t_presim || o.reinit_states_sim || o.reinit_states_presim) {
         last_error() = "pre-/post-equilibration and presimulation are not implemented for block-solver models";
         return AB_E_UNSUPPORTED;
     }

@@ -132,6 +132,11 @@ int launch_model_preeq(const ab_solver_options& o, const ab_batch& b, int* queue
 
 template <class M>
 int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
+    if ((o.reinit_states_sim | o.reinit_states_presim) && !M::X0_FIXED_REINIT_ALLOWED) {
+        // Model::set_reinitialize_fixed_parameter_initial_states (reference src/model.cpp:1074-1081)
+        last_error() = "State reinitialization cannot be enabled for this model: initial states depending on fixed parameters also depend on parameters";
+        return AB_E_UNSUPPORTED;
+    }
     if (b.k_preeq || o.posteq || b.t_presim) return launch_model_preeq<M>(o, b, queue_head, pg, st);   // the variant with the steady-state code
     return launch_model_impl<M, false>(o, b, queue_head, pg, st);
 }

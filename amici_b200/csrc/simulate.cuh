@@ -114,6 +114,28 @@ struct Simulation {
         }
     }
 
+    // Model::reinitialize (reference src/model.cpp:280-295; generated x0_fixedParameters.cpp / sx0_fixedParameters.cpp): the
+    // selected states whose initial value is a function of the fixed parameters are reset to it, their sensitivities to 0
+    AB_HD void reinitialize_states(const unsigned long long idxs) {
+        const unsigned long long m = idxs & M::X0_FIXED_MASK;
+        if (m == 0) return;
+        auto& g = bdf.g;
+        g.sync();
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!bdf.active(c)) continue;
+            const int cc = bdf.col(c);
+            double v[NX];
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) v[r] = 0.0;
+            if (cc == 0) M::x0(S.p, S.k, v);
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r)
+                if (m >> r & 1) S.zn[0][r][cc] = v[r];
+        }
+        g.sync();
+    }
+
     AB_HD double chain(double v, double pc) const { return v != 0.0 ? v * pc : v; }
 
     // ReturnData::get_data_output + get_data_sensis_fsa for timepoint `it` from the solver state
@@ -669,6 +691,7 @@ struct Simulation {
         if (PREEQ && phase == 0 && has_presim) {
             // Model::initialize at t0 - t_presim under the presimulation context, Solver::setup (src/forwardproblem.cpp:299-316)
             t = o.t0 - b.t_presim[n];
+            reinitialize_states(o.reinit_states_presim);   // update_and_reinit_states_and_sensitivities (:316)
             bdf.init(t);
             phase = 4;
         } else if (phase == 0) {
@@ -705,6 +728,7 @@ struct Simulation {
                             M::derived(S.p, S.k);
                         }
                         g.sync();
+                        reinitialize_states(o.reinit_states_sim);
                         write_initial_state();
                         bdf.amici_reinit(o.t0);   // the solver is not set up again: counters and step-size history carry on
                         t = o.t0;
@@ -767,9 +791,11 @@ struct Simulation {
                     }
                     g.sync();
                     if (has_presim) {   // the presimulation starts from the steady state (src/forwardproblem.cpp:301-316)
+                        reinitialize_states(o.reinit_states_presim);
                         t = o.t0 - b.t_presim[n];
                         phase = 4;
                     } else {
+                        reinitialize_states(o.reinit_states_sim);   // src/forwardproblem.cpp:350-352
                         write_initial_state();
                         t = o.t0;
                         phase = 0;

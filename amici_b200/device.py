@@ -20,6 +20,9 @@ class DeviceBatch:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.opts = solver._options(model.t0(), model)
         self.opts.posteq = int(len(batch.ts) > 0 and not np.all(np.isfinite(batch.ts)))
+        from . import _reinit_mask
+        self.opts.reinit_states_sim = _reinit_mask(getattr(batch, "reinit_states_sim", None), model)
+        self.opts.reinit_states_presim = _reinit_mask(getattr(batch, "reinit_states_presim", None), model, presim=True)
         d = dict(model.dims(), nz=model.nz, nmaxevent=self.opts.nmaxevent)
         N, nt = len(batch), len(batch.ts)
         plist = np.asarray(model.get_parameter_list(), dtype=np.int32) if batch.plist is None else batch.plist

@@ -55,6 +55,11 @@ typedef struct ab_solver_options {
     int nmaxevent;             /* Model::set_n_max_event (10): event-observable slots per event                           */
     int posteq;                /* 1 if ts ends with t = inf output points: post-equilibration after the last finite timepoint
                                   (reference src/forwardproblem.cpp:376-387); ab_run_batch sets it itself from the host ts  */
+    /* ExpData::reinitialization_state_idxs_sim / _presim as bit sets (bit i = state i; all ones =
+       ExpData::reinitialize_fixed_parameter_initial_states): after a pre-equilibration or presimulation, the selected states whose
+       initial value depends on fixed parameters are reset to x0(k) of the next phase and their sensitivities to 0
+       (Model::reinitialize, reference src/model.cpp:280-295, src/forwardproblem.cpp:316, :350-352). Models with nx <= 64. */
+    unsigned long long reinit_states_sim, reinit_states_presim;
 } ab_solver_options;
 
 /* One batch of N conditions (replaces std::vector<ExpData*> in, std::vector<ReturnData> out). */

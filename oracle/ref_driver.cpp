@@ -104,6 +104,11 @@ extern "C" int ref_run(ref_options const* o, ref_batch* b) {
             if (b->k_presim)
                 e->fixed_parameters_presimulation.assign(b->k_presim + (size_t)i * nk, b->k_presim + (size_t)(i + 1) * nk);
             if (b->t_presim) e->t_presim = b->t_presim[i];
+            e->reinitialize_fixed_parameter_initial_states = o->reinit_all != 0;
+            for (int ix = 0; ix < 31; ++ix) {
+                if (o->reinit_states_sim >> ix & 1) e->reinitialization_state_idxs_sim.push_back(ix);
+                if (o->reinit_states_presim >> ix & 1) e->reinitialization_state_idxs_presim.push_back(ix);
+            }
             e->pscale = pscale;
             e->plist = plist;
             if (b->x0_in) e->x0.assign(b->x0_in + (size_t)i * nx, b->x0_in + (size_t)(i + 1) * nx);

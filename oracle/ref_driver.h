@@ -40,6 +40,9 @@ typedef struct {
     int reporting;               /* RDataReporting: 0 full … 2 likelihood             */
     int num_threads;             /* OpenMP threads for run_simulations                */
     int failfast;
+    int reinit_all;              /* ExpData::reinitialize_fixed_parameter_initial_states                          */
+    int reinit_states_sim;       /* ExpData::reinitialization_state_idxs_sim as a bit set (bit i = state i)       */
+    int reinit_states_presim;    /* ExpData::reinitialization_state_idxs_presim as a bit set                      */
 } ref_options;
 
 typedef struct {

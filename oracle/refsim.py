@@ -31,7 +31,7 @@ class RefOptions(C.Structure):
         (n, C.c_int) for n in (
             "sensi_order", "sensi_meth", "ism", "linsol", "maxsteps", "newton_maxsteps",
             "ss_mode", "ss_sensi_mode", "nmaxevent", "stldet", "reporting", "num_threads",
-            "failfast")]
+            "failfast", "reinit_all", "reinit_states_sim", "reinit_states_presim")]
 
 
 _IN_D = ("ts",)
@@ -117,7 +117,7 @@ class RefModel:
             return max(1, os.cpu_count() or int(self.lib.ref_max_threads()))
 
     def run(self, ts, p, k, *, plist=None, pscale=None, k_preeq=None, my=None, sigmay=None, x0=None, sx0=None,
-            k_presim=None, t_presim=None,
+            k_presim=None, t_presim=None, reinit_all=False, reinit_states_sim=0, reinit_states_presim=0,
             mz=None, sigmaz=None, rtol=1e-8, atol=1e-12, rtol_fsa=np.nan, atol_fsa=np.nan,
             sensi_order=1, sensi_meth=1, ism=1, linsol=9, maxsteps=10000, newton_maxsteps=0,
             ss_mode=-1, ss_sensi_mode=-1, nmaxevent=-1, stldet=-1, reporting=0, num_threads=1,
@@ -137,7 +137,9 @@ class RefModel:
                          sensi_order=sensi_order, sensi_meth=sensi_meth, ism=ism, linsol=linsol,
                          maxsteps=maxsteps, newton_maxsteps=newton_maxsteps, ss_mode=ss_mode,
                          ss_sensi_mode=ss_sensi_mode, nmaxevent=nmaxevent, stldet=stldet,
-                         reporting=reporting, num_threads=num_threads, failfast=int(failfast))
+                         reporting=reporting, num_threads=num_threads, failfast=int(failfast),
+                         reinit_all=int(reinit_all), reinit_states_sim=int(reinit_states_sim),
+                         reinit_states_presim=int(reinit_states_presim))
         b = RefBatch(N=N, nt=nt, nplist=q)
         keep = [ts, p, k, plist, pscale]
         b.ts, b.p, b.k = ts.ctypes.data_as(_dp), p.ctypes.data_as(_dp), k.ctypes.data_as(_dp)

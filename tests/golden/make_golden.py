@@ -120,6 +120,11 @@ def make_presim():
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=21, tag="_presim", presim=True)
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=22, tag="_preeq_presim", preeq=True, presim=True, newton_maxsteps=50,
          ss_mode=2, ss_sensi_mode=0)
+    # state re-initialisation (ExpData::reinitialization_state_idxs_sim / _presim as bit sets; reference src/model.cpp:280-295)
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=23, tag="_preeq_reinit", preeq=True, newton_maxsteps=50,
+         ss_mode=2, ss_sensi_mode=0, reinit_states_sim=0b101)
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=24, tag="_preeq_presim_reinit", preeq=True, presim=True, newton_maxsteps=50,
+         ss_mode=2, ss_sensi_mode=0, reinit_states_sim=0b010, reinit_states_presim=0b101)
 
 
 if __name__ == "__main__":

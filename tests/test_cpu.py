@@ -69,7 +69,7 @@ def test_emulation_preequilibration_matches_golden(built, fixture):
     np.testing.assert_array_equal(np.isnan(out["preeq_t"]), np.isnan(g["klu_preeq_t"]))
 
 
-@pytest.mark.parametrize("fixture", ["steadystate_presim", "steadystate_preeq_presim"])
+@pytest.mark.parametrize("fixture", ["steadystate_presim", "steadystate_preeq_presim", "steadystate_preeq_presim_reinit"])
 def test_emulation_presimulation_matches_golden(built, fixture):
     """Presimulation (ExpData::t_presim, fixed_parameters_presimulation; reference src/forwardproblem.cpp:284-321), alone and
     after a pre-equilibration: x0 / sx0 are the presimulated state, the step counter runs on through AMICI's solver
@@ -83,6 +83,18 @@ def test_emulation_presimulation_matches_golden(built, fixture):
     i = int(np.flatnonzero(g["t_presim"] == 0)[0])
     np.testing.assert_array_equal(out["x"][i], plain["x"][i])
     assert not np.allclose(out["x0"][0], plain["x0"][0])
+
+
+def test_emulation_state_reinitialisation_matches_golden(built):
+    """ExpData::reinitialization_state_idxs_sim after a pre-equilibration (Model::reinitialize, reference src/model.cpp:280-295):
+    states 0 and 2 restart from x0(k) with zero sensitivities, state 1 keeps its steady state; x0 / sx0 report exactly that."""
+    g = np.load(os.path.join(GOLD, "steadystate_preeq_reinit.npz"))
+    out = run_emul(_emul(built), "steadystate", g)
+    parity.check_against_golden(out, g)
+    np.testing.assert_array_equal(out["x0"][:, [0, 2]], g["k"][:, [0, 2]])
+    np.testing.assert_array_equal(out["sx0"][:, :, [0, 2]], 0.0)
+    np.testing.assert_array_equal(out["x0"][:, 1], out["x_ss"][:, 1])
+    np.testing.assert_array_equal(out["sx0"][:, :, 1], out["sx_ss"][:, :, 1])
 
 
 @pytest.mark.parametrize("model", ["events", "neuron"])

@@ -31,8 +31,13 @@ def _run(model_name, g, sensi=True, ts=None, **solver_kw):
     batch = ab.ExpDataBatch(m.get_timepoints(), g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
                             k_preeq=g["k_preeq"] if "k_preeq" in g else None, mz=g["mz"] if "mz" in g else None,
                             k_presim=g["k_presim"] if "k_presim" in g else None,
-                            t_presim=g["t_presim"] if "t_presim" in g else None)
+                            t_presim=g["t_presim"] if "t_presim" in g else None,
+                            reinit_states_sim=_bits(g, "opt_reinit_states_sim"), reinit_states_presim=_bits(g, "opt_reinit_states_presim"))
     return ab.run_simulations(m, s, batch)
+
+
+def _bits(g, key):
+    return [i for i in range(32) if int(g[key]) >> i & 1] if key in g else None
 
 
 @pytest.mark.parametrize("fixture,model", [("jakstat_adjoint", "jakstat_adjoint"), ("jakstat_adjoint_log10", "jakstat_adjoint"),
@@ -98,7 +103,7 @@ def test_cuda_preequilibration_matches_golden(fixture):
     assert (np.abs(res["preeq_numsteps"][:, 1] - sim) <= 0.15 * sim + 2).all()
 
 
-@pytest.mark.parametrize("fixture", ["steadystate_presim", "steadystate_preeq_presim"])
+@pytest.mark.parametrize("fixture", ["steadystate_presim", "steadystate_preeq_presim", "steadystate_preeq_presim_reinit"])
 def test_cuda_presimulation_matches_golden(fixture):
     """Presimulation (reference src/forwardproblem.cpp:284-321) alone and after a pre-equilibration, through the C ABI; also as
     a list of ExpData objects (t_presim / fixed_parameters_presimulation), which must give the same result bit for bit."""
@@ -129,12 +134,90 @@ def test_cuda_presimulation_matches_golden(fixture):
             e.fixed_parameters_presimulation = list(g["k_presim"][i])
         if "k_preeq" in g:
             e.fixed_parameters_pre_equilibration = list(g["k_preeq"][i])
+        e.reinitialization_state_idxs_sim = _bits(g, "opt_reinit_states_sim") or []
+        e.reinitialization_state_idxs_presim = _bits(g, "opt_reinit_states_presim") or []
         edatas.append(e)
     rl = ab.run_simulations(m, s, edatas)
     for i, r in enumerate(rl):
         if g["t_presim"][i] > 0:   # without presimulation the list path uses k, the batch path k_presim: both unused
             np.testing.assert_array_equal(r["x"], res["x"][i])
             np.testing.assert_array_equal(r["sllh"], res["sllh"][i])
+
+
+def test_cuda_presimulation_jakstat_matches_reference():
+    """Presimulation on the one-warp-per-condition kernel (JAK-STAT, 17 sensitivities, spline input evaluated at t < t0)
+    against the compiled reference; a condition with t_presim = 0 is bit-identical to the run without presimulation."""
+    import amici_b200 as ab
+    from oracle import refsim
+    if not refsim.available("jakstat_adjoint"):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint.npz"))
+    N = 4
+    p, k, ts = g["p"][:N], g["k"][:N], g["ts"]
+    kps, tps = k * np.array([[1.3, 0.8]]), np.array([5.0, 0.0, 20.0, 1.0])
+    m = ab.get_model("jakstat_adjoint")
+    m.set_timepoints(ts)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k, k_presim=kps, t_presim=tps))
+    plain = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
+    r = refsim.RefModel("jakstat_adjoint").run(ts, p, k, sensi_order=1, k_presim=kps, t_presim=tps)
+    np.testing.assert_array_equal(res["status"], r["status"])
+    np.testing.assert_allclose(res["x0"], r["x0"].reshape(res["x0"].shape), rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(res["x"], r["x"].reshape(res["x"].shape), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(res["sx"], r["sx"].reshape(res["sx"].shape), rtol=1e-3, atol=1e-6)
+    ref = r["numsteps"][:, -1]
+    assert (np.abs(res["numsteps"][:, -1] - ref) <= 0.1 * ref).all()
+    np.testing.assert_array_equal(res["x"][1], plain["x"][1])
+    assert not np.allclose(res["x0"][0], plain["x0"][0])
+
+
+def test_cuda_state_reinitialisation_matches_golden():
+    """Re-initialisation of fixed-parameter-dependent initial states after a pre-equilibration: the index-list golden, then
+    `reinitialize_fixed_parameter_initial_states = True` on ExpData objects against the live reference, and the model-level
+    setter; a model whose k-dependent initial states also depend on parameters refuses it like the reference."""
+    import amici_b200 as ab
+    from oracle import refsim
+    g = np.load(os.path.join(GOLD, "steadystate_preeq_reinit.npz"))
+    res = _run("steadystate", g)
+    parity.check_against_golden(res.fields, g)
+    np.testing.assert_array_equal(res["x0"][:, [0, 2]], g["k"][:, [0, 2]])
+    np.testing.assert_array_equal(res["sx0"][:, :, [0, 2]], 0.0)
+    np.testing.assert_array_equal(res["x0"][:, 1], res["x_ss"][:, 1])
+    m = ab.get_model("steadystate")
+    m.set_timepoints(g["ts"])
+    m.set_steady_state_computation_mode(2)
+    m.set_steady_state_sensitivity_mode(0)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    s.set_newton_max_steps(50)
+    edatas = []
+    for i in range(len(g["p"])):
+        e = ab.ExpData(m)
+        e.free_parameters, e.fixed_parameters = list(g["p"][i]), list(g["k"][i])
+        e.fixed_parameters_pre_equilibration = list(g["k_preeq"][i])
+        e.reinitialize_fixed_parameter_initial_states = True
+        edatas.append(e)
+    rl = ab.run_simulations(m, s, edatas)
+    m.set_reinitialize_fixed_parameter_initial_states(True)
+    rm = ab.run_simulations(m, s, ab.ExpDataBatch(g["ts"], g["p"], g["k"], k_preeq=g["k_preeq"]))
+    for i, r in enumerate(rl):
+        np.testing.assert_array_equal(r["x0"], g["k"][i, :3])
+        np.testing.assert_array_equal(r["x"], rm["x"][i])
+    if refsim.available("steadystate"):
+        r = refsim.RefModel("steadystate").run(g["ts"], g["p"], g["k"], k_preeq=g["k_preeq"], sensi_order=1, newton_maxsteps=50,
+                                               ss_mode=2, ss_sensi_mode=0, reinit_all=True)
+        np.testing.assert_allclose(rm["x"], r["x"].reshape(rm["x"].shape), rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(rm["sx"], r["sx"].reshape(rm["sx"].shape), rtol=1e-3, atol=1e-6)
+    n = ab.get_model("neuron")
+    n.set_timepoints([0.0, 1.0])
+    n.set_reinitialize_fixed_parameter_initial_states(True)
+    with pytest.raises(RuntimeError, match="[Rr]einitiali"):
+        ab.run_simulations(n, n.create_solver(), ab.ExpDataBatch([0.0, 1.0], [n.get_free_parameters()], [n.get_fixed_parameters()]))
 
 
 def test_presimulation_is_refused_for_event_models():
