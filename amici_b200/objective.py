@@ -44,6 +44,17 @@ class ParameterMapping:
         return ParameterMapping(self.index[lo:hi], self.value[lo:hi])
 
 
+class FixedParameterMapping(ParameterMapping):
+    """Array form of PEtab's ``map_sim_fix`` / ``map_preeq_fix`` (reference petab/v1/_conditions.py: fixed parameters of the
+    simulation and of the pre-equilibration condition): ``k[n, i]`` is the UNSCALED value of problem parameter ``index[n, i]``,
+    or the number ``value[n, i]`` where ``index[n, i] == -1``.  Fixed parameters carry no gradient."""
+
+
+def unscale(theta: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """Problem parameters from their parameter scale (0 none, 1 ln, 2 log10; reference include/amici/misc.h:164-195)."""
+    return torch.where(scale == 2, torch.pow(10.0, theta), torch.where(scale == 1, torch.exp(theta), theta))
+
+
 def fill_parameters(theta: torch.Tensor, index: torch.Tensor, value: torch.Tensor) -> torch.Tensor:
     """``fill_in_parameters``: p[n, i] = theta[index[n, i]] where mapped, else value[n, i]."""
     return torch.where(index >= 0, theta[index.clamp(min=0)], value)
@@ -69,9 +80,24 @@ class ShardedObjective:
     ``from_device_batch`` builds it from a ``DeviceBatch`` (the CUDA engine); tests may inject another one.
     """
 
-    def __init__(self, n_problem: int, mapping: ParameterMapping, plist, solve, device=None):
+    def __init__(self, n_problem: int, mapping: ParameterMapping, plist, solve, device=None, fixed=None, fixed_preeq=None,
+                 theta_scale=None):
         self.n_problem = int(n_problem)
         self.device = device or torch.device("cpu")
+        # fixed parameters mapped from problem parameters: ``solve`` is then called as solve(p, k, k_preeq) (None = not mapped)
+        self.fixed = self.fixed_preeq = None
+        for name, fm in (("fixed", fixed), ("fixed_preeq", fixed_preeq)):
+            if fm is None:
+                continue
+            if len(fm) != len(mapping):
+                raise ValueError("one fixed-parameter mapping row per condition")
+            if fm.index.size and fm.index.max() >= self.n_problem:
+                raise ValueError("fixed-parameter mapping refers to a problem parameter >= n_problem")
+            setattr(self, name, (torch.as_tensor(fm.index, device=self.device), torch.as_tensor(fm.value, device=self.device)))
+        ts = np.zeros(self.n_problem, dtype=np.int64) if theta_scale is None else np.asarray([int(v) for v in theta_scale], dtype=np.int64)
+        if ts.shape != (self.n_problem,):
+            raise ValueError("theta_scale must have n_problem entries")
+        self.theta_scale = torch.as_tensor(ts, device=self.device)
         if mapping.index.size and mapping.index.max() >= self.n_problem:
             raise ValueError("mapping refers to a problem parameter >= n_problem")
         self.index = torch.as_tensor(mapping.index, device=self.device)
@@ -82,24 +108,36 @@ class ShardedObjective:
         self.last = None   # (status, llh, sllh) of the last call, per condition of this shard
 
     @classmethod
-    def from_device_batch(cls, db, n_problem: int, mapping: ParameterMapping):
-        """Objective over the conditions of a ``DeviceBatch`` (this rank's shard); ``mapping`` has one row per condition."""
+    def from_device_batch(cls, db, n_problem: int, mapping: ParameterMapping, fixed=None, fixed_preeq=None, theta_scale=None):
+        """Objective over the conditions of a ``DeviceBatch`` (this rank's shard); ``mapping`` has one row per condition.
+        ``fixed`` / ``fixed_preeq`` (``FixedParameterMapping``) fill the batch's k / k_preeq from the problem parameters too."""
         if len(mapping) != db.N:
             raise ValueError("one mapping row per condition of the batch")
+        if fixed_preeq is not None and "k_preeq" not in db.inputs:
+            raise ValueError("the batch has no pre-equilibration condition (k_preeq) to map onto")
 
-        def solve(p):
+        def solve(p, k=None, k_preeq=None):
             db.inputs["p"].copy_(p)
+            if k is not None:
+                db.inputs["k"].copy_(k)
+            if k_preeq is not None:
+                db.inputs["k_preeq"].copy_(k_preeq)
             db.solve()
             return db.out["status"], db.out["llh"], db.out.get("sllh")
         plist = db.host_inputs["plist"][: db.q] if db.q else []
-        return cls(n_problem, mapping, plist, solve, db.device)
+        return cls(n_problem, mapping, plist, solve, db.device, fixed=fixed, fixed_preeq=fixed_preeq, theta_scale=theta_scale)
 
     def __call__(self, theta):
         theta = torch.as_tensor(theta, dtype=torch.float64, device=self.device)
         if theta.shape != (self.n_problem,):
             raise ValueError("theta must have n_problem entries")
         p = fill_parameters(theta, self.index, self.value)
-        status, llh, sllh = self.solve(p)
+        if self.fixed is None and self.fixed_preeq is None:
+            status, llh, sllh = self.solve(p)
+        else:
+            lin = unscale(theta, self.theta_scale)
+            ks = [None if fm is None else fill_parameters(lin, fm[0], fm[1]) for fm in (self.fixed, self.fixed_preeq)]
+            status, llh, sllh = self.solve(p, ks[0], ks[1])
         self.last = (status, llh, sllh)
         obj = aggregate(self.n_problem, self.index_plist, status, llh, sllh)
         allreduce_objective(obj)

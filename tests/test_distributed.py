@@ -161,3 +161,26 @@ def test_objective_failed_condition_gives_nan_and_no_gradient():
         return torch.tensor([0, -4], dtype=torch.int32), torch.tensor([1.0, float("nan")]), torch.zeros(2, 2, dtype=torch.float64)
     llh, grad = ShardedObjective(2, ParameterMapping(index), [0, 1], solve)(np.array([1.0, 2.0]))
     assert np.isnan(llh) and grad is None
+
+
+def test_objective_fills_fixed_parameters_from_problem_parameters():
+    """map_sim_fix / map_preeq_fix: k and k_preeq get the UNSCALED problem parameter (or the condition table's number), the
+    free parameters stay on their scale; fixed parameters add nothing to the gradient."""
+    import torch
+    from amici_b200.objective import FixedParameterMapping, ParameterMapping, ShardedObjective
+    seen = {}
+
+    def solve(p, k, k_preeq):
+        seen.update(p=p.clone(), k=k.clone(), k_preeq=k_preeq)
+        return torch.zeros(2, dtype=torch.int32), torch.tensor([1.0, 2.0], dtype=torch.float64), torch.ones(2, 1, dtype=torch.float64)
+    theta = np.array([-1.0, 2.0, np.log(3.0)])
+    obj = ShardedObjective(3, ParameterMapping(np.array([[0], [0]])), [0], solve,
+                           fixed=FixedParameterMapping(np.array([[1, -1], [2, 0]]), np.array([[0.0, 7.0], [0.0, 0.0]])),
+                           theta_scale=[2, 0, 1])
+    llh, grad = obj(theta)
+    np.testing.assert_allclose(seen["p"].numpy(), [[-1.0], [-1.0]])
+    np.testing.assert_allclose(seen["k"].numpy(), [[2.0, 7.0], [3.0, 0.1]], rtol=1e-15)
+    assert seen["k_preeq"] is None and llh == 3.0
+    np.testing.assert_array_equal(grad, [2.0, 0.0, 0.0])
+    with pytest.raises(ValueError):
+        ShardedObjective(3, ParameterMapping(np.array([[0], [0]])), [0], solve, fixed=FixedParameterMapping(np.array([[3, -1], [2, 0]])))

@@ -763,3 +763,52 @@ def test_objective_gradient_matches_finite_differences():
         e[i] = 1e-5
         fd = (obj(theta + e)[0] - obj(theta - e)[0]) / 2e-5
         np.testing.assert_allclose(grad[i], fd, rtol=2e-5, atol=1e-6, err_msg=f"problem parameter {i}")
+
+
+def test_objective_with_mapped_fixed_parameters_and_preequilibration():
+    """The PEtab-shaped objective on a pre-equilibrated batch: k and k_preeq are filled on the device from the problem
+    parameters (map_sim_fix / map_preeq_fix), states 0 and 2 are re-initialised for the simulation condition; llh and the
+    aggregated gradient equal a direct run_simulations call with the same numbers."""
+    import torch
+    import amici_b200 as ab
+    from amici_b200.device import DeviceBatch
+    from amici_b200.objective import FixedParameterMapping, ParameterMapping, ShardedObjective
+    g = np.load(os.path.join(GOLD, "steadystate_preeq_reinit.npz"))
+    N, npar = g["p"].shape
+    m = ab.get_model("steadystate")
+    m.set_timepoints(g["ts"])
+    m.set_parameter_scale([ab.ParameterScaling.log10] * npar)
+    m.set_steady_state_computation_mode(2)
+    m.set_steady_state_sensitivity_mode(0)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    s.set_newton_max_steps(50)
+    my = np.nan_to_num(g["my"], nan=0.3)
+    sig = np.full_like(my, 0.1)
+    # problem parameters: the 5 model parameters (log10), then one dose per condition (linear) used as k[0] of the simulation
+    # condition and, halved by the table for even conditions, left as a number in the pre-equilibration condition
+    theta = np.concatenate([np.log10(g["p"][0]), g["k"][:, 0]])
+    index = np.tile(np.arange(npar), (N, 1))
+    kidx = np.full((N, 4), -1)
+    kidx[:, 0] = npar + np.arange(N)
+    kval = g["k"].copy()
+    kpidx = np.full((N, 4), -1)
+    kpidx[::2, 1] = npar + np.arange(N)[::2]
+    kpval = g["k_preeq"].copy()
+    k_expect, kp_expect = g["k"].copy(), g["k_preeq"].copy()
+    kp_expect[::2, 1] = g["k"][::2, 0]
+    batch = ab.ExpDataBatch(g["ts"], np.zeros((N, npar)), np.ones((N, 4)), my=my, sigmay=sig, pscale=[2] * npar,
+                            k_preeq=np.ones((N, 4)), reinit_states_sim=[0, 2])
+    db = DeviceBatch(m, s, batch, torch.device("cuda", 0))
+    obj = ShardedObjective.from_device_batch(db, npar + N, ParameterMapping(index), fixed=FixedParameterMapping(kidx, kval),
+                                             fixed_preeq=FixedParameterMapping(kpidx, kpval), theta_scale=[2] * npar + [0] * N)
+    llh, grad = obj(theta)
+    direct = ab.run_simulations(m, s, ab.ExpDataBatch(g["ts"], np.tile(theta[:npar], (N, 1)), k_expect, my=my, sigmay=sig,
+                                                      pscale=[2] * npar, k_preeq=kp_expect, reinit_states_sim=[0, 2]))
+    assert (direct["status"] == 0).all()
+    np.testing.assert_allclose(llh, direct["llh"].sum(), rtol=1e-12)
+    np.testing.assert_allclose(grad[:npar], direct["sllh"].sum(0), rtol=1e-10, atol=1e-12)
+    np.testing.assert_array_equal(grad[npar:], 0.0)
+    np.testing.assert_array_equal(direct["x0"][:, [0, 2]], k_expect[:, [0, 2]])
