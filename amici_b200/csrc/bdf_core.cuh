@@ -1452,17 +1452,19 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
     // -----------------------------------------------------------------------------------------
     // max over active columns of WRMS(v_col, ewt_col)  (N_VWrmsNorm_SensWrapper + cvSensUpdateNorm,
     // reference sundials_nvector_senswrapper.c:426-440; errconS = TRUE in AMICI, src/solver.cpp:641-656)
+    // (three partial sums per column: the dependent DFMA chain of a 9-state column is 3 + 2 long instead of 9)
     AB_HD double wrms_max(const double (&v)[C][NX]) const {
         double m = 0.0;
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             if (!active(c)) continue;
-            double s = 0.0;
+            double s3[3] = {0.0, 0.0, 0.0};
             AB_UNROLL
             for (int r = 0; r < NX; ++r) {
                 const double pr = v[c][r] * ewt[c][r];
-                s += pr * pr;
+                s3[r % 3] += pr * pr;
             }
+            const double s = (s3[0] + s3[1]) + s3[2];
             const double n = sqrt(s * (1.0 / NX));
             m = (n > m || n != n) ? n : m;
         }
@@ -1474,12 +1476,13 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             if (!active(c)) continue;
-            double s = 0.0;
+            double s3[3] = {0.0, 0.0, 0.0};
             AB_UNROLL
             for (int r = 0; r < NX; ++r) {
                 const double pr = (pending ? S.zn[j][r][col(c)] + lj * acor[c][r] : S.zn[j][r][col(c)]) * ewt[c][r];
-                s += pr * pr;
+                s3[r % 3] += pr * pr;
             }
+            const double s = (s3[0] + s3[1]) + s3[2];
             const double n = sqrt(s * (1.0 / NX));
             m = (n > m || n != n) ? n : m;
         }
