@@ -27,7 +27,8 @@ def scaled(a, b):
     return float(np.max(np.abs(a[both] - b[both]) / (10 * ATOL + 10 * RTOL * np.abs(b[both]))))
 
 
-def report(title, model, refname, ts, p, k, K, fields, sensi=True, k_preeq=None, setup=None, ref_kw=None, my=None):
+def report(title, model, refname, ts, p, k, K, fields, sensi=True, k_preeq=None, setup=None, ref_kw=None, my=None, batch_kw=None,
+           ref_batch_kw=None):
     m = ab.get_model(model)
     m.set_timepoints(ts)
     if setup:
@@ -42,11 +43,12 @@ def report(title, model, refname, ts, p, k, K, fields, sensi=True, k_preeq=None,
     N = len(p)
     sig = None if my is None else np.full_like(my, 0.1)
     want = ["status", "numsteps"] + fields
-    res = ab.run_batch(m, s, ab.ExpDataBatch(ts, p, k, my=my, sigmay=sig, k_preeq=k_preeq), fields=want)
+    res = ab.run_batch(m, s, ab.ExpDataBatch(ts, p, k, my=my, sigmay=sig, k_preeq=k_preeq, **(batch_kw or {})), fields=want)
     ref = RefModel(refname)
     kw = dict(sensi_order=1 if sensi else 0, rtol=RTOL, atol=ATOL, num_threads=ref.max_threads(), fields=want, **(ref_kw or {}))
     sl = slice(0, K)
     common = dict(my=None if my is None else my[sl], sigmay=None if sig is None else sig[sl], k_preeq=None if k_preeq is None else k_preeq[sl])
+    common.update({k_: (v[sl] if isinstance(v, np.ndarray) else v) for k_, v in (ref_batch_kw or {}).items()})
     r_klu = ref.run(ts, p[sl], k[sl], linsol=9, **common, **kw)
     r_dense = ref.run(ts, p[sl], k[sl], linsol=1, **common, **kw)
     st_g, st_r = res["status"][sl], r_klu["status"]
@@ -72,7 +74,27 @@ def noisy_measurements(refname, ts, p, k, rng, **kw):
     return None
 
 
+def presim_report(N=65536, K=2048):
+    """configs[2]-sized steadystate batch with the full condition context: pre-equilibration, presimulation with its own fixed
+    parameters (a quarter of the conditions have none), re-initialisation of states 0 and 2 for the simulation."""
+    p0, k0 = nominal("steadystate")
+    rng = np.random.default_rng(5)
+    p = np.tile(p0, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, 5))
+    k, kp, kps = (np.tile(k0, (N, 1)) * rng.uniform(0.5, 2, (N, 4)) for _ in range(3))
+    tps = rng.uniform(0.1, 5.0, N)
+    tps[::4] = 0.0
+    report("steadystate: pre-equilibration + presimulation + state re-initialisation, forward sensitivities", "steadystate", "steadystate",
+           np.linspace(0, 10, 11), p, k, K, ["x0", "sx0", "x", "sx", "llh", "sllh", "x_ss", "sx_ss"], k_preeq=kp,
+           my=rng.uniform(0.1, 1.0, (N, 11, 3)),
+           setup=lambda m: (m.set_steady_state_computation_mode(2), m.set_steady_state_sensitivity_mode(0)),
+           ref_kw=dict(newton_maxsteps=50, ss_mode=2, ss_sensi_mode=0, reinit_states_sim=0b101),
+           batch_kw=dict(k_presim=kps, t_presim=tps, reinit_states_sim=[0, 2]), ref_batch_kw=dict(k_presim=kps, t_presim=tps))
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["presim"]:
+        presim_report()
+        sys.exit(0)
     print("# Round 1 — parity at BASELINE sizes (tools/parity_report.py, run on the B200 box)\n")
     print("Unit: multiples of the tolerance BASELINE.json states (10*rtol relative / 10*atol absolute at rtol 1e-8, atol 1e-12); the second "
           "column is the reference's own spread between its two linear solvers on the same inputs.")
