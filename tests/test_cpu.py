@@ -403,3 +403,36 @@ def test_emitter_is_reproducible(tmp_path):
     for p in models.generate_all(str(tmp_path)):
         committed = os.path.join(ROOT, "amici_b200", "csrc", "models", os.path.basename(p))
         assert open(p).read() == open(committed).read(), os.path.basename(p)
+
+
+@pytest.mark.parametrize("preeq", [False, True])
+def test_emulation_full_condition_context_matches_reference(built, preeq):
+    """ForwardProblem::run end to end (reference src/forwardproblem.cpp:241-253): [pre-equilibration ->] presimulation -> main
+    simulation with state 2 re-initialised -> post-equilibration, against the compiled reference: status, Newton step counts
+    of the post-equilibration, integrator step counts, values."""
+    from oracle import refsim
+    if not refsim.available("steadystate"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = refsim.RefModel("steadystate")
+    rng = np.random.default_rng(8)
+    N = 6
+    p = np.tile(ref.p_nominal, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, 5))
+    k, kps, kpe = (np.tile(ref.k_nominal, (N, 1)) * rng.uniform(0.5, 2, (N, 4)) for _ in range(3))
+    tps = np.array([2.0, 0.5, 0.0, 10.0, 1e-3, 3.0])
+    ts = np.concatenate([np.linspace(0, 10, 6), [np.inf]])
+    kp = kpe if preeq else None
+    kw = dict(newton_maxsteps=50, ss_mode=2, ss_sensi_mode=0, reinit_states_sim=0b100)
+    r = ref.run(ts, p, k, k_preeq=kp, sensi_order=1, k_presim=kps, t_presim=tps, **kw)
+    b, out, keep = _capi.make_batch(MODEL_DIMS["steadystate"], ts, p, k, k_preeq=kp, k_presim=kps, t_presim=tps)
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1, posteq=1, **kw)
+    assert _emul(built).emul_run(b"steadystate", C.byref(o), C.byref(b)) == 0
+    np.testing.assert_array_equal(out["status"], r["status"])
+    np.testing.assert_array_equal(out["posteq_status"], r["posteq_status"])
+    np.testing.assert_array_equal(out["posteq_numsteps"][:, 0], r["posteq_numsteps"][:, 0])
+    steps = r["numsteps"][:, -2]
+    assert (np.abs(out["numsteps"][:, -2] - steps) <= 0.1 * steps + 2).all()
+    np.testing.assert_array_equal(out["x0"][:, 2], k[:, 2])
+    np.testing.assert_allclose(out["x0"], r["x0"].reshape(out["x0"].shape), rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(out["x"], r["x"].reshape(out["x"].shape), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(out["sx"], r["sx"].reshape(out["sx"].shape), rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out["llh"], r["llh"], rtol=1e-5)
