@@ -812,3 +812,41 @@ def test_objective_with_mapped_fixed_parameters_and_preequilibration():
     np.testing.assert_allclose(grad[:npar], direct["sllh"].sum(0), rtol=1e-10, atol=1e-12)
     np.testing.assert_array_equal(grad[npar:], 0.0)
     np.testing.assert_array_equal(direct["x0"][:, [0, 2]], k_expect[:, [0, 2]])
+
+
+@pytest.mark.parametrize("preeq", [False, True])
+def test_cuda_full_condition_context_matches_reference(preeq):
+    """[pre-equilibration ->] presimulation -> main simulation with state 2 re-initialised -> post-equilibration through the
+    C ABI against the compiled reference (the CPU suite runs the same case on the host emulation)."""
+    import amici_b200 as ab
+    from oracle import refsim
+    if not refsim.available("steadystate"):
+        pytest.skip("oracle/_ref not built")
+    ref = refsim.RefModel("steadystate")
+    rng = np.random.default_rng(8)
+    N = 6
+    p = np.tile(ref.p_nominal, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, 5))
+    k, kps, kpe = (np.tile(ref.k_nominal, (N, 1)) * rng.uniform(0.5, 2, (N, 4)) for _ in range(3))
+    tps = np.array([2.0, 0.5, 0.0, 10.0, 1e-3, 3.0])
+    ts = np.concatenate([np.linspace(0, 10, 6), [np.inf]])
+    kp = kpe if preeq else None
+    r = ref.run(ts, p, k, k_preeq=kp, sensi_order=1, k_presim=kps, t_presim=tps, newton_maxsteps=50, ss_mode=2, ss_sensi_mode=0,
+                reinit_states_sim=0b100)
+    m = ab.get_model("steadystate")
+    m.set_timepoints(ts)
+    m.set_steady_state_computation_mode(2)
+    m.set_steady_state_sensitivity_mode(0)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    s.set_newton_max_steps(50)
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k, k_preeq=kp, k_presim=kps, t_presim=tps, reinit_states_sim=[2]))
+    np.testing.assert_array_equal(res["status"], r["status"])
+    np.testing.assert_array_equal(res["posteq_status"], r["posteq_status"])
+    np.testing.assert_array_equal(res["posteq_numsteps"][:, 0], r["posteq_numsteps"][:, 0])
+    steps = r["numsteps"][:, -2]
+    assert (np.abs(res["numsteps"][:, -2] - steps) <= 0.1 * steps + 2).all()
+    np.testing.assert_array_equal(res["x0"][:, 2], k[:, 2])
+    np.testing.assert_allclose(res["x"], r["x"].reshape(res["x"].shape), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(res["sx"], r["sx"].reshape(res["sx"].shape), rtol=1e-3, atol=1e-6)
