@@ -570,7 +570,7 @@ AB_HD int bdf_sldet_lanes(const Group<G>& g, const double (&ssdat)[5][8], const 
 
 // x^(1/n) for the four step-size formulas (eta = 1/((bias*err)^(1/n) + addon))
 AB_HD double nth_root(double x, int n) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(AB_EXACT_ROOT)
     // Step-size ratios are heuristics that CVODES itself clips and thresholds (eta < 1.5 keeps h, eta <= etamax):
     // single-precision exp2/log2 (relative error ~1e-6 in eta) instead of the ~150-instruction double pow.
     return (double)exp2f(__log2f((float)x) * (1.0f / (float)n));

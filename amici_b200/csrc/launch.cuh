@@ -18,6 +18,9 @@
 #ifndef AB_THREADS_G32
 #define AB_THREADS_G32 256
 #endif
+#ifndef AB_THREADS_SMALL
+#define AB_THREADS_SMALL 64
+#endif
 
 namespace amici_b200 {
 
@@ -77,11 +80,16 @@ constexpr int pow2_at_least(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4
 template <class M>
 struct Config {
     static constexpr int COLS = M::NP + 1;
+#ifdef AB_FORCE_G   // experiment only (tools/build_variant.py)
+    static constexpr int G = AB_FORCE_G;
+    static constexpr int C = 1;
+#else
     static constexpr int G = pow2_at_least(COLS);
     static constexpr int C = (COLS + G - 1) / G;
+#endif
     // One warp per condition (G == 32): all resident warps of an SM in ONE block, so that they can align their steps
     // (Bdf::step_sync_*).  Otherwise small blocks: shared-memory granularity decides occupancy.
-    static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : 64;
+    static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : AB_THREADS_SMALL;
     static constexpr int MINBLOCKS = (G == 32) ? 1 : AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
 };
 
@@ -117,7 +125,7 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
 template <class M, bool PREEQ>
 int launch_model_impl(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
     if (o.sensi >= 1 && b.nplist > 0) {
-        if (b.nplist + 1 > Config<M>::COLS) {
+        if (b.nplist + 1 > Config<M>::COLS || b.nplist + 1 > Config<M>::G * Config<M>::C) {
             last_error() = "nplist exceeds the number of model parameters";
             return AB_E_UNSUPPORTED;
         }

@@ -59,7 +59,7 @@ using std::isfinite;
 // matters as much as the count (the step loop competes for the SM's instruction cache, DESIGN.md §2.6: dropping the
 // residual-correction step, 2 more instructions per site, was worth +3.7 %).  Host builds divide.
 AB_HD double fast_div(double a, double b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(AB_EXACT_DIV)   // AB_EXACT_DIV: A/B experiments only (tools/event_spread.py)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(r, fma(-b, r, 1.0), r);   // seed is good to ~2^-20 (rcp.approx.ftz.f64 reads the upper 32 bits): 2^-40 here
@@ -71,7 +71,7 @@ AB_HD double fast_div(double a, double b) {
 
 // 1 / b for finite, normal, non-zero b (pivots of the emitted sparse LU): reciprocal seed + two Newton steps, within 1-2 ulp
 AB_HD double fast_rcp(double b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(AB_EXACT_DIV)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(r, fma(-b, r, 1.0), r);

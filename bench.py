@@ -166,6 +166,8 @@ def main():
     solver.set_relative_tolerance(RTOL)
     solver.set_absolute_tolerance(ATOL)
     solver.set_sensitivity_order(ab.SensitivityOrder.first)
+    if os.environ.get("BENCH_NPLIST"):      # experiment only: sensitivities w.r.t. the first parameters only
+        model.set_parameter_list(list(range(int(os.environ["BENCH_NPLIST"]))))
     if os.environ.get("BENCH_NO_STLDET"):   # experiment only: upper bound of what cvBDFStab costs (not the reference's default)
         solver.set_stability_limit_flag(False)
     n = args.n_conditions

@@ -17,7 +17,7 @@ REF=${AMICI_REFERENCE:-/root/reference}
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/_ref"
 JOBS=${JOBS:-$(nproc)}
-MODELS=${MODELS:-"jakstat_adjoint steadystate events neuron robertson massaction_small massaction"}
+MODELS=${MODELS:-"jakstat_adjoint steadystate events neuron robertson robertson_ode massaction_small massaction"}
 CFLAGS_COMMON="-O2 -fPIC -fopenmp -w"
 
 if [ ! -d "$REF/src" ]; then
@@ -194,8 +194,11 @@ rm -f "$OUT/libamici.a"; ar rcs "$OUT/libamici.a" "$OUT"/obj/amici/*.o
 for m in $MODELS; do
   MD="$REF/models/model_${m}_py"
   if [ ! -d "$MD" ]; then
-    # not a shipped model: a synthetic mass-action network written in the reference's generated-code format
-    MD="$(python "$HERE/gen_massaction_ref.py" "$m" "$OUT/gen" "$REF")"
+    # not a shipped model: written in the reference's generated-code format from the tables / ModelSpec the engine uses
+    case "$m" in
+      massaction*) MD="$(python "$HERE/gen_massaction_ref.py" "$m" "$OUT/gen" "$REF")" ;;
+      *)           MD="$(python "$HERE/gen_ref_model.py" "$m" "$OUT/gen" "$REF")" ;;
+    esac
   fi
   MSRC=()
   for s in "$MD"/*.cpp; do case "$s" in */main.cpp) ;; *) MSRC+=("$s");; esac; done

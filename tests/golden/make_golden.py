@@ -65,12 +65,14 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=N
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
-def make_robertson(N=8, seed=1):
-    """BASELINE config 1: the shipped Robertson model is the index-1 DAE integrated by IDAS (reference
-    models/model_robertson_py); the engine integrates the equivalent ODE form (x3' = p3 x2^2) with its CVODES-equivalent
-    BDF.  ts is the reference's own Robertson grid (tests/generateTestConfig/example_robertson.py:17-20), k1 = 0.9,
+def make_robertson(N=8, seed=1, model="robertson"):
+    """BASELINE config 1.  model="robertson_ode" (robertson_ode.npz, the PRIMARY fixture): Robertson's problem in ODE form,
+    written in the reference's generated-code format by oracle/gen_ref_model.py from the ModelSpec the CUDA emitter consumes,
+    integrated by the reference's CVODES — the integrator the engine must be equivalent to.  model="robertson"
+    (robertson.npz, cross-check): the shipped index-1 DAE model integrated by IDAS (reference models/model_robertson_py).
+    ts is the reference's own Robertson grid (tests/generateTestConfig/example_robertson.py:17-20), k1 = 0.9,
     p = nominal x 10^U(-1, 1).  Both a plain forward run (config 1) and a forward-sensitivity run are stored."""
-    m = RefModel("robertson")
+    m = RefModel(model)
     ts = np.concatenate([[0.0], 4 * np.logspace(-6, 6, 50)])
     rng = np.random.default_rng(seed)
     p = np.tile(m.p_nominal, (N, 1)) * 10 ** rng.uniform(-1, 1, (N, 3))
@@ -79,13 +81,13 @@ def make_robertson(N=8, seed=1):
     out = dict(ts=ts, p=p, k=k, pscale=np.zeros(3, int))
     for name, extra in (("klu", dict(linsol=9)), ("dense", dict(linsol=1)),
                         ("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=500000))):
-        r0 = m.run(ts, p, k, sensi_order=0, fields=["status", "x", "y"], **extra)
-        r1 = m.run(ts, p, k, sensi_order=1, fields=["status", "x", "y", "sx", "sy"], **extra)
-        for f in ("status", "x", "y"):
+        r0 = m.run(ts, p, k, sensi_order=0, fields=["status", "x", "y", "numsteps"], **extra)
+        r1 = m.run(ts, p, k, sensi_order=1, fields=["status", "x", "y", "sx", "sy", "numsteps"], **extra)
+        for f in ("status", "x", "y", "numsteps"):
             out[f"{name}_{f}"] = r1[f]
             out[f"{name}_nosens_{f}"] = r0[f]
         out[f"{name}_sx"], out[f"{name}_sy"] = r1["sx"], r1["sy"]
-    path = os.path.join(HERE, "robertson.npz")
+    path = os.path.join(HERE, model + ".npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
@@ -133,12 +135,14 @@ if __name__ == "__main__":
         sys.exit(0)
     if sys.argv[1:] == ["robertson"]:
         make_robertson()
+        make_robertson(model="robertson_ode")
         sys.exit(0)
     if sys.argv[1:] == ["massaction"]:
         make("massaction_small", np.linspace(0, 10, 11), N=6, seed=19, kscale=(1.0, 1.0))
         make_massaction_big()
         sys.exit(0)
     make_robertson()
+    make_robertson(model="robertson_ode")
     make("jakstat_adjoint", np.arange(0, 61, 5.0), N=6, seed=11)
     make("jakstat_adjoint", np.arange(0, 61, 5.0), N=4, seed=12, pscale=[2] * 17, tag="_log10")
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=13)

@@ -59,8 +59,23 @@ def robertson_view(g, sensi):
     """tests/golden/robertson.npz holds a plain forward run (`*_nosens_*`) and a forward-sensitivity run; select one."""
     v = {}
     for name in ("klu", "dense", "truth"):
-        for f in ("status", "x", "y"):
-            v[f"{name}_{f}"] = g[f"{name}_{f}"] if sensi else g[f"{name}_nosens_{f}"]
+        for f in ("status", "x", "y", "numsteps"):
+            if f"{name}_{f}" in g:
+                v[f"{name}_{f}"] = g[f"{name}_{f}"] if sensi else g[f"{name}_nosens_{f}"]
         if sensi:
             v[f"{name}_sx"], v[f"{name}_sy"] = g[f"{name}_sx"], g[f"{name}_sy"]
     return v
+
+
+def reference_triple(ref, ts, p, k, fields, num_threads=1, truth=True, **kw):
+    """Three runs of the compiled reference on the same inputs — KLU, dense, tight-tolerance truth — in the layout of a
+    golden fixture, so that a fresh batch is checked by the same protocol as the committed vectors (check_against_golden)."""
+    out = {}
+    runs = [("klu", dict(linsol=9)), ("dense", dict(linsol=1))]
+    if truth:
+        runs.append(("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=500000)))
+    for name, extra in runs:
+        r = ref.run(ts, p, k, fields=list(fields), num_threads=num_threads, **{**kw, **extra})
+        for f in r:
+            out[f"{name}_{f}"] = r[f]
+    return out
