@@ -313,6 +313,21 @@ def emit_model(spec: ModelSpec) -> str:
     allowed = not any(sp.sympify(x0[i]).free_symbols & kset and sp.sympify(x0[i]).free_symbols & pset for i in range(nx))
     A(f"    static constexpr unsigned long long X0_FIXED_MASK = {fixed_mask:#x}ull;")
     A(f"    static constexpr bool X0_FIXED_REINIT_ALLOWED = {'true' if allowed else 'false'};")
+    # Parameters whose state-sensitivity column is identically zero: no entry of xdot, of the initial state or of a spline
+    # depends on them (observable offsets / scalings / noise parameters) and the model has no events.  For such a column
+    # sx0 = 0 and d/dt sx = J*sx + 0, so CVODES carries exact zeros that never win a max-norm: the engine can leave the
+    # column out of the integration (Layout<.., COMPACT>) without changing a single step-control decision; their output
+    # sensitivities (sy = dy/dp, ssigmay, sres, FIM, sllh) are formed from sx = 0 at the output points.
+    static_mask = 0
+    if ne == 0 and npar <= 64:
+        for ip in range(npar):
+            par = spec.params[ip]
+            dyn = any(sp.diff(e, par) != 0 for e in xdot) or any(sp.diff(e, par) != 0 for e in x0) or \
+                any(sp.diff(sp.sympify(v), par) != 0 for spl in spec.splines for v in spl.values)
+            if not dyn:
+                static_mask |= 1 << ip
+    A(f"    static constexpr unsigned long long SX_STATIC_MASK = {static_mask:#x}ull;   // parameters with sx == 0 identically")
+    A(f"    static constexpr int NP_DYN = {npar - bin(static_mask).count('1')};   // parameters that need an integrated sensitivity column")
     A("    AB_HD static void x0(const double* p, const double* k, double* x0) {")
     A("        (void)p; (void)k;")
     A(W.body([(f"x0[{i}]", x0[i]) for i in range(nx)]).rstrip("\n"))

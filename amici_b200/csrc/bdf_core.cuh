@@ -48,23 +48,33 @@ struct TrajShared {
     double savedJ[M::NNZ_J > 0 ? M::NNZ_J : 1];
     double ybuf[M::NX];              // broadcast buffer for the state column
     double xfin[M::NX];              // state at the last successful solver return (ReturnData::xdot/J are evaluated there)
-    double scratch[NCOLS];
+    double scratch[M::NP + 1];       // exchange buffer over OUTPUT columns (FIM rows)
     double p[M::NP > 0 ? M::NP : 1];
     double k[M::NK_EXT > 0 ? M::NK_EXT : 1];   // fixed parameters, then the model's derived constants (M::derived)
     double h[M::NH > 0 ? M::NH : 1];
-    double pcoef[NCOLS];             // chain-rule factor per column
+    double pcoef[NCOLS];             // chain-rule factor per integrated column
+    double pcoef_out[M::NP + 1];     // ... per output column (0 = state, 1 + il = plist entry il)
     double ctl[16];                  // mirrors of tau[0..6] (ctl[0..6]) and l[0..5] (ctl[8..13]) for indexing by the run-time order
     double ssdat[5][8];              // cvBDFStab history: ring buffer of (sqm2^2, sqm1^2, sq^2) in [1..3] and their ratios to
                                      // the next older entry in [5..7] (the rat[][] of cvSLdet, computed once), newest at ss_head
     int piv[M::NX];
-    int ip_of_col[NCOLS];
+    int ip_of_col[NCOLS];            // parameter index of an integrated column (-1: state / unused)
+    int il_of_col[NCOLS];            // its position in plist
+    int col_of_out[M::NP + 1];       // integrated column of an output column, -1 if the parameter's sensitivity is identically 0
     SplineTable<M, NCOLS> spl;
 };
 
+// COMPACT: the lane group is too small for one column per parameter, but large enough for the parameters whose state
+// sensitivity is not identically zero (M::SX_STATIC_MASK, written by the emitter): only those columns are integrated.  The
+// dropped columns are exact zeros in CVODES too (zero initial value, zero right-hand side) and a zero column never wins the
+// max-norms that drive the step control, so every decision and every integrated value is unchanged; the outputs of the
+// dropped parameters are formed from sx = 0 at the output points (Simulation::datapoint).
 template <class M, int G, int C>
 struct Layout {
     static constexpr int NX = M::NX;
-    static constexpr int NCOLS = (G * C < M::NP + 1) ? G * C : M::NP + 1;  // columns that can ever be active
+    static constexpr bool COMPACT = M::SX_STATIC_MASK != 0ull && G * C < M::NP + 1 && G * C >= M::NP_DYN + 1;
+    static constexpr int NCOLS_MAX = COMPACT ? M::NP_DYN + 1 : M::NP + 1;
+    static constexpr int NCOLS = (G * C < NCOLS_MAX) ? G * C : NCOLS_MAX;  // columns that can ever be active
     using Shared = TrajShared<M, NCOLS>;
 };
 
@@ -688,6 +698,16 @@ struct BdfControl {
     bool jcur, tstopset;
     bool pending;          // the accepted correction has not been added to the history yet: see history_pass
     bool reinit_pending;   // AMICI's CVodeSolver::reinit happened: the next call starts with reInit_post_process
+    // A step in progress (the locals of cvStep) and a solver call in progress (the locals of CVode): members, so that the
+    // nested driver (solve_to / step) and the flat one (flat.cuh: one attempt per iteration of a warp-uniform loop) run the
+    // same pieces: solve_begin, step_pre, step_begin, attempt, step_finish, step_post.
+    double st_saved_t, st_dsm;
+    int st_ncf, st_nef, st_nflag, st_dq;
+    bool st_restore, st_resc, st_reload;
+    int so_nstloc, so_mxstep, so_nst_saved;
+    bool so_post, so_one_step;
+    double so_tout;
+    static constexpr int CONTINUE = 1 << 20;   // "no return code yet" of the pieces
 
     AB_HD BdfControl(SharedT& s, const SolverOptions& opt) : S(s), o(opt) {}
     AB_HD D& self() { return static_cast<D&>(*this); }
@@ -973,96 +993,111 @@ struct BdfControl {
     // cvStep (cvodes.c:5800) with cvHandleNFlag (:7309) and cvDoErrorTest (:7461) folded in: every
     // retry path sets flags that are executed at the single history-manipulation site at the loop top.
     // -----------------------------------------------------------------------------------------
-    AB_HD int step() {
-        const double saved_t = tn;
-        int ncf = 0, nef = 0, nflag = FIRST_CALL;
-        double dsm = 0.0;
-        bool restore = false, resc = false, reload = false;
-        int dq = 0;
+    AB_HD void step_begin() {
+        st_saved_t = tn;
+        st_ncf = st_nef = 0;
+        st_nflag = FIRST_CALL;
+        st_dsm = 0.0;
+        st_restore = st_resc = st_reload = false;
+        st_dq = 0;
         if (nst > 0 && hprime != h) {  // cvAdjustParams
-            dq = qprime - q;
-            resc = true;
+            st_dq = qprime - q;
+            st_resc = true;
         }
+    }
+    // One attempt of the step: CONTINUE = repeat with the flags set here, AB_SUCCESS = passed the error test, < 0 = failure
+    AB_HD int attempt() {
+        // the one history-manipulation site: [restore] -> [complete] -> [order change] -> [rescale] -> predict
+        if (st_restore) {
+            self().template history_pass<-1>(false, false);
+            tn = st_saved_t;
+        }
+        if (st_dq != 0) {
+            flush_pending();   // cvAdjustOrder works on the completed history (rare)
+            adjust_order(st_dq);
+            q += st_dq;
+            L = q + 1;
+            qwait = L;
+            st_dq = 0;
+        }
+        if (st_resc) {   // scalar part of cvRescale; the history is scaled in the pass below
+            h = hscale * eta;
+            hscale = h;
+            nscon = 0;
+        }
+        if (st_reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
+            const bool ok = self().rhs_to_zn1(h);
+            nfe++;
+            if (!ok) return AB_UNREC_RHSFUNC_ERR;
+        }
+        tn += h;  // cvPredict
+        if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
+        self().template history_pass<1>(pending, st_resc);
+        pending = false;
+        st_restore = st_resc = st_reload = false;
+        set_coeffs();
+        st_nflag = self().nls(st_nflag);
+        if (st_nflag != AB_SUCCESS) {  // cvHandleNFlag
+            ncfn++;
+            st_ncf++;
+            etamax = 1.0;
+            if (st_ncf == o.max_conv_fails) {
+                tn = st_saved_t;
+                return (st_nflag == NLS_RHS_RECVR) ? AB_REPTD_RHSFUNC_ERR : AB_CONV_FAILURE;
+            }
+            eta = 0.25;  // max(eta_cf, hmin/|h|), hmin = 0
+            st_nflag = PREV_CONV_FAIL;
+            st_restore = st_resc = true;
+            return CONTINUE;
+        }
+        st_dsm = acnrm * tq[2];  // cvDoErrorTest
+        if (st_dsm <= 1.0) return AB_SUCCESS;
+        st_nef++;
+        netf++;
+        st_nflag = PREV_ERR_FAIL;
+        st_restore = true;
+        if (st_nef == o.max_err_test_fails) {
+            tn = st_saved_t;
+            return AB_ERR_FAILURE;
+        }
+        etamax = 1.0;
+        if (st_nef <= 3) {  // MXNEF1
+            eta = 1.0 / (nth_root(6.0 * st_dsm, L) + 1e-6);
+            eta = ab_max(0.1, eta);
+            if (st_nef >= 2) eta = ab_min(eta, 0.2);
+            st_resc = true;
+        } else if (q > 1) {  // force an order reduction
+            eta = 0.1;
+            st_dq = -1;
+            st_resc = true;
+        } else {  // already at order 1: restart from scratch with h*eta
+            eta = 0.1;
+            h *= eta;
+            hscale = h;
+            qwait = 10;  // LONG_WAIT
+            nscon = 0;
+            st_reload = true;
+        }
+        return CONTINUE;
+    }
+    AB_HD void step_finish() {
+        complete_step();
+        prepare_next_step(st_dsm);
+        if (o.stldet) bdf_stab();
+        etamax = 10.0;  // eta_max_es == eta_max_gs == 10
+    }
+    AB_HD int step() {
+        step_begin();
         for (;;) {
             // Step alignment is per ATTEMPT: a warp that repeats a step after a failed error or convergence test joins
             // the others at their next step instead of making them wait a whole attempt.
             self().step_sync_arrive();
-            // the one history-manipulation site: [restore] -> [complete] -> [order change] -> [rescale] -> predict
-            if (restore) {
-                self().template history_pass<-1>(false, false);
-                tn = saved_t;
-            }
-            if (dq != 0) {
-                flush_pending();   // cvAdjustOrder works on the completed history (rare)
-                adjust_order(dq);
-                q += dq;
-                L = q + 1;
-                qwait = L;
-                dq = 0;
-            }
-            if (resc) {   // scalar part of cvRescale; the history is scaled in the pass below
-                h = hscale * eta;
-                hscale = h;
-                nscon = 0;
-            }
-            if (reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
-                const bool ok = self().rhs_to_zn1(h);
-                nfe++;
-                if (!ok) return AB_UNREC_RHSFUNC_ERR;
-            }
-            tn += h;  // cvPredict
-            if (tstopset && (tn - tstop) * h > 0.0) tn = tstop;
-            self().template history_pass<1>(pending, resc);
-            pending = false;
-            restore = resc = reload = false;
-            set_coeffs();
-            nflag = self().nls(nflag);
-            if (nflag != AB_SUCCESS) {  // cvHandleNFlag
-                ncfn++;
-                ncf++;
-                etamax = 1.0;
-                if (ncf == o.max_conv_fails) {
-                    tn = saved_t;
-                    return (nflag == NLS_RHS_RECVR) ? AB_REPTD_RHSFUNC_ERR : AB_CONV_FAILURE;
-                }
-                eta = 0.25;  // max(eta_cf, hmin/|h|), hmin = 0
-                nflag = PREV_CONV_FAIL;
-                restore = resc = true;
-                continue;
-            }
-            dsm = acnrm * tq[2];  // cvDoErrorTest
-            if (dsm <= 1.0) break;
-            nef++;
-            netf++;
-            nflag = PREV_ERR_FAIL;
-            restore = true;
-            if (nef == o.max_err_test_fails) {
-                tn = saved_t;
-                return AB_ERR_FAILURE;
-            }
-            etamax = 1.0;
-            if (nef <= 3) {  // MXNEF1
-                eta = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
-                eta = ab_max(0.1, eta);
-                if (nef >= 2) eta = ab_min(eta, 0.2);
-                resc = true;
-            } else if (q > 1) {  // force an order reduction
-                eta = 0.1;
-                dq = -1;
-                resc = true;
-            } else {  // already at order 1: restart from scratch with h*eta
-                eta = 0.1;
-                h *= eta;
-                hscale = h;
-                qwait = 10;  // LONG_WAIT
-                nscon = 0;
-                reload = true;
-            }
+            const int r = attempt();
+            if (r == CONTINUE) continue;
+            if (r != AB_SUCCESS) return r;
+            break;
         }
-        complete_step();
-        prepare_next_step(dsm);
-        if (o.stldet) bdf_stab();
-        etamax = 10.0;  // eta_max_es == eta_max_gs == 10
+        step_finish();
         return AB_SUCCESS;
     }
 
@@ -1109,20 +1144,22 @@ struct BdfControl {
     // gives the direction and the scale of the initial step; returns AB_SUCCESS after one internal step.
     // Both modes share this function so that the (inlined) step has a single call site.
     // -----------------------------------------------------------------------------------------
-    AB_HD int solve_to(double tout, bool one_step = false) {
+    AB_HD int solve_begin(double tout, bool one_step = false) {
         constexpr bool ROOTS = D::ROOTS;
         // Solver::apply_max_num_steps (reference src/solver.cpp:107-119)
         if (o.maxsteps <= nst) return AB_ERROR;
-        const int mxstep = o.maxsteps - nst;
+        so_mxstep = o.maxsteps - nst;
+        so_tout = tout;
+        so_one_step = one_step;
         tstop = tout;
         tstopset = !one_step;
         // reInit_post_process (reference src/solver_cvodes.cpp:517-565): after an event the first step is taken as a
         // "first call" (nst = 0) in one-step mode with tstop = tout, then the step counter is restored
-        bool post = D::EVENTS ? reinit_pending : false;
-        int nst_saved = 0;
-        if (post) {
+        so_post = D::EVENTS ? reinit_pending : false;
+        so_nst_saved = 0;
+        if (so_post) {
             reinit_pending = false;
-            nst_saved = nst;
+            so_nst_saved = nst;
             nst = 0;
             self().set_ewt();   // cvInitialSetup
         }
@@ -1174,65 +1211,81 @@ struct BdfControl {
                 }
             }
         }
-        // Step loop.  Every exit goes through the epilogue below: a pending completion is written to the history (the
-        // caller reads zn[0]) and the warp leaves the step-alignment group.
-        int nstloc = 0, rc = AB_SUCCESS;
-        self().step_sync_join();
-        for (;;) {
-            if (nst > 0) self().set_ewt();
-            if (nstloc >= mxstep) { tretlast = tn; rc = AB_TOO_MUCH_WORK; break; }
-            // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the
-            // norm is below 1/rtol and the test can only fire when rtol is of the order of the unit round-off.
-            if (!(o.rtol > 8.0 * DBL_EPSILON && o.rtol_fsa > 8.0 * DBL_EPSILON)) {
-                const double nrm = self().wrms_max_zn(0, 1.0);
-                if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; rc = AB_TOO_MUCH_ACC; break; }
+        so_nstloc = 0;
+        return CONTINUE;
+    }
+    // top of the CVode step loop: error weights, step budget, tolsf test
+    AB_HD int step_pre() {
+        if (nst > 0) self().set_ewt();
+        if (so_nstloc >= so_mxstep) { tretlast = tn; return AB_TOO_MUCH_WORK; }
+        // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the
+        // norm is below 1/rtol and the test can only fire when rtol is of the order of the unit round-off.
+        if (!(o.rtol > 8.0 * DBL_EPSILON && o.rtol_fsa > 8.0 * DBL_EPSILON)) {
+            const double nrm = self().wrms_max_zn(0, 1.0);
+            if (DBL_EPSILON * nrm > 1.0) { tretlast = tn; return AB_TOO_MUCH_ACC; }
+        }
+        return CONTINUE;
+    }
+    // after a successful step: root check and stop logic; CONTINUE = take another step
+    AB_HD int step_post() {
+        constexpr bool ROOTS = D::ROOTS;
+        so_nstloc++;
+        double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
+        const bool at_tstop = tstopset && fabs(tn - tstop) <= troundoff;
+        if (at_tstop) tn = tstop;
+        if constexpr (ROOTS) {
+            flush_pending();   // the root finder interpolates on the completed history
+            if (self().rcheck3(so_tout, so_one_step || so_post)) {
+                self().irfnd = 1;
+                tretlast = self().tlo;
+                // a root right after re-initialisation is an error in the reference (src/solver_cvodes.cpp:531-540)
+                if (so_post) { nst = so_nst_saved + 1; return AB_ERROR; }
+                self().collapse_to(self().tlo);
+                return AB_ROOT_RETURN;
             }
-            const int kflag = step();
-            if (kflag != AB_SUCCESS) { tretlast = tn; rc = kflag; break; }
-            nstloc++;
-            double troundoff = 100.0 * DBL_EPSILON * (fabs(tn) + fabs(h));
-            const bool at_tstop = tstopset && fabs(tn - tstop) <= troundoff;
-            if (at_tstop) tn = tstop;
-            if constexpr (ROOTS) {
-                flush_pending();   // the root finder interpolates on the completed history
-                if (self().rcheck3(tout, one_step || post)) {
-                    self().irfnd = 1;
-                    tretlast = self().tlo;
-                    // a root right after re-initialisation is an error in the reference (src/solver_cvodes.cpp:531-540)
-                    if (post) { nst = nst_saved + 1; rc = AB_ERROR; break; }
-                    self().collapse_to(self().tlo);
-                    rc = AB_ROOT_RETURN;
-                    break;
-                }
-            }
-            if (D::EVENTS && post) {
-                // end of reInit_post_process: anything but CV_SUCCESS throws there; then the regular call starts
-                nst = nst_saved + 1;
-                post = false;
-                nstloc = 0;
-                tretlast = tn;
-                if (at_tstop) { rc = AB_ERROR; break; }
-                if ((tn + hprime - tstop) * h > 0.0) {
-                    hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                    eta = fast_div(hprime, h);
-                }
-                if constexpr (ROOTS) {
-                    const int rc2 = self().rcheck2();
-                    if (rc2 == 3) { rc = AB_ILL_INPUT; break; }
-                    if (rc2 == 1) { tretlast = self().tlo; self().collapse_to(self().tlo); rc = AB_ROOT_RETURN; break; }
-                }
-                continue;
-            }
-            if (one_step) { tretlast = tn; rc = AB_SUCCESS; break; }
-            if (at_tstop) {
-                tretlast = tstop;
-                tstopset = false;
-                rc = AB_TSTOP_RETURN;
-                break;
-            } else if ((tn + hprime - tstop) * h > 0.0) {
+        }
+        if (D::EVENTS && so_post) {
+            // end of reInit_post_process: anything but CV_SUCCESS throws there; then the regular call starts
+            nst = so_nst_saved + 1;
+            so_post = false;
+            so_nstloc = 0;
+            tretlast = tn;
+            if (at_tstop) return AB_ERROR;
+            if ((tn + hprime - tstop) * h > 0.0) {
                 hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
                 eta = fast_div(hprime, h);
             }
+            if constexpr (ROOTS) {
+                const int rc2 = self().rcheck2();
+                if (rc2 == 3) return AB_ILL_INPUT;
+                if (rc2 == 1) { tretlast = self().tlo; self().collapse_to(self().tlo); return AB_ROOT_RETURN; }
+            }
+            return CONTINUE;
+        }
+        if (so_one_step) { tretlast = tn; return AB_SUCCESS; }
+        if (at_tstop) {
+            tretlast = tstop;
+            tstopset = false;
+            return AB_TSTOP_RETURN;
+        } else if ((tn + hprime - tstop) * h > 0.0) {
+            hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
+            eta = fast_div(hprime, h);
+        }
+        return CONTINUE;
+    }
+    AB_HD int solve_to(double tout, bool one_step = false) {
+        int rc = solve_begin(tout, one_step);
+        if (rc != CONTINUE) return rc;
+        // Step loop.  Every exit goes through the epilogue below: a pending completion is written to the history (the
+        // caller reads zn[0]) and the warp leaves the step-alignment group.
+        self().step_sync_join();
+        for (;;) {
+            rc = step_pre();
+            if (rc != CONTINUE) break;
+            const int kflag = step();
+            if (kflag != AB_SUCCESS) { tretlast = tn; rc = kflag; break; }
+            rc = step_post();
+            if (rc != CONTINUE) break;
         }
         self().step_sync_leave();   // first: the other warps of the group must not wait for the flush below
         flush_pending();

@@ -7,7 +7,7 @@
 #include <string>
 
 #include "registry.h"
-#include "simulate.cuh"
+#include "flat.cuh"
 
 #ifndef AB_MINBLOCKS
 #define AB_MINBLOCKS 4
@@ -21,10 +21,40 @@
 #ifndef AB_THREADS_SMALL
 #define AB_THREADS_SMALL 64
 #endif
+#ifndef AB_FLAT
+// 1: event-free models without pre-equilibration run the flat driver (flat.cuh: one attempt per iteration of a warp-uniform
+// loop, so that the step alignment also works for two conditions per warp).  Measured on B200 (profiles/r02_variants.md) the
+// nested driver is faster at the current code size, so it stays the default; both are covered by the tests.
+#define AB_FLAT 0
+#endif
+#ifndef AB_COMPACT
+#define AB_COMPACT 1     // leave identically-zero sensitivity columns out of the integration when that halves the lane group
+#endif
+#ifndef AB_THREADS_G16
+#define AB_THREADS_G16 256
+#endif
 
 namespace amici_b200 {
 
 constexpr int SYNC_BYTES = 128;
+
+// Completion tracking for the streaming host path (ab_run_batch): conditions are handed out in index order, so the
+// sub-batches [c*chunk, (c+1)*chunk) complete roughly in order; the group that finishes the last condition of a sub-batch
+// raises its flag in mapped host memory and the host starts that sub-batch's D2H copies.
+template <int G>
+__device__ __forceinline__ void report_done(const Progress& pg, const Group<G>& g, const int N, const int n) {
+    if (!pg.done) return;
+    __threadfence();   // every lane: its ReturnData stores are visible device-wide before the count below
+    g.sync();
+    if (g.lane == 0) {
+        const int c = n / pg.chunk;
+        const int size = (N - c * pg.chunk < pg.chunk) ? N - c * pg.chunk : pg.chunk;
+        if (atomicAdd(pg.done + c, 1) == size - 1) {
+            __threadfence_system();
+            *reinterpret_cast<volatile int*>(pg.host_flags + c) = 1;
+        }
+    }
+}
 
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head, const Progress pg) {
@@ -54,22 +84,29 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
         }
         sim.run();
         g.sync();
-        if (pg.done) {
-            // Completion tracking for the streaming host path (ab_run_batch): conditions are handed out in index order, so
-            // the sub-batches [c*chunk, (c+1)*chunk) complete roughly in order; the group that finishes the last condition
-            // of a sub-batch raises its flag in mapped host memory and the host starts that sub-batch's D2H copies.
-            __threadfence();   // every lane: its ReturnData stores are visible device-wide before the count below
-            g.sync();
-            if (g.lane == 0) {
-                const int c = n / pg.chunk;
-                const int size = (b.N - c * pg.chunk < pg.chunk) ? b.N - c * pg.chunk : pg.chunk;
-                if (atomicAdd(pg.done + c, 1) == size - 1) {
-                    __threadfence_system();
-                    *reinterpret_cast<volatile int*>(pg.host_flags + c) = 1;
-                }
-            }
-        }
+        report_done<G>(pg, g, b.N, n);
     }
+}
+
+// Event-free models without pre-equilibration: the flat driver (flat.cuh), one step attempt per iteration of a warp-uniform loop.
+template <class M, int G, int C, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_flat_kernel(const ab_solver_options o, const ab_batch b, int* queue_head, const Progress pg) {
+    using Shared = typename FlatDriver<M, G, C>::Shared;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* sync_pos = reinterpret_cast<int*>(smem_raw);
+    Shared* slices = reinterpret_cast<Shared*>(smem_raw + SYNC_BYTES);
+    Shared& S = slices[threadIdx.x / G];
+    constexpr bool STEP_SYNC = AB_STEP_SYNC && G >= 16 && THREADS > 32;
+    WarpAlign align;
+    if (STEP_SYNC) {
+        if (threadIdx.x < THREADS / 32) sync_pos[threadIdx.x] = 0x7fffffff;
+        __syncthreads();
+        align.pos = sync_pos;
+        align.n = THREADS / 32;
+        align.w = threadIdx.x / 32;
+    }
+    Group<G> g;
+    flat_run<M, G, C>(S, o, b, queue_head, align, [&](const int n) { report_done<G>(pg, g, b.N, n); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -77,9 +114,10 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
 // ---------------------------------------------------------------------------------------------
 constexpr int pow2_at_least(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
 
-template <class M>
+// COMPACT: one column per parameter whose state sensitivity is not identically zero (bdf_core.cuh Layout)
+template <class M, bool COMPACT = false>
 struct Config {
-    static constexpr int COLS = M::NP + 1;
+    static constexpr int COLS = COMPACT ? M::NP_DYN + 1 : M::NP + 1;
 #ifdef AB_FORCE_G   // experiment only (tools/build_variant.py)
     static constexpr int G = AB_FORCE_G;
     static constexpr int C = 1;
@@ -87,16 +125,28 @@ struct Config {
     static constexpr int G = pow2_at_least(COLS);
     static constexpr int C = (COLS + G - 1) / G;
 #endif
-    // One warp per condition (G == 32): all resident warps of an SM in ONE block, so that they can align their steps
-    // (Bdf::step_sync_*).  Otherwise small blocks: shared-memory granularity decides occupancy.
-    static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : AB_THREADS_SMALL;
-    static constexpr int MINBLOCKS = (G == 32) ? 1 : AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
+    // One warp per condition (G == 32), or two (G == 16): all resident warps of an SM in ONE block, so that they can align
+    // their steps (Bdf::step_sync_*, WarpAlign).  Otherwise small blocks: shared-memory granularity decides occupancy.
+    static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : (G == 16) ? AB_THREADS_G16 : AB_THREADS_SMALL;
+    static constexpr int MINBLOCKS = (G >= 16) ? 1 : AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
 };
+// compaction pays when it halves the lane group (JAK-STAT: 18 columns in 32 lanes -> 11 in 16, two conditions per warp)
+template <class M>
+constexpr bool compact_pays() {
+    return AB_COMPACT && M::SX_STATIC_MASK != 0ull && Config<M, true>::G * Config<M, true>::C < Config<M, false>::G * Config<M, false>::C &&
+           Config<M, true>::G * Config<M, true>::C < M::NP + 1;
+}
+
+template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
+auto select_kernel() {
+    if constexpr (AB_FLAT && !PREEQ && M::NE == 0) return bdf_flat_kernel<M, G, C, THREADS, MINBLOCKS>;
+    else return bdf_solve_kernel<M, G, C, THREADS, MINBLOCKS, PREEQ>;
+}
 
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
 int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
     using Sim = Simulation<M, G, C, PREEQ>;
-    auto kern = bdf_solve_kernel<M, G, C, THREADS, MINBLOCKS, PREEQ>;
+    auto kern = select_kernel<M, G, C, THREADS, MINBLOCKS, PREEQ>();
     constexpr int groups = THREADS / G;
     const size_t smem = SYNC_BYTES + sizeof(typename Sim::Shared) * groups;
     int dev = 0, sms = 0;
@@ -125,8 +175,17 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
 template <class M, bool PREEQ>
 int launch_model_impl(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
     if (o.sensi >= 1 && b.nplist > 0) {
-        if (b.nplist + 1 > Config<M>::COLS || b.nplist + 1 > Config<M>::G * Config<M>::C) {
+        if (b.nplist + 1 > Config<M>::COLS) {
             last_error() = "nplist exceeds the number of model parameters";
+            return AB_E_UNSUPPORTED;
+        }
+        if constexpr (!PREEQ && compact_pays<M>()) {
+            // given initial sensitivities may be non-zero for any parameter: every column is integrated then
+            using CC = Config<M, true>;
+            if (!b.sx0_in) return launch_variant<M, CC::G, CC::C, CC::THREADS, CC::MINBLOCKS, PREEQ>(o, b, queue_head, pg, st);
+        }
+        if (b.nplist + 1 > Config<M>::G * Config<M>::C) {
+            last_error() = "nplist exceeds the lane group of this build";
             return AB_E_UNSUPPORTED;
         }
         return launch_variant<M, Config<M>::G, Config<M>::C, Config<M>::THREADS, Config<M>::MINBLOCKS, PREEQ>(o, b, queue_head, pg, st);

@@ -31,6 +31,13 @@ struct Simulation {
     using Solver = Bdf<M, G, C, PREEQ>;
     static constexpr int NX = M::NX, NY = M::NY, NCOLS = Solver::NCOLS;
     using Shared = typename Solver::Shared;
+    // Output columns: 0 = state, 1 + il = entry il of plist.  Normally they are the integrated columns; with a COMPACT layout
+    // (bdf_core.cuh Layout) the parameters whose state sensitivity is identically zero have no integrated column, and a
+    // lane serves the output columns lane, lane + G, ... (C_OUT slots) with sx = 0 for those.
+    static constexpr bool COMPACT = Layout<M, G, C>::COMPACT;
+    static_assert(!(COMPACT && M::NE > 0), "compact layouts are for event-free models");
+    static constexpr int C_OUT = COMPACT ? (M::NP + 1 + G - 1) / G : C;
+    static constexpr int NSPLV = M::NSPL > 0 ? M::NSPL : 1;
 
     Shared& S;
     const SolverOptions& o;
@@ -39,7 +46,7 @@ struct Simulation {
     int n;       // trajectory index
     int nplist;
     double llh, chi2;
-    double sllh[C];
+    double sllh[C_OUT];
     // event bookkeeping (FwdSimWorkspace, reference include/amici/forwardproblem.h:109-175): group-uniform registers
     static constexpr int NEV = M::NE > 0 ? M::NE : 1, NZV = M::NZ > 0 ? M::NZ : 1;
     int roots_found[NEV], nroots[NEV];
@@ -49,10 +56,26 @@ struct Simulation {
     double tlastroot, t_trig_done;
 
     AB_HD Simulation(Shared& s, const SolverOptions& opt, const BatchView& bv, int n_)
-        : S(s), o(opt), b(bv), bdf(s, opt, (opt.sensi >= 1 ? 1 + bv.nplist : 1)), n(n_),
+        : S(s), o(opt), b(bv), bdf(s, opt, integrated_columns(opt, bv)), n(n_),
           nplist(opt.sensi >= 1 ? bv.nplist : 0) {}
 
+    // 1 + the number of plist entries that get an integrated sensitivity column
+    AB_HD static int integrated_columns(const SolverOptions& opt, const BatchView& bv) {
+        if (opt.sensi < 1) return 1;
+        if (!COMPACT) return 1 + bv.nplist;
+        unsigned long long dyn = 0ull;   // one integrated column per DISTINCT parameter with a non-zero state sensitivity
+        for (int il = 0; il < bv.nplist; ++il) dyn |= 1ull << bv.plist[il];
+        dyn &= ~M::SX_STATIC_MASK;
+        int nc = 1;
+        for (; dyn; dyn &= dyn - 1) ++nc;
+        return nc;
+    }
+
     AB_HD bool full() const { return o.reporting == 0; }
+    // output slot j of this lane
+    AB_HD int out_col(const int j) const { return bdf.g.lane + G * j; }
+    AB_HD bool out_active(const int j) const { return out_col(j) <= nplist; }
+    AB_HD int int_col(const int oc) const { return COMPACT ? S.col_of_out[oc] : oc; }
 
     // ConditionContext + Model::initialize (reference src/edata.cpp:438-556, src/model.cpp:251-278):
     // unscale parameters (reference include/amici/misc.h:164-195), x0, sx0, spline tables.
@@ -70,16 +93,34 @@ struct Simulation {
             M::derived(S.p, S.k);
             for (int i = 0; i < M::NH; ++i) S.h[i] = 0.0;
             for (int cc = 0; cc < NCOLS; ++cc) {
-                int ip = -1;
-                double pc = 1.0;
-                if (cc >= 1 && cc <= nplist) {
-                    ip = b.plist[cc - 1];
-                    const int sc = b.pscale ? b.pscale[ip] : AB_PSCALE_NONE;
-                    // pcoefficient of ReturnData::apply_chain_rule_factor_to_simulation_results (rdata.cpp:783-796)
-                    pc = sc == AB_PSCALE_LOG10 ? S.p[ip] * log(10.0) : sc == AB_PSCALE_LN ? S.p[ip] : 1.0;
+                S.ip_of_col[cc] = -1;
+                S.il_of_col[cc] = -1;
+                S.pcoef[cc] = 1.0;
+            }
+            S.col_of_out[0] = 0;
+            S.pcoef_out[0] = 1.0;
+            int cc = 1;
+            for (int il = 0; il < nplist; ++il) {
+                const int ip = b.plist[il];
+                const int sc = b.pscale ? b.pscale[ip] : AB_PSCALE_NONE;
+                // pcoefficient of ReturnData::apply_chain_rule_factor_to_simulation_results (rdata.cpp:783-796)
+                const double pc = sc == AB_PSCALE_LOG10 ? S.p[ip] * log(10.0) : sc == AB_PSCALE_LN ? S.p[ip] : 1.0;
+                S.pcoef_out[il + 1] = pc;
+                int have = -1;   // COMPACT: a parameter listed twice shares its column (identical vectors, same max-norms)
+                if (COMPACT)
+                    for (int c2 = 1; c2 < cc; ++c2)
+                        if (S.ip_of_col[c2] == ip) have = c2;
+                if (COMPACT && (M::SX_STATIC_MASK >> ip & 1ull)) {
+                    S.col_of_out[il + 1] = -1;   // sx == 0 identically: no integrated column
+                } else if (have > 0) {
+                    S.col_of_out[il + 1] = have;
+                } else {
+                    S.col_of_out[il + 1] = cc;
+                    S.ip_of_col[cc] = ip;
+                    S.il_of_col[cc] = il;
+                    S.pcoef[cc] = pc;
+                    ++cc;
                 }
-                S.ip_of_col[cc] = ip;
-                S.pcoef[cc] = pc;
             }
         }
         g.sync();
@@ -110,7 +151,7 @@ struct Simulation {
             M::sx0(S.ip_of_col[cc], S.p, S.k, v);
             if (b.sx0_in)
                 AB_UNROLL
-                for (int r = 0; r < NX; ++r) v[r] = b.sx0_in[((size_t)n * nplist + (cc - 1)) * NX + r] / S.pcoef[cc];
+                for (int r = 0; r < NX; ++r) v[r] = b.sx0_in[((size_t)n * nplist + S.il_of_col[cc]) * NX + r] / S.pcoef[cc];
         }
     }
 
@@ -145,18 +186,20 @@ struct Simulation {
         auto& g = bdf.g;
         const int nt = b.nt;
         const double t = b.ts[it];
-        typename Solver::Eval e;
-        double xc[C][NX];
+        double xs[NX], spl[NSPLV];
+        SplineLoc loc[NSPLV];
+        g.sync();
         AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            AB_UNROLL
-            for (int r = 0; r < NX; ++r) xc[c][r] = bdf.active(c) ? S.zn[0][r][bdf.col(c)] : 0.0;
+        for (int r = 0; r < NX; ++r) xs[r] = S.zn[0][r][0];
+        AB_UNROLL
+        for (int is = 0; is < M::NSPL; ++is) {
+            loc[is] = spline_locate<M>(is, t);
+            const double v = spline_eval_at<M, NCOLS>(S.spl, is, 0, loc[is], true);
+            spl[is] = M::SPL_LOG ? exp(v) : v;
         }
-        bcast_state<M, G, C>(S, g, xc, e);
-        eval_splines<M, G, C>(S, g, bdf.ncols, t, e);
         double y[NY], sig[NY], my[NY];
         bool my_set[NY], sig_set[NY];
-        M::y(t, e.y, S.p, S.k, S.h, e.spl, y);
+        M::y(t, xs, S.p, S.k, S.h, spl, y);
         M::sigmay(S.p, S.k, y, sig);
         AB_UNROLL
         for (int iy = 0; iy < NY; ++iy) {
@@ -170,15 +213,17 @@ struct Simulation {
         double res[NY];
         AB_UNROLL
         for (int iy = 0; iy < NY; ++iy) res[iy] = my_set[iy] ? (my[iy] - y[iy]) / sig[iy] : 0.0;
-
+        double srv[C_OUT][NY];   // this lane's rows of sres (chain rule applied), for the FIM
         AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!bdf.active(c)) continue;
-            const int cc = bdf.col(c);
-            if (cc == 0) {
+        for (int j = 0; j < C_OUT; ++j) {
+            AB_UNROLL
+            for (int iy = 0; iy < NY; ++iy) srv[j][iy] = 0.0;
+            if (!out_active(j)) continue;
+            const int oc = out_col(j);
+            if (oc == 0) {
                 if (b.x && full())
                     AB_UNROLL
-                    for (int r = 0; r < NX; ++r) b.x[((size_t)n * nt + it) * NX + r] = e.y[r];
+                    for (int r = 0; r < NX; ++r) b.x[((size_t)n * nt + it) * NX + r] = xs[r];
                 AB_UNROLL
                 for (int iy = 0; iy < NY; ++iy) {
                     const size_t idx = ((size_t)n * nt + it) * NY + iy;
@@ -193,22 +238,31 @@ struct Simulation {
                     }
                 }
             } else {
-                const int ip = S.ip_of_col[cc];
-                const int il = cc - 1;  // index in plist
-                const double pc = S.pcoef[cc];
-                double sy[NY], ssig_tot[NY], dsig[NY];
-                M::sy(ip, t, e.y, S.p, S.k, S.h, e.spl, e.sspl[c], xc[c], sy);
-                M::ssigmay(ip, S.p, S.k, y, sy, ssig_tot);
-                M::dsigmaydp(ip, S.p, S.k, y, dsig);
+                const int il = oc - 1;  // index in plist
+                const int cc = int_col(oc);   // integrated column, or -1: sx == 0
+                const int ip = COMPACT ? b.plist[il] : S.ip_of_col[oc];
+                const double pc = S.pcoef_out[oc];
+                double sxv[NX], sspl[NSPLV], sy[NY], ssig_tot[NY];
+                AB_UNROLL
+                for (int r = 0; r < NX; ++r) sxv[r] = (!COMPACT || cc >= 0) ? S.zn[0][r][cc >= 0 ? cc : 0] : 0.0;
+                AB_UNROLL
+                for (int is = 0; is < M::NSPL; ++is) {
+                    sspl[is] = 0.0;
+                    if (COMPACT && cc < 0) continue;
+                    const double sv = spline_eval_at<M, NCOLS>(S.spl, is, cc, loc[is], false);
+                    sspl[is] = M::SPL_LOG ? sv * spl[is] : sv;
+                }
+                M::sy(ip, t, xs, S.p, S.k, S.h, spl, sspl, sxv, sy);
+                M::ssigmay(ip, S.p, S.k, y, sy, ssig_tot);   // dsigmay/dp + dsigmay/dy * sy
                 if (b.sx && full())
                     AB_UNROLL
                     for (int r = 0; r < NX; ++r)
-                        b.sx[(((size_t)n * nt + it) * nplist + il) * NX + r] = chain(xc[c][r], pc);
+                        b.sx[(((size_t)n * nt + it) * nplist + il) * NX + r] = chain(sxv[r], pc);
                 AB_UNROLL
                 for (int iy = 0; iy < NY; ++iy) {
-                    // sigma given by the data overrides the model sigma: dsigmaydp := 0 (src/model.cpp:2199-2209)
-                    const double dsp = sig_set[iy] ? 0.0 : dsig[iy];
-                    const double ssig = dsp + (ssig_tot[iy] - dsig[iy]);
+                    // sigma given by the data overrides the model sigma: dsigmaydp := 0 and dsigmaydy := 0
+                    // (reference src/model.cpp:2199-2209, :2231-2238)
+                    const double ssig = sig_set[iy] ? 0.0 : ssig_tot[iy];
                     const size_t idx = (((size_t)n * nt + it) * nplist + il) * NY + iy;
                     if (b.sy && full()) b.sy[idx] = chain(sy[iy], pc);
                     if (b.ssigmay && full()) b.ssigmay[idx] = chain(ssig, pc);
@@ -217,10 +271,13 @@ struct Simulation {
                         const double s2 = sig[iy] * sig[iy];
                         const double dJydy = r_ / s2;
                         const double dJyds = 1.0 / sig[iy] - r_ * r_ / (s2 * sig[iy]);
-                        sllh[c] -= dJydy * sy[iy] + dJyds * dsp;
+                        // dJydy of the reference carries dJydsigma * dsigmaydy (src/model.cpp:2278-2290): together
+                        // -(dJydy * sy + dJydsigma * (dsigmaydp + dsigmaydy * sy))
+                        sllh[j] -= dJydy * sy[iy] + dJyds * ssig;
                         const double sr = (-sy[iy] - ssig * res[iy]) / sig[iy];
+                        srv[j][iy] = chain(sr, pc);
                         if (b.sres && full())
-                            b.sres[((size_t)n * nt * NY + (size_t)it * NY + iy) * nplist + il] = chain(sr, pc);
+                            b.sres[((size_t)n * nt * NY + (size_t)it * NY + iy) * nplist + il] = srv[j][iy];
                     }
                 }
             }
@@ -230,29 +287,16 @@ struct Simulation {
             AB_UNROLL
             for (int iy = 0; iy < NY; ++iy) {
                 if (!my_set[iy]) continue;
-                double mine[C];
                 g.sync();
                 AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    mine[c] = 0.0;
-                    if (!bdf.active(c) || bdf.col(c) == 0) continue;
-                    const int cc = bdf.col(c);
-                    double sy[NY], ssig_tot[NY], dsig[NY];
-                    M::sy(S.ip_of_col[cc], t, e.y, S.p, S.k, S.h, e.spl, e.sspl[c], xc[c], sy);
-                    M::ssigmay(S.ip_of_col[cc], S.p, S.k, y, sy, ssig_tot);
-                    M::dsigmaydp(S.ip_of_col[cc], S.p, S.k, y, dsig);
-                    const double dsp = sig_set[iy] ? 0.0 : dsig[iy];
-                    const double ssig = dsp + (ssig_tot[iy] - dsig[iy]);
-                    mine[c] = chain((-sy[iy] - ssig * res[iy]) / sig[iy], S.pcoef[cc]);
-                    S.scratch[cc] = mine[c];
-                }
+                for (int j = 0; j < C_OUT; ++j)
+                    if (out_active(j) && out_col(j) > 0) S.scratch[out_col(j)] = srv[j][iy];
                 g.sync();
                 AB_UNROLL
-                for (int c = 0; c < C; ++c) {
-                    if (!bdf.active(c) || bdf.col(c) == 0) continue;
-                    const int il = bdf.col(c) - 1;
-                    double* row = b.FIM + ((size_t)n * nplist + il) * nplist;
-                    for (int jl = 0; jl < nplist; ++jl) row[jl] += mine[c] * S.scratch[jl + 1];
+                for (int j = 0; j < C_OUT; ++j) {
+                    if (!out_active(j) || out_col(j) == 0) continue;
+                    double* row = b.FIM + ((size_t)n * nplist + (out_col(j) - 1)) * nplist;
+                    for (int jl = 0; jl < nplist; ++jl) row[jl] += srv[j][iy] * S.scratch[jl + 1];
                 }
             }
         }
@@ -275,14 +319,14 @@ struct Simulation {
         llh = nan_;
         chi2 = nan_;
         AB_UNROLL
-        for (int c = 0; c < C; ++c) sllh[c] = nan_;
+        for (int j = 0; j < C_OUT; ++j) sllh[j] = nan_;
         if (!full()) return;
         AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!bdf.active(c)) continue;
-            const int cc = bdf.col(c);
+        for (int j = 0; j < C_OUT; ++j) {
+            if (!out_active(j)) continue;
+            const int oc = out_col(j);
             for (int it = it_start; it < nt; ++it) {
-                if (cc == 0) {
+                if (oc == 0) {
                     for (int r = 0; r < NX; ++r)
                         if (b.x) b.x[((size_t)n * nt + it) * NX + r] = nan_;
                     for (int iy = 0; iy < NY; ++iy) {
@@ -291,7 +335,7 @@ struct Simulation {
                         if (b.res) b.res[(size_t)n * nt * NY + (size_t)it * NY + iy] = nan_;
                     }
                 } else {
-                    const int il = cc - 1;
+                    const int il = oc - 1;
                     for (int r = 0; r < NX; ++r)
                         if (b.sx) b.sx[(((size_t)n * nt + it) * nplist + il) * NX + r] = nan_;
                     for (int iy = 0; iy < NY; ++iy) {
@@ -302,42 +346,40 @@ struct Simulation {
                     }
                 }
             }
-            if (cc > 0 && b.FIM)
-                for (int jl = 0; jl < nplist; ++jl) b.FIM[((size_t)n * nplist + (cc - 1)) * nplist + jl] = nan_;
+            if (oc > 0 && b.FIM)
+                for (int jl = 0; jl < nplist; ++jl) b.FIM[((size_t)n * nplist + (oc - 1)) * nplist + jl] = nan_;
         }
     }
 
     // x0 / sx0 outputs: the state the main simulation starts from (reference src/rdata.cpp:326-334)
     AB_HD void write_initial_state(const bool valid = true) {
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!bdf.active(c)) continue;
-            const int cc = bdf.col(c);
-            if (cc == 0) {
-                AB_UNROLL
-                for (int r = 0; r < NX; ++r) S.xfin[r] = S.zn[0][r][0];
-            }
-            if (!full()) continue;
+        auto& g = bdf.g;
+        g.sync();
+        if (g.lane == 0) {
             AB_UNROLL
-            for (int r = 0; r < NX; ++r) {
-                const double v = valid ? S.zn[0][r][cc] : ab_nan();
-                if (cc == 0) { if (b.x0) b.x0[(size_t)n * NX + r] = v; }
-                else if (b.sx0) b.sx0[((size_t)n * nplist + (cc - 1)) * NX + r] = chain(v, S.pcoef[cc]);
-            }
+            for (int r = 0; r < NX; ++r) S.xfin[r] = S.zn[0][r][0];
         }
+        if (!full()) return;
+        write_state_columns(b.x0, b.sx0, valid);
     }
 
     // x_ss / sx_ss outputs (ReturnData::process_pre_equilibration, reference src/rdata.cpp:261-286, chain rule :874)
     AB_HD void write_steady_state(const bool valid = true) {
+        if (!full()) return;
+        write_state_columns(b.x_ss, b.sx_ss, valid);
+    }
+
+    // zn[0] of every output column -> xout[n][nx], sxout[n][nplist][nx] (0 for a column that is not integrated)
+    AB_HD void write_state_columns(double* xout, double* sxout, const bool valid) {
         AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!bdf.active(c) || !full()) continue;
-            const int cc = bdf.col(c);
+        for (int j = 0; j < C_OUT; ++j) {
+            if (!out_active(j)) continue;
+            const int oc = out_col(j), cc = int_col(oc);
             AB_UNROLL
             for (int r = 0; r < NX; ++r) {
-                const double v = valid ? S.zn[0][r][cc] : ab_nan();
-                if (cc == 0) { if (b.x_ss) b.x_ss[(size_t)n * NX + r] = v; }
-                else if (b.sx_ss) b.sx_ss[((size_t)n * nplist + (cc - 1)) * NX + r] = chain(v, S.pcoef[cc]);
+                const double v = !valid ? ab_nan() : (!COMPACT || cc >= 0) ? S.zn[0][r][cc >= 0 ? cc : 0] : 0.0;
+                if (oc == 0) { if (xout) xout[(size_t)n * NX + r] = v; }
+                else if (sxout) sxout[((size_t)n * nplist + (oc - 1)) * NX + r] = chain(v, S.pcoef_out[oc]);
             }
         }
     }
@@ -641,10 +683,7 @@ struct Simulation {
     AB_HD void run() {
         auto& g = bdf.g;
         const int nt = b.nt;
-        llh = 0.0;
-        chi2 = 0.0;
-        AB_UNROLL
-        for (int c = 0; c < C; ++c) sllh[c] = 0.0;
+        reset_objective();
         const bool has_preeq = PREEQ && b.k_preeq != nullptr;
         // presimulation (reference src/forwardproblem.cpp:284-321): integrate [t0 - t_presim, t0] with the presimulation
         // fixed parameters (the simulation's if none are given, src/edata.cpp:531-548), nothing is recorded
@@ -954,6 +993,19 @@ struct Simulation {
             if (b.preeq_t) b.preeq_t[n] = done ? pre_t : pe_t;
         }
         if (status != AB_SUCCESS && !(PREEQ && posteq_failed)) invalidate(it, (PREEQ && preeq_failed) ? 0.0 : ab_nan());
+        finish(status, t);
+    }
+
+    AB_HD void reset_objective() {
+        llh = 0.0;
+        chi2 = 0.0;
+        AB_UNROLL
+        for (int j = 0; j < C_OUT; ++j) sllh[j] = 0.0;
+    }
+
+    // end of a condition: xdot / J at the final state, status and objective
+    AB_HD void finish(const int status, const double t) {
+        auto& g = bdf.g;
         // xdot and J at the final state = the last solution the solver returned (ReturnData::store_jacobian_and_derivative,
         // reference rdata.h:707-728; FinalStateStorer, src/forwardproblem.cpp:245-256)
         if (full() && (b.xdot || b.J)) {
@@ -971,15 +1023,15 @@ struct Simulation {
             }
         }
         AB_UNROLL
-        for (int c = 0; c < C; ++c) {
-            if (!bdf.active(c)) continue;
-            const int cc = bdf.col(c);
-            if (cc == 0) {
+        for (int j = 0; j < C_OUT; ++j) {
+            if (!out_active(j)) continue;
+            const int oc = out_col(j);
+            if (oc == 0) {
                 if (b.status) b.status[n] = status;
                 if (b.llh) b.llh[n] = llh;
                 if (b.chi2) b.chi2[n] = chi2;
             } else if (b.sllh) {
-                b.sllh[(size_t)n * nplist + (cc - 1)] = chain(sllh[c], S.pcoef[cc]);
+                b.sllh[(size_t)n * nplist + (oc - 1)] = chain(sllh[j], S.pcoef_out[oc]);
             }
         }
     }

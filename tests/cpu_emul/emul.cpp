@@ -3,7 +3,7 @@
 // Compiles the solver source (amici_b200/csrc/*.cuh) for the host with a lane-group of one
 // lane that owns every column, so the step-control logic can be checked against the compiled
 // reference on machines without a GPU.  The product path is the CUDA build of the same source.
-#include "../../amici_b200/csrc/simulate.cuh"
+#include "../../amici_b200/csrc/flat.cuh"
 #include "../../amici_b200/csrc/models/jakstat_adjoint.cuh"
 #include "../../amici_b200/csrc/models/robertson_ode.cuh"
 #include "../../amici_b200/csrc/models/steadystate.cuh"
@@ -26,6 +26,30 @@ static int run_model(const SolverOptions* o, const BatchView* b) {
         sim.run();
     }
     return 0;
+}
+
+// The flat driver (flat.cuh) with the compact column layout where the model has identically-zero sensitivity columns:
+// what the CUDA build launches for event-free models.  Must agree with run_model bit for bit.
+template <class M>
+static int run_model_flat(const SolverOptions* o, const BatchView* b) {
+    constexpr int NC = M::NP_DYN + 1;
+    using D = FlatDriver<M, 1, NC>;
+    static_assert(M::NP_DYN == M::NP || Layout<M, 1, NC>::COMPACT, "compact layout expected");
+    auto S = std::make_unique<typename D::Shared>();
+    if (o->sensi >= 1 && b->nplist > M::NP) return -1;
+    if (b->sx0_in && M::NP_DYN != M::NP) return -3;
+    int head = 0;
+    WarpAlign align;
+    flat_run<M, 1, NC>(*S, *o, *b, &head, align, [](int) {});
+    return 0;
+}
+
+extern "C" int emul_run_flat(const char* model, const SolverOptions* o, const BatchView* b) {
+    std::string m(model);
+    if (m == "jakstat_adjoint") return run_model_flat<models::jakstat_adjoint>(o, b);
+    if (m == "steadystate") return run_model_flat<models::steadystate>(o, b);
+    if (m == "robertson_ode") return run_model_flat<models::robertson_ode>(o, b);
+    return -2;
 }
 
 extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchView* b) {

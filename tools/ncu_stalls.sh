@@ -7,7 +7,7 @@ M="gpu__time_duration.sum,launch__registers_per_thread,smsp__inst_executed.sum,s
 for s in no_instruction wait short_scoreboard long_scoreboard branch_resolving sleeping math_pipe_throttle barrier dispatch_stall drain imc_miss lg_throttle membar mio_throttle misc not_selected selected tex_throttle; do M="$M,${R}_${s}_per_issue_active.ratio"; done
 mkdir -p gpurun_out
 for v in "$@"; do
-  AMICI_B200_LIB=$PWD/amici_b200/lib/libamici_b200$v.so timeout 300 ncu --metrics $M --clock-control none -k regex:bdf_solve -s 1 -c 1 --csv --log-file gpurun_out/stalls_$tag$v.csv \
+  AMICI_B200_LIB=$PWD/amici_b200/lib/libamici_b200$v.so timeout 300 ncu --metrics $M --clock-control none -k regex:bdf_ -s 1 -c 1 --csv --log-file gpurun_out/stalls_$tag$v.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --n-conditions 4736 > gpurun_out/stalls_$tag$v.log 2>&1
   python - <<PY
 import csv
