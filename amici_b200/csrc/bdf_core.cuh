@@ -57,6 +57,7 @@ struct TrajShared {
     double ctl[16];                  // mirrors of tau[0..6] (ctl[0..6]) and l[0..5] (ctl[8..13]) for indexing by the run-time order
     double ssdat[5][8];              // cvBDFStab history: ring buffer of (sqm2^2, sqm1^2, sq^2) in [1..3] and their ratios to
                                      // the next older entry in [5..7] (the rat[][] of cvSLdet, computed once), newest at ss_head
+    double sld[40];                  // exchange area of bdf_sldet_xchg (ten rounds of up to four values)
     int piv[M::NX];
     int ip_of_col[NCOLS];            // parameter index of an integrated column (-1: state / unused)
     int il_of_col[NCOLS];            // its position in plist
@@ -301,6 +302,9 @@ AB_COLD int cold_hin(typename Layout<M, G, C>::Shared& S, const SolverOptions& o
 void sldet_trace(int tag, double rr);
 #else
 #define AB_SLDET_TRACE(tag, rr)
+#endif
+#if defined(AB_SLDET_RECORD) && !defined(__CUDA_ARCH__)
+void sldet_record(const double* ssdat, int head, int q, int rc);
 #endif
 AB_HD int bdf_sldet(const double (&s)[6][4], const double (&ratc)[5][4], const int q) {
     const double TINY_ = 1e-10;
@@ -576,6 +580,159 @@ AB_HD int bdf_sldet_lanes(const Group<G>& g, const double (&ssdat)[5][8], const 
     if (kflag == 2) kflag = 5;
     if (kflag == 3) kflag = 6;
     return kflag;
+}
+
+// cvSLdet with the three orders in three lanes and the cross-order values exchanged through the group's shared-memory
+// slice (one store + one group barrier + broadcast loads per exchange, each exchange in its own slots).  For lane groups that
+// share their warp with other conditions (G < 32): register shuffles / votes with a partial lane mask compile into a
+// divergence check plus an out-of-line serialised region per call site, and the all-orders-per-lane form (bdf_sldet) is
+// 5.5 KB of straight-line code in a step loop whose speed is set by instruction supply (profiles/r02_*).  Same arithmetic per
+// order and same return values as bdf_sldet / bdf_sldet_lanes.
+template <int G>
+AB_HD int bdf_sldet_xchg(const Group<G>& g, const double (&ssdat)[5][8], double (&xb)[40], const int ss_head, const int q) {
+    const double TINY_ = 1e-10;
+    const double rrcut = 0.98, vrrtol = 1.0e-4, vrrt2 = 5.0e-4, sqtol = 1.0e-3, rrtol = 1.0e-2;
+    const int k = ((g.lane & 3) == 3) ? 1 : (g.lane & 3) + 1;
+    const bool pub = g.lane < 3;   // lanes 0..2 publish orders 1..3
+    // exchange round `slot`: every lane gets the three lanes' values
+#define AB_X3(slot, v, v1, v2, v3)        \
+    do {                                  \
+        if (pub) xb[4 * (slot) + g.lane] = (v); \
+        g.sync();                         \
+        v1 = xb[4 * (slot)];              \
+        v2 = xb[4 * (slot) + 1];          \
+        v3 = xb[4 * (slot) + 2];          \
+    } while (0)
+    double s[6], rat[5];
+    g.sync();   // the previous call's loads are done before this call's stores
+    AB_UNROLL
+    for (int i = 1; i <= 5; ++i) {
+        int idx = ss_head + i - 1;
+        idx = idx >= 5 ? idx - 5 : idx;
+        s[i] = ssdat[idx][k];
+        if (i <= 4) rat[i] = ssdat[idx][4 + k];
+    }
+    double smink = s[1], smaxk = 0.0;
+    AB_UNROLL
+    for (int i = 1; i <= 5; i++) {
+        smink = ab_min(smink, s[i]);
+        smaxk = ab_max(smaxk, s[i]);
+    }
+    const double smax = smaxk, ssmax = smaxk * smaxk;
+    double sumrat = 0.0, sumrsq = 0.0;
+    AB_UNROLL
+    for (int i = 1; i <= 4; i++) {
+        sumrat += rat[i];
+        sumrsq += rat[i] * rat[i];
+    }
+    const double rav = 0.25 * sumrat;
+    const double vrat = fabs(0.25 * sumrsq - rav * rav);
+    const double qc5 = s[1] * s[3] - s[2] * s[2];
+    const double qc4 = s[2] * s[3] - s[1] * s[4];
+    const double qc2 = s[2] * s[5] - s[3] * s[4];
+    const double qc1 = s[4] * s[4] - s[3] * s[5];
+    double b1, b2, b3, v1, v2, v3;
+    AB_X3(0, (smink < TINY_ * smaxk) ? 1.0 : 0.0, b1, b2, b3);
+    if (b1 + b2 + b3 != 0.0) return -1;
+    AB_X3(1, vrat, v1, v2, v3);
+    const double vmin = ab_min(v1, ab_min(v2, v3)), vmax = ab_max(v1, ab_max(v2, v3));
+    double rr = 0.0;
+    int kflag = 0;
+    if (vmin < vrrtol * vrrtol) {
+        if (vmax > vrrt2 * vrrt2) return -2;
+        double r1, r2, r3;
+        AB_X3(2, rav, r1, r2, r3);
+        rr = (r1 + r2 + r3) / 3.0;
+        const double drrmax = ab_max(fabs(r1 - rr), ab_max(fabs(r2 - rr), fabs(r3 - rr)));
+        if (drrmax > vrrt2) return -3;
+        kflag = 1;
+    } else {
+        // eliminate with column 1, then column 2; rr from column 3 (rows 1, 2, 4, 5; row 3 is zero)
+        if (g.lane == 0) { xb[8] = qc1; xb[9] = qc2; xb[10] = qc4; xb[11] = qc5; xb[12] = ssmax; }
+        g.sync();
+        const double a1 = xb[8], a2 = xb[9], a4 = xb[10], a5 = xb[11];
+        if (fabs(a1) < TINY_ * xb[12]) return -4;
+        const double tem1 = fast_div(qc1, a1);
+        const double e2 = qc2 - tem1 * a2, e4 = qc4 - tem1 * a4, e5 = qc5 - tem1 * a5;
+        if (g.lane == 1) { xb[13] = e2; xb[14] = e4; xb[15] = e5; xb[16] = ssmax; }
+        g.sync();
+        const double bb2 = xb[13], bb4 = xb[14], bb5 = xb[15];
+        if (fabs(bb2) < TINY_ * xb[16]) return -4;
+        const double tem2 = fast_div(e2, bb2);
+        const double f4 = e4 - tem2 * bb4, f5 = e5 - tem2 * bb5;
+        if (g.lane == 2) { xb[17] = f4; xb[18] = f5; xb[19] = ssmax; }
+        g.sync();
+        const double c4 = xb[17], c5 = xb[18];
+        if (fabs(c4) < TINY_ * xb[19]) return -4;
+        rr = -fast_div(c5, c4);
+        if (rr < TINY_ || rr > 100.0) return -5;
+        double qkr = qc5 + rr * (qc4 + rr * rr * (qc2 + rr * qc1));
+        double n1, n2, n3;
+        AB_X3(5, (fabs(qkr) < sqtol * ssmax) ? 0.0 : 1.0, n1, n2, n3);
+        if (n1 + n2 + n3 == 0.0) {
+            kflag = 2;
+        } else {
+            const double inv_ssmax = fast_div(1.0, ssmax);
+            double sqmin = 0.0;
+            AB_NOUNROLL
+            for (int it = 1; it <= 3; it++) {
+                const double qp = qc4 + rr * rr * (3.0 * qc2 + rr * 4.0 * qc1);
+                double drr = 0.0;
+                if (fabs(qp) > TINY_ * ssmax) drr = -fast_div(qkr, qp);
+                const double rrc = rr + drr;
+                double sv1, sv2, sv3;
+                g.sync();   // slots 6..9 are re-used by the iterations
+                AB_X3(6, rrc, sv1, sv2, sv3);
+                const double p1 = qc5 + sv1 * (qc4 + sv1 * sv1 * (qc2 + sv1 * qc1));
+                const double p2 = qc5 + sv2 * (qc4 + sv2 * sv2 * (qc2 + sv2 * qc1));
+                const double p3 = qc5 + sv3 * (qc4 + sv3 * sv3 * (qc2 + sv3 * qc1));
+                // m_j = max over the orders of |p_j| / ssmax: three values per publishing lane
+                if (pub) { xb[28 + g.lane] = fabs(p1) * inv_ssmax; xb[32 + g.lane] = fabs(p2) * inv_ssmax; xb[36 + g.lane] = fabs(p3) * inv_ssmax; }
+                g.sync();
+                const double m1 = ab_max(xb[28], ab_max(xb[29], xb[30])), m2 = ab_max(xb[32], ab_max(xb[33], xb[34]));
+                const double m3 = ab_max(xb[36], ab_max(xb[37], xb[38]));
+                sqmin = m1 + 1.0;
+                int kmin = 1;
+                if (m1 < sqmin) { kmin = 1; sqmin = m1; }
+                if (m2 < sqmin) { kmin = 2; sqmin = m2; }
+                if (m3 < sqmin) { kmin = 3; sqmin = m3; }
+                rr = (kmin == 1) ? sv1 : (kmin == 2) ? sv2 : sv3;
+                if (sqmin < sqtol) {
+                    kflag = 3;
+                    break;
+                }
+                qkr = (kmin == 1) ? p1 : (kmin == 2) ? p2 : p3;
+            }
+            if (sqmin > sqtol) return -6;
+        }
+    }
+    if (!(rr > rrcut)) return kflag;   // only a result > 3 acts, and that needs rr > rrcut
+    const double rsa = s[1], rsb = s[2] * rr, rsc = s[3] * rr * rr;
+    const double rsd = s[4] * rr * rr * rr;
+    const double rd1a = rsa - rsb, rd1b = rsb - rsc, rd1c = rsc - rsd;
+    const double rd2a = rd1a - rd1b, rd2b = rd1b - rd1c, rd3a = rd2a - rd2b;
+    const bool small = fabs(rd1b) < TINY_ * smax;
+    const double cest1 = small ? 1.0 : -fast_div(rd3a, rd1b);
+    double w1, w2, w3;
+    g.sync();
+    AB_X3(0, (small || cest1 < TINY_ || cest1 > 4.0) ? 1.0 : 0.0, w1, w2, w3);
+    if (w1 + w2 + w3 != 0.0) return -7;
+    const double sigsq = s[3] + fast_div(rd2b, cest1 * (rr * rr));
+    double sg1, sg2, sg3;
+    AB_X3(1, sigsq, sg1, sg2, sg3);
+    if (sg2 < TINY_) return -8;
+    const double ratp = fast_div(sg3, sg2), ratm = fast_div(sg1, sg2);
+    const double qfac1 = 0.25 * (q * q - 1.0), qfac2 = (q == 3) ? 1.0 : (q == 4) ? (2.0 / 3.0) : 0.5;
+    const double bb = ratp * ratm - 1.0 - qfac1 * ratp;
+    const double tem = 1.0 - qfac2 * bb;
+    if (fabs(tem) < TINY_) return -8;
+    const double rrb = fast_div(1.0, tem);
+    if (fabs(rrb - rr) > rrtol) return -9;
+    if (kflag == 1) kflag = 4;
+    if (kflag == 2) kflag = 5;
+    if (kflag == 3) kflag = 6;
+    return kflag;
+#undef AB_X3
 }
 
 // x^(1/n) for the four step-size formulas (eta = 1/((bias*err)^(1/n) + addon))
@@ -864,7 +1021,11 @@ struct BdfControl {
                 if (i <= 4) ratc[i][kk] = S.ssdat[idx][4 + kk];
             }
         }
-        return bdf_sldet(s, ratc, q);
+        const int rc = bdf_sldet(s, ratc, q);
+#if defined(AB_SLDET_RECORD) && !defined(__CUDA_ARCH__)
+        sldet_record(&S.ssdat[0][0], ss_head, q, rc);   // tests/cpu_emul: harvest real ring buffers as test vectors
+#endif
+        return rc;
     }
 
     // cvSetEta (cvodes.c:7798) with eta_min_fx = 0, eta_max_fx = 1.5, hmin = 0
@@ -1346,7 +1507,11 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
     AB_HD int nx() const { return NX; }
     AB_HD int sldet() const {
 #if defined(__CUDA_ARCH__)
-        if (G >= 4) return bdf_sldet_lanes<G>(g, S.ssdat, Base::ss_head, q);
+        // one condition per warp: the three orders in three lanes (a shorter dependent chain on the pace-setting path of the
+        // aligned warps).  Smaller groups share their warp with other conditions: every collective of the lane version is then
+        // a divergence check plus a serialised region per group, and the serial form is both fewer instructions and less code.
+        if (G == 32) return bdf_sldet_lanes<G>(g, S.ssdat, Base::ss_head, q);
+        if (G >= 4) return bdf_sldet_xchg<G>(g, S.ssdat, S.sld, Base::ss_head, q);
 #endif
         return Base::sldet_serial();
     }
@@ -1476,6 +1641,7 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
             if (g.lane == 0) sync_pos[sync_w] = 0x7fffffff;
             __syncwarp();
         }
+        if (G == 16 && sync_pos && g.lane == 0) sync_pos[sync_w] = 0x7fffffff;   // see step_sync_arrive
 #endif
     }
     AB_HD void step_sync_arrive() {
@@ -1491,6 +1657,38 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
                     if (pv < m) m = pv;
                 }
                 if (m >= sync_gen) break;
+                __nanosleep(40);
+            }
+        }
+        // Two conditions per warp (G == 16): the warp takes part in the alignment only while BOTH of its conditions are at the
+        // top of a step attempt together (__activemask() is full: the two halves execute this very instruction as one
+        // stream, and they stay together through the uniform poll loop).  A half that is here alone — its partner repeats an
+        // attempt, writes a timepoint, or waits at a re-convergence point for this half — must not wait for anybody (the
+        // partner could be waiting for it), so it takes the warp out of the group and runs free; the warp re-joins, at the
+        // generation of the slowest member, the next time both halves arrive together.  sync_pos[w] itself carries the
+        // membership and the generation, so the two halves cannot disagree about them.
+        if (G == 16 && sync_pos) {
+            if (__activemask() != 0xffffffffu) {
+                if (g.lane == 0) sync_pos[sync_w] = 0x7fffffff;
+                return;
+            }
+            int cur = sync_pos[sync_w], m = 0x7fffffff;
+            for (int v = 0; v < sync_n; ++v) {
+                const int pv = sync_pos[v];
+                if (v != sync_w && pv < m) m = pv;
+            }
+            if (cur == 0x7fffffff) cur = (m != 0x7fffffff) ? m : 0;
+            const int gen = cur + 1;
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) sync_pos[sync_w] = gen;
+            __syncwarp();
+            for (;;) {
+                m = 0x7fffffff;
+                for (int v = 0; v < sync_n; ++v) {
+                    const int pv = sync_pos[v];
+                    if (pv < m) m = pv;
+                }
+                if (m >= gen) break;
                 __nanosleep(40);
             }
         }
@@ -1637,9 +1835,14 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
     // stored once per step instead of three times.  The pass is flat: zn[j] is NX*NCOLS contiguous doubles and an
     // elementwise update does not care which lane owns a column, so all G lanes share the elements (JAK-STAT: 162
     // elements in 6 rounds of a warp instead of 9 rows on 18 lanes).  pred = +1 predict, -1 restore, 0 neither.
-    template <int Q, int PRED>
-    AB_HD void history_pass_q(const bool cmpl, const bool resc) {
+    // One instantiation serves every order: rows above the current order are taken as zero and not written back (x + 0 and
+    // x * f are exact, so the values are those of an order-specific pass).  Two conditions that share a warp (G = 16) at
+    // different orders then run ONE instruction stream instead of two serialised instantiations, and the hot loop holds one
+    // copy of the pass instead of one per order in use.
+    template <int PRED>
+    AB_HD void history_pass(const bool cmpl, const bool resc) {
         constexpr int NEL = NX * NCOLS;
+        constexpr int Q = QMAX;
         double* z0 = &S.zn[0][0][0];
         const double* ab = &S.acorbuf[0][0];
         double f[Q + 1], lc[Q + 1];
@@ -1647,13 +1850,13 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
         AB_UNROLL
         for (int jj = 1; jj <= Q; ++jj) f[jj] = f[jj - 1] * eta;
         AB_UNROLL
-        for (int jj = 0; jj <= Q; ++jj) lc[jj] = cmpl ? l[jj] : 0.0;   // no pending correction: add 0 * acorbuf
+        for (int jj = 0; jj <= Q; ++jj) lc[jj] = (cmpl && jj <= q) ? l[jj] : 0.0;   // no pending correction: add 0 * acorbuf
         g.sync();
         AB_NOUNROLL
         for (int e = g.lane; e < NEL; e += G) {
             double z[Q + 1];
             AB_UNROLL
-            for (int jj = 0; jj <= Q; ++jj) z[jj] = z0[jj * NEL + e];
+            for (int jj = 0; jj <= Q; ++jj) z[jj] = (jj <= 1 || jj <= q) ? z0[jj * NEL + e] : 0.0;
             const double a = cmpl ? ab[e] : 0.0;
             AB_UNROLL
             for (int jj = 0; jj <= Q; ++jj) z[jj] += lc[jj] * a;
@@ -1669,19 +1872,10 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
                 }
             }
             AB_UNROLL
-            for (int jj = 0; jj <= Q; ++jj) z0[jj * NEL + e] = z[jj];
+            for (int jj = 0; jj <= Q; ++jj)
+                if (jj <= 1 || jj <= q) z0[jj * NEL + e] = z[jj];
         }
         g.sync();
-    }
-    template <int PRED>
-    AB_HD void history_pass(const bool cmpl, const bool resc) {
-        switch (q) {
-            case 1: history_pass_q<1, PRED>(cmpl, resc); break;
-            case 2: history_pass_q<2, PRED>(cmpl, resc); break;
-            case 3: history_pass_q<3, PRED>(cmpl, resc); break;
-            case 4: history_pass_q<4, PRED>(cmpl, resc); break;
-            default: history_pass_q<5, PRED>(cmpl, resc); break;
-        }
     }
     // -----------------------------------------------------------------------------------------
     // nonlinear solve: cvNls (cvodes.c:6894) + SUNNonlinSolSolve_Newton (sunnonlinsol_newton.c:176-330)

@@ -32,6 +32,20 @@ struct Group {
 #endif
     }
 
+    // G == 16: two conditions share a warp.  When both halves execute a collective together (the common case: they follow
+    // the same instruction stream until a data-dependent branch separates them), a collective with the half's own mask is
+    // compiled into a divergence check plus a serialised WARPSYNC.COLLECTIVE region per half (~20 out-of-line instructions
+    // per call site).  If the whole warp is here (__activemask() is full: all 32 lanes execute this very instruction, so all
+    // 32 also reach the full-mask collective that follows), ONE full-warp instruction serves both halves instead: shuffles
+    // address the own half, reductions are done once per half with the other half's input neutralised.
+    AB_HD bool whole_warp() const {
+#if defined(__CUDA_ARCH__)
+        if (G == 16) return __activemask() == 0xffffffffu;
+#endif
+        return false;
+    }
+    AB_HD bool upper() const { return (mask & 1u) == 0u; }   // G == 16: this group is the upper half of its warp
+
     AB_HD void sync() const {
 #if defined(__CUDA_ARCH__)
         if (G > 1) __syncwarp(mask);
@@ -45,8 +59,18 @@ struct Group {
 #if defined(__CUDA_ARCH__)
         if (G > 1) {
             const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
-            const unsigned mhi = __reduce_max_sync(mask, hi);
-            const unsigned mlo = __reduce_max_sync(mask, hi == mhi ? lo : 0u);
+            unsigned mhi, mlo;
+            if (whole_warp()) {
+                const bool up = upper();
+                const unsigned a = __reduce_max_sync(0xffffffffu, up ? 0u : hi), b = __reduce_max_sync(0xffffffffu, up ? hi : 0u);
+                mhi = up ? b : a;
+                const unsigned l2 = hi == mhi ? lo : 0u;
+                const unsigned c = __reduce_max_sync(0xffffffffu, up ? 0u : l2), d = __reduce_max_sync(0xffffffffu, up ? l2 : 0u);
+                mlo = up ? d : c;
+            } else {
+                mhi = __reduce_max_sync(mask, hi);
+                mlo = __reduce_max_sync(mask, hi == mhi ? lo : 0u);
+            }
             v = __hiloint2double((int)mhi, (int)mlo);
         }
 #endif
@@ -58,8 +82,18 @@ struct Group {
 #if defined(__CUDA_ARCH__)
         if (G > 1) {
             const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
-            const unsigned mhi = __reduce_min_sync(mask, hi);
-            const unsigned mlo = __reduce_min_sync(mask, hi == mhi ? lo : 0xffffffffu);
+            unsigned mhi, mlo;
+            if (whole_warp()) {
+                const bool up = upper();
+                const unsigned a = __reduce_min_sync(0xffffffffu, up ? 0xffffffffu : hi), b = __reduce_min_sync(0xffffffffu, up ? hi : 0xffffffffu);
+                mhi = up ? b : a;
+                const unsigned l2 = hi == mhi ? lo : 0xffffffffu;
+                const unsigned c = __reduce_min_sync(0xffffffffu, up ? 0xffffffffu : l2), d = __reduce_min_sync(0xffffffffu, up ? l2 : 0xffffffffu);
+                mlo = up ? d : c;
+            } else {
+                mhi = __reduce_min_sync(mask, hi);
+                mlo = __reduce_min_sync(mask, hi == mhi ? lo : 0xffffffffu);
+            }
             v = __hiloint2double((int)mhi, (int)mlo);
         }
 #endif
@@ -68,7 +102,10 @@ struct Group {
 
     AB_HD double bcast(double v, int src) const {
 #if defined(__CUDA_ARCH__)
-        if (G > 1) v = __shfl_sync(mask, v, src, G);
+        if (G > 1) {
+            if (whole_warp()) v = __shfl_sync(0xffffffffu, v, src, G);   // width G: every half reads its own lane src
+            else v = __shfl_sync(mask, v, src, G);
+        }
 #else
         (void)src;
 #endif
@@ -77,7 +114,10 @@ struct Group {
 
     AB_HD int bcast(int v, int src) const {
 #if defined(__CUDA_ARCH__)
-        if (G > 1) v = __shfl_sync(mask, v, src, G);
+        if (G > 1) {
+            if (whole_warp()) v = __shfl_sync(0xffffffffu, v, src, G);
+            else v = __shfl_sync(mask, v, src, G);
+        }
 #else
         (void)src;
 #endif
@@ -86,7 +126,10 @@ struct Group {
 
     AB_HD bool any(bool p) const {
 #if defined(__CUDA_ARCH__)
-        if (G > 1) return (__ballot_sync(mask, p) & mask) != 0u;
+        if (G > 1) {
+            if (whole_warp()) return (__ballot_sync(0xffffffffu, p) & mask) != 0u;
+            return (__ballot_sync(mask, p) & mask) != 0u;
+        }
 #endif
         return p;
     }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <string>
 
 #include "registry.h"
@@ -17,6 +18,9 @@
 #endif
 #ifndef AB_THREADS_G32
 #define AB_THREADS_G32 256
+#endif
+#ifndef AB_STEP_SYNC_G16
+#define AB_STEP_SYNC_G16 0   // opportunistic alignment of warps that hold two conditions (Bdf::step_sync_arrive): measured neutral
 #endif
 #ifndef AB_THREADS_SMALL
 #define AB_THREADS_SMALL 64
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
     Shared* slices = reinterpret_cast<Shared*>(smem_raw + SYNC_BYTES);
     Shared& S = slices[threadIdx.x / G];
     Group<G> g;
-    constexpr bool STEP_SYNC = AB_STEP_SYNC && G == 32 && THREADS > 32;
+    constexpr bool STEP_SYNC = AB_STEP_SYNC && (G == 32 || (G == 16 && AB_STEP_SYNC_G16)) && THREADS > 32;
     if (STEP_SYNC) {
         if (threadIdx.x < THREADS / 32) sync_pos[threadIdx.x] = 0x7fffffff;
         __syncthreads();
@@ -159,6 +163,8 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
         last_error() = "kernel does not fit on an SM";
         return AB_E_CUDA;
     }
+    if (const char* cap = std::getenv("AMICI_B200_BLOCKS_PER_SM"))   // experiments only (profiles/r02_variants.md)
+        if (std::atoi(cap) > 0 && std::atoi(cap) < per_sm) per_sm = std::atoi(cap);
     long want = ((long)b.N + groups - 1) / groups;
     long grid = (long)sms * per_sm;
     if (want < grid) grid = want;

@@ -177,6 +177,13 @@ int ab_measure_fp64_peak(double* tflops);
 /* Number of kernels launched by this library since load (for bench accounting). */
 long ab_kernel_launch_count(void);
 
+/* Device self-test (test hook, not a product path): the engine's forms of CVODES' stability-limit detection (cvSLdet,
+ * reference ThirdParty/sundials/src/cvodes/cvodes.c:8256-8570) on n caller-supplied ring buffers ssdat[n][5][8] (host memory;
+ * entry [i][1..3] = squared scaled derivative norms, [i][5..7] = their ratios to the next older entry), newest entry at
+ * head[n], order q[n] in 3..5.  out[n][4] = results of (all orders per lane, three lanes + shuffles, three lanes + shared
+ * memory in a 16-lane group, the same in a 4-lane group); all four must be equal. */
+int ab_selftest_sldet(int n, const double* ssdat, const int* head, const int* q, int* out);
+
 /* Last CUDA error string seen by the library on this thread ("" if none). */
 const char* ab_last_error(void);
 

@@ -15,6 +15,22 @@
 
 using namespace amici_b200;
 
+#if defined(AB_SLDET_RECORD)
+// harvest of the ring buffers cvSLdet is called with (tests/golden/make_sldet_cases.py): 43 doubles per call
+static double* g_rec = nullptr;
+static long g_rec_cap = 0, g_rec_n = 0;
+namespace amici_b200 {
+void sldet_record(const double* ssdat, int head, int q, int rc) {
+    if (!g_rec || g_rec_n >= g_rec_cap) return;
+    double* d = g_rec + 43 * g_rec_n++;
+    for (int i = 0; i < 40; ++i) d[i] = ssdat[i];
+    d[40] = head; d[41] = q; d[42] = rc;
+}
+}
+extern "C" void emul_sldet_record(double* buf, long cap) { g_rec = buf; g_rec_cap = cap; g_rec_n = 0; }
+extern "C" long emul_sldet_recorded() { return g_rec_n; }
+#endif
+
 template <class M>
 static int run_model(const SolverOptions* o, const BatchView* b) {
     constexpr int NC = M::NP + 1;

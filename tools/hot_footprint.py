@@ -69,7 +69,7 @@ def main():
         steps = sorted(counts)[int(0.9 * len(counts))]
     thresh = 0.2 * steps
     franges = {}
-    dyn, hot, stall, noinst = (collections.Counter() for _ in range(4))
+    dyn, hot, stall, noinst, thr = (collections.Counter() for _ in range(5))
     tot_dyn = tot_hot = tot_stall = 0
     for r in rows:
         off = int(r["Address"], 16) - base
@@ -88,6 +88,7 @@ def main():
             key = "%s:%s" % (os.path.basename(f), name)
         n = int(r["Instructions Executed"])
         dyn[key] += n
+        thr[key] += int(r.get("Thread Instructions Executed", 0) or 0)
         tot_dyn += n
         if n >= thresh:
             hot[key] += 16
@@ -98,10 +99,10 @@ def main():
         noinst[key] += int(r.get("stall_no_inst", 0) or 0)
     print("steps=%.3g  executed warp-instr=%.4g (%.0f per step)  hot bytes=%d  stall samples=%d" %
           (steps, tot_dyn, tot_dyn / steps, tot_hot, tot_stall))
-    print("%-44s %9s %6s %8s %6s %7s" % ("function", "instr/step", "dyn%", "hotB", "stall%", "noinst%"))
+    print("%-44s %9s %6s %8s %6s %7s %6s" % ("function", "instr/step", "dyn%", "hotB", "stall%", "noinst%", "lanes"))
     for k, n in dyn.most_common(45):
-        print("%-44s %9.1f %6.1f %8d %6.1f %7.1f" % (k, n / steps, 100.0 * n / tot_dyn, hot[k], 100.0 * stall[k] / max(1, tot_stall),
-                                                  100.0 * noinst[k] / max(1, stall[k])))
+        print("%-44s %9.1f %6.1f %8d %6.1f %7.1f %6.1f" % (k, n / steps, 100.0 * n / tot_dyn, hot[k], 100.0 * stall[k] / max(1, tot_stall),
+                                                        100.0 * noinst[k] / max(1, stall[k]), thr[k] / max(1, n)))
 
 
 if __name__ == "__main__":
