@@ -121,6 +121,7 @@ def load_library() -> C.CDLL:
     lib.ab_reduce_objective.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ab_kernel_launch_count.restype = C.c_long
     lib.ab_last_error.restype = C.c_char_p
+    lib.ab_last_kernel_name.restype = C.c_char_p
     _lib = lib
     return lib
 

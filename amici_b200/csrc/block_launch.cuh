@@ -87,6 +87,7 @@ int launch_block_variant(const ab_solver_options& o, const ab_batch& b, int* que
     AB_CUDA(cudaMemsetAsync(queue_head, 0, sizeof(int), st));
     kern<<<(unsigned)grid, NCP, smem, st>>>(o, b, queue_head, pg, w.dev);
     g_launches++;
+    last_kernel() = std::string("block_solve_kernel<") + M::name() + "," + std::to_string(NCP) + ">";
     AB_CUDA(cudaGetLastError());
     return AB_OK;
 }

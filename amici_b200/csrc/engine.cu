@@ -28,6 +28,10 @@ std::string& last_error() {
     static thread_local std::string e;
     return e;
 }
+std::string& last_kernel() {
+    static thread_local std::string k;
+    return k;
+}
 #define g_err last_error()
 
 // sum of llh / sllh over successful conditions; one block per output column, tree reduction in shared memory
@@ -216,6 +220,8 @@ int ab_measure_fp64_peak(double* tflops) {
 long ab_kernel_launch_count(void) { return g_launches.load(); }
 
 const char* ab_last_error(void) { return last_error().c_str(); }
+
+const char* ab_last_kernel_name(void) { return last_kernel().c_str(); }
 
 // ---- host-buffer entry point ------------------------------------------------------------------
 namespace {

@@ -172,6 +172,8 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
     AB_CUDA(cudaMemsetAsync(queue_head, 0, sizeof(int), st));
     kern<<<(unsigned)grid, THREADS, smem, st>>>(o, b, queue_head, pg);
     g_launches++;
+    last_kernel() = std::string((AB_FLAT && !PREEQ && M::NE == 0) ? "bdf_flat_kernel<" : "bdf_solve_kernel<") + M::name() + "," + std::to_string(G) + "," +
+                    std::to_string(C) + "," + std::to_string(THREADS) + "," + std::to_string(MINBLOCKS) + "," + (PREEQ ? "preeq" : "plain") + ">";
     AB_CUDA(cudaGetLastError());
     return AB_OK;
 }

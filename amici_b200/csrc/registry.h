@@ -12,6 +12,7 @@ namespace amici_b200 {
 
 extern std::atomic<long> g_launches;  // kernels launched by this library
 std::string& last_error();            // thread-local message behind ab_last_error()
+std::string& last_kernel();           // description of the solve kernel this thread launched last (ab_last_kernel_name)
 
 inline bool cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;

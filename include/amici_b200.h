@@ -187,6 +187,10 @@ int ab_selftest_sldet(int n, const double* ssdat, const int* head, const int* q,
 /* Last CUDA error string seen by the library on this thread ("" if none). */
 const char* ab_last_error(void);
 
+/* The solve kernel this thread launched last, as "kernel<model,G,C,threads,minblocks,variant>" (G lanes per condition,
+ * C columns per lane), "" if none: which instantiation served a batch (bench.py reports it in `roofline.kernel`). */
+const char* ab_last_kernel_name(void);
+
 #ifdef __cplusplus
 }
 #endif

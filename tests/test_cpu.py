@@ -450,3 +450,34 @@ def test_emulation_full_condition_context_matches_reference(built, preeq):
     np.testing.assert_allclose(out["x"], r["x"].reshape(out["x"].shape), rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(out["sx"], r["sx"].reshape(out["sx"].shape), rtol=1e-3, atol=1e-6)
     np.testing.assert_allclose(out["llh"], r["llh"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("fixture,model", [("jakstat_adjoint", "jakstat_adjoint"), ("jakstat_adjoint_log10", "jakstat_adjoint"),
+                                           ("steadystate", "steadystate")])
+def test_emulation_flat_compact_is_bit_identical(built, fixture, model):
+    """Two engine variants against each other on the host build of the solver source: (a) the nested driver with one
+    integrated column per parameter, (b) the flat driver (flat.cuh) with the compact layout that leaves out the columns whose
+    state sensitivity is identically zero (JAK-STAT: 11 integrated columns instead of 18; what the CUDA build launches).
+    Dropping exact-zero columns changes no max-norm and no decision: every ReturnData field is identical bit for bit."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    lib = _emul(built)
+    outs = []
+    for fn in (lib.emul_run, lib.emul_run_flat):
+        b, out, keep = _capi.make_batch(MODEL_DIMS[model], g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"])
+        o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
+        assert fn(model.encode(), C.byref(o), C.byref(b)) == 0
+        outs.append(out)
+    for f in outs[0]:
+        np.testing.assert_array_equal(outs[0][f], outs[1][f], err_msg=f)
+    # a parameter listed twice shares its integrated column; a subset keeps its order
+    plist = np.array([3, 11, 3, 16, 5, 0], dtype=np.int32) if model == "jakstat_adjoint" else np.array([1, 1, 0], dtype=np.int32)
+    outs = []
+    for fn in (lib.emul_run, lib.emul_run_flat):
+        b, out, keep = _capi.make_batch(MODEL_DIMS[model], g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"], plist=plist)
+        o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
+        assert fn(model.encode(), C.byref(o), C.byref(b)) == 0
+        outs.append(out)
+    for f in outs[0]:
+        np.testing.assert_array_equal(outs[0][f], outs[1][f], err_msg=f)
+    dup = (0, 2) if model == "jakstat_adjoint" else (0, 1)
+    np.testing.assert_array_equal(outs[1]["sx"][:, :, dup[0]], outs[1]["sx"][:, :, dup[1]])
