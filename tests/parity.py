@@ -79,3 +79,56 @@ def reference_triple(ref, ts, p, k, fields, num_threads=1, truth=True, **kw):
         for f in r:
             out[f"{name}_{f}"] = r[f]
     return out
+
+
+def per_condition_err(a, b, truth, rtol=10 * RTOL, atol=10 * ATOL):
+    """max over the elements of one condition of |a - b| / (10 atol + 10 rtol |truth|); arrays are [N, ...]."""
+    a, b, truth = (np.asarray(v, float) for v in (a, b, truth))
+    b, truth = b.reshape(a.shape), truth.reshape(a.shape)
+    n = a.shape[0]
+    err = np.abs(a - b) / (atol + rtol * np.abs(truth))
+    err = np.where(np.isnan(a) & np.isnan(b), 0.0, err)     # same NaN (an unset z slot): no error
+    return err.reshape(n, -1).max(axis=1) if err.size else np.zeros(n)
+
+
+QUANTILES = (50, 90, 99)
+
+
+def check_distribution(cand: dict, gold: dict, fields, ok=None, factor=FACTOR, qfactor=1.5, verbose=True):
+    """Parity protocol for LARGE batches (hundreds to thousands of reference-checked conditions).  A maximum over thousands of
+    chaotic step sequences is an extreme-value statistic, so next to the max-based rule of check_against_golden this
+    compares DISTRIBUTIONS over conditions of the per-condition scaled error:
+
+      accuracy  : every quantile (50 / 90 / 99 %) of the candidate's error against `truth` is at most qfactor x the same
+                  quantile of the reference's own error (max of klu, dense), or inside the stated tolerance outright (<= 1);
+      deviation : every quantile of the candidate's deviation from `klu` is at most factor x max(quantile of dense-vs-klu,
+                  quantile of the reference's error against truth), or <= 1;
+      maximum   : the rule of check_against_golden on the maxima.
+
+    `ok`: boolean mask of the conditions to compare (those that succeed in every run)."""
+    report = {}
+    for f in fields:
+        c = np.asarray(cand[f], float)
+        klu, dense, truth = (np.asarray(gold[f"{n}_{f}"], float).reshape(c.shape) for n in ("klu", "dense", "truth"))
+        if ok is not None:
+            c, klu, dense, truth = c[ok], klu[ok], dense[ok], truth[ok]
+        assert (np.isnan(c) == np.isnan(klu)).all(), f"{f}: NaN pattern differs from the reference's"
+        e_c, e_k, e_d = (per_condition_err(v, truth, truth) for v in (c, klu, dense))
+        d_c, d_d = per_condition_err(c, klu, truth), per_condition_err(dense, klu, truth)
+        row = {}
+        for q in QUANTILES:
+            qc, qr = np.percentile(e_c, q), max(np.percentile(e_k, q), np.percentile(e_d, q))
+            dc, dr = np.percentile(d_c, q), max(np.percentile(d_d, q), qr)
+            row[q] = (qc, qr, dc, np.percentile(d_d, q))
+            assert qc <= max(1.0, qfactor * qr), (f, "accuracy", q, qc, qr)
+            assert dc <= max(1.0, factor * dr), (f, "deviation", q, dc, dr)
+        mc, mr = e_c.max(), max(e_k.max(), e_d.max())
+        md, mdr = d_c.max(), max(d_d.max(), mr)
+        row["max"] = (mc, mr, md, d_d.max())
+        assert mc <= max(1.0, factor * mr), (f, "max accuracy", mc, mr)
+        assert md <= max(1.0, factor * mdr), (f, "max deviation", md, mdr)
+        report[f] = row
+        if verbose:
+            for q, (qc, qr, dc, dd) in row.items():
+                print(f"{f:6s} {str(q):>4s}  cand-truth {qc:10.3e} (ref {qr:10.3e})   cand-klu {dc:10.3e} (dense-klu {dd:10.3e})")
+    return report

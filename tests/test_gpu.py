@@ -40,6 +40,29 @@ def _bits(g, key):
     return [i for i in range(32) if int(g[key]) >> i & 1] if key in g else None
 
 
+def _check_live(res, ref, ts, p, k, fields, ok=None, status_equal=True, **kw):
+    """Parity protocol (tests/parity.py) for a FRESH batch: three runs of the compiled reference on the same
+    inputs (KLU, dense, tight-tolerance truth) take the place of a committed fixture.  No ad-hoc tolerances: the candidate must
+    be as close to the truth as the reference is, and as close to the KLU run as the dense run is (factor 4)."""
+    fields = list(fields)
+    gold = parity.reference_triple(ref, ts, p, k, ["status"] + fields, num_threads=min(ref.max_threads(), 16), **kw)
+    st = np.asarray(res["status"])
+    if status_equal:
+        np.testing.assert_array_equal(st, gold["klu_status"], err_msg="status differs from the reference's")
+    sel = (st == 0) & (gold["klu_status"] == 0) & (gold["dense_status"] == 0) & (gold["truth_status"] == 0)
+    if ok is not None:
+        sel &= ok
+    assert sel.any()
+    cand, g2 = {}, {}
+    for f in fields:
+        a = np.asarray(res[f], float)
+        cand[f] = a[sel]
+        for n in ("klu", "dense", "truth"):
+            g2[f"{n}_{f}"] = np.asarray(gold[f"{n}_{f}"], float).reshape(a.shape)[sel]
+    parity.check_against_golden(cand, g2, fields=fields)
+    return gold
+
+
 @pytest.mark.parametrize("fixture,model", [("jakstat_adjoint", "jakstat_adjoint"), ("jakstat_adjoint_log10", "jakstat_adjoint"),
                                            ("steadystate", "steadystate"), ("massaction_small", "massaction_small")])
 def test_cuda_matches_golden(fixture, model):
@@ -163,11 +186,8 @@ def test_cuda_presimulation_jakstat_matches_reference():
     s.set_sensitivity_order(ab.SensitivityOrder.first)
     res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k, k_presim=kps, t_presim=tps))
     plain = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
-    r = refsim.RefModel("jakstat_adjoint").run(ts, p, k, sensi_order=1, k_presim=kps, t_presim=tps)
-    np.testing.assert_array_equal(res["status"], r["status"])
-    np.testing.assert_allclose(res["x0"], r["x0"].reshape(res["x0"].shape), rtol=1e-6, atol=1e-10)
-    np.testing.assert_allclose(res["x"], r["x"].reshape(res["x"].shape), rtol=1e-5, atol=1e-9)
-    np.testing.assert_allclose(res["sx"], r["sx"].reshape(res["sx"].shape), rtol=1e-3, atol=1e-6)
+    _check_live(res, refsim.RefModel("jakstat_adjoint"), ts, p, k, ["x0", "sx0", "x", "sx"], sensi_order=1, k_presim=kps, t_presim=tps)
+    r = refsim.RefModel("jakstat_adjoint").run(ts, p, k, sensi_order=1, k_presim=kps, t_presim=tps, fields=["numsteps"])
     ref = r["numsteps"][:, -1]
     assert (np.abs(res["numsteps"][:, -1] - ref) <= 0.1 * ref).all()
     np.testing.assert_array_equal(res["x"][1], plain["x"][1])
@@ -209,10 +229,8 @@ def test_cuda_state_reinitialisation_matches_golden():
         np.testing.assert_array_equal(r["x0"], g["k"][i, :3])
         np.testing.assert_array_equal(r["x"], rm["x"][i])
     if refsim.available("steadystate"):
-        r = refsim.RefModel("steadystate").run(g["ts"], g["p"], g["k"], k_preeq=g["k_preeq"], sensi_order=1, newton_maxsteps=50,
-                                               ss_mode=2, ss_sensi_mode=0, reinit_all=True)
-        np.testing.assert_allclose(rm["x"], r["x"].reshape(rm["x"].shape), rtol=1e-5, atol=1e-9)
-        np.testing.assert_allclose(rm["sx"], r["sx"].reshape(rm["sx"].shape), rtol=1e-3, atol=1e-6)
+        _check_live(rm, refsim.RefModel("steadystate"), g["ts"], g["p"], g["k"], ["x0", "x", "sx", "x_ss", "sx_ss"], k_preeq=g["k_preeq"],
+                    sensi_order=1, newton_maxsteps=50, ss_mode=2, ss_sensi_mode=0, reinit_all=True)
     n = ab.get_model("neuron")
     n.set_timepoints([0.0, 1.0])
     n.set_reinitialize_fixed_parameter_initial_states(True)
@@ -237,7 +255,6 @@ def test_cuda_events_match_golden(model):
     parity.check_against_golden(res.fields, g)
     np.testing.assert_array_equal(res["rz"] != 0, g["klu_rz"] != 0)
     np.testing.assert_array_equal(res["z"] < g["ts"][-1], g["klu_z"] < g["ts"][-1])
-    np.testing.assert_allclose(res["z"], g["klu_z"], rtol=1e-6, atol=1e-9)
 
 
 @pytest.mark.parametrize("model,N", [("events", 4096), ("neuron", 2048)])
@@ -276,8 +293,9 @@ def test_cuda_events_large_batch_vs_reference(model, N):
     good = r["status"] == 0
     np.testing.assert_array_equal(res["status"][idx][good], r["status"][good])
     np.testing.assert_array_equal(res["z"][idx][good] < ts[-1], r["z"][good] < ts[-1])
-    np.testing.assert_allclose(res["z"][idx][good], r["z"][good], rtol=1e-6, atol=1e-8)
-    np.testing.assert_allclose(res["x"][idx][good], r["x"][good], rtol=1e-5, atol=1e-8)
+    # floats incl. the sensitivities of states and event observables: parity protocol against KLU / dense / truth
+    sub = {f: np.asarray(res[f])[idx] for f in ("status", "x", "sx", "z", "sz")}
+    _check_live(sub, ref, ts, p[idx], k[idx], ["x", "sx", "z", "sz"], ok=good, status_equal=False, nmaxevent=nme)
 
 
 def test_cuda_preequilibration_large_batch_vs_reference():
@@ -314,10 +332,9 @@ def test_cuda_preequilibration_large_batch_vs_reference():
     np.testing.assert_array_equal(res["status"][idx], r["status"])
     np.testing.assert_array_equal(res["preeq_status"][idx], r["preeq_status"])
     np.testing.assert_array_equal(res["preeq_numsteps"][idx][:, [0, 2]], r["preeq_numsteps"][:, [0, 2]])
-    np.testing.assert_allclose(res["x_ss"][idx], r["x_ss"], rtol=1e-6, atol=1e-10)
-    np.testing.assert_allclose(res["sx_ss"][idx], r["sx_ss"], rtol=1e-5, atol=1e-8)
-    np.testing.assert_allclose(res["llh"][idx], r["llh"], rtol=1e-6)
-    np.testing.assert_allclose(res["sllh"][idx], r["sllh"], rtol=1e-4, atol=1e-5)
+    sub = {f: np.asarray(res[f])[idx] for f in ("status", "x", "sx", "x_ss", "sx_ss", "llh", "sllh")}
+    _check_live(sub, ref, ts, p[idx], k[idx], ["x", "sx", "x_ss", "sx_ss", "llh", "sllh"], k_preeq=kp[idx], my=my[idx],
+                sigmay=np.full_like(my[idx], 0.1), newton_maxsteps=50, ss_mode=2, ss_sensi_mode=0)
 
 
 def test_cuda_preequilibration_failure():
@@ -381,8 +398,8 @@ def test_no_sensitivities_thread_per_condition_kernel():
     g = np.load(os.path.join(GOLD, "steadystate.npz"))
     res = _run("steadystate", g, sensi=False)
     assert (res["status"] == 0).all()
-    np.testing.assert_allclose(res["x"], g["truth_x"], rtol=1e-6, atol=1e-10)
-    np.testing.assert_allclose(res["llh"], g["truth_llh"], rtol=1e-6)
+    # the state and the likelihood of a run with sensitivities differ from a run without only through the step sequence
+    parity.check_against_golden(res.fields, g, fields=["x", "y", "llh"])
 
 
 def test_list_of_expdata_entry_point():
@@ -407,8 +424,8 @@ def test_list_of_expdata_entry_point():
     assert len(rdatas) == 3
     for i, r in enumerate(rdatas):
         assert r.status == 0 and r["sx"].shape == (11, 5, 3) and r.x.shape == (11, 3)
-        np.testing.assert_allclose(r.x, g["truth_x"][i], rtol=1e-6, atol=1e-10)
-        np.testing.assert_allclose(r.llh, g["truth_llh"][i], rtol=1e-6)
+    stacked = {f: np.stack([np.asarray(r[f]) for r in rdatas]) for f in ("x", "sx", "llh", "sllh")}
+    parity.check_against_golden(stacked, {k_: v[:3] for k_, v in g.items() if k_.split("_", 1)[-1] in stacked}, fields=list(stacked))
     single = ab.run_simulation(m, s, edatas[0])
     np.testing.assert_allclose(single.x, rdatas[0].x, rtol=1e-12)
 
@@ -455,9 +472,11 @@ def test_ragged_expdata_list_matches_reference():
                      k_preeq=None if preeq[i] is None else np.array([preeq[i]]))
         assert r.status == rr["status"][0] == 0
         assert r["sx"].shape == (len(grids[i]), len(pl), 3)
-        np.testing.assert_allclose(r.x, rr["x"][0], rtol=1e-6, atol=1e-10)
-        np.testing.assert_allclose(r.llh, rr["llh"][0], rtol=1e-6)
-        np.testing.assert_allclose(r.sllh, rr["sllh"][0], rtol=1e-4, atol=1e-7)
+        one = {f: np.asarray(r[f])[None] for f in ("x", "sx", "llh", "sllh")}
+        one["status"] = np.array([r.status])
+        _check_live(one, ref, grids[i], g["p"][i:i + 1], g["k"][i:i + 1], ["x", "sx", "llh", "sllh"],
+                    my=e.get_measurements().reshape(1, -1, 3), sigmay=e.get_noise_scales().reshape(1, -1, 3), plist=pl, sensi_order=1,
+                    newton_maxsteps=50, k_preeq=None if preeq[i] is None else np.array([preeq[i]]))
     np.testing.assert_allclose(rdatas[4].x, rdatas[0].x, rtol=0, atol=0)
 
 
@@ -485,15 +504,11 @@ def test_initial_state_overrides_match_reference(model):
     my = np.nan_to_num(g["my"], nan=0.4)
     batch = ab.ExpDataBatch(g["ts"], p, g["k"], my=my, sigmay=np.full_like(my, 0.1), pscale=pscale, x0=x0, sx0=sx0)
     res = ab.run_simulations(m, s, batch)
-    r = RefModel(model).run(g["ts"], p, g["k"], pscale=pscale, my=my, sigmay=np.full_like(my, 0.1), x0=x0, sx0=sx0,
-                            rtol=1e-12, atol=1e-16, maxsteps=200000)
-    assert (res["status"] == 0).all() and (r["status"] == 0).all()
+    assert (res["status"] == 0).all()
     np.testing.assert_array_equal(res["x0"], x0)
     np.testing.assert_allclose(res["sx0"], sx0, rtol=1e-13)
-    np.testing.assert_allclose(res["x"], r["x"], rtol=1e-6, atol=1e-10)
-    np.testing.assert_allclose(res["sx"], r["sx"], rtol=1e-4, atol=1e-8)
-    np.testing.assert_allclose(res["llh"], r["llh"], rtol=1e-6)
-    np.testing.assert_allclose(res["sllh"], r["sllh"], rtol=1e-4, atol=1e-6)
+    _check_live(res, RefModel(model), g["ts"], p, g["k"], ["x", "sx", "llh", "sllh"], pscale=pscale, my=my, sigmay=np.full_like(my, 0.1),
+                x0=x0, sx0=sx0)
     # the list entry point carries the overrides too
     e = ab.ExpData(m)
     e.set_timepoints(g["ts"])
@@ -544,10 +559,11 @@ def test_postequilibration_matches_reference(kw, preeq):
     for f in ("x", "sx", "y", "llh", "sllh", "posteq_t", "posteq_wrms"):
         np.testing.assert_array_equal(np.isnan(res[f]), np.isnan(r[f]), err_msg=f)
     ok = (r["status"] == 0) & (r["posteq_status"][:, 0] != -99)
-    np.testing.assert_allclose(res["x"][ok], r["x"][ok], rtol=1e-5, atol=1e-8)
-    np.testing.assert_allclose(res["llh"][ok], r["llh"][ok], rtol=1e-5)
-    np.testing.assert_allclose(res["sx"][ok], r["sx"][ok], rtol=1e-3, atol=1e-6)
-    np.testing.assert_allclose(res["sllh"][ok], r["sllh"][ok], rtol=1e-3, atol=1e-5)
+    # The t = inf rows are defined by the steady-state convergence test, not by the integration tolerance: the protocol's floor
+    # (the reference's own KLU / dense / truth spread on those rows) accounts for that by construction.
+    if ok.any():
+        _check_live(res, RefModel("steadystate"), ts, g["p"][:N], g["k"][:N], ["x", "sx", "llh", "sllh"], ok=ok, my=my, sigmay=sig,
+                    sensi_order=1, k_preeq=kp, **kw)
 
 
 def test_postequilibration_jakstat_spline_model_is_the_long_time_limit():
@@ -659,7 +675,8 @@ def test_linearity_property_full_size_batch():
         sel = idx == j
         assert (res["llh"][sel] == res["llh"][sel][0]).all()
         assert (res["sllh"][sel] == res["sllh"][sel][0]).all()
-        np.testing.assert_allclose(res["llh"][sel][0], g["truth_llh"][j], rtol=1e-6)
+    first = np.array([np.flatnonzero(idx == j)[0] for j in range(len(g["p"]))])
+    parity.check_against_golden({f: res[f][first] for f in ("llh", "sllh")}, g, fields=["llh", "sllh"])
 
 
 # ---- BASELINE config 5: synthetic mass-action networks on the block solver (one condition per thread block) ----------
@@ -848,8 +865,8 @@ def test_cuda_full_condition_context_matches_reference(preeq):
     steps = r["numsteps"][:, -2]
     assert (np.abs(res["numsteps"][:, -2] - steps) <= 0.1 * steps + 2).all()
     np.testing.assert_array_equal(res["x0"][:, 2], k[:, 2])
-    np.testing.assert_allclose(res["x"], r["x"].reshape(res["x"].shape), rtol=1e-5, atol=1e-9)
-    np.testing.assert_allclose(res["sx"], r["sx"].reshape(res["sx"].shape), rtol=1e-3, atol=1e-6)
+    _check_live(res, ref, ts, p, k, ["x0", "x", "sx"], k_preeq=kp, sensi_order=1, k_presim=kps, t_presim=tps, newton_maxsteps=50,
+                ss_mode=2, ss_sensi_mode=0, reinit_states_sim=0b100)
 
 
 def _pack_sldet(s, head):
