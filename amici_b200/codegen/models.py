@@ -113,8 +113,91 @@ def neuron() -> ModelSpec:
                      events=evs, event_observables=[EventObservable("z1", 0, t_sym)])
 
 
+# ---- the reference's closed-form event models (reference python/tests/test_events.py:40-746) --------------------------------------
+# Known-answer models: x(t) and (by central differences of the closed form) sx(t) are analytic.  The reference builds them from
+# SBML rate rules / events; here the same ODEs, triggers and assignments in SymPy.  All SBML parameters are free parameters
+# (initial values included), there are no fixed parameters.  A `piecewise(a, cond, b)` of the SBML model is written with the
+# Heaviside state of the event whose root is the condition (the reference importer does the same, cf. models/model_events_py).
+def _ev_model(name, states, params, nominal, xdot, x0, evs, heavisides=None) -> ModelSpec:
+    obs = [Observable(f"obs_{s}", s) for s in states]
+    return ModelSpec(name=name, states=states, params=params, fixed=[], xdot=xdot, x0=x0, observables=obs, p_nominal=nominal,
+                     k_nominal=[], events=evs, heavisides=heavisides)
+
+
+def ev_heavisides() -> ModelSpec:
+    """events_plus_heavisides (reference python/tests/test_events.py:116-262)"""
+    x1, x2, x3 = states = _syms("x_1 x_2 x_3")
+    k1, k2, k3, alpha, beta, gamma, delta, eta, zeta = params = _syms("k1 k2 k3 alpha beta gamma delta eta zeta")
+    h_delta, h_zeta = _syms("H_delta H_zeta")
+    t = t_sym
+    xdot = [-alpha * x1 * h_delta, beta * x1 - gamma * x2, -eta * x3 + h_zeta]
+    evs = [Event(k1 - x3, assignments={x1: x1 - x3 / 2}, initial_value=False), Event(t - zeta, assignments={x3: x3 + zeta / 3}, initial_value=False),
+           Event(t - delta, initial_value=False)]
+    return _ev_model("ev_heavisides", states, params, [2, 0.01, 5, 2, 3, 2, 3, 1, 5], xdot, [k1, k2, k3], evs, {h_delta: 2, h_zeta: 1})
+
+
+def ev_nested() -> ModelSpec:
+    """nested_events (reference python/tests/test_events.py:265-377): the second event is triggered by the first one's bolus"""
+    x1, x2 = states = _syms("x_1 x_2")
+    k1, k2, inflow_1, decay_1, decay_2, bolus = params = _syms("k1 k2 inflow_1 decay_1 decay_2 bolus")
+    t = t_sym
+    xdot = [inflow_1 - decay_1 * x1, -decay_2 * x2]
+    evs = [Event(x1 - inflow_1 / decay_2, assignments={x2: x2 - 1 / t}, initial_value=False),
+           Event(-sp.Rational(1, 2) - x2, assignments={x1: x1 + bolus, x2: x2 + bolus}, initial_value=False)]
+    return _ev_model("ev_nested", states, params, [0, 0, 4, 2, 5, 0], xdot, [k1, k2], evs)
+
+
+def ev_pw_simple() -> ModelSpec:
+    """piecewise_plus_event_simple_case (reference python/tests/test_events.py:380-450)"""
+    (x1,) = states = _syms("x_1")
+    alpha, beta, gamma, x_1_0 = params = _syms("alpha beta gamma x_1_0")
+    h_a, h_b = _syms("H_alpha H_beta")
+    t = t_sym
+    evs = [Event(t - alpha, assignments={x1: gamma}, initial_value=False), Event(t - beta, assignments={x1: x1 + sp.Float(2.5)}, initial_value=False)]
+    return _ev_model("ev_pw_simple", states, params, [2, 3, 4.5, 1], [h_a * (1 - h_b)], [x_1_0], evs, {h_a: 0, h_b: 1})
+
+
+def ev_ddeltax() -> ModelSpec:
+    """event_state_dep_ddeltax_dtpx (reference python/tests/test_events.py:453-535): boluses whose derivatives w.r.t. time,
+    parameters and states depend on the state"""
+    (x1,) = states = _syms("x_1")
+    alpha, beta, gamma, delta, x_1_0 = params = _syms("alpha beta gamma delta x_1_0")
+    t = t_sym
+    evs = [Event(t - alpha, assignments={x1: x1 * t}, initial_value=False), Event(t - beta, assignments={x1: x1 * delta}, initial_value=False),
+           Event(t - gamma, assignments={x1: 2 * x1 * x1}, initial_value=False)]
+    return _ev_model("ev_ddeltax", states, params, [1.5, 2.5, 3.5, 5.5, 1], [sp.Integer(1)], [x_1_0], evs)
+
+
+def ev_pw_semi() -> ModelSpec:
+    """piecewise_plus_event_semi_complicated (reference python/tests/test_events.py:538-620)"""
+    x1, x2 = states = _syms("x_1 x_2")
+    alpha, beta, gamma, x_1_0, x_2_0, delta, eta = params = _syms("alpha beta gamma x_1_0 x_2_0 delta eta")
+    h_a, h_b = _syms("H_alpha H_beta")
+    t = t_sym
+    inside = h_a * (1 - h_b)
+    xdot = [delta * x1 * inside - x1 * (1 - inside), -eta * x2]
+    evs = [Event(t - alpha / 2, assignments={x1: gamma}, initial_value=False), Event(t - beta, assignments={x1: x1 + x2}, initial_value=False),
+           Event(t - alpha, initial_value=False)]
+    return _ev_model("ev_pw_semi", states, params, [2, 3, 4.5, 1, 5, 2.5, 1.4], xdot, [x_1_0, x_2_0], evs, {h_a: 2, h_b: 1})
+
+
+def ev_pw_state() -> ModelSpec:
+    """piecewise_plus_event_trigger_depends_on_state (reference python/tests/test_events.py:623-706)"""
+    x1, x2 = states = _syms("x_1 x_2")
+    alpha, beta, gamma, x_1_0, x_2_0 = params = _syms("alpha beta gamma x_1_0 x_2_0")
+    h_a, h_b = _syms("H_alpha H_beta")
+    t = t_sym
+    evs = [Event(x1 - sp.Float(1.4), assignments={x1: x1 + gamma}, initial_value=False), Event(t - beta, assignments={x1: x1 + x2}, initial_value=False),
+           Event(t - alpha, initial_value=False)]
+    return _ev_model("ev_pw_state", states, params, [2, 3, 4.5, 1, 5], [h_a * (1 - h_b), -x2], [x_1_0, x_2_0], evs, {h_a: 2, h_b: 1})
+
+
+ANALYTIC = {"ev_heavisides": ev_heavisides, "ev_nested": ev_nested, "ev_pw_simple": ev_pw_simple, "ev_ddeltax": ev_ddeltax,
+            "ev_pw_semi": ev_pw_semi, "ev_pw_state": ev_pw_state}
+
+
 ALL = {"jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode,
-       "events": events, "neuron": neuron}
+       "events": events, "neuron": neuron, **ANALYTIC}
 
 
 def generate_all(out_dir: str | None = None) -> list[str]:

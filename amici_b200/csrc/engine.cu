@@ -75,6 +75,12 @@ static const ModelEntry* registry(int* count) {
         entry_neuron(),
         entry_massaction(),
         entry_massaction_small(),
+        entry_ev_heavisides(),
+        entry_ev_nested(),
+        entry_ev_pw_simple(),
+        entry_ev_ddeltax(),
+        entry_ev_pw_semi(),
+        entry_ev_pw_state(),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;

@@ -47,6 +47,13 @@ ModelEntry entry_events();
 ModelEntry entry_neuron();
 ModelEntry entry_massaction();
 ModelEntry entry_massaction_small();
+// closed-form event models of the reference's python/tests/test_events.py (known-answer tests)
+ModelEntry entry_ev_heavisides();
+ModelEntry entry_ev_nested();
+ModelEntry entry_ev_pw_simple();
+ModelEntry entry_ev_ddeltax();
+ModelEntry entry_ev_pw_semi();
+ModelEntry entry_ev_pw_state();
 
 }  // namespace amici_b200
 #endif

@@ -9,6 +9,12 @@
 #include "../../amici_b200/csrc/models/steadystate.cuh"
 #include "../../amici_b200/csrc/models/events.cuh"
 #include "../../amici_b200/csrc/models/neuron.cuh"
+#include "../../amici_b200/csrc/models/ev_heavisides.cuh"
+#include "../../amici_b200/csrc/models/ev_nested.cuh"
+#include "../../amici_b200/csrc/models/ev_pw_simple.cuh"
+#include "../../amici_b200/csrc/models/ev_ddeltax.cuh"
+#include "../../amici_b200/csrc/models/ev_pw_semi.cuh"
+#include "../../amici_b200/csrc/models/ev_pw_state.cuh"
 
 #include <memory>
 #include <string>
@@ -75,5 +81,11 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "robertson_ode") return run_model<models::robertson_ode>(o, b);
     if (m == "events") return run_model<models::events>(o, b);
     if (m == "neuron") return run_model<models::neuron>(o, b);
+    if (m == "ev_heavisides") return run_model<models::ev_heavisides>(o, b);
+    if (m == "ev_nested") return run_model<models::ev_nested>(o, b);
+    if (m == "ev_pw_simple") return run_model<models::ev_pw_simple>(o, b);
+    if (m == "ev_ddeltax") return run_model<models::ev_ddeltax>(o, b);
+    if (m == "ev_pw_semi") return run_model<models::ev_pw_semi>(o, b);
+    if (m == "ev_pw_state") return run_model<models::ev_pw_state>(o, b);
     return -2;
 }

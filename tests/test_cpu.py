@@ -481,3 +481,24 @@ def test_emulation_flat_compact_is_bit_identical(built, fixture, model):
         np.testing.assert_array_equal(outs[0][f], outs[1][f], err_msg=f)
     dup = (0, 2) if model == "jakstat_adjoint" else (0, 1)
     np.testing.assert_array_equal(outs[1]["sx"][:, :, dup[0]], outs[1]["sx"][:, :, dup[1]])
+
+
+@pytest.mark.parametrize("name", ["ev_heavisides", "ev_nested", "ev_pw_simple", "ev_ddeltax", "ev_pw_semi", "ev_pw_state"])
+def test_emulation_analytic_event_models(built, name):
+    """Known answers of the reference's own event tests (reference python/tests/test_events.py:40-746): six models with
+    closed-form x(t) — Heaviside switches, state- and time-triggered events, boluses that depend on time / parameters / the
+    state, an event triggered by another event's bolus — at the reference's solver tolerances and within the reference's
+    acceptance tolerances (python/tests/util.py:46-85: x to 5e-9 / 1e-10 relative, sx to 1e-7)."""
+    from tests import known_answers as ka
+    par, ts, _ = ka.EVENT_MODELS[name]
+    _, x, sx = ka.event_model_expectation(name)
+    p, k = np.array([list(par.values())], float), np.zeros((1, 0))
+    for mode in ("nosens", "fsa"):
+        tol = ka.EVENT_TOL[mode]
+        b, out, keep = _capi.make_batch(ka.EVENT_MODEL_DIMS[name], ts, p, k)
+        o = _capi.default_options(rtol=tol["solver"][0], atol=tol["solver"][1], sensi=int(mode == "fsa"))
+        assert _emul(built).emul_run(name.encode(), C.byref(o), C.byref(b)) == 0
+        assert out["status"][0] == 0
+        np.testing.assert_allclose(out["x"][0], x, rtol=tol["x"][0], atol=tol["x"][1])
+        if mode == "fsa":
+            np.testing.assert_allclose(out["sx"][0], sx, rtol=tol["sx"][0], atol=tol["sx"][1])

@@ -920,3 +920,37 @@ def test_cuda_stability_limit_detection_variants_agree():
     head = rng.integers(0, 5, n).astype(np.int32)
     codes = run(_pack_sldet(s, head), head, rng.integers(3, 6, n).astype(np.int32))
     assert len(set(np.unique(codes).tolist())) >= 6, np.unique(codes)
+
+
+@pytest.mark.parametrize("name", ["ev_heavisides", "ev_nested", "ev_pw_simple", "ev_ddeltax", "ev_pw_semi", "ev_pw_state"])
+def test_cuda_analytic_event_models(name):
+    """Known answers of the reference's own event tests (reference python/tests/test_events.py:40-746; closed forms restated
+    in tests/known_answers.py) through the C ABI, at the reference's solver tolerances and inside its acceptance tolerances
+    (python/tests/util.py:46-85).  Condition 0 is the reference's parameter vector; 63 more conditions perturb every parameter
+    by up to 5 % (the closed forms are parametric), so that event times, trigger order and boluses differ between the lanes
+    of a warp."""
+    import amici_b200 as ab
+    from tests import known_answers as ka
+    par, ts, _ = ka.EVENT_MODELS[name]
+    rng = np.random.default_rng(11)
+    names = list(par)
+    p0 = np.array(list(par.values()), float)
+    P = np.tile(p0, (64, 1))
+    P[1:] *= rng.uniform(0.95, 1.05, (63, len(p0)))
+    expect = [ka.event_model_expectation(name, dict(zip(names, row))) for row in P]
+    x = np.stack([e[1] for e in expect])
+    sx = np.stack([e[2] for e in expect])
+    m = ab.get_model(name)
+    m.set_timepoints(ts)
+    for mode in ("nosens", "fsa"):
+        tol = ka.EVENT_TOL[mode]
+        s = m.create_solver()
+        s.set_relative_tolerance(tol["solver"][0])
+        s.set_absolute_tolerance(tol["solver"][1])
+        if mode == "fsa":
+            s.set_sensitivity_order(ab.SensitivityOrder.first)
+        res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, P, np.zeros((64, 0))))
+        assert (res["status"] == 0).all()
+        np.testing.assert_allclose(res["x"], x, rtol=tol["x"][0], atol=tol["x"][1])
+        if mode == "fsa":
+            np.testing.assert_allclose(res["sx"], sx, rtol=tol["sx"][0], atol=tol["sx"][1])
