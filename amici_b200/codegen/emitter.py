@@ -45,6 +45,22 @@ class Spline:
     nodes: Sequence[float]
     values: Sequence[sp.Expr]
     logarithmic: bool = True
+    # the rest of the reference's HermiteSpline configuration (csrc/hermite_spline.cuh); defaults = the shipped models'
+    derivatives: Sequence[sp.Expr] | None = None      # node slopes; None: finite differences
+    bc: tuple = ("zeroDerivative", "zeroDerivative")   # given | zeroDerivative | natural | periodic
+    extrapolate: tuple = ("constant", "constant")      # noExtrapolation | constant | linear | polynomial | periodic
+    equidistant: bool = False                           # nodes = linspace(nodes[0], nodes[-1], len(values))
+
+    def is_default(self) -> bool:
+        return (self.derivatives is None and tuple(self.bc) == ("zeroDerivative", "zeroDerivative")
+                and tuple(self.extrapolate) == ("constant", "constant") and not self.equidistant)
+
+    def node_list(self) -> list:
+        if not self.equidistant:
+            return [float(v) for v in self.nodes]
+        n = len(self.values)
+        step = (float(self.nodes[-1]) - float(self.nodes[0])) / (n - 1)    # reference src/splinefunctions.cpp:40-51
+        return [float(self.nodes[0]) + i * step for i in range(n - 1)] + [float(self.nodes[-1])]
 
 
 @dataclasses.dataclass
@@ -276,7 +292,7 @@ def emit_model(spec: ModelSpec) -> str:
         e = sp.diff(expr, spec.params[ip])
         for i, s in enumerate(spl_syms):
             # d spl_i / d p_ip is supplied at run time (sspl[i]) for the lane's own parameter
-            if spec.splines[i] and any(sp.diff(v, spec.params[ip]) != 0 for v in spec.splines[i].values):
+            if spec.splines[i] and any(sp.diff(sp.sympify(v), spec.params[ip]) != 0 for v in list(spec.splines[i].values) + list(spec.splines[i].derivatives or [])):
                 e = e + sp.diff(expr, s) * sspl_syms[i]
         return sp.simplify(e) if e != 0 else e
 
@@ -286,7 +302,7 @@ def emit_model(spec: ModelSpec) -> str:
     A(f"// GENERATED by amici_b200/codegen/emitter.py from amici_b200/codegen/models.py::{spec.name} — do not edit.")
     A(f"// Device functions of model '{spec.name}' for the batched BDF engine (see emitter.py for the")
     A("// mapping onto the reference's generated <fn>_<model>.cpp files).")
-    A(f"#ifndef {guard}\n#define {guard}\n#include \"../model_common.cuh\"\nnamespace amici_b200 {{ namespace models {{\n")
+    A(f"#ifndef {guard}\n#define {guard}\n#include \"../hermite_spline.cuh\"\n#include \"../model_common.cuh\"\nnamespace amici_b200 {{ namespace models {{\n")
     A(f"struct {spec.name} {{")
     A(f"    static constexpr int NX = {nx}, NP = {npar}, NK = {nk}, NY = {ny}, NSPL = {nspl}, NE = {ne}, NH = {ne};")
     A(f"    static constexpr int NNZ_J = {nnz};")
@@ -295,6 +311,8 @@ def emit_model(spec: ModelSpec) -> str:
     nn_max = max([len(s.nodes) for s in spec.splines], default=1)
     A(f"    static constexpr int SPL_NN = {nn_max};  // nodes per spline")
     A(f"    static constexpr bool SPL_LOG = {'true' if all(s.logarithmic for s in spec.splines) else 'false'};")
+    spl_general = any(not s.is_default() for s in spec.splines) or len({bool(s.logarithmic) for s in spec.splines}) > 1
+    A(f"    static constexpr bool SPL_GENERAL = {'true' if spl_general else 'false'};   // any spline outside the default HermiteSpline configuration")
     A(f"    static const char* name() {{ return \"{spec.name}\"; }}")
     A("    static void nominal(double* p, double* k) {")
     for i, v in enumerate(spec.p_nominal):
@@ -323,7 +341,7 @@ def emit_model(spec: ModelSpec) -> str:
         for ip in range(npar):
             par = spec.params[ip]
             dyn = any(sp.diff(e, par) != 0 for e in xdot) or any(sp.diff(e, par) != 0 for e in x0) or \
-                any(sp.diff(sp.sympify(v), par) != 0 for spl in spec.splines for v in spl.values)
+                any(sp.diff(sp.sympify(v), par) != 0 for spl in spec.splines for v in list(spl.values) + list(spl.derivatives or []))
             if not dyn:
                 static_mask |= 1 << ip
     A(f"    static constexpr unsigned long long SX_STATIC_MASK = {static_mask:#x}ull;   // parameters with sx == 0 identically")
@@ -747,9 +765,38 @@ def emit_model(spec: ModelSpec) -> str:
         A("    // spline node data (reference create_splines_<model>.cpp / dspline_valuesdp_<model>.cpp)")
         A("    AB_HD static double spline_node(const int ispl, const int i) {")
         for i, s in enumerate(spec.splines):
-            arr = ", ".join(repr(float(v)) for v in s.nodes)
-            A(f"        {{ const double n{i}[{len(s.nodes)}] = {{{arr}}}; if (ispl == {i}) return n{i}[i]; }}")
+            arr = ", ".join(repr(float(v)) for v in s.node_list())
+            A(f"        {{ const double n{i}[{len(s.values)}] = {{{arr}}}; if (ispl == {i}) return n{i}[i]; }}")
         A("        return 0.0;\n    }")
+        BCV = {"given": -1, "zeroDerivative": 0, "natural": 1, "periodic": 3}
+        EPV = {"noExtrapolation": -1, "constant": 0, "linear": 1, "polynomial": 2, "periodic": 3}
+        A("    // HermiteSpline configuration per spline (reference create_splines_<model>.cpp constructor arguments)")
+        A("    AB_HD static constexpr int spline_n_nodes(const int ispl) { return " +
+          " : ".join(f"(ispl == {i}) ? {len(s.values)}" for i, s in enumerate(spec.splines)) + " : 2; }")
+        A("    AB_HD static constexpr SplineCfg spline_cfg(const int ispl) {")
+        A("        return " + " : ".join(
+            f"(ispl == {i}) ? SplineCfg{{{BCV[s.bc[0]]}, {BCV[s.bc[1]]}, {EPV[s.extrapolate[0]]}, {EPV[s.extrapolate[1]]}, "
+            f"{'true' if s.derivatives is None else 'false'}, {'true' if s.equidistant else 'false'}, {'true' if s.logarithmic else 'false'}}}"
+            for i, s in enumerate(spec.splines)) + " : spline_cfg_default(true);")
+        A("    }")
+        A("    AB_HD static void spline_slopes(const int ispl, const double* p, const double* k, double* m) {")
+        A("        (void)p; (void)k; (void)ispl; (void)m;")
+        for i, s in enumerate(spec.splines):
+            if s.derivatives is not None:
+                A(f"        if (ispl == {i}) {{")
+                A(W.body([(f"m[{j}]", sp.sympify(e)) for j, e in enumerate(s.derivatives)], indent="            ").rstrip("\n"))
+                A("        }")
+        A("    }")
+        A("    AB_HD static void spline_dslopesdp(const int ispl, const int ip, const double* p, const double* k, double* dm) {")
+        A("        (void)p; (void)k; (void)ip; (void)ispl; (void)dm;")
+        for i, s in enumerate(spec.splines):
+            if s.derivatives is not None:
+                A(f"        if (ispl == {i}) {{")
+                for j, e in enumerate(s.derivatives):
+                    cases = [(ip, W._pr(sp.diff(sp.sympify(e), spec.params[ip]))) for ip in range(npar) if sp.diff(sp.sympify(e), spec.params[ip]) != 0]
+                    A(f"            dm[{j}] = {_select_chain('ip', cases)};")
+                A("        }")
+        A("    }")
         A("    AB_HD static void spline_values(const int ispl, const double* p, const double* k, double* v) {")
         A("        (void)p; (void)k;")
         for i, s in enumerate(spec.splines):

@@ -192,12 +192,34 @@ def ev_pw_state() -> ModelSpec:
     return _ev_model("ev_pw_state", states, params, [2, 3, 4.5, 1, 5], [h_a * (1 - h_b), -x2], [x_1_0, x_2_0], evs, {h_a: 2, h_b: 1})
 
 
+def spline_modes() -> ModelSpec:
+    """Two forcing splines outside the default HermiteSpline configuration (csrc/hermite_spline.cuh, spline.cuh general path):
+    u1 — equidistant nodes, finite-difference slopes, `given` boundaries, linear extrapolation on both sides, logarithmic;
+    u2 — explicit nodes, slopes given as parameter expressions, periodic boundaries and periodic extrapolation, not logarithmic
+    (the reference's periodic extrapolation of a LOGARITHMIC spline exponentiates twice outside the node range — reproduced by
+    hermite_spline.cuh and covered by the random spline cases — which would put a jump into the forcing here).
+    The output grid starts before the first node and ends after the last one."""
+    x1, x2 = states = _syms("x1 x2")
+    kd, a0, a1, a2, a3, b0, b1, b2, d = params = _syms("kd a0 a1 a2 a3 b0 b1 b2 d")
+    (x10,) = fixed = _syms("x10")
+    u1, u2 = _syms("u1 u2")
+    xdot = [-kd * x1 + u1, -x2 + u2]
+    obs = [Observable("obs_x1", x1), Observable("obs_x2", x2), Observable("obs_u2", u2)]
+    return ModelSpec(
+        name="spline_modes", states=states, params=params, fixed=fixed, xdot=xdot, x0=[x10, sp.Integer(0)], observables=obs,
+        p_nominal=[0.7, 1.0, 2.5, 0.6, 1.4, 0.8, 2.0, 0.5, 0.3], k_nominal=[1.0],
+        splines=[Spline("u1", [1.0, 4.0], [a0, a1, a2, a3], logarithmic=True, bc=("given", "given"), extrapolate=("linear", "linear"),
+                        equidistant=True),
+                 Spline("u2", [0.5, 1.25, 2.75, 3.5], [b0, b1, b2, b0], logarithmic=False, derivatives=[d, -d, d / 2, d],
+                        bc=("periodic", "periodic"), extrapolate=("periodic", "periodic"))])
+
+
 ANALYTIC = {"ev_heavisides": ev_heavisides, "ev_nested": ev_nested, "ev_pw_simple": ev_pw_simple, "ev_ddeltax": ev_ddeltax,
             "ev_pw_semi": ev_pw_semi, "ev_pw_state": ev_pw_state}
 
 
 ALL = {"jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode,
-       "events": events, "neuron": neuron, **ANALYTIC}
+       "events": events, "neuron": neuron, **ANALYTIC, "spline_modes": spline_modes}
 
 
 def generate_all(out_dir: str | None = None) -> list[str]:

@@ -110,14 +110,14 @@ AB_HD void eval_splines(const typename Layout<M, G, C>::Shared& S, const Group<G
     for (int is = 0; is < M::NSPL; ++is) {
         const SplineLoc loc = spline_locate<M>(is, t);
         const double v = spline_eval_at<M, NCOLS>(S.spl, is, 0, loc, true);
-        e.spl[is] = M::SPL_LOG ? exp(v) : v;
+        e.spl[is] = spline_is_log<M>(is) ? exp(v) : v;
         AB_UNROLL
         for (int c = 0; c < C; ++c) {
             const int cc = g.lane + G * c;
             e.sspl[c][is] = 0.0;
             if (cc >= ncols || cc == 0) continue;
             const double s = spline_eval_at<M, NCOLS>(S.spl, is, cc, loc, false);
-            e.sspl[c][is] = M::SPL_LOG ? s * e.spl[is] : s;
+            e.sspl[c][is] = spline_is_log<M>(is) ? s * e.spl[is] : s;
         }
     }
 }
@@ -1995,7 +1995,7 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
         AB_UNROLL
         for (int is = 0; is < M::NSPL; ++is) {
             const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
-            spl[is] = M::SPL_LOG ? exp(v) : v;
+            spl[is] = spline_is_log<M>(is) ? exp(v) : v;
         }
         M::root(t, y, S.p, S.k, S.h, spl, rv);
         AB_UNROLL

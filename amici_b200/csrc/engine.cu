@@ -75,6 +75,7 @@ static const ModelEntry* registry(int* count) {
         entry_neuron(),
         entry_massaction(),
         entry_massaction_small(),
+        entry_spline_modes(),
         entry_ev_heavisides(),
         entry_ev_nested(),
         entry_ev_pw_simple(),

@@ -50,6 +50,7 @@ enum : int { AB_PSCALE_NONE = 0, AB_PSCALE_LN = 1, AB_PSCALE_LOG10 = 2 };
 
 #if !defined(__CUDACC__)
 using std::isfinite;
+using std::isinf;
 #endif
 
 // a / b for finite, normal, non-zero b: reciprocal seed + one Newton step, then the product — 4 instructions, relative

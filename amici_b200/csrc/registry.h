@@ -48,6 +48,7 @@ ModelEntry entry_neuron();
 ModelEntry entry_massaction();
 ModelEntry entry_massaction_small();
 // closed-form event models of the reference's python/tests/test_events.py (known-answer tests)
+ModelEntry entry_spline_modes();   // general HermiteSpline configurations
 ModelEntry entry_ev_heavisides();
 ModelEntry entry_ev_nested();
 ModelEntry entry_ev_pw_simple();

@@ -195,7 +195,7 @@ struct Simulation {
         for (int is = 0; is < M::NSPL; ++is) {
             loc[is] = spline_locate<M>(is, t);
             const double v = spline_eval_at<M, NCOLS>(S.spl, is, 0, loc[is], true);
-            spl[is] = M::SPL_LOG ? exp(v) : v;
+            spl[is] = spline_is_log<M>(is) ? exp(v) : v;
         }
         double y[NY], sig[NY], my[NY];
         bool my_set[NY], sig_set[NY];
@@ -250,7 +250,7 @@ struct Simulation {
                     sspl[is] = 0.0;
                     if (COMPACT && cc < 0) continue;
                     const double sv = spline_eval_at<M, NCOLS>(S.spl, is, cc, loc[is], false);
-                    sspl[is] = M::SPL_LOG ? sv * spl[is] : sv;
+                    sspl[is] = spline_is_log<M>(is) ? sv * spl[is] : sv;
                 }
                 M::sy(ip, t, xs, S.p, S.k, S.h, spl, sspl, sxv, sy);
                 M::ssigmay(ip, S.p, S.k, y, sy, ssig_tot);   // dsigmay/dp + dsigmay/dy * sy

@@ -34,7 +34,7 @@ AB_HD void spline_values_at(const typename Layout<M, G, C>::Shared& S, double t,
     AB_UNROLL
     for (int is = 0; is < M::NSPL; ++is) {
         const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
-        spl[is] = M::SPL_LOG ? exp(v) : v;
+        spl[is] = spline_is_log<M>(is) ? exp(v) : v;
     }
 }
 

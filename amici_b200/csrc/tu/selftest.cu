@@ -63,3 +63,68 @@ extern "C" int ab_selftest_sldet(int n, const double* ssdat, const int* head, co
     cudaFree(d_s); cudaFree(d_h); cudaFree(d_q); cudaFree(d_o);
     return AB_OK;
 }
+
+// ---- general Hermite spline (hermite_spline.cuh) on caller-supplied configurations ---------------------------------------
+#include "../hermite_spline.cuh"
+namespace amici_b200 {
+constexpr int ST_SPL_NN = 8, ST_SPL_NP = 4;
+
+__global__ void selftest_spline_kernel(int ncases, const int* cfg, const double* nodes, const double* values, const double* slopes, int npar,
+                                       const double* dvaluesdp, const double* dslopesdp, int nt, const double* ts, double* value_out,
+                                       double* sens_out, int* err_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncases) return;
+    const int* k = cfg + 8 * c;
+    const SplineCfg sc{k[1], k[2], k[3], k[4], k[5] != 0, k[6] != 0, k[7] != 0};
+    HermiteSplineData<ST_SPL_NN, ST_SPL_NP> H;
+    hs_build(H, sc, k[0], nodes + (size_t)c * ST_SPL_NN, values + (size_t)c * ST_SPL_NN, slopes + (size_t)c * ST_SPL_NN, npar,
+             dvaluesdp + (size_t)c * ST_SPL_NN * npar, dslopesdp + (size_t)c * ST_SPL_NN * npar);
+    for (int i = 0; i < nt; ++i) {
+        bool err = false;
+        const double t = ts[(size_t)c * nt + i];
+        value_out[(size_t)c * nt + i] = hs_value(H, t, &err);
+        for (int ip = 0; ip < npar; ++ip) sens_out[((size_t)c * nt + i) * npar + ip] = hs_sensitivity(H, t, ip, &err);
+        err_out[(size_t)c * nt + i] = err ? 1 : 0;
+    }
+}
+}  // namespace amici_b200
+
+extern "C" int ab_selftest_spline(int ncases, const int* cfg, const double* nodes, const double* values, const double* slopes, int npar,
+                                  const double* dvaluesdp, const double* dslopesdp, int nt, const double* ts, double* value_out,
+                                  double* sens_out, int* err_out) {
+    using namespace amici_b200;
+    if (ncases <= 0 || nt <= 0 || npar < 0 || npar > ST_SPL_NP || !cfg || !nodes || !values || !slopes || !ts || !value_out || !err_out)
+        return AB_E_BAD_ARGUMENT;
+    for (int c = 0; c < ncases; ++c)
+        if (cfg[8 * c] < 2 || cfg[8 * c] > ST_SPL_NN) return AB_E_BAD_ARGUMENT;
+    const size_t nn = (size_t)ncases * ST_SPL_NN, np = npar > 0 ? npar : 1;
+    int *d_cfg = nullptr, *d_err = nullptr;
+    double *d_x = nullptr, *d_v = nullptr, *d_m = nullptr, *d_dv = nullptr, *d_dm = nullptr, *d_t = nullptr, *d_val = nullptr, *d_s = nullptr;
+    AB_CUDA(cudaMalloc(&d_cfg, sizeof(int) * 8 * ncases));
+    AB_CUDA(cudaMalloc(&d_err, sizeof(int) * ncases * nt));
+    AB_CUDA(cudaMalloc(&d_x, sizeof(double) * nn));
+    AB_CUDA(cudaMalloc(&d_v, sizeof(double) * nn));
+    AB_CUDA(cudaMalloc(&d_m, sizeof(double) * nn));
+    AB_CUDA(cudaMalloc(&d_dv, sizeof(double) * nn * np));
+    AB_CUDA(cudaMalloc(&d_dm, sizeof(double) * nn * np));
+    AB_CUDA(cudaMalloc(&d_t, sizeof(double) * ncases * nt));
+    AB_CUDA(cudaMalloc(&d_val, sizeof(double) * ncases * nt));
+    AB_CUDA(cudaMalloc(&d_s, sizeof(double) * ncases * nt * np));
+    AB_CUDA(cudaMemcpy(d_cfg, cfg, sizeof(int) * 8 * ncases, cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemcpy(d_x, nodes, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemcpy(d_v, values, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemcpy(d_m, slopes, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    if (npar > 0) {
+        AB_CUDA(cudaMemcpy(d_dv, dvaluesdp, sizeof(double) * nn * npar, cudaMemcpyHostToDevice));
+        AB_CUDA(cudaMemcpy(d_dm, dslopesdp, sizeof(double) * nn * npar, cudaMemcpyHostToDevice));
+    }
+    AB_CUDA(cudaMemcpy(d_t, ts, sizeof(double) * ncases * nt, cudaMemcpyHostToDevice));
+    selftest_spline_kernel<<<(ncases + 63) / 64, 64>>>(ncases, d_cfg, d_x, d_v, d_m, npar, d_dv, d_dm, nt, d_t, d_val, d_s, d_err);
+    g_launches++;
+    AB_CUDA(cudaGetLastError());
+    AB_CUDA(cudaMemcpy(value_out, d_val, sizeof(double) * ncases * nt, cudaMemcpyDeviceToHost));
+    if (npar > 0 && sens_out) AB_CUDA(cudaMemcpy(sens_out, d_s, sizeof(double) * ncases * nt * npar, cudaMemcpyDeviceToHost));
+    AB_CUDA(cudaMemcpy(err_out, d_err, sizeof(int) * ncases * nt, cudaMemcpyDeviceToHost));
+    cudaFree(d_cfg); cudaFree(d_err); cudaFree(d_x); cudaFree(d_v); cudaFree(d_m); cudaFree(d_dv); cudaFree(d_dm); cudaFree(d_t); cudaFree(d_val); cudaFree(d_s);
+    return AB_OK;
+}

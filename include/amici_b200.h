@@ -184,6 +184,17 @@ long ab_kernel_launch_count(void);
  * memory in a 16-lane group, the same in a 4-lane group); all four must be equal. */
 int ab_selftest_sldet(int n, const double* ssdat, const int* head, const int* q, int* out);
 
+/* Self-test of the device Hermite spline (csrc/hermite_spline.cuh; replaces amici::HermiteSpline, reference
+ * include/amici/splinefunctions.h:219-424, src/splinefunctions.cpp) on caller-supplied splines, one per case:
+ * cfg[c][8] = {n_nodes (2..8), first / last SplineBoundaryCondition, first / last SplineExtrapolation (numeric values of
+ * reference include/amici/defines.h:249-264), node_derivative_by_FD, equidistant_spacing, logarithmic_parametrization};
+ * nodes / values / slopes [c][8] (equidistant: nodes[c][0..1] = first, last), dvaluesdp / dslopesdp [c][8][npar] (npar <= 4),
+ * ts[c][nt] (may contain +inf: the final value).  Out: value_out[c][nt] = get_value, sens_out[c][nt][npar] = get_sensitivity,
+ * err_out[c][nt] = 1 where the reference throws (evaluation outside the nodes without extrapolation; outputs NaN). */
+int ab_selftest_spline(int ncases, const int* cfg, const double* nodes, const double* values, const double* slopes, int npar,
+                       const double* dvaluesdp, const double* dslopesdp, int nt, const double* ts, double* value_out,
+                       double* sens_out, int* err_out);
+
 /* Last CUDA error string seen by the library on this thread ("" if none). */
 const char* ab_last_error(void);
 

@@ -208,3 +208,8 @@ for m in $MODELS; do
      "$OUT/libamici.a" "$OUT/libsundials.a" "$OUT/libsuitesparse.a" -ldl -lm
   echo "built $OUT/libref_$m.so"
 done
+
+# ---- the reference's HermiteSpline class behind a C entry point (oracle/ref_spline.cpp) ----------------------------
+g++ -std=c++20 $CFLAGS_COMMON $AMINC -shared -o "$OUT/libref_spline.so" "$HERE/ref_spline.cpp" "$OUT/libamici.a" "$OUT/libsundials.a" \
+   "$OUT/libsuitesparse.a" -ldl -lm
+echo "built $OUT/libref_spline.so"

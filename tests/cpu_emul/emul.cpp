@@ -9,6 +9,7 @@
 #include "../../amici_b200/csrc/models/steadystate.cuh"
 #include "../../amici_b200/csrc/models/events.cuh"
 #include "../../amici_b200/csrc/models/neuron.cuh"
+#include "../../amici_b200/csrc/models/spline_modes.cuh"
 #include "../../amici_b200/csrc/models/ev_heavisides.cuh"
 #include "../../amici_b200/csrc/models/ev_nested.cuh"
 #include "../../amici_b200/csrc/models/ev_pw_simple.cuh"
@@ -81,6 +82,7 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "robertson_ode") return run_model<models::robertson_ode>(o, b);
     if (m == "events") return run_model<models::events>(o, b);
     if (m == "neuron") return run_model<models::neuron>(o, b);
+    if (m == "spline_modes") return run_model<models::spline_modes>(o, b);
     if (m == "ev_heavisides") return run_model<models::ev_heavisides>(o, b);
     if (m == "ev_nested") return run_model<models::ev_nested>(o, b);
     if (m == "ev_pw_simple") return run_model<models::ev_pw_simple>(o, b);
@@ -88,4 +90,29 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "ev_pw_semi") return run_model<models::ev_pw_semi>(o, b);
     if (m == "ev_pw_state") return run_model<models::ev_pw_state>(o, b);
     return -2;
+}
+
+// host twin of ab_selftest_spline (include/amici_b200.h): the same hermite_spline.cuh functions, compiled for the host
+#include "../../amici_b200/csrc/hermite_spline.cuh"
+extern "C" int emul_selftest_spline(int ncases, const int* cfg, const double* nodes, const double* values, const double* slopes, int npar,
+                                    const double* dvaluesdp, const double* dslopesdp, int nt, const double* ts, double* value_out,
+                                    double* sens_out, int* err_out) {
+    using namespace amici_b200;
+    constexpr int NN = 8, NP = 4;
+    if (npar > NP) return -1;
+    for (int c = 0; c < ncases; ++c) {
+        const int* k = cfg + 8 * c;
+        const SplineCfg sc{k[1], k[2], k[3], k[4], k[5] != 0, k[6] != 0, k[7] != 0};
+        HermiteSplineData<NN, NP> H;
+        hs_build(H, sc, k[0], nodes + (size_t)c * NN, values + (size_t)c * NN, slopes + (size_t)c * NN, npar,
+                 dvaluesdp + (size_t)c * NN * npar, dslopesdp + (size_t)c * NN * npar);
+        for (int i = 0; i < nt; ++i) {
+            bool err = false;
+            const double t = ts[(size_t)c * nt + i];
+            value_out[(size_t)c * nt + i] = hs_value(H, t, &err);
+            for (int ip = 0; ip < npar; ++ip) sens_out[((size_t)c * nt + i) * npar + ip] = hs_sensitivity(H, t, ip, &err);
+            err_out[(size_t)c * nt + i] = err ? 1 : 0;
+        }
+    }
+    return 0;
 }

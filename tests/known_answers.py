@@ -147,3 +147,143 @@ def event_model_expectation(name, parameters=None):
 # tolerances of the reference's checks (python/tests/util.py:46-85)
 EVENT_TOL = dict(nosens=dict(solver=(1e-12, 1e-15), x=(5e-9, 1e-13)),
                  fsa=dict(solver=(1e-13, 1e-15), x=(1e-10, 1e-12), sx=(1e-7, 1e-9)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Hermite spline: tests/golden/spline_cases.npz (tests/golden/make_spline_cases.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+def check_spline_cases(golden_path, run):
+    """run(cfg, nodes, values, slopes, dv, dm, ts) -> (value[c][nt], sens[c][nt][4], err[c][nt]) is the implementation under test.
+    (1) every literal table of reference tests/cpp/unittests/testSplines.cpp:66-720 with the tolerance that test uses
+    (ASSERT_DOUBLE_EQ = 4 ulp), its ASSERT_THROW times and its final values / final sensitivities; the compiled reference's
+    own outputs stored next to them must pass the same check (pins the oracle wrapper and the parser).
+    (2) ~1300 random splines over every valid boundary condition x extrapolation x FD x equidistant x logarithmic
+    combination against the reference class, bit for bit (same operations in the same order), incl. where it throws."""
+    g = np.load(golden_path)
+    ulp4 = 4 * np.finfo(float).eps
+
+    def close(v, e, rt, at):
+        v, e = np.asarray(v, float), np.asarray(e, float)
+        if rt or at:
+            return bool((np.abs(v - e) <= at + rt * np.abs(e)).all())
+        return bool(((v == e) | (np.abs(v - e) <= ulp4 * np.maximum(np.abs(v), np.abs(e)))).all())
+
+    def check_literal(val, sens, err, who):
+        n_checked = 0
+        for i, name in enumerate(g["lit_names"]):
+            rt, at = g["lit_tol"][i]
+            for j in range(g["lit_ts"].shape[1]):
+                k = g["lit_kind"][i, j]
+                where = f"{who}: {name} t={g['lit_ts'][i, j]}"
+                if k == 1:
+                    assert close(val[i, j], g["lit_expect_v"][i, j], rt, at), (where, val[i, j], g["lit_expect_v"][i, j])
+                elif k == 2:
+                    e = g["lit_expect_s"][i, j]
+                    m = ~np.isnan(e)
+                    assert close(sens[i, j][m], e[m], rt, at), (where, sens[i, j], e)
+                elif k == 3:
+                    assert err[i, j] == 1 and np.isnan(val[i, j]), where
+                elif k in (4, 5):
+                    e = g["lit_expect_v"][i, j]
+                    if k == 4:
+                        assert (np.isnan(e) and np.isnan(val[i, j])) or close(val[i, j], e, 0, 0), (where, val[i, j], e)
+                    es = g["lit_expect_s"][i, j]
+                    m = ~np.isnan(es)
+                    assert close(sens[i, j][m], es[m], 0, 0), (where, sens[i, j], es)
+                else:
+                    continue
+                n_checked += 1
+        return n_checked
+
+    assert check_literal(g["lit_ref_v"], g["lit_ref_s"], g["lit_ref_thrown"], "compiled reference") > 150
+    val, sens, err = run(*(g["lit_" + k] for k in ("cfg", "nodes", "values", "slopes", "dv", "dm", "ts")))
+    check_literal(val, sens, err, "candidate")
+    np.testing.assert_array_equal(val, g["lit_ref_v"])     # also the rows the tables do not list (NaN == NaN)
+    np.testing.assert_array_equal(sens, g["lit_ref_s"])
+    val, sens, err = run(*(g["rnd_" + k] for k in ("cfg", "nodes", "values", "slopes", "dv", "dm", "ts")))
+    np.testing.assert_array_equal(err, g["rnd_ref_thrown"])
+    np.testing.assert_array_equal(val, g["rnd_ref_v"])
+    np.testing.assert_array_equal(sens, g["rnd_ref_s"])
+    return len(g["rnd_cfg"])
+
+
+def spline_runner(fn):
+    """adapts a C entry point with the signature of ab_selftest_spline (include/amici_b200.h) to check_spline_cases"""
+    import ctypes as C
+    fn.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4
+    fn.restype = C.c_int
+
+    def run(cfg, nodes, values, slopes, dv, dm, ts):
+        a = [np.ascontiguousarray(x) for x in (cfg, nodes, values, slopes, dv, dm, ts)]
+        n, nt = a[6].shape
+        val, sens, err = np.zeros((n, nt)), np.zeros((n, nt, 4)), np.zeros((n, nt), np.int32)
+        rc = fn(n, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, 4, a[4].ctypes.data, a[5].ctypes.data, nt,
+                a[6].ctypes.data, val.ctypes.data, sens.ctypes.data, err.ctypes.data)
+        assert rc == 0, rc
+        return val, sens, err
+    return run
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# model `spline_modes` (amici_b200/codegen/models.py): two forcing splines outside the default configuration
+# ---------------------------------------------------------------------------------------------------------------------------
+SPLINE_MODES_TS = np.linspace(0.0, 6.0, 25)      # starts before both splines' first node, ends after their last
+
+
+def spline_modes_expectation(spline_run, p, x10):
+    """x(t), sx(t) of  x1' = -kd x1 + u1(t), x2' = -x2 + u2(t)  by scipy (LSODA-free: explicit RK at 1e-13) with u1 / u2 and their
+    parameter sensitivities evaluated by `spline_run` (an implementation pinned against the reference class by
+    check_spline_cases).  p = (kd, a0..a3, b0, b1, b2, d)."""
+    from scipy.integrate import solve_ivp
+    kd, a, b, d = p[0], p[1:5], p[5:8], p[8]
+    cfg = np.array([[4, -1, -1, 1, 1, 1, 1, 1], [4, 3, 3, 3, 3, 0, 0, 0]], np.int32)
+    nodes = np.zeros((2, 8)); values = np.ones((2, 8)); slopes = np.zeros((2, 8))
+    nodes[0, :2] = [1.0, 4.0]
+    nodes[1, :4] = [0.5, 1.25, 2.75, 3.5]
+    values[0, :4] = a
+    values[1, :4] = [b[0], b[1], b[2], b[0]]
+    slopes[1, :4] = [d, -d, d / 2, d]
+    # the self-test interface carries 4 parameters per call: u1 w.r.t. a0..a3; u2 w.r.t. (b0, b1, b2, d)
+    dv, dm = np.zeros((2, 8, 4)), np.zeros((2, 8, 4))
+    dv[0, :4, :] = np.eye(4)
+    dv[1, 0, 0] = dv[1, 3, 0] = 1.0
+    dv[1, 1, 1] = dv[1, 2, 2] = 1.0
+    dm[1, :4, 3] = [1.0, -1.0, 0.5, 1.0]
+
+    def u(t):
+        val, sens, err = spline_run(cfg, nodes, values, slopes, dv, dm, np.full((2, 1), t))
+        assert not err.any()
+        return val[:, 0], sens[:, 0, :]
+
+    def rhs(t, z):     # z = x1, x2, then sx[ip][x] for the 9 parameters
+        val, sens = u(t)
+        x1, x2 = z[0], z[1]
+        s = z[2:].reshape(9, 2)
+        ds = np.zeros((9, 2))
+        du1 = np.zeros(9); du2 = np.zeros(9)
+        du1[1:5] = sens[0]
+        du2[5:8] = sens[1, :3]
+        du2[8] = sens[1, 3]
+        ds[:, 0] = -kd * s[:, 0] + du1
+        ds[0, 0] -= x1
+        ds[:, 1] = -s[:, 1] + du2
+        return np.concatenate([[-kd * x1 + val[0], -x2 + val[1]], ds.reshape(-1)])
+
+    z0 = np.zeros(20)
+    z0[0] = x10
+    # the splines are only C1 (C0 at the extrapolation joints): integrate piecewise between all nodes
+    breaks = sorted(set([0.0, 6.0, 1.0, 2.0, 3.0, 4.0, 0.5, 1.25, 2.75, 3.5] + [0.5 + 3.0 * k_ + off for k_ in (-1, 1) for off in (0.0, 0.75, 2.25)]))
+    breaks = [t for t in breaks if 0.0 <= t <= 6.0]
+    out_t, out_z = [0.0], [z0]
+    z = z0
+    for t0, t1 in zip(breaks[:-1], breaks[1:]):
+        te = [t for t in SPLINE_MODES_TS if t0 < t <= t1]
+        sol = solve_ivp(rhs, (t0, t1), z, method="DOP853", rtol=1e-12, atol=1e-14, t_eval=sorted(set(te + [t1])))
+        for t, col in zip(sol.t, sol.y.T):
+            if any(abs(t - q) < 1e-12 for q in SPLINE_MODES_TS) and t > out_t[-1] + 1e-12:
+                out_t.append(t); out_z.append(col)
+        z = sol.y[:, -1]
+    Z = np.array(out_z)
+    assert len(Z) == len(SPLINE_MODES_TS)
+    uvals = np.array([u(t)[0][1] for t in SPLINE_MODES_TS])
+    return Z[:, :2], Z[:, 2:].reshape(-1, 9, 2), uvals

@@ -502,3 +502,28 @@ def test_emulation_analytic_event_models(built, name):
         np.testing.assert_allclose(out["x"][0], x, rtol=tol["x"][0], atol=tol["x"][1])
         if mode == "fsa":
             np.testing.assert_allclose(out["sx"][0], sx, rtol=tol["sx"][0], atol=tol["sx"][1])
+
+
+def test_hermite_spline_known_answers_host(built):
+    """csrc/hermite_spline.cuh (host build) against the literal tables of the reference's spline unit tests and, bit for bit,
+    against the reference class on ~1300 random configurations (tests/known_answers.py::check_spline_cases)."""
+    from tests import known_answers as ka
+    n = ka.check_spline_cases(os.path.join(GOLD, "spline_cases.npz"), ka.spline_runner(_emul(built).emul_selftest_spline))
+    assert n > 1000
+
+
+def test_emulation_general_spline_model(built):
+    """A model with two forcing splines outside the default HermiteSpline configuration (equidistant + FD slopes + `given`
+    boundaries + linear extrapolation + logarithmic; explicit nodes + given slopes + periodic boundaries / extrapolation) through
+    the engine's general spline path (spline.cuh), against an independent integration (scipy DOP853 at 1e-12) whose forcing
+    is evaluated by the implementation that check_spline_cases pins to the reference class."""
+    from tests import known_answers as ka
+    lib = _emul(built)
+    p = np.array([0.7, 1.0, 2.5, 0.6, 1.4, 0.8, 2.0, 0.5, 0.3])
+    x, sx, u2 = ka.spline_modes_expectation(ka.spline_runner(lib.emul_selftest_spline), p, 1.0)
+    b, out, keep = _capi.make_batch(dict(nx=2, np=9, nk=1, ny=3), ka.SPLINE_MODES_TS, p[None], np.array([[1.0]]))
+    o = _capi.default_options(rtol=1e-10, atol=1e-12, sensi=1)
+    assert lib.emul_run(b"spline_modes", C.byref(o), C.byref(b)) == 0 and out["status"][0] == 0
+    np.testing.assert_allclose(out["y"][0][:, 2], u2, rtol=1e-14)
+    np.testing.assert_allclose(out["x"][0], x, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(out["sx"][0], sx, rtol=1e-7, atol=1e-9)

@@ -954,3 +954,50 @@ def test_cuda_analytic_event_models(name):
         np.testing.assert_allclose(res["x"], x, rtol=tol["x"][0], atol=tol["x"][1])
         if mode == "fsa":
             np.testing.assert_allclose(res["sx"], sx, rtol=tol["sx"][0], atol=tol["sx"][1])
+
+
+def test_cuda_hermite_spline_known_answers():
+    """The device Hermite spline (csrc/hermite_spline.cuh through ab_selftest_spline): every literal table of the reference's
+    tests/cpp/unittests/testSplines.cpp:66-720 and, bit for bit apart from FMA contraction, the reference class on ~1300
+    random splines covering every boundary condition / extrapolation / FD / equidistant / logarithmic combination."""
+    import amici_b200 as ab
+    from tests import known_answers as ka
+    g = np.load(os.path.join(GOLD, "spline_cases.npz"))
+    run = ka.spline_runner(ab.load_library().ab_selftest_spline)
+    # the device compiler contracts a*b+c into FMAs and has its own exp / log: literal tables with the tests' own tolerances,
+    # the random cases to a few ulp of the largest term instead of bit for bit
+    lit = run(*(g["lit_" + k] for k in ("cfg", "nodes", "values", "slopes", "dv", "dm", "ts")))
+    np.testing.assert_array_equal(lit[2], g["lit_ref_thrown"])
+    val, sens, err = run(*(g["rnd_" + k] for k in ("cfg", "nodes", "values", "slopes", "dv", "dm", "ts")))
+    np.testing.assert_array_equal(err, g["rnd_ref_thrown"])
+    for got, ref in ((lit[0], g["lit_ref_v"]), (lit[1], g["lit_ref_s"]), (val, g["rnd_ref_v"]), (sens, g["rnd_ref_s"])):
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+        np.testing.assert_array_equal(np.isinf(got), np.isinf(ref))
+        fin = np.isfinite(ref)
+        scale = np.maximum(np.abs(ref[fin]), 1.0)
+        assert (np.abs(got[fin] - ref[fin]) <= 1e-10 * scale).all(), np.abs(got[fin] - ref[fin]).max()
+        assert np.median(np.abs(got[fin] - ref[fin]) / scale) < 1e-15
+
+
+def test_cuda_general_spline_model():
+    """Model `spline_modes` (two splines outside the default HermiteSpline configuration, csrc/spline.cuh general path) through
+    the C ABI for four parameter vectors, against an independent integration whose forcing is the reference-pinned spline."""
+    import amici_b200 as ab
+    from tests import known_answers as ka
+    run = ka.spline_runner(ab.load_library().ab_selftest_spline)
+    rng = np.random.default_rng(3)
+    P = np.array([0.7, 1.0, 2.5, 0.6, 1.4, 0.8, 2.0, 0.5, 0.3]) * rng.uniform(0.8, 1.25, (4, 9))
+    K = np.array([[1.0], [0.5], [2.0], [0.0]])
+    m = ab.get_model("spline_modes")
+    m.set_timepoints(ka.SPLINE_MODES_TS)
+    s = m.create_solver()
+    s.set_relative_tolerance(1e-10)
+    s.set_absolute_tolerance(1e-12)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ka.SPLINE_MODES_TS, P, K))
+    assert (res["status"] == 0).all()
+    for i in range(4):
+        x, sx, u2 = ka.spline_modes_expectation(run, P[i], K[i, 0])
+        np.testing.assert_allclose(res["y"][i][:, 2], u2, rtol=1e-13)
+        np.testing.assert_allclose(res["x"][i], x, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(res["sx"][i], sx, rtol=1e-7, atol=1e-9)
