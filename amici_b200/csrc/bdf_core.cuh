@@ -1368,7 +1368,7 @@ struct BdfControl {
                     return AB_TSTOP_RETURN;
                 } else if ((tn + hprime - tstop) * h > 0.0) {
                     hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                    eta = hprime / h;   // IEEE: tn + h must land within 100 ulp of tstop (a 2^-40 quotient misses it whenever h > 0.02 |tn|: one extra step per output time)
+                    eta = fast_div_1ulp(hprime, h);   // tn + h * eta must land within 100 ulp of tstop: a 2^-40 quotient misses it whenever h > 0.02 |tn| (one extra step per output time)
                 }
             }
         }
@@ -1414,7 +1414,7 @@ struct BdfControl {
             if (at_tstop) return AB_ERROR;
             if ((tn + hprime - tstop) * h > 0.0) {
                 hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-                eta = hprime / h;   // IEEE: tn + h must land within 100 ulp of tstop (a 2^-40 quotient misses it whenever h > 0.02 |tn|: one extra step per output time)
+                eta = fast_div_1ulp(hprime, h);   // tn + h * eta must land within 100 ulp of tstop: a 2^-40 quotient misses it whenever h > 0.02 |tn| (one extra step per output time)
             }
             if constexpr (ROOTS) {
                 const int rc2 = self().rcheck2();
@@ -1430,7 +1430,7 @@ struct BdfControl {
             return AB_TSTOP_RETURN;
         } else if ((tn + hprime - tstop) * h > 0.0) {
             hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
-            eta = hprime / h;   // IEEE: tn + h must land within 100 ulp of tstop (a 2^-40 quotient misses it whenever h > 0.02 |tn|: one extra step per output time)
+            eta = fast_div_1ulp(hprime, h);   // tn + h * eta must land within 100 ulp of tstop: a 2^-40 quotient misses it whenever h > 0.02 |tn| (one extra step per output time)
         }
         return CONTINUE;
     }

@@ -70,6 +70,20 @@ AB_HD double fast_div(double a, double b) {
 #endif
 }
 
+// a / b to ~1 ulp: fast_div plus one residual correction (two more FMAs).  For the quotient that must reproduce its numerator when
+// multiplied back: eta = hprime / h at the tstop clipping, where tn + h * eta has to land within 100 ulp of tstop.
+AB_HD double fast_div_1ulp(double a, double b) {
+#if defined(__CUDA_ARCH__) && !defined(AB_EXACT_DIV)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(r, fma(-b, r, 1.0), r);
+    const double q = a * r;
+    return fma(fma(-q, b, a), r, q);
+#else
+    return a / b;
+#endif
+}
+
 // 1 / b for finite, normal, non-zero b (pivots of the emitted sparse LU): reciprocal seed + two Newton steps, within 1-2 ulp
 AB_HD double fast_rcp(double b) {
 #if defined(__CUDA_ARCH__) && !defined(AB_EXACT_DIV)

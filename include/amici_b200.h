@@ -157,6 +157,56 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
  * Solver/Model clone that run_simulations destroys after every condition, src/amici.cpp:241-242). */
 void ab_release_workspace(void);
 
+/* ---- list-of-conditions entry point: std::vector<ExpData*> as it is --------------------------------------------------
+ * One condition = one amici::ExpData (reference include/amici/edata.h:20, include/amici/simulation_parameters.h:120-215).
+ * A NULL pointer / zero count means "not set": the value of ab_model_state applies, exactly as ConditionContext does it
+ * (reference src/edata.cpp:409-581). */
+typedef struct ab_condition {
+    int none;                 /* 1: the ExpData pointer is NULL (simulate the model as it is); every other member is ignored */
+    int nt; const double* ts; /* ExpData::ts_                                                                              */
+    int nplist; const int* plist;   /* SimulationParameters::plist                                                          */
+    const int* pscale;        /* [np]  SimulationParameters::pscale; without `p` the model's parameters are re-scaled so that
+                                 their unscaled values stay (Model::set_parameter_scale, reference src/model.cpp:513-527)     */
+    const double* p;          /* [np]  free_parameters, on the scale pscale                                                */
+    const double* k;          /* [nk]  fixed_parameters                                                                    */
+    const double* k_preeq;    /* [nk]  fixed_parameters_pre_equilibration: pre-equilibrate                                 */
+    const double* k_presim;   /* [nk]  fixed_parameters_presimulation                                                      */
+    double t_presim;          /*       presimulate over [t_start - t_presim, t_start] if > 0                               */
+    double t_start;           /*       ExpData::t_start (replaces Model::t0 whenever an ExpData is given)                  */
+    const double* x0;         /* [nx]              */
+    const double* sx0;        /* [nplist][nx]      */
+    const double* my;         /* [nt][ny]   NaN = missing            */
+    const double* sigmay;     /* [nt][ny]   NaN = the model's sigma  */
+    const double* mz;         /* [nmaxevent][nz]   */
+    const double* sigmaz;     /* [nmaxevent][nz]   */
+    int reinit_all;           /* ExpData::reinitialize_fixed_parameter_initial_states                                      */
+    int n_reinit_sim; const int* reinit_sim;        /* reinitialization_state_idxs_sim    */
+    int n_reinit_presim; const int* reinit_presim;  /* reinitialization_state_idxs_presim */
+} ab_condition;
+
+/* The amici::Model settings a condition falls back to (Model::get_timepoints / get_parameter_list / get_parameter_scale /
+ * get_free_parameters / get_fixed_parameters / t0 / get_reinitialize_fixed_parameter_initial_states /
+ * get_reinitialization_state_idxs). */
+typedef struct ab_model_state {
+    int nt; const double* ts;
+    int nplist; const int* plist;
+    const int* pscale;        /* [np] */
+    const double* p;          /* [np] on the scale pscale */
+    const double* k;          /* [nk] */
+    double t0;
+    int reinit_all; int n_reinit; const int* reinit_idxs;
+} ab_model_state;
+
+/* Replacement for amici::run_simulations(solver, std::vector<ExpData*>, model, failfast, num_threads) (reference
+ * src/amici.cpp:220-264) on a list of n conditions: applies the ConditionContext rules, groups the conditions that can share
+ * a launch, runs ab_run_batch per group and writes every condition's results to ITS OWN buffers: outs[i] is an ab_batch whose
+ * OUTPUT pointers (N = 1 layouts: x[nt][nx], sx[nt][nplist][nx], ...) point into the caller's per-condition storage, e.g. the
+ * std::vector members of a ReturnData; its input members are ignored.  failfast != 0: conditions after the first failed one
+ * get status AMICI_NOT_RUN (-1001) and their buffers are not touched (single-thread semantics of the reference).
+ * opt->t0 / reinit_states_* / posteq are set per group by the call.  n_batches (may be NULL): number of launches. */
+int ab_run_conditions(const char* model, const ab_solver_options* opt, const ab_model_state* ms, int n, const ab_condition* conds,
+                      const ab_batch* outs, int failfast, int* n_batches);
+
 /* Solve a batch whose arrays are all DEVICE memory (ts/plist/pscale included), asynchronously on
  * `stream` (a cudaStream_t passed as void*). `work_counter` is one device int used as the
  * trajectory queue head; it is reset by the call. res/sres/FIM are zero-filled by the call. */

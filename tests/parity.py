@@ -43,8 +43,9 @@ def check_against_golden(cand: dict, gold, fields=None, factor=FACTOR, verbose=T
             continue
         klu, dense, truth = gold[f"klu_{f}"], gold[f"dense_{f}"], gold[f"truth_{f}"]
         scale_ref = truth
-        floor_truth = max(scaled_err(klu, truth, scale_ref), scaled_err(dense, truth, scale_ref))
-        floor_pair = scaled_err(dense, klu, scale_ref)
+        others = [dense] + [gold[k_] for k_ in (f"s{j}_{f}" for j in range(64)) if k_ in gold]   # reference_triple(spread_runs=...)
+        floor_truth = max(scaled_err(r, truth, scale_ref) for r in [klu] + others)
+        floor_pair = max(scaled_err(r, klu, scale_ref) for r in others)
         e_truth = scaled_err(cand[f], truth, scale_ref)
         e_klu = scaled_err(cand[f], klu, scale_ref)
         report[f] = dict(err_vs_truth=e_truth, ref_err_vs_truth=floor_truth, dev_vs_klu=e_klu, ref_dev=floor_pair)
@@ -67,11 +68,18 @@ def robertson_view(g, sensi):
     return v
 
 
-def reference_triple(ref, ts, p, k, fields, num_threads=1, truth=True, **kw):
+def reference_triple(ref, ts, p, k, fields, num_threads=1, truth=True, spread_runs=0, **kw):
     """Three runs of the compiled reference on the same inputs — KLU, dense, tight-tolerance truth — in the layout of a
-    golden fixture, so that a fresh batch is checked by the same protocol as the committed vectors (check_against_golden)."""
+    golden fixture, so that a fresh batch is checked by the same protocol as the committed vectors (check_against_golden).
+    spread_runs > 0 adds that many runs `s0`, `s1`, ... with immaterially perturbed tolerances (rtol x (1 + 1e-6 (j + 1)),
+    alternating linear solver): step sequences are chaotic w.r.t. such perturbations, so these sample the reference's own
+    error distribution — two runs on a handful of conditions underestimate its tail (sx error of 512 steadystate conditions:
+    median 2.4, p99 35, max 60 tolerances)."""
     out = {}
     runs = [("klu", dict(linsol=9)), ("dense", dict(linsol=1))]
+    base_rtol = kw.get("rtol", RTOL)
+    for j in range(spread_runs):
+        runs.append((f"s{j}", dict(linsol=9 if j % 2 else 1, rtol=base_rtol * (1.0 + 1e-6 * (j + 1)))))
     if truth:
         runs.append(("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=500000)))
     for name, extra in runs:

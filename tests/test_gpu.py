@@ -45,11 +45,16 @@ def _check_live(res, ref, ts, p, k, fields, ok=None, status_equal=True, **kw):
     inputs (KLU, dense, tight-tolerance truth) take the place of a committed fixture.  No ad-hoc tolerances: the candidate must
     be as close to the truth as the reference is, and as close to the KLU run as the dense run is (factor 4)."""
     fields = list(fields)
-    gold = parity.reference_triple(ref, ts, p, k, ["status"] + fields, num_threads=min(ref.max_threads(), 16), **kw)
+    n_cond = len(np.atleast_2d(p))
+    gold = parity.reference_triple(ref, ts, p, k, ["status"] + fields, num_threads=min(ref.max_threads(), 16),
+                                   spread_runs=0 if n_cond >= 64 else 8, **kw)
     st = np.asarray(res["status"])
     if status_equal:
         np.testing.assert_array_equal(st, gold["klu_status"], err_msg="status differs from the reference's")
     sel = (st == 0) & (gold["klu_status"] == 0) & (gold["dense_status"] == 0) & (gold["truth_status"] == 0)
+    for j in range(8):
+        if f"s{j}_status" in gold:
+            sel &= gold[f"s{j}_status"] == 0
     if ok is not None:
         sel &= ok
     assert sel.any()
@@ -57,9 +62,14 @@ def _check_live(res, ref, ts, p, k, fields, ok=None, status_equal=True, **kw):
     for f in fields:
         a = np.asarray(res[f], float)
         cand[f] = a[sel]
-        for n in ("klu", "dense", "truth"):
+        for n in ["klu", "dense", "truth"] + [f"s{j}" for j in range(8) if f"s{j}_{f}" in gold]:
             g2[f"{n}_{f}"] = np.asarray(gold[f"{n}_{f}"], float).reshape(a.shape)[sel]
-    parity.check_against_golden(cand, g2, fields=fields)
+    if sel.sum() >= 64:
+        # enough conditions to compare error DISTRIBUTIONS: two reference runs on a handful of conditions underestimate the tail of
+        # the reference's own error (a 512-condition sample of this kind: reference sx error median 2.4, p99 35, max 60 tolerances)
+        parity.check_distribution(cand, g2, fields)
+    else:
+        parity.check_against_golden(cand, g2, fields=fields)
     return gold
 
 
@@ -487,10 +497,12 @@ def test_initial_state_overrides_match_reference(model):
     from oracle.refsim import RefModel, available
     if not available(model):
         pytest.skip("oracle/_ref not built")
-    g = np.load(os.path.join(GOLD, model + ".npz"))
-    N, npar = g["p"].shape
-    nx = g["klu_x"].shape[-1]
+    g0 = np.load(os.path.join(GOLD, model + ".npz"))
+    N, npar = 256, g0["p"].shape[1]
+    nx = g0["klu_x"].shape[-1]
     rng = np.random.default_rng(8)
+    rep = rng.integers(0, len(g0["p"]), N)
+    g = dict(ts=g0["ts"], p=g0["p"][rep] * 10 ** rng.normal(0, 0.05, (N, npar)), k=g0["k"][rep], my=g0["my"][rep])
     x0 = rng.uniform(0.2, 1.2, (N, nx))
     sx0 = rng.normal(0, 0.2, (N, npar, nx))
     pscale = np.full(npar, 2, dtype=np.int32)
@@ -1001,3 +1013,91 @@ def test_cuda_general_spline_model():
         np.testing.assert_allclose(res["y"][i][:, 2], u2, rtol=1e-13)
         np.testing.assert_allclose(res["x"][i], x, rtol=1e-8, atol=1e-10)
         np.testing.assert_allclose(res["sx"][i], sx, rtol=1e-7, atol=1e-9)
+
+
+# ---- the compiled reference-side binding: amici::run_simulations_gpu (integration/amici_gpu.cpp) ---------------------------------
+_BINDING_FIELDS = ["status", "llh", "chi2", "sllh", "ts", "x", "sx", "y", "sy", "sigmay", "ssigmay", "res", "sres", "FIM", "x0", "sx0", "xdot", "J",
+                   "numsteps", "numrhsevals", "numerrtestfails", "numnonlinsolvconvfails", "order", "x_ss", "sx_ss", "preeq_status",
+                   "preeq_numsteps", "preeq_wrms", "preeq_t", "posteq_status", "posteq_numsteps", "posteq_wrms", "posteq_t", "z", "sz", "rz",
+                   "srz", "sigmaz", "n_messages", "nplist", "nt", "id"]
+
+
+def _binding_run(lib, which, n, seed, scenario, failfast=0, threads=8, linsol=0, rtol=1e-8, atol=1e-12):
+    import ctypes as C
+    lib.binding_run.restype = C.c_long
+    lib.binding_run.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_long,
+                                C.c_char_p, C.c_int]
+    out = np.zeros(4_000_000)
+    err = C.create_string_buffer(1024)
+    got = lib.binding_run(which, n, seed, scenario, failfast, threads, linsol, rtol, atol, out.ctypes.data, len(out), err, 1024)
+    assert got > 0, (got, err.value.decode())
+    res, pos = [], 0
+    for _ in range(n):
+        r = {}
+        for f in _BINDING_FIELDS:
+            cnt = int(out[pos])
+            r[f] = out[pos + 1:pos + 1 + cnt].copy()
+            pos += 1 + cnt
+        res.append(r)
+    assert pos == got
+    return res
+
+
+@pytest.mark.parametrize("model,scenario", [("jakstat_adjoint", 1), ("steadystate", 1), ("steadystate", 2)])
+def test_reference_side_binding_matches_run_simulations(model, scenario):
+    """north_star: "host code in AMICI's own C++ core ... calling CUDA through a thin C-ABI".  integration/amici_gpu.cpp is that
+    host code, compiled against the unmodified reference headers and linked with libamici: the SAME std::vector<ExpData*> — own
+    timepoints / plist / pscale (with and without parameters) / fixed parameters / x0 per condition, a NULL entry,
+    pre-equilibration + presimulation + re-initialisation — goes through amici::run_simulations (host) and
+    amici::run_simulations_gpu (C ABI -> B200), and every ReturnData field is compared: sizes and discrete fields exactly,
+    floats by the parity protocol against the reference's KLU / dense / perturbed-tolerance / truth runs."""
+    import ctypes as C
+    path = os.path.join(ROOT, "integration", "_build", f"libbinding_{model}.so")
+    if not os.path.exists(path):
+        pytest.skip("integration/_build not built")
+    import amici_b200 as ab
+    C.CDLL(ab.load_library()._name, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)
+    n, seed = 16, 7
+    gpu = _binding_run(lib, 1, n, seed, scenario)
+    runs = {"klu": _binding_run(lib, 0, n, seed, scenario, linsol=9), "dense": _binding_run(lib, 0, n, seed, scenario, linsol=1),
+            "truth": _binding_run(lib, 0, n, seed, scenario, linsol=9, rtol=1e-12, atol=1e-16)}
+    for j in range(6):
+        runs[f"s{j}"] = _binding_run(lib, 0, n, seed, scenario, linsol=9 if j % 2 else 1, rtol=1e-8 * (1 + 1e-6 * (j + 1)))
+    exact = ["status", "ts", "nplist", "nt", "id", "n_messages", "preeq_status", "posteq_status"]
+    floats = ["llh", "chi2", "sllh", "x", "sx", "y", "sy", "sigmay", "ssigmay", "res", "sres", "FIM", "x0", "sx0", "xdot", "J", "x_ss", "sx_ss"]
+    for i in range(n):
+        for f in _BINDING_FIELDS:
+            assert gpu[i][f].shape == runs["klu"][i][f].shape, (i, f)
+        for f in exact:
+            np.testing.assert_array_equal(gpu[i][f], runs["klu"][i][f], err_msg=f"condition {i}: {f}")
+        np.testing.assert_array_equal(gpu[i]["preeq_numsteps"][[0, 2]] if len(gpu[i]["preeq_numsteps"]) else [], 
+                                      runs["klu"][i]["preeq_numsteps"][[0, 2]] if len(gpu[i]["preeq_numsteps"]) else [])
+        ref_steps = runs["klu"][i]["numsteps"][-1]
+        assert abs(gpu[i]["numsteps"][-1] - ref_steps) <= 0.15 * ref_steps + 2
+        gold = {f"{k_}_{f}": v[i][f][None] for k_, v in runs.items() for f in floats}
+        parity.check_against_golden({f: gpu[i][f][None] for f in floats}, gold, fields=[f for f in floats if gpu[i][f].size], verbose=False)
+
+
+def test_reference_side_binding_failfast_and_messages():
+    """failfast and per-condition messages through the compiled binding (reference src/amici.cpp:246-260, :112-130): with a step
+    budget no condition can meet, the first condition fails with the reference's status and one message, and with failfast the
+    rest is returned as freshly constructed ReturnData with status AMICI_NOT_RUN (-1001) — field by field what the reference returns."""
+    import ctypes as C
+    path = os.path.join(ROOT, "integration", "_build", "libbinding_jakstat_adjoint.so")
+    if not os.path.exists(path):
+        pytest.skip("integration/_build not built")
+    import amici_b200 as ab
+    C.CDLL(ab.load_library()._name, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)
+    for failfast in (0, 1):
+        gpu = _binding_run(lib, 1, 6, 3, 3, failfast=failfast)
+        ref = _binding_run(lib, 0, 6, 3, 3, failfast=failfast, threads=1)
+        for i in range(6):
+            np.testing.assert_array_equal(gpu[i]["status"], ref[i]["status"], err_msg=f"failfast={failfast} condition {i}")
+            np.testing.assert_array_equal(gpu[i]["n_messages"], ref[i]["n_messages"])
+            for f in ("x", "sx", "llh", "sllh", "y", "res", "FIM"):
+                np.testing.assert_array_equal(np.isnan(gpu[i][f]), np.isnan(ref[i][f]), err_msg=f"{f} NaN pattern, condition {i}")
+                if failfast and i > 0:
+                    np.testing.assert_array_equal(gpu[i][f], ref[i][f])   # untouched constructor defaults
+        assert gpu[0]["status"][0] < 0 and (not failfast or all(g["status"][0] == -1001 for g in gpu[1:]))
