@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <mutex>
+#include <vector>
 
 #include "bdf_block.cuh"
 #include "registry.h"
@@ -44,16 +45,39 @@ __global__ void __launch_bounds__(NCP, AB_BLOCK_MINB) block_solve_kernel(const a
     }
 }
 
-// Per-process workspace of the block solver (one slice of BV_COUNT vectors per resident block), kept between launches.
+// Workspaces of the block solver (one slice of BV_COUNT vectors per resident block).  ab_solve_device is asynchronous on the
+// caller's stream, so two launches may be in flight at once (two DeviceBatch objects, two models): every launch takes its OWN
+// buffer from a pool and marks it busy with an event recorded behind its kernel; a buffer is handed out again only when that
+// event has completed, and nothing is freed while a kernel may still use it.
 struct BlockWorkspace {
-    std::mutex mu;
     double* dev = nullptr;
     size_t cap = 0;
     int device = -1;
+    cudaEvent_t busy = nullptr;
 };
-inline BlockWorkspace& block_workspace() {
-    static BlockWorkspace w;
-    return w;
+struct BlockWorkspacePool {
+    std::mutex mu;
+    std::vector<BlockWorkspace> items;
+};
+inline BlockWorkspacePool& block_pool() {
+    static BlockWorkspacePool p;
+    return p;
+}
+// returns the index of a free buffer of at least `need` bytes on device `dev` (allocating one if necessary), -1 on error
+inline int block_workspace_acquire(int dev, size_t need) {
+    BlockWorkspacePool& pool = block_pool();
+    std::lock_guard<std::mutex> lock(pool.mu);
+    for (size_t i = 0; i < pool.items.size(); ++i) {
+        BlockWorkspace& w = pool.items[i];
+        if (w.device == dev && w.cap >= need && cudaEventQuery(w.busy) == cudaSuccess) return (int)i;
+    }
+    BlockWorkspace w;
+    if (!cuda_ok(cudaMalloc((void**)&w.dev, need), "cudaMalloc (block workspace)")) return -1;
+    if (!cuda_ok(cudaEventCreateWithFlags(&w.busy, cudaEventDisableTiming), "cudaEventCreate")) return -1;
+    w.cap = need;
+    w.device = dev;
+    pool.items.push_back(w);
+    return (int)pool.items.size() - 1;
 }
 
 template <class M, int NCP>
@@ -72,20 +96,19 @@ int launch_block_variant(const ab_solver_options& o, const ab_batch& b, int* que
     long grid = (long)sms * per_sm;
     if (b.N < grid) grid = b.N;
     if (grid < 1) grid = 1;
-    BlockWorkspace& w = block_workspace();
-    std::lock_guard<std::mutex> lock(w.mu);
     const size_t need = (size_t)grid * BV_COUNT * M::NX * NCP * sizeof(double);
-    if (w.device != dev || need > w.cap) {
-        // a previous launch may still be using the old buffer: cudaFree synchronises with it
-        if (w.dev) cudaFree(w.dev);
-        w.dev = nullptr;
-        w.cap = 0;
-        AB_CUDA(cudaMalloc((void**)&w.dev, need));
-        w.cap = need;
-        w.device = dev;
+    const int slot = block_workspace_acquire(dev, need);
+    if (slot < 0) return AB_E_CUDA;
+    double* ws_dev;
+    cudaEvent_t ws_busy;
+    {
+        std::lock_guard<std::mutex> lock(block_pool().mu);
+        ws_dev = block_pool().items[slot].dev;
+        ws_busy = block_pool().items[slot].busy;
     }
     AB_CUDA(cudaMemsetAsync(queue_head, 0, sizeof(int), st));
-    kern<<<(unsigned)grid, NCP, smem, st>>>(o, b, queue_head, pg, w.dev);
+    kern<<<(unsigned)grid, NCP, smem, st>>>(o, b, queue_head, pg, ws_dev);
+    AB_CUDA(cudaEventRecord(ws_busy, st));   // the buffer is taken until this launch has finished
     g_launches++;
     last_kernel() = std::string("block_solve_kernel<") + M::name() + "," + std::to_string(NCP) + ">";
     AB_CUDA(cudaGetLastError());

@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
+#include <vector>
 #include <string>
 #include <thread>
 
@@ -152,10 +154,10 @@ int ab_get_dims(const char* model, ab_dims* out) {
 int ab_get_nominal(const char* model, double* p, double* k) {
     const ModelEntry* e = find_model(model);
     if (!e) return AB_E_UNKNOWN_MODEL;
-    double pt[512], kt[64];
-    e->nominal(pt, kt);
-    if (p) std::memcpy(p, pt, sizeof(double) * e->dims.np);
-    if (k) std::memcpy(k, kt, sizeof(double) * e->dims.nk);
+    std::vector<double> pt(e->dims.np + 1), kt(e->dims.nk + 1);
+    e->nominal(pt.data(), kt.data());
+    if (p) std::memcpy(p, pt.data(), sizeof(double) * e->dims.np);
+    if (k) std::memcpy(k, kt.data(), sizeof(double) * e->dims.nk);
     return AB_OK;
 }
 
@@ -172,6 +174,14 @@ int ab_solve_device(const char* model, const ab_solver_options* opt, const ab_ba
     if (b->res) AB_CUDA(cudaMemsetAsync(b->res, 0, sizeof(double) * N * nt * ny, st));
     if (b->sres && npl) AB_CUDA(cudaMemsetAsync(b->sres, 0, sizeof(double) * N * nt * ny * npl, st));
     if (b->FIM && npl) AB_CUDA(cudaMemsetAsync(b->FIM, 0, sizeof(double) * N * npl * npl, st));
+    // outputs that a failing condition does not write from the failing timepoint on keep the reference's default 0
+    // (ReturnData::invalidate touches only the fields it lists, src/rdata.cpp:684-735); callers re-use their output tensors
+    if (b->sigmay) AB_CUDA(cudaMemsetAsync(b->sigmay, 0, sizeof(double) * N * nt * ny, st));
+    if (b->ssigmay && npl) AB_CUDA(cudaMemsetAsync(b->ssigmay, 0, sizeof(double) * N * nt * ny * npl, st));
+    for (int* cnt : {b->numsteps, b->numrhsevals, b->numerrtestfails, b->numnonlinsolvconvfails, b->order})
+        if (cnt) AB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * N * nt, st));
+    for (int* st3 : {b->posteq_status, b->posteq_numsteps, b->preeq_status, b->preeq_numsteps})
+        if (st3) AB_CUDA(cudaMemsetAsync(st3, 0, sizeof(int) * N * 3, st));
     // event-observable slots that are never reached stay 0 as in the reference (src/rdata.cpp:160-165, :203-205)
     const size_t nzs = (size_t)e->dims.nz * (opt->nmaxevent > 0 ? opt->nmaxevent : 0) * N;
     if (nzs) {
@@ -282,7 +292,7 @@ struct Workspace {
         int d = 0;
         if (!cuda_ok(cudaGetDevice(&d), "cudaGetDevice")) return false;
         if (device == d) return true;
-        release();   // the caller switched devices: start over on the new one
+        release();   // first use on this device
         if (!cuda_ok(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
         if (!cuda_ok(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
         if (!cuda_ok(cudaEventCreate(&ev0), "cudaEventCreate") || !cuda_ok(cudaEventCreate(&ev1), "cudaEventCreate")) return false;
@@ -291,16 +301,32 @@ struct Workspace {
         return true;
     }
 };
-Workspace& workspace() {
-    static Workspace w;
+// One workspace per device: a process that drives several GPUs (one host thread each) neither serialises on a global
+// lock nor re-allocates when the current device changes.
+constexpr int WS_MAX_DEVICES = 64;
+Workspace* workspaces() {
+    static Workspace w[WS_MAX_DEVICES];
     return w;
+}
+Workspace* workspace_of_current_device() {
+    int d = 0;
+    if (!cuda_ok(cudaGetDevice(&d), "cudaGetDevice")) return nullptr;
+    if (d < 0 || d >= WS_MAX_DEVICES) { last_error() = "device index out of range"; return nullptr; }
+    return workspaces() + d;
 }
 }  // namespace
 
 void ab_release_workspace(void) {
-    Workspace& w = workspace();
-    std::lock_guard<std::mutex> lock(w.mu);
-    w.release();
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return;
+    for (int d = 0; d < WS_MAX_DEVICES; ++d) {
+        Workspace& w = workspaces()[d];
+        std::lock_guard<std::mutex> lock(w.mu);
+        if (w.device < 0) continue;
+        cudaSetDevice(w.device);
+        w.release();
+    }
+    cudaSetDevice(cur);
 }
 
 // One launch per super-batch (all inputs resident first), outputs streamed back while the kernel runs: the kernel raises
@@ -367,7 +393,9 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
     if (super < chunk) super = chunk;
     if (super > N) super = N;
 
-    Workspace& w = workspace();
+    Workspace* wp = workspace_of_current_device();
+    if (!wp) return AB_E_CUDA;
+    Workspace& w = *wp;
     std::lock_guard<std::mutex> lock(w.mu);
     if (!w.init()) return AB_E_CUDA;
     if (!w.reserve(S_TS, D * (nt ? nt : 1)) || !w.reserve(S_PLIST, I * (hb->nplist ? hb->nplist : 1)) ||
@@ -420,12 +448,16 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
         for (int c = 0; c < nchunks && !fail; ++c) {
             unsigned spins = 0;
             bool finished = false;
+            // A sub-batch takes tens of milliseconds: after a short spin the thread sleeps between polls instead of burning a
+            // host core per rank for the whole solve (the reference arm and other ranks' copies need those cores).
             while (!flags[c]) {
-                if ((++spins & 0x3ffu) == 0) {
+                ++spins;
+                if ((spins & 0x3fu) == 0) {
                     // the kernel ended (or died) without raising the flag: stop waiting; a clean end has set every flag
                     if (cudaEventQuery(w.ev1) != cudaErrorNotReady) { finished = true; break; }
                 }
-                std::this_thread::yield();
+                if (spins < 64) std::this_thread::yield();
+                else std::this_thread::sleep_for(std::chrono::microseconds(spins < 1024 ? 20 : 100));
             }
             if (finished && !flags[c]) {
                 if (!cuda_ok(cudaStreamSynchronize(w.compute), "solve kernel")) fail = true;

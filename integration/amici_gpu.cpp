@@ -170,7 +170,11 @@ std::vector<std::unique_ptr<ReturnData>> run_simulations_gpu(
         if (e) results[i]->id = e->id;
         bind_outputs(*results[i], preeq_st[i], posteq_st[i], outs[i]);
         if (!e) {
+            // no data: the reference computes no objective (ReturnData::process_simulation_objects only does so `if (edata)`,
+            // src/rdata.cpp:213-260): llh / chi2 / sllh / res / sres / FIM keep the constructor's values (NaN / 0)
             c.none = 1;
+            ab_batch& o = outs[i];
+            o.llh = o.chi2 = o.sllh = o.res = o.sres = o.FIM = nullptr;
             continue;
         }
         if (e->nytrue() != model.nytrue || e->nztrue() != model.nztrue)

@@ -15,6 +15,7 @@ def _flow(s, a, beta, gamma, eta, x):
     """exp(s A) x for A = [[a, 0, 0], [beta, -gamma, 0], [0, 0, -eta]] in closed form (the reference's test calls mpmath.expm,
     python/tests/test_events.py:742-748; the matrix is triangular, so the flow is elementary and exact)"""
     e1, e2, e3 = np.exp(a * s), np.exp(-gamma * s), np.exp(-eta * s)
+    x = np.asarray(x, np.longdouble)
     z = (a + gamma) * s   # (e1 - e2) / (a + gamma) = e2 * s * expm1(z) / z: no cancellation at the resonance a = -gamma (the nominal point)
     phi = e2 * s * (np.expm1(z) / z if z != 0.0 else 1.0)
     return np.array([x[0] * e1, x[1] * e2 + beta * x[0] * phi, x[2] * e3])
@@ -126,11 +127,15 @@ EVENT_MODEL_DIMS = {"ev_heavisides": dict(nx=3, np=9, nk=0, ny=3), "ev_nested": 
 
 
 def event_model_expectation(name, parameters=None):
-    """(ts, x[nt][nx], sx[nt][np][nx]) as the reference's test computes them (test_events.py:709-718)"""
+    """(ts, x[nt][nx], sx[nt][np][nx]) as the reference's test computes them (test_events.py:709-718): central differences of
+    the closed form with eps = 1e-6 — evaluated in extended precision here.  In double precision the difference quotient carries
+    |x| * 2^-53 / eps of round-off (3e-7 relative on ev_pw_semi's sx[x_1][x_2_0], measured against the exact derivative), which is
+    the size of the reference's own acceptance tolerance; the engine's error there is 4e-12."""
     par0, ts, fx = EVENT_MODELS[name]
-    par = dict(par0 if parameters is None else parameters)
+    par = {k_: np.longdouble(v) for k_, v in dict(par0 if parameters is None else parameters).items()}
+    ts = [np.longdouble(t) for t in np.asarray(ts, float)]
     x = np.array([fx(t, **par) for t in ts])
-    eps = 1e-6
+    eps = np.longdouble(1e-6)
     sx = []
     for t in ts:
         row = []
@@ -141,7 +146,7 @@ def event_model_expectation(name, parameters=None):
             pp[ip] -= 2 * eps
             row.append((up - np.array(fx(t, **pp))) / (2 * eps))
         sx.append(row)
-    return ts, x, np.array(sx)
+    return np.asarray(ts, float), np.asarray(x, float), np.asarray(sx, float)
 
 
 # tolerances of the reference's checks (python/tests/util.py:46-85)
