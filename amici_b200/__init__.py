@@ -327,8 +327,8 @@ class Solver:
     def get_sensitivity_method(self): return self._sensi_meth
     def set_internal_sensitivity_method(self, v):
         v = InternalSensitivityMethod(int(v))
-        if v != InternalSensitivityMethod.simultaneous:
-            raise RuntimeError("amici_b200: only InternalSensitivityMethod.simultaneous is implemented")
+        if v == InternalSensitivityMethod.staggered1:
+            raise RuntimeError("amici_b200: InternalSensitivityMethod.staggered1 is not implemented (simultaneous and staggered are)")
         self._ism = v
     def get_internal_sensitivity_method(self): return self._ism
     def set_max_steps(self, v):

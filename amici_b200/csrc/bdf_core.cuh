@@ -848,6 +848,7 @@ struct BdfControl {
     double tn, h, hscale, hprime, eta, etamax, etaq, etaqm1, etaqp1, hu;
     double tau[LMAX + 1], l[LMAX], tq[6];
     double rl1, gamma, gammap, gamrat, crate, delp, acnrm, saved_tq5;
+    double crateS, acnrmS;   // staggered corrector (D::STG): convergence rate and correction norm of the sensitivity solve
     double tstop, tretlast;
     int q, qprime, qwait, L, qu;
     int nst, nstlp, nstlj, nscon, nfe, netf, ncfn, nni, nsetups, nje;
@@ -860,6 +861,7 @@ struct BdfControl {
     // same pieces: solve_begin, step_pre, step_begin, attempt, step_finish, step_post.
     double st_saved_t, st_dsm;
     int st_ncf, st_nef, st_nflag, st_dq;
+    int st_ncfS, st_nefS;    // staggered corrector: failure counters of the sensitivity stage (the locals ncfS / nefS of cvStep)
     bool st_restore, st_resc, st_reload;
     int so_nstloc, so_mxstep, so_nst_saved;
     bool so_post, so_one_step;
@@ -1157,6 +1159,7 @@ struct BdfControl {
     AB_HD void step_begin() {
         st_saved_t = tn;
         st_ncf = st_nef = 0;
+        st_ncfS = st_nefS = 0;
         st_nflag = FIRST_CALL;
         st_dsm = 0.0;
         st_restore = st_resc = st_reload = false;
@@ -1212,20 +1215,28 @@ struct BdfControl {
             return CONTINUE;
         }
         st_dsm = acnrm * tq[2];  // cvDoErrorTest
-        if (st_dsm <= 1.0) return AB_SUCCESS;
-        st_nef++;
-        netf++;
+        if (st_dsm > 1.0) return error_test_failed(st_nef, st_dsm, true);
+        if constexpr (D::STG) {
+            if (o.ism == 2 && self().has_sens()) return staggered_stage();
+        }
+        return AB_SUCCESS;
+    }
+    // cvDoErrorTest (cvodes.c:7461) after a failed test: count, restore, shrink the step / lower the order / restart at order 1.
+    // `nef` is the failure counter of the stage (states, or sensitivities of the staggered corrector).
+    AB_HD int error_test_failed(int& nef, const double dsm, const bool count) {
+        nef++;
+        if (count) netf++;   // ReturnData reports the state stage's counter (CVodeGetNumErrTestFails)
         st_nflag = PREV_ERR_FAIL;
         st_restore = true;
-        if (st_nef == o.max_err_test_fails) {
+        if (nef == o.max_err_test_fails) {
             tn = st_saved_t;
             return AB_ERR_FAILURE;
         }
         etamax = 1.0;
-        if (st_nef <= 3) {  // MXNEF1
-            eta = 1.0 / (nth_root(6.0 * st_dsm, L) + 1e-6);
+        if (nef <= 3) {  // MXNEF1
+            eta = 1.0 / (nth_root(6.0 * dsm, L) + 1e-6);
             eta = ab_max(0.1, eta);
-            if (st_nef >= 2) eta = ab_min(eta, 0.2);
+            if (nef >= 2) eta = ab_min(eta, 0.2);
             st_resc = true;
         } else if (q > 1) {  // force an order reduction
             eta = 0.1;
@@ -1240,6 +1251,36 @@ struct BdfControl {
             st_reload = true;
         }
         return CONTINUE;
+    }
+    // The sensitivity stage of the STAGGERED corrector (cvStep, cvodes.c:5936-5990; cvStgrNls :7167-7210; cvodes_nls_stg.c): the
+    // states have converged and passed their error test; now the right-hand side is evaluated at the converged state, the
+    // sensitivities of all parameters are corrected together by their own Newton iteration (same linear system, no setup
+    // unless the iteration fails with stale Jacobian data), and they take their own error test with their own counters.
+    AB_HD int staggered_stage() {
+        st_ncf = st_nef = 0;   // "reset counters for states"
+        nfe++;
+        if (!self().stg_rhs_at_converged_state()) {
+            // a recoverable failure of f at the converged state: CVODES predicts again without restoring the history (:5950-5954)
+            st_nflag = PREV_CONV_FAIL;
+            return CONTINUE;
+        }
+        const int sflag = self().nls_stg();
+        if (sflag != AB_SUCCESS) {   // cvHandleNFlag with ncfS / ncfnS
+            st_ncfS++;
+            etamax = 1.0;
+            if (st_ncfS == o.max_conv_fails) {
+                tn = st_saved_t;
+                return (sflag == NLS_RHS_RECVR) ? AB_REPTD_SRHSFUNC_ERR : AB_CONV_FAILURE;
+            }
+            eta = 0.25;
+            st_nflag = PREV_CONV_FAIL;
+            st_restore = st_resc = true;
+            return CONTINUE;
+        }
+        const double dsmS = acnrmS * tq[2];   // errconS = TRUE in AMICI (reference src/solver.cpp:641-656)
+        if (dsmS > 1.0) return error_test_failed(st_nefS, dsmS, false);
+        if (dsmS > st_dsm) st_dsm = dsmS;     // cvPrepareNextStep sees the larger of the two
+        return AB_SUCCESS;
     }
     AB_HD void step_finish() {
         complete_step();
@@ -1283,6 +1324,7 @@ struct BdfControl {
         mirror_l();
         rl1 = gamma = gammap = gamrat = 1.0;
         crate = 1.0; delp = 0.0; acnrm = 0.0; saved_tq5 = 0.0;
+        crateS = 1.0; acnrmS = 0.0;
         etaq = etaqm1 = etaqp1 = 0.0;
         tstopset = false; tstop = 0.0; tretlast = t0;
         convfail = CONVFAIL_NONE; jcur = false;         reinit_pending = false;
@@ -1465,6 +1507,10 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
     static constexpr int NCOLS = Layout<M, G, C>::NCOLS;
     static constexpr bool ROOTS = M::NE_SOLVER > 0;   // the integrator tracks event triggers
     static constexpr bool EVENTS = M::NE > 0 || REINIT;   // AMICI re-initialises the solver after events
+    // The STAGGERED sensitivity corrector (InternalSensitivityMethod::staggered, reference include/amici/defines.h:181) is compiled
+    // into the full-featured kernel variant (pre-equilibration / presimulation) and into event models' kernels only, so that
+    // the headline kernel's step loop does not grow.
+    static constexpr bool STG = REINIT || M::NE > 0;
     using Shared = typename Layout<M, G, C>::Shared;
     using Eval = ModelEval<M, C>;
     using Base = BdfControl<Bdf<M, G, C, REINIT>, Shared>;
@@ -1479,6 +1525,7 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
 
     Group<G> g;
     int ncols;  // active columns: 1 + nplist (1 without sensitivities)
+    int col_lo = 0;   // first active column: 1 while the staggered corrector iterates on the sensitivities alone
 
     // per-lane column registers
     double acor[C][NX];
@@ -1696,7 +1743,11 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
     }
 
     AB_HD int col(int c) const { return g.lane + G * c; }
-    AB_HD bool active(int c) const { return col(c) < ncols; }
+    AB_HD bool active(int c) const {
+        if constexpr (STG) return col(c) < ncols && col(c) >= col_lo;
+        else return col(c) < ncols;
+    }
+    AB_HD bool has_sens() const { return ncols > 1; }
 
     // -----------------------------------------------------------------------------------------
     // norms
@@ -1820,6 +1871,7 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
         gamrat = 1.0;
         gammap = gamma;
         crate = 1.0;
+        Base::crateS = 1.0;
         nstlp = nst;
         if (!fin || !okf) return NLS_CONV_RECVR;  // recoverable setup failure
         return AB_SUCCESS;
@@ -1883,6 +1935,20 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
     // One residual site, one solve site.
     // -----------------------------------------------------------------------------------------
     AB_HD int nls(int nflag) {
+        if constexpr (STG) {
+            if (o.ism == 2 && ncols > 1) {
+                // staggered corrector: the states alone (cvNls with ism = CV_STAGGERED, cvodes_nls.c): the sensitivity columns sit
+                // this iteration out (they take part in the group's barriers and reductions as inactive columns)
+                const int ncols_all = ncols;
+                ncols = 1;
+                const int rc = nls_impl(nflag);
+                ncols = ncols_all;
+                return rc;
+            }
+        }
+        return nls_impl(nflag);
+    }
+    AB_HD int nls_impl(int nflag) {
         convfail = (nflag == FIRST_CALL || nflag == PREV_ERR_FAIL) ? CONVFAIL_NONE : CONVFAIL_OTHER;
         bool callSetup = (nflag == PREV_CONV_FAIL) || (nflag == PREV_ERR_FAIL) || (nst == 0) ||
                          (nst >= nstlp + 20) || (fabs(gamrat - 1.0) > 0.3);
@@ -1960,6 +2026,108 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
             }
             break;
         }
+        return ret;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // staggered corrector, sensitivity stage (BdfControl::staggered_stage)
+    // -----------------------------------------------------------------------------------------
+    // f(tn, y) at the converged state (cvodes.c:5944-5954); the Jacobian of the sensitivity right-hand sides is evaluated from
+    // the same state inside model_rhs, so only the finiteness of f is of interest here
+    AB_HD bool stg_rhs_at_converged_state() {
+        const int ncols_all = ncols;
+        ncols = 1;
+        Eval e;
+        double ycur[C][NX], f[C][NX];
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) ycur[c][r] = active(c) ? S.zn[0][r][col(c)] + acor[c][r] : 0.0;
+        }
+        const bool ok = model_rhs<M, G, C>(S, g, ncols, tn, ycur, f, e);
+        ncols = ncols_all;
+        return ok;
+    }
+    // cvStgrNls (cvodes.c:7167-7210) + SUNNonlinSolSolve_Newton with cvNlsResidualSensStg / cvNlsLSolveSensStg /
+    // cvNlsConvTestSensStg (cvodes_nls_stg.c:276-405): Newton on the sensitivity columns with the converged state held fixed.
+    // No linear-solver setup on entry; one after a recoverable failure with stale Jacobian data (cvNlsLSetupSensStg).  At most
+    // NLS_MAXCOR = 3 iterations (CVodeSetMaxNonlinIters only reaches the state solver).
+    AB_HD int nls_stg() {
+        col_lo = 1;
+        AB_UNROLL
+        for (int c = 0; c < C; ++c) {
+            if (!active(c)) continue;
+            AB_UNROLL
+            for (int r = 0; r < NX; ++r) acor[c][r] = 0.0;
+        }
+        bool callSetup = false, jbad = false, jcur_stg = false;
+        int ret = AB_SUCCESS;
+        Eval e;
+        double delta[C][NX];
+        for (;;) {
+            int m = 0;
+            for (;;) {
+                {
+                    double ycur[C][NX];   // all columns: the state column carries the converged state
+                    AB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r) ycur[c][r] = (col(c) < ncols) ? S.zn[0][r][col(c)] + acor[c][r] : 0.0;
+                    }
+                    const bool ok = model_rhs<M, G, C>(S, g, ncols, tn, ycur, delta, e, m > 0);
+                    if (!ok) { ret = NLS_RHS_RECVR; break; }
+                }
+                if (m == 0 && callSetup) {
+                    ret = lsetup(jbad, e);   // cvNlsLSetupSensStg: convfail = CV_FAIL_BAD_J, Jacobian data from the converged state
+                    jcur_stg = jcur;
+                    if (ret != AB_SUCCESS) break;
+                }
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r)
+                        delta[c][r] = -(rl1 * S.zn[1][r][col(c)] + acor[c][r] - gamma * delta[c][r]);
+                }
+                lu_solve(delta);
+                const double sc = (gamrat != 1.0) ? fast_div(2.0, 1.0 + gamrat) : 1.0;
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) {
+                        if (gamrat != 1.0) delta[c][r] *= sc;
+                        acor[c][r] += delta[c][r];
+                    }
+                }
+                const double Del = wrms_max(delta);
+                if (m > 0) Base::crateS = ab_max(0.3 * Base::crateS, fast_div(Del, delp));
+                const double dcon = fast_div(Del * ab_min(1.0, Base::crateS), tq[4]);
+                if (dcon <= 1.0) {
+                    Base::acnrmS = (m == 0) ? Del : wrms_max(acor);
+                    jcur = false;
+                    col_lo = 0;
+                    return AB_SUCCESS;
+                }
+                if (!(Del == Del) || (m >= 1 && Del > 2.0 * delp)) { ret = NLS_CONV_RECVR; break; }
+                delp = Del;
+                m++;
+                if (m >= 3) { ret = NLS_CONV_RECVR; break; }
+            }
+            if (ret > 0 && !jcur_stg) {
+                callSetup = true;
+                jbad = true;
+                AB_UNROLL
+                for (int c = 0; c < C; ++c) {
+                    if (!active(c)) continue;
+                    AB_UNROLL
+                    for (int r = 0; r < NX; ++r) acor[c][r] = 0.0;
+                }
+                continue;
+            }
+            break;
+        }
+        col_lo = 0;
         return ret;
     }
 

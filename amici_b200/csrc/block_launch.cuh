@@ -122,6 +122,10 @@ int launch_block_model(const ab_solver_options& o, const ab_batch& b, int* queue
         return AB_E_UNSUPPORTED;
     }
     const int npl = (o.sensi >= 1) ? b.nplist : 0;
+    if (npl > 0 && o.ism != 1) {
+        last_error() = "block-solver models implement the simultaneous corrector only";
+        return AB_E_UNSUPPORTED;
+    }
     if (npl > M::NP) {
         last_error() = "nplist exceeds the number of model parameters";
         return AB_E_UNSUPPORTED;

@@ -105,7 +105,10 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
     if (!b->p || !b->status) { g_err = "p/status is NULL"; return AB_E_BAD_ARGUMENT; }
     if (!std::isfinite(o->t0)) { g_err = "t0 must be finite"; return AB_E_BAD_ARGUMENT; }
     if (o->sensi >= 1 && b->nplist > 0 && !b->plist) { g_err = "plist is NULL"; return AB_E_BAD_ARGUMENT; }
-    if (o->sensi >= 1 && o->ism != 1) { g_err = "only simultaneous forward sensitivities are implemented"; return AB_E_UNSUPPORTED; }
+    if (o->sensi >= 1 && o->ism != 1 && o->ism != 2) {
+        g_err = "InternalSensitivityMethod must be simultaneous (1) or staggered (2); staggered1 is not implemented";
+        return AB_E_UNSUPPORTED;
+    }
     if (!(o->rtol >= 0) || !(o->atol >= 0)) { g_err = "negative tolerance"; return AB_E_BAD_ARGUMENT; }
     if (o->nmaxevent < 0) { g_err = "nmaxevent must be non-negative"; return AB_E_BAD_ARGUMENT; }
     if (b->k_presim && !b->t_presim) { g_err = "k_presim without t_presim"; return AB_E_BAD_ARGUMENT; }

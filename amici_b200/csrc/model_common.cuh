@@ -36,6 +36,7 @@ enum : int {
     AB_REPTD_RHSFUNC_ERR = -10,
     AB_UNREC_RHSFUNC_ERR = -11,
     AB_ILL_INPUT = -22,
+    AB_REPTD_SRHSFUNC_ERR = -43,   // CV_REPTD_SRHSFUNC_ERR (staggered corrector)
     AB_TOO_CLOSE = -27,
     AB_NO_STEADY_STATE = -81,
     AB_DAMPING_FACTOR_ERROR = -86,

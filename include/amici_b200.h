@@ -35,7 +35,7 @@ typedef struct ab_solver_options {
     double t0;                 /* Model::set_t0                                                      */
     double hmax_inv;           /* 1 / Solver::set_max_step_size, 0 = unbounded                       */
     int sensi;                 /* SensitivityOrder: 0 none, 1 first (forward)                        */
-    int ism;                   /* InternalSensitivityMethod: 1 simultaneous                          */
+    int ism;                   /* InternalSensitivityMethod: 1 simultaneous, 2 staggered (lane-group models) */
     int maxsteps;              /* Solver::set_max_steps (budget for the whole simulation)            */
     int stldet;                /* Solver::set_stability_limit_flag                                   */
     int max_nonlin_iters;      /* Solver::set_max_nonlin_iters (3)                                   */

@@ -527,3 +527,39 @@ def test_emulation_general_spline_model(built):
     np.testing.assert_allclose(out["y"][0][:, 2], u2, rtol=1e-14)
     np.testing.assert_allclose(out["x"][0], x, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(out["sx"][0], sx, rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("model", ["jakstat_adjoint", "steadystate", "robertson_ode", "events", "neuron"])
+def test_emulation_staggered_corrector_matches_reference(built, model):
+    """InternalSensitivityMethod::staggered (reference include/amici/defines.h:181; CVODES cvStep :5936-5990, cvStgrNls,
+    cvodes_nls_stg.c): states first (own Newton iteration, own error test), then all sensitivities together with the converged
+    state held fixed.  Against the compiled reference run with ism = 2: status, the solver counters the reference reports (the
+    staggered corrector has a signature — one extra right-hand side per step and almost no error-test failures, because the
+    sensitivities no longer take part in the state's test) and x / sx by the parity protocol."""
+    from oracle.refsim import RefModel, available
+    if not available(model):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, model + ".npz"))
+    kw = {} if model == "robertson_ode" else dict(my=g["my"], sigmay=g["sigmay_in"])
+    nme = int(g["opt_nmaxevent"]) if "opt_nmaxevent" in g else 10
+    rkw = dict(kw, nmaxevent=nme) if "opt_nmaxevent" in g else dict(kw)
+    counters = ["numsteps", "numrhsevals", "numerrtestfails", "numnonlinsolvconvfails"]
+    fields = ["status", "x", "sx"] + counters + (["llh", "sllh"] if kw else [])
+    ref = RefModel(model)
+    gold = parity.reference_triple(ref, g["ts"], g["p"], g["k"], fields, num_threads=min(ref.max_threads(), 8), ism=2, spread_runs=4, **rkw)
+    sim = ref.run(g["ts"], g["p"], g["k"], fields=counters, num_threads=min(ref.max_threads(), 8), ism=1, **rkw)
+    b, out, keep = _capi.make_batch(MODEL_DIMS[model], g["ts"], g["p"], g["k"], nmaxevent=nme, **kw)
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1, ism=2, nmaxevent=nme)
+    assert _emul(built).emul_run(model.encode(), C.byref(o), C.byref(b)) == 0
+    np.testing.assert_array_equal(out["status"], gold["klu_status"])
+    ok = (out["status"] == 0) & (gold["dense_status"] == 0) & (gold["truth_status"] == 0)
+    for cnt in ("numsteps", "numrhsevals"):
+        e_, r_ = out[cnt][ok][:, -1].mean(), gold["klu_" + cnt][ok][:, -1].mean()
+        assert abs(e_ / r_ - 1) < 0.03, (cnt, e_, r_)
+    # the signature of the staggered corrector, relative to the simultaneous one on the same inputs
+    assert out["numrhsevals"][ok][:, -1].mean() > 1.5 * sim["numrhsevals"][ok][:, -1].mean()
+    assert out["numerrtestfails"][ok][:, -1].mean() < 0.75 * sim["numerrtestfails"][ok][:, -1].mean() + 1
+    assert abs(out["numerrtestfails"][ok][:, -1].mean() - gold["klu_numerrtestfails"][ok][:, -1].mean()) <= 0.25 * gold["klu_numerrtestfails"][ok][:, -1].mean() + 2
+    fl = ["x", "sx"] + (["llh", "sllh"] if kw else [])
+    sel = {k_: v[ok] for k_, v in gold.items() if k_.split("_", 1)[1] in fl}
+    parity.check_against_golden({f: out[f][ok] for f in fl}, sel, fields=fl)

@@ -1101,3 +1101,39 @@ def test_reference_side_binding_failfast_and_messages():
                 if failfast and i > 0:
                     np.testing.assert_array_equal(gpu[i][f], ref[i][f])   # untouched constructor defaults
         assert gpu[0]["status"][0] < 0 and (not failfast or all(g["status"][0] == -1001 for g in gpu[1:]))
+
+
+@pytest.mark.parametrize("model", ["jakstat_adjoint", "steadystate", "events", "neuron"])
+def test_cuda_staggered_corrector_matches_reference(model):
+    """InternalSensitivityMethod.staggered through the C ABI (ab_solver_options.ism = 2) on 256 seeded conditions per model against
+    the compiled reference run with the staggered corrector: status codes, the counters' signature, floats by the parity protocol
+    on distributions."""
+    import amici_b200 as ab
+    import bench
+    from oracle import refsim
+    name = {"jakstat_adjoint": "jakstat", "steadystate": "steadystate", "events": "events", "neuron": "neuron"}[model]
+    c = dict(bench.CONFIGS[name])
+    c.pop("preeq", None)
+    if not refsim.available(c["ref"]):
+        pytest.skip("oracle/_ref not built")
+    N = 256
+    m, make_solver, w = bench.build_engine_objects(ab, c, N, 0)
+    s = make_solver(True)
+    s.set_internal_sensitivity_method(ab.InternalSensitivityMethod.staggered)
+    counters = ["numsteps", "numrhsevals", "numerrtestfails"]
+    fields = ["x", "sx"] + (["z", "sz"] if m.nz else [])
+    res = ab.run_batch(m, s, ab.ExpDataBatch(c["ts"], w["p"], w["k"]), fields=["status"] + fields + counters)
+    ssim = make_solver(True)
+    sim = ab.run_batch(m, ssim, ab.ExpDataBatch(c["ts"], w["p"], w["k"]), fields=["status"] + counters)
+    ref = refsim.RefModel(c["ref"])
+    kw = {k_: v for k_, v in bench.reference_kwargs(c).items() if k_ not in ("rtol", "atol")}
+    gold = parity.reference_triple(ref, c["ts"], w["p"], w["k"], ["status"] + fields + counters, num_threads=min(ref.max_threads(), 16), ism=2, **kw)
+    np.testing.assert_array_equal(res["status"] == 0, gold["klu_status"] == 0)
+    ok = (res["status"] == 0) & (gold["klu_status"] == 0) & (gold["dense_status"] == 0) & (gold["truth_status"] == 0)
+    assert ok.mean() > 0.9
+    for cnt in ("numsteps", "numrhsevals"):
+        e_, r_ = res[cnt][ok][:, -1].mean(), gold["klu_" + cnt][ok][:, -1].mean()
+        assert abs(e_ / r_ - 1) < 0.01, (cnt, e_, r_)
+    assert res["numrhsevals"][ok][:, -1].mean() > 1.5 * sim["numrhsevals"][ok][:, -1].mean()
+    assert res["numerrtestfails"][ok][:, -1].mean() < 0.75 * sim["numerrtestfails"][ok][:, -1].mean() + 1
+    parity.check_distribution({f: np.asarray(res[f]) for f in fields}, gold, fields, ok=ok)
