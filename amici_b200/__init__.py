@@ -354,10 +354,7 @@ class Solver:
         self._max_step_size = float(v)
     def get_max_step_size(self): return self._max_step_size
     def set_return_data_reporting_mode(self, v):
-        v = RDataReporting(int(v))
-        if v not in (RDataReporting.full, RDataReporting.likelihood):
-            raise RuntimeError("amici_b200: reporting modes implemented: full, likelihood")
-        self._reporting = v
+        self._reporting = RDataReporting(int(v))
     def get_return_data_reporting_mode(self): return self._reporting
     def set_newton_max_steps(self, v):
         if v < 0:
@@ -782,9 +779,16 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
             if arr.shape != (N, opts.nmaxevent, model.nz):
                 raise RuntimeError(f"amici_b200: {name} must have shape [N][nmaxevent][nz]")
             setattr(b, name, arr.ctypes.data_as(dp))
-    likelihood_only = opts.reporting == int(RDataReporting.likelihood)
-    lk_fields = {"status", "llh", "chi2", "sllh", "numsteps", "numrhsevals", "numerrtestfails",
-                 "numnonlinsolvconvfails", "order"}
+    # which ReturnData fields a reporting mode holds (ReturnData::initialize_*_reporting, reference src/rdata.cpp:104-211); the
+    # per-timepoint solver counters are kept in every mode (the reference has them in `full` only; bench.py reads them)
+    counters = {"status", "numsteps", "numrhsevals", "numerrtestfails", "numnonlinsolvconvfails", "order"}
+    mode_fields = {
+        int(RDataReporting.likelihood): counters | {"llh", "sllh", "FIM"},
+        int(RDataReporting.observables_likelihood): counters | {"llh", "sllh", "FIM", "y", "sigmay", "sy", "ssigmay"},
+        int(RDataReporting.residuals): counters | {"chi2", "y", "sigmay", "sy", "ssigmay", "res", "sres"},
+    }.get(opts.reporting)
+    likelihood_only = mode_fields is not None
+    lk_fields = mode_fields or set()
     out = {}
     for name, t, shp in _capi.OUT_FIELDS:
         if fields is not None and name not in fields and name != "status":
@@ -813,6 +817,12 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
         setattr(b, name, a.ctypes.data_as(dp if t == "d" else ip))
     kms = C.c_float(0.0)
     _check(lib.ab_run_batch(model.name.encode(), C.byref(opts), C.byref(b), C.byref(kms)))
+    if likelihood_only and (fields is None or "chi2" in fields or "llh" in fields):
+        # the objective scalars a mode does not compute keep the reference's defaults (src/rdata.cpp:104-107, :970-982)
+        if "chi2" not in lk_fields:
+            out["chi2"] = np.full(N, np.nan)
+        if "llh" not in lk_fields:
+            out["llh"] = np.zeros(N)
     res = BatchResult(out, batch.ts, q, float(kms.value))
     res._keep = keep
     return res

@@ -130,10 +130,6 @@ int launch_block_model(const ab_solver_options& o, const ab_batch& b, int* queue
         last_error() = "nplist exceeds the number of model parameters";
         return AB_E_UNSUPPORTED;
     }
-    if (b.FIM && !b.sres && npl > 0) {
-        last_error() = "block-solver models compute FIM from sres: request sres together with FIM";
-        return AB_E_UNSUPPORTED;
-    }
     // one thread per column, padded to a compiled block size
     constexpr int FULL = ((M::NP + 1 + 31) / 32) * 32;
     static_assert(FULL <= 320, "block solver supports at most 319 sensitivity columns");

@@ -71,7 +71,7 @@ struct Simulation {
         return nc;
     }
 
-    AB_HD bool full() const { return o.reporting == 0; }
+    AB_HD bool full() const { return o.reporting != 2; }   // RDataReporting::likelihood = 2: objective only; the other modes are selected by which output pointers are given
     // output slot j of this lane
     AB_HD int out_col(const int j) const { return bdf.g.lane + G * j; }
     AB_HD bool out_active(const int j) const { return out_col(j) <= nplist; }
@@ -283,7 +283,7 @@ struct Simulation {
             }
         }
         // FIM += sres sres^T per set measurement (reference src/rdata.cpp:1106-1205)
-        if (b.FIM && full() && nplist > 0) {
+        if (b.FIM && nplist > 0) {   // every reporting mode with sensitivities has the FIM (reference src/rdata.cpp:104-119)
             AB_UNROLL
             for (int iy = 0; iy < NY; ++iy) {
                 if (!my_set[iy]) continue;

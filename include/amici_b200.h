@@ -41,7 +41,8 @@ typedef struct ab_solver_options {
     int max_nonlin_iters;      /* Solver::set_max_nonlin_iters (3)                                   */
     int max_conv_fails;        /* Solver::set_max_conv_fails (10)                                    */
     int max_err_test_fails;    /* CVODES default 7                                                   */
-    int reporting;             /* RDataReporting: 0 full, 2 likelihood                               */
+    int reporting;             /* RDataReporting: 0 full, 1 residuals, 2 likelihood, 3 observables_likelihood: 2 skips the
+                                  per-timepoint outputs; otherwise the non-NULL output pointers select what is reported       */
     /* steady-state (pre-equilibration) settings: amici::Solver / amici::Model, reference
      * include/amici/solver.h:2040-2100, include/amici/defines.h:204-232 */
     double rtol_ss, atol_ss;             /* resolved get_{relative,absolute}_tolerance_steady_state (solver.cpp:981-998)        */

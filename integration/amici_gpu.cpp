@@ -65,8 +65,10 @@ T* ptr(std::vector<T>& v) { return v.empty() ? nullptr : v.data(); }
 void bind_outputs(ReturnData& r, std::vector<int>& preeq_status, std::vector<int>& posteq_status, ab_batch& b) {
     std::memset(&b, 0, sizeof b);
     b.status = &r.status;
-    b.llh = &r.llh;
-    b.chi2 = &r.chi2;
+    // which objective scalars a reporting mode computes: ReturnData::initialize_objective_function (reference src/rdata.cpp:970-982)
+    auto const mode = r.rdata_reporting;
+    if (mode != RDataReporting::residuals) b.llh = &r.llh;
+    if (mode == RDataReporting::full || mode == RDataReporting::residuals) b.chi2 = &r.chi2;
     b.sllh = ptr(r.sllh);
     b.x = ptr(r.x);
     b.sx = ptr(r.sx);

@@ -24,7 +24,7 @@ struct Case {
 // A deliberately heterogeneous list (ConditionContext in full): own timepoints, plist, pscale with and without parameters,
 // fixed parameters, pre-equilibration / presimulation / re-initialisation where the model has fixed parameters, x0 / sx0, a NULL
 // entry, and one condition that must fail (maxsteps) when `with_failure` is set.
-Case make_case(int n, unsigned seed, int scenario, int linsol, double rtol, double atol) {
+Case make_case(int n, unsigned seed, int scenario, int linsol, double rtol, double atol, int reporting = 0) {
     Case c;
     c.model = amici::generic_model::get_model();
     c.solver = c.model->create_solver();
@@ -34,6 +34,7 @@ Case make_case(int n, unsigned seed, int scenario, int linsol, double rtol, doub
     s.set_absolute_tolerance(atol);
     if (linsol > 0) s.set_linear_solver(static_cast<LinearSolver>(linsol));
     if (rtol < 1e-10) s.set_max_steps(500000);
+    s.set_return_data_reporting_mode(static_cast<RDataReporting>(reporting));
     s.set_sensitivity_order(SensitivityOrder::first);
     s.set_sensitivity_method(SensitivityMethod::forward);
     std::vector<realtype> ts;
@@ -136,7 +137,8 @@ void flatten(ReturnData const& r, Flat& f) {
 extern "C" long binding_run(int which, int n, unsigned seed, int scenario, int failfast, int num_threads, int linsol, double rtol, double atol,
                             double* out, long cap, char* err, int errcap) {
     try {
-        Case c = make_case(n, seed, scenario, linsol, rtol, atol);
+        // scenario 10 + m: the plain list of scenario 0 in RDataReporting mode m
+        Case c = scenario >= 10 ? make_case(n, seed, 0, linsol, rtol, atol, scenario - 10) : make_case(n, seed, scenario, linsol, rtol, atol);
         auto res = which == 0 ? run_simulations(*c.solver, c.edatas, *c.model, failfast != 0, num_threads)
                               : run_simulations_gpu(*c.solver, c.edatas, *c.model, failfast != 0, num_threads);
         Flat f;
