@@ -785,7 +785,7 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
     mode_fields = {
         int(RDataReporting.likelihood): counters | {"llh", "sllh", "FIM"},
         int(RDataReporting.observables_likelihood): counters | {"llh", "sllh", "FIM", "y", "sigmay", "sy", "ssigmay"},
-        int(RDataReporting.residuals): counters | {"chi2", "y", "sigmay", "sy", "ssigmay", "res", "sres"},
+        int(RDataReporting.residuals): counters | {"llh", "chi2", "y", "sigmay", "sy", "ssigmay", "res", "sres"},
     }.get(opts.reporting)
     likelihood_only = mode_fields is not None
     lk_fields = mode_fields or set()
@@ -821,8 +821,6 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
         # the objective scalars a mode does not compute keep the reference's defaults (src/rdata.cpp:104-107, :970-982)
         if "chi2" not in lk_fields:
             out["chi2"] = np.full(N, np.nan)
-        if "llh" not in lk_fields:
-            out["llh"] = np.zeros(N)
     res = BatchResult(out, batch.ts, q, float(kms.value))
     res._keep = keep
     return res

@@ -66,8 +66,10 @@ void bind_outputs(ReturnData& r, std::vector<int>& preeq_status, std::vector<int
     std::memset(&b, 0, sizeof b);
     b.status = &r.status;
     // which objective scalars a reporting mode computes: ReturnData::initialize_objective_function (reference src/rdata.cpp:970-982)
+    // llh is accumulated in every mode (in `residuals` it starts from the member's default 0 and is never reset); chi2 only where it
+    // is initialised to 0, elsewhere it stays NaN
     auto const mode = r.rdata_reporting;
-    if (mode != RDataReporting::residuals) b.llh = &r.llh;
+    b.llh = &r.llh;
     if (mode == RDataReporting::full || mode == RDataReporting::residuals) b.chi2 = &r.chi2;
     b.sllh = ptr(r.sllh);
     b.x = ptr(r.x);
