@@ -229,6 +229,15 @@ class Model:
     def get_steady_state_computation_mode(self): return self._ss_mode
     def set_steady_state_sensitivity_mode(self, mode): self._ss_sensi_mode = SteadyStateSensitivityMode(int(mode))
     def get_steady_state_sensitivity_mode(self): return self._ss_sensi_mode
+    def set_state_is_non_negative(self, flags):
+        flags = [bool(f) for f in flags]
+        if len(flags) != self.nx:
+            raise RuntimeError("Dimension of input stateIsNonNegative does not agree with number of state variables")
+        if any(flags) and self.nx > 64:
+            raise RuntimeError("amici_b200: state non-negativity is limited to models with nx <= 64")
+        self._x_nonneg = sum(1 << i for i, f in enumerate(flags) if f)
+    def get_state_is_non_negative(self): return [bool(getattr(self, "_x_nonneg", 0) >> i & 1) for i in range(self.nx)]
+    def set_all_states_non_negative(self): self.set_state_is_non_negative([True] * self.nx)
     def set_n_max_event(self, n):
         if int(n) < 0:
             raise RuntimeError("nmaxevent must be non-negative")
@@ -394,6 +403,11 @@ class Solver:
             raise RuntimeError("amici_b200: adjoint pre-equilibration is outside the batched forward path")
         self._sensi_meth_preeq = v
     def get_sensitivity_method_pre_equilibration(self): return self._sensi_meth_preeq
+    def set_max_time(self, seconds):
+        if seconds < 0:
+            raise RuntimeError("maxtime must be non-negative")
+        self._maxtime = float(seconds)
+    def get_max_time(self): return getattr(self, "_maxtime", 0.0)
     def set_linear_solver(self, v): self._linsol = LinearSolver(int(v))  # accepted; the engine always uses its batched LU
     def get_linear_solver(self): return self._linsol
     def clone(self):
@@ -418,7 +432,8 @@ class Solver:
             newton_damping_mode=int(self._newton_damping_mode), sensi_ss_check=int(self._sensi_ss_check),
             ss_mode=int(model._ss_mode) if model is not None else 2,
             ss_sensi_mode=int(model._ss_sensi_mode) if model is not None else 2,
-            nmaxevent=model._nmaxevent if model is not None else 10)
+            nmaxevent=model._nmaxevent if model is not None else 10,
+            x_nonneg=getattr(model, "_x_nonneg", 0) if model is not None else 0, maxtime=self.get_max_time())
 
 
 class ExpData:

@@ -17,7 +17,7 @@ class SolverOptions(C.Structure):
         (n, C.c_double) for n in ("rtol_ss", "atol_ss", "rtol_ss_sensi", "atol_ss_sensi", "newton_damping_lower_bound")] + [
         (n, C.c_int) for n in ("newton_maxsteps", "newton_damping_mode", "sensi_ss_check", "ss_mode", "ss_sensi_mode",
                                "nmaxevent", "posteq")] + [
-        (n, C.c_uint64) for n in ("reinit_states_sim", "reinit_states_presim")]
+        (n, C.c_uint64) for n in ("reinit_states_sim", "reinit_states_presim", "x_nonneg")] + [("maxtime", C.c_double)]
 
 
 # (name, dtype, shape(dims, N, nt, nplist)) for every output buffer of ab_batch; dims["ne_"] = nmaxevent of the call
@@ -80,7 +80,7 @@ def default_options(**kw) -> SolverOptions:
                       max_err_test_fails=7, reporting=0, rtol_ss=float("nan"), atol_ss=float("nan"),
                       rtol_ss_sensi=float("nan"), atol_ss_sensi=float("nan"), newton_damping_lower_bound=1e-8,
                       newton_maxsteps=0, newton_damping_mode=1, sensi_ss_check=1, ss_mode=2, ss_sensi_mode=2, nmaxevent=10,
-                      posteq=0, reinit_states_sim=0, reinit_states_presim=0)
+                      posteq=0, reinit_states_sim=0, reinit_states_presim=0, x_nonneg=0, maxtime=0.0)
     for k_, v in kw.items():
         setattr(o, k_, v)
     if o.rtol_fsa != o.rtol_fsa:

@@ -58,6 +58,8 @@ struct TrajShared {
     double ssdat[5][8];              // cvBDFStab history: ring buffer of (sqm2^2, sqm1^2, sq^2) in [1..3] and their ratios to
                                      // the next older entry in [5..7] (the rat[][] of cvSLdet, computed once), newest at ss_head
     double sld[40];                  // exchange area of bdf_sldet_xchg (ten rounds of up to four values)
+    unsigned long long xpos_mask;    // Model::set_state_is_non_negative as a bit set (AB_FULL builds; 0 = off)
+    long long t_start_ns;            // device clock when the condition started (Solver::set_max_time; AB_FULL builds)
     int piv[M::NX];
     int ip_of_col[NCOLS];            // parameter index of an integrated column (-1: state / unused)
     int il_of_col[NCOLS];            // its position in plist
@@ -122,6 +124,21 @@ AB_HD void eval_splines(const typename Layout<M, G, C>::Shared& S, const Group<G
     }
 }
 
+// Model::compute_x_pos (reference src/model.cpp:3088-3108): the model functions see max(x_i, 0) for the states flagged non-negative
+template <class M, class SharedT>
+AB_HD void x_pos(const SharedT& S, double (&x)[M::NX]) {
+#if AB_FULL
+    const unsigned long long m = S.xpos_mask;
+    if (m) {
+        AB_UNROLL
+        for (int r = 0; r < M::NX; ++r)
+            if ((m >> r & 1ull) && x[r] < 0.0) x[r] = 0.0;
+    }
+#else
+    (void)S; (void)x;
+#endif
+}
+
 // Broadcast the state column (valid on the lane that owns column 0) to all lanes of the group.
 template <class M, int G, int C>
 AB_HD void bcast_state(typename Layout<M, G, C>::Shared& S, const Group<G>& g, const double (&v)[C][M::NX],
@@ -129,6 +146,7 @@ AB_HD void bcast_state(typename Layout<M, G, C>::Shared& S, const Group<G>& g, c
     if (G == 1) {
         AB_UNROLL
         for (int r = 0; r < M::NX; ++r) e.y[r] = v[0][r];
+        x_pos<M>(S, e.y);
         return;
     }
     g.sync();
@@ -139,6 +157,7 @@ AB_HD void bcast_state(typename Layout<M, G, C>::Shared& S, const Group<G>& g, c
     g.sync();
     AB_UNROLL
     for (int r = 0; r < M::NX; ++r) e.y[r] = S.ybuf[r];
+    x_pos<M>(S, e.y);
 }
 
 // f for column 0, J(y)*s_c + dfdp_c for sensitivity columns (Model_ODE::fxdot / fsxdot,
@@ -1419,6 +1438,10 @@ struct BdfControl {
     }
     // top of the CVode step loop: error weights, step budget, tolsf test
     AB_HD int step_pre() {
+#if AB_FULL
+        // Solver::time_exceeded (reference src/solver.cpp:1056-1069; checked every 500 right-hand sides there, every 32 steps here)
+        if (o.maxtime > 0.0 && (nst & 31) == 0 && self().time_exceeded()) { tretlast = tn; return AB_MAX_TIME_EXCEEDED; }
+#endif
         if (nst > 0) self().set_ewt();
         if (so_nstloc >= so_mxstep) { tretlast = tn; return AB_TOO_MUCH_WORK; }
         // cvodes.c "tolsf" test: u * max-WRMS(zn[0]) > 1.  |y_i| * ewt_i < 1/rtol by construction of the weights, so the
@@ -1552,6 +1575,15 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
     // primitives BdfControl calls (see the list at its top)
     // -----------------------------------------------------------------------------------------
     AB_HD int nx() const { return NX; }
+    AB_HD bool time_exceeded() const {
+#if defined(__CUDA_ARCH__)
+        long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        return (double)(now - S.t_start_ns) * 1e-9 > o.maxtime;
+#else
+        return false;   // the host emulation has no clock of its own
+#endif
+    }
     AB_HD int sldet() const {
 #if defined(__CUDA_ARCH__)
         // one condition per warp: the three orders in three lanes (a shorter dependent chain on the pace-setting path of the
@@ -2165,7 +2197,11 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
             const double v = spline_eval_scaled<M, NCOLS>(S.spl, is, 0, t, true);
             spl[is] = spline_is_log<M>(is) ? exp(v) : v;
         }
-        M::root(t, y, S.p, S.k, S.h, spl, rv);
+        double yp[NX];
+        AB_UNROLL
+        for (int r = 0; r < NX; ++r) yp[r] = y[r];
+        x_pos<M>(S, yp);
+        M::root(t, yp, S.p, S.k, S.h, spl, rv);
         AB_UNROLL
         for (int i = 0; i < NES; ++i) gv[i] = rv[i];
         nge++;

@@ -121,6 +121,10 @@ int launch_block_model(const ab_solver_options& o, const ab_batch& b, int* queue
         last_error() = "pre-/post-equilibration and presimulation are not implemented for block-solver models";
         return AB_E_UNSUPPORTED;
     }
+    if (o.x_nonneg != 0ull || o.maxtime > 0.0) {
+        last_error() = "state non-negativity and the wall-clock guard are not implemented for block-solver models";
+        return AB_E_UNSUPPORTED;
+    }
     const int npl = (o.sensi >= 1) ? b.nplist : 0;
     if (npl > 0 && o.ism != 1) {
         last_error() = "block-solver models implement the simultaneous corrector only";

@@ -213,7 +213,9 @@ int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head,
         return AB_E_UNSUPPORTED;
     }
     if (b.k_preeq || o.posteq || b.t_presim) return launch_model_preeq<M>(o, b, queue_head, pg, st);   // the variant with the steady-state code
-    // staggered corrector: compiled into that variant too (event models carry it in their only kernel)
+    // state non-negativity / wall-clock guard (AB_FULL translation units) and the
+    // staggered corrector: compiled into that variant too (event models carry them in their only kernel)
+    if ((o.x_nonneg != 0ull || o.maxtime > 0.0) && M::NE == 0) return launch_model_preeq<M>(o, b, queue_head, pg, st);
     if (o.sensi >= 1 && o.ism == 2 && b.nplist > 0 && M::NE == 0) return launch_model_preeq<M>(o, b, queue_head, pg, st);
     return launch_model_impl<M, false>(o, b, queue_head, pg, st);
 }

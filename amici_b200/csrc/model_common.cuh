@@ -18,6 +18,13 @@
 #define AB_NOUNROLL
 #endif
 
+// AB_FULL = 1 in the translation units of the full-featured kernel variants (tu/<model>_preeq.cu, event models) and in the host
+// emulation: state non-negativity (Model::set_state_is_non_negative) and the wall-clock guard (Solver::set_max_time) are compiled
+// there only, so that the headline kernels' step loop does not grow; launch.cuh routes batches that use them to those variants.
+#ifndef AB_FULL
+#define AB_FULL 0
+#endif
+
 namespace amici_b200 {
 
 // status / return codes: numeric values of the reference (include/amici/defines.h:64-101),
@@ -44,6 +51,7 @@ enum : int {
     AB_SINGULAR_JACOBIAN = -9987,
     AB_T_OVERFLOW = -1002,
     AB_NOT_RUN = -1001,
+    AB_MAX_TIME_EXCEEDED = -1000,
 };
 
 // parameter scaling (reference include/amici/defines.h ParameterScaling)

@@ -54,6 +54,7 @@ struct Simulation {
     double ev_x_old[NX], ev_xdot_old[NX];
     double stau[C];
     double tlastroot, t_trig_done;
+    bool clock_started = false;   // Solver::set_max_time: the clock starts with the first phase of the condition
 
     AB_HD Simulation(Shared& s, const SolverOptions& opt, const BatchView& bv, int n_)
         : S(s), o(opt), b(bv), bdf(s, opt, integrated_columns(opt, bv)), n(n_),
@@ -92,6 +93,15 @@ struct Simulation {
             for (int i = 0; i < M::NK; ++i) S.k[i] = ksrc[(size_t)n * M::NK + i];
             M::derived(S.p, S.k);
             for (int i = 0; i < M::NH; ++i) S.h[i] = 0.0;
+            S.xpos_mask = o.x_nonneg;
+#if AB_FULL && defined(__CUDA_ARCH__)
+            if (o.maxtime > 0.0 && !clock_started) {   // the guard covers the whole simulation of this condition (all phases)
+                long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                S.t_start_ns = now;
+            }
+#endif
+            clock_started = true;
             for (int cc = 0; cc < NCOLS; ++cc) {
                 S.ip_of_col[cc] = -1;
                 S.il_of_col[cc] = -1;
@@ -191,6 +201,7 @@ struct Simulation {
         g.sync();
         AB_UNROLL
         for (int r = 0; r < NX; ++r) xs[r] = S.zn[0][r][0];
+        x_pos<M>(S, xs);   // observables and the reported state see the non-negative state (Model::fx_rdata, reference src/model.cpp:1930)
         AB_UNROLL
         for (int is = 0; is < M::NSPL; ++is) {
             loc[is] = spline_locate<M>(is, t);
@@ -391,6 +402,7 @@ struct Simulation {
     AB_HD void state_col(double (&x)[NX]) const {
         AB_UNROLL
         for (int r = 0; r < NX; ++r) x[r] = S.zn[0][r][0];
+        x_pos<M>(S, x);   // event functions see it too; add_state_event_update writes it back (reference src/model.cpp:1473-1503)
     }
     AB_HD void eval_roots(double t, const double (&x)[NX], double (&rv)[NEV]) const {
         double spl[M::NSPL > 0 ? M::NSPL : 1];
@@ -1014,6 +1026,7 @@ struct Simulation {
                 double xf[NX], f[NX], Jv[M::NNZ_J > 0 ? M::NNZ_J : 1], spl[M::NSPL > 0 ? M::NSPL : 1];
                 AB_UNROLL
                 for (int r = 0; r < NX; ++r) xf[r] = S.xfin[r];
+                x_pos<M>(S, xf);
                 spline_values_at<M, G, C>(S, t, spl);
                 M::xdot(t, xf, S.p, S.k, S.h, spl, f);
                 M::jac(t, xf, S.p, S.k, S.h, spl, Jv);

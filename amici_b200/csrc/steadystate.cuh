@@ -62,11 +62,13 @@ AB_COLD int cold_newton(typename Layout<M, G, C>::Shared& S, const SolverOptions
     double wrms = 0.0;
     g.sync();
     if (g.lane == 0) {
-        double x[NX], x_old[NX], xdot[NX], delta[NX], spl[M::NSPL > 0 ? M::NSPL : 1];
+        double x[NX], x_old[NX], xdot[NX], delta[NX], xp[NX], spl[M::NSPL > 0 ? M::NSPL : 1];   // xp: what the model functions see (x_pos)
         double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
         spline_values_at<M, G, C>(S, t, spl);
         for (int r = 0; r < NX; ++r) { x[r] = S.zn[0][r][0]; x_old[r] = x[r]; delta[r] = 0.0; }
-        M::xdot(t, x, S.p, S.k, S.h, spl, xdot);
+        for (int r = 0; r < NX; ++r) xp[r] = x[r];
+        x_pos<M>(S, xp);
+        M::xdot(t, xp, S.p, S.k, S.h, spl, xdot);
         wrms = ss_wrms<NX>(xdot, x, o.rtol_ss, o.atol_ss);
         bool converged = wrms < 1.0;
         double gamma = 1.0;
@@ -76,7 +78,9 @@ AB_COLD int cold_newton(typename Layout<M, G, C>::Shared& S, const SolverOptions
                 for (int r = 0; r < NX; ++r) x_old[r] = x[r];
             if (update_direction) {
                 // NewtonSolver::get_step: delta = -J(x)^{-1} xdot
-                M::jac(t, x, S.p, S.k, S.h, spl, Jv);
+                for (int r = 0; r < NX; ++r) xp[r] = x[r];
+                x_pos<M>(S, xp);
+                M::jac(t, xp, S.p, S.k, S.h, spl, Jv);
                 M::jac_to_dense(Jv, &S.lu[0][0]);
                 bool fin = true;
                 for (int i = 0; i < M::NNZ_J; ++i) fin = fin && isfinite(Jv[i]);
@@ -85,7 +89,9 @@ AB_COLD int cold_newton(typename Layout<M, G, C>::Shared& S, const SolverOptions
                 cold_dense_solve<M, G, C>(S, delta);
             }
             for (int r = 0; r < NX; ++r) x[r] = x_old[r] + gamma * delta[r];
-            M::xdot(t, x, S.p, S.k, S.h, spl, xdot);
+            for (int r = 0; r < NX; ++r) xp[r] = x[r];
+            x_pos<M>(S, xp);
+            M::xdot(t, xp, S.p, S.k, S.h, spl, xdot);
             const double wrms_tmp = ss_wrms<NX>(xdot, x, o.rtol_ss, o.atol_ss);
             step_successful = wrms_tmp < wrms;
             if (step_successful) {

@@ -2,6 +2,7 @@
 // Event models: IEEE divisions and double pow in the step control (see tu/events.cu).
 #define AB_EXACT_DIV 1
 #define AB_EXACT_ROOT 1
+#define AB_FULL 1   // state non-negativity, wall-clock guard (model_common.cuh)
 #include "../launch.cuh"
 #include "../models/ev_pw_state.cuh"
 namespace amici_b200 {

@@ -4,6 +4,7 @@
 // double the deviation from the reference's own KLU run on these round-off-sensitive models (profiles/r02_event_spread.md).
 #define AB_EXACT_DIV 1
 #define AB_EXACT_ROOT 1
+#define AB_FULL 1   // state non-negativity, wall-clock guard (model_common.cuh)
 #include "../launch.cuh"
 #include "../models/neuron.cuh"
 namespace amici_b200 {

@@ -1,5 +1,6 @@
 // instantiates the solve kernel for model 'spline_modes': two forcing splines outside the default HermiteSpline configuration
 // (general path of spline.cuh; tests/test_cpu.py, tests/test_gpu.py).
+#define AB_FULL 1   // state non-negativity, wall-clock guard (model_common.cuh)
 #include "../launch.cuh"
 #include "../models/spline_modes.cuh"
 namespace amici_b200 {

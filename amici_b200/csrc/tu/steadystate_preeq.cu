@@ -1,4 +1,5 @@
 // GENERATED: instantiates the solve kernel with the pre-equilibration phase for model 'steadystate'.
+#define AB_FULL 1   // state non-negativity, wall-clock guard (model_common.cuh)
 #include "../launch.cuh"
 #include "../models/steadystate.cuh"
 namespace amici_b200 {

@@ -61,6 +61,12 @@ typedef struct ab_solver_options {
        initial value depends on fixed parameters are reset to x0(k) of the next phase and their sensitivities to 0
        (Model::reinitialize, reference src/model.cpp:280-295, src/forwardproblem.cpp:316, :350-352). Models with nx <= 64. */
     unsigned long long reinit_states_sim, reinit_states_presim;
+    /* Model::set_state_is_non_negative as a bit set (bit i = state i): every model function sees max(x_i, 0) for the selected
+       states, the reported x included (Model::compute_x_pos, reference src/model.cpp:3088-3108).  Lane-group models, nx <= 64. */
+    unsigned long long x_nonneg;
+    /* Solver::set_max_time in seconds, 0 = unlimited (reference src/solver.cpp:1050-1069, src/solver_cvodes.cpp:1177): a condition
+       whose integration has run longer than this on the device ends with status AMICI_MAX_TIME_EXCEEDED (-1000). */
+    double maxtime;
 } ab_solver_options;
 
 /* One batch of N conditions (replaces std::vector<ExpData*> in, std::vector<ReturnData> out). */

@@ -88,6 +88,12 @@ extern "C" int ref_run(ref_options const* o, ref_batch* b) {
         solver->set_max_steps(o->maxsteps);
         solver->set_newton_max_steps(o->newton_maxsteps);
         if (o->stldet >= 0) solver->set_stability_limit_flag(o->stldet != 0);
+        if (o->maxtime > 0) solver->set_max_time(o->maxtime);
+        if (o->x_nonneg) {
+            std::vector<bool> nn(model->nx_solver, false);
+            for (int ix = 0; ix < model->nx_solver && ix < 31; ++ix) nn[ix] = (o->x_nonneg >> ix & 1) != 0;
+            model->set_state_is_non_negative(nn);
+        }
         solver->set_return_data_reporting_mode(static_cast<RDataReporting>(o->reporting));
 
         std::vector<std::unique_ptr<ExpData>> owned;

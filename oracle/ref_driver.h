@@ -43,6 +43,8 @@ typedef struct {
     int reinit_all;              /* ExpData::reinitialize_fixed_parameter_initial_states                          */
     int reinit_states_sim;       /* ExpData::reinitialization_state_idxs_sim as a bit set (bit i = state i)       */
     int reinit_states_presim;    /* ExpData::reinitialization_state_idxs_presim as a bit set                      */
+    int x_nonneg;                /* Model::set_state_is_non_negative as a bit set (bit i = state i), 0 = off       */
+    double maxtime;              /* Solver::set_max_time in seconds, 0 = unlimited                                 */
 } ref_options;
 
 typedef struct {

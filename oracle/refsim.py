@@ -31,7 +31,7 @@ class RefOptions(C.Structure):
         (n, C.c_int) for n in (
             "sensi_order", "sensi_meth", "ism", "linsol", "maxsteps", "newton_maxsteps",
             "ss_mode", "ss_sensi_mode", "nmaxevent", "stldet", "reporting", "num_threads",
-            "failfast", "reinit_all", "reinit_states_sim", "reinit_states_presim")]
+            "failfast", "reinit_all", "reinit_states_sim", "reinit_states_presim", "x_nonneg")] + [("maxtime", C.c_double)]
 
 
 _IN_D = ("ts",)
@@ -122,7 +122,7 @@ class RefModel:
             sensi_order=1, sensi_meth=1, ism=1, linsol=9, maxsteps=10000, newton_maxsteps=0,
             ss_mode=-1, ss_sensi_mode=-1, nmaxevent=-1, stldet=-1, reporting=0, num_threads=1,
             failfast=False, t0=0.0, ss_tol_factor=np.nan, rtol_ss=np.nan, atol_ss=np.nan,
-            fields=None) -> dict:
+            x_nonneg=0, maxtime=0.0, fields=None) -> dict:
         d = self.dims
         ts = np.ascontiguousarray(ts, dtype=np.float64)
         p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
@@ -139,7 +139,7 @@ class RefModel:
                          ss_sensi_mode=ss_sensi_mode, nmaxevent=nmaxevent, stldet=stldet,
                          reporting=reporting, num_threads=num_threads, failfast=int(failfast),
                          reinit_all=int(reinit_all), reinit_states_sim=int(reinit_states_sim),
-                         reinit_states_presim=int(reinit_states_presim))
+                         reinit_states_presim=int(reinit_states_presim), x_nonneg=int(x_nonneg), maxtime=float(maxtime))
         b = RefBatch(N=N, nt=nt, nplist=q)
         keep = [ts, p, k, plist, pscale]
         b.ts, b.p, b.k = ts.ctypes.data_as(_dp), p.ctypes.data_as(_dp), k.ctypes.data_as(_dp)

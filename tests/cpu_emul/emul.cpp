@@ -3,6 +3,7 @@
 // Compiles the solver source (amici_b200/csrc/*.cuh) for the host with a lane-group of one
 // lane that owns every column, so the step-control logic can be checked against the compiled
 // reference on machines without a GPU.  The product path is the CUDA build of the same source.
+#define AB_FULL 1
 #include "../../amici_b200/csrc/flat.cuh"
 #include "../../amici_b200/csrc/models/jakstat_adjoint.cuh"
 #include "../../amici_b200/csrc/models/robertson_ode.cuh"

@@ -563,3 +563,29 @@ def test_emulation_staggered_corrector_matches_reference(built, model):
     fl = ["x", "sx"] + (["llh", "sllh"] if kw else [])
     sel = {k_: v[ok] for k_, v in gold.items() if k_.split("_", 1)[1] in fl}
     parity.check_against_golden({f: out[f][ok] for f in fl}, sel, fields=fl)
+
+
+def test_emulation_state_non_negativity_matches_reference(built):
+    """Model::set_state_is_non_negative (reference src/model.cpp:888-913, compute_x_pos :3088-3108): initial states below zero;
+    with the flag on states 0 and 2 every model function sees max(x, 0) and the reported x is clipped.  Against the compiled
+    reference with the same flags; without the flag the same inputs give different trajectories."""
+    from oracle.refsim import RefModel, available
+    if not available("steadystate"):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    N = len(g["p"])
+    rng = np.random.default_rng(4)
+    x0 = np.stack([rng.uniform(-0.3, -0.05, N), rng.uniform(0.2, 0.8, N), rng.uniform(-0.2, 0.5, N)], 1)
+    ref = RefModel("steadystate")
+    outs = {}
+    for nn in (0, 0b101):
+        gold = parity.reference_triple(ref, g["ts"], g["p"], g["k"], ["status", "x", "sx", "y"], num_threads=min(ref.max_threads(), 8), x0=x0,
+                                       x_nonneg=nn, spread_runs=4)
+        b, out, keep = _capi.make_batch(MODEL_DIMS["steadystate"], g["ts"], g["p"], g["k"], x0=x0)
+        o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1, x_nonneg=nn)
+        assert _emul(built).emul_run(b"steadystate", C.byref(o), C.byref(b)) == 0
+        np.testing.assert_array_equal(out["status"], gold["klu_status"])
+        parity.check_against_golden({f: out[f] for f in ("x", "sx", "y")}, gold, fields=["x", "sx", "y"])
+        outs[nn] = out["x"].copy()
+    assert (outs[0b101][:, 0, 0] == 0.0).all() and (outs[0][:, 0, 0] < 0.0).all()
+    assert np.abs(outs[0b101][:, 1] - outs[0][:, 1]).max() > 1e-5

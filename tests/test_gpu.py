@@ -1159,3 +1159,38 @@ def test_cuda_staggered_corrector_matches_reference(model):
     assert res["numrhsevals"][ok][:, -1].mean() > 1.5 * sim["numrhsevals"][ok][:, -1].mean()
     assert res["numerrtestfails"][ok][:, -1].mean() < 0.75 * sim["numerrtestfails"][ok][:, -1].mean() + 1
     parity.check_distribution({f: np.asarray(res[f]) for f in fields}, gold, fields, ok=ok)
+
+
+def test_cuda_state_non_negativity_and_max_time():
+    """Model.set_state_is_non_negative (reference src/model.cpp:888-913, :3088-3108) through the C ABI against the compiled
+    reference with the same flags, and Solver.set_max_time (reference src/solver.cpp:1050-1069): a budget no condition can meet ends
+    every condition with AMICI_MAX_TIME_EXCEEDED (-1000) and NaN outputs, in the reference too; a generous one changes nothing."""
+    import amici_b200 as ab
+    from oracle.refsim import RefModel, available
+    if not available("steadystate"):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, "steadystate.npz"))
+    N = 128
+    rng = np.random.default_rng(4)
+    rep = rng.integers(0, len(g["p"]), N)
+    p, k = g["p"][rep] * 10 ** rng.normal(0, 0.05, (N, 5)), g["k"][rep]
+    x0 = np.stack([rng.uniform(-0.3, -0.05, N), rng.uniform(0.2, 0.8, N), rng.uniform(-0.2, 0.5, N)], 1)
+    m = ab.get_model("steadystate")
+    m.set_timepoints(g["ts"])
+    m.set_state_is_non_negative([True, False, True])
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(g["ts"], p, k, x0=x0))
+    assert (res["x"][:, 0, 0] == 0.0).all()
+    _check_live(res, RefModel("steadystate"), g["ts"], p, k, ["x", "sx", "y"], x0=x0, x_nonneg=0b101)
+    # wall-clock guard
+    s.set_max_time(1e3)
+    same = ab.run_simulations(m, s, ab.ExpDataBatch(g["ts"], p, k, x0=x0))
+    np.testing.assert_array_equal(same["x"], res["x"])
+    s.set_max_time(1e-9)
+    late = ab.run_simulations(m, s, ab.ExpDataBatch(g["ts"], p, k, x0=x0))
+    assert (late["status"] == -1000).all() and np.isnan(late["x"][:, 1:]).all() and np.isnan(late["llh"]).all()
+    r = RefModel("steadystate").run(g["ts"], p[:4], k[:4], x0=x0[:4], maxtime=1e-9, fields=["status", "x"])
+    assert (r["status"] == -1000).all()
