@@ -1191,6 +1191,7 @@ def test_cuda_state_non_negativity_and_max_time():
     np.testing.assert_array_equal(same["x"], res["x"])
     s.set_max_time(1e-9)
     late = ab.run_simulations(m, s, ab.ExpDataBatch(g["ts"], p, k, x0=x0))
-    assert (late["status"] == -1000).all() and np.isnan(late["x"][:, 1:]).all() and np.isnan(late["llh"]).all()
+    # the clock is read every 32 steps (every 500 right-hand sides in the reference): the first output points may have been reached
+    assert (late["status"] == -1000).all() and np.isnan(late["x"][:, -1]).all() and np.isnan(late["llh"]).all()
     r = RefModel("steadystate").run(g["ts"], p[:4], k[:4], x0=x0[:4], maxtime=1e-9, fields=["status", "x"])
     assert (r["status"] == -1000).all()
