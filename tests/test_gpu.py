@@ -1193,5 +1193,6 @@ def test_cuda_state_non_negativity_and_max_time():
     late = ab.run_simulations(m, s, ab.ExpDataBatch(g["ts"], p, k, x0=x0))
     # the clock is read every 32 steps (every 500 right-hand sides in the reference): the first output points may have been reached
     assert (late["status"] == -1000).all() and np.isnan(late["x"][:, -1]).all() and np.isnan(late["llh"]).all()
-    r = RefModel("steadystate").run(g["ts"], p[:4], k[:4], x0=x0[:4], maxtime=1e-9, fields=["status", "x"])
-    assert (r["status"] == -1000).all()
+    # the reference reads its clock at every 500th right-hand side of the calling thread, so short solves can slip through there
+    r = RefModel("steadystate").run(g["ts"], p[:16], k[:16], x0=x0[:16], maxtime=1e-9, fields=["status", "x"])
+    assert np.isin(r["status"], (0, -1000)).all() and (r["status"] == -1000).any()
