@@ -12,6 +12,29 @@ import torch
 from . import _capi, load_library, Model, Solver, ExpDataBatch, RDataReporting, _check
 
 
+def bind_to_gpu_numa(index: int) -> list[int] | None:
+    """Pin the calling process to the host cores next to GPU `index` (its PCI device's `local_cpulist`), before any pinned host
+    memory is allocated: with first-touch placement the rank's page-locked result buffers then live on the GPU's NUMA node, and
+    the eight ranks of one box stream their ReturnData over eight root complexes into their own memory controllers instead of
+    contending for one.  Returns the cores, or None if the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{dev}/local_cpulist").read().strip()
+        cores: set[int] = set()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cores.update(range(int(lo), int(hi or lo) + 1))
+        cores &= os.sched_getaffinity(0)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return sorted(cores)
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 class DeviceBatch:
     def __init__(self, model: Model, solver: Solver, batch: ExpDataBatch, device: torch.device | None = None,
                  fields=None):

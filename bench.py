@@ -276,6 +276,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = None
+    if world > 1 and not os.environ.get("BENCH_NO_NUMA_BIND"):
+        from amici_b200.device import bind_to_gpu_numa
+        numa_cores = bind_to_gpu_numa(local)   # before the pinned result buffers of the end-to-end leg are allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = ab.load_library()
@@ -363,6 +367,7 @@ def main():
                                    + ("RDataReporting.likelihood" if c.get("likelihood_only") else "RDataReporting.full"),
                        "baseline_config": c["baseline_config"], "name": args.config,
                        "parallelism": f"shard{world}" if world > 1 else "single",
+                       "numa_bind": (f"rank 0 on {len(numa_cores)} cores next to its GPU" if numa_cores else "off"),
                        "l2": "explicit 256 MiB flush between timed steps",
                        "n_failed": n_failed, "sum_llh": float(objective[0])},
             "clocks": clocks, "gpu_launches": int(launches)}

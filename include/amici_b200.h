@@ -157,7 +157,7 @@ int ab_get_nominal(const char* model, double* p, double* k);
  * This is the replacement for amici::run_simulations (reference src/amici.cpp:220-264).
  * kernel_ms (may be NULL) receives the device time of the solve kernel alone.
  * Outputs are streamed: the batch is one launch (per 16 GB of device buffers), and the outputs of each completed
- * sub-batch of 8192 conditions are copied back while the kernel keeps integrating the rest. Page-locked output
+ * sub-batch (1/64 of the batch, 512 .. 8192 conditions) are copied back while the kernel keeps integrating the rest. Page-locked output
  * arrays make those copies asynchronous. The device buffers are kept for the next call (ab_release_workspace). */
 int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch* host_batch, float* kernel_ms);
 /* Free the device workspace ab_run_batch keeps between calls (the reference's counterpart is the per-thread
