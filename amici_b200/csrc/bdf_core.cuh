@@ -1373,8 +1373,18 @@ struct BdfControl {
         so_mxstep = o.maxsteps - nst;
         so_tout = tout;
         so_one_step = one_step;
-        tstop = tout;
-        tstopset = !one_step;
+        if (!one_step) {
+            tstop = tout;
+            tstopset = true;
+        } else if (!(D::EVENTS)) {
+            tstopset = false;
+        } else if (reinit_pending) {
+            // Solver::step never sets a stop time, but reInit_post_process does (CVodeSetStopTime(tout), reference
+            // src/solver_cvodes.cpp:538) and CVODES keeps it until it is reached: the steady-state simulation of a model
+            // with events stops at the tout of the first step after every event
+            tstop = tout;
+            tstopset = true;
+        }
         // reInit_post_process (reference src/solver_cvodes.cpp:517-565): after an event the first step is taken as a
         // "first call" (nst = 0) in one-step mode with tstop = tout, then the step counter is restored
         so_post = D::EVENTS ? reinit_pending : false;
@@ -1488,7 +1498,7 @@ struct BdfControl {
             }
             return CONTINUE;
         }
-        if (so_one_step) { tretlast = tn; return AB_SUCCESS; }
+        if (so_one_step && !(D::EVENTS && tstopset)) { tretlast = tn; return AB_SUCCESS; }
         if (at_tstop) {
             tretlast = tstop;
             tstopset = false;
@@ -1497,6 +1507,7 @@ struct BdfControl {
             hprime = (tstop - tn) * (1.0 - 4.0 * DBL_EPSILON);
             eta = fast_div_1ulp(hprime, h);   // tn + h * eta must land within 100 ulp of tstop: a 2^-40 quotient misses it whenever h > 0.02 |tn| (one extra step per output time)
         }
+        if (D::EVENTS && so_one_step) { tretlast = tn; return AB_SUCCESS; }   // CV_ONE_STEP with a stop time pending (cvodes.c: the tstop test comes first)
         return CONTINUE;
     }
     AB_HD int solve_to(double tout, bool one_step = false) {

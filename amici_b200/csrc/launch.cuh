@@ -212,6 +212,13 @@ int launch_model(const ab_solver_options& o, const ab_batch& b, int* queue_head,
         last_error() = "State reinitialization cannot be enabled for this model: initial states depending on fixed parameters also depend on parameters";
         return AB_E_UNSUPPORTED;
     }
+    if (M::NE > 0 && o.posteq) {
+        // the reference has no working path here either: SteadyStateProblem(is_preeq = false) of a model with events ends in
+        // std::out_of_range ("vector::_M_range_check") for every condition, status AMICI_ERROR (observed with the compiled
+        // reference on model_events_py, profiles/r02_events_phases.md)
+        last_error() = "post-equilibration (t = inf output points) of models with events is not implemented";
+        return AB_E_UNSUPPORTED;
+    }
     if (b.k_preeq || o.posteq || b.t_presim) return launch_model_preeq<M>(o, b, queue_head, pg, st);   // the variant with the steady-state code
     // state non-negativity / wall-clock guard (AB_FULL translation units) and the
     // staggered corrector: compiled into that variant too (event models carry them in their only kernel)

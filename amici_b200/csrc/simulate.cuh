@@ -54,6 +54,7 @@ struct Simulation {
     double ev_x_old[NX], ev_xdot_old[NX];
     double stau[C];
     double tlastroot, t_trig_done;
+    bool recording = true;   // false during pre-equilibration and presimulation: events act on the state, nothing is stored (edata == nullptr / PeriodResult of another simulator)
     bool clock_started = false;   // Solver::set_max_time: the clock starts with the first phase of the condition
 
     AB_HD Simulation(Shared& s, const SolverOptions& opt, const BatchView& bv, int n_)
@@ -424,8 +425,11 @@ struct Simulation {
         }
         g.sync();
     }
-    // Model::initialize_events / reinit_events (reference src/model.cpp:407-442)
-    AB_HD void initialize_events(double t) {
+    // Model::initialize_events / reinit_events (reference src/model.cpp:407-442).  from_model_state: the "old" Heaviside
+    // vector is the model's current one (re-initialisation after a pre-equilibration / presimulation, reference
+    // src/forwardproblem.cpp:305-311, :353-360) instead of the events' initial values; the workspace's root values
+    // (FwdSimWorkspace::rootvals) are kept then.
+    AB_HD void initialize_events(double t, const bool from_model_state = false) {
         auto& g = bdf.g;
         double x[NX], rv[NEV];
         g.sync();
@@ -433,9 +437,10 @@ struct Simulation {
         eval_roots(t, x, rv);
         AB_UNROLL
         for (int ie = 0; ie < M::NE; ++ie) {
-            roots_found[ie] = (!(rv[ie] < 0.0) && !M::event_initial_value(ie)) ? 1 : 0;
+            const bool h_old = from_model_state ? (S.h[ie] > 0.0) : M::event_initial_value(ie);
+            roots_found[ie] = (!(rv[ie] < 0.0) && !h_old) ? 1 : 0;   // only false -> true triggers an event
             nroots[ie] = 0;
-            rootvals[ie] = rval_tmp[ie] = 0.0;
+            if (!from_model_state) rootvals[ie] = rval_tmp[ie] = 0.0;
         }
         g.sync();
         if (g.lane == 0) {
@@ -571,7 +576,7 @@ struct Simulation {
         eval_roots(t, x, rootvals);
         AB_UNROLL
         for (int ie = 0; ie < M::NE; ++ie) rval_tmp[ie] = rootvals[ie];
-        if (M::NZ > 0) store_event(t);
+        if (M::NZ > 0 && recording) store_event(t);
         if (nplist > 0 || o.sensi >= 1) {
             AB_UNROLL
             for (int r = 0; r < NX; ++r) ev_x_old[r] = x[r];
@@ -681,6 +686,27 @@ struct Simulation {
         return AB_SUCCESS;
     }
 
+    // roots reported at time t: the solver's root directions (Solver::get_root_info) and the explicit triggers scheduled at t,
+    // whose direction comes from the root values of the previous evaluation: copysign(1, -rootvals), i.e. -1 for +0.0
+    // (reference src/forwardproblem.cpp:116-131, :214-231)
+    AB_HD void collect_roots(const double t, const double next_t_event) {
+        AB_UNROLL
+        for (int ie = 0; ie < M::NE_SOLVER; ++ie) roots_found[ie] = bdf.iroots[ie];
+        if (t == next_t_event) {
+            AB_UNROLL
+            for (int ie = M::NE_SOLVER; ie < M::NE; ++ie)
+                if (M::explicit_time(ie, S.p, S.k) == t) roots_found[ie] = (copysign(1.0, rootvals[ie]) < 0.0) ? 1 : -1;
+            t_trig_done = t;
+        }
+    }
+    // EventHandlingSimulator::handle_initial_events (reference src/forwardproblem.cpp:516-522)
+    AB_HD void handle_initial_events(const double t) {
+        bool any = false;
+        AB_UNROLL
+        for (int ie = 0; ie < M::NE; ++ie) any = any || roots_found[ie] == 1;
+        if (any) handle_events(t, true);
+    }
+
     // SteadyStateProblem::run for pre-equilibration (reference src/forwardproblem.cpp:812-870, :1107-1206), part 1:
     // Newton's method (stage 0 or 2). Returns true if the steady state was found.
     AB_HD bool preeq_newton(int stage, int (&pe_status)[3], int (&pe_steps)[3], double& pe_wrms) {
@@ -724,38 +750,74 @@ struct Simulation {
                           (sens && o.ss_sensi_mode == SS_INTEGRATION_ONLY));
             sim_on = o.ss_mode != SS_NEWTON_ONLY;
             phase = 3;
+            if (M::NE > 0) {
+                // Model::initialize at t0 under the pre-equilibration condition (src/forwardproblem.cpp:265-269); events of this
+                // period act on the state but store nothing (EventHandlingSimulator with edata == nullptr)
+                recording = false;
+                initialize_events(o.t0);
+                if (newton_on) handle_initial_events(o.t0);   // find_steady_state_by_newtons_method (:1160-1164)
+            }
             if (newton_on && preeq_newton(0, pe_status, pe_steps, pe_wrms)) phase = 2;
             else if (sim_on) {
                 // find_steady_state_by_simulation: restart from the initial state with a fresh solver; sensitivities
                 // are integrated along unless they come from the Newton solve afterwards (:872-920, :1023-1033)
-                if (newton_on && g.lane == 0) {
+                if (newton_on && M::NE == 0 && g.lane == 0) {
                     double v[NX];
                     initial_column(0, v);
                     for (int r = 0; r < NX; ++r) S.zn[0][r][0] = v[r];
                 }
+                if (newton_on && M::NE > 0) {
+                    // the stored initial state (all columns, Heaviside variables) comes back; the workspace's root flags do
+                    // not (they were cleared while the Newton attempt handled the initial events), so the fresh simulator
+                    // finds nothing to handle at t0
+                    g.sync();
+                    AB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        if (!bdf.active(c)) continue;
+                        double v[NX];
+                        initial_column(bdf.col(c), v);
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r) S.zn[0][r][bdf.col(c)] = v[r];
+                    }
+                    g.sync();
+                    double rv_keep[NEV], rt_keep[NEV];
+                    AB_UNROLL
+                    for (int ie = 0; ie < M::NE; ++ie) { rv_keep[ie] = rootvals[ie]; rt_keep[ie] = rval_tmp[ie]; }
+                    initialize_events(o.t0);
+                    AB_UNROLL
+                    for (int ie = 0; ie < M::NE; ++ie) { roots_found[ie] = 0; rootvals[ie] = rv_keep[ie]; rval_tmp[ie] = rt_keep[ie]; }
+                }
                 g.sync();
                 bdf.ncols = (sens && o.ss_sensi_mode != SS_NEWTON_ONLY) ? ncols_main : 1;
-                bdf.init(o.t0);
+                bdf.init(o.t0);   // the fresh solver is set up first (:902-904); initial events then leave a re-initialisation pending
+                if (M::NE > 0) handle_initial_events(o.t0);   // run_steadystate_simulation_fwd (:1088)
                 phase = 1;
             }
         }
         if (PREEQ && phase == 0 && has_presim) {
             // Model::initialize at t0 - t_presim under the presimulation context, Solver::setup (src/forwardproblem.cpp:299-316)
             t = o.t0 - b.t_presim[n];
+            if (M::NE > 0) {
+                recording = false;   // the presimulation's events belong to another simulator's record
+                initialize_events(t);
+            }
             reinitialize_states(o.reinit_states_presim);   // update_and_reinit_states_and_sensitivities (:316)
             bdf.init(t);
+            if (M::NE > 0) {
+                handle_initial_events(t);
+                double x[NX];
+                g.sync();
+                state_col(x);
+                eval_roots(t, x, rootvals);
+            }
             phase = 4;
         } else if (phase == 0) {
-            if (M::NE > 0) {
-                // Model::initialize_events, then EventHandlingSimulator::handle_initial_events (src/forwardproblem.cpp:516-522)
-                initialize_events(o.t0);
-                bool any = false;
-                AB_UNROLL
-                for (int ie = 0; ie < M::NE; ++ie) any = any || roots_found[ie] == 1;
-                if (any) handle_events(o.t0, true);
-            }
-            write_initial_state();
+            if (M::NE > 0) initialize_events(o.t0);
+            // Solver::setup comes before the simulator handles the initial events (src/forwardproblem.cpp:341-345, :62): an
+            // initial event leaves a solver re-initialisation pending
             bdf.init(o.t0);
+            if (M::NE > 0) handle_initial_events(o.t0);   // EventHandlingSimulator::handle_initial_events (:516-522)
+            write_initial_state();
             if (M::NE > 0) {   // root information at t0 (src/forwardproblem.cpp:66-67)
                 double x[NX];
                 g.sync();
@@ -767,10 +829,16 @@ struct Simulation {
         for (;;) {
             double tout = 0.0;
             bool one_step = false;
+            double next_t_event = INFINITY;
             if (PREEQ && phase != 0) {
                 if (phase == 4) {
-                    if (t < o.t0 && !next_t_too_close(t, o.t0)) tout = o.t0;
-                    else {
+                    if (t < o.t0 && !next_t_too_close(t, o.t0)) {
+                        tout = o.t0;
+                        if (M::NE > M::NE_SOLVER) {   // EventHandlingSimulator::run with timepoints = {t0} (src/forwardproblem.cpp:319, :70-106)
+                            next_t_event = next_trigger(o.t0);
+                            tout = ab_min(tout, next_t_event);
+                        }
+                    } else {
                         // handle_main_simulation after a presimulation (src/forwardproblem.cpp:323-372): back to the simulation
                         // condition, x0 / sx0 = the presimulated state, Solver::reinit + sens_reinit at t0
                         g.sync();
@@ -779,11 +847,24 @@ struct Simulation {
                             M::derived(S.p, S.k);
                         }
                         g.sync();
+                        // the root flags for the main simulation come from the presimulated state, before the state
+                        // re-initialisation reaches the workspace (src/forwardproblem.cpp:350-365)
+                        if (M::NE > 0) initialize_events(o.t0, true);
                         reinitialize_states(o.reinit_states_sim);
+                        if (M::NE > 0) {
+                            recording = true;
+                            handle_initial_events(o.t0);
+                        }
                         write_initial_state();
                         bdf.amici_reinit(o.t0);   // the solver is not set up again: counters and step-size history carry on
                         t = o.t0;
                         phase = 0;
+                        if (M::NE > 0) {   // root information at t0 (src/forwardproblem.cpp:66-67)
+                            double x[NX];
+                            g.sync();
+                            state_col(x);
+                            eval_roots(o.t0, x, rootvals);
+                        }
                     }
                 }
                 if (phase == 1) {
@@ -799,6 +880,10 @@ struct Simulation {
                     } else {
                         pe_steps[1]++;
                         tout = ab_max(t, 1.0) * 10.0;
+                        if (M::NE > M::NE_SOLVER) {   // run_steady_state: the next time-triggered event is the target (src/forwardproblem.cpp:166-176, :203-205)
+                            next_t_event = next_trigger(INFINITY);
+                            if (isfinite(next_t_event)) tout = next_t_event;
+                        }
                         one_step = true;
                         if (!isfinite(tout)) {
                             pe_status[1] = SS_FAILED_TOO_LONG;
@@ -842,16 +927,30 @@ struct Simulation {
                     }
                     g.sync();
                     if (has_presim) {   // the presimulation starts from the steady state (src/forwardproblem.cpp:301-316)
-                        reinitialize_states(o.reinit_states_presim);
                         t = o.t0 - b.t_presim[n];
+                        if (M::NE > 0) initialize_events(t, true);   // Model::reinit_events with the Heaviside state of the pre-equilibration (:305-311)
+                        reinitialize_states(o.reinit_states_presim);
+                        bdf.init(t);
+                        if (M::NE > 0) handle_initial_events(t);    // pre_simulator_.run (:319): still nothing is stored
                         phase = 4;
                     } else {
-                        reinitialize_states(o.reinit_states_sim);   // src/forwardproblem.cpp:350-352
-                        write_initial_state();
                         t = o.t0;
+                        if (M::NE > 0) initialize_events(t, true);   // :353-360, from the steady state before its re-initialisation
+                        reinitialize_states(o.reinit_states_sim);   // src/forwardproblem.cpp:350-352
+                        bdf.init(t);
+                        if (M::NE > 0) {
+                            recording = true;
+                            handle_initial_events(t);
+                        }
+                        write_initial_state();
                         phase = 0;
                     }
-                    bdf.init(t);
+                    if (M::NE > 0) {   // root information at the start of the period (src/forwardproblem.cpp:66-67)
+                        double x[NX];
+                        g.sync();
+                        state_col(x);
+                        eval_roots(t, x, rootvals);
+                    }
                     AB_UNROLL
                     for (int i = 0; i < 3; ++i) {   // keep the pre-equilibration record; pe_* are re-used by a post-equilibration
                         pre_status[i] = pe_status[i];
@@ -865,7 +964,6 @@ struct Simulation {
                     if (phase == 4) continue;   // next: the presimulation
                 }
             }
-            double next_t_event = INFINITY;
             if (!PREEQ || phase == 0) {
                 if (it >= nt) break;
                 tout = b.ts[it];
@@ -924,22 +1022,33 @@ struct Simulation {
                 status = flag;
                 break;
             }
-            if (!PREEQ || phase == 0) {
-                g.sync();
-                if (g.lane == 0) {
-                    AB_UNROLL
-                    for (int r = 0; r < NX; ++r) S.xfin[r] = S.zn[0][r][0];
+            if (PREEQ && M::NE > 0 && phase == 1) {
+                // run_steady_state (src/forwardproblem.cpp:208-235): Solver::step may have over-stepped the next time-triggered
+                // event; the solution is read back there (Solver::write_solution(t, sol)) and the solver restarts from it
+                if (flag == AB_ROOT_RETURN || t >= next_t_event) {
+                    if (t >= next_t_event) {
+                        if (t > next_t_event) bdf.collapse_to(next_t_event);
+                        t = next_t_event;
+                    }
+                    collect_roots(t, next_t_event);
+                    if (handle_events(t, false) != AB_SUCCESS) {   // AmiException inside the steady-state simulation (:938-945)
+                        pe_status[1] = SS_FAILED;
+                        phase = 3;
+                    }
+                }
+                continue;
+            }
+            if (!PREEQ || phase == 0 || (M::NE > 0 && phase == 4)) {
+                if (!PREEQ || phase == 0) {
+                    g.sync();
+                    if (g.lane == 0) {
+                        AB_UNROLL
+                        for (int r = 0; r < NX; ++r) S.xfin[r] = S.zn[0][r][0];
+                    }
                 }
                 if (M::NE > 0 && (flag == AB_ROOT_RETURN || t == next_t_event)) {
                     // solver-tracked or time-triggered event (src/forwardproblem.cpp:116-134)
-                    AB_UNROLL
-                    for (int ie = 0; ie < M::NE_SOLVER; ++ie) roots_found[ie] = bdf.iroots[ie];
-                    if (t == next_t_event) {
-                        AB_UNROLL
-                        for (int ie = M::NE_SOLVER; ie < M::NE; ++ie)
-                            if (M::explicit_time(ie, S.p, S.k) == t) roots_found[ie] = rootvals[ie] > 0.0 ? -1 : 1;   // copysign(1, -rootvals)
-                        t_trig_done = t;
-                    }
+                    collect_roots(t, next_t_event);
                     const int rc = handle_events(t, false);
                     if (rc != AB_SUCCESS) {
                         status = rc;

@@ -6,9 +6,4 @@
 #include "../launch.cuh"
 #include "../models/ev_pw_state.cuh"
 namespace amici_b200 {
-template <>
-int launch_model_preeq<models::ev_pw_state>(const ab_solver_options&, const ab_batch&, int*, const Progress&, cudaStream_t) {
-    last_error() = "pre-/post-equilibration and presimulation of models with events are not implemented";
-    return AB_E_UNSUPPORTED;
-}
 ModelEntry entry_ev_pw_state() { return make_entry<models::ev_pw_state>(); } }

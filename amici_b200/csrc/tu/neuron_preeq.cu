@@ -1,4 +1,4 @@
-// GENERATED: instantiates the solve kernel for model 'neuron' (one translation unit per model keeps builds parallel).
+// GENERATED: instantiates the solve kernel with the pre-equilibration / presimulation phases for model 'neuron' (one translation unit per model keeps builds parallel).
 // Event models: IEEE divisions and double pow in the step control.  The approximations used by the event-free kernels
 // (model_common.cuh fast_div, bdf_core.cuh nth_root) do not change the error against a tight-tolerance run, but they
 // double the deviation from the reference's own KLU run on these round-off-sensitive models (profiles/r02_event_spread.md).
@@ -8,4 +8,8 @@
 #include "../launch.cuh"
 #include "../models/neuron.cuh"
 namespace amici_b200 {
-ModelEntry entry_neuron() { return make_entry<models::neuron>(); } }
+template <>
+int launch_model_preeq<models::neuron>(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
+    return launch_model_impl<models::neuron, true>(o, b, queue_head, pg, st);
+}
+}  // namespace amici_b200

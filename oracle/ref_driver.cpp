@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -159,6 +160,8 @@ extern "C" int ref_run(ref_options const* o, ref_batch* b) {
 
         for (int i = 0; i < N; ++i) {
             auto const& r = *rdatas[i];
+            if (std::getenv("REF_VERBOSE"))   // diagnostic: the reference's per-simulation log (ReturnData::messages)
+                for (auto const& msg : r.messages) fprintf(stderr, "ref[%d] %s: %s\n", i, msg.identifier.c_str(), msg.message.c_str());
             if (b->status) b->status[i] = r.status;
             if (b->llh) b->llh[i] = r.llh;
             if (b->chi2) b->chi2[i] = r.chi2;

@@ -21,12 +21,14 @@ PREEQ_FIELDS = ["x_ss", "sx_ss", "preeq_status", "preeq_numsteps", "preeq_wrms",
 EVENT_FIELDS = ["z", "sz", "rz", "srz", "sigmaz"]
 
 
-def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=None, presim=False, **run_kw):
+def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=None, presim=False, pfix=None, **run_kw):
     m = RefModel(model)
     d = m.dims
     rng = np.random.default_rng(seed)
     p = np.tile(m.p_nominal, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, d.np))
     p[0] = m.p_nominal
+    if pfix is not None:
+        p = pfix(p)
     k = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.8, 1.25, (N, d.nk))
     k[0] = m.k_nominal
     k_preeq = np.tile(m.k_nominal, (N, 1)) * rng.uniform(0.5, 2.0, (N, d.nk)) if preeq else None
@@ -129,7 +131,31 @@ def make_presim():
          ss_mode=2, ss_sensi_mode=0, reinit_states_sim=0b010, reinit_states_presim=0b101)
 
 
+def _events_p(p):
+    # During a pre-equilibration / presimulation the reference carries the root flags of the time-triggered events over to
+    # the next state-triggered one (Solver::get_root_info fills the solver-tracked entries only), so the Heaviside state of
+    # "p4 - t" becomes -1 when x1 crosses x3 and x1 decays at twice its rate.  For p1 > 1/2 the trajectories then re-cross at
+    # once and the outcome ("root after reinitialization" or not) hinges on whether x1 - x3 rounds to exactly zero at the
+    # located root: not reproducible by any second implementation.  The fixtures keep p1 below 0.47.
+    p = p.copy()
+    p[:, 0] = np.minimum(p[:, 0], 0.94 - p[:, 0])
+    return p
+
+
+def make_events_phases():
+    # models with events: pre-equilibration (events act on the state, nothing is stored), presimulation, both
+    # (reference src/forwardproblem.cpp:153-243, :284-372)
+    ts = np.linspace(0, 10, 11)
+    make("events", ts, N=6, seed=31, tag="_preeq", preeq=True, pfix=_events_p, nmaxevent=4)
+    make("events", ts, N=6, seed=32, tag="_presim", presim=True, pfix=_events_p, nmaxevent=4)
+    make("events", ts, N=6, seed=33, tag="_preeq_presim", preeq=True, presim=True, pfix=_events_p, nmaxevent=4)
+    make("neuron", np.linspace(0, 50, 11), N=6, seed=34, tag="_presim", presim=True, kscale=(1.0, 1.0), nmaxevent=10)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["events_phases"]:
+        make_events_phases()
+        sys.exit(0)
     if sys.argv[1:] == ["presim"]:
         make_presim()
         sys.exit(0)
@@ -161,3 +187,4 @@ if __name__ == "__main__":
     make("steadystate", np.linspace(0, 10, 11), N=6, seed=16, tag="_preeq_newton2", preeq=True, newton_maxsteps=2,
          ss_mode=2, ss_sensi_mode=0)
     make_presim()
+    make_events_phases()

@@ -111,6 +111,27 @@ def test_emulation_state_reinitialisation_matches_golden(built):
     np.testing.assert_array_equal(out["sx0"][:, :, 1], out["sx_ss"][:, :, 1])
 
 
+@pytest.mark.parametrize("fixture", ["events_preeq", "events_presim", "events_preeq_presim", "neuron_presim"])
+def test_emulation_event_models_preequilibration_presimulation(built, fixture):
+    """Models with events through a pre-equilibration (EventHandlingSimulator::run_steady_state, reference
+    src/forwardproblem.cpp:153-243: events act on the state, nothing is stored, a time-triggered event is the target of the
+    next step), a presimulation (:284-321) and the re-initialisation of the events at the start of the next period
+    (Model::reinit_events with the old Heaviside state, :305-311, :353-360): status, steady-state status triple, event
+    counts and all values against the compiled reference."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    model = fixture.split("_")[0]
+    out = run_emul(_emul(built), model, g)
+    np.testing.assert_array_equal(out["status"], g["klu_status"])
+    if "k_preeq" in g:
+        np.testing.assert_array_equal(out["preeq_status"], g["klu_preeq_status"])
+        sim = g["klu_preeq_numsteps"][:, 1]
+        assert (np.abs(out["preeq_numsteps"][:, 1] - sim) <= 0.1 * sim + 2).all()
+    parity.check_against_golden(out, g)
+    np.testing.assert_array_equal(out["rz"] != 0, g["klu_rz"] != 0)
+    np.testing.assert_array_equal(out["z"] < g["ts"][-1], g["klu_z"] < g["ts"][-1])
+    np.testing.assert_allclose(out["z"], g["klu_z"], rtol=1e-6, atol=1e-9)
+
+
 @pytest.mark.parametrize("model", ["events", "neuron"])
 def test_emulation_events_match_golden(built, model):
     """Heaviside switches, root finding and state resets (BASELINE config 4): event observables z/sz/rz/srz, the number

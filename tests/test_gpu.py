@@ -248,13 +248,69 @@ def test_cuda_state_reinitialisation_matches_golden():
         ab.run_simulations(n, n.create_solver(), ab.ExpDataBatch([0.0, 1.0], [n.get_free_parameters()], [n.get_fixed_parameters()]))
 
 
-def test_presimulation_is_refused_for_event_models():
+def test_postequilibration_is_refused_for_event_models():
+    """t = inf output points of a model with events: the compiled reference ends every such condition with an exception
+    (std::out_of_range inside SteadyStateProblem, status AMICI_ERROR); the engine refuses the combination."""
     import amici_b200 as ab
     m = ab.get_model("events")
-    m.set_timepoints(np.linspace(0, 10, 5))
+    m.set_timepoints([0.0, 1.0, np.inf])
     s = m.create_solver()
-    with pytest.raises(RuntimeError, match="presimulation"):
-        ab.run_simulations(m, s, ab.ExpDataBatch(m.get_timepoints(), [m.get_free_parameters()], [m.get_fixed_parameters()], t_presim=[1.0]))
+    with pytest.raises(RuntimeError, match="post-equilibration"):
+        ab.run_simulations(m, s, ab.ExpDataBatch(m.get_timepoints(), [m.get_free_parameters()], [m.get_fixed_parameters()]))
+
+
+@pytest.mark.parametrize("fixture", ["events_preeq", "events_presim", "events_preeq_presim", "neuron_presim"])
+def test_cuda_event_models_preequilibration_presimulation(fixture):
+    """Pre-equilibration and presimulation of models with events (reference src/forwardproblem.cpp:153-243, :284-372) through
+    the C ABI: status, SteadyStateStatus triple, event counts and every value against the compiled reference's fixtures."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    res = _run(fixture.split("_")[0], g)
+    np.testing.assert_array_equal(res["status"], g["klu_status"])
+    if "k_preeq" in g:
+        np.testing.assert_array_equal(res["preeq_status"], g["klu_preeq_status"])
+        sim = g["klu_preeq_numsteps"][:, 1]
+        assert (np.abs(res["preeq_numsteps"][:, 1] - sim) <= 0.1 * sim + 2).all()
+    parity.check_against_golden(res.fields, g)
+    np.testing.assert_array_equal(res["rz"] != 0, g["klu_rz"] != 0)
+    np.testing.assert_array_equal(res["z"] < g["ts"][-1], g["klu_z"] < g["ts"][-1])
+
+
+def test_cuda_events_preequilibration_presimulation_batch_vs_reference():
+    """1024 parameter samples of model_events_py, pre-equilibrated under k x U(0.5, 2) and presimulated for U(0, 4) under a third
+    condition: status codes, steady-state status and event counts identical to the compiled reference on a 96-condition subset,
+    floats by the parity protocol.  p1 is kept below 0.47 (tests/golden/make_golden.py::_events_p: above 1/2 the reference's
+    outcome hinges on an exact-zero root value)."""
+    import amici_b200 as ab
+    from oracle import refsim
+    N, nme = 1024, 4
+    m = ab.get_model("events")
+    ts = np.linspace(0, 10, 11)
+    m.set_timepoints(ts)
+    m.set_n_max_event(nme)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    rng = np.random.default_rng(41)
+    p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.normal(0, 0.1, (N, m.np()))
+    p[:, 0] = np.minimum(p[:, 0], 0.94 - p[:, 0])
+    k = np.tile(m.get_fixed_parameters(), (N, 1))
+    kpe, kps = k * rng.uniform(0.5, 2.0, k.shape), k * rng.uniform(0.5, 2.0, k.shape)
+    tps = rng.uniform(0.0, 4.0, N)
+    res = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k, k_preeq=kpe, k_presim=kps, t_presim=tps))
+    assert (res["status"] == 0).mean() > 0.9
+    if not refsim.available("events"):
+        return
+    idx = np.union1d(rng.choice(N, 96, replace=False), np.nonzero(res["status"] != 0)[0][:32])
+    ref = refsim.RefModel("events")
+    kw = dict(k_preeq=kpe[idx], k_presim=kps[idx], t_presim=tps[idx], nmaxevent=nme)
+    r = ref.run(ts, p[idx], k[idx], num_threads=min(ref.max_threads(), 16), **kw)
+    np.testing.assert_array_equal(res["status"][idx], r["status"])
+    np.testing.assert_array_equal(res["preeq_status"][idx], r["preeq_status"])
+    good = r["status"] == 0
+    np.testing.assert_array_equal(res["z"][idx][good] < ts[-1], r["z"][good] < ts[-1])
+    sub = {f: np.asarray(res[f])[idx] for f in ("status", "x", "sx", "x0", "sx0", "x_ss", "sx_ss", "z", "sz")}
+    _check_live(sub, ref, ts, p[idx], k[idx], ["x", "sx", "x0", "sx0", "x_ss", "sx_ss", "z", "sz"], ok=good, status_equal=False, **kw)
 
 
 @pytest.mark.parametrize("model", ["events", "neuron"])
