@@ -32,6 +32,24 @@ def scaled_err(a, b, truth, rtol=10 * RTOL, atol=10 * ATOL):
     return float(np.nanmax(err)) if err.size and not nan_a.all() else 0.0
 
 
+def _propagated_scale(f, gold, truth):
+    """Magnitude that the relative tolerance refers to.  For every field it is |truth|, except for the residuals and chi2: they
+    are differences of near-equal numbers, res = (y - my) / sigma, so a deviation of y INSIDE its tolerance moves res by
+    delta_y / sigma, which relative to |res| is larger by |y| / |y - my| (~100 on the fixtures).  Their tolerance is the one of y
+    carried through the formula: |y| / sigma for res, sum 2 |res| |y| / sigma for chi2 (never smaller than |truth|)."""
+    truth = np.asarray(truth, float)
+    if f not in ("res", "chi2") or "truth_y" not in gold or "truth_sigmay" not in gold or "truth_res" not in gold:
+        return truth
+    y, sig, res = (np.asarray(gold["truth_" + k_], float) for k_ in ("y", "sigmay", "res"))
+    if y.size != res.size:
+        return truth
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sc = np.nan_to_num(np.abs(y) / sig, nan=0.0, posinf=0.0).reshape(res.shape)
+    if f == "res":
+        return np.maximum(np.abs(truth), sc)
+    return np.maximum(np.abs(truth), (2.0 * np.abs(np.nan_to_num(res)) * sc).reshape(res.shape[0], -1).sum(-1).reshape(truth.shape))
+
+
 def check_against_golden(cand: dict, gold, fields=None, factor=FACTOR, verbose=True):
     """cand: field -> array; gold: loaded npz. Returns report dict; raises AssertionError on failure."""
     report = {}
@@ -42,7 +60,7 @@ def check_against_golden(cand: dict, gold, fields=None, factor=FACTOR, verbose=T
         if f not in cand or f"klu_{f}" not in gold:
             continue
         klu, dense, truth = gold[f"klu_{f}"], gold[f"dense_{f}"], gold[f"truth_{f}"]
-        scale_ref = truth
+        scale_ref = _propagated_scale(f, gold, truth)
         others = [dense] + [gold[k_] for k_ in (f"s{j}_{f}" for j in range(64)) if k_ in gold]   # reference_triple(spread_runs=...)
         floor_truth = max(scaled_err(r, truth, scale_ref) for r in [klu] + others)
         floor_pair = max(scaled_err(r, klu, scale_ref) for r in others)
