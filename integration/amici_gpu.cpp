@@ -55,6 +55,11 @@ ab_solver_options solver_options(Solver const& solver, Model const& model) {
     o.ss_mode = static_cast<int>(model.get_steady_state_computation_mode());
     o.ss_sensi_mode = static_cast<int>(model.get_steady_state_sensitivity_mode());
     o.nmaxevent = model.n_max_event();
+    o.maxtime = solver.get_max_time();   // Solver::set_max_time, seconds; 0 = unlimited
+    o.x_nonneg = 0ull;                   // Model::set_state_is_non_negative as a bit set
+    auto const& nonneg = model.get_state_is_non_negative();
+    for (size_t i = 0; i < nonneg.size() && i < 64; ++i)
+        if (nonneg[i]) o.x_nonneg |= 1ull << i;
     return o;
 }
 
