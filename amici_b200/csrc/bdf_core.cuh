@@ -857,6 +857,14 @@ AB_COLD void cold_dense_solve(const typename Layout<M, G, C>::Shared& S, double*
 //   and, if D::ROOTS: rcheck1() rcheck2() rcheck3(tout, one_step) collapse_to(t), members tlo, irfnd
 // and everything here is scalar logic that every thread executes identically.
 // ---------------------------------------------------------------------------------------------
+// optional features of a derived solver (adjoint.cuh): quadrature variables that are corrected after the states have passed
+// their error test (cvQuadNls) and take their own (D::QUAD), and a callback after every internal step (D::HIST: the forward
+// pass of the adjoint method stores its solution there).  Solvers that do not declare them compile none of it.
+template <class D, class = void> struct HasQuad { static constexpr bool value = false; };
+template <class D> struct HasQuad<D, decltype((void)D::QUAD)> { static constexpr bool value = D::QUAD; };
+template <class D, class = void> struct HasHist { static constexpr bool value = false; };
+template <class D> struct HasHist<D, decltype((void)D::HIST)> { static constexpr bool value = D::HIST; };
+
 template <class D, class SharedT>
 struct BdfControl {
     SharedT& S;
@@ -1238,6 +1246,29 @@ struct BdfControl {
         if constexpr (D::STG) {
             if (o.ism == 2 && self().has_sens()) return staggered_stage();
         }
+        if constexpr (HasQuad<D>::value) return quadrature_stage();
+        return AB_SUCCESS;
+    }
+    // Quadrature variables (cvStep, cvodes.c:5870-5905): after the states have converged and passed their error test the
+    // quadratures are corrected explicitly (cvQuadNls: acorQ = rl1 * (h * fQ(tn, y) - znQ[1])) and take their own error test
+    // (errconQ, which AMICI switches on for the backward problem: reference src/solver.cpp:674-691); dsm = max of both.
+    AB_HD int quadrature_stage() {
+        st_ncf = st_nef = 0;
+        if (!self().quad_correct()) {   // fQ failed recoverably: cvHandleNFlag
+            st_ncfS++;
+            etamax = 1.0;
+            if (st_ncfS == o.max_conv_fails) {
+                tn = st_saved_t;
+                return AB_CONV_FAILURE;
+            }
+            eta = 0.25;
+            st_nflag = PREV_CONV_FAIL;
+            st_restore = st_resc = true;
+            return CONTINUE;
+        }
+        const double dsmQ = self().quad_norm() * tq[2];
+        if (dsmQ > 1.0) return error_test_failed(st_nefS, dsmQ, false);
+        if (dsmQ > st_dsm) st_dsm = dsmQ;
         return AB_SUCCESS;
     }
     // cvDoErrorTest (cvodes.c:7461) after a failed test: count, restore, shrink the step / lower the order / restart at order 1.
@@ -1522,6 +1553,7 @@ struct BdfControl {
             const int kflag = step();
             if (kflag != AB_SUCCESS) { tretlast = tn; rc = kflag; break; }
             rc = step_post();
+            if constexpr (HasHist<D>::value) { if (rc >= 0) self().on_step(); }   // CVodeF: every internal step is a data point of the interpolation (cvodea.c:395-560)
             if (rc != CONTINUE) break;
         }
         self().step_sync_leave();   // first: the other warps of the group must not wait for the flush below

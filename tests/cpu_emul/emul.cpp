@@ -5,6 +5,7 @@
 // reference on machines without a GPU.  The product path is the CUDA build of the same source.
 #define AB_FULL 1
 #include "../../amici_b200/csrc/flat.cuh"
+#include "../../amici_b200/csrc/adjoint.cuh"
 #include "../../amici_b200/csrc/models/jakstat_adjoint.cuh"
 #include "../../amici_b200/csrc/models/robertson_ode.cuh"
 #include "../../amici_b200/csrc/models/steadystate.cuh"
@@ -20,6 +21,7 @@
 
 #include <memory>
 #include <string>
+#include <vector>
 
 using namespace amici_b200;
 
@@ -66,6 +68,29 @@ static int run_model_flat(const SolverOptions* o, const BatchView* b) {
     WarpAlign align;
     flat_run<M, 1, NC>(*S, *o, *b, &head, align, [](int) {});
     return 0;
+}
+
+// adjoint sensitivity analysis (adjoint.cuh): one condition after the other, history on the heap
+template <class M>
+static int run_model_adjoint(const SolverOptions* o, const BatchView* b) {
+    const int cap = o->maxsteps + 2;
+    std::vector<double> ht(cap), hy((size_t)cap * M::NX), dj((size_t)(b->nt > 0 ? b->nt : 1) * M::NX);
+    std::vector<int> hq(cap);
+    auto hist = std::make_unique<FwdHistory<M::NX>>();
+    hist->t = ht.data(); hist->y = hy.data(); hist->ord = hq.data(); hist->stride = 1; hist->cap = cap;
+    for (int n = 0; n < b->N; ++n) {
+        auto sim = std::make_unique<AdjointSimulation<M>>(*o, *b, *hist, dj.data(), n);
+        sim->run();
+    }
+    return 0;
+}
+
+extern "C" int emul_run_adjoint(const char* model, const SolverOptions* o, const BatchView* b) {
+    std::string m(model);
+    if (m == "jakstat_adjoint") return run_model_adjoint<models::jakstat_adjoint>(o, b);
+    if (m == "steadystate") return run_model_adjoint<models::steadystate>(o, b);
+    if (m == "robertson_ode") return run_model_adjoint<models::robertson_ode>(o, b);
+    return -2;
 }
 
 extern "C" int emul_run_flat(const char* model, const SolverOptions* o, const BatchView* b) {
