@@ -329,10 +329,8 @@ class Solver:
     def set_sensitivity_order(self, v): self._sensi = SensitivityOrder(int(v))
     def get_sensitivity_order(self): return self._sensi
     def set_sensitivity_method(self, v):
-        v = SensitivityMethod(int(v))
-        if v == SensitivityMethod.adjoint:
-            raise RuntimeError("amici_b200: adjoint sensitivities are outside the batched forward path")
-        self._sensi_meth = v
+        # adjoint: event-free lane-group models, plain simulations (amici_b200/csrc/adjoint.cuh); the engine refuses the rest
+        self._sensi_meth = SensitivityMethod(int(v))
     def get_sensitivity_method(self): return self._sensi_meth
     def set_internal_sensitivity_method(self, v):
         v = InternalSensitivityMethod(int(v))
@@ -415,7 +413,7 @@ class Solver:
         return copy.deepcopy(self)
 
     def _options(self, t0: float, model: "Model | None" = None) -> _capi.SolverOptions:
-        fsa = self._sensi >= SensitivityOrder.first and self._sensi_meth == SensitivityMethod.forward
+        fsa = self._sensi >= SensitivityOrder.first and self._sensi_meth in (SensitivityMethod.forward, SensitivityMethod.adjoint)
         if self._sensi >= SensitivityOrder.second:
             raise RuntimeError("amici_b200: second-order sensitivities are not implemented")
         return _capi.default_options(
@@ -433,7 +431,8 @@ class Solver:
             ss_mode=int(model._ss_mode) if model is not None else 2,
             ss_sensi_mode=int(model._ss_sensi_mode) if model is not None else 2,
             nmaxevent=model._nmaxevent if model is not None else 10,
-            x_nonneg=getattr(model, "_x_nonneg", 0) if model is not None else 0, maxtime=self.get_max_time())
+            x_nonneg=getattr(model, "_x_nonneg", 0) if model is not None else 0, maxtime=self.get_max_time(),
+            sensi_meth=int(self._sensi_meth) if fsa else 0)
 
 
 class ExpData:
@@ -825,6 +824,10 @@ def run_batch(model: Model, solver: Solver, batch: ExpDataBatch, fields: Sequenc
         shape = shp(d, N, nt, q)
         if q == 0 and name in ("sllh", "sx", "sy", "ssigmay", "sres", "FIM", "sx0", "sx_ss", "sz", "srz"):
             out[name] = np.zeros(shape)
+            continue
+        if opts.sensi_meth == 2 and name in ("sx", "sy", "ssigmay", "sres", "FIM", "sx0", "sx_ss", "sz", "srz"):
+            # adjoint sensitivity analysis gives the gradient sllh only (the reference leaves these fields empty)
+            out[name] = np.full(shape, np.nan)
             continue
         a, t_keep = _pinned_empty(shape, np.float64 if t == "d" else np.int32)
         keep.append(t_keep)

@@ -17,7 +17,8 @@ class SolverOptions(C.Structure):
         (n, C.c_double) for n in ("rtol_ss", "atol_ss", "rtol_ss_sensi", "atol_ss_sensi", "newton_damping_lower_bound")] + [
         (n, C.c_int) for n in ("newton_maxsteps", "newton_damping_mode", "sensi_ss_check", "ss_mode", "ss_sensi_mode",
                                "nmaxevent", "posteq")] + [
-        (n, C.c_uint64) for n in ("reinit_states_sim", "reinit_states_presim", "x_nonneg")] + [("maxtime", C.c_double)]
+        (n, C.c_uint64) for n in ("reinit_states_sim", "reinit_states_presim", "x_nonneg")] + [("maxtime", C.c_double),
+                                                                                               ("sensi_meth", C.c_int), ("reserved_", C.c_int)]
 
 
 # (name, dtype, shape(dims, N, nt, nplist)) for every output buffer of ab_batch; dims["ne_"] = nmaxevent of the call

@@ -26,6 +26,14 @@ AB_HD bool adj_too_close(double cur_t, double t_next) {
     return fabs(tdiff) < 2.0 * DBL_EPSILON * ab_max(fabs(cur_t), fabs(t_next));
 }
 
+// the large pieces are real functions: the forward and the backward solver instantiate the step control twice, and a thread's
+// state is in local memory anyway
+#if defined(__CUDACC__)
+#define AB_NI __host__ __device__ __noinline__
+#else
+#define AB_NI __attribute__((noinline))
+#endif
+
 struct ScalarShared {
     double ctl[16];
     double ssdat[5][8];
@@ -66,7 +74,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     AB_HD void on_step() { prob.store_point(tn, Base::qu, zn[0], pending ? acor : nullptr); }
 
     AB_HD static double upd(double m, double v) { return (v > m || v != v) ? v : m; }
-    AB_HD double wrms2(const double* a, const double* b, double fb, const double* w, int n) const {
+    AB_NI double wrms2(const double* a, const double* b, double fb, const double* w, int n) const {
         double s = 0.0;
         for (int r = 0; r < n; ++r) {
             const double v = (b ? a[r] + fb * b[r] : a[r]) * w[r];
@@ -84,7 +92,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         if (QUAD) m = upd(m, wrms2(acorQ, znQ[QMAX], -cquot, ewtQ, nq));
         return m;
     }
-    AB_HD void set_ewt() {
+    AB_NI void set_ewt() {
         for (int r = 0; r < NX; ++r) ewt[r] = 1.0 / (prob.rtol * fabs(pending ? zn[0][r] + acor[r] : zn[0][r]) + prob.atol);
         if (QUAD)
             for (int r = 0; r < nq; ++r) ewtQ[r] = 1.0 / (prob.rtolq * fabs(pending ? znQ[0][r] + acorQ[r] : znQ[0][r]) + prob.atolq);
@@ -98,7 +106,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     }
     // cvCompleteStep / cvRescale / cvPredict / cvRestore in one pass per row (see Bdf::history_pass)
     template <int PRED, int N>
-    AB_HD void pass(double (&z)[LMAX][N], const double* ac, int n, const bool cmpl, const bool resc) {
+    AB_NI void pass(double (&z)[LMAX][N], const double* ac, int n, const bool cmpl, const bool resc) {
         double f[QMAX + 1];
         f[0] = 1.0;
         for (int j = 1; j <= QMAX; ++j) f[j] = f[j - 1] * eta;
@@ -179,7 +187,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         return ok;
     }
     // cvHin / cvUpperBoundH0 / cvYddNorm (cvodes.c:5436-5798) with the quadrature terms of errconQ; zn[1] = y'(tn) unscaled
-    AB_HD int initial_step(double tout, double* h_out, int* nfe_hin) {
+    AB_NI int initial_step(double tout, double* h_out, int* nfe_hin) {
         const double tdiff = tout - tn;
         if (tdiff == 0.0) return AB_TOO_CLOSE;
         const double sign = tdiff > 0.0 ? 1.0 : -1.0;
@@ -244,7 +252,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         return AB_SUCCESS;
     }
     // cvLsSetup + cvLsLinSys (cvodes_ls.c:1611-1710, :1386-1470) with a dense LU with partial pivoting (SUNLinSol_Dense semantics)
-    AB_HD int lsetup(bool jbad_nls, const double* ycur) {
+    AB_NI int lsetup(bool jbad_nls, const double* ycur) {
         if (jbad_nls) convfail = CONVFAIL_BAD_J;
         const double dgamma = fabs(gamma / gammap - 1.0);
         const bool jbad = (nst == 0) || (nst >= nstlj + 51) || (convfail == CONVFAIL_BAD_J && dgamma < 0.2) || (convfail == CONVFAIL_OTHER);
@@ -299,7 +307,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         }
     }
     // cvNls + SUNNonlinSolSolve_Newton (see Bdf::nls_impl)
-    AB_HD int nls(int nflag) {
+    AB_NI int nls(int nflag) {
         convfail = (nflag == FIRST_CALL || nflag == PREV_ERR_FAIL) ? CONVFAIL_NONE : CONVFAIL_OTHER;
         bool callSetup = (nflag == PREV_CONV_FAIL) || (nflag == PREV_ERR_FAIL) || (nst == 0) || (nst >= nstlp + 20) ||
                          (fabs(gamrat - 1.0) > 0.3);
@@ -350,7 +358,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         return ret;
     }
     // cvQuadNls (cvodes.c:7236-7262)
-    AB_HD bool quad_correct() {
+    AB_NI bool quad_correct() {
         double y[NX], fq[NQA];
         for (int r = 0; r < NX; ++r) y[r] = zn[0][r] + acor[r];
         const bool ok = prob.quad(tn, y, fq);
@@ -359,7 +367,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     }
     AB_HD double quad_norm() const { return wrms2(acorQ, nullptr, 0.0, ewtQ, nq); }
     // CVodeGetDky(t, 0) / CVodeGetQuadDky(t, 0) on the completed history
-    AB_HD void interpolate(double t, double* y, double* yq) {
+    AB_NI void interpolate(double t, double* y, double* yq) {
         Base::flush_pending();
         const double s = (t - tn) / h;
         for (int r = 0; r < NX; ++r) {
@@ -402,7 +410,7 @@ struct FwdHistory {
         new_data = true;
     }
     // y(t) by the Newton polynomial through order + 1 stored points ending at the right end of the step that contains t
-    AB_HD bool get(double tt, double* out) {
+    AB_NI bool get(double tt, double* out) {
         bool newpoint = false;
         if (new_data) {
             ilast = np - 1;
@@ -503,7 +511,7 @@ struct FwdProblem {
     const AdjCond<M>& c;
     FwdHistory<M::NX>& hist;
     double rtol, atol, rtolq, atolq;
-    AB_HD bool rhs(double t, const double* y, double* f) const {
+    AB_NI bool rhs(double t, const double* y, double* f) const {
         double spl[AdjCond<M>::NSPLV];
         c.splines(t, spl);
         M::xdot(t, y, c.p, c.k, c.h, spl, f);
@@ -531,7 +539,7 @@ struct BwdProblem {
     double rtol, atol, rtolq, atolq;
     double tc, x[NX], Jd[NX * NX], spl[AdjCond<M>::NSPLV];
     bool have;
-    AB_HD bool at(double t) {   // CVArhs / CVArhsQ / the Jacobian wrapper: forward solution from the interpolation
+    AB_NI bool at(double t) {   // CVArhs / CVArhsQ / the Jacobian wrapper: forward solution from the interpolation
         if (have && t == tc) return true;
         if (!hist.get(t, x)) return false;
         double Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
@@ -558,7 +566,7 @@ struct BwdProblem {
         for (int r = 0; r < NX; ++r)
             for (int cc = 0; cc < NX; ++cc) J[r][cc] = -Jd[cc * NX + r];
     }
-    AB_HD bool quad(double t, const double* xB, double* fq) {
+    AB_NI bool quad(double t, const double* xB, double* fq) {
         if (!at(t)) return false;
         bool ok = true;
         for (int il = 0; il < c.nplist; ++il) {
@@ -592,10 +600,16 @@ struct AdjointSimulation {
     AB_HD AdjointSimulation(const SolverOptions& opt, const BatchView& bv, FwdHistory<NX>& hs, double* dj, int n_)
         : o(opt), b(bv), hist(hs), dJydx(dj), n(n_) {}
     AB_HD bool full() const { return o.reporting != 2; }
-    AB_HD static double nan_() { return ab_nan(); }
+    AB_HD static double nan_() {
+#ifdef __CUDA_ARCH__
+        return __longlong_as_double(0x7ff8000000000000LL);
+#else
+        return NAN;
+#endif
+    }
     AB_HD double& dj(int it, int r) { return dJydx[((size_t)it * NX + r) * hist.stride]; }
 
-    AB_HD void load() {
+    AB_NI void load() {
         for (int i = 0; i < M::NP; ++i) {
             const double v = b.p[(size_t)n * M::NP + i];
             const int sc = b.pscale ? b.pscale[i] : AB_PSCALE_NONE;
@@ -618,7 +632,7 @@ struct AdjointSimulation {
     }
 
     // observables, objective, dJ/dx and the direct parameter dependence of the objective at output time it
-    AB_HD void datapoint(int it, const double* xs, const int* counters) {
+    AB_NI void datapoint(int it, const double* xs, const int* counters) {
         const int nt = b.nt;
         const double t = b.ts[it];
         double spl[AdjCond<M>::NSPLV], y[NY], sig[NY], dJy[NY], dJs[NY];

@@ -110,6 +110,12 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
         return AB_E_UNSUPPORTED;
     }
     if (!(o->rtol >= 0) || !(o->atol >= 0)) { g_err = "negative tolerance"; return AB_E_BAD_ARGUMENT; }
+    if (o->sensi_meth != 0 && o->sensi_meth != 1 && o->sensi_meth != 2) { g_err = "unknown SensitivityMethod"; return AB_E_BAD_ARGUMENT; }
+    if (o->sensi >= 1 && o->sensi_meth == 2 && (b->k_preeq || b->t_presim || o->posteq || o->reinit_states_sim || o->reinit_states_presim ||
+                                                  o->x_nonneg != 0ull || o->maxtime > 0.0)) {
+        g_err = "adjoint sensitivity analysis: plain simulations only (no pre-/post-equilibration, presimulation, re-initialisation, non-negativity, time limit)";
+        return AB_E_UNSUPPORTED;
+    }
     if (o->nmaxevent < 0) { g_err = "nmaxevent must be non-negative"; return AB_E_BAD_ARGUMENT; }
     if (b->k_presim && !b->t_presim) { g_err = "k_presim without t_presim"; return AB_E_BAD_ARGUMENT; }
     if ((b->k_preeq || o->posteq) && (!(o->rtol_ss >= 0) || !(o->atol_ss >= 0) || !(o->rtol_ss_sensi >= 0) || !(o->atol_ss_sensi >= 0))) {
@@ -126,6 +132,12 @@ static int check_args(const ab_solver_options* o, const ab_batch* b) {
         return AB_E_BAD_ARGUMENT;
     }
     return AB_OK;
+}
+
+// forward sensitivities (or none): the model's own kernels; SensitivityMethod::adjoint: adjoint.cuh
+static int launch_solve(const ModelEntry* e, const ab_solver_options& o, const ab_batch& b, int* queue, const Progress& pg, cudaStream_t st) {
+    if (o.sensi >= 1 && o.sensi_meth == 2 && b.nplist > 0) return launch_adjoint(e->name, o, b, queue, pg, st);
+    return e->launch(o, b, queue, pg, st);
 }
 
 }  // namespace amici_b200
@@ -194,7 +206,7 @@ int ab_solve_device(const char* model, const ab_solver_options* opt, const ab_ba
         if (b->sz && npl) AB_CUDA(cudaMemsetAsync(b->sz, 0, sizeof(double) * nzs * npl, st));
         if (b->srz && npl) AB_CUDA(cudaMemsetAsync(b->srz, 0, sizeof(double) * nzs * npl, st));
     }
-    return e->launch(*opt, *b, work_counter, Progress{}, st);
+    return launch_solve(e, *opt, *b, work_counter, Progress{}, st);
 }
 
 int ab_reduce_objective(int N, int nplist, const int* status, const double* llh, const double* sllh, double* out, void* stream) {
@@ -448,7 +460,7 @@ int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch
         pg.host_flags = dev_flags;
         pg.chunk = (int)chunk;
         cudaEventRecord(w.ev0, w.compute);
-        rc = e->launch(*opt, db, (int*)w.dev[S_QUEUE], pg, w.compute);
+        rc = launch_solve(e, *opt, db, (int*)w.dev[S_QUEUE], pg, w.compute);
         cudaEventRecord(w.ev1, w.compute);
         if (rc != AB_OK) break;
         volatile int* flags = w.host_flags;

@@ -39,6 +39,9 @@ struct ModelEntry {
     int (*launch)(const ab_solver_options&, const ab_batch&, int*, const Progress&, cudaStream_t);
 };
 
+// SensitivityMethod::adjoint (adjoint.cuh), dispatched by model name; defined in tu/adjoint.cu
+int launch_adjoint(const char* model, const ab_solver_options&, const ab_batch&, int* queue_head, const Progress&, cudaStream_t);
+
 // defined in tu/<model>.cu
 ModelEntry entry_jakstat_adjoint();
 ModelEntry entry_steadystate();

@@ -1,0 +1,8 @@
+// instantiates the adjoint kernel (adjoint.cuh) for model 'robertson_ode'.
+#include "../adjoint_launch.cuh"
+#include "../models/robertson_ode.cuh"
+namespace amici_b200 {
+int launch_adjoint_robertson_ode(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
+    return launch_adjoint_model<models::robertson_ode>(o, b, queue_head, pg, st);
+}
+}  // namespace amici_b200

@@ -1,0 +1,8 @@
+// instantiates the adjoint kernel (adjoint.cuh) for model 'spline_modes'.
+#include "../adjoint_launch.cuh"
+#include "../models/spline_modes.cuh"
+namespace amici_b200 {
+int launch_adjoint_spline_modes(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
+    return launch_adjoint_model<models::spline_modes>(o, b, queue_head, pg, st);
+}
+}  // namespace amici_b200

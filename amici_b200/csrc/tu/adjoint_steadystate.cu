@@ -1,0 +1,8 @@
+// instantiates the adjoint kernel (adjoint.cuh) for model 'steadystate'.
+#include "../adjoint_launch.cuh"
+#include "../models/steadystate.cuh"
+namespace amici_b200 {
+int launch_adjoint_steadystate(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
+    return launch_adjoint_model<models::steadystate>(o, b, queue_head, pg, st);
+}
+}  // namespace amici_b200

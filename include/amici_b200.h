@@ -67,6 +67,11 @@ typedef struct ab_solver_options {
     /* Solver::set_max_time in seconds, 0 = unlimited (reference src/solver.cpp:1050-1069, src/solver_cvodes.cpp:1177): a condition
        whose integration has run longer than this on the device ends with status AMICI_MAX_TIME_EXCEEDED (-1000). */
     double maxtime;
+    /* SensitivityMethod with sensi = 1: 0 or 1 forward (default), 2 adjoint (reference include/amici/defines.h:160-165,
+       src/backwardproblem.cpp).  Adjoint: event-free lane-group models, plain simulations (no pre-/post-equilibration or
+       presimulation); reports llh, sllh and the sensitivity-free fields, sx / sy / sres / FIM are not computed (NaN). */
+    int sensi_meth;
+    int reserved_;
 } ab_solver_options;
 
 /* One batch of N conditions (replaces std::vector<ExpData*> in, std::vector<ReturnData> out). */

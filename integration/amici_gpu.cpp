@@ -28,8 +28,8 @@ ab_solver_options solver_options(Solver const& solver, Model const& model) {
     std::memset(&o, 0, sizeof o);
     if (solver.get_sensitivity_order() > SensitivityOrder::first)
         throw AmiException("amici_b200: second-order sensitivities are not implemented");
-    if (solver.get_sensitivity_order() == SensitivityOrder::first && solver.get_sensitivity_method() != SensitivityMethod::forward)
-        throw AmiException("amici_b200: only forward sensitivity analysis is implemented");
+    if (solver.get_sensitivity_order() == SensitivityOrder::first && solver.get_sensitivity_method() == SensitivityMethod::none)
+        throw AmiException("amici_b200: sensitivity order first needs a sensitivity method");
     o.rtol = solver.get_relative_tolerance();
     o.atol = solver.get_absolute_tolerance();
     o.rtol_fsa = solver.get_relative_tolerance_fsa();
@@ -38,6 +38,7 @@ ab_solver_options solver_options(Solver const& solver, Model const& model) {
     o.hmax_inv = solver.get_max_step_size() > 0 ? 1.0 / solver.get_max_step_size() : 0.0;
     o.sensi = solver.get_sensitivity_order() == SensitivityOrder::first ? 1 : 0;
     o.ism = static_cast<int>(solver.get_internal_sensitivity_method());
+    o.sensi_meth = static_cast<int>(solver.get_sensitivity_method());   // 1 forward, 2 adjoint (plain simulations of event-free models)
     o.maxsteps = static_cast<int>(solver.get_max_steps());
     o.stldet = solver.get_stability_limit_flag() ? 1 : 0;
     o.max_nonlin_iters = solver.get_max_nonlin_iters();

@@ -102,6 +102,7 @@ extern "C" int emul_run_flat(const char* model, const SolverOptions* o, const Ba
 }
 
 extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchView* b) {
+    if (o->sensi >= 1 && o->sensi_meth == 2 && b->nplist > 0) return emul_run_adjoint(model, o, b);   // as engine.cu launch_solve
     std::string m(model);
     if (m == "jakstat_adjoint") return run_model<models::jakstat_adjoint>(o, b);
     if (m == "steadystate") return run_model<models::steadystate>(o, b);

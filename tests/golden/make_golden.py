@@ -158,7 +158,18 @@ def make_events_phases():
     make("neuron", np.linspace(0, 50, 11), N=6, seed=34, tag="_presim", presim=True, kscale=(1.0, 1.0), spread=8, nmaxevent=10)
 
 
+def make_adjoint():
+    # SensitivityMethod::adjoint (sensi_meth = 2): sllh by the backward problem; klu / dense / truth + spread runs
+    make("jakstat_adjoint", np.arange(0, 61, 5.0), N=6, seed=41, tag="_asa", sensi_meth=2, spread=8)
+    make("jakstat_adjoint", np.arange(0, 61, 5.0), N=4, seed=42, pscale=[2] * 17, tag="_asa_log10", sensi_meth=2, spread=8)
+    make("steadystate", np.linspace(0, 10, 11), N=6, seed=43, tag="_asa", sensi_meth=2, spread=8)
+    make("robertson_ode", 4.0 * 10.0 ** np.arange(-6, 7), N=6, seed=44, tag="_asa", sensi_meth=2, spread=8, kscale=(1.0, 1.0))
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["adjoint"]:
+        make_adjoint()
+        sys.exit(0)
     if sys.argv[1:] == ["events_phases"]:
         make_events_phases()
         sys.exit(0)
@@ -194,3 +205,4 @@ if __name__ == "__main__":
          ss_mode=2, ss_sensi_mode=0)
     make_presim()
     make_events_phases()
+    make_adjoint()

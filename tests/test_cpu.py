@@ -111,6 +111,27 @@ def test_emulation_state_reinitialisation_matches_golden(built):
     np.testing.assert_array_equal(out["sx0"][:, :, 1], out["sx_ss"][:, :, 1])
 
 
+ADJOINT_FIELDS = ["x", "y", "llh", "chi2", "sigmay", "res", "x0", "sllh"]
+
+
+@pytest.mark.parametrize("fixture", ["jakstat_adjoint_asa", "jakstat_adjoint_asa_log10", "steadystate_asa", "robertson_ode_asa"])
+def test_emulation_adjoint_matches_golden(built, fixture):
+    """SensitivityMethod::adjoint (amici_b200/csrc/adjoint.cuh; reference src/backwardproblem.cpp, cvodea.c): the gradient from the
+    backward problem over the stored forward history against the reference's own adjoint runs (KLU / dense / tight-tolerance
+    truth / perturbed-tolerance spread), and against the FORWARD-sensitivity gradient of the same engine: two independent paths
+    to the same numbers."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    model = fixture.split("_asa")[0]
+    out = run_emul(_emul(built), model, g)
+    np.testing.assert_array_equal(out["status"], g["klu_status"])
+    parity.check_against_golden(out, g, fields=ADJOINT_FIELDS)
+    fsa = run_emul(_emul(built), model, g, sensi_meth=1)
+    scale = np.abs(fsa["sllh"]).max(axis=1, keepdims=True)
+    np.testing.assert_allclose(out["sllh"], fsa["sllh"], rtol=1e-4, atol=1e-6 * scale.max())
+    # the forward pass integrates the state alone: fewer steps than with 17 sensitivity columns in the error test
+    assert (out["numsteps"][:, -1] <= fsa["numsteps"][:, -1]).all()
+
+
 @pytest.mark.parametrize("fixture", ["events_preeq", "events_presim", "events_preeq_presim", "neuron_presim"])
 def test_emulation_event_models_preequilibration_presimulation(built, fixture):
     """Models with events through a pre-equilibration (EventHandlingSimulator::run_steady_state, reference

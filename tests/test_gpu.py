@@ -28,6 +28,8 @@ def _run(model_name, g, sensi=True, ts=None, **solver_kw):
         m.set_steady_state_sensitivity_mode(int(g["opt_ss_sensi_mode"]))
     if "opt_nmaxevent" in g:
         m.set_n_max_event(int(g["opt_nmaxevent"]))
+    if "opt_sensi_meth" in g and "sensitivity_method" not in solver_kw:
+        s.set_sensitivity_method(int(g["opt_sensi_meth"]))
     batch = ab.ExpDataBatch(m.get_timepoints(), g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], pscale=g["pscale"],
                             k_preeq=g["k_preeq"] if "k_preeq" in g else None, mz=g["mz"] if "mz" in g else None,
                             k_presim=g["k_presim"] if "k_presim" in g else None,
@@ -1252,3 +1254,54 @@ def test_cuda_state_non_negativity_and_max_time():
     # the reference reads its clock at every 500th right-hand side of the calling thread, so short solves can slip through there
     r = RefModel("steadystate").run(g["ts"], p[:16], k[:16], x0=x0[:16], maxtime=1e-9, fields=["status", "x"])
     assert np.isin(r["status"], (0, -1000)).all() and (r["status"] == -1000).any()
+
+
+ADJOINT_FIELDS = ["x", "y", "llh", "chi2", "sigmay", "res", "x0", "sllh"]
+
+
+@pytest.mark.parametrize("fixture", ["jakstat_adjoint_asa", "jakstat_adjoint_asa_log10", "steadystate_asa", "robertson_ode_asa"])
+def test_cuda_adjoint_matches_golden(fixture):
+    """SensitivityMethod::adjoint through the C ABI (adjoint_kernel, one thread per condition) against the reference's adjoint
+    runs; the fields the adjoint method does not compute are NaN like the reference's empty vectors."""
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    res = _run(fixture.split("_asa")[0], g)
+    np.testing.assert_array_equal(res["status"], g["klu_status"])
+    parity.check_against_golden(res.fields, g, fields=ADJOINT_FIELDS)
+    assert np.isnan(res["sx"]).all() and np.isnan(res["sy"]).all()
+
+
+def test_cuda_adjoint_batch_vs_reference_and_forward():
+    """4096 JAK-STAT conditions: the adjoint gradient against the compiled reference's adjoint runs on a 96-condition subset
+    (parity protocol on quantiles) and against the forward-sensitivity gradient of the engine on the whole batch."""
+    import amici_b200 as ab
+    from oracle import refsim
+    N = 4096
+    m = ab.get_model("jakstat_adjoint")
+    ts = np.arange(0, 61, 5.0)
+    m.set_timepoints(ts)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    rng = np.random.default_rng(51)
+    p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.normal(0, 0.1, (N, m.np()))
+    k = np.tile(m.get_fixed_parameters(), (N, 1))
+    s0 = m.create_solver()
+    s0.set_relative_tolerance(parity.RTOL)
+    s0.set_absolute_tolerance(parity.ATOL)
+    y0 = ab.run_simulations(m, s0, ab.ExpDataBatch(ts, p, k))["y"]
+    my = y0 + 0.1 * rng.standard_normal(y0.shape)
+    batch = ab.ExpDataBatch(ts, p, k, my=my, sigmay=np.full_like(my, 0.1))
+    fsa = ab.run_simulations(m, s, batch)
+    s.set_sensitivity_method(ab.SensitivityMethod.adjoint)
+    asa = ab.run_simulations(m, s, batch)
+    assert (asa["status"] == 0).all() and (fsa["status"] == 0).all()
+    np.testing.assert_allclose(asa["llh"], fsa["llh"], rtol=1e-9)
+    scale = np.abs(fsa["sllh"]).max(axis=1, keepdims=True)
+    assert (np.abs(asa["sllh"] - fsa["sllh"]) <= 1e-4 * np.abs(fsa["sllh"]) + 1e-6 * scale).all()
+    if not refsim.available("jakstat_adjoint"):
+        return
+    idx = rng.choice(N, 96, replace=False)
+    ref = refsim.RefModel("jakstat_adjoint")
+    sub = {f: np.asarray(asa[f])[idx] for f in ("status", "llh", "sllh", "x")}
+    _check_live(sub, ref, ts, p[idx], k[idx], ["llh", "sllh", "x"], my=my[idx], sigmay=np.full_like(my[idx], 0.1), sensi_meth=2)
