@@ -2,6 +2,8 @@
 // (tu/adjoint_<model>.cu), dispatch by model name in tu/adjoint.cu.
 #ifndef AMICI_B200_ADJOINT_LAUNCH_CUH
 #define AMICI_B200_ADJOINT_LAUNCH_CUH
+#include <cstdlib>
+
 #include "adjoint.cuh"
 #include "block_launch.cuh"   // pooled, event-guarded device workspaces
 
@@ -50,6 +52,8 @@ int launch_adjoint_model(const ab_solver_options& o, const ab_batch& b, int* que
         last_error() = "adjoint kernel does not fit on an SM";
         return AB_E_CUDA;
     }
+    if (const char* capenv = std::getenv("AMICI_B200_ADJ_BLOCKS_PER_SM"))   // experiments (profiles/r02_adjoint.md)
+        if (std::atoi(capenv) > 0 && std::atoi(capenv) < per_sm) per_sm = std::atoi(capenv);
     // one history slot per thread: every internal step of the forward pass is a data point, so a slot holds maxsteps + 2 points
     // (AMICI calls CVodeAdjInit with steps = maxsteps: one check-point interval, no re-integration)
     const int cap = o.maxsteps + 2;

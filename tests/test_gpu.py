@@ -1296,7 +1296,7 @@ def test_cuda_adjoint_batch_vs_reference_and_forward():
     s.set_sensitivity_method(ab.SensitivityMethod.adjoint)
     asa = ab.run_simulations(m, s, batch)
     assert (asa["status"] == 0).all() and (fsa["status"] == 0).all()
-    np.testing.assert_allclose(asa["llh"], fsa["llh"], rtol=1e-9)
+    np.testing.assert_allclose(asa["llh"], fsa["llh"], rtol=1e-6)   # two integrations at rtol 1e-8 with different step sequences
     scale = np.abs(fsa["sllh"]).max(axis=1, keepdims=True)
     assert (np.abs(asa["sllh"] - fsa["sllh"]) <= 1e-4 * np.abs(fsa["sllh"]) + 1e-6 * scale).all()
     if not refsim.available("jakstat_adjoint"):
