@@ -132,6 +132,22 @@ def test_emulation_adjoint_matches_golden(built, fixture):
     assert (out["numsteps"][:, -1] <= fsa["numsteps"][:, -1]).all()
 
 
+def test_emulation_adjoint_failure_semantics_match_reference(built):
+    """A forward pass that runs out of steps ends the adjoint simulation like the reference's: status AMICI_TOO_MUCH_WORK, outputs
+    NaN from the failing timepoint on, llh and the whole gradient NaN (no backward pass)."""
+    from oracle import refsim
+    if not refsim.available("jakstat_adjoint"):
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, "jakstat_adjoint_asa.npz"))
+    ref = refsim.RefModel("jakstat_adjoint")
+    r = ref.run(g["ts"], g["p"], g["k"], my=g["my"], sigmay=g["sigmay_in"], sensi_order=1, sensi_meth=2, maxsteps=300)
+    out = run_emul(_emul(built), "jakstat_adjoint", g, maxsteps=300)
+    np.testing.assert_array_equal(out["status"], r["status"])
+    assert (out["status"] == -1).all()
+    for f in ("llh", "sllh", "x", "y"):
+        np.testing.assert_array_equal(np.isnan(out[f]), np.isnan(r[f]), err_msg=f)
+
+
 @pytest.mark.parametrize("fixture", ["events_preeq", "events_presim", "events_preeq_presim", "neuron_presim"])
 def test_emulation_event_models_preequilibration_presimulation(built, fixture):
     """Models with events through a pre-equilibration (EventHandlingSimulator::run_steady_state, reference
