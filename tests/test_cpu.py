@@ -126,8 +126,8 @@ def test_emulation_adjoint_matches_golden(built, fixture):
     np.testing.assert_array_equal(out["status"], g["klu_status"])
     parity.check_against_golden(out, g, fields=ADJOINT_FIELDS)
     fsa = run_emul(_emul(built), model, g, sensi_meth=1)
-    scale = np.abs(fsa["sllh"]).max(axis=1, keepdims=True)
-    np.testing.assert_allclose(out["sllh"], fsa["sllh"], rtol=1e-4, atol=1e-6 * scale.max())
+    scale = np.abs(fsa["sllh"]).max(axis=1, keepdims=True)   # relative to the largest entry: single entries are cancellations
+    assert (np.abs(out["sllh"] - fsa["sllh"]) <= 1e-4 * scale).all()
     # the forward pass integrates the state alone: fewer steps than with 17 sensitivity columns in the error test
     assert (out["numsteps"][:, -1] <= fsa["numsteps"][:, -1]).all()
 
