@@ -75,6 +75,12 @@ CONFIGS = {
     "jakstat": dict(model="jakstat_adjoint", ref="jakstat_adjoint", n=65536, seed=2, ts=np.arange(0, 61, 5.0), sensi=True, inputs=_wl_jakstat,
                     label="model_jakstat_adjoint_py FSA 17 params", metric="ODE solves/sec w/ forward sens (JAK-STAT)",
                     flops=dict(n=9, s=17, zJ=18, Ff=45, FJ=12, FP=30, ny=3), baseline_config=1),
+    # the same workload with SensitivityMethod::adjoint on both arms (amici_b200/csrc/adjoint.cuh; reference src/backwardproblem.cpp):
+    # llh + gradient only (the adjoint method has no sx / sy), likelihood reporting
+    "jakstat_asa": dict(model="jakstat_adjoint", ref="jakstat_adjoint", n=65536, seed=2, ts=np.arange(0, 61, 5.0), sensi=True, inputs=_wl_jakstat,
+                        label="model_jakstat_adjoint_py ADJOINT sensitivities 17 params, likelihood reporting",
+                        metric="ODE solves/sec w/ adjoint sens (JAK-STAT)", adjoint=True, likelihood_only=True,
+                        flops=dict(n=9, s=17, zJ=18, Ff=45, FJ=12, FP=30, ny=3), baseline_config=1),
     "robertson": dict(model="robertson_ode", ref="robertson_ode", n=4096, seed=1, ts=np.concatenate([[0.0], 4 * np.logspace(-6, 6, 50)]),
                       sensi=False, inputs=_wl_robertson, label="Robertson (ODE form, CVODES-equivalent BDF) forward simulation, log-uniform draws",
                       metric="ODE solves/sec, forward simulation (Robertson)", flops=dict(n=3, s=0, zJ=7, Ff=12, FJ=8, FP=0, ny=3),
@@ -158,6 +164,9 @@ def reference_kwargs(c):
         kw["nmaxevent"] = c["nmaxevent"]
     if c.get("likelihood_only"):
         kw["reporting"] = 1
+    if c.get("adjoint"):
+        kw["sensi_meth"] = 2
+        kw["reporting"] = 2   # RDataReporting::likelihood
     return kw
 
 
@@ -244,6 +253,8 @@ def build_engine_objects(ab, c, n, rank):
             s.set_newton_max_steps(50)
         if c.get("likelihood_only"):
             s.set_return_data_reporting_mode(ab.RDataReporting.likelihood)
+        if c.get("adjoint") and sensi:
+            s.set_sensitivity_method(ab.SensitivityMethod.adjoint)
         if os.environ.get("BENCH_NO_STLDET"):   # experiment only: what cvBDFStab costs (not the reference's default)
             s.set_stability_limit_flag(False)
         return s
