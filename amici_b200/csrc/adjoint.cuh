@@ -107,19 +107,28 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     // cvCompleteStep / cvRescale / cvPredict / cvRestore in one pass per row (see Bdf::history_pass)
     template <int PRED, int N>
     AB_NI void pass(double (&z)[LMAX][N], const double* ac, int n, const bool cmpl, const bool resc) {
-        double f[QMAX + 1];
+        double f[QMAX + 1], lc[QMAX + 1];
         f[0] = 1.0;
-        for (int j = 1; j <= QMAX; ++j) f[j] = f[j - 1] * eta;
+        AB_UNROLL
+        for (int j = 1; j <= QMAX; ++j) f[j] = resc ? f[j - 1] * eta : 1.0;
+        AB_UNROLL
+        for (int j = 0; j <= QMAX; ++j) lc[j] = (cmpl && j <= q && j < LMAX) ? l[j < LMAX ? j : 0] : 0.0;
+        AB_NOUNROLL
         for (int r = 0; r < n; ++r) {
             double v[QMAX + 1];
-            for (int j = 0; j <= QMAX; ++j) v[j] = (j <= 1 || j <= q) ? z[j][r] : 0.0;
-            if (cmpl)
-                for (int j = 0; j <= q; ++j) v[j] += l[j] * ac[r];
-            if (resc)
-                for (int j = 1; j <= QMAX; ++j) v[j] *= f[j];
-            if (PRED != 0)
-                for (int k = 1; k <= QMAX; ++k)
+            const double a = cmpl ? ac[r] : 0.0;
+            AB_UNROLL
+            for (int j = 0; j <= QMAX; ++j) v[j] = ((j <= 1 || j <= q) ? z[j][r] : 0.0) + lc[j] * a;
+            AB_UNROLL
+            for (int j = 1; j <= QMAX; ++j) v[j] *= f[j];
+            if (PRED != 0) {
+                AB_UNROLL
+                for (int k = 1; k <= QMAX; ++k) {
+                    AB_UNROLL
                     for (int j = QMAX; j >= k; --j) v[j - 1] = PRED > 0 ? v[j - 1] + v[j] : v[j - 1] - v[j];
+                }
+            }
+            AB_UNROLL
             for (int j = 0; j <= QMAX; ++j)
                 if (j <= 1 || j <= q) z[j][r] = v[j];
         }
@@ -295,11 +304,14 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         return ok ? AB_SUCCESS : NLS_CONV_RECVR;
     }
     AB_HD void lu_solve(double* b) const {
+        AB_NOUNROLL
         for (int kk = 0; kk < NX; ++kk) {
             const int pr = piv[kk];
             if (pr != kk) { const double tmp = b[kk]; b[kk] = b[pr]; b[pr] = tmp; }
-            for (int r = kk + 1; r < NX; ++r) b[r] -= lu[r][kk] * b[kk];
+            const double bk = b[kk];
+            for (int r = kk + 1; r < NX; ++r) b[r] -= lu[r][kk] * bk;
         }
+        AB_NOUNROLL
         for (int r = NX - 1; r >= 0; --r) {
             double s = b[r];
             for (int c = r + 1; c < NX; ++c) s -= lu[r][c] * b[c];
@@ -456,22 +468,41 @@ struct FwdHistory {
             if (order > QMAX) order = QMAX;
             if (indx < order) base += order - indx;
             if (base > np - 1) { order -= base - (np - 1); base = np - 1; }
-            for (int j = 0; j <= order; ++j) {
-                T[j] = tp(base - j);
-                for (int r = 0; r < NX; ++r) Y[j][r] = y[((size_t)(base - j) * NX + r) * stride];
+            // the divided differences row by row in registers; the factors dt / (T[j] - T[j - i]) are the same for every row
+            double Tl[QMAX + 1], fac[QMAX + 1][QMAX + 1];
+            AB_UNROLL
+            for (int j = 0; j <= QMAX; ++j) Tl[j] = j <= order ? tp(base - j) : 0.0;
+            AB_UNROLL
+            for (int j = 0; j <= QMAX; ++j) T[j] = Tl[j];
+            AB_UNROLL
+            for (int i = 1; i <= QMAX; ++i) {
+                AB_UNROLL
+                for (int j = QMAX; j >= i; --j) fac[i][j] = j <= order ? dt / (Tl[j] - Tl[j - i]) : 0.0;
             }
-            for (int i = 1; i <= order; ++i)
-                for (int j = order; j >= i; --j) {
-                    const double factor = dt / (T[j] - T[j - i]);
-                    for (int r = 0; r < NX; ++r) Y[j][r] = factor * Y[j][r] - factor * Y[j - 1][r];
+            AB_NOUNROLL
+            for (int r = 0; r < NX; ++r) {
+                double yy[QMAX + 1];
+                AB_UNROLL
+                for (int j = 0; j <= QMAX; ++j) yy[j] = j <= order ? y[((size_t)(base - j) * NX + r) * stride] : 0.0;
+                AB_UNROLL
+                for (int i = 1; i <= QMAX; ++i) {
+                    AB_UNROLL
+                    for (int j = QMAX; j >= i; --j)
+                        if (j <= order) yy[j] = fac[i][j] * yy[j] - fac[i][j] * yy[j - 1];
                 }
+                AB_UNROLL
+                for (int j = 0; j <= QMAX; ++j) Y[j][r] = yy[j];
+            }
         }
         double cv[QMAX + 1];
         cv[0] = 1.0;
-        for (int i = 0; i < order; ++i) cv[i + 1] = cv[i] * (tt - T[i]) / dt;
+        AB_UNROLL
+        for (int i = 0; i < QMAX; ++i) cv[i + 1] = i < order ? cv[i] * (tt - T[i]) / dt : 0.0;
+        AB_UNROLL
         for (int r = 0; r < NX; ++r) {
             double v = 0.0;
-            for (int i = 0; i <= order; ++i) v += cv[i] * Y[i][r];
+            AB_UNROLL
+            for (int i = 0; i <= QMAX; ++i) v += cv[i] * Y[i][r];   // rows above the order hold zeros
             out[r] = v;
         }
         return true;
@@ -499,6 +530,13 @@ struct AdjCond {
         for (int is = 0; is < M::NSPL; ++is) {
             const SplineLoc loc = spline_locate<M>(is, t);
             const double u = spline_eval_at<M, M::NP + 1>(spl, is, 1 + il, loc, false);
+            sv[is] = spline_is_log<M>(is) ? u * v[is] : u;
+        }
+    }
+    // the same with the interval located once for all parameters
+    AB_HD void spline_sens_at(const SplineLoc* loc, int il, const double* v, double* sv) const {
+        for (int is = 0; is < M::NSPL; ++is) {
+            const double u = spline_eval_at<M, M::NP + 1>(spl, is, 1 + il, loc[is], false);
             sv[is] = spline_is_log<M>(is) ? u * v[is] : u;
         }
     }
@@ -569,9 +607,11 @@ struct BwdProblem {
     AB_NI bool quad(double t, const double* xB, double* fq) {
         if (!at(t)) return false;
         bool ok = true;
+        SplineLoc loc[AdjCond<M>::NSPLV];
+        for (int is = 0; is < M::NSPL; ++is) loc[is] = spline_locate<M>(is, t);
         for (int il = 0; il < c.nplist; ++il) {
             double sspl[AdjCond<M>::NSPLV], col[NX];
-            c.spline_sens(t, il, spl, sspl);
+            c.spline_sens_at(loc, il, spl, sspl);
             M::dxdotdp(c.plist[il], t, x, c.p, c.k, c.h, spl, sspl, col);
             double s = 0.0;
             for (int r = 0; r < NX; ++r) s += col[r] * xB[r];
