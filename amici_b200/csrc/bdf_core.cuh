@@ -37,6 +37,13 @@ using BatchView = ab_batch;
 // per-trajectory shared storage
 // ---------------------------------------------------------------------------------------------
 constexpr int QMAX = 5;           // BDF_Q_MAX
+#ifndef AB_SLDET_SVC
+#define AB_SLDET_SVC 0            // 1: lane groups of 16 hand cvSLdet to a service warp of their block (launch.cuh sldet_service)
+#endif
+#ifndef AB_SLDET_SVC_SLEEP
+#define AB_SLDET_SVC_SLEEP 32
+#endif
+enum : int { SVC_REQ = 0x10000, SVC_ANS = 0x20000 };
 constexpr int LMAX = QMAX + 1;
 
 template <class M, int NCOLS>
@@ -60,6 +67,7 @@ struct TrajShared {
     double sld[40];                  // exchange area of bdf_sldet_xchg (ten rounds of up to four values)
     unsigned long long xpos_mask;    // Model::set_state_is_non_negative as a bit set (AB_FULL builds; 0 = off)
     long long t_start_ns;            // device clock when the condition started (Solver::set_max_time; AB_FULL builds)
+    int svc;                         // mailbox of the block's cvSLdet service warp (AB_SLDET_SVC, launch.cuh): request / result word
     int piv[M::NX];
     int ip_of_col[NCOLS];            // parameter index of an integrated column (-1: state / unused)
     int il_of_col[NCOLS];            // its position in plist
@@ -1633,10 +1641,32 @@ struct Bdf : BdfControl<Bdf<M, G, C, REINIT>, typename Layout<M, G, C>::Shared> 
         // aligned warps).  Smaller groups share their warp with other conditions: every collective of the lane version is then
         // a divergence check plus a serialised region per group, and the serial form is both fewer instructions and less code.
         if (G == 32) return bdf_sldet_lanes<G>(g, S.ssdat, Base::ss_head, q);
+#if AB_SLDET_SVC && !defined(AB_SLDET_SVC_LOCAL)
+        if (G == 16) return sldet_remote();
+#endif
         if (G >= 4) return bdf_sldet_xchg<G>(g, S.ssdat, S.sld, Base::ss_head, q);
 #endif
         return Base::sldet_serial();
     }
+#if AB_SLDET_SVC && defined(__CUDA_ARCH__)
+    // cvSLdet evaluated by the block's service warp (sldet_service, launch.cuh): the ring buffer already lives in this group's
+    // shared-memory slice (bdf_stab's group barrier has made the newest entry visible), so the request is one word
+    // (order, ring head) and the answer one word (return code).  The 5.5 KB routine leaves the step loop of the sixteen
+    // conditions of the block: one instruction stream evaluates it for all of them.
+    __device__ int sldet_remote() const {
+        volatile int* svc = &S.svc;
+        if (g.lane == 0) {
+            __threadfence_block();
+            *svc = SVC_REQ | (q << 8) | Base::ss_head;
+        }
+        g.sync();   // the request is posted before any lane polls (an older answer is overwritten)
+        int v;
+        while (((v = *svc) & SVC_ANS) == 0)
+            if (AB_SLDET_SVC_SLEEP > 0) __nanosleep(AB_SLDET_SVC_SLEEP);
+        g.sync();
+        return (v & 0xff) - 16;
+    }
+#endif
     AB_HD void gsync() const { g.sync(); }
     AB_HD bool leader() const { return g.lane == 0; }
     AB_HD bool rhs_to_zn1(double scale) { return cold_rhs_store<M, G, C>(S, ncols, tn, 0.0, scale, 1); }

@@ -60,6 +60,45 @@ __device__ __forceinline__ void report_done(const Progress& pg, const Group<G>& 
     }
 }
 
+// cvSLdet service warps (AB_SLDET_SVC; the last warpgroup of a block of 16-lane groups): four lanes serve one lane group, the
+// three orders in three of them (bdf_sldet_xchg).  A group posts (order, ring head) in its slice's mailbox (Bdf::sldet_remote),
+// the ring buffer itself is read from the group's slice, the return code goes back through the same word.
+template <class Shared, int NG>
+__device__ void sldet_service(Shared* slices, volatile int* done, const int st) {
+    constexpr int NGW = (NG + 3) / 4;            // lane groups served by one of the four warps
+    const int w = st >> 5, wl = st & 31, sub = wl >> 2;
+    const int gi = w * NGW + sub;
+    const bool mine = sub < NGW && gi < NG;
+#if defined(AB_SLDET_SVC_LOCAL) && AB_SLDET_SVC_LOCAL == 2
+    return;
+#endif
+    Group<4> g4;
+    Shared& S = slices[mine ? gi : 0];
+    volatile int* svc = &S.svc;
+    for (;;) {
+        int v = 0;
+        if (mine && g4.lane == 0) v = *svc;
+        v = __shfl_sync(0xffffffffu, v, wl & ~3);
+        const bool req = (v & SVC_REQ) != 0;
+        if (__any_sync(0xffffffffu, req)) {
+            // the groups of this warp that have a request pending evaluate the routine together
+            if (req) {
+                __threadfence_block();
+                const int rc = bdf_sldet_xchg<4>(g4, S.ssdat, S.sld, v & 0xff, (v >> 8) & 0xff);
+                g4.sync();
+                if (g4.lane == 0) *svc = SVC_ANS | (rc + 16);
+            }
+            __syncwarp();
+        } else {
+            if (*done >= NG) break;
+            if (AB_SLDET_SVC_SLEEP > 0) __nanosleep(AB_SLDET_SVC_SLEEP);
+        }
+    }
+}
+
+template <int G>
+struct SldetSvc { static constexpr bool value = AB_SLDET_SVC && G == 16; };
+
 template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_solver_options o, const ab_batch b, int* queue_head, const Progress pg) {
     using Sim = Simulation<M, G, C, PREEQ>;
@@ -68,12 +107,28 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
     // [0, SYNC_BYTES): step-alignment generations of the block's warps (Bdf::step_sync_*), then one slice per group
     int* sync_pos = reinterpret_cast<int*>(smem_raw);
     Shared* slices = reinterpret_cast<Shared*>(smem_raw + SYNC_BYTES);
-    Shared& S = slices[threadIdx.x / G];
+    constexpr bool SVC = SldetSvc<G>::value;
+    constexpr int CT = SVC ? THREADS - 128 : THREADS;   // threads that integrate
+    Shared& S = slices[(SVC && threadIdx.x >= CT) ? 0 : threadIdx.x / G];
     Group<G> g;
     constexpr bool STEP_SYNC = AB_STEP_SYNC && (G == 32 || (G == 16 && AB_STEP_SYNC_G16)) && THREADS > 32;
+    static_assert(!(SVC && STEP_SYNC), "the service warp does not take part in the step alignment");
     if (STEP_SYNC) {
         if (threadIdx.x < THREADS / 32) sync_pos[threadIdx.x] = 0x7fffffff;
         __syncthreads();
+    }
+    if (SVC) {
+        if (threadIdx.x < CT / G) slices[threadIdx.x].svc = 0;
+        if (threadIdx.x == 0) sync_pos[31] = 0;
+        __syncthreads();
+        // register file per scheduler: two integrating warps + one service warp; the service warpgroup hands most of its
+        // share to the integrating ones (launch bound 168 -> 232 + 232 + 40)
+        if (threadIdx.x >= CT) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+            sldet_service<Shared, CT / G>(slices, sync_pos + 31, (int)threadIdx.x - CT);
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     }
     for (;;) {
         int n = 0;
@@ -89,6 +144,10 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
         sim.run();
         g.sync();
         report_done<G>(pg, g, b.N, n);
+    }
+    if (SVC) {
+        g.sync();
+        if (g.lane == 0) atomicAdd(sync_pos + 31, 1);
     }
 }
 
@@ -131,7 +190,7 @@ struct Config {
 #endif
     // One warp per condition (G == 32), or two (G == 16): all resident warps of an SM in ONE block, so that they can align
     // their steps (Bdf::step_sync_*, WarpAlign).  Otherwise small blocks: shared-memory granularity decides occupancy.
-    static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : (G == 16) ? AB_THREADS_G16 : AB_THREADS_SMALL;
+    static constexpr int THREADS = (G == 32) ? AB_THREADS_G32 : (G == 16) ? AB_THREADS_G16 + (AB_SLDET_SVC ? 128 : 0) : AB_THREADS_SMALL;
     static constexpr int MINBLOCKS = (G >= 16) ? 1 : AB_MINBLOCKS;  // register cap = 65536 / (MINBLOCKS * THREADS)
 };
 // compaction pays when it halves the lane group (JAK-STAT: 18 columns in 32 lanes -> 11 in 16, two conditions per warp)
@@ -151,7 +210,7 @@ template <class M, int G, int C, int THREADS, int MINBLOCKS, bool PREEQ>
 int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
     using Sim = Simulation<M, G, C, PREEQ>;
     auto kern = select_kernel<M, G, C, THREADS, MINBLOCKS, PREEQ>();
-    constexpr int groups = THREADS / G;
+    constexpr int groups = (SldetSvc<G>::value ? THREADS - 128 : THREADS) / G;
     const size_t smem = SYNC_BYTES + sizeof(typename Sim::Shared) * groups;
     int dev = 0, sms = 0;
     AB_CUDA(cudaGetDevice(&dev));
