@@ -299,7 +299,8 @@ def emit_model(spec: ModelSpec) -> str:
     out = []
     A = out.append
     guard = f"AMICI_B200_MODEL_{spec.name.upper()}_CUH"
-    A(f"// GENERATED by amici_b200/codegen/emitter.py from amici_b200/codegen/models.py::{spec.name} — do not edit.")
+    origin = spec.doc if spec.doc.startswith("from ") else f"from amici_b200/codegen/models.py::{spec.name}"
+    A(f"// GENERATED by amici_b200/codegen/emitter.py {origin} — do not edit.")
     A(f"// Device functions of model '{spec.name}' for the batched BDF engine (see emitter.py for the")
     A("// mapping onto the reference's generated <fn>_<model>.cpp files).")
     A(f"#ifndef {guard}\n#define {guard}\n#include \"../hermite_spline.cuh\"\n#include \"../model_common.cuh\"\nnamespace amici_b200 {{ namespace models {{\n")

@@ -58,6 +58,8 @@ ModelEntry entry_ev_pw_simple();
 ModelEntry entry_ev_ddeltax();
 ModelEntry entry_ev_pw_semi();
 ModelEntry entry_ev_pw_state();
+// emitted from the reference's symbolic model object through codegen/de_export.py (no ModelSpec in codegen/models.py)
+ModelEntry entry_dirac();
 
 }  // namespace amici_b200
 #endif

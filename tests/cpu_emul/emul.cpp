@@ -18,6 +18,7 @@
 #include "../../amici_b200/csrc/models/ev_ddeltax.cuh"
 #include "../../amici_b200/csrc/models/ev_pw_semi.cuh"
 #include "../../amici_b200/csrc/models/ev_pw_state.cuh"
+#include "../../amici_b200/csrc/models/dirac.cuh"
 
 #include <memory>
 #include <string>
@@ -116,6 +117,7 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "ev_ddeltax") return run_model<models::ev_ddeltax>(o, b);
     if (m == "ev_pw_semi") return run_model<models::ev_pw_semi>(o, b);
     if (m == "ev_pw_state") return run_model<models::ev_pw_state>(o, b);
+    if (m == "dirac") return run_model<models::dirac>(o, b);
     return -2;
 }
 

@@ -158,6 +158,12 @@ def make_events_phases():
     make("neuron", np.linspace(0, 50, 11), N=6, seed=34, tag="_presim", presim=True, kscale=(1.0, 1.0), spread=8, nmaxevent=10)
 
 
+def make_dirac():
+    # the shipped Dirac model (bolus at the parameter-dependent time p2): its engine header is emitted from the reference's
+    # symbolic model object (tests/golden/make_de_models.py)
+    make("dirac", np.linspace(0, 3, 16), N=6, seed=51, spread=8)
+
+
 def make_adjoint():
     # SensitivityMethod::adjoint (sensi_meth = 2): sllh by the backward problem; klu / dense / truth + spread runs
     make("jakstat_adjoint", np.arange(0, 61, 5.0), N=6, seed=41, tag="_asa", sensi_meth=2, spread=8)
@@ -169,6 +175,9 @@ def make_adjoint():
 if __name__ == "__main__":
     if sys.argv[1:] == ["adjoint"]:
         make_adjoint()
+        sys.exit(0)
+    if sys.argv[1:] == ["dirac"]:
+        make_dirac()
         sys.exit(0)
     if sys.argv[1:] == ["events_phases"]:
         make_events_phases()
@@ -206,3 +215,4 @@ if __name__ == "__main__":
     make_presim()
     make_events_phases()
     make_adjoint()
+    make_dirac()

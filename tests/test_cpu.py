@@ -12,7 +12,8 @@ from tests import parity
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 MODEL_DIMS = {"robertson_ode": dict(nx=3, np=3, nk=1, ny=3), "jakstat_adjoint": dict(nx=9, np=17, nk=2, ny=3), "steadystate": dict(nx=3, np=5, nk=4, ny=3),
-              "events": dict(nx=3, np=4, nk=4, ny=1, nz=2), "neuron": dict(nx=2, np=4, nk=2, ny=1, nz=1)}
+              "events": dict(nx=3, np=4, nk=4, ny=1, nz=2), "neuron": dict(nx=2, np=4, nk=2, ny=1, nz=1),
+              "dirac": dict(nx=2, np=4, nk=0, ny=1)}
 
 
 def _emul(built):
@@ -647,3 +648,110 @@ def test_emulation_state_non_negativity_matches_reference(built):
         outs[nn] = out["x"].copy()
     assert (outs[0b101][:, 0, 0] == 0.0).all() and (outs[0][:, 0, 0] < 0.0).all()
     assert np.abs(outs[0b101][:, 1] - outs[0][:, 1]).max() > 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the CUDA emitter behind the reference's code exporter (amici_b200/codegen/de_export.py)
+# ---------------------------------------------------------------------------------------------------------------------------
+_SHIPPED = {"jakstat_adjoint": "model_jakstat_adjoint_py", "steadystate": "model_steadystate_py", "events": "model_events_py",
+            "neuron": "model_neuron_py"}
+
+
+def _need_ref_python():
+    from tests import ref_python
+    if not ref_python.available():
+        pytest.skip("the reference's Python package is not present (needs /root/reference)")
+    ref_python.load()
+
+
+def _same_but_provenance(a: str, b: str) -> bool:
+    return a.splitlines()[1:] == b.splitlines()[1:]
+
+
+@pytest.mark.parametrize("name", sorted(_SHIPPED))
+def test_de_export_hook_in_the_reference_exporter(name, tmp_path):
+    """The shipped test model as the reference's own `DEModel` (tests/de_models.py) goes through the reference's UNMODIFIED
+    `DEExporter` with the CUDA hook installed.  (a) Every model-function source the exporter writes is byte-identical to the
+    shipped `/root/reference/models/model_<name>_py/<fn>.cpp` — the very sources the compiled oracle is built from — so the
+    `DEModel` is the reference's model; (b) the `<name>.cuh` the hook writes next to them is the committed engine header.
+    Hence the parity tests of these models compare two outputs of ONE symbolic model object."""
+    _need_ref_python()
+    from amici.exporters.sundials.de_export import DEExporter
+    from amici_b200.codegen import de_export
+    from tests import de_models
+    de_export.install_hook(DEExporter)
+    ref_name = _SHIPPED[name]
+    exporter = DEExporter(de_models.build(name), output_dir=str(tmp_path / ref_name), model_name=ref_name)
+    exporter._prepare_model_folder()
+    exporter._generate_c_code()
+    out = str(exporter.model_path)
+    shipped = os.path.join("/root/reference/models", ref_name)
+    checked = 0
+    for f in sorted(os.listdir(out)):
+        # the model class files embed the commit hash of the generating checkout, CMakeLists.txt the package version
+        if not os.path.isfile(os.path.join(out, f)) or not os.path.exists(os.path.join(shipped, f)) or \
+                f in ("CMakeLists.txt", ref_name + ".cpp", ref_name + ".h"):
+            continue
+        assert open(os.path.join(out, f)).read() == open(os.path.join(shipped, f)).read(), f
+        checked += 1
+    assert checked >= 30 and os.path.exists(os.path.join(out, "xdot.cpp")) and os.path.exists(os.path.join(out, "dxdotdp_explicit.cpp"))
+    committed = open(os.path.join(ROOT, "amici_b200", "csrc", "models", name + ".cuh")).read()
+    # the hook names the header after the exporter's model name; the engine registers the short name
+    emitted = de_export.emit_cuda_source(exporter.model, name)
+    assert _same_but_provenance(emitted, committed)
+    hooked = open(os.path.join(out, ref_name + ".cuh")).read()
+    assert hooked.replace(ref_name.upper(), name.upper()).replace(ref_name, name).splitlines()[1:] == committed.splitlines()[1:]
+
+
+def test_de_export_inlines_expressions_and_orders_them():
+    """a model written with intermediate expressions `w` (one depending on another, given out of order) emits the same header"""
+    _need_ref_python()
+    from amici_b200.codegen import de_export
+    from tests import de_models
+    committed = open(os.path.join(ROOT, "amici_b200", "csrc", "models", "steadystate.cuh")).read()
+    assert _same_but_provenance(de_export.emit_cuda_source(de_models.build("steadystate_with_expressions"), "steadystate"), committed)
+    assert _same_but_provenance(de_export.emit_cuda_source(de_models.build("robertson_ode"), "robertson_ode"),
+                                open(os.path.join(ROOT, "amici_b200", "csrc", "models", "robertson_ode.cuh")).read())
+
+
+def test_de_export_refuses_what_the_engine_does_not_implement():
+    _need_ref_python()
+    import sympy as sp
+    from amici._symbolic import de_model_components as C
+    from amici.importers.utils import symbol_with_assumptions as S
+    from amici_b200.codegen import de_export
+    from tests import de_models
+    m = de_models.steadystate()
+    a = S("a1")
+    m.add_component(C.AlgebraicState(a, "a1", sp.Float(1.0)))
+    m.add_component(C.AlgebraicEquation(S("ae1"), a - 1))
+    with pytest.raises(de_export.CudaEmitterError, match="algebraic"):
+        de_export.modelspec_from_de_model(m, "x")
+    m = de_models.steadystate()
+    y, my, sig = S("obs_l"), S("mobs_l"), S("sigma_obs_l")
+    m.add_component(C.Observable(y, "obs_l", S("x1"), my))
+    m.add_component(C.SigmaY(sig, str(sig), sp.Float(1.0)))
+    m.add_component(C.LogLikelihoodY(S("Jobs_l"), "Jobs_l", sp.log(2 * sig) + sp.Abs(y - my) / sig))   # Laplace noise
+    with pytest.raises(de_export.CudaEmitterError, match="Gaussian"):
+        de_export.modelspec_from_de_model(m, "x")
+
+
+def test_de_export_only_models_are_reproduced():
+    """`dirac.cuh` has no ModelSpec in codegen/models.py: it is what de_export emits from the reference's `DEModel` (tests/golden/make_de_models.py)"""
+    _need_ref_python()
+    from tests.golden import make_de_models
+    for name in make_de_models.DE_ONLY:
+        assert make_de_models.source(name) == open(os.path.join(ROOT, "amici_b200", "csrc", "models", name + ".cuh")).read(), name
+
+
+def test_emulation_dirac_matches_golden(built):
+    """The shipped Dirac model (bolus at the parameter-dependent time p2), engine header emitted from the reference's symbolic
+    model object through the DEExporter back end, against the compiled reference built from the shipped C++ of the same model."""
+    g = np.load(os.path.join(GOLD, "dirac.npz"))
+    out = run_emul(_emul(built), "dirac", g)
+    parity.check_against_golden(out, g)
+    assert abs(out["numsteps"][:, -1] / g["klu_numsteps"][:, -1] - 1).max() < 0.1
+    # closed form before / after the bolus: x1 = 0 for t < p2, exp(-p1 (t - p2)) afterwards
+    p, ts = g["p"], g["ts"]
+    want = np.where(ts[None, :] < p[:, 1:2], 0.0, np.exp(-p[:, 0:1] * (ts[None, :] - p[:, 1:2])))
+    np.testing.assert_allclose(out["x"][:, :, 0], want, rtol=1e-6, atol=1e-9)

@@ -1308,3 +1308,37 @@ def test_cuda_adjoint_batch_vs_reference_and_forward():
     ref = refsim.RefModel("jakstat_adjoint")
     sub = {f: np.asarray(asa[f])[idx] for f in ("status", "llh", "sllh", "x")}
     _check_live(sub, ref, ts, p[idx], k[idx], ["llh", "sllh", "x"], my=my[idx], sigmay=np.full_like(my[idx], 0.1), sensi_meth=2)
+
+
+@pytest.mark.gpu
+def test_cuda_dirac_emitted_from_the_reference_model_object():
+    """`dirac.cuh` has no hand-written model description — it is emitted from the reference's own `DEModel` of
+    model_dirac_py by the DEExporter back end (amici_b200/codegen/de_export.py, tests/golden/make_de_models.py), while the oracle
+    is the shipped C++ of the same model.  Golden fixture, then 2048 parameter samples (the bolus time p2 varies per sample):
+    status codes identical to the compiled reference on a 128-condition subset, floats by the parity protocol, and the closed
+    form x1(t) = [t >= p2] exp(-p1 (t - p2)) on the whole batch."""
+    import amici_b200 as ab
+    from oracle import refsim
+    g = np.load(os.path.join(GOLD, "dirac.npz"))
+    res = _run("dirac", g)
+    parity.check_against_golden(res.fields, g)
+    N = 2048
+    m = ab.get_model("dirac")
+    ts = np.linspace(0, 3, 16)
+    m.set_timepoints(ts)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    rng = np.random.default_rng(61)
+    p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.normal(0, 0.1, (N, m.np()))
+    k = np.zeros((N, 0))
+    out = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
+    assert (out["status"] == 0).all()
+    want = np.where(ts[None, :] < p[:, 1:2], 0.0, np.exp(-p[:, 0:1] * (ts[None, :] - p[:, 1:2])))
+    np.testing.assert_allclose(out["x"][:, :, 0], want, rtol=1e-6, atol=1e-9)
+    if not refsim.available("dirac"):
+        return
+    idx = rng.choice(N, 128, replace=False)
+    sub = {f: np.asarray(out[f])[idx] for f in ("status", "x", "sx", "y", "sy")}
+    _check_live(sub, refsim.RefModel("dirac"), ts, p[idx], k[idx], ["x", "sx", "y", "sy"])
