@@ -13,7 +13,7 @@ The reference turns a symbolic model (`DEModel`, reference python/sdist/amici/_s
 
 The module is duck-typed: it imports nothing from the reference, so it also runs where the reference's package is not
 installed (the objects only have to offer the accessors named above).  What the engine does not implement is refused with
-`CudaEmitterError` instead of being emitted wrongly: algebraic states (DAE models), conservation laws, observable
+`CudaEmitterError` instead of being emitted wrongly: DAE models with events or splines, conservation laws, observable
 transformations other than `lin`, noise models other than the Gaussian one, event priorities.
 
 Tests: tests/test_cpu.py::test_de_export_* build the reference's `DEModel` for the shipped test models with the reference's own
@@ -100,8 +100,11 @@ def _spline(spl, inline, de_model):
 
 
 def modelspec_from_de_model(de_model, name: str, doc: str = "") -> em.ModelSpec:
-    if list(de_model.algebraic_states()) or list(de_model.algebraic_equations()):
-        raise CudaEmitterError("algebraic states (DAE models) are not supported by the batched BDF engine")
+    alg_states, alg_eqs = list(de_model.algebraic_states()), list(de_model.algebraic_equations())
+    if len(alg_states) != len(alg_eqs):
+        raise CudaEmitterError("one algebraic equation per algebraic state expected")
+    if alg_states and (list(de_model.events()) or getattr(de_model, "_splines", [])):
+        raise CudaEmitterError("DAE models with events or splines are not supported (csrc/dae.cuh)")
     if de_model.num_cons_law() > 0 or list(de_model.conservation_laws()):
         raise CudaEmitterError("conservation laws (x_rdata != x_solver) are not supported: import with compute_conservation_laws=False")
     inline = _inline_expressions(de_model)
@@ -110,7 +113,7 @@ def modelspec_from_de_model(de_model, name: str, doc: str = "") -> em.ModelSpec:
         return _retime(sp.sympify(v).subs(inline), de_model)
 
     xs = list(de_model.differential_states())
-    states = [s.get_sym() for s in xs]
+    states = [s.get_sym() for s in xs] + [s.get_sym() for s in alg_states]
     ps, ks = list(de_model.free_parameters()), list(de_model.fixed_parameters())
     obs, sigmas = list(de_model.observables()), list(de_model.sigma_ys())
     if len(sigmas) != len(obs):
@@ -148,7 +151,9 @@ def modelspec_from_de_model(de_model, name: str, doc: str = "") -> em.ModelSpec:
     splines = [_spline(s, inline, de_model) for s in getattr(de_model, "_splines", [])]
     return em.ModelSpec(
         name=name, states=states, params=[p.get_sym() for p in ps], fixed=[k.get_sym() for k in ks],
-        xdot=[ex(s.get_dt()) for s in xs], x0=[ex(s.get_val()) for s in xs], observables=observables,
+        xdot=[ex(s.get_dt()) for s in xs] + [ex(e.get_val()) for e in alg_eqs],
+        x0=[ex(s.get_val()) for s in xs] + [ex(s.get_val()) for s in alg_states], observables=observables,
+        algebraic=[False] * len(xs) + [True] * len(alg_states) if alg_states else (),
         p_nominal=[float(p.get_val()) for p in ps], k_nominal=[float(k.get_val()) for k in ks], splines=splines,
         events=events, event_observables=event_observables, heavisides=heavisides, doc=doc)
 

@@ -110,6 +110,8 @@ class ModelSpec:
     events: Sequence[Event] = ()
     event_observables: Sequence[EventObservable] = ()
     heavisides: dict | None = None         # {symbol used in xdot/y: event index}: value of h[event index]
+    algebraic: Sequence[bool] = ()         # DAE models: True for algebraic states; their `xdot` entry is the algebraic equation
+                                           # 0 = g(t, x, p, k) (mass matrix diag(not algebraic), reference src/model_dae.cpp)
     doc: str = ""
 
 
@@ -347,6 +349,9 @@ def emit_model(spec: ModelSpec) -> str:
                 static_mask |= 1 << ip
     A(f"    static constexpr unsigned long long SX_STATIC_MASK = {static_mask:#x}ull;   // parameters with sx == 0 identically")
     A(f"    static constexpr int NP_DYN = {npar - bin(static_mask).count('1')};   // parameters that need an integrated sensitivity column")
+    alg_mask = sum(1 << i for i, a in enumerate(spec.algebraic) if a)
+    if alg_mask:
+        A(f"    static constexpr unsigned long long ALG_MASK = {alg_mask:#x}ull;   // algebraic states (DAE): row r of xdot is 0 = g_r")
     A("    AB_HD static void x0(const double* p, const double* k, double* x0) {")
     A("        (void)p; (void)k;")
     A(W.body([(f"x0[{i}]", x0[i]) for i in range(nx)]).rstrip("\n"))

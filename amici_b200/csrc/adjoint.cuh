@@ -34,6 +34,12 @@ AB_HD bool adj_too_close(double cur_t, double t_next) {
 #define AB_NI __attribute__((noinline))
 #endif
 
+// DAE models (emitter: ALG_MASK): bit r set = state r is algebraic, row r of the right-hand side is 0 = g_r(t, x)
+template <class M, class = void>
+struct alg_mask_of { static constexpr unsigned long long value = 0ull; };
+template <class M>
+struct alg_mask_of<M, decltype((void)M::ALG_MASK)> { static constexpr unsigned long long value = M::ALG_MASK; };
+
 struct ScalarShared {
     double ctl[16];
     double ssdat[5][8];
@@ -42,11 +48,17 @@ struct ScalarShared {
 // ---------------------------------------------------------------------------------------------------------------------
 // BdfControl's vector primitives for one thread and NX ODE rows + NQ quadrature rows.  P supplies
 //   bool rhs(t, y, ydot)   void jac(t, y, J[NX][NX])   bool quad(t, y, qdot)   double rtol, atol, rtolq, atolq
+// P::ALG_MASK != 0 (dae.cuh): index-1 DAE M y' = f(t, y) with M = diag(state is differential).  The BDF formula and the step
+// control are unchanged; the corrector solves M (rl1 zn[1] + acor) - gamma f(zn[0] + acor) = 0 with the Newton matrix
+// M - gamma J (algebraic rows divided by gamma: 0 = g with the matrix row -dg/dx), the algebraic states carry no derivative at the start and are left out of every norm of the local error test
+// and the order / step-size selection (IDASetSuppressAlg(true), reference src/solver.cpp:252) but not of the Newton convergence test.
 // ---------------------------------------------------------------------------------------------------------------------
 template <class P>
 struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     static constexpr int NX = P::NX, NQ = P::NQ, NQA = P::NQ > 0 ? P::NQ : 1;
     static constexpr bool ROOTS = false, EVENTS = true, STG = false, QUAD = P::NQ > 0, HIST = P::HIST;
+    static constexpr unsigned long long AM = P::ALG_MASK;
+    AB_HD static bool alg(int r) { return AM != 0ull && ((AM >> r) & 1ull) != 0ull; }
     using Base = BdfControl<ScalarBdf<P>, ScalarShared>;
     using Base::o; using Base::tn; using Base::h; using Base::l; using Base::tq; using Base::rl1; using Base::gamma;
     using Base::gammap; using Base::gamrat; using Base::crate; using Base::delp; using Base::acnrm; using Base::q; using Base::L;
@@ -57,6 +69,8 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     P& prob;
     int nq;   // active quadrature rows (nplist)
     double zn[LMAX][NX], acor[NX], ewt[NX];
+    double ewt_d[AM != 0ull ? NX : 1];   // DAE: ewt with zeros for the algebraic states (error test, order selection)
+    AB_HD const double* we() const { return AM != 0ull ? ewt_d : ewt; }
     double znQ[LMAX][NQA], acorQ[NQA], ewtQ[NQA];
     double lu[NX][NX], savedJ[NX][NX];
     int piv[NX];
@@ -83,23 +97,25 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         return n > 0 ? sqrt(s / n) : 0.0;
     }
     AB_HD double wrms_max_zn(int j, const double lj = 0.0) const {
-        double m = wrms2(zn[j], pending ? acor : nullptr, lj, ewt, NX);
+        double m = wrms2(zn[j], pending ? acor : nullptr, lj, we(), NX);
         if (QUAD) m = upd(m, wrms2(znQ[j], pending ? acorQ : nullptr, lj, ewtQ, nq));   // cvQuadUpdateNorm
         return m;
     }
     AB_HD double wrms_max_up(const double cquot) const {
-        double m = wrms2(acor, zn[QMAX], -cquot, ewt, NX);
+        double m = wrms2(acor, zn[QMAX], -cquot, we(), NX);
         if (QUAD) m = upd(m, wrms2(acorQ, znQ[QMAX], -cquot, ewtQ, nq));
         return m;
     }
     AB_NI void set_ewt() {
         for (int r = 0; r < NX; ++r) ewt[r] = 1.0 / (prob.rtol * fabs(pending ? zn[0][r] + acor[r] : zn[0][r]) + prob.atol);
+        if (AM != 0ull)
+            for (int r = 0; r < NX; ++r) ewt_d[r] = alg(r) ? 0.0 : ewt[r];
         if (QUAD)
             for (int r = 0; r < nq; ++r) ewtQ[r] = 1.0 / (prob.rtolq * fabs(pending ? znQ[0][r] + acorQ[r] : znQ[0][r]) + prob.atolq);
     }
     AB_HD void stab_sums(const double lq, const double lqm1, double& s1, double& s2) const {
         for (int r = 0; r < NX; ++r) {
-            const double a = (zn[q][r] + lq * acor[r]) * ewt[r], b = (zn[q - 1][r] + lqm1 * acor[r]) * ewt[r];
+            const double a = (zn[q][r] + lq * acor[r]) * we()[r], b = (zn[q - 1][r] + lqm1 * acor[r]) * we()[r];
             s1 += a * a;
             s2 += b * b;
         }
@@ -187,7 +203,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     AB_HD bool rhs_to_zn1(double scale) {
         double f[NX];
         bool ok = prob.rhs(tn, zn[0], f);
-        for (int r = 0; r < NX; ++r) zn[1][r] = scale * f[r];
+        for (int r = 0; r < NX; ++r) zn[1][r] = alg(r) ? 0.0 : scale * f[r];
         if (QUAD) {
             double fq[NQA];
             ok = prob.quad(tn, zn[0], fq) && ok;
@@ -205,7 +221,8 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         if (tdist < 2.0 * tround) return AB_TOO_CLOSE;
         const double hlb = 100.0 * tround;
         double hub_inv = 0.0;
-        for (int r = 0; r < NX; ++r) hub_inv = upd(hub_inv, fabs(zn[1][r]) / (0.1 * fabs(zn[0][r]) + 1.0 / ewt[r]));
+        for (int r = 0; r < NX; ++r)
+            if (!alg(r)) hub_inv = upd(hub_inv, fabs(zn[1][r]) / (0.1 * fabs(zn[0][r]) + 1.0 / ewt[r]));
         if (QUAD)
             for (int r = 0; r < nq; ++r) hub_inv = upd(hub_inv, fabs(znQ[1][r]) / (0.1 * fabs(znQ[0][r]) + 1.0 / ewtQ[r]));
         double hub = 0.1 * tdist;
@@ -228,7 +245,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
                 if (QUAD) ok = prob.quad(tn + hgs, y, fq) && ok;
                 if (ok) {
                     for (int r = 0; r < NX; ++r) f[r] = (1.0 / hgs) * f[r] - (1.0 / hgs) * zn[1][r];
-                    yddnrm = wrms2(f, nullptr, 0.0, ewt, NX);
+                    yddnrm = wrms2(f, nullptr, 0.0, we(), NX);
                     if (QUAD) {
                         for (int r = 0; r < nq; ++r) fq[r] = (1.0 / hgs) * fq[r] - (1.0 / hgs) * znQ[1][r];
                         yddnrm = upd(yddnrm, wrms2(fq, nullptr, 0.0, ewtQ, nq));
@@ -277,7 +294,8 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         for (int r = 0; r < NX; ++r)
             for (int c = 0; c < NX; ++c) {
                 ok = ok && isfinite(savedJ[r][c]);
-                lu[r][c] = (r == c ? 1.0 : 0.0) - gamma * savedJ[r][c];
+                // algebraic rows without gamma (as in IDAS, where cj only multiplies dF/dy'): a stale gamma does not touch them
+                lu[r][c] = alg(r) ? -savedJ[r][c] : (r == c ? 1.0 : 0.0) - gamma * savedJ[r][c];
             }
         for (int kk = 0; kk < NX && ok; ++kk) {
             int pr = kk;
@@ -339,7 +357,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
                     if (ret != AB_SUCCESS) break;
                 }
                 nni++;
-                for (int r = 0; r < NX; ++r) delta[r] = -(rl1 * zn[1][r] + acor[r] - gamma * delta[r]);
+                for (int r = 0; r < NX; ++r) delta[r] = alg(r) ? delta[r] : -(rl1 * zn[1][r] + acor[r] - gamma * delta[r]);
                 lu_solve(delta);
                 const double sc = (gamrat != 1.0) ? 2.0 / (1.0 + gamrat) : 1.0;
                 for (int r = 0; r < NX; ++r) {
@@ -350,7 +368,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
                 if (m > 0) crate = ab_max(0.3 * crate, Del / delp);
                 const double dcon = Del * ab_min(1.0, crate) / tq[4];
                 if (dcon <= 1.0) {
-                    acnrm = (m == 0) ? Del : wrms2(acor, nullptr, 0.0, ewt, NX);
+                    acnrm = (m == 0 && AM == 0ull) ? Del : wrms2(acor, nullptr, 0.0, we(), NX);
                     jcur = false;
                     return AB_SUCCESS;
                 }
@@ -546,6 +564,7 @@ template <class M>
 struct FwdProblem {
     static constexpr int NX = M::NX, NQ = 0;
     static constexpr bool HIST = true;
+    static constexpr unsigned long long ALG_MASK = 0ull;
     const AdjCond<M>& c;
     FwdHistory<M::NX>& hist;
     double rtol, atol, rtolq, atolq;
@@ -572,6 +591,7 @@ template <class M>
 struct BwdProblem {
     static constexpr int NX = M::NX, NQ = M::NP > 0 ? M::NP : 1;
     static constexpr bool HIST = false;
+    static constexpr unsigned long long ALG_MASK = 0ull;
     const AdjCond<M>& c;
     FwdHistory<M::NX>& hist;
     double rtol, atol, rtolq, atolq;

@@ -1,0 +1,149 @@
+// dae.cuh — index-1 DAE models: forward simulation of M x' = f(t, x, p, k) with the mass matrix
+// M = diag(state is differential), the form of the reference's DAE models (reference src/model_dae.cpp:31-64: residual
+// F = xdot(x) - M dx, Jacobian dF/dx - cj M; the shipped model_robertson_py: two differential states and the algebraic
+// equation 0 = x1 + x2 + x3 - 1).  ONE THREAD PER CONDITION on ScalarBdf (adjoint.cuh).
+//
+// The reference integrates these models with IDAS (variable-coefficient BDF in fixed-leading-coefficient form,
+// src/solver_idas.cpp).  This path is NOT a restatement of IDAS: it is the engine's CVODES-equivalent Nordsieck BDF with a
+// mass matrix — same formulas of order 1..5, same step-size / order control (BdfControl), corrector
+// M (rl1 zn[1] + acor) - gamma f = 0 with the Newton matrix M - gamma J, algebraic states left out of the error test as
+// AMICI configures IDAS (IDASetSuppressAlg(true), src/solver.cpp:252).  Step sequences therefore differ from IDAS'; results
+// are compared with the reference's IDAS runs by the parity protocol (error against a tight-tolerance IDAS run no larger
+// than IDAS' own, tests/parity.py).
+//
+//   consistent start   IDACalcIC(IDA_YA_YDP_INIT) (src/solver_idas.cpp:831-840): differential states fixed, Newton on the
+//                      algebraic equations for the algebraic states at t0 (the shipped Robertson model starts from the
+//                      inconsistent x3 = 0); the reported x0 is the corrected one, as in the reference's ReturnData
+//   outputs            x, y, sigmay, llh, res, chi2, counters, status (AdjointSimulation's forward outputs)
+//   not implemented    sensitivities, events, pre-/post-equilibration of DAE models: refused by the launch
+#ifndef AMICI_B200_DAE_CUH
+#define AMICI_B200_DAE_CUH
+#include "adjoint.cuh"
+
+namespace amici_b200 {
+
+template <class M>
+struct DaeProblem {
+    static constexpr int NX = M::NX, NQ = 0;
+    static constexpr bool HIST = false;
+    static constexpr unsigned long long ALG_MASK = alg_mask_of<M>::value;
+    const AdjCond<M>& c;
+    double rtol, atol, rtolq, atolq;
+    AB_NI bool rhs(double t, const double* y, double* f) const {
+        double spl[AdjCond<M>::NSPLV];
+        c.splines(t, spl);
+        M::xdot(t, y, c.p, c.k, c.h, spl, f);
+        bool ok = true;
+        for (int r = 0; r < NX; ++r) ok = ok && isfinite(f[r]);
+        return ok;
+    }
+    AB_HD void jac(double t, const double* y, double (&J)[NX][NX]) const {
+        double spl[AdjCond<M>::NSPLV], Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
+        c.splines(t, spl);
+        M::jac(t, y, c.p, c.k, c.h, spl, Jv);
+        M::jac_to_dense(Jv, &J[0][0]);
+    }
+    AB_HD bool quad(double, const double*, double*) const { return true; }
+    AB_HD void store_point(double, int, const double*, const double*) {}
+};
+
+template <class M>
+struct DaeSimulation {
+    static constexpr int NX = M::NX;
+    static constexpr unsigned long long AM = alg_mask_of<M>::value;
+    const SolverOptions& o;
+    const BatchView& b;
+    int n;
+    AB_HD DaeSimulation(const SolverOptions& opt, const BatchView& bv, int n_) : o(opt), b(bv), n(n_) {}
+    AB_HD static bool alg(int r) { return ((AM >> r) & 1ull) != 0ull; }
+
+    // IDACalcIC(IDA_YA_YDP_INIT): Newton on the algebraic rows for the algebraic states, differential states fixed.
+    // Convergence as IDAS tests it (idas_ic.c: WRMS norm of the update below epiccon = 0.01 * 0.33), at most 10 iterations
+    // with a fresh Jacobian each (maxnj x maxnit of IDAS are 4 x 10).
+    AB_NI bool consistent_start(const DaeProblem<M>& dp, double t0, double* x) const {
+        int ia[NX], na = 0;
+        for (int r = 0; r < NX; ++r)
+            if (alg(r)) ia[na++] = r;
+        if (na == 0) return true;
+        for (int it = 0; it < 10; ++it) {
+            double f[NX], J[NX][NX], A[NX][NX], rhs[NX];
+            if (!dp.rhs(t0, x, f)) return false;
+            dp.jac(t0, x, J);
+            for (int i = 0; i < na; ++i) {
+                rhs[i] = -f[ia[i]];
+                for (int j = 0; j < na; ++j) A[i][j] = J[ia[i]][ia[j]];
+            }
+            for (int kk = 0; kk < na; ++kk) {   // Gaussian elimination with partial pivoting on the na x na block
+                int pr = kk;
+                for (int r = kk + 1; r < na; ++r)
+                    if (fabs(A[r][kk]) > fabs(A[pr][kk])) pr = r;
+                if (A[pr][kk] == 0.0) return false;
+                if (pr != kk) {
+                    for (int cc = 0; cc < na; ++cc) { const double tmp = A[kk][cc]; A[kk][cc] = A[pr][cc]; A[pr][cc] = tmp; }
+                    const double tmp = rhs[kk]; rhs[kk] = rhs[pr]; rhs[pr] = tmp;
+                }
+                for (int r = kk + 1; r < na; ++r) {
+                    const double mlt = A[r][kk] / A[kk][kk];
+                    for (int cc = kk; cc < na; ++cc) A[r][cc] -= mlt * A[kk][cc];
+                    rhs[r] -= mlt * rhs[kk];
+                }
+            }
+            double nrm = 0.0;
+            for (int i = na - 1; i >= 0; --i) {
+                double s = rhs[i];
+                for (int j = i + 1; j < na; ++j) s -= A[i][j] * rhs[j];
+                rhs[i] = s / A[i][i];
+            }
+            for (int i = 0; i < na; ++i) {
+                const double w = 1.0 / (dp.rtol * fabs(x[ia[i]]) + dp.atol);
+                nrm += rhs[i] * w * rhs[i] * w;
+                x[ia[i]] += rhs[i];
+            }
+            if (!(nrm == nrm)) return false;
+            if (sqrt(nrm / NX) <= 0.0033) return true;
+        }
+        return false;
+    }
+
+    AB_HD void run() {
+        FwdHistory<NX> none;
+        none.t = none.y = nullptr;
+        none.ord = nullptr;
+        none.stride = 1;
+        none.cap = 0;
+        AdjointSimulation<M> out(o, b, none, nullptr, n);   // load / datapoint / invalidate / finish of the forward outputs
+        out.load();
+        out.c.nplist = 0;
+        const int nt = b.nt;
+        DaeProblem<M> dp{out.c, o.rtol, o.atol, o.rtol, o.atol};
+        ScalarBdf<DaeProblem<M>> bdf(dp, o, 0);
+        double x0[NX];
+        M::x0(out.c.p, out.c.k, x0);
+        if (b.x0_in)
+            for (int r = 0; r < NX; ++r) x0[r] = b.x0_in[(size_t)n * NX + r];
+        int status = AB_SUCCESS, it = 0;
+        if (!consistent_start(dp, o.t0, x0)) status = AB_IC_FAIL;
+        if (b.x0 && out.full())
+            for (int r = 0; r < NX; ++r) b.x0[(size_t)n * NX + r] = x0[r];
+        if (status == AB_SUCCESS) {
+            for (int r = 0; r < NX; ++r) bdf.zn[0][r] = x0[r];
+            bdf.init(o.t0);
+            double t = o.t0;
+            for (; it < nt; ++it) {
+                const double tout = b.ts[it];
+                if (tout > o.t0 && t < tout && !adj_too_close(t, tout)) {
+                    const int flag = bdf.solve_to(tout, false);
+                    if (flag < 0) { status = flag; break; }
+                    t = bdf.tretlast;
+                }
+                const int counters[5] = {bdf.nst, bdf.nfe, bdf.netf, bdf.ncfn, bdf.qu};
+                out.datapoint(it, bdf.zn[0], counters);
+            }
+        }
+        if (status != AB_SUCCESS) out.invalidate(it);
+        out.finish(status);
+    }
+};
+
+}  // namespace amici_b200
+#endif

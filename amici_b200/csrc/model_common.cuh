@@ -42,6 +42,7 @@ enum : int {
     AB_FIRST_RHSFUNC_ERR = -9,
     AB_REPTD_RHSFUNC_ERR = -10,
     AB_UNREC_RHSFUNC_ERR = -11,
+    AB_IC_FAIL = -14,              // IDA_NO_RECOVERY: no consistent initial values (IDACalcIC, DAE models)
     AB_ILL_INPUT = -22,
     AB_REPTD_SRHSFUNC_ERR = -43,   // CV_REPTD_SRHSFUNC_ERR (staggered corrector)
     AB_TOO_CLOSE = -27,

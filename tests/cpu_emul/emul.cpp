@@ -19,6 +19,8 @@
 #include "../../amici_b200/csrc/models/ev_pw_semi.cuh"
 #include "../../amici_b200/csrc/models/ev_pw_state.cuh"
 #include "../../amici_b200/csrc/models/dirac.cuh"
+#include "../../amici_b200/csrc/models/robertson.cuh"
+#include "../../amici_b200/csrc/dae.cuh"
 
 #include <memory>
 #include <string>
@@ -118,6 +120,14 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "ev_pw_semi") return run_model<models::ev_pw_semi>(o, b);
     if (m == "ev_pw_state") return run_model<models::ev_pw_state>(o, b);
     if (m == "dirac") return run_model<models::dirac>(o, b);
+    if (m == "robertson") {   // DAE path (dae.cuh): forward simulation only, as launch_dae_model
+        if (o->sensi >= 1 && b->nplist > 0) return -3;
+        for (int n = 0; n < b->N; ++n) {
+            auto sim = std::make_unique<DaeSimulation<models::robertson>>(*o, *b, n);
+            sim->run();
+        }
+        return 0;
+    }
     return -2;
 }
 

@@ -157,6 +157,21 @@ def dirac():
     return m
 
 
+def robertson():
+    """the shipped index-1 DAE form of Robertson's problem (python/sdist/amici/testing/models.py:90-134; models/model_robertson_py):
+    two differential states, the algebraic state x3 with 0 = x1 + x2 + x3 - 1 and the inconsistent start x3 = 0 that
+    IDACalcIC repairs"""
+    _, C, S, _ = _ref()
+    x1, x2, x3 = S("x1"), S("x2"), S("x3")
+    p1, p2, p3 = params = [S(f"p{i}") for i in range(1, 4)]
+    (k1,) = fixed = [S("k1")]
+    m = _base([x1, x2], [k1, sp.Float(0.0)], [-p1 * x1 + p2 * x2 * x3, p1 * x1 - p2 * x2 * x3 - p3 * x2 ** 2], params, [0.04, 1e4, 3e7],
+              fixed, [0.9], [("obs_x1", x1), ("obs_x2", 1e4 * x2), ("obs_x3", x3)])
+    m.add_component(C.AlgebraicState(x3, "x3", sp.Float(0.0)))
+    m.add_component(C.AlgebraicEquation(S("ae_0"), x1 + x2 + x3 - 1))
+    return m
+
+
 def build(name):
     """-> the model as the importers hand it to `DEExporter`: `generate_basic_variables()` parses the events (Heaviside
     functions -> root pairs, reference de_model.py:1156-1171) and creates the symbolic identifiers"""
@@ -165,4 +180,4 @@ def build(name):
     return m
 
 
-ALL = {"dirac": dirac, "jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode, "neuron": neuron, "events": events}
+ALL = {"robertson": robertson, "dirac": dirac, "jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode, "neuron": neuron, "events": events}

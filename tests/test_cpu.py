@@ -721,11 +721,11 @@ def test_de_export_refuses_what_the_engine_does_not_implement():
     from amici.importers.utils import symbol_with_assumptions as S
     from amici_b200.codegen import de_export
     from tests import de_models
-    m = de_models.steadystate()
+    m = de_models.neuron()   # a DAE model with events: the DAE path (csrc/dae.cuh) has no event handling
     a = S("a1")
     m.add_component(C.AlgebraicState(a, "a1", sp.Float(1.0)))
     m.add_component(C.AlgebraicEquation(S("ae1"), a - 1))
-    with pytest.raises(de_export.CudaEmitterError, match="algebraic"):
+    with pytest.raises(de_export.CudaEmitterError, match="DAE models with events"):
         de_export.modelspec_from_de_model(m, "x")
     m = de_models.steadystate()
     y, my, sig = S("obs_l"), S("mobs_l"), S("sigma_obs_l")
@@ -755,3 +755,24 @@ def test_emulation_dirac_matches_golden(built):
     p, ts = g["p"], g["ts"]
     want = np.where(ts[None, :] < p[:, 1:2], 0.0, np.exp(-p[:, 0:1] * (ts[None, :] - p[:, 1:2])))
     np.testing.assert_allclose(out["x"][:, :, 0], want, rtol=1e-6, atol=1e-9)
+
+
+def test_emulation_dae_robertson_matches_the_reference_idas(built):
+    """the shipped index-1 DAE form of Robertson's problem (models/model_robertson_py; engine header emitted
+    from the reference's `DEModel`) on the DAE path (csrc/dae.cuh: mass-matrix BDF, consistent start) against the reference's
+    IDAS runs (KLU / dense / tight-tolerance truth) by the parity protocol; the inconsistent start x3 = 0 is repaired like
+    IDACalcIC does (x0 = (k1, 0, 1 - k1) in the reference's ReturnData), the algebraic equation holds at every output."""
+    g = np.load(os.path.join(GOLD, "robertson.npz"))
+    b, out, keep = _capi.make_batch(dict(nx=3, np=3, nk=1, ny=3), g["ts"], g["p"], g["k"])
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=0)
+    assert _emul(built).emul_run(b"robertson", C.byref(o), C.byref(b)) == 0
+    np.testing.assert_array_equal(out["status"], g["klu_nosens_status"])
+    parity.check_against_golden(out, parity.robertson_view(g, 0), fields=["x", "y"])
+    np.testing.assert_allclose(out["x0"], np.stack([g["k"][:, 0], 0 * g["k"][:, 0], 1 - g["k"][:, 0]], axis=1), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(out["x"].sum(-1), 1.0, rtol=0, atol=1e-11)
+    ratio = out["numsteps"][:, -1] / g["klu_nosens_numsteps"][:, -1]   # another integrator: same size, not the same sequence
+    assert 0.5 < ratio.min() and ratio.max() < 2.0
+    # forward sensitivities of DAE models are refused, not silently dropped
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
+    b2, _, keep2 = _capi.make_batch(dict(nx=3, np=3, nk=1, ny=3), g["ts"], g["p"], g["k"])
+    assert _emul(built).emul_run(b"robertson", C.byref(o), C.byref(b2)) != 0 or b2.nplist == 0
