@@ -85,6 +85,7 @@ static const ModelEntry* registry(int* count) {
         entry_ev_pw_semi(),
         entry_ev_pw_state(),
         entry_dirac(),
+        entry_nested_events(),
         entry_robertson(),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));

@@ -60,6 +60,7 @@ ModelEntry entry_ev_pw_semi();
 ModelEntry entry_ev_pw_state();
 // emitted from the reference's symbolic model object through codegen/de_export.py (no ModelSpec in codegen/models.py)
 ModelEntry entry_dirac();
+ModelEntry entry_nested_events();
 // index-1 DAE model (dae.cuh): the shipped model_robertson_py, emitted from the reference's symbolic model object
 ModelEntry entry_robertson();
 

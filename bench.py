@@ -6,6 +6,7 @@
 --config (default jakstat = BASELINE.json configs[1], the configuration the metric is quoted on):
   jakstat      model_jakstat_adjoint_py, 17 forward sensitivities, 65,536 synthetic ExpData conditions
   robertson    Robertson (ODE form), forward simulation, 4096 log-uniform parameter draws            (configs[0])
+  robertson_dae  the shipped model_robertson_py (index-1 DAE): engine DAE path vs the reference's IDAS, same draws          (configs[0])
   steadystate  model_steadystate_py, pre-equilibration (Newton, simulation if it fails) + FSA, 65,536  (configs[2])
   events       model_events_py, Heaviside events + root finding + FSA, 65,536 parameter samples        (configs[3])
   neuron       model_neuron_py, spike events (divergent step control) + FSA, 65,536 samples            (configs[3])
@@ -85,6 +86,12 @@ CONFIGS = {
                       sensi=False, inputs=_wl_robertson, label="Robertson (ODE form, CVODES-equivalent BDF) forward simulation, log-uniform draws",
                       metric="ODE solves/sec, forward simulation (Robertson)", flops=dict(n=3, s=0, zJ=7, Ff=12, FJ=8, FP=0, ny=3),
                       baseline_config=0),
+    # BASELINE configs[0] as literally named: the SHIPPED model_robertson_py (index-1 DAE) — engine: the DAE path (csrc/dae.cuh, one
+    # thread per condition), reference arm: the shipped model through IDAS
+    "robertson_dae": dict(model="robertson", ref="robertson", n=4096, seed=1, ts=np.concatenate([[0.0], 4 * np.logspace(-6, 6, 50)]),
+                          sensi=False, inputs=_wl_robertson, label="model_robertson_py (shipped index-1 DAE; engine: mass-matrix BDF, reference: IDAS) forward simulation, log-uniform draws",
+                          metric="DAE solves/sec, forward simulation (Robertson DAE)", flops=dict(n=3, s=0, zJ=7, Ff=12, FJ=8, FP=0, ny=3),
+                          baseline_config=0),
     "steadystate": dict(model="steadystate", ref="steadystate", n=65536, seed=3, ts=np.linspace(0, 10, 11), sensi=True, inputs=_wl_steadystate,
                         preeq=True, label="model_steadystate_py pre-equilibration (Newton, simulation if it fails) + FSA 5 params",
                         metric="ODE solves/sec w/ forward sens + pre-equilibration (steadystate)",

@@ -19,6 +19,7 @@
 #include "../../amici_b200/csrc/models/ev_pw_semi.cuh"
 #include "../../amici_b200/csrc/models/ev_pw_state.cuh"
 #include "../../amici_b200/csrc/models/dirac.cuh"
+#include "../../amici_b200/csrc/models/nested_events.cuh"
 #include "../../amici_b200/csrc/models/robertson.cuh"
 #include "../../amici_b200/csrc/dae.cuh"
 
@@ -120,6 +121,7 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "ev_pw_semi") return run_model<models::ev_pw_semi>(o, b);
     if (m == "ev_pw_state") return run_model<models::ev_pw_state>(o, b);
     if (m == "dirac") return run_model<models::dirac>(o, b);
+    if (m == "nested_events") return run_model<models::nested_events>(o, b);
     if (m == "robertson") {   // DAE path (dae.cuh): forward simulation only, as launch_dae_model
         if (o->sensi >= 1 && b->nplist > 0) return -3;
         for (int n = 0; n < b->N; ++n) {

@@ -172,6 +172,20 @@ def robertson():
     return m
 
 
+def nested_events():
+    """the reference's nested-events test model (python/sdist/amici/testing/models.py:446-480; shipped sources
+    models/model_nested_events_py): growth switched on by a STATE-dependent Heaviside (Virus > 1) and an injection at the
+    parameter-dependent time t_0 that flips the switch — a secondary event of the first"""
+    _, C, S, t = _ref()
+    (virus,) = states = [S("Virus")]
+    V_0, V_0_inject, t_0, rho_V, delta_V = params = [S(n) for n in ("V_0", "V_0_inject", "t_0", "rho_V", "delta_V")]
+    xdot = [virus * rho_V * sp.Heaviside(virus - 1, 1) - virus * delta_V]
+    m = _base(states, [V_0], xdot, params, [0.1, 1000.0, 2.0, 0.8, 1.6], [], [], [("obs_Virus", virus)])
+    m.add_component(C.Event(S("injection"), "injection", t - t_0, use_values_from_trigger_time=False,
+                            assignments={virus: virus + V_0_inject}, initial_value=True))
+    return m
+
+
 def build(name):
     """-> the model as the importers hand it to `DEExporter`: `generate_basic_variables()` parses the events (Heaviside
     functions -> root pairs, reference de_model.py:1156-1171) and creates the symbolic identifiers"""
@@ -180,4 +194,4 @@ def build(name):
     return m
 
 
-ALL = {"robertson": robertson, "dirac": dirac, "jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode, "neuron": neuron, "events": events}
+ALL = {"nested_events": nested_events, "robertson": robertson, "dirac": dirac, "jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode, "neuron": neuron, "events": events}

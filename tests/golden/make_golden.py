@@ -162,6 +162,8 @@ def make_dirac():
     # the shipped Dirac model (bolus at the parameter-dependent time p2): its engine header is emitted from the reference's
     # symbolic model object (tests/golden/make_de_models.py)
     make("dirac", np.linspace(0, 3, 16), N=6, seed=51, spread=8)
+    # nested events: a state-dependent Heaviside switch flipped by the injection at t_0 (secondary event)
+    make("nested_events", np.linspace(0, 10, 21), N=6, seed=52, spread=8)
 
 
 def make_adjoint():

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 MODEL_DIMS = {"robertson_ode": dict(nx=3, np=3, nk=1, ny=3), "jakstat_adjoint": dict(nx=9, np=17, nk=2, ny=3), "steadystate": dict(nx=3, np=5, nk=4, ny=3),
               "events": dict(nx=3, np=4, nk=4, ny=1, nz=2), "neuron": dict(nx=2, np=4, nk=2, ny=1, nz=1),
-              "dirac": dict(nx=2, np=4, nk=0, ny=1)}
+              "dirac": dict(nx=2, np=4, nk=0, ny=1), "nested_events": dict(nx=1, np=5, nk=0, ny=1)}
 
 
 def _emul(built):
@@ -776,3 +776,12 @@ def test_emulation_dae_robertson_matches_the_reference_idas(built):
     o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
     b2, _, keep2 = _capi.make_batch(dict(nx=3, np=3, nk=1, ny=3), g["ts"], g["p"], g["k"])
     assert _emul(built).emul_run(b"robertson", C.byref(o), C.byref(b2)) != 0 or b2.nplist == 0
+
+
+def test_emulation_nested_events_matches_golden(built):
+    """The shipped nested-events model (state-dependent Heaviside switch, flipped by an injection at the parameter-dependent time
+    t_0: a secondary event), engine header emitted from the reference's `DEModel`, against the compiled reference."""
+    g = np.load(os.path.join(GOLD, "nested_events.npz"))
+    out = run_emul(_emul(built), "nested_events", g)
+    parity.check_against_golden(out, g)
+    assert abs(out["numsteps"][:, -1] / g["klu_numsteps"][:, -1] - 1).max() < 0.1

@@ -1394,3 +1394,32 @@ def test_cuda_dae_robertson_shipped_model_vs_reference_idas():
     ref = refsim.RefModel("robertson")
     sub = {f: np.asarray(out[f])[idx] for f in ("status", "x", "y")}
     _check_live(sub, ref, ts, p[idx], k[idx], ["x", "y"], sensi_order=0)
+
+
+@pytest.mark.gpu
+def test_cuda_nested_events_emitted_from_the_reference_model_object():
+    """model_nested_events_py through the DEExporter back end (no hand-written model description): golden fixture, then 2048
+    parameter samples against the compiled reference on a 96-sample subset (status identical, floats incl. sx by the protocol)."""
+    import amici_b200 as ab
+    from oracle import refsim
+    g = np.load(os.path.join(GOLD, "nested_events.npz"))
+    res = _run("nested_events", g)
+    parity.check_against_golden(res.fields, g)
+    N = 2048
+    m = ab.get_model("nested_events")
+    ts = np.linspace(0, 10, 21)
+    m.set_timepoints(ts)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    s.set_sensitivity_order(ab.SensitivityOrder.first)
+    rng = np.random.default_rng(62)
+    p = np.tile(m.get_free_parameters(), (N, 1)) * 10 ** rng.normal(0, 0.1, (N, m.np()))
+    k = np.zeros((N, 0))
+    out = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
+    if not refsim.available("nested_events"):
+        assert (out["status"] == 0).all()
+        return
+    idx = rng.choice(N, 96, replace=False)
+    sub = {f: np.asarray(out[f])[idx] for f in ("status", "x", "sx", "y", "sy")}
+    _check_live(sub, refsim.RefModel("nested_events"), ts, p[idx], k[idx], ["x", "sx", "y", "sy"])
