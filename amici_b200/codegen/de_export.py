@@ -13,7 +13,7 @@ The reference turns a symbolic model (`DEModel`, reference python/sdist/amici/_s
 
 The module is duck-typed: it imports nothing from the reference, so it also runs where the reference's package is not
 installed (the objects only have to offer the accessors named above).  What the engine does not implement is refused with
-`CudaEmitterError` instead of being emitted wrongly: DAE models with events or splines, conservation laws, observable
+`CudaEmitterError` instead of being emitted wrongly: DAE models with state-changing / state-triggered events, conservation laws, observable
 transformations other than `lin`, noise models other than the Gaussian one, event priorities.
 
 Tests: tests/test_cpu.py::test_de_export_* build the reference's `DEModel` for the shipped test models with the reference's own
@@ -103,8 +103,14 @@ def modelspec_from_de_model(de_model, name: str, doc: str = "") -> em.ModelSpec:
     alg_states, alg_eqs = list(de_model.algebraic_states()), list(de_model.algebraic_equations())
     if len(alg_states) != len(alg_eqs):
         raise CudaEmitterError("one algebraic equation per algebraic state expected")
-    if alg_states and (list(de_model.events()) or getattr(de_model, "_splines", [])):
-        raise CudaEmitterError("DAE models with events or splines are not supported (csrc/dae.cuh)")
+    if alg_states:
+        # the DAE path (csrc/dae.cuh) handles time-triggered Heaviside switches only
+        state_syms = {s.get_sym() for s in de_model.differential_states()} | {s.get_sym() for s in alg_states}
+        for e in de_model.events():
+            if e._assignments or (sp.sympify(e.get_val()).subs(_inline_expressions(de_model)).free_symbols & state_syms):
+                raise CudaEmitterError("DAE models with events that change the state or are triggered by it are not supported (csrc/dae.cuh)")
+        if list(de_model.event_observables()) or getattr(de_model, "_splines", []):
+            raise CudaEmitterError("DAE models with event observables or splines are not supported (csrc/dae.cuh)")
     if de_model.num_cons_law() > 0 or list(de_model.conservation_laws()):
         raise CudaEmitterError("conservation laws (x_rdata != x_solver) are not supported: import with compute_conservation_laws=False")
     inline = _inline_expressions(de_model)

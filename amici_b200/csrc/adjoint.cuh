@@ -322,10 +322,15 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         return ok ? AB_SUCCESS : NLS_CONV_RECVR;
     }
     AB_HD void lu_solve(double* b) const {
+        // SUNDIALS' denseGETRS: ALL row interchanges first (lsetup swaps whole rows, so the multipliers of a column sit where
+        // the later interchanges have moved them), then L y = b, then U x = y
         AB_NOUNROLL
         for (int kk = 0; kk < NX; ++kk) {
             const int pr = piv[kk];
             if (pr != kk) { const double tmp = b[kk]; b[kk] = b[pr]; b[pr] = tmp; }
+        }
+        AB_NOUNROLL
+        for (int kk = 0; kk < NX; ++kk) {
             const double bk = b[kk];
             for (int r = kk + 1; r < NX; ++r) b[r] -= lu[r][kk] * bk;
         }

@@ -14,8 +14,13 @@
 //   consistent start   IDACalcIC(IDA_YA_YDP_INIT) (src/solver_idas.cpp:831-840): differential states fixed, Newton on the
 //                      algebraic equations for the algebraic states at t0 (the shipped Robertson model starts from the
 //                      inconsistent x3 = 0); the reported x0 is the corrected one, as in the reference's ReturnData
+//   events             time-triggered Heaviside switches only (NE_SOLVER == 0, no state updates; model_calvetti_py's forcing):
+//                      the trigger times are stop times (src/forwardproblem.cpp:100-106), h += direction of the crossing
+//                      (Model::update_heaviside), the solver restarts at order 1 as after every AMICI event; the algebraic
+//                      states are NOT re-initialised there — the first step after the event pulls them onto the new
+//                      constraint, exactly what IDAS does after IDAReInit with the error test blind to them
 //   outputs            x, y, sigmay, llh, res, chi2, counters, status (AdjointSimulation's forward outputs)
-//   not implemented    sensitivities, events, pre-/post-equilibration of DAE models: refused by the launch
+//   not implemented    sensitivities, state-triggered or state-changing events, pre-/post-equilibration of DAE models
 #ifndef AMICI_B200_DAE_CUH
 #define AMICI_B200_DAE_CUH
 #include "adjoint.cuh"
@@ -105,6 +110,21 @@ struct DaeSimulation {
         return false;
     }
 
+    // next explicit trigger time in (t_done, t_end] (Simulation::next_trigger)
+    AB_HD double next_trigger(const AdjCond<M>& c, double t_done, double t_end) const {
+        double best = INFINITY;
+        for (int ie = 0; ie < M::NE; ++ie) {
+            const double te = M::explicit_time(ie, c.p, c.k);
+            if (te > t_done && te <= t_end && te < best) best = te;
+        }
+        return best;
+    }
+    AB_HD void roots_at(const AdjCond<M>& c, double t, const double* x, double* rv) const {
+        double spl[AdjCond<M>::NSPLV];
+        c.splines(t, spl);
+        M::root(t, x, c.p, c.k, c.h, spl, rv);
+    }
+
     AB_HD void run() {
         FwdHistory<NX> none;
         none.t = none.y = nullptr;
@@ -116,7 +136,11 @@ struct DaeSimulation {
         out.c.nplist = 0;
         const int nt = b.nt;
         DaeProblem<M> dp{out.c, o.rtol, o.atol, o.rtol, o.atol};
-        ScalarBdf<DaeProblem<M>> bdf(dp, o, 0);
+        // IDAS allows four Newton iterations per step (MAXIT, idas_impl.h) where CVODES allows three: the jump of the algebraic
+        // states after a switch is absorbed by the first corrector solve after the restart, whatever the step size
+        SolverOptions od = o;
+        od.max_nonlin_iters = o.max_nonlin_iters < 4 ? 4 : o.max_nonlin_iters;
+        ScalarBdf<DaeProblem<M>> bdf(dp, od, 0);
         double x0[NX];
         M::x0(out.c.p, out.c.k, x0);
         if (b.x0_in)
@@ -125,19 +149,44 @@ struct DaeSimulation {
         if (!consistent_start(dp, o.t0, x0)) status = AB_IC_FAIL;
         if (b.x0 && out.full())
             for (int r = 0; r < NX; ++r) b.x0[(size_t)n * NX + r] = x0[r];
+        constexpr int NEV = M::NE > 0 ? M::NE : 1;
+        double rootvals[NEV];
+        if (M::NE > 0) {   // Model::initialize_events (reference src/model.cpp:407-442): the Heaviside state of the roots at t0
+            roots_at(out.c, o.t0, x0, rootvals);
+            for (int ie = 0; ie < M::NE; ++ie) out.c.h[ie] = rootvals[ie] < 0.0 ? 0.0 : 1.0;
+        }
         if (status == AB_SUCCESS) {
             for (int r = 0; r < NX; ++r) bdf.zn[0][r] = x0[r];
             bdf.init(o.t0);
-            double t = o.t0;
-            for (; it < nt; ++it) {
-                const double tout = b.ts[it];
-                if (tout > o.t0 && t < tout && !adj_too_close(t, tout)) {
-                    const int flag = bdf.solve_to(tout, false);
-                    if (flag < 0) { status = flag; break; }
-                    t = bdf.tretlast;
+            double t = o.t0, t_done = o.t0;
+            while (it < nt) {
+                double tout = b.ts[it];
+                if (!(tout > o.t0) || !(t < tout) || adj_too_close(t, tout)) {
+                    const int counters[5] = {bdf.nst, bdf.nfe, bdf.netf, bdf.ncfn, bdf.qu};
+                    out.datapoint(it, bdf.zn[0], counters);
+                    ++it;
+                    continue;
                 }
-                const int counters[5] = {bdf.nst, bdf.nfe, bdf.netf, bdf.ncfn, bdf.qu};
-                out.datapoint(it, bdf.zn[0], counters);
+                double t_event = INFINITY;
+                if (M::NE > 0) {
+                    t_event = next_trigger(out.c, t_done, b.ts[nt - 1]);
+                    tout = ab_min(tout, t_event);
+                }
+                const int flag = bdf.solve_to(tout, false);
+                if (flag < 0) { status = flag; break; }
+                t = bdf.tretlast;
+                if (M::NE > 0 && t == t_event) {
+                    // every switch whose trigger time is t flips in the direction of its crossing (Simulation::collect_roots:
+                    // the sign of the root before the trigger), h += roots_found, CVodeSolver::reinit semantics for the solver
+                    for (int ie = 0; ie < M::NE; ++ie)
+                        if (M::explicit_time(ie, out.c.p, out.c.k) == t) out.c.h[ie] += (copysign(1.0, rootvals[ie]) < 0.0) ? 1.0 : -1.0;
+                    roots_at(out.c, t, bdf.zn[0], rootvals);
+                    for (int ie = 0; ie < M::NE; ++ie)   // a root that is exactly zero at its trigger keeps the sign it is heading to
+                        if (rootvals[ie] == 0.0) rootvals[ie] = out.c.h[ie] > 0.0 ? 0.0 : -0.0;
+                    t_done = t;
+                    bdf.flush_pending();
+                    bdf.amici_reinit(t);
+                }
             }
         }
         if (status != AB_SUCCESS) out.invalidate(it);

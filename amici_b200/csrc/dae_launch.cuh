@@ -62,7 +62,8 @@ int launch_dae_model(const ab_solver_options& o, const ab_batch& b, int* queue_h
 
 template <class M>
 ModelEntry make_dae_entry() {
-    static_assert(M::NE == 0 && M::NSPL == 0 && alg_mask_of<M>::value != 0ull, "DAE path: event-free, spline-free models with algebraic states");
+    static_assert(M::NE_SOLVER == 0 && M::NZ == 0 && M::NSPL == 0 && alg_mask_of<M>::value != 0ull,
+                  "DAE path: spline-free models with algebraic states whose only events are time-triggered Heaviside switches");
     ModelEntry e;
     e.name = M::name();
     e.dims = ab_dims{M::NX, M::NP, M::NK, M::NY, M::NZ, M::NE, M::NSPL, 1, 1};

@@ -87,6 +87,7 @@ static const ModelEntry* registry(int* count) {
         entry_dirac(),
         entry_nested_events(),
         entry_robertson(),
+        entry_calvetti(),
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;

@@ -63,6 +63,7 @@ ModelEntry entry_dirac();
 ModelEntry entry_nested_events();
 // index-1 DAE model (dae.cuh): the shipped model_robertson_py, emitted from the reference's symbolic model object
 ModelEntry entry_robertson();
+ModelEntry entry_calvetti();
 
 }  // namespace amici_b200
 #endif

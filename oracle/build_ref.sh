@@ -17,7 +17,7 @@ REF=${AMICI_REFERENCE:-/root/reference}
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/_ref"
 JOBS=${JOBS:-$(nproc)}
-MODELS=${MODELS:-"jakstat_adjoint steadystate events neuron dirac nested_events robertson robertson_ode massaction_small massaction"}
+MODELS=${MODELS:-"jakstat_adjoint steadystate events neuron dirac nested_events calvetti robertson robertson_ode massaction_small massaction"}
 CFLAGS_COMMON="-O2 -fPIC -fopenmp -w"
 
 if [ ! -d "$REF/src" ]; then

@@ -21,6 +21,7 @@
 #include "../../amici_b200/csrc/models/dirac.cuh"
 #include "../../amici_b200/csrc/models/nested_events.cuh"
 #include "../../amici_b200/csrc/models/robertson.cuh"
+#include "../../amici_b200/csrc/models/calvetti.cuh"
 #include "../../amici_b200/csrc/dae.cuh"
 
 #include <memory>
@@ -122,11 +123,11 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "ev_pw_state") return run_model<models::ev_pw_state>(o, b);
     if (m == "dirac") return run_model<models::dirac>(o, b);
     if (m == "nested_events") return run_model<models::nested_events>(o, b);
-    if (m == "robertson") {   // DAE path (dae.cuh): forward simulation only, as launch_dae_model
+    if (m == "robertson" || m == "calvetti") {   // DAE path (dae.cuh): forward simulation only, as launch_dae_model
         if (o->sensi >= 1 && b->nplist > 0) return -3;
         for (int n = 0; n < b->N; ++n) {
-            auto sim = std::make_unique<DaeSimulation<models::robertson>>(*o, *b, n);
-            sim->run();
+            if (m == "robertson") std::make_unique<DaeSimulation<models::robertson>>(*o, *b, n)->run();
+            else std::make_unique<DaeSimulation<models::calvetti>>(*o, *b, n)->run();
         }
         return 0;
     }

@@ -186,6 +186,39 @@ def nested_events():
     return m
 
 
+def calvetti():
+    """the reference's Calvetti test model (python/sdist/amici/testing/models.py:37-88, :137-160; shipped sources
+    models/model_calvetti_py): an index-1 DAE with three differential and three algebraic states, sixteen intermediate
+    expressions, no free parameters, and a forcing s(t) = [10 <= t <= 12] that the importer turns into time-triggered
+    Heaviside switches"""
+    _, C, S, t = _ref()
+    V1, V2, V3, f1, f2, f3 = [S(n) for n in ("V1", "V2", "V3", "f1", "f2", "f3")]
+    V1ss, R1ss, V2ss, R2ss, V3ss, R3ss = fixed = [S(n) for n in ("V1ss", "R1ss", "V2ss", "R2ss", "V3ss", "R3ss")]
+    p2, p3, L1, L2, L3, C1ss, C2ss, C3ss, R1, R2, R3, f0, s_, rV1, rV2, rV3 = [S(n) for n in (
+        "p2 p3 L1 L2 L3 C1ss C2ss C3ss R1 R2 R3 f0 s rate_of_V1 rate_of_V2 rate_of_V3").split()]
+    Q = sp.Rational
+    third = Q(1, 3)
+    flow = (R1 + R2) * f1 + (R2 + R3) * f2 + R3 * f3
+    expressions = [
+        (p2, 1 - R1ss), (p3, 1 - (R1ss + R2ss)),
+        (L1, (R1ss * V1ss ** 2) ** third), (L2, (R2ss * V2ss ** 2) ** third), (L3, (R3ss * V3ss ** 2) ** third),
+        (C1ss, V1ss / (1 - Q(1, 2) * R1ss)), (C2ss, V2ss / (p2 - Q(1, 2) * R2ss)), (C3ss, V3ss / (p3 - Q(1, 2) * R3ss)),
+        (R1, L1 ** 3 / V1 ** 2), (R2, L2 ** 3 / V2 ** 2), (R3, L3 ** 3 / V3 ** 2),
+        (f0, 2 / R1 - flow / R1),
+        (s_, sp.Heaviside(t - 10, 1) * sp.Heaviside(12 - t, 1)),
+        (rV1, Q(1, 31) * ((Q(129, 100) - V1 / V1ss) / (Q(129, 100) - 1) + s_ - 2 * (V1 / (C1ss * flow)))),
+        (rV2, Q(1, 163) * ((Q(151, 100) - V2 / V2ss) / (Q(151, 100) - 1) - 2 * (V2 / (C2ss * ((R2 + R3) * f2 + R3 * f3))))),
+        (rV3, Q(1, 122) * ((1000000 - V3 / V3ss) / (1000000 - 1) - 2 * (V3 / (C3ss * (R3 * f3))))),
+    ]
+    m = _base([V1, V2, V3], [V1ss, V2ss, V3ss], [rV1, rV2, rV3], [], [], fixed, [0.29, 0.74, 0.44, 0.08, 0.27, 0.18],
+              [("obs_V1", V1), ("obs_V2", V2), ("obs_V3", V3), ("obs_f0", f0), ("obs_f1", f1), ("obs_f2", f2)], expressions=expressions)
+    for a in (f1, f2, f3):
+        m.add_component(C.AlgebraicState(a, str(a), sp.Float(1.0)))
+    for i, e in enumerate((f0 - rV1 - f1, f1 - rV2 - f2, f2 - rV3 - f3)):
+        m.add_component(C.AlgebraicEquation(S(f"ae_{i}"), e))
+    return m
+
+
 def build(name):
     """-> the model as the importers hand it to `DEExporter`: `generate_basic_variables()` parses the events (Heaviside
     functions -> root pairs, reference de_model.py:1156-1171) and creates the symbolic identifiers"""
@@ -194,4 +227,4 @@ def build(name):
     return m
 
 
-ALL = {"nested_events": nested_events, "robertson": robertson, "dirac": dirac, "jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode, "neuron": neuron, "events": events}
+ALL = {"calvetti": calvetti, "nested_events": nested_events, "robertson": robertson, "dirac": dirac, "jakstat_adjoint": jakstat_adjoint, "steadystate": steadystate, "robertson_ode": robertson_ode, "neuron": neuron, "events": events}

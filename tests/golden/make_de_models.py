@@ -15,6 +15,7 @@ from tests import de_models  # noqa: E402
 
 DE_ONLY = {"dirac": "from the reference's DEModel of model_dirac_py (tests/de_models.py::dirac) by amici_b200/codegen/de_export.py",
            "nested_events": "from the reference's DEModel of model_nested_events_py (tests/de_models.py::nested_events) by amici_b200/codegen/de_export.py",
+           "calvetti": "from the reference's DEModel of model_calvetti_py, an index-1 DAE with time-triggered switches (tests/de_models.py::calvetti), by amici_b200/codegen/de_export.py",
            "robertson": "from the reference's DEModel of model_robertson_py, the index-1 DAE form (tests/de_models.py::robertson), by amici_b200/codegen/de_export.py"}
 
 

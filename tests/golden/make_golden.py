@@ -21,7 +21,8 @@ PREEQ_FIELDS = ["x_ss", "sx_ss", "preeq_status", "preeq_numsteps", "preeq_wrms",
 EVENT_FIELDS = ["z", "sz", "rz", "srz", "sigmaz"]
 
 
-def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=None, presim=False, pfix=None, spread=0, **run_kw):
+def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=None, presim=False, pfix=None, spread=0,
+         truth_tol=(1e-12, 1e-16), **run_kw):
     m = RefModel(model)
     d = m.dims
     rng = np.random.default_rng(seed)
@@ -57,7 +58,7 @@ def make(model, ts, N, seed, sensi=1, pscale=None, tag="", preeq=False, kscale=N
     # handful of conditions two runs underestimate the tail of the reference's own error
     spread_runs = tuple((f"s{j}", dict(linsol=9 if j % 2 else 1, rtol=1e-8 * (1.0 + 1e-6 * (j + 1)))) for j in range(spread))
     for name, extra in (("klu", dict(linsol=9)), ("dense", dict(linsol=1)),
-                        ("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=200000))) + spread_runs:
+                        ("truth", dict(linsol=9, rtol=truth_tol[0], atol=truth_tol[1], maxsteps=200000))) + spread_runs:
         r = m.run(ts, pin, k, **{**kw, **extra})
         for f in fields:
             out[f"{name}_{f}"] = r[f]
@@ -164,6 +165,9 @@ def make_dirac():
     make("dirac", np.linspace(0, 3, 16), N=6, seed=51, spread=8)
     # nested events: a state-dependent Heaviside switch flipped by the injection at t_0 (secondary event)
     make("nested_events", np.linspace(0, 10, 21), N=6, seed=52, spread=8)
+    # Calvetti: index-1 DAE (IDAS in the reference) with switches at t = 10 and t = 12, both on the output grid; no free parameters
+    # (the reference's IDAS fails on every condition at rtol 1e-11 / atol 1e-15 and below: the truth run is 1e-10 / 1e-14)
+    make("calvetti", np.linspace(0, 20, 41), N=6, seed=53, sensi=0, spread=8, truth_tol=(1e-10, 1e-14))
 
 
 def make_adjoint():

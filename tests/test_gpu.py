@@ -1423,3 +1423,36 @@ def test_cuda_nested_events_emitted_from_the_reference_model_object():
     idx = rng.choice(N, 96, replace=False)
     sub = {f: np.asarray(out[f])[idx] for f in ("status", "x", "sx", "y", "sy")}
     _check_live(sub, refsim.RefModel("nested_events"), ts, p[idx], k[idx], ["x", "sx", "y", "sy"])
+
+
+@pytest.mark.gpu
+def test_cuda_dae_calvetti_shipped_model_vs_reference_idas():
+    """model_calvetti_py (index-1 DAE with time-triggered switches) through the C ABI on the DAE path: the fixture of the reference's
+    IDAS runs incl. the condition the reference gives up on, then 1024 draws of the six constants (k x U(0.9, 1.1)): status codes
+    identical to IDAS on a 48-draw subset, floats by the max-based protocol."""
+    import amici_b200 as ab
+    from oracle import refsim
+    from tests.test_cpu import _calvetti_checks
+    g = np.load(os.path.join(GOLD, "calvetti.npz"))
+    res = _run("calvetti", g, sensi=False)
+    _calvetti_checks(res.fields, g)
+    N = 1024
+    m = ab.get_model("calvetti")
+    ts = np.linspace(0, 20, 41)
+    m.set_timepoints(ts)
+    s = m.create_solver()
+    s.set_relative_tolerance(parity.RTOL)
+    s.set_absolute_tolerance(parity.ATOL)
+    rng = np.random.default_rng(63)
+    p = np.zeros((N, 0))
+    k = np.tile(m.get_fixed_parameters(), (N, 1)) * rng.uniform(0.9, 1.1, (N, 6))
+    out = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
+    assert (out["status"] == 0).mean() > 0.9
+    if not refsim.available("calvetti"):
+        return
+    idx = rng.choice(N, 48, replace=False)
+    ref = refsim.RefModel("calvetti")
+    sub = {f: np.asarray(out[f])[idx] for f in ("status", "x", "y")}
+    r = ref.run(ts, p[idx], k[idx], sensi_order=0, num_threads=min(ref.max_threads(), 16), fields=["status"])
+    np.testing.assert_array_equal(sub["status"], r["status"])
+    _check_live(sub, ref, ts, p[idx], k[idx], ["x", "y"], sensi_order=0, status_equal=False)
