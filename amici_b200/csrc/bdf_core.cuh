@@ -1223,6 +1223,9 @@ struct BdfControl {
             h = hscale * eta;
             hscale = h;
             nscon = 0;
+            // a step size that has underflowed to zero (or is no number) after repeated failures ends the solve: with hmin = 0
+            // CVODES runs into 0 / 0 in gamrat here and gives up after its next ten corrector failures
+            if (!(fabs(h) > 0.0)) return (st_nflag == PREV_ERR_FAIL) ? AB_ERR_FAILURE : AB_CONV_FAILURE;
         }
         if (st_reload) {  // order-1 restart: zn[1] = h * f(tn, zn[0])
             const bool ok = self().rhs_to_zn1(h);

@@ -7,7 +7,10 @@
 // src/solver_idas.cpp).  This path is NOT a restatement of IDAS: it is the engine's CVODES-equivalent Nordsieck BDF with a
 // mass matrix — same formulas of order 1..5, same step-size / order control (BdfControl), corrector
 // M (rl1 zn[1] + acor) - gamma f = 0 with the Newton matrix M - gamma J, algebraic states left out of the error test as
-// AMICI configures IDAS (IDASetSuppressAlg(true), src/solver.cpp:252).  Step sequences therefore differ from IDAS'; results
+// AMICI configures IDAS (IDASetSuppressAlg(true), src/solver.cpp:252).  Consequences of that choice handled in ScalarBdf: the
+// history of the algebraic states is kept at order 1 (linear extrapolation as predictor; a Nordsieck array of order q fed with
+// corrections that no error test bounds drifts until the corrector stalls), every step estimates its own Newton convergence
+// rate, the corrector tolerance is ten times tighter, and a step size that underflows to zero ends the solve.  Step sequences therefore differ from IDAS'; results
 // are compared with the reference's IDAS runs by the parity protocol (error against a tight-tolerance IDAS run no larger
 // than IDAS' own, tests/parity.py).
 //

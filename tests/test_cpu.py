@@ -769,7 +769,7 @@ def test_emulation_dae_robertson_matches_the_reference_idas(built):
     np.testing.assert_array_equal(out["status"], g["klu_nosens_status"])
     parity.check_against_golden(out, parity.robertson_view(g, 0), fields=["x", "y"])
     np.testing.assert_allclose(out["x0"], np.stack([g["k"][:, 0], 0 * g["k"][:, 0], 1 - g["k"][:, 0]], axis=1), rtol=0, atol=1e-15)
-    np.testing.assert_allclose(out["x"].sum(-1), 1.0, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(out["x"].sum(-1), 1.0, rtol=0, atol=1e-8)   # the Newton tolerance, not round-off (here 1.8e-9; the reference 5.7e-11 on this fixture, 2.0e-9 on wider draws)
     ratio = out["numsteps"][:, -1] / g["klu_nosens_numsteps"][:, -1]   # another integrator: same size, not the same sequence
     assert 0.5 < ratio.min() and ratio.max() < 2.0
     # forward sensitivities of DAE models are refused, not silently dropped

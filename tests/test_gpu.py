@@ -1447,7 +1447,7 @@ def test_cuda_dae_calvetti_shipped_model_vs_reference_idas():
     p = np.zeros((N, 0))
     k = np.tile(m.get_fixed_parameters(), (N, 1)) * rng.uniform(0.9, 1.1, (N, 6))
     out = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p, k))
-    assert (out["status"] == 0).mean() > 0.9
+    assert (out["status"] == 0).all()   # the reference's IDAS succeeds on every one of these draws
     if not refsim.available("calvetti"):
         return
     idx = rng.choice(N, 48, replace=False)
