@@ -94,12 +94,13 @@ def reference_triple(ref, ts, p, k, fields, num_threads=1, truth=True, spread_ru
     error distribution — two runs on a handful of conditions underestimate its tail (sx error of 512 steadystate conditions:
     median 2.4, p99 35, max 60 tolerances)."""
     out = {}
+    truth_tol = kw.pop("truth_tol", (1e-12, 1e-16))   # model_calvetti_py: the reference's IDAS fails below 1e-10 / 1e-14
     runs = [("klu", dict(linsol=9)), ("dense", dict(linsol=1))]
     base_rtol = kw.get("rtol", RTOL)
     for j in range(spread_runs):
         runs.append((f"s{j}", dict(linsol=9 if j % 2 else 1, rtol=base_rtol * (1.0 + 1e-6 * (j + 1)))))
     if truth:
-        runs.append(("truth", dict(linsol=9, rtol=1e-12, atol=1e-16, maxsteps=500000)))
+        runs.append(("truth", dict(linsol=9, rtol=truth_tol[0], atol=truth_tol[1], maxsteps=500000)))
     for name, extra in runs:
         r = ref.run(ts, p, k, fields=list(fields), num_threads=num_threads, **{**kw, **extra})
         for f in r:
