@@ -58,7 +58,12 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     static constexpr int NX = P::NX, NQ = P::NQ, NQA = P::NQ > 0 ? P::NQ : 1;
     static constexpr bool ROOTS = false, EVENTS = true, STG = false, QUAD = P::NQ > 0, HIST = P::HIST;
     static constexpr unsigned long long AM = P::ALG_MASK;
+    // P::SENS (dae.cuh): the NQ "quadrature" rows are forward sensitivities, column il in rows il * NX .. il * NX + NX - 1; they
+    // are corrected after the states by a Newton iteration on their own linear system with the states' factors (the staggered
+    // corrector, CV_STAGGERED) instead of cvQuadNls' explicit formula, and take the error test of the quadratures (errconS)
+    static constexpr bool SENS = P::SENS;
     AB_HD static bool alg(int r) { return AM != 0ull && ((AM >> r) & 1ull) != 0ull; }
+    AB_HD static bool algq(int r) { return SENS && alg(r % NX); }
     using Base = BdfControl<ScalarBdf<P>, ScalarShared>;
     using Base::o; using Base::tn; using Base::h; using Base::l; using Base::tq; using Base::rl1; using Base::gamma;
     using Base::gammap; using Base::gamrat; using Base::crate; using Base::delp; using Base::acnrm; using Base::q; using Base::L;
@@ -111,7 +116,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         if (AM != 0ull)
             for (int r = 0; r < NX; ++r) ewt_d[r] = alg(r) ? 0.0 : ewt[r];
         if (QUAD)
-            for (int r = 0; r < nq; ++r) ewtQ[r] = 1.0 / (prob.rtolq * fabs(pending ? znQ[0][r] + acorQ[r] : znQ[0][r]) + prob.atolq);
+            for (int r = 0; r < nq; ++r) ewtQ[r] = algq(r) ? 0.0 : 1.0 / (prob.rtolq * fabs(pending ? znQ[0][r] + acorQ[r] : znQ[0][r]) + prob.atolq);
     }
     AB_HD void stab_sums(const double lq, const double lqm1, double& s1, double& s2) const {
         for (int r = 0; r < NX; ++r) {
@@ -138,7 +143,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
             // growing amplitude until the corrector stalls).  Their history is therefore kept at order 1 whatever the order of
             // the method — zn[1] = last backward difference, i.e. l = (1, 1, 0, ...): a linear extrapolation as predictor; the
             // corrector puts them on the constraint.
-            const bool arow = N == NX && alg(r);
+            const bool arow = ((const void*)&z[0][0] == (const void*)&zn[0][0]) ? alg(r) : algq(r);
             AB_UNROLL
             for (int j = 0; j <= QMAX; ++j)
                 v[j] = arow ? (j <= 1 ? z[j][r] + a : 0.0) : ((j <= 1 || j <= q) ? z[j][r] : 0.0) + lc[j] * a;
@@ -214,7 +219,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         if (QUAD) {
             double fq[NQA];
             ok = prob.quad(tn, zn[0], fq) && ok;
-            for (int r = 0; r < nq; ++r) znQ[1][r] = scale * fq[r];
+            for (int r = 0; r < nq; ++r) znQ[1][r] = algq(r) ? 0.0 : scale * fq[r];
         }
         return ok;
     }
@@ -407,6 +412,7 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
     }
     // cvQuadNls (cvodes.c:7236-7262)
     AB_NI bool quad_correct() {
+        if (SENS) return sens_correct();
         double y[NX], fq[NQA];
         for (int r = 0; r < NX; ++r) y[r] = zn[0][r] + acor[r];
         const bool ok = prob.quad(tn, y, fq);
@@ -414,6 +420,42 @@ struct ScalarBdf : BdfControl<ScalarBdf<P>, ScalarShared> {
         return ok;
     }
     AB_HD double quad_norm() const { return wrms2(acorQ, nullptr, 0.0, ewtQ, nq); }
+    // Staggered corrector of the sensitivities (cvStgrNls, cvodes_nls_stg.c) at the converged state: the system is linear in the
+    // sensitivities, M (rl1 znS[1] + acorS) - gamma (J s + df/dp) = 0 column by column, solved with the factors of the states'
+    // last setup (M - gammap J): a fixed-point iteration that contracts with |1 - gamma / gammap| and the drift of J
+    AB_NI bool sens_correct() {
+        double y[NX], sd[NQA];
+        for (int r = 0; r < NX; ++r) y[r] = zn[0][r] + acor[r];
+        for (int r = 0; r < nq; ++r) acorQ[r] = 0.0;
+        double delp_s = 0.0, crate_s = 1.0;
+        for (int m = 0;; ++m) {
+            for (int r = 0; r < nq; ++r) sd[r] = znQ[0][r] + acorQ[r];
+            if (!prob.sens_rhs(tn, y, sd, sd)) return false;   // sd <- J s + df/dp (algebraic rows: dg/dx s + dg/dp)
+            double Del = 0.0;
+            for (int il = 0; il * NX < nq; ++il) {
+                double d[NX];
+                for (int r = 0; r < NX; ++r) {
+                    const int i = il * NX + r;
+                    d[r] = alg(r) ? sd[i] : -(rl1 * znQ[1][i] + acorQ[i] - gamma * sd[i]);
+                }
+                lu_solve(d);
+                const double sc = (gamrat != 1.0) ? 2.0 / (1.0 + gamrat) : 1.0;
+                double s2 = 0.0;
+                for (int r = 0; r < NX; ++r) {
+                    const int i = il * NX + r;
+                    d[r] *= sc;
+                    acorQ[i] += d[r];
+                    const double w = d[r] / (prob.rtolq * fabs(znQ[0][i]) + prob.atolq);
+                    s2 += w * w;
+                }
+                Del = upd(Del, sqrt(s2 / NX));
+            }
+            if (m > 0) crate_s = ab_max(0.3 * crate_s, Del / delp_s);
+            if (Del * ab_min(1.0, crate_s) / (0.1 * tq[4]) <= 1.0) return true;
+            if (!(Del == Del) || (m >= 1 && Del > 2.0 * delp_s) || m + 1 >= 4) return false;
+            delp_s = Del;
+        }
+    }
     // CVodeGetDky(t, 0) / CVodeGetQuadDky(t, 0) on the completed history
     AB_NI void interpolate(double t, double* y, double* yq) {
         Base::flush_pending();
@@ -581,7 +623,8 @@ struct AdjCond {
 template <class M>
 struct FwdProblem {
     static constexpr int NX = M::NX, NQ = 0;
-    static constexpr bool HIST = true;
+    static constexpr bool HIST = true, SENS = false;
+    AB_HD bool sens_rhs(double, const double*, const double*, double*) const { return true; }
     static constexpr unsigned long long ALG_MASK = 0ull;
     const AdjCond<M>& c;
     FwdHistory<M::NX>& hist;
@@ -608,7 +651,8 @@ struct FwdProblem {
 template <class M>
 struct BwdProblem {
     static constexpr int NX = M::NX, NQ = M::NP > 0 ? M::NP : 1;
-    static constexpr bool HIST = false;
+    static constexpr bool HIST = false, SENS = false;
+    AB_HD bool sens_rhs(double, const double*, const double*, double*) const { return true; }
     static constexpr unsigned long long ALG_MASK = 0ull;
     const AdjCond<M>& c;
     FwdHistory<M::NX>& hist;
@@ -710,7 +754,9 @@ struct AdjointSimulation {
     }
 
     // observables, objective, dJ/dx and the direct parameter dependence of the objective at output time it
-    AB_NI void datapoint(int it, const double* xs, const int* counters) {
+    // sx != nullptr: forward sensitivities of the state (column il in sx[il * NX ..]): sx / sy / ssigmay are reported and sllh is
+    // completed here (Model::get_observable_sensitivity + add_observable_objective_sensitivity), nothing is kept for a backward pass
+    AB_NI void datapoint(int it, const double* xs, const int* counters, const double* sx = nullptr) {
         const int nt = b.nt;
         const double t = b.ts[it];
         double spl[AdjCond<M>::NSPLV], y[NY], sig[NY], dJy[NY], dJs[NY];
@@ -749,6 +795,31 @@ struct AdjointSimulation {
             if (b.order) b.order[idx] = counters[4];
         }
         if (c.nplist == 0) return;
+        if (sx) {
+            for (int il = 0; il < c.nplist; ++il) {
+                const int ip = c.plist[il];
+                double sspl[AdjCond<M>::NSPLV], syv[NY], ssv[NY];
+                c.spline_sens(t, il, spl, sspl);
+                M::sy(ip, t, xs, c.p, c.k, c.h, spl, sspl, sx + il * NX, syv);
+                M::ssigmay(ip, c.p, c.k, y, syv, ssv);
+                const double pc = pcoef[il];
+                if (b.sx && full())
+                    for (int r = 0; r < NX; ++r) {
+                        const double v = sx[il * NX + r];
+                        b.sx[(((size_t)n * nt + it) * c.nplist + il) * NX + r] = v != 0.0 ? v * pc : v;
+                    }
+                double s = 0.0;
+                for (int iy = 0; iy < NY; ++iy) {
+                    const double ssig = sig_set[iy] ? 0.0 : ssv[iy];
+                    const size_t idx = (((size_t)n * nt + it) * c.nplist + il) * NY + iy;
+                    if (b.sy && full()) b.sy[idx] = syv[iy] != 0.0 ? syv[iy] * pc : syv[iy];
+                    if (b.ssigmay && full()) b.ssigmay[idx] = ssig != 0.0 ? ssig * pc : ssig;
+                    s += dJy[iy] * syv[iy] + dJs[iy] * ssig;
+                }
+                sllh[il] -= s;
+            }
+            return;
+        }
         // dy/dx column by column from the emitted sy = dy/dx sx + dy/dp (linear in sx), dsigmay/dy likewise from ssigmay
         double zero[NX], sy0[NY], ss0[NY], sspl[AdjCond<M>::NSPLV];
         for (int r = 0; r < NX; ++r) zero[r] = 0.0;
@@ -781,6 +852,10 @@ struct AdjointSimulation {
     AB_HD void invalidate(int it_start) {
         const int nt = b.nt;
         for (int it = it_start; it < nt; ++it) {
+            for (int il = 0; il < c.nplist; ++il) {   // forward sensitivities (dae.cuh)
+                if (b.sx && full()) for (int r = 0; r < NX; ++r) b.sx[(((size_t)n * nt + it) * c.nplist + il) * NX + r] = nan_();
+                if (b.sy && full()) for (int iy = 0; iy < NY; ++iy) b.sy[(((size_t)n * nt + it) * c.nplist + il) * NY + iy] = nan_();
+            }
             if (b.x && full()) for (int r = 0; r < NX; ++r) b.x[((size_t)n * nt + it) * NX + r] = nan_();
             for (int iy = 0; iy < NY; ++iy) {
                 const size_t idx = ((size_t)n * nt + it) * NY + iy;

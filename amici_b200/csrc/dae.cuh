@@ -30,10 +30,12 @@
 
 namespace amici_b200 {
 
-template <class M>
+// S: with forward sensitivities (the NQ rows of ScalarBdf's second vector are the columns s_il = dx / dp_plist[il])
+template <class M, bool S = false>
 struct DaeProblem {
-    static constexpr int NX = M::NX, NQ = 0;
-    static constexpr bool HIST = false;
+    static constexpr int NX = M::NX, NQ = S ? (M::NP > 0 ? M::NP : 1) * M::NX : 0;
+    static constexpr bool HIST = false, SENS = S;
+    const double* s_now = nullptr;   // the solver's current sensitivities (for the derivative at a restart and cvHin)
     static constexpr unsigned long long ALG_MASK = alg_mask_of<M>::value;
     const AdjCond<M>& c;
     double rtol, atol, rtolq, atolq;
@@ -51,7 +53,26 @@ struct DaeProblem {
         M::jac(t, y, c.p, c.k, c.h, spl, Jv);
         M::jac_to_dense(Jv, &J[0][0]);
     }
-    AB_HD bool quad(double, const double*, double*) const { return true; }
+    // out <- J(t, y) s + dxdot/dp for every column (Model_DAE::fsxdot, reference src/model_dae.cpp; algebraic rows: dg/dx s + dg/dp)
+    AB_NI bool sens_rhs(double t, const double* y, const double* s, double* out) const {
+        double spl[AdjCond<M>::NSPLV], sspl[AdjCond<M>::NSPLV], Jv[M::NNZ_J > 0 ? M::NNZ_J : 1];
+        c.splines(t, spl);
+        M::jac(t, y, c.p, c.k, c.h, spl, Jv);
+        bool ok = true;
+        for (int il = 0; il < c.nplist; ++il) {
+            double col[NX], sc[NX];
+            for (int r = 0; r < NX; ++r) sc[r] = s[il * NX + r];
+            c.spline_sens(t, il, spl, sspl);
+            M::dxdotdp(c.plist[il], t, y, c.p, c.k, c.h, spl, sspl, col);
+            M::jac_mul_add(Jv, sc, col);
+            for (int r = 0; r < NX; ++r) {
+                out[il * NX + r] = col[r];
+                ok = ok && isfinite(col[r]);
+            }
+        }
+        return ok;
+    }
+    AB_HD bool quad(double t, const double* y, double* fq) const { return S && s_now ? sens_rhs(t, y, s_now, fq) : true; }
     AB_HD void store_point(double, int, const double*, const double*) {}
 };
 
@@ -68,7 +89,8 @@ struct DaeSimulation {
     // IDACalcIC(IDA_YA_YDP_INIT): Newton on the algebraic rows for the algebraic states, differential states fixed.
     // Convergence as IDAS tests it (idas_ic.c: WRMS norm of the update below epiccon = 0.01 * 0.33), at most 10 iterations
     // with a fresh Jacobian each (maxnj x maxnit of IDAS are 4 x 10).
-    AB_NI bool consistent_start(const DaeProblem<M>& dp, double t0, double* x) const {
+    template <class DP>
+    AB_NI bool consistent_start(const DP& dp, double t0, double* x) const {
         int ia[NX], na = 0;
         for (int r = 0; r < NX; ++r)
             if (alg(r)) ia[na++] = r;
@@ -128,7 +150,57 @@ struct DaeSimulation {
         M::root(t, x, c.p, c.k, c.h, spl, rv);
     }
 
+    // the algebraic rows of the initial sensitivities from the differentiated constraints, dg/dx_a s_a = -(dg/dx_d s_d + dg/dp)
+    // (IDACalcIC with sensitivities): sens_rhs with s_a = 0 gives the right-hand side
+    template <class DP>
+    AB_NI bool consistent_start_sens(const DP& dp, double t0, const double* x, double* s, int nplist) const {
+        int ia[NX], na = 0;
+        for (int r = 0; r < NX; ++r)
+            if (alg(r)) ia[na++] = r;
+        if (na == 0 || nplist == 0) return true;
+        double J[NX][NX], g[(M::NP > 0 ? M::NP : 1) * NX];
+        for (int il = 0; il < nplist; ++il)
+            for (int i = 0; i < na; ++i) s[il * NX + ia[i]] = 0.0;
+        if (!dp.sens_rhs(t0, x, s, g)) return false;
+        dp.jac(t0, x, J);
+        for (int il = 0; il < nplist; ++il) {
+            double A[NX][NX], rhs[NX];
+            for (int i = 0; i < na; ++i) {
+                rhs[i] = -g[il * NX + ia[i]];
+                for (int j = 0; j < na; ++j) A[i][j] = J[ia[i]][ia[j]];
+            }
+            for (int kk = 0; kk < na; ++kk) {
+                int pr = kk;
+                for (int r = kk + 1; r < na; ++r)
+                    if (fabs(A[r][kk]) > fabs(A[pr][kk])) pr = r;
+                if (A[pr][kk] == 0.0) return false;
+                if (pr != kk) {
+                    for (int cc = 0; cc < na; ++cc) { const double tmp = A[kk][cc]; A[kk][cc] = A[pr][cc]; A[pr][cc] = tmp; }
+                    const double tmp = rhs[kk]; rhs[kk] = rhs[pr]; rhs[pr] = tmp;
+                }
+                for (int r = kk + 1; r < na; ++r) {
+                    const double mlt = A[r][kk] / A[kk][kk];
+                    for (int cc = kk; cc < na; ++cc) A[r][cc] -= mlt * A[kk][cc];
+                    rhs[r] -= mlt * rhs[kk];
+                }
+            }
+            for (int i = na - 1; i >= 0; --i) {
+                double v = rhs[i];
+                for (int j = i + 1; j < na; ++j) v -= A[i][j] * rhs[j];
+                rhs[i] = v / A[i][i];
+                s[il * NX + ia[i]] = rhs[i];
+            }
+        }
+        return true;
+    }
+
     AB_HD void run() {
+        if (o.sensi >= 1 && b.nplist > 0 && M::NP > 0) run_impl<true>();
+        else run_impl<false>();
+    }
+
+    template <bool S>
+    AB_HD void run_impl() {
         FwdHistory<NX> none;
         none.t = none.y = nullptr;
         none.ord = nullptr;
@@ -136,14 +208,17 @@ struct DaeSimulation {
         none.cap = 0;
         AdjointSimulation<M> out(o, b, none, nullptr, n);   // load / datapoint / invalidate / finish of the forward outputs
         out.load();
-        out.c.nplist = 0;
-        const int nt = b.nt;
-        DaeProblem<M> dp{out.c, o.rtol, o.atol, o.rtol, o.atol};
+        if (!S) out.c.nplist = 0;
+        const int nt = b.nt, nplist = out.c.nplist;
+        const double rtol_s = o.rtol_fsa == o.rtol_fsa && o.rtol_fsa > 0.0 ? o.rtol_fsa : o.rtol;
+        const double atol_s = o.atol_fsa == o.atol_fsa && o.atol_fsa > 0.0 ? o.atol_fsa : o.atol;
+        DaeProblem<M, S> dp{nullptr, out.c, o.rtol, o.atol, rtol_s, atol_s};
         // IDAS allows four Newton iterations per step (MAXIT, idas_impl.h) where CVODES allows three: the jump of the algebraic
         // states after a switch is absorbed by the first corrector solve after the restart, whatever the step size
         SolverOptions od = o;
         od.max_nonlin_iters = o.max_nonlin_iters < 4 ? 4 : o.max_nonlin_iters;
-        ScalarBdf<DaeProblem<M>> bdf(dp, od, 0);
+        ScalarBdf<DaeProblem<M, S>> bdf(dp, od, S ? nplist * NX : 0);
+        if (S) dp.s_now = bdf.znQ[0];
         double x0[NX];
         M::x0(out.c.p, out.c.k, x0);
         if (b.x0_in)
@@ -158,6 +233,22 @@ struct DaeSimulation {
             roots_at(out.c, o.t0, x0, rootvals);
             for (int ie = 0; ie < M::NE; ++ie) out.c.h[ie] = rootvals[ie] < 0.0 ? 0.0 : 1.0;
         }
+        if (S && status == AB_SUCCESS) {   // sx(t0): Model::fsx0 (+ ExpData::sx0 on the parameter scale), algebraic rows made consistent
+            for (int il = 0; il < nplist; ++il) {
+                double col[NX];
+                M::sx0(out.c.plist[il], out.c.p, out.c.k, col);
+                if (b.sx0_in)
+                    for (int r = 0; r < NX; ++r) col[r] = b.sx0_in[((size_t)n * nplist + il) * NX + r] / out.pcoef[il];
+                for (int r = 0; r < NX; ++r) bdf.znQ[0][il * NX + r] = col[r];
+            }
+            if (!consistent_start_sens(dp, o.t0, x0, bdf.znQ[0], nplist)) status = AB_IC_FAIL;
+            if (b.sx0 && out.full())
+                for (int il = 0; il < nplist; ++il)
+                    for (int r = 0; r < NX; ++r) {
+                        const double v = bdf.znQ[0][il * NX + r];
+                        b.sx0[((size_t)n * nplist + il) * NX + r] = v != 0.0 ? v * out.pcoef[il] : v;
+                    }
+        }
         if (status == AB_SUCCESS) {
             for (int r = 0; r < NX; ++r) bdf.zn[0][r] = x0[r];
             bdf.init(o.t0);
@@ -166,7 +257,7 @@ struct DaeSimulation {
                 double tout = b.ts[it];
                 if (!(tout > o.t0) || !(t < tout) || adj_too_close(t, tout)) {
                     const int counters[5] = {bdf.nst, bdf.nfe, bdf.netf, bdf.ncfn, bdf.qu};
-                    out.datapoint(it, bdf.zn[0], counters);
+                    out.datapoint(it, bdf.zn[0], counters, S ? bdf.znQ[0] : nullptr);
                     ++it;
                     continue;
                 }

@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(DAE_THREADS) dae_kernel(const ab_solver_option
 
 template <class M>
 int launch_dae_model(const ab_solver_options& o, const ab_batch& b, int* queue_head, const Progress& pg, cudaStream_t st) {
-    if (o.sensi >= 1 && b.nplist > 0) {
-        last_error() = "sensitivities of DAE models are not implemented (forward simulation only)";
+    if (o.sensi >= 1 && b.nplist > 0 && (o.sensi > 1 || o.sensi_meth == 2 || M::NE > 0)) {
+        last_error() = "DAE models: first-order forward sensitivities of event-free models only";
         return AB_E_UNSUPPORTED;
     }
     if (b.k_preeq || o.posteq || b.t_presim || o.x_nonneg != 0ull || o.maxtime > 0.0 || o.reinit_states_sim || o.reinit_states_presim) {

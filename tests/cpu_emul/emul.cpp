@@ -124,7 +124,7 @@ extern "C" int emul_run(const char* model, const SolverOptions* o, const BatchVi
     if (m == "dirac") return run_model<models::dirac>(o, b);
     if (m == "nested_events") return run_model<models::nested_events>(o, b);
     if (m == "robertson" || m == "calvetti") {   // DAE path (dae.cuh): forward simulation only, as launch_dae_model
-        if (o->sensi >= 1 && b->nplist > 0) return -3;
+        if (o->sensi >= 1 && b->nplist > 0 && m != "robertson") return -3;   // as launch_dae_model: FSA of event-free DAE models only
         for (int n = 0; n < b->N; ++n) {
             if (m == "robertson") std::make_unique<DaeSimulation<models::robertson>>(*o, *b, n)->run();
             else std::make_unique<DaeSimulation<models::calvetti>>(*o, *b, n)->run();

@@ -772,10 +772,13 @@ def test_emulation_dae_robertson_matches_the_reference_idas(built):
     np.testing.assert_allclose(out["x"].sum(-1), 1.0, rtol=0, atol=1e-8)   # the Newton tolerance, not round-off (here 1.8e-9; the reference 5.7e-11 on this fixture, 2.0e-9 on wider draws)
     ratio = out["numsteps"][:, -1] / g["klu_nosens_numsteps"][:, -1]   # another integrator: same size, not the same sequence
     assert 0.5 < ratio.min() and ratio.max() < 2.0
-    # forward sensitivities of DAE models are refused, not silently dropped
+    # forward sensitivities (staggered corrector on the states' factors, consistent sx(t0)) against the reference's IDAS FSA run
     o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
-    b2, _, keep2 = _capi.make_batch(dict(nx=3, np=3, nk=1, ny=3), g["ts"], g["p"], g["k"])
-    assert _emul(built).emul_run(b"robertson", C.byref(o), C.byref(b2)) != 0 or b2.nplist == 0
+    b2, out2, keep2 = _capi.make_batch(dict(nx=3, np=3, nk=1, ny=3), g["ts"], g["p"], g["k"])
+    assert _emul(built).emul_run(b"robertson", C.byref(o), C.byref(b2)) == 0
+    np.testing.assert_array_equal(out2["status"], g["klu_status"])
+    parity.check_against_golden(out2, parity.robertson_view(g, 1), fields=["x", "y", "sx", "sy"])
+    np.testing.assert_allclose(out2["sx"].sum(-1), 0.0, rtol=0, atol=1e-6 * np.abs(out2["sx"]).max())   # d/dp of x1 + x2 + x3 = 1
 
 
 def test_emulation_nested_events_matches_golden(built):

@@ -1350,7 +1350,8 @@ def test_cuda_dae_robertson_shipped_model_vs_reference_idas():
     simulation of 4096 log-uniform parameter draws through the C ABI on the DAE path (csrc/dae.cuh), against the reference's
     IDAS: golden fixture by the parity protocol; on the full batch every draw succeeds, the algebraic equation holds, the
     consistent start is the reference's; a random 48-draw subset against IDAS runs on the host cores (status identical,
-    error against the tight-tolerance IDAS run no larger than IDAS' own, factor 4) and against the engine's ODE-form run."""
+    error against the tight-tolerance IDAS run no larger than IDAS' own, factor 4) and against the engine's ODE-form run.
+    Forward sensitivities of the DAE path: IDAS FSA fixture, 512 draws against the ODE-form sensitivities."""
     import amici_b200 as ab
     from oracle import refsim
     g = np.load(os.path.join(GOLD, "robertson.npz"))
@@ -1382,9 +1383,20 @@ def test_cuda_dae_robertson_shipped_model_vs_reference_idas():
     so.set_absolute_tolerance(parity.ATOL)
     ode = ab.run_simulations(mo, so, ab.ExpDataBatch(ts, p, k))
     np.testing.assert_allclose(out["x"], ode["x"], rtol=2e-5, atol=1e-10)   # two integrations at rtol 1e-8 over 12 decades of time
+    # forward sensitivities: the IDAS FSA fixture by the protocol, then the batch against the engine's ODE-form sensitivities;
+    # the adjoint method is refused for DAE models
+    fsa = _run("robertson", gg, sensi=True)
+    np.testing.assert_array_equal(fsa["status"], g["klu_status"])
+    parity.check_against_golden(fsa.fields, parity.robertson_view(g, 1), fields=["x", "y", "sx", "sy"])
     s.set_sensitivity_order(ab.SensitivityOrder.first)
-    with pytest.raises(RuntimeError, match="DAE"):
-        ab.run_simulations(m, s, ab.ExpDataBatch(ts, p[:4], k[:4]))
+    so.set_sensitivity_order(ab.SensitivityOrder.first)
+    sd, sod = ab.run_simulations(m, s, ab.ExpDataBatch(ts, p[:512], k[:512])), ab.run_simulations(mo, so, ab.ExpDataBatch(ts, p[:512], k[:512]))
+    assert (sd["status"] == 0).all()
+    scale = np.abs(sod["sx"]).max(axis=(1, 3), keepdims=True)
+    assert (np.abs(sd["sx"] - sod["sx"]) <= 1e-4 * scale).all()
+    s.set_sensitivity_method(ab.SensitivityMethod.adjoint)
+    with pytest.raises(RuntimeError):
+        ab.run_simulations(m, s, ab.ExpDataBatch(ts, p[:4], k[:4], my=np.zeros((4, len(ts), 3)), sigmay=np.ones((4, len(ts), 3))))
     if not refsim.available("robertson"):
         return
     # max-based rule of the protocol (factor 4, with eight spread runs of the reference): this path and IDAS are different BDF
