@@ -22,8 +22,13 @@
 //                      (Model::update_heaviside), the solver restarts at order 1 as after every AMICI event; the algebraic
 //                      states are NOT re-initialised there — the first step after the event pulls them onto the new
 //                      constraint, exactly what IDAS does after IDAReInit with the error test blind to them
+//   sensitivities      first-order forward sensitivities of event-free models: M s' = J s + df/dp column by column, corrected after
+//                      the states by a Newton iteration on the states' factors (the staggered corrector; ScalarBdf::sens_correct),
+//                      error test over states and sensitivities (errconS), algebraic rows of sx(t0) from the differentiated
+//                      constraints; sx, sy, ssigmay, sllh reported
 //   outputs            x, y, sigmay, llh, res, chi2, counters, status (AdjointSimulation's forward outputs)
-//   not implemented    sensitivities, state-triggered or state-changing events, pre-/post-equilibration of DAE models
+//   not implemented    adjoint / second-order sensitivities, sensitivities of models with switches, state-triggered or
+//                      state-changing events, pre-/post-equilibration of DAE models
 #ifndef AMICI_B200_DAE_CUH
 #define AMICI_B200_DAE_CUH
 #include "adjoint.cuh"
