@@ -796,6 +796,7 @@ struct AdjointSimulation {
         }
         if (c.nplist == 0) return;
         if (sx) {
+            double srv[NPA][NY];   // sres of this timepoint (chain rule applied), for the FIM
             for (int il = 0; il < c.nplist; ++il) {
                 const int ip = c.plist[il];
                 double sspl[AdjCond<M>::NSPLV], syv[NY], ssv[NY];
@@ -815,9 +816,25 @@ struct AdjointSimulation {
                     if (b.sy && full()) b.sy[idx] = syv[iy] != 0.0 ? syv[iy] * pc : syv[iy];
                     if (b.ssigmay && full()) b.ssigmay[idx] = ssig != 0.0 ? ssig * pc : ssig;
                     s += dJy[iy] * syv[iy] + dJs[iy] * ssig;
+                    // sres = (-sy - ssigmay res) / sigma for set measurements (Simulation::datapoint; reference src/rdata.cpp:1060-1104)
+                    const double my = b.my ? b.my[((size_t)n * nt + it) * NY + iy] : nan_();
+                    srv[il][iy] = 0.0;
+                    if (my == my) {
+                        const double res = -(y[iy] - my) / sig[iy];
+                        const double sr = (-syv[iy] - ssig * res) / sig[iy];
+                        srv[il][iy] = sr != 0.0 ? sr * pc : sr;
+                        if (b.sres && full()) b.sres[((size_t)n * nt * NY + (size_t)it * NY + iy) * c.nplist + il] = srv[il][iy];
+                    }
                 }
                 sllh[il] -= s;
             }
+            if (b.FIM)   // FIM += sres sres^T per set measurement (reference src/rdata.cpp:1106-1205)
+                for (int iy = 0; iy < NY; ++iy) {
+                    const double my = b.my ? b.my[((size_t)n * nt + it) * NY + iy] : nan_();
+                    if (!(my == my)) continue;
+                    for (int il = 0; il < c.nplist; ++il)
+                        for (int jl = 0; jl < c.nplist; ++jl) b.FIM[((size_t)n * c.nplist + il) * c.nplist + jl] += srv[il][iy] * srv[jl][iy];
+                }
             return;
         }
         // dy/dx column by column from the emitted sy = dy/dx sx + dy/dp (linear in sx), dsigmay/dy likewise from ssigmay

@@ -8,7 +8,7 @@
 
 namespace amici_b200 {
 
-constexpr int DAE_THREADS = 64;
+constexpr int DAE_THREADS = 32;   // BASELINE configs[0] is 4,096 conditions: 128 one-warp blocks cover the 148 SMs better than 64 two-warp ones
 
 template <class M>
 __global__ void __launch_bounds__(DAE_THREADS) dae_kernel(const ab_solver_options o, const ab_batch b, int* queue_head, const Progress pg) {

@@ -312,7 +312,9 @@ def main():
         my = rng.uniform(0.5, 1.5, (n, len(c["ts"]), model.ny))
     elif w["noise"] is not None:
         # noise-free observables of every condition (one un-timed solve without sensitivities), then add noise
-        pre = DeviceBatch(model, make_solver(False), ab.ExpDataBatch(c["ts"], p, k, k_preeq=kp), dev, fields=["y"])
+        pre_solver = make_solver(False)
+        pre_solver.set_return_data_reporting_mode(ab.RDataReporting.full)   # the observables are needed here, whatever the timed mode
+        pre = DeviceBatch(model, pre_solver, ab.ExpDataBatch(c["ts"], p, k, k_preeq=kp), dev, fields=["y"])
         pre.solve()
         torch.cuda.synchronize()
         my = pre.out["y"].cpu().numpy() + w["noise"]

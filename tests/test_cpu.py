@@ -817,3 +817,29 @@ def test_emulation_dae_calvetti_matches_the_reference_idas(built):
     o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=0)
     assert _emul(built).emul_run(b"calvetti", C.byref(o), C.byref(b)) == 0
     _calvetti_checks(out, g)
+
+
+def test_emulation_dae_robertson_objective_and_sensitivities_live(built):
+    """DAE forward sensitivities with measurements: llh, sllh, res, sres and the FIM of the shipped Robertson DAE against the
+    compiled reference (IDAS, FSA) on fresh draws — KLU / dense / truth + eight spread runs, parity protocol."""
+    from oracle import refsim
+    if not refsim.available("robertson"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = refsim.RefModel("robertson")
+    rng = np.random.default_rng(71)
+    N = 6
+    ts = 4.0 * 10.0 ** np.arange(-5.0, 4.0)
+    p = np.tile(ref.p_nominal, (N, 1)) * 10 ** rng.normal(0, 0.1, (N, 3))
+    k = np.full((N, 1), 0.9)
+    y0 = ref.run(ts, p, k, sensi_order=0, fields=["y"])["y"].reshape(N, len(ts), 3)
+    sig = np.maximum(0.05 * np.abs(y0), 1e-3)
+    my = y0 + sig * rng.standard_normal(y0.shape)
+    my[1, 2, :] = np.nan
+    fields = ["x", "y", "sx", "sy", "llh", "sllh", "res", "sres", "FIM", "chi2", "x0", "sx0"]
+    gold = parity.reference_triple(ref, ts, p, k, ["status"] + fields, spread_runs=8, my=my, sigmay=sig)
+    b, out, keep = _capi.make_batch(dict(nx=3, np=3, nk=1, ny=3), ts, p, k, my=my, sigmay=sig)
+    o = _capi.default_options(rtol=parity.RTOL, atol=parity.ATOL, sensi=1)
+    assert _emul(built).emul_run(b"robertson", C.byref(o), C.byref(b)) == 0
+    np.testing.assert_array_equal(out["status"], gold["klu_status"])
+    cand = {f: np.asarray(out[f], float).reshape(np.asarray(gold["klu_" + f]).shape) for f in fields}
+    parity.check_against_golden(cand, gold, fields=fields)
