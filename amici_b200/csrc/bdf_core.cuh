@@ -67,7 +67,9 @@ struct TrajShared {
     double sld[40];                  // exchange area of bdf_sldet_xchg (ten rounds of up to four values)
     unsigned long long xpos_mask;    // Model::set_state_is_non_negative as a bit set (AB_FULL builds; 0 = off)
     long long t_start_ns;            // device clock when the condition started (Solver::set_max_time; AB_FULL builds)
+#if AB_SLDET_SVC
     int svc;                         // mailbox of the block's cvSLdet service warp (AB_SLDET_SVC, launch.cuh): request / result word
+#endif
     int piv[M::NX];
     int ip_of_col[NCOLS];            // parameter index of an integrated column (-1: state / unused)
     int il_of_col[NCOLS];            // its position in plist

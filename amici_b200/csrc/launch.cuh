@@ -60,6 +60,7 @@ __device__ __forceinline__ void report_done(const Progress& pg, const Group<G>& 
     }
 }
 
+#if AB_SLDET_SVC
 // cvSLdet service warps (AB_SLDET_SVC; the last warpgroup of a block of 16-lane groups): four lanes serve one lane group, the
 // three orders in three of them (bdf_sldet_xchg).  A group posts (order, ring head) in its slice's mailbox (Bdf::sldet_remote),
 // the ring buffer itself is read from the group's slice, the return code goes back through the same word.
@@ -96,6 +97,8 @@ __device__ void sldet_service(Shared* slices, volatile int* done, const int st) 
     }
 }
 
+#endif
+
 template <int G>
 struct SldetSvc { static constexpr bool value = AB_SLDET_SVC && G == 16; };
 
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
         if (threadIdx.x < THREADS / 32) sync_pos[threadIdx.x] = 0x7fffffff;
         __syncthreads();
     }
+#if AB_SLDET_SVC
     if (SVC) {
         if (threadIdx.x < CT / G) slices[threadIdx.x].svc = 0;
         if (threadIdx.x == 0) sync_pos[31] = 0;
@@ -130,6 +134,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
         }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     }
+#endif
     for (;;) {
         int n = 0;
         if (g.lane == 0) n = atomicAdd(queue_head, 1);
