@@ -12,6 +12,7 @@ constexpr int DAE_THREADS = 32;   // BASELINE configs[0] is 4,096 conditions: 12
 
 template <class M>
 __global__ void __launch_bounds__(DAE_THREADS) dae_kernel(const ab_solver_options o, const ab_batch b, int* queue_head, const Progress pg) {
+    if ((int)(threadIdx.x & 31) >= pg.lanes) return;   // small batches: see Progress::lanes
     for (;;) {
         const int n = atomicAdd(queue_head, 1);
         if (n >= b.N) break;
@@ -49,11 +50,14 @@ int launch_dae_model(const ab_solver_options& o, const ab_batch& b, int* queue_h
         return AB_E_CUDA;
     }
     long grid = (long)sms * per_sm;
-    const long want = ((long)b.N + DAE_THREADS - 1) / DAE_THREADS;
+    Progress pgl = pg;
+    pgl.lanes = lanes_for_batch(b.N, grid * (DAE_THREADS / 32));
+    const long per_block = (long)pgl.lanes * (DAE_THREADS / 32);
+    const long want = ((long)b.N + per_block - 1) / per_block;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     AB_CUDA(cudaMemsetAsync(queue_head, 0, sizeof(int), st));
-    kern<<<(unsigned)grid, DAE_THREADS, 0, st>>>(o, b, queue_head, pg);
+    kern<<<(unsigned)grid, DAE_THREADS, 0, st>>>(o, b, queue_head, pgl);
     g_launches++;
     last_kernel() = std::string("dae_kernel<") + M::name() + ">";
     AB_CUDA(cudaGetLastError());

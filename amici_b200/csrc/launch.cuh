@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) bdf_solve_kernel(const ab_
     Group<G> g;
     constexpr bool STEP_SYNC = AB_STEP_SYNC && (G == 32 || (G == 16 && AB_STEP_SYNC_G16)) && THREADS > 32;
     static_assert(!(SVC && STEP_SYNC), "the service warp does not take part in the step alignment");
+    if (G == 1 && (int)(threadIdx.x & 31) >= pg.lanes) return;   // small batches: see Progress::lanes
     if (STEP_SYNC) {
         if (threadIdx.x < THREADS / 32) sync_pos[threadIdx.x] = 0x7fffffff;
         __syncthreads();
@@ -231,10 +232,15 @@ int launch_variant(const ab_solver_options& o, const ab_batch& b, int* queue_hea
         if (std::atoi(cap) > 0 && std::atoi(cap) < per_sm) per_sm = std::atoi(cap);
     long want = ((long)b.N + groups - 1) / groups;
     long grid = (long)sms * per_sm;
+    Progress pgl = pg;
+    if (G == 1) {
+        pgl.lanes = lanes_for_batch(b.N, grid * (THREADS / 32));
+        want = ((long)b.N + pgl.lanes * (THREADS / 32) - 1) / (pgl.lanes * (THREADS / 32));
+    }
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     AB_CUDA(cudaMemsetAsync(queue_head, 0, sizeof(int), st));
-    kern<<<(unsigned)grid, THREADS, smem, st>>>(o, b, queue_head, pg);
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(o, b, queue_head, pgl);
     g_launches++;
     last_kernel() = std::string((AB_FLAT && !PREEQ && M::NE == 0) ? "bdf_flat_kernel<" : "bdf_solve_kernel<") + M::name() + "," + std::to_string(G) + "," +
                     std::to_string(C) + "," + std::to_string(THREADS) + "," + std::to_string(MINBLOCKS) + "," + (PREEQ ? "preeq" : "plain") + ">";

@@ -30,7 +30,18 @@ struct Progress {
     int* done = nullptr;
     int* host_flags = nullptr;   // device-side address of the mapped host array
     int chunk = 0;
+    // one-thread-per-condition kernels (G == 1, dae_kernel): lanes of a warp that take conditions.  A small batch is spread over
+    // more warps than N / 32 (set by the launch): less divergence inside a warp, all SMs busy
+    int lanes = 32;
 };
+
+// lanes per warp for a one-thread-per-condition launch of N conditions on `slots` resident warps: the smallest power of two
+// that still fits the batch into one wave
+inline int lanes_for_batch(long N, long slots) {
+    int lanes = 1;
+    while (lanes < 32 && (N + lanes - 1) / lanes > slots) lanes *= 2;
+    return lanes;
+}
 
 struct ModelEntry {
     const char* name;
