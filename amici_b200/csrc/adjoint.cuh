@@ -28,7 +28,10 @@ AB_HD bool adj_too_close(double cur_t, double t_next) {
 
 // the large pieces are real functions: the forward and the backward solver instantiate the step control twice, and a thread's
 // state is in local memory anyway
-#if defined(__CUDACC__)
+#if defined(AB_NI)
+// a translation unit with one small problem (tu/robertson.cu: 3 states) may ask for inlined pieces: loops over NX unroll, the
+// solver state moves from local memory into registers
+#elif defined(__CUDACC__)
 #define AB_NI __host__ __device__ __noinline__
 #else
 #define AB_NI __attribute__((noinline))
