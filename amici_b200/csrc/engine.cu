@@ -102,11 +102,11 @@ static const ModelEntry* find_model(const char* name) {
     return nullptr;
 }
 
-static int check_args(const ab_solver_options* o, const ab_batch* b) {
+static int check_args(const ab_solver_options* o, const ab_batch* b, const int np = 1) {
     if (!o || !b) { g_err = "null argument"; return AB_E_BAD_ARGUMENT; }
     if (b->N < 0 || b->nt < 0 || b->nplist < 0) { g_err = "negative size"; return AB_E_BAD_ARGUMENT; }
     if (!b->ts && b->nt > 0) { g_err = "ts is NULL"; return AB_E_BAD_ARGUMENT; }
-    if (!b->p || !b->status) { g_err = "p/status is NULL"; return AB_E_BAD_ARGUMENT; }
+    if ((!b->p && np > 0) || !b->status) { g_err = "p/status is NULL"; return AB_E_BAD_ARGUMENT; }   // a model without free parameters has no p
     if (!std::isfinite(o->t0)) { g_err = "t0 must be finite"; return AB_E_BAD_ARGUMENT; }
     if (o->sensi >= 1 && b->nplist > 0 && !b->plist) { g_err = "plist is NULL"; return AB_E_BAD_ARGUMENT; }
     if (o->sensi >= 1 && o->ism != 1 && o->ism != 2) {
@@ -183,7 +183,7 @@ int ab_get_nominal(const char* model, double* p, double* k) {
 int ab_solve_device(const char* model, const ab_solver_options* opt, const ab_batch* b, int* work_counter, void* stream) {
     const ModelEntry* e = find_model(model);
     if (!e) return AB_E_UNKNOWN_MODEL;
-    int rc = check_args(opt, b);
+    int rc = check_args(opt, b, e->dims.np);
     if (rc != AB_OK) return rc;
     if (!work_counter) { g_err = "work_counter is NULL"; return AB_E_BAD_ARGUMENT; }
     if (b->N == 0) return AB_OK;
@@ -355,7 +355,7 @@ void ab_release_workspace(void) {
 int ab_run_batch(const char* model, const ab_solver_options* opt, const ab_batch* hb, float* kernel_ms) {
     const ModelEntry* e = find_model(model);
     if (!e) return AB_E_UNKNOWN_MODEL;
-    int rc = check_args(opt, hb);
+    int rc = check_args(opt, hb, e->dims.np);
     if (rc != AB_OK) return rc;
     if (kernel_ms) *kernel_ms = 0.f;
     if (hb->N == 0) return AB_OK;

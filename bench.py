@@ -7,6 +7,7 @@
   jakstat      model_jakstat_adjoint_py, 17 forward sensitivities, 65,536 synthetic ExpData conditions
   robertson    Robertson (ODE form), forward simulation, 4096 log-uniform parameter draws            (configs[0])
   robertson_dae  the shipped model_robertson_py (index-1 DAE): engine DAE path vs the reference's IDAS, same draws          (configs[0])
+  calvetti     the shipped model_calvetti_py (index-1 DAE with switches), 16,384 draws of its constants: DAE path vs IDAS
   steadystate  model_steadystate_py, pre-equilibration (Newton, simulation if it fails) + FSA, 65,536  (configs[2])
   events       model_events_py, Heaviside events + root finding + FSA, 65,536 parameter samples        (configs[3])
   neuron       model_neuron_py, spike events (divergent step control) + FSA, 65,536 samples            (configs[3])
@@ -52,6 +53,11 @@ def _wl_robertson(n, seed, p0, k0):
     return dict(p=np.tile(p0, (n, 1)) * 10 ** rng.uniform(-1, 1, (n, 3)), k=np.full((n, 1), 0.9), noise=None)
 
 
+def _wl_calvetti(n, seed, p0, k0):
+    rng = np.random.default_rng(seed)
+    return dict(p=np.zeros((n, 0)), k=np.tile(k0, (n, 1)) * rng.uniform(0.9, 1.1, (n, len(k0))), noise=None)
+
+
 def _wl_steadystate(n, seed, p0, k0):
     rng = np.random.default_rng(seed)
     p = np.tile(p0, (n, 1)) * 10 ** rng.normal(0, 0.1, (n, 5))
@@ -92,6 +98,11 @@ CONFIGS = {
                           sensi=False, inputs=_wl_robertson, label="model_robertson_py (shipped index-1 DAE; engine: mass-matrix BDF, reference: IDAS) forward simulation, log-uniform draws",
                           metric="DAE solves/sec, forward simulation (Robertson DAE)", flops=dict(n=3, s=0, zJ=7, Ff=12, FJ=8, FP=0, ny=3),
                           baseline_config=0),
+    # the other shipped DAE model: three differential + three algebraic states, switches at t = 10 and t = 12 (not a BASELINE config)
+    "calvetti": dict(model="calvetti", ref="calvetti", n=16384, seed=6, ts=np.linspace(0, 20, 41), sensi=False, inputs=_wl_calvetti,
+                     label="model_calvetti_py (shipped index-1 DAE with time-triggered switches; reference: IDAS) forward simulation, constants x U(0.9, 1.1)",
+                     metric="DAE solves/sec, forward simulation (Calvetti)", flops=dict(n=6, s=0, zJ=23, Ff=80, FJ=120, FP=0, ny=6),
+                     baseline_config=0),
     "steadystate": dict(model="steadystate", ref="steadystate", n=65536, seed=3, ts=np.linspace(0, 10, 11), sensi=True, inputs=_wl_steadystate,
                         preeq=True, label="model_steadystate_py pre-equilibration (Newton, simulation if it fails) + FSA 5 params",
                         metric="ODE solves/sec w/ forward sens + pre-equilibration (steadystate)",
