@@ -13,6 +13,8 @@
 // The work per condition is nx + nplist scalars (JAK-STAT: 26) against nx * (1 + nplist) = 162 of the forward method, and
 // the conditions of a warp share nothing, so the lane-group layout has nothing to offer here: all vectors are thread-private
 // (local memory, L1-resident), the history is in HBM, interleaved over the thread slots of the grid.
+// ScalarBdf, the one-thread solver defined here, also carries the DAE path (dae.cuh): mass matrix, algebraic-state handling and
+// the staggered sensitivity corrector are compiled in only for problems that declare ALG_MASK / SENS.
 #ifndef AMICI_B200_ADJOINT_CUH
 #define AMICI_B200_ADJOINT_CUH
 #include "bdf_core.cuh"

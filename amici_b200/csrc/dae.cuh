@@ -10,8 +10,8 @@
 // AMICI configures IDAS (IDASetSuppressAlg(true), src/solver.cpp:252).  Consequences of that choice handled in ScalarBdf: the
 // history of the algebraic states is kept at order 1 (linear extrapolation as predictor; a Nordsieck array of order q fed with
 // corrections that no error test bounds drifts until the corrector stalls), every step estimates its own Newton convergence
-// rate, the corrector tolerance is ten times tighter, and a step size that underflows to zero ends the solve.  Step sequences therefore differ from IDAS'; results
-// are compared with the reference's IDAS runs by the parity protocol (error against a tight-tolerance IDAS run no larger
+// rate, the corrector tolerance is ten times tighter, and a step size that underflows to zero ends the solve.  Step sequences
+// therefore differ from IDAS'; results are compared with the reference's IDAS runs by the parity protocol (error against a tight-tolerance IDAS run no larger
 // than IDAS' own, tests/parity.py).
 //
 //   consistent start   IDACalcIC(IDA_YA_YDP_INIT) (src/solver_idas.cpp:831-840): differential states fixed, Newton on the
@@ -25,7 +25,7 @@
 //   sensitivities      first-order forward sensitivities of event-free models: M s' = J s + df/dp column by column, corrected after
 //                      the states by a Newton iteration on the states' factors (the staggered corrector; ScalarBdf::sens_correct),
 //                      error test over states and sensitivities (errconS), algebraic rows of sx(t0) from the differentiated
-//                      constraints; sx, sy, ssigmay, sllh reported
+//                      constraints; sx, sy, ssigmay, sllh, sres and the FIM reported
 //   outputs            x, y, sigmay, llh, res, chi2, counters, status (AdjointSimulation's forward outputs)
 //   not implemented    adjoint / second-order sensitivities, sensitivities of models with switches, state-triggered or
 //                      state-changing events, pre-/post-equilibration of DAE models
