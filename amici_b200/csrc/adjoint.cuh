@@ -723,6 +723,7 @@ struct AdjointSimulation {
     int n;
     AdjCond<M> c;
     double pcoef[NPA], sllh[NPA], llh, chi2;
+    bool fsa = false;   // forward sensitivities are reported (dae.cuh): a failure also invalidates sres and the FIM
 
     AB_HD AdjointSimulation(const SolverOptions& opt, const BatchView& bv, FwdHistory<NX>& hs, double* dj, int n_)
         : o(opt), b(bv), hist(hs), dJydx(dj), n(n_) {}
@@ -874,9 +875,12 @@ struct AdjointSimulation {
     AB_HD void invalidate(int it_start) {
         const int nt = b.nt;
         for (int it = it_start; it < nt; ++it) {
-            for (int il = 0; il < c.nplist; ++il) {   // forward sensitivities (dae.cuh)
+            for (int il = 0; il < (fsa ? c.nplist : 0); ++il) {   // forward sensitivities (dae.cuh), as Simulation::invalidate
                 if (b.sx && full()) for (int r = 0; r < NX; ++r) b.sx[(((size_t)n * nt + it) * c.nplist + il) * NX + r] = nan_();
-                if (b.sy && full()) for (int iy = 0; iy < NY; ++iy) b.sy[(((size_t)n * nt + it) * c.nplist + il) * NY + iy] = nan_();
+                for (int iy = 0; iy < NY; ++iy) {
+                    if (b.sy && full()) b.sy[(((size_t)n * nt + it) * c.nplist + il) * NY + iy] = nan_();
+                    if (b.sres && full()) b.sres[((size_t)n * nt * NY + (size_t)it * NY + iy) * c.nplist + il] = nan_();
+                }
             }
             if (b.x && full()) for (int r = 0; r < NX; ++r) b.x[((size_t)n * nt + it) * NX + r] = nan_();
             for (int iy = 0; iy < NY; ++iy) {
@@ -886,6 +890,8 @@ struct AdjointSimulation {
                 if (b.res && full()) b.res[(size_t)n * nt * NY + (size_t)it * NY + iy] = nan_();
             }
         }
+        if (fsa && b.FIM)
+            for (int i = 0; i < c.nplist * c.nplist; ++i) b.FIM[(size_t)n * c.nplist * c.nplist + i] = nan_();
         llh = chi2 = nan_();
     }
 

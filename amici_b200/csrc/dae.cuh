@@ -213,6 +213,7 @@ struct DaeSimulation {
         none.cap = 0;
         AdjointSimulation<M> out(o, b, none, nullptr, n);   // load / datapoint / invalidate / finish of the forward outputs
         out.load();
+        out.fsa = S;
         if (!S) out.c.nplist = 0;
         const int nt = b.nt, nplist = out.c.nplist;
         const double rtol_s = o.rtol_fsa == o.rtol_fsa && o.rtol_fsa > 0.0 ? o.rtol_fsa : o.rtol;
